@@ -1,0 +1,58 @@
+"""Shared helpers for the test-suite (golden fixture access, seeded synthetic inputs)."""
+import gzip
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent.parent
+GOLDEN = REPO / "tests" / "golden"
+REF = GOLDEN / "ref"
+
+# case -> min_match_length used by the reference's integration tests
+# (tests/integration_tests/test_from_msa.py:35-220 in the reference)
+SMALL_CASES = {
+    "match": 7, "match.nonmatch": 7, "match.nonmatch.match": 7, "match.nonmatch.shortmatch": 7,
+    "match.staggereddash": 7, "nonmatch": 7, "nonmatch.match": 7, "nonmatch.shortmatch": 7,
+    "shortmatch.nonmatch": 7, "shortmatch.nonmatch.match": 7, "contains_n": 7,
+    "contains_n_and_RYKMSW": 7, "contains_n_no_variants": 7, "contains_RYKMSW": 7,
+    "a_column_full_of_Ns": 7, "nested_snps_seq_backgrounds": 3,
+    "nested_snps_seq_backgrounds_more_seqs": 3, "nested_snps_deletion": 1,
+}
+
+
+def truth_prg(case):
+    return (REF / "truth" / case / f"{case}.prg.fa").read_text().split("\n")[1]
+
+
+def truth_multi(setname):
+    lines = (REF / "truth" / setname / f"{setname}.prg.fa").read_text().split("\n")
+    return {lines[i][1:]: lines[i + 1] for i in range(0, len(lines) - 1, 2)}
+
+
+def locus_name(path):
+    return re.sub(r"\.(fa|fasta)(\.gz)?$", "", Path(path).name)
+
+
+def synthetic_cases():
+    with open(GOLDEN / "synthetic.json") as fh:
+        return json.load(fh)
+
+
+def unit_cases():
+    with open(GOLDEN / "units.json") as fh:
+        return json.load(fh)
+
+
+def kmeans_cases():
+    z = np.load(GOLDEN / "kmeans_cases.npz")
+    for i in range(int(z["count"])):
+        yield (z[f"X{i}"].astype(np.float64), int(z[f"K{i}"]), z[f"labels{i}"],
+               float(z[f"inertia{i}"]))
+
+
+def rows_to_matrix(rows):
+    if not rows or len(rows[0]) == 0:
+        return np.zeros((len(rows), 0), np.uint8)
+    return np.frombuffer("".join(rows).encode(), np.uint8).reshape(len(rows), -1).copy()
