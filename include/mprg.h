@@ -1,0 +1,178 @@
+/*
+ * mprg.h -- C ABI of libmprg.so, the sm_100a implementation of make_prg's `from_msa` compute core.
+ *
+ * The reference (iqbal-lab-org/make_prg v0.5.0) is pure Python and has no FFI layer; the seams this
+ * library sits behind are the Python calls listed next to each entry point (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MPRG_E_* code otherwise; no C++ exception
+ *     crosses the ABI; mprg_last_error(ctx) gives the text of the last failure on that context.
+ *   - plain pointers and sizes only.  Pointers named h_* are HOST memory, d_* are DEVICE memory
+ *     owned by the caller (e.g. torch tensors' data_ptr()); the library never frees caller memory.
+ *   - one context per GPU, used from one host thread at a time; all work is enqueued on the
+ *     context's stream; entry points that return host results synchronise that stream.
+ *   - there is NO CPU fallback: without a CUDA device mprg_create fails with MPRG_E_NO_DEVICE.
+ *
+ * Symbol codes of the 4-bit packed MSA (two columns per byte, even column in the low nibble, rows
+ * padded to 16 bytes with MPRG_SYM_PAD):
+ *   A C G T = 0..3, '-' = 4, R Y K M S W = 5..10, N = 11, pad/disallowed = 15.
+ */
+#ifndef MPRG_H
+#define MPRG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPRG_OK 0
+#define MPRG_E_NO_DEVICE (-1)
+#define MPRG_E_CUDA (-2)
+#define MPRG_E_BAD_ARG (-3)
+#define MPRG_E_PARTITION (-4) /* PartitioningError (interval_partition.py:12) */
+#define MPRG_E_INTERNAL (-5)
+
+#define MPRG_SYM_GAP 4
+#define MPRG_SYM_N 11
+#define MPRG_SYM_PAD 15
+
+#define MPRG_IV_MATCH 0
+#define MPRG_IV_NONMATCH 1
+
+/* node kinds of the recursion tree (recursion_tree.py:176-391) */
+#define MPRG_NODE_LEAF 0
+#define MPRG_NODE_INTERVAL 1
+#define MPRG_NODE_CLUSTER 2
+
+/* per-locus status of mprg_build */
+#define MPRG_LOCUS_OK 0
+#define MPRG_LOCUS_CURATION_ERROR 1 /* SequenceCurationError => locus skipped (from_msa.py:147-151) */
+
+typedef struct mprg_ctx mprg_ctx;
+typedef struct mprg_batch mprg_batch;   /* a set of loci resident in HBM (4-bit packed) */
+typedef struct mprg_result mprg_result; /* trees + PRG strings of one mprg_build call */
+
+/* A sub-alignment: rows (subset, input order) x columns [c0, c1) of one locus of a batch.
+ * Mirrors what NodeFactory.build receives (recursion_tree.py:401-406): every sub-alignment the
+ * reference ever builds is a (row subset, contiguous column range) of the root MSA. */
+typedef struct {
+    int32_t locus;    /* index into the batch */
+    int32_t rows_off; /* offset into the caller's row-index array, or -1 for "all rows" */
+    int32_t n_rows;
+    int32_t c0, c1;
+} mprg_task;
+
+typedef struct {
+    int32_t start, stop; /* closed interval, columns relative to the task's c0 */
+    int32_t type;        /* MPRG_IV_MATCH / MPRG_IV_NONMATCH */
+} mprg_interval;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int mprg_create(int device_ordinal, mprg_ctx **out);
+void mprg_destroy(mprg_ctx *ctx);
+const char *mprg_last_error(const mprg_ctx *ctx);
+int mprg_device_info(const mprg_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t mprg_launch_count(const mprg_ctx *ctx);
+/* device time (ms, CUDA events on the context's stream) and algorithmic bytes of the column-scan
+ * kernel accumulated since the last reset; used by bench.py for the roofline object */
+int mprg_scan_stats(mprg_ctx *ctx, double *ms, double *bytes, int64_t *launches, int reset);
+
+/* ---- loader -> HBM (replaces the in-memory Biopython MSA of io_utils.py:17-49) --------------- */
+/* h_ascii: concatenated row-major ASCII matrices (upper or lower case, N already replaced by the
+ * host loader); locus i occupies n_rows[i]*n_cols[i] bytes starting at h_offsets[i].
+ * Copies to the device, packs to 4 bits there, records per-locus alphabet flags. */
+int mprg_batch_upload(mprg_ctx *ctx, const uint8_t *h_ascii, const int64_t *h_offsets,
+                      const int32_t *n_rows, const int32_t *n_cols, int32_t n_loci,
+                      mprg_batch **out);
+void mprg_batch_free(mprg_ctx *ctx, mprg_batch *batch);
+/* flags[i] bit0: locus holds a character outside ACGTRYKMSWN- (=> SequenceCurationError),
+ * bit1: holds N, bit2: holds RYKMSW */
+int mprg_batch_flags(mprg_ctx *ctx, const mprg_batch *batch, int32_t *h_flags);
+/* debug/parity: copy the packed rows of one locus back (n_rows * stride bytes) */
+int mprg_batch_download_packed(mprg_ctx *ctx, const mprg_batch *batch, int32_t locus,
+                               uint8_t *h_out, int64_t capacity, int32_t *stride);
+
+/* ---- kernel (a): column scan  (get_consensus_from_MSA seq_utils.py:219-239,
+ *      has_empty_sequence seq_utils.py:37-42 in its gap-reach form) ---------- */
+/* For each task: h_consensus gets c1-c0 bytes ('*' for non-match, else the base), h_gap_reach gets
+ * c1-c0 int32 (relative to c0): has_empty_sequence([s,e]) == (gap_reach[s] >= e).
+ * Outputs of task t start at h_col_offsets[t] (the caller provides the prefix sums). */
+int mprg_scan_tasks(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks,
+                    int32_t n_tasks, const int32_t *h_rows, int64_t n_row_entries,
+                    const int64_t *h_col_offsets, uint8_t *h_consensus, int32_t *h_gap_reach);
+
+/* ---- kernel (a'): interval partition (IntervalPartitioner interval_partition.py:81-252,
+ *      NodeFactory._get_vertical_partition recursion_tree.py:500-513) --------------------------- */
+/* Full vertical partition of each task: scan + run state machine + single-sequence demotion
+ * (enforce_multisequence_nonmatch_intervals) + bijection check.  h_intervals receives, per task,
+ * h_iv_counts[t] intervals sorted by start at h_iv_offsets[t] (capacity max(1, c1-c0) each). */
+int mprg_partition_tasks(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks,
+                         int32_t n_tasks, const int32_t *h_rows, int64_t n_row_entries,
+                         int32_t min_match_length, const int64_t *h_iv_offsets,
+                         mprg_interval *h_intervals, int32_t *h_iv_counts);
+/* The state machine alone on a caller-supplied consensus string (the reference's unit tests drive
+ * IntervalPartitioner with hand-written consensus strings and an empty alignment,
+ * tests/from_msa/test_interval_partition.py:80-136).  gap_reach may be NULL (no empty rows). */
+int mprg_partition_consensus(mprg_ctx *ctx, const uint8_t *h_consensus, const int32_t *h_gap_reach,
+                             int32_t n_cols, int32_t min_match_length, mprg_interval *h_intervals,
+                             int32_t capacity, int32_t *h_count);
+
+/* ---- kernels (b), (c): clustering of one sub-alignment per task
+ *      (kmeans_cluster_seqs cluster_sequences.py:211-296) --------------------------------------- */
+/* Row de-duplication (cluster_sequences.py:220-233, seq_utils.py:58-70): per row of each task the
+ * index (in first-seen order) of its distinct ungapped sequence, the ungapped length, and per task
+ * the number of distinct ungapped / gapped rows.  Row outputs start at h_row_offsets[t]. */
+int mprg_dedupe_rows(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks,
+                     int32_t n_tasks, const int32_t *h_rows, int64_t n_row_entries,
+                     const int64_t *h_row_offsets, int32_t *h_group, int32_t *h_ungapped_len,
+                     int32_t *h_n_ungapped, int32_t *h_n_gapped);
+/* k-mer count matrix of one task (count_distinct_kmers / count_kmer_occurrences
+ * cluster_sequences.py:26-56): distinct ungapped sequences of length >= k in first-seen order are
+ * the rows, k-mers in first-occurrence order the columns.  h_counts (row-major doubles, capacity
+ * given in elements) may be NULL to query the shape only. */
+int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_task,
+                     const int32_t *h_rows, int32_t kmer_size, int32_t *n_seqs, int32_t *n_kmers,
+                     double *h_counts, int64_t capacity);
+/* KMeans(n_clusters=K, random_state=2, algorithm="elkan") of scikit-learn 1.3.0 (n_init=10),
+ * .fit(X).predict(X) as called at cluster_sequences.py:262-266.  X row-major [n, F] doubles. */
+int mprg_kmeans(mprg_ctx *ctx, const double *h_X, int32_t n, int32_t F, int32_t K,
+                int32_t *h_labels, double *h_inertia);
+/* sequences_are_one_reference_like over clusters of gapped rows (cluster_sequences.py:59-111):
+ * cluster_of_row[i] in [0, n_clusters) for each row of the task (in member order = the order the
+ * caller lists them in h_rows); out_flags[c] = 1 when cluster c is one-reference-like. */
+int mprg_one_ref_like(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_task,
+                      const int32_t *h_rows, const int32_t *h_cluster_of_row, int32_t n_clusters,
+                      int32_t *h_flags);
+/* Whole kmeans_cluster_seqs for a list of tasks.  Per row (at h_row_offsets[t]) the cluster index in
+ * the order of ClusteringResult.clustered_ids; h_n_clusters[t] == 1 means "no clustering". */
+int mprg_cluster_tasks(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks,
+                       int32_t n_tasks, const int32_t *h_rows, int64_t n_row_entries,
+                       int32_t kmer_size, const int64_t *h_row_offsets, int32_t *h_cluster,
+                       int32_t *h_n_clusters);
+
+/* ---- the whole path: PrgBuilder.__init__ + build_prg for every locus of a batch
+ *      (prg_builder.py:24-42,100-110; NodeFactory.build recursion_tree.py:401-471) -------------- */
+int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, int32_t min_match_length,
+               mprg_result **out);
+void mprg_result_free(mprg_result *res);
+int32_t mprg_result_n_loci(const mprg_result *res);
+int32_t mprg_result_status(const mprg_result *res, int32_t locus);
+/* PRG string of a locus (not NUL-terminated); valid until mprg_result_free */
+const char *mprg_result_prg(const mprg_result *res, int32_t locus, int64_t *length);
+int32_t mprg_result_n_nodes(const mprg_result *res, int32_t locus);
+int32_t mprg_result_n_sites(const mprg_result *res, int32_t locus);
+/* Node table of a locus in pre-order (== node_id order).  Arrays of n_nodes entries; rows of node i
+ * are h_rows[row_off[i] .. row_off[i]+n_rows[i]) of the locus' own row-index pool. */
+int mprg_result_nodes(const mprg_result *res, int32_t locus, int32_t *kind, int32_t *parent,
+                      int32_t *nesting_level, int32_t *c0, int32_t *c1, int32_t *n_rows,
+                      int64_t *row_off, int32_t *n_children);
+int64_t mprg_result_row_pool_size(const mprg_result *res, int32_t locus);
+int mprg_result_row_pool(const mprg_result *res, int32_t locus, int32_t *h_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPRG_H */

@@ -1,0 +1,112 @@
+// C-ABI entry points for the individual kernels (parity tests and the Python mirrors of the
+// reference's functions call these); the whole-path entry point mprg_build lives in engine.cu.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace mprg;
+
+static void account_scan(mprg_ctx *ctx, const Level &lv) {
+    float ms = 0;
+    if (!lv.units.empty() && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) {
+        ctx->scan_ms += ms;
+        ctx->scan_bytes += lv.algo_bytes;
+        ctx->scan_launches += 1;
+    }
+}
+
+extern "C" int mprg_scan_tasks(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks,
+                               int32_t n_tasks, const int32_t *h_rows, int64_t n_row_entries,
+                               const int64_t *h_col_offsets, uint8_t *h_consensus,
+                               int32_t *h_gap_reach) {
+    if (!ctx || !batch || n_tasks < 0 || (n_tasks > 0 && (!h_tasks || !h_col_offsets)))
+        return MPRG_E_BAD_ARG;
+    Level lv;
+    int rc = level_run(ctx, batch, h_tasks, n_tasks, h_rows, n_row_entries, 1, false, lv);
+    if (rc != MPRG_OK) return rc;
+    if (n_tasks == 0) return MPRG_OK;
+    std::vector<uint8_t> cls((size_t)lv.total_cols);
+    std::vector<int> reach((size_t)lv.total_cols);
+    MPRG_CUDA(ctx, cudaMemcpyAsync(cls.data(), ctx->d_cls.p, cls.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(reach.data(), ctx->d_reach.p, sizeof(int) * reach.size(),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    MPRG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    account_scan(ctx, lv);
+    for (int i = 0; i < n_tasks; ++i) {
+        const DTask &t = lv.tasks[i];
+        const int n = t.c1 - t.c0, shift = t.c0 & 31;
+        if (h_consensus && n) memcpy(h_consensus + h_col_offsets[i], cls.data() + t.col_off + shift, n);
+        if (h_gap_reach && n)
+            memcpy(h_gap_reach + h_col_offsets[i], reach.data() + t.col_off + shift, sizeof(int) * n);
+    }
+    return MPRG_OK;
+}
+
+extern "C" int mprg_partition_tasks(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks,
+                                    int32_t n_tasks, const int32_t *h_rows, int64_t n_row_entries,
+                                    int32_t min_match_length, const int64_t *h_iv_offsets,
+                                    mprg_interval *h_intervals, int32_t *h_iv_counts) {
+    if (!ctx || !batch || n_tasks < 0 ||
+        (n_tasks > 0 && (!h_tasks || !h_iv_offsets || !h_intervals || !h_iv_counts)))
+        return MPRG_E_BAD_ARG;
+    Level lv;
+    int rc = level_run(ctx, batch, h_tasks, n_tasks, h_rows, n_row_entries, min_match_length, true, lv);
+    if (rc != MPRG_OK) return rc;
+    if (n_tasks == 0) return MPRG_OK;
+    std::vector<DInterval> iv((size_t)lv.total_iv);
+    std::vector<int> cnt(n_tasks + 1);
+    MPRG_CUDA(ctx, cudaMemcpyAsync(iv.data(), ctx->d_iv.p, sizeof(DInterval) * iv.size(),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(cnt.data(), ctx->d_ivcnt.p, sizeof(int) * cnt.size(),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    MPRG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    account_scan(ctx, lv);
+    if (cnt[n_tasks]) MPRG_FAIL(ctx, MPRG_E_PARTITION, "Failed interval partitioning");
+    for (int i = 0; i < n_tasks; ++i) {
+        h_iv_counts[i] = cnt[i];
+        for (int k = 0; k < cnt[i]; ++k) {
+            const DInterval &d = iv[lv.tasks[i].iv_off + k];
+            h_intervals[h_iv_offsets[i] + k] = mprg_interval{d.start, d.stop, d.type};
+        }
+    }
+    return MPRG_OK;
+}
+
+extern "C" int mprg_partition_consensus(mprg_ctx *ctx, const uint8_t *h_consensus,
+                                        const int32_t *h_gap_reach, int32_t n_cols,
+                                        int32_t min_match_length, mprg_interval *h_intervals,
+                                        int32_t capacity, int32_t *h_count) {
+    if (!ctx || n_cols < 0 || (n_cols > 0 && !h_consensus) || !h_intervals || !h_count)
+        return MPRG_E_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const int n = n_cols;
+    const size_t ivcap = std::max(n, 1);
+    MPRG_CUDA(ctx, ctx->d_cls.reserve(std::max(n, 1)));
+    MPRG_CUDA(ctx, ctx->d_reach.reserve(sizeof(int) * std::max(n, 1)));
+    MPRG_CUDA(ctx, ctx->d_misc.reserve(sizeof(uint32_t) * (n / 32 + 2)));
+    MPRG_CUDA(ctx, ctx->d_iv.reserve(sizeof(DInterval) * ivcap));
+    MPRG_CUDA(ctx, ctx->d_ivcnt.reserve(sizeof(int) * 2));
+    if (n) MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_cls.p, h_consensus, n, cudaMemcpyHostToDevice, s));
+    if (n && h_gap_reach)
+        MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_reach.p, h_gap_reach, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemsetAsync(ctx->d_ivcnt.p, 0, sizeof(int) * 2, s));
+    int *cnt = ctx->d_ivcnt.as<int>();
+    MPRG_CUDA(ctx, launch_partition_consensus(s, ctx->d_cls.as<uint8_t>(),
+                                              h_gap_reach ? ctx->d_reach.as<int>() : nullptr, n,
+                                              min_match_length, ctx->d_misc.as<uint32_t>(),
+                                              ctx->d_iv.as<DInterval>(), cnt, cnt + 1));
+    ctx->launches++;
+    int hc[2] = {0, 0};
+    std::vector<DInterval> iv(ivcap);
+    MPRG_CUDA(ctx, cudaMemcpyAsync(hc, cnt, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(iv.data(), ctx->d_iv.p, sizeof(DInterval) * ivcap, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    if (hc[1]) MPRG_FAIL(ctx, MPRG_E_PARTITION, "Failed interval partitioning");
+    if (hc[0] > capacity) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "interval capacity too small");
+    *h_count = hc[0];
+    for (int k = 0; k < hc[0]; ++k) h_intervals[k] = mprg_interval{iv[k].start, iv[k].stop, iv[k].type};
+    return MPRG_OK;
+}

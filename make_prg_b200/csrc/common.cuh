@@ -1,0 +1,139 @@
+// Shared definitions for libmprg (sm_100a).  See include/mprg.h for the ABI and DESIGN.md for the
+// data layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mprg.h"
+
+namespace mprg {
+
+constexpr int SYM_GAP = MPRG_SYM_GAP;
+constexpr int SYM_N = MPRG_SYM_N;
+constexpr int SYM_PAD = MPRG_SYM_PAD;
+constexpr int COLS_PER_CHUNK = 32;  // one 16-byte vector load = 32 columns of one row
+constexpr int CHUNK_BYTES = 16;
+
+// Device-side task descriptor (one sub-alignment).
+struct DTask {
+    long long base;   // byte offset of the locus in the packed arena
+    int stride;       // bytes per packed row (multiple of 16)
+    int rows_off;     // offset into the row-index arena, -1 => rows are 0..n_rows-1
+    int n_rows;
+    int c0, c1;       // column window [c0, c1) in locus coordinates
+    int col_off;      // offset (columns, multiple of 32) of this task's per-column outputs; the
+                      // outputs cover the chunk-aligned window [c0 & ~31, roundup(c1, 32))
+    int iv_off;       // offset into the interval arena (capacity max(1, c1-c0))
+    int flags;        // bit0: locus may hold N (use the wildcard path)
+};
+
+struct DInterval {
+    int start, stop, type;
+};
+
+// A unit of scan work: a row range of one task (all its columns), handled by one CTA.
+struct ScanUnit {
+    int task;
+    int row_begin;
+    int row_count;
+};
+
+// Growable device buffer (never shrinks); all launches of a context share one stream, so reuse
+// across calls is ordered.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+}  // namespace mprg
+
+struct mprg_batch {
+    int n_loci = 0;
+    std::vector<int> n_rows, n_cols, stride;
+    std::vector<long long> base;  // byte offsets into d_packed
+    std::vector<int> flags;       // alphabet flags per locus (host copy)
+    long long packed_bytes = 0;
+    uint8_t *d_packed = nullptr;
+    bool any_n = false;
+};
+
+struct mprg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+    // scan-kernel accounting for the roofline object
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double scan_ms = 0, scan_bytes = 0;
+    long long scan_launches = 0;
+    // scratch (device)
+    mprg::DevBuf d_tasks, d_units, d_rows, d_colwords, d_colB, d_cls, d_reach, d_iv, d_ivcnt, d_misc,
+        d_stage;
+    // scratch for clustering
+    mprg::DevBuf d_c[16];
+    // scratch (pinned host)
+    mprg::PinnedBuf h_a, h_b, h_c, h_d;
+};
+
+#define MPRG_CUDA(ctx, call)                                                                   \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
+            return MPRG_E_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define MPRG_FAIL(ctx, code, msg) \
+    do {                          \
+        (ctx)->err = (msg);       \
+        return (code);            \
+    } while (0)

@@ -1,0 +1,116 @@
+// Host side of one recursion level: task table, scan units, launches.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mprg {
+
+constexpr int MAX_UNIT_ROWS = 1024;  // rows of one task handled by one CTA
+
+int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, int n_tasks,
+              const int32_t *h_rows, long long n_row_entries, int mml, bool do_partition, Level &lv) {
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    lv = Level();
+    lv.n_tasks = n_tasks;
+    lv.tasks.resize(n_tasks);
+    lv.has_n = batch->any_n;
+    long long col_off = 0, iv_off = 0;
+    for (int i = 0; i < n_tasks; ++i) {
+        const mprg_task &ht = h_tasks[i];
+        if (ht.locus < 0 || ht.locus >= batch->n_loci) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "task locus out of range");
+        const int R = batch->n_rows[ht.locus], C = batch->n_cols[ht.locus];
+        if (ht.c0 < 0 || ht.c1 < ht.c0 || ht.c1 > C || ht.n_rows < 0 ||
+            (ht.rows_off < 0 && ht.n_rows > R) ||
+            (ht.rows_off >= 0 && (long long)ht.rows_off + ht.n_rows > n_row_entries))
+            MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "task window / rows out of range");
+        DTask &t = lv.tasks[i];
+        t.base = batch->base[ht.locus];
+        t.stride = batch->stride[ht.locus];
+        t.rows_off = ht.rows_off;
+        t.n_rows = ht.n_rows;
+        t.c0 = ht.c0;
+        t.c1 = ht.c1;
+        const int a0 = ht.c0 & ~31, a1 = (ht.c1 + 31) & ~31;
+        const int aligned = std::max(a1 - a0, 32);
+        if (col_off + aligned > 0x7fffffffLL) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "level too wide");
+        t.col_off = (int)col_off;
+        t.iv_off = (int)iv_off;
+        t.flags = batch->any_n ? 1 : 0;
+        col_off += aligned;
+        iv_off += std::max(ht.c1 - ht.c0, 1);
+        const double r = ht.n_rows, c = ht.c1 - ht.c0;
+        lv.algo_bytes += r * c / 2 + (ht.rows_off >= 0 ? 4.0 * r : 0.0) + 5.0 * c;
+        for (int rb = 0; rb < ht.n_rows; rb += MAX_UNIT_ROWS) {
+            const int cnt = std::min(MAX_UNIT_ROWS, ht.n_rows - rb);
+            lv.units.push_back(ScanUnit{i, rb, cnt});
+            lv.max_unit_rows = std::max(lv.max_unit_rows, cnt);
+        }
+    }
+    lv.total_cols = col_off;
+    lv.total_iv = iv_off;
+    if (n_tasks == 0) return MPRG_OK;
+    // validate row indices are inside their locus (cheap, protects the kernels)
+    for (int i = 0; i < n_tasks; ++i) {
+        const mprg_task &ht = h_tasks[i];
+        if (ht.rows_off < 0) continue;
+        const int R = batch->n_rows[ht.locus];
+        for (int k = 0; k < ht.n_rows; ++k) {
+            const int r = h_rows[ht.rows_off + k];
+            if (r < 0 || r >= R) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "row index out of range");
+        }
+    }
+
+    const size_t n_units = lv.units.size();
+    MPRG_CUDA(ctx, ctx->d_tasks.reserve(sizeof(DTask) * n_tasks));
+    MPRG_CUDA(ctx, ctx->d_units.reserve(sizeof(ScanUnit) * std::max<size_t>(n_units, 1)));
+    MPRG_CUDA(ctx, ctx->d_rows.reserve(sizeof(int) * std::max<long long>(n_row_entries, 1)));
+    // colwords: colOR | colNOR (total_cols/8 words each) ; colB: total_cols unsigned
+    const size_t words = (size_t)lv.total_cols / 8;
+    MPRG_CUDA(ctx, ctx->d_colwords.reserve(sizeof(uint32_t) * 2 * words));
+    MPRG_CUDA(ctx, ctx->d_colB.reserve(sizeof(unsigned) * lv.total_cols));
+    MPRG_CUDA(ctx, ctx->d_cls.reserve((size_t)lv.total_cols));
+    MPRG_CUDA(ctx, ctx->d_reach.reserve(sizeof(int) * lv.total_cols));
+    MPRG_CUDA(ctx, ctx->d_misc.reserve(sizeof(uint32_t) * (lv.total_cols / 32) + 64));
+    MPRG_CUDA(ctx, ctx->d_iv.reserve(sizeof(DInterval) * lv.total_iv));
+    MPRG_CUDA(ctx, ctx->d_ivcnt.reserve(sizeof(int) * (n_tasks + 1)));
+
+    MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_tasks.p, lv.tasks.data(), sizeof(DTask) * n_tasks,
+                                   cudaMemcpyHostToDevice, s));
+    if (n_units)
+        MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_units.p, lv.units.data(), sizeof(ScanUnit) * n_units,
+                                       cudaMemcpyHostToDevice, s));
+    if (n_row_entries > 0)
+        MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_rows.p, h_rows, sizeof(int) * n_row_entries,
+                                       cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemsetAsync(ctx->d_colwords.p, 0, sizeof(uint32_t) * 2 * words, s));
+    MPRG_CUDA(ctx, cudaMemsetAsync(ctx->d_colB.p, 0, sizeof(unsigned) * lv.total_cols, s));
+    // last int of d_ivcnt is the partition error flag
+    MPRG_CUDA(ctx, cudaMemsetAsync(ctx->d_ivcnt.p, 0, sizeof(int) * (n_tasks + 1), s));
+
+    uint32_t *colOR = ctx->d_colwords.as<uint32_t>();
+    uint32_t *colNOR = colOR + words;
+    MPRG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    MPRG_CUDA(ctx, launch_scan(s, lv.has_n, batch->d_packed, ctx->d_tasks.as<DTask>(),
+                               ctx->d_units.as<ScanUnit>(), (int)n_units, lv.max_unit_rows,
+                               ctx->d_rows.as<int>(), colOR, colNOR, ctx->d_colB.as<unsigned>()));
+    MPRG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    ctx->launches += n_units ? 1 : 0;
+    MPRG_CUDA(ctx, launch_classify(s, ctx->d_tasks.as<DTask>(), n_tasks, colOR, colNOR,
+                                   ctx->d_colB.as<unsigned>(), ctx->d_cls.as<uint8_t>(),
+                                   ctx->d_reach.as<int>(), ctx->d_misc.as<uint32_t>()));
+    ctx->launches++;
+    if (do_partition) {
+        int *cnt = ctx->d_ivcnt.as<int>();
+        MPRG_CUDA(ctx, launch_partition(s, ctx->d_tasks.as<DTask>(), n_tasks, ctx->d_misc.as<uint32_t>(),
+                                        ctx->d_reach.as<int>(), mml, ctx->d_iv.as<DInterval>(), cnt,
+                                        cnt + n_tasks));
+        MPRG_CUDA(ctx, launch_demote(s, batch->d_packed, ctx->d_tasks.as<DTask>(), n_tasks,
+                                     ctx->d_rows.as<int>(), ctx->d_iv.as<DInterval>(), cnt));
+        ctx->launches += 2;
+    }
+    return MPRG_OK;
+}
+
+}  // namespace mprg
