@@ -88,6 +88,7 @@ extern "C" int mprg_create(int device_ordinal, mprg_ctx **out) {
         delete ctx;
         return MPRG_E_CUDA;
     }
+    cudaDeviceSetLimit(cudaLimitStackSize, 8192);  // recursive pairwise summation in kmeans.cu
     uint8_t lut[256];
     build_lut(lut);
     if (cudaMemcpyToSymbol(c_sym_lut, lut, 256) != cudaSuccess) {

@@ -1,0 +1,404 @@
+// Kernels (b) and the integer part of (c): everything kmeans_cluster_seqs does around KMeans.
+//
+//   unpack_kernel      gapped rows of a task -> one byte per symbol (scratch G, row-major)
+//   dedupe_kernel      distinct ungapped / gapped rows in first-seen order
+//                      (cluster_sequences.py:220-233, seq_utils.py:58-70); hashes are only a filter,
+//                      every merge is verified symbol by symbol
+//   kmer_kernel        ungapped k-mer extraction, first-occurrence column numbering and the dense
+//                      count matrix (count_distinct_kmers / count_kmer_occurrences,
+//                      cluster_sequences.py:26-56)
+//   refcheck_kernel    cluster_further / sequences_are_one_reference_like (majority string with
+//                      first-seen tie-break, Hamming distance, threshold; cluster_sequences.py:59-111)
+//                      plus the loop control of kmeans_cluster_seqs (:256-261)
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mprg {
+
+__device__ __forceinline__ int sym_of(const uint8_t *row, int col) {
+    const uint8_t b = row[col >> 1];
+    return (col & 1) ? (b >> 4) : (b & 15);
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+// ---- unpack -------------------------------------------------------------------------------------
+// one CTA per task, warps over rows, lanes over columns
+__global__ void __launch_bounds__(256)
+unpack_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks,
+              const int *__restrict__ rows_arena, const long long *__restrict__ g_off,
+              uint8_t *__restrict__ G) {
+    const DTask t = tasks[blockIdx.x];
+    const int w = t.c1 - t.c0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int *rows = t.rows_off >= 0 ? rows_arena + t.rows_off : nullptr;
+    uint8_t *out = G + g_off[blockIdx.x];
+    for (int r = warp; r < t.n_rows; r += nw) {
+        const uint8_t *row = packed + t.base + (long long)(rows ? rows[r] : r) * t.stride;
+        for (int i = lane; i < w; i += 32) out[(long long)r * w + i] = (uint8_t)sym_of(row, t.c0 + i);
+    }
+}
+
+// ---- dedupe ---------------------------------------------------------------------------------------
+struct RowSig {
+    uint64_t hu, hg;
+    int len;
+    int pad;
+};
+
+__device__ bool same_ungapped(const uint8_t *a, const uint8_t *b, int w) {
+    int i = 0, j = 0;
+    while (true) {
+        while (i < w && a[i] == SYM_GAP) ++i;
+        while (j < w && b[j] == SYM_GAP) ++j;
+        if (i >= w || j >= w) return (i >= w) == (j >= w);
+        if (a[i] != b[j]) return false;
+        ++i;
+        ++j;
+    }
+}
+
+// one CTA per task.  Outputs per row (at row_off[t]): group = index of the row's distinct ungapped
+// sequence in first-seen order, ulen = ungapped length; per task the distinct counts.
+__global__ void __launch_bounds__(256)
+dedupe_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ g_off,
+              const uint8_t *__restrict__ G, const long long *__restrict__ row_off,
+              RowSig *__restrict__ sig, int *__restrict__ leader_u, int *__restrict__ leader_g,
+              int *__restrict__ group, int *__restrict__ ulen, int *__restrict__ n_ungapped,
+              int *__restrict__ n_gapped, int *__restrict__ err) {
+    const int ti = blockIdx.x;
+    const DTask t = tasks[ti];
+    const int w = t.c1 - t.c0, R = t.n_rows;
+    const uint8_t *g = G + g_off[ti];
+    const long long ro = row_off[ti];
+    RowSig *s = sig + ro;
+    int *lu = leader_u + ro, *lg = leader_g + ro;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const uint8_t *row = g + (long long)r * w;
+        uint64_t hu = 0x9e3779b97f4a7c15ULL, hg = 0x2545f4914f6cdd1dULL;
+        int len = 0;
+        for (int i = 0; i < w; ++i) {
+            const uint64_t c = row[i];
+            hg = (hg ^ (c + 1)) * 0x100000001b3ULL;
+            hg ^= hg >> 29;
+            if (c != SYM_GAP) {
+                hu = (hu ^ (c + 1)) * 0x9fb21c651e98df25ULL;
+                hu ^= hu >> 31;
+                ++len;
+            }
+        }
+        s[r] = RowSig{mix64(hu), mix64(hg), len, 0};
+        ulen[ro + r] = len;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const RowSig me = s[r];
+        int a = r, b = r;
+        for (int q = 0; q < r; ++q) {
+            const RowSig o = s[q];
+            if (a == r && o.hu == me.hu && o.len == me.len) a = q;
+            if (b == r && o.hg == me.hg) b = q;
+            if (a != r && b != r) break;
+        }
+        // verify the merges exactly (hash equality is only a filter)
+        if (a != r && !same_ungapped(g + (long long)a * w, g + (long long)r * w, w)) atomicExch(err, 2);
+        if (b != r) {
+            const uint8_t *x = g + (long long)b * w, *y = g + (long long)r * w;
+            bool eq = true;
+            for (int i = 0; i < w && eq; ++i) eq = x[i] == y[i];
+            if (!eq) atomicExch(err, 2);
+        }
+        lu[r] = a;
+        lg[r] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nu = 0, ng = 0;
+        for (int r = 0; r < R; ++r) {
+            if (lu[r] == r) group[ro + r] = nu++;
+            else group[ro + r] = group[ro + lu[r]];
+            ng += lg[r] == r;
+        }
+        n_ungapped[ti] = nu;
+        n_gapped[ti] = ng;
+    }
+}
+
+// ---- k-mer counting -------------------------------------------------------------------------------
+// Per clustering problem (one CTA): the n distinct long sequences are rows seq_rows[0..n) (task-local
+// row positions) of the task's unpacked block G.
+
+__device__ __forceinline__ uint64_t kmer_hash(const uint8_t *p, int k) {
+    uint64_t h = 0x243f6a8885a308d3ULL;
+    for (int i = 0; i < k; ++i) h = (h ^ (uint64_t)(p[i] + 1)) * 0x9e3779b97f4a7c15ULL + (h >> 32);
+    h = mix64(h);
+    return h == ~0ULL ? 0 : h;  // ~0 marks an empty slot
+}
+
+// block-wide exclusive prefix sum over `n` ints in place (values small); returns the total
+__device__ int block_exclusive_scan(int *a, int n, int *s_warp /* >= 33 ints */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? a[i] : 0;
+        int x = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += o;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int y = lane < nw ? s_warp[lane] : 0;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, y, d);
+                if (lane >= d) y += o;
+            }
+            s_warp[lane] = y;  // inclusive over warps
+        }
+        __syncthreads();
+        const int warp_excl = warp ? s_warp[warp - 1] : 0;
+        if (i < n) a[i] = carry + warp_excl + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += s_warp[nw - 1];
+        __syncthreads();
+    }
+    return carry;
+}
+
+__global__ void __launch_bounds__(256)
+kmer_kernel(const KmerProb *__restrict__ probs, const int *__restrict__ seq_rows,
+            const uint8_t *__restrict__ G, int k, uint8_t *__restrict__ useq_all,
+            int *__restrict__ ints_all, uint64_t *__restrict__ keys_all, int *__restrict__ ming_all,
+            double *__restrict__ X_all, int *__restrict__ out_F, int *__restrict__ err) {
+    __shared__ int s_warp[33];
+    const KmerProb p = probs[blockIdx.x];
+    const uint8_t *g = G + p.g_off;
+    const int *srow = seq_rows + p.seq_off;
+    uint8_t *useq = useq_all + p.useq_off;
+    int *ulen = ints_all + p.pos_off;
+    int *pos = ulen + p.n;
+    int *mref = pos + p.n + 1;
+    int *kid = mref + p.Pmax;
+    uint64_t *keys = keys_all + p.tab_off;
+    int *ming = ming_all + p.tab_off;
+    double *X = X_all + p.x_off;
+    const int w = p.w, n = p.n;
+
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const uint8_t *row = g + (long long)srow[j] * w;
+        uint8_t *u = useq + (long long)j * w;
+        int len = 0;
+        for (int i = 0; i < w; ++i)
+            if (row[i] != SYM_GAP) u[len++] = row[i];
+        ulen[j] = len;
+    }
+    for (int i = threadIdx.x; i < p.T; i += blockDim.x) {
+        keys[i] = ~0ULL;
+        ming[i] = 0x7fffffff;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int j = 0; j < n; ++j) {
+            pos[j] = acc;
+            acc += ulen[j] - k + 1;  // every sequence here has ulen >= k
+        }
+        pos[n] = acc;
+    }
+    __syncthreads();
+    const int P = pos[n];
+    const int mask = p.T - 1;
+    // insert: slot key claimed by CAS, first-occurrence position by atomicMin
+    for (int gidx = threadIdx.x; gidx < P; gidx += blockDim.x) {
+        int lo = 0, hi = n;  // pos[lo] <= gidx < pos[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pos[mid] <= gidx) lo = mid; else hi = mid;
+        }
+        const uint8_t *km = useq + (long long)lo * w + (gidx - pos[lo]);
+        const uint64_t key = kmer_hash(km, k);
+        int slot = (int)(key & mask);
+        while (true) {
+            const uint64_t old = atomicCAS((unsigned long long *)&keys[slot], ~0ULL, key);
+            if (old == ~0ULL || old == key) {
+                atomicMin(&ming[slot], gidx);
+                break;
+            }
+            slot = (slot + 1) & mask;
+        }
+        mref[gidx] = slot;
+    }
+    __syncthreads();
+    for (int gidx = threadIdx.x; gidx < P; gidx += blockDim.x) {
+        const int first = ming[mref[gidx]];
+        kid[gidx] = first == gidx ? 1 : 0;
+        mref[gidx] = first;
+        if (first != gidx) {  // verify: same hash must mean same k-mer
+            int lo = 0, hi = n;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pos[mid] <= gidx) lo = mid; else hi = mid;
+            }
+            const uint8_t *a = useq + (long long)lo * w + (gidx - pos[lo]);
+            int lo2 = 0, hi2 = n;
+            while (hi2 - lo2 > 1) {
+                const int mid = (lo2 + hi2) >> 1;
+                if (pos[mid] <= first) lo2 = mid; else hi2 = mid;
+            }
+            const uint8_t *b = useq + (long long)lo2 * w + (first - pos[lo2]);
+            bool eq = true;
+            for (int i = 0; i < k && eq; ++i) eq = a[i] == b[i];
+            if (!eq) atomicExch(err, 3);
+        }
+    }
+    __syncthreads();
+    const int F = block_exclusive_scan(kid, P, s_warp);  // kid[g] = column id when g is a first occurrence
+    if (threadIdx.x == 0) out_F[blockIdx.x] = F;
+    for (long long i = threadIdx.x; i < (long long)n * F; i += blockDim.x) X[i] = 0.0;
+    __syncthreads();
+    for (int gidx = threadIdx.x; gidx < P; gidx += blockDim.x) {
+        int lo = 0, hi = n;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pos[mid] <= gidx) lo = mid; else hi = mid;
+        }
+        atomicAdd(&X[(long long)lo * F + kid[mref[gidx]]], 1.0);
+    }
+}
+
+// ---- one-reference-like check + loop control ------------------------------------------------------
+__global__ void __launch_bounds__(128)
+refcheck_kernel(ClusterState *__restrict__ states, const uint8_t *__restrict__ G,
+                const int *__restrict__ mem_off_all, const int *__restrict__ mem_rows_all,
+                int *__restrict__ assign_all, uint8_t *__restrict__ maj_all, int max_clusters,
+                int *__restrict__ flags_out) {
+    __shared__ int cnt_s[16][128];
+    __shared__ int first_s[16][128];
+    __shared__ int s_bad, s_bad_c;
+    ClusterState &st = states[blockIdx.x];
+    if (st.status != 0) return;
+    const uint8_t *g = G + st.g_off;
+    const int w = st.w, n = st.n, K = st.K;
+    const int *mem_off = mem_off_all + st.mem_off;   // n + 1 entries, into mem_rows
+    const int *mem_rows = mem_rows_all + st.mem_rows_off;
+    const int *assign = assign_all + st.assign_off;
+    uint8_t *maj = maj_all + st.maj_off;
+    const int thr = w < 5 ? 1 : (int)(0.2 * (double)w);
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    for (int c = 0; c < K; ++c) {
+        if (threadIdx.x == 0) s_bad_c = 0;
+        // majority symbol per column over the members of cluster c in member order
+        for (int col0 = 0; col0 < w; col0 += blockDim.x) {
+            const int col = col0 + threadIdx.x;
+            if (col < w) {
+#pragma unroll
+                for (int s = 0; s < 16; ++s) cnt_s[s][threadIdx.x] = 0;
+                int order = 0;
+                for (int j = 0; j < n; ++j) {
+                    if (assign[j] != c) continue;
+                    for (int m = mem_off[j]; m < mem_off[j + 1]; ++m) {
+                        const int s = g[(long long)mem_rows[m] * w + col];
+                        if (cnt_s[s][threadIdx.x]++ == 0) first_s[s][threadIdx.x] = order;
+                        ++order;
+                    }
+                }
+                int best = -1, best_cnt = 0, best_first = 0;
+                for (int s = 0; s < 16; ++s) {
+                    const int cn = cnt_s[s][threadIdx.x];
+                    if (cn == 0) continue;
+                    const int fi = first_s[s][threadIdx.x];
+                    if (cn > best_cnt || (cn == best_cnt && fi < best_first)) {
+                        best = s;
+                        best_cnt = cn;
+                        best_first = fi;
+                    }
+                }
+                maj[col] = (uint8_t)best;
+            }
+        }
+        __syncthreads();
+        // Hamming distance of every member to the majority string
+        for (int j = 0; j < n; ++j) {
+            if (assign[j] != c) continue;
+            const int m0 = mem_off[j], m1 = mem_off[j + 1];
+            for (int m = m0 + threadIdx.x; m < m1; m += blockDim.x) {
+                const uint8_t *row = g + (long long)mem_rows[m] * w;
+                int d = 0;
+                for (int i = 0; i < w; ++i) d += row[i] != maj[i];
+                if (d > thr) {
+                    s_bad = 1;
+                    s_bad_c = 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (flags_out) {
+            if (threadIdx.x == 0) flags_out[st.assign_off + c] = s_bad_c ? 0 : 1;
+        } else if (s_bad) {
+            break;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // kmeans_cluster_seqs loop control (cluster_sequences.py:256-261)
+        if (!s_bad) {
+            st.status = 1;
+        } else {
+            st.K = K + 1;
+            if (st.K > max_clusters || st.K == n) st.status = 1;
+            else st.run_kmeans = 1;
+        }
+    }
+}
+
+cudaError_t launch_unpack(cudaStream_t s, const uint8_t *packed, const DTask *d_tasks, int n_tasks,
+                          const int *d_rows, const long long *g_off, uint8_t *G) {
+    if (n_tasks <= 0) return cudaSuccess;
+    unpack_kernel<<<n_tasks, 256, 0, s>>>(packed, d_tasks, d_rows, g_off, G);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, const long long *g_off,
+                          const uint8_t *G, const long long *row_off, void *sig, int *leader_u,
+                          int *leader_g, int *group, int *ulen, int *n_ungapped, int *n_gapped,
+                          int *err) {
+    if (n_tasks <= 0) return cudaSuccess;
+    dedupe_kernel<<<n_tasks, 256, 0, s>>>(d_tasks, g_off, G, row_off, (RowSig *)sig, leader_u, leader_g,
+                                          group, ulen, n_ungapped, n_gapped, err);
+    return cudaGetLastError();
+}
+
+size_t rowsig_bytes() { return sizeof(RowSig); }
+
+cudaError_t launch_kmer(cudaStream_t s, const void *d_probs, int n_probs, const int *seq_rows,
+                        const uint8_t *G, int k, uint8_t *useq, int *ints, uint64_t *keys, int *ming,
+                        double *X, int *out_F, int *err) {
+    if (n_probs <= 0) return cudaSuccess;
+    kmer_kernel<<<n_probs, 256, 0, s>>>((const KmerProb *)d_probs, seq_rows, G, k, useq, ints, keys, ming,
+                                        X, out_F, err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_refcheck(cudaStream_t s, ClusterState *states, int n_probs, const uint8_t *G,
+                            const int *mem_off, const int *mem_rows, int *assign, uint8_t *maj,
+                            int max_clusters, int *flags_out) {
+    if (n_probs <= 0) return cudaSuccess;
+    refcheck_kernel<<<n_probs, 128, 0, s>>>(states, G, mem_off, mem_rows, assign, maj, max_clusters,
+                                            flags_out);
+    return cudaGetLastError();
+}
+
+}  // namespace mprg

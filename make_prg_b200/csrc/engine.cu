@@ -1,0 +1,1006 @@
+// Host side of the hot path: the level-synchronous replacement of NodeFactory.build's recursion
+// (make_prg/recursion_tree.py:401-471) and of kmeans_cluster_seqs' control flow
+// (make_prg/from_msa/cluster_sequences.py:211-296), PRG emission (recursion_tree.py:194-300,
+// prg_builder.py:100-110) and the C-ABI entry points built on them.
+//
+// At every recursion depth all pending sub-alignments of all loci form ONE device batch:
+//   level_run()      scan -> classify -> partition -> demote            (scan.cu, partition.cu)
+//   cluster_level()  unpack -> dedupe -> k-mer counts -> [refcheck, KMeans] x K  (cluster.cu, kmeans.cu)
+// The host only keeps the tree bookkeeping (nodes, row subsets, child tasks), the cluster-merge
+// ordering rules and the string assembly.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <unordered_set>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace mprg;
+
+namespace mprg {
+
+// ---- MT19937 as numpy's RandomState(seed) / random_sample ---------------------------------------
+static void randomstate_doubles(uint32_t seed, double *out, int count) {
+    const int N = 624, M = 397;
+    uint32_t mt[N];
+    mt[0] = seed;
+    for (int i = 1; i < N; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    int idx = N;
+    auto gen = [&]() -> uint32_t {
+        if (idx >= N) {
+            for (int k = 0; k < N; ++k) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % N] & 0x7fffffffu);
+                mt[k] = mt[(k + M) % N] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    };
+    for (int i = 0; i < count; ++i) {
+        const uint32_t a = gen() >> 5, b = gen() >> 6;
+        out[i] = (a * 67108864.0 + b) / 9007199254740992.0;
+    }
+}
+
+static bool g_rand_uploaded = false;
+static int ensure_rand(mprg_ctx *ctx) {
+    if (g_rand_uploaded) return MPRG_OK;
+    double r[KM_RAND_COUNT];
+    randomstate_doubles(2u, r, KM_RAND_COUNT);
+    MPRG_CUDA(ctx, kmeans_upload_rand(r));
+    g_rand_uploaded = true;
+    return MPRG_OK;
+}
+
+// ---- allele extraction ---------------------------------------------------------------------------
+struct ExtractItem {
+    long long base;
+    int stride, row, c0, c1;
+    long long out_off;
+};
+
+__global__ void __launch_bounds__(128)
+extract_kernel(const uint8_t *__restrict__ packed, const ExtractItem *__restrict__ items, int n_items,
+               uint8_t *__restrict__ out, int *__restrict__ out_len) {
+    // one warp per item: ordered compaction of the non-gap symbols, 32 columns at a time
+    const int lane = threadIdx.x & 31;
+    const int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (it >= n_items) return;
+    const ExtractItem e = items[it];
+    const uint8_t *row = packed + e.base + (long long)e.row * e.stride;
+    const char *alphabet = "ACGT-RYKMSWN????";
+    int len = 0;
+    for (int c0 = e.c0; c0 < e.c1; c0 += 32) {
+        const int c = c0 + lane;
+        int sym = SYM_GAP;
+        if (c < e.c1) {
+            const uint8_t b = row[c >> 1];
+            sym = (c & 1) ? (b >> 4) : (b & 15);
+        }
+        const unsigned keep = __ballot_sync(0xffffffffu, sym != SYM_GAP);
+        if (sym != SYM_GAP) out[e.out_off + len + __popc(keep & ((1u << lane) - 1u))] = (uint8_t)alphabet[sym];
+        len += __popc(keep);
+    }
+    if (lane == 0) out_len[it] = len;
+}
+
+// ---- clustering of a level ------------------------------------------------------------------------
+struct ClusterOut {
+    int n_ungapped = 0, n_gapped = 0;
+    std::vector<int> group;  // per task row: distinct ungapped sequence (first-seen order)
+    std::vector<int> ulen;   // per task row: ungapped length
+    bool no_clustering = true;
+    std::vector<std::vector<int>> clusters;  // ClusteringResult.clustered_ids as task-local row positions
+};
+
+static void single_cluster(const std::vector<std::vector<int>> &long_ids,
+                           const std::vector<std::vector<int>> &small_ids, ClusterOut &o) {
+    // cluster_sequences.py:237-246 / 276-285 + merge_clusters (:194-208): everything in one cluster,
+    // the first record moved to the front
+    std::vector<int> all;
+    for (auto &v : long_ids) all.insert(all.end(), v.begin(), v.end());
+    for (auto &v : small_ids) all.insert(all.end(), v.begin(), v.end());
+    auto it = std::find(all.begin(), all.end(), 0);
+    if (it != all.end()) {
+        all.erase(it);
+        all.insert(all.begin(), 0);
+    }
+    o.no_clustering = true;
+    o.clusters.clear();
+    o.clusters.push_back(std::move(all));
+}
+
+// want_clusters[t] == 0: only the de-duplication outputs are needed for task t
+static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, int n_tasks,
+                         const int32_t *h_rows, long long n_row_entries, int kmer_size,
+                         const uint8_t *want_clusters, std::vector<ClusterOut> &out,
+                         bool skip_if_issues = false) {
+    out.assign(n_tasks, ClusterOut());
+    if (n_tasks == 0) return MPRG_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    int rc = ensure_rand(ctx);
+    if (rc != MPRG_OK) return rc;
+
+    // device task table (only base/stride/rows/window are used by these kernels)
+    std::vector<DTask> tasks(n_tasks);
+    std::vector<long long> g_off(n_tasks), row_off(n_tasks);
+    long long g_total = 0, row_total = 0;
+    for (int i = 0; i < n_tasks; ++i) {
+        const mprg_task &ht = h_tasks[i];
+        if (ht.locus < 0 || ht.locus >= batch->n_loci || ht.c0 < 0 || ht.c1 < ht.c0 ||
+            ht.c1 > batch->n_cols[ht.locus] || ht.n_rows < 0 ||
+            (ht.rows_off < 0 && ht.n_rows > batch->n_rows[ht.locus]) ||
+            (ht.rows_off >= 0 && (long long)ht.rows_off + ht.n_rows > n_row_entries))
+            MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "cluster task out of range");
+        DTask &t = tasks[i];
+        t.base = batch->base[ht.locus];
+        t.stride = batch->stride[ht.locus];
+        t.rows_off = ht.rows_off;
+        t.n_rows = ht.n_rows;
+        t.c0 = ht.c0;
+        t.c1 = ht.c1;
+        t.col_off = t.iv_off = t.flags = 0;
+        g_off[i] = g_total;
+        row_off[i] = row_total;
+        g_total += (long long)ht.n_rows * (ht.c1 - ht.c0);
+        row_total += ht.n_rows;
+    }
+    DevBuf *B = ctx->d_c;  // 0 tasks, 1 g_off, 2 row_off, 3 G, 4 sig, 5 ints(leader_u|leader_g|group|ulen|nu|ng|err)
+    MPRG_CUDA(ctx, B[0].reserve(sizeof(DTask) * n_tasks));
+    MPRG_CUDA(ctx, B[1].reserve(sizeof(long long) * n_tasks));
+    MPRG_CUDA(ctx, B[2].reserve(sizeof(long long) * n_tasks));
+    MPRG_CUDA(ctx, B[3].reserve((size_t)std::max<long long>(g_total, 1)));
+    MPRG_CUDA(ctx, B[4].reserve(rowsig_bytes() * std::max<long long>(row_total, 1)));
+    const long long n_int = 4 * row_total + 2LL * n_tasks + 1;
+    MPRG_CUDA(ctx, B[5].reserve(sizeof(int) * n_int));
+    MPRG_CUDA(ctx, ctx->d_rows.reserve(sizeof(int) * std::max<long long>(n_row_entries, 1)));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(B[0].p, tasks.data(), sizeof(DTask) * n_tasks, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(B[1].p, g_off.data(), sizeof(long long) * n_tasks, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(B[2].p, row_off.data(), sizeof(long long) * n_tasks, cudaMemcpyHostToDevice, s));
+    if (n_row_entries > 0)
+        MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_rows.p, h_rows, sizeof(int) * n_row_entries, cudaMemcpyHostToDevice, s));
+    int *d_leader_u = B[5].as<int>();
+    int *d_leader_g = d_leader_u + row_total;
+    int *d_group = d_leader_g + row_total;
+    int *d_ulen = d_group + row_total;
+    int *d_nu = d_ulen + row_total;
+    int *d_ng = d_nu + n_tasks;
+    int *d_err = d_ng + n_tasks;
+    MPRG_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(int), s));
+    MPRG_CUDA(ctx, launch_unpack(s, batch->d_packed, B[0].as<DTask>(), n_tasks, ctx->d_rows.as<int>(),
+                                 B[1].as<long long>(), B[3].as<uint8_t>()));
+    MPRG_CUDA(ctx, launch_dedupe(s, B[0].as<DTask>(), n_tasks, B[1].as<long long>(), B[3].as<uint8_t>(),
+                                 B[2].as<long long>(), B[4].p, d_leader_u, d_leader_g, d_group, d_ulen,
+                                 d_nu, d_ng, d_err));
+    ctx->launches += 2;
+    std::vector<int> h_ints((size_t)(2 * row_total + 2LL * n_tasks + 1));
+    // group|ulen|nu|ng|err are contiguous
+    MPRG_CUDA(ctx, cudaMemcpyAsync(h_ints.data(), d_group, sizeof(int) * h_ints.size(), cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    const int *h_group = h_ints.data();
+    const int *h_ulen = h_group + row_total;
+    const int *h_nu = h_ulen + row_total;
+    const int *h_ng = h_nu + n_tasks;
+    if (h_ng[n_tasks]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while de-duplicating rows");
+
+    // host: long / short distinct sequences per task, trivial outcomes, KMeans problems
+    struct Prob {
+        int task;
+        int n;
+        long long P;
+        std::vector<int> leaders;               // task-local row position of each distinct long sequence
+        std::vector<std::vector<int>> long_ids; // rows of each distinct long sequence
+        std::vector<std::vector<int>> small_ids;
+    };
+    std::vector<Prob> probs;
+    for (int i = 0; i < n_tasks; ++i) {
+        ClusterOut &o = out[i];
+        const int R = h_tasks[i].n_rows;
+        o.n_ungapped = h_nu[i];
+        o.n_gapped = h_ng[i];
+        o.group.assign(h_group + row_off[i], h_group + row_off[i] + R);
+        o.ulen.assign(h_ulen + row_off[i], h_ulen + row_off[i] + R);
+        if (want_clusters && !want_clusters[i]) continue;
+        if (R == 0) continue;
+        // NodeFactory._alignment_has_issues (recursion_tree.py:475-494) discards the clustering anyway
+        if (skip_if_issues && (o.n_ungapped <= 2 || o.n_ungapped < o.n_gapped)) continue;
+        // distinct sequences in first-seen order; long ones (len >= k) keep their own numbering
+        std::vector<int> long_index(o.n_ungapped, -1), small_index(o.n_ungapped, -1);
+        Prob p;
+        p.task = i;
+        for (int r = 0; r < R; ++r) {
+            const int gidx = o.group[r];
+            if (o.ulen[r] >= kmer_size) {
+                if (long_index[gidx] < 0) {
+                    long_index[gidx] = (int)p.long_ids.size();
+                    p.long_ids.emplace_back();
+                    p.leaders.push_back(r);
+                }
+                p.long_ids[long_index[gidx]].push_back(r);
+            } else {
+                if (small_index[gidx] < 0) {
+                    small_index[gidx] = (int)p.small_ids.size();
+                    p.small_ids.emplace_back();
+                }
+                p.small_ids[small_index[gidx]].push_back(r);
+            }
+        }
+        p.n = (int)p.long_ids.size();
+        if (p.n <= 2) {
+            single_cluster(p.long_ids, p.small_ids, o);
+            continue;
+        }
+        p.P = 0;
+        for (int r : p.leaders) p.P += o.ulen[r] - kmer_size + 1;
+        probs.push_back(std::move(p));
+    }
+    const int np = (int)probs.size();
+    if (np == 0) return MPRG_OK;
+
+    // ---- k-mer count matrices ----
+    std::vector<KmerProb> kp(np);
+    std::vector<int> seq_rows, mem_off, mem_rows;
+    long long useq_total = 0, ints_total = 0, tab_total = 0, x_total = 0;
+    std::vector<ClusterState> st(np);
+    long long maj_total = 0, assign_total = 0;
+    for (int q = 0; q < np; ++q) {
+        const Prob &p = probs[q];
+        const mprg_task &ht = h_tasks[p.task];
+        const int w = ht.c1 - ht.c0;
+        if (p.P > 0x3fffffffLL) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "clustering problem too large");
+        KmerProb &k = kp[q];
+        k.g_off = g_off[p.task];
+        k.w = w;
+        k.n = p.n;
+        k.seq_off = (int)seq_rows.size();
+        seq_rows.insert(seq_rows.end(), p.leaders.begin(), p.leaders.end());
+        k.useq_off = useq_total;
+        useq_total += (long long)p.n * w;
+        k.pos_off = ints_total;
+        ints_total += 2LL * p.n + 1 + 2 * p.P;
+        int T = 64;
+        while (T < 2 * p.P) T <<= 1;
+        k.T = T;
+        k.tab_off = tab_total;
+        tab_total += T;
+        k.Pmax = (int)p.P;
+        k.x_off = x_total;
+        x_total += (long long)p.n * p.P;
+        ClusterState &c = st[q];
+        memset(&c, 0, sizeof(c));
+        c.K = 1;
+        c.n = p.n;
+        c.w = w;
+        c.g_off = g_off[p.task];
+        c.mem_off = (int)mem_off.size();
+        c.mem_rows_off = (int)mem_rows.size();
+        int acc = 0;
+        for (auto &v : p.long_ids) {
+            mem_off.push_back(acc);
+            acc += (int)v.size();
+            mem_rows.insert(mem_rows.end(), v.begin(), v.end());
+        }
+        mem_off.push_back(acc);
+        c.assign_off = (int)assign_total;
+        assign_total += p.n;
+        c.maj_off = maj_total;
+        maj_total += w;
+        c.x_off = k.x_off;
+    }
+    if (x_total * 8 > (24LL << 30)) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "k-mer count matrices exceed the 24 GiB scratch budget");
+    // 6 kprobs, 7 seq_rows, 8 useq, 9 ints, 10 keys, 11 ming, 12 X, 13 states|F, 14 mem|assign|newlab|maj, 15 kmeans scratch
+    MPRG_CUDA(ctx, B[6].reserve(sizeof(KmerProb) * np));
+    MPRG_CUDA(ctx, B[7].reserve(sizeof(int) * seq_rows.size()));
+    MPRG_CUDA(ctx, B[8].reserve((size_t)useq_total));
+    MPRG_CUDA(ctx, B[9].reserve(sizeof(int) * ints_total));
+    MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * tab_total));
+    MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * tab_total));
+    MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * x_total));
+    MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * np + 64));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(B[6].p, kp.data(), sizeof(KmerProb) * np, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(B[7].p, seq_rows.data(), sizeof(int) * seq_rows.size(), cudaMemcpyHostToDevice, s));
+    ClusterState *d_states = B[13].as<ClusterState>();
+    int *d_F = reinterpret_cast<int *>(d_states + np);
+    MPRG_CUDA(ctx, launch_kmer(s, B[6].p, np, B[7].as<int>(), B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
+                               B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), B[12].as<double>(), d_F,
+                               d_err));
+    ctx->launches++;
+    std::vector<int> h_F(np + 1);
+    MPRG_CUDA(ctx, cudaMemcpyAsync(h_F.data(), d_F, sizeof(int) * np, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(&h_F[np], d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    if (h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
+
+    // ---- KMeans loop (cluster_sequences.py:256-274) ----
+    long long kmd_total = 0, kmi_total = 0;
+    for (int q = 0; q < np; ++q) {
+        st[q].F = h_F[q];
+        st[q].kmd_off = kmd_total;
+        st[q].kmi_off = kmi_total;
+        kmd_total += kmeans_dscratch_doubles(st[q].n, st[q].F);
+        kmi_total += kmeans_iscratch_ints(st[q].n);
+    }
+    const size_t o_memoff = 0;
+    const size_t o_memrows = o_memoff + sizeof(int) * mem_off.size();
+    const size_t o_assign = o_memrows + sizeof(int) * mem_rows.size();
+    const size_t o_newlab = o_assign + sizeof(int) * assign_total;
+    const size_t o_maj = o_newlab + sizeof(int) * assign_total;
+    MPRG_CUDA(ctx, B[14].reserve(o_maj + (size_t)maj_total + 16));
+    MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * kmd_total + sizeof(int) * kmi_total + 64));
+    uint8_t *b14 = B[14].as<uint8_t>();
+    int *d_memoff = reinterpret_cast<int *>(b14 + o_memoff);
+    int *d_memrows = reinterpret_cast<int *>(b14 + o_memrows);
+    int *d_assign = reinterpret_cast<int *>(b14 + o_assign);
+    int *d_newlab = reinterpret_cast<int *>(b14 + o_newlab);
+    uint8_t *d_maj = b14 + o_maj;
+    double *d_kmd = B[15].as<double>();
+    int *d_kmi = reinterpret_cast<int *>(d_kmd + kmd_total);
+    MPRG_CUDA(ctx, cudaMemcpyAsync(d_states, st.data(), sizeof(ClusterState) * np, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(d_memoff, mem_off.data(), sizeof(int) * mem_off.size(), cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(d_memrows, mem_rows.data(), sizeof(int) * mem_rows.size(), cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemsetAsync(d_assign, 0, sizeof(int) * assign_total, s));
+    const int MAX_CLUSTERS = 10;
+    MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
+    ctx->launches++;
+    for (int round = 2; round <= MAX_CLUSTERS; ++round) {
+        MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab));
+        MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
+        ctx->launches += 2;
+    }
+    std::vector<int> h_assign((size_t)assign_total);
+    MPRG_CUDA(ctx, cudaMemcpyAsync(st.data(), d_states, sizeof(ClusterState) * np, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(h_assign.data(), d_assign, sizeof(int) * assign_total, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+
+    for (int q = 0; q < np; ++q) {
+        const Prob &p = probs[q];
+        ClusterOut &o = out[p.task];
+        const ClusterState &c = st[q];
+        if (c.status != 1) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "clustering loop did not terminate");
+        const int K = c.K;
+        if (K == 1 || K == p.n) {
+            single_cluster(p.long_ids, p.small_ids, o);
+            continue;
+        }
+        const int *assign = h_assign.data() + c.assign_off;
+        const int n_lab = std::min(K, MAX_CLUSTERS);  // K == 11 keeps the 10-cluster assignment
+        std::vector<std::vector<int>> cl(n_lab);
+        for (int j = 0; j < p.n; ++j) {
+            if (assign[j] < 0 || assign[j] >= n_lab) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "label out of range");
+            cl[assign[j]].insert(cl[assign[j]].end(), p.long_ids[j].begin(), p.long_ids[j].end());
+        }
+        for (auto &v : p.small_ids) cl.push_back(v);
+        // merge_clusters: the cluster holding the first record goes first, that record first in it
+        size_t fi = 0;
+        for (size_t a = 0; a < cl.size(); ++a)
+            if (std::find(cl[a].begin(), cl[a].end(), 0) != cl[a].end()) fi = a;
+        std::vector<int> first = cl[fi];
+        first.erase(std::find(first.begin(), first.end(), 0));
+        first.insert(first.begin(), 0);
+        o.clusters.clear();
+        o.clusters.push_back(std::move(first));
+        for (size_t a = 0; a < cl.size(); ++a)
+            if (a != fi) o.clusters.push_back(std::move(cl[a]));
+        o.no_clustering = o.clusters.size() == 1;
+    }
+    return MPRG_OK;
+}
+
+}  // namespace mprg
+
+// =================================================================================================
+// C ABI: clustering entry points
+// =================================================================================================
+extern "C" int mprg_dedupe_rows(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks,
+                                int32_t n_tasks, const int32_t *h_rows, int64_t n_row_entries,
+                                const int64_t *h_row_offsets, int32_t *h_group, int32_t *h_ungapped_len,
+                                int32_t *h_n_ungapped, int32_t *h_n_gapped) {
+    if (!ctx || !batch || n_tasks < 0 || (n_tasks > 0 && (!h_tasks || !h_row_offsets))) return MPRG_E_BAD_ARG;
+    std::vector<ClusterOut> out;
+    std::vector<uint8_t> want(std::max(n_tasks, 1), 0);
+    int rc = cluster_level(ctx, batch, h_tasks, n_tasks, h_rows, n_row_entries, 1, want.data(), out);
+    if (rc != MPRG_OK) return rc;
+    for (int i = 0; i < n_tasks; ++i) {
+        const int R = h_tasks[i].n_rows;
+        if (h_group && R) memcpy(h_group + h_row_offsets[i], out[i].group.data(), sizeof(int) * R);
+        if (h_ungapped_len && R) memcpy(h_ungapped_len + h_row_offsets[i], out[i].ulen.data(), sizeof(int) * R);
+        if (h_n_ungapped) h_n_ungapped[i] = out[i].n_ungapped;
+        if (h_n_gapped) h_n_gapped[i] = out[i].n_gapped;
+    }
+    return MPRG_OK;
+}
+
+extern "C" int mprg_cluster_tasks(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks,
+                                  int32_t n_tasks, const int32_t *h_rows, int64_t n_row_entries,
+                                  int32_t kmer_size, const int64_t *h_row_offsets, int32_t *h_cluster,
+                                  int32_t *h_n_clusters) {
+    if (!ctx || !batch || n_tasks < 0 || kmer_size < 1 ||
+        (n_tasks > 0 && (!h_tasks || !h_row_offsets || !h_cluster || !h_n_clusters)))
+        return MPRG_E_BAD_ARG;
+    std::vector<ClusterOut> out;
+    int rc = cluster_level(ctx, batch, h_tasks, n_tasks, h_rows, n_row_entries, kmer_size, nullptr, out);
+    if (rc != MPRG_OK) return rc;
+    for (int i = 0; i < n_tasks; ++i) {
+        h_n_clusters[i] = (int)out[i].clusters.size();
+        for (size_t c = 0; c < out[i].clusters.size(); ++c)
+            for (int r : out[i].clusters[c]) h_cluster[h_row_offsets[i] + r] = (int)c;
+    }
+    return MPRG_OK;
+}
+
+extern "C" int mprg_kmeans(mprg_ctx *ctx, const double *h_X, int32_t n, int32_t F, int32_t K,
+                           int32_t *h_labels, double *h_inertia) {
+    if (!ctx || !h_X || !h_labels || n < 1 || F < 1 || K < 1 || K > 10 || K > n) return MPRG_E_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    int rc = ensure_rand(ctx);
+    if (rc != MPRG_OK) return rc;
+    DevBuf *B = ctx->d_c;
+    const long long nd = kmeans_dscratch_doubles(n, F), ni = kmeans_iscratch_ints(n);
+    MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * (size_t)n * F));
+    MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * (nd + 1) + sizeof(int) * (ni + n)));
+    double *d_d = B[15].as<double>();
+    double *d_inertia = d_d + nd;
+    int *d_i = reinterpret_cast<int *>(d_inertia + 1);
+    int *d_labels = d_i + ni;
+    MPRG_CUDA(ctx, cudaMemcpyAsync(B[12].p, h_X, sizeof(double) * (size_t)n * F, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, launch_kmeans_single(s, B[12].as<double>(), n, F, K, d_d, d_i, d_labels, d_inertia));
+    ctx->launches++;
+    MPRG_CUDA(ctx, cudaMemcpyAsync(h_labels, d_labels, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    double inertia = 0;
+    MPRG_CUDA(ctx, cudaMemcpyAsync(&inertia, d_inertia, sizeof(double), cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    if (h_inertia) *h_inertia = inertia;
+    return MPRG_OK;
+}
+
+extern "C" int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_task,
+                                const int32_t *h_rows, int32_t kmer_size, int32_t *n_seqs,
+                                int32_t *n_kmers, double *h_counts, int64_t capacity) {
+    if (!ctx || !batch || !h_task || kmer_size < 1 || !n_seqs || !n_kmers) return MPRG_E_BAD_ARG;
+    std::vector<ClusterOut> out;
+    uint8_t want = 0;
+    mprg_task t = *h_task;
+    const long long n_row_entries = t.rows_off >= 0 ? (long long)t.rows_off + t.n_rows : 0;
+    int rc = cluster_level(ctx, batch, &t, 1, h_rows, n_row_entries, kmer_size, &want, out);
+    if (rc != MPRG_OK) return rc;
+    cudaStream_t s = ctx->stream;
+    DevBuf *B = ctx->d_c;
+    const ClusterOut &o = out[0];
+    std::vector<int> leaders;
+    std::vector<char> seen(o.n_ungapped, 0);
+    long long P = 0;
+    for (int r = 0; r < t.n_rows; ++r)
+        if (o.ulen[r] >= kmer_size && !seen[o.group[r]]) {
+            seen[o.group[r]] = 1;
+            leaders.push_back(r);
+            P += o.ulen[r] - kmer_size + 1;
+        }
+    const int n = (int)leaders.size();
+    *n_seqs = n;
+    *n_kmers = 0;
+    if (n == 0) return MPRG_OK;
+    const int w = t.c1 - t.c0;
+    KmerProb k;
+    memset(&k, 0, sizeof(k));
+    k.g_off = 0;
+    k.w = w;
+    k.n = n;
+    k.seq_off = 0;
+    k.useq_off = 0;
+    k.pos_off = 0;
+    k.tab_off = 0;
+    int T = 64;
+    while (T < 2 * P) T <<= 1;
+    k.T = T;
+    k.Pmax = (int)P;
+    k.x_off = 0;
+    MPRG_CUDA(ctx, B[6].reserve(sizeof(KmerProb)));
+    MPRG_CUDA(ctx, B[7].reserve(sizeof(int) * n));
+    MPRG_CUDA(ctx, B[8].reserve((size_t)n * w + 1));
+    MPRG_CUDA(ctx, B[9].reserve(sizeof(int) * (2LL * n + 1 + 2 * P)));
+    MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * T));
+    MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * T));
+    MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * (size_t)n * P));
+    MPRG_CUDA(ctx, B[13].reserve(sizeof(int) * 2));
+    int *d_F = B[13].as<int>();
+    MPRG_CUDA(ctx, cudaMemsetAsync(d_F, 0, sizeof(int) * 2, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(B[6].p, &k, sizeof(k), cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(B[7].p, leaders.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, launch_kmer(s, B[6].p, 1, B[7].as<int>(), B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
+                               B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), B[12].as<double>(), d_F,
+                               d_F + 1));
+    ctx->launches++;
+    int hF[2] = {0, 0};
+    MPRG_CUDA(ctx, cudaMemcpyAsync(hF, d_F, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    if (hF[1]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
+    *n_kmers = hF[0];
+    if (h_counts) {
+        if (capacity < (int64_t)n * hF[0]) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "count matrix capacity too small");
+        MPRG_CUDA(ctx, cudaMemcpyAsync(h_counts, B[12].p, sizeof(double) * (size_t)n * hF[0], cudaMemcpyDeviceToHost, s));
+        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    return MPRG_OK;
+}
+
+extern "C" int mprg_one_ref_like(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_task,
+                                 const int32_t *h_rows, const int32_t *h_cluster_of_row,
+                                 int32_t n_clusters, int32_t *h_flags) {
+    if (!ctx || !batch || !h_task || !h_cluster_of_row || !h_flags || n_clusters < 1) return MPRG_E_BAD_ARG;
+    std::vector<ClusterOut> out;
+    uint8_t want = 0;
+    mprg_task t = *h_task;
+    const long long n_row_entries = t.rows_off >= 0 ? (long long)t.rows_off + t.n_rows : 0;
+    int rc = cluster_level(ctx, batch, &t, 1, h_rows, n_row_entries, 1, &want, out);
+    if (rc != MPRG_OK) return rc;
+    cudaStream_t s = ctx->stream;
+    DevBuf *B = ctx->d_c;
+    const int R = t.n_rows, w = t.c1 - t.c0;
+    for (int r = 0; r < R; ++r)
+        if (h_cluster_of_row[r] < 0 || h_cluster_of_row[r] >= n_clusters) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "cluster index out of range");
+    ClusterState c;
+    memset(&c, 0, sizeof(c));
+    c.K = n_clusters;
+    c.n = R;
+    c.w = w;
+    std::vector<int> mem_off(R + 1), mem_rows(R);
+    for (int r = 0; r < R; ++r) {
+        mem_off[r] = r;
+        mem_rows[r] = r;
+    }
+    mem_off[R] = R;
+    const size_t o_memrows = sizeof(int) * (R + 1), o_assign = o_memrows + sizeof(int) * R;
+    const size_t o_flags = o_assign + sizeof(int) * R, o_maj = o_flags + sizeof(int) * n_clusters;
+    MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState)));
+    MPRG_CUDA(ctx, B[14].reserve(o_maj + w + 16));
+    uint8_t *b = B[14].as<uint8_t>();
+    MPRG_CUDA(ctx, cudaMemcpyAsync(B[13].p, &c, sizeof(c), cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(b, mem_off.data(), sizeof(int) * (R + 1), cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(b + o_memrows, mem_rows.data(), sizeof(int) * R, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, cudaMemcpyAsync(b + o_assign, h_cluster_of_row, sizeof(int) * R, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, launch_refcheck(s, B[13].as<ClusterState>(), 1, B[3].as<uint8_t>(), (int *)b, (int *)(b + o_memrows),
+                                   (int *)(b + o_assign), b + o_maj, 10, (int *)(b + o_flags)));
+    ctx->launches++;
+    MPRG_CUDA(ctx, cudaMemcpyAsync(h_flags, b + o_flags, sizeof(int) * n_clusters, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    return MPRG_OK;
+}
+
+// =================================================================================================
+// The whole path: PrgBuilder.__init__ + build_prg for every locus of a batch
+// =================================================================================================
+namespace mprg {
+
+struct HNode {
+    int kind = -1;
+    int parent = -1;
+    int level = 0;
+    int c0 = 0, c1 = 0;
+    long long row_off = -1;  // into the locus row pool, -1 = all rows
+    int n_rows = 0;
+    std::vector<int> children;
+    int allele_first = -1, allele_count = 0;  // extract items of a leaf
+};
+
+struct LocusResult {
+    int status = MPRG_LOCUS_OK;
+    std::vector<HNode> nodes;       // creation (level) order; node 0 is the root
+    std::vector<int> row_pool;
+    std::vector<int> preorder;      // node indices in pre-order == node_id order
+    std::string prg;
+    int n_sites = 0;
+};
+
+static const char *iupac_alternatives(char c) {
+    switch (c) {
+        case 'R': return "GA";
+        case 'Y': return "TC";
+        case 'K': return "GT";
+        case 'M': return "AC";
+        case 'S': return "GC";
+        case 'W': return "AT";
+        default: return nullptr;
+    }
+}
+
+// SequenceExpander.get_expanded_sequences (seq_utils.py:116-153) on already distinct sequences
+static bool expand_sequences(const std::vector<std::string> &seqs, std::vector<std::string> &out) {
+    out.clear();
+    std::unordered_set<std::string> seen;
+    for (const std::string &sq : seqs) {
+        if (sq.find('N') != std::string::npos) continue;
+        bool plain = true;
+        for (char c : sq) plain &= (c == 'A' || c == 'C' || c == 'G' || c == 'T');
+        if (plain) {
+            if (seen.insert(sq).second) out.push_back(sq);
+            continue;
+        }
+        // itertools.product order: the leftmost position varies slowest
+        std::vector<int> amb;
+        for (size_t i = 0; i < sq.size(); ++i)
+            if (iupac_alternatives(sq[i])) amb.push_back((int)i);
+        const size_t total = (size_t)1 << amb.size();
+        for (size_t m = 0; m < total; ++m) {
+            std::string e = sq;
+            for (size_t a = 0; a < amb.size(); ++a) {
+                const int bit = (int)((m >> (amb.size() - 1 - a)) & 1u);
+                e[amb[a]] = iupac_alternatives(sq[amb[a]])[bit];
+            }
+            if (seen.insert(e).second) out.push_back(e);
+        }
+    }
+    return !out.empty();
+}
+
+}  // namespace mprg
+
+struct mprg_result {
+    std::vector<LocusResult> loci;
+};
+
+extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
+                          int32_t min_match_length, mprg_result **out_res) {
+    if (!ctx || !batch || !out_res || min_match_length < 1) return MPRG_E_BAD_ARG;
+    *out_res = nullptr;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const int n_loci = batch->n_loci;
+    mprg_result *res = new mprg_result();
+    res->loci.resize(n_loci);
+    struct Pending {
+        int locus, node;
+    };
+    struct Allele {
+        int locus, row, c0, c1;
+    };
+    std::vector<Pending> pending, next;
+    std::vector<Allele> alleles;
+    auto fail = [&](int code) {
+        delete res;
+        return code;
+    };
+    for (int l = 0; l < n_loci; ++l) {
+        LocusResult &L = res->loci[l];
+        if (batch->flags[l] & 1) {
+            L.status = MPRG_LOCUS_CURATION_ERROR;
+            continue;
+        }
+        if ((batch->flags[l] & 2) || batch->n_rows[l] <= 0) {
+            L.status = 2;  // N present (loader must replace it first) or empty alignment
+            continue;
+        }
+        HNode root;
+        root.parent = -1;
+        root.level = 0;
+        root.c0 = 0;
+        root.c1 = batch->n_cols[l];
+        root.row_off = -1;
+        root.n_rows = batch->n_rows[l];
+        L.nodes.push_back(root);
+        pending.push_back(Pending{l, 0});
+    }
+    auto first_row = [&](const LocusResult &L, const HNode &nd) {
+        return nd.row_off < 0 ? 0 : L.row_pool[nd.row_off];
+    };
+    auto make_match_leaf = [&](int l, HNode &nd) {
+        LocusResult &L = res->loci[l];
+        nd.kind = MPRG_NODE_LEAF;
+        nd.allele_first = (int)alleles.size();
+        nd.allele_count = 1;
+        alleles.push_back(Allele{l, first_row(L, nd), nd.c0, nd.c1});
+    };
+
+    std::vector<mprg_task> tasks;
+    std::vector<int32_t> arena;
+    std::vector<DInterval> iv;
+    std::vector<int> cnt;
+    while (!pending.empty()) {
+        const int nt = (int)pending.size();
+        tasks.resize(nt);
+        arena.clear();
+        for (int i = 0; i < nt; ++i) {
+            const LocusResult &L = res->loci[pending[i].locus];
+            const HNode &nd = L.nodes[pending[i].node];
+            mprg_task &t = tasks[i];
+            t.locus = pending[i].locus;
+            t.n_rows = nd.n_rows;
+            t.c0 = nd.c0;
+            t.c1 = nd.c1;
+            if (nd.row_off < 0) {
+                t.rows_off = -1;
+            } else {
+                if (arena.size() + (size_t)nd.n_rows > 0x7fffffffULL) {
+                    ctx->err = "row arena overflow";
+                    return fail(MPRG_E_BAD_ARG);
+                }
+                t.rows_off = (int)arena.size();
+                arena.insert(arena.end(), L.row_pool.begin() + nd.row_off,
+                             L.row_pool.begin() + nd.row_off + nd.n_rows);
+            }
+        }
+        Level lv;
+        int rc = level_run(ctx, batch, tasks.data(), nt, arena.data(), (long long)arena.size(),
+                           min_match_length, true, lv);
+        if (rc != MPRG_OK) return fail(rc);
+        iv.resize((size_t)lv.total_iv);
+        cnt.resize(nt + 1);
+        cudaError_t e;
+        if ((e = cudaMemcpyAsync(iv.data(), ctx->d_iv.p, sizeof(DInterval) * iv.size(), cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(cnt.data(), ctx->d_ivcnt.p, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(s)) != cudaSuccess) {
+            ctx->err = std::string("level D2H: ") + cudaGetErrorString(e);
+            return fail(MPRG_E_CUDA);
+        }
+        {
+            float ms = 0;
+            if (!lv.units.empty() && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) {
+                ctx->scan_ms += ms;
+                ctx->scan_bytes += lv.algo_bytes;
+                ctx->scan_launches += 1;
+            }
+        }
+        if (cnt[nt]) {
+            ctx->err = "Failed interval partitioning";
+            return fail(MPRG_E_PARTITION);
+        }
+        next.clear();
+        std::vector<int> cluster_idx;  // indices into pending/tasks
+        for (int i = 0; i < nt; ++i) {
+            const int l = pending[i].locus;
+            LocusResult &L = res->loci[l];
+            const int ni = pending[i].node;
+            const DInterval *ivs = iv.data() + lv.tasks[i].iv_off;
+            const int c = cnt[i];
+            const bool is_root = L.nodes[ni].parent < 0;
+            if (c == 1 && ivs[0].type != MPRG_IV_NONMATCH) {
+                make_match_leaf(l, L.nodes[ni]);
+            } else if (c > 1 || is_root) {
+                if (c == 0) {
+                    L.status = 2;  // zero-column root: the reference trips an assertion here
+                    continue;
+                }
+                L.nodes[ni].kind = MPRG_NODE_INTERVAL;
+                for (int k = 0; k < c; ++k) {
+                    HNode ch;
+                    ch.parent = ni;
+                    ch.level = L.nodes[ni].level;
+                    ch.c0 = L.nodes[ni].c0 + ivs[k].start;
+                    ch.c1 = L.nodes[ni].c0 + ivs[k].stop + 1;
+                    ch.row_off = L.nodes[ni].row_off;
+                    ch.n_rows = L.nodes[ni].n_rows;
+                    const int ci = (int)L.nodes.size();
+                    L.nodes.push_back(ch);
+                    L.nodes[ni].children.push_back(ci);
+                    // a pure match interval re-partitions to itself: leaf without another scan
+                    if (ivs[k].type == MPRG_IV_MATCH) make_match_leaf(l, L.nodes[ci]);
+                    else next.push_back(Pending{l, ci});
+                }
+            } else {
+                cluster_idx.push_back(i);
+            }
+        }
+        if (!cluster_idx.empty()) {
+            const int nc = (int)cluster_idx.size();
+            std::vector<mprg_task> ctasks(nc);
+            std::vector<uint8_t> want(nc);
+            for (int q = 0; q < nc; ++q) {
+                const int i = cluster_idx[q];
+                ctasks[q] = tasks[i];
+                const HNode &nd = res->loci[pending[i].locus].nodes[pending[i].node];
+                want[q] = (nd.level + 1 < max_nesting) ? 1 : 0;
+            }
+            std::vector<ClusterOut> cout_;
+            rc = cluster_level(ctx, batch, ctasks.data(), nc, arena.data(), (long long)arena.size(),
+                               min_match_length, want.data(), cout_, true);
+            if (rc != MPRG_OK) return fail(rc);
+            for (int q = 0; q < nc; ++q) {
+                const int i = cluster_idx[q];
+                const int l = pending[i].locus, ni = pending[i].node;
+                LocusResult &L = res->loci[l];
+                const ClusterOut &o = cout_[q];
+                const bool has_issues = o.n_ungapped <= 2 || o.n_ungapped < o.n_gapped;
+                const bool further = want[q] && !has_issues && !o.no_clustering && !o.clusters.empty();
+                const int R = L.nodes[ni].n_rows;
+                auto row_id = [&](int pos) {
+                    const HNode &nd = L.nodes[ni];
+                    return nd.row_off < 0 ? pos : L.row_pool[nd.row_off + pos];
+                };
+                if (further) {
+                    L.nodes[ni].kind = MPRG_NODE_CLUSTER;
+                    L.nodes[ni].level += 1;
+                    for (const std::vector<int> &cl : o.clusters) {
+                        std::vector<int> pos(cl);
+                        std::sort(pos.begin(), pos.end());  // sub-alignments keep the input row order
+                        HNode ch;
+                        ch.parent = ni;
+                        ch.level = L.nodes[ni].level;
+                        ch.c0 = L.nodes[ni].c0;
+                        ch.c1 = L.nodes[ni].c1;
+                        ch.row_off = (long long)L.row_pool.size();
+                        ch.n_rows = (int)pos.size();
+                        for (int p : pos) L.row_pool.push_back(row_id(p));
+                        const int ci = (int)L.nodes.size();
+                        L.nodes.push_back(ch);
+                        L.nodes[ni].children.push_back(ci);
+                        next.push_back(Pending{l, ci});
+                    }
+                } else {
+                    // forced leaf: one allele per distinct ungapped row, first-seen order
+                    HNode &nd = L.nodes[ni];
+                    nd.kind = MPRG_NODE_LEAF;
+                    nd.allele_first = (int)alleles.size();
+                    std::vector<char> seen(o.n_ungapped, 0);
+                    for (int r = 0; r < R; ++r)
+                        if (!seen[o.group[r]]) {
+                            seen[o.group[r]] = 1;
+                            alleles.push_back(Allele{l, row_id(r), nd.c0, nd.c1});
+                        }
+                    nd.allele_count = (int)alleles.size() - nd.allele_first;
+                }
+            }
+        }
+        pending.swap(next);
+    }
+
+    // ---- leaf alleles: ungapped strings cut on the device ----
+    const int na = (int)alleles.size();
+    std::vector<ExtractItem> items(na);
+    long long out_total = 0;
+    for (int a = 0; a < na; ++a) {
+        const Allele &al = alleles[a];
+        items[a] = ExtractItem{batch->base[al.locus], batch->stride[al.locus], al.row, al.c0, al.c1, out_total};
+        out_total += al.c1 - al.c0;
+    }
+    std::vector<uint8_t> h_out((size_t)std::max<long long>(out_total, 1));
+    std::vector<int> h_len(std::max(na, 1));
+    if (na > 0) {
+        DevBuf *B = ctx->d_c;
+        cudaError_t e;
+        if ((e = B[0].reserve(sizeof(ExtractItem) * na)) != cudaSuccess ||
+            (e = B[3].reserve((size_t)std::max<long long>(out_total, 1))) != cudaSuccess ||
+            (e = B[5].reserve(sizeof(int) * na)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(B[0].p, items.data(), sizeof(ExtractItem) * na, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
+            ctx->err = std::string("extract setup: ") + cudaGetErrorString(e);
+            return fail(MPRG_E_CUDA);
+        }
+        extract_kernel<<<(na + 3) / 4, 128, 0, s>>>(batch->d_packed, B[0].as<ExtractItem>(), na, B[3].as<uint8_t>(),
+                                                    B[5].as<int>());
+        ctx->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess ||
+            (e = cudaMemcpyAsync(h_out.data(), B[3].p, (size_t)out_total, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(h_len.data(), B[5].p, sizeof(int) * na, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(s)) != cudaSuccess) {
+            ctx->err = std::string("extract: ") + cudaGetErrorString(e);
+            return fail(MPRG_E_CUDA);
+        }
+    }
+
+    // ---- pre-order numbering and PRG strings (recursion_tree.py:194-300, prg_builder.py:100-110) ----
+    std::vector<std::string> raw, expanded;
+    for (int l = 0; l < n_loci; ++l) {
+        LocusResult &L = res->loci[l];
+        if (L.status != MPRG_LOCUS_OK) continue;
+        int site = 5;
+        struct Frame {
+            int node;
+            int next_child;
+            int site;
+        };
+        std::vector<Frame> stack;
+        stack.push_back(Frame{0, 0, 0});
+        auto emit_marker = [&](int m) {
+            L.prg.push_back(' ');
+            L.prg += std::to_string(m);
+            L.prg.push_back(' ');
+        };
+        while (!stack.empty() && L.status == MPRG_LOCUS_OK) {
+            Frame &f = stack.back();
+            HNode &nd = L.nodes[f.node];
+            if (f.next_child == 0) {
+                L.preorder.push_back(f.node);
+                if (nd.kind == MPRG_NODE_LEAF) {
+                    raw.clear();
+                    for (int a = 0; a < nd.allele_count; ++a) {
+                        const ExtractItem &it = items[nd.allele_first + a];
+                        raw.emplace_back(reinterpret_cast<const char *>(h_out.data() + it.out_off),
+                                         (size_t)h_len[nd.allele_first + a]);
+                    }
+                    if (!expand_sequences(raw, expanded)) {
+                        L.status = MPRG_LOCUS_CURATION_ERROR;
+                        break;
+                    }
+                    if (expanded.size() == 1) {
+                        L.prg += expanded[0];
+                    } else {
+                        const int sn = site;
+                        site += 2;
+                        emit_marker(sn);
+                        for (size_t a = 0; a < expanded.size(); ++a) {
+                            L.prg += expanded[a];
+                            emit_marker(a + 1 < expanded.size() ? sn + 1 : sn);
+                        }
+                    }
+                    stack.pop_back();
+                    continue;
+                }
+                if (nd.kind == MPRG_NODE_CLUSTER) {
+                    f.site = site;
+                    site += 2;
+                    emit_marker(f.site);
+                }
+            } else if (nd.kind == MPRG_NODE_CLUSTER) {
+                // separator after child (next_child - 1)
+                emit_marker(f.next_child < (int)nd.children.size() ? f.site + 1 : f.site);
+            }
+            if (f.next_child < (int)nd.children.size()) {
+                const int ch = nd.children[f.next_child];
+                f.next_child++;
+                stack.push_back(Frame{ch, 0, 0});
+            } else {
+                stack.pop_back();
+            }
+        }
+        L.n_sites = (site - 5) / 2;
+        if (L.status != MPRG_LOCUS_OK) {
+            L.prg.clear();
+            L.preorder.clear();
+        }
+    }
+    *out_res = res;
+    return MPRG_OK;
+}
+
+extern "C" void mprg_result_free(mprg_result *res) { delete res; }
+extern "C" int32_t mprg_result_n_loci(const mprg_result *res) { return res ? (int32_t)res->loci.size() : 0; }
+extern "C" int32_t mprg_result_status(const mprg_result *res, int32_t l) {
+    return (res && l >= 0 && l < (int)res->loci.size()) ? res->loci[l].status : -1;
+}
+extern "C" const char *mprg_result_prg(const mprg_result *res, int32_t l, int64_t *length) {
+    if (!res || l < 0 || l >= (int)res->loci.size()) return nullptr;
+    if (length) *length = (int64_t)res->loci[l].prg.size();
+    return res->loci[l].prg.data();
+}
+extern "C" int32_t mprg_result_n_nodes(const mprg_result *res, int32_t l) {
+    return (res && l >= 0 && l < (int)res->loci.size()) ? (int32_t)res->loci[l].preorder.size() : 0;
+}
+extern "C" int32_t mprg_result_n_sites(const mprg_result *res, int32_t l) {
+    return (res && l >= 0 && l < (int)res->loci.size()) ? res->loci[l].n_sites : 0;
+}
+extern "C" int mprg_result_nodes(const mprg_result *res, int32_t l, int32_t *kind, int32_t *parent,
+                                 int32_t *nesting_level, int32_t *c0, int32_t *c1, int32_t *n_rows,
+                                 int64_t *row_off, int32_t *n_children) {
+    if (!res || l < 0 || l >= (int)res->loci.size()) return MPRG_E_BAD_ARG;
+    const LocusResult &L = res->loci[l];
+    std::vector<int> new_id(L.nodes.size(), -1);
+    for (size_t i = 0; i < L.preorder.size(); ++i) new_id[L.preorder[i]] = (int)i;
+    for (size_t i = 0; i < L.preorder.size(); ++i) {
+        const HNode &nd = L.nodes[L.preorder[i]];
+        if (kind) kind[i] = nd.kind;
+        if (parent) parent[i] = nd.parent < 0 ? -1 : new_id[nd.parent];
+        if (nesting_level) nesting_level[i] = nd.level;
+        if (c0) c0[i] = nd.c0;
+        if (c1) c1[i] = nd.c1;
+        if (n_rows) n_rows[i] = nd.n_rows;
+        if (row_off) row_off[i] = nd.row_off;
+        if (n_children) n_children[i] = (int)nd.children.size();
+    }
+    return MPRG_OK;
+}
+extern "C" int64_t mprg_result_row_pool_size(const mprg_result *res, int32_t l) {
+    return (res && l >= 0 && l < (int)res->loci.size()) ? (int64_t)res->loci[l].row_pool.size() : 0;
+}
+extern "C" int mprg_result_row_pool(const mprg_result *res, int32_t l, int32_t *h_rows) {
+    if (!res || l < 0 || l >= (int)res->loci.size() || !h_rows) return MPRG_E_BAD_ARG;
+    const LocusResult &L = res->loci[l];
+    if (!L.row_pool.empty()) memcpy(h_rows, L.row_pool.data(), sizeof(int) * L.row_pool.size());
+    return MPRG_OK;
+}

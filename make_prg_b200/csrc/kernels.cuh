@@ -37,4 +37,60 @@ struct Level {
 int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, int n_tasks,
               const int32_t *h_rows, long long n_row_entries, int mml, bool do_partition, Level &lv);
 
+// ---- clustering (cluster.cu, kmeans.cu) -----------------------------------------------------------
+constexpr int KM_RAND_COUNT = 400;  // doubles of RandomState(2) a 10-init, K<=10 fit can consume
+
+// k-mer counting problem: the n distinct long sequences of one clustering task
+struct KmerProb {
+    long long g_off;     // unpacked rows of the task (bytes into G)
+    int w;               // gapped width
+    int n;               // distinct long sequences
+    int seq_off;         // offset into seq_rows (task-local row positions of the n sequences)
+    long long useq_off;  // scratch bytes: ungapped symbols, n * w
+    long long pos_off;   // scratch ints: ulen[n] | pos[n+1] | mref[Pmax] | kid[Pmax]
+    long long tab_off;   // hash table slots (keys u64 / ming int), T entries
+    int T;               // table size (power of two >= 2 * Pmax)
+    int Pmax;            // upper bound on the number of k-mer positions
+    long long x_off;     // count matrix (doubles), capacity n * Pmax, stride F once known
+};
+
+// per clustering problem: loop state of kmeans_cluster_seqs (cluster_sequences.py:249-274)
+struct ClusterState {
+    int status;      // 0 = looping, 1 = finished
+    int run_kmeans;  // set by refcheck_kernel when KMeans(K) has to run
+    int K;           // num_clusters
+    int n;           // distinct long sequences
+    int F;           // distinct k-mers
+    int w;           // gapped width of the task
+    long long g_off;         // unpacked rows of the task
+    int mem_off;             // n + 1 offsets into mem_rows (members of each distinct sequence)
+    int mem_rows_off;        // base of this problem's member list
+    int assign_off;          // n ints: cluster of each distinct sequence
+    long long maj_off;       // w bytes scratch: majority string
+    long long x_off;         // count matrix
+    long long kmd_off;       // KMeans double scratch
+    long long kmi_off;       // KMeans int scratch
+};
+
+cudaError_t launch_unpack(cudaStream_t s, const uint8_t *packed, const DTask *d_tasks, int n_tasks,
+                          const int *d_rows, const long long *g_off, uint8_t *G);
+cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, const long long *g_off,
+                          const uint8_t *G, const long long *row_off, void *sig, int *leader_u,
+                          int *leader_g, int *group, int *ulen, int *n_ungapped, int *n_gapped,
+                          int *err);
+size_t rowsig_bytes();
+cudaError_t launch_kmer(cudaStream_t s, const void *d_probs, int n_probs, const int *seq_rows,
+                        const uint8_t *G, int k, uint8_t *useq, int *ints, uint64_t *keys, int *ming,
+                        double *X, int *out_F, int *err);
+cudaError_t launch_refcheck(cudaStream_t s, ClusterState *states, int n_probs, const uint8_t *G,
+                            const int *mem_off, const int *mem_rows, int *assign, uint8_t *maj,
+                            int max_clusters, int *flags_out = nullptr);
+long long kmeans_dscratch_doubles(long long n, long long F);
+long long kmeans_iscratch_ints(long long n);
+cudaError_t kmeans_upload_rand(const double *h_rand);
+cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, const double *X,
+                          double *dscratch, int *iscratch, int *assign, int *newlab);
+cudaError_t launch_kmeans_single(cudaStream_t s, const double *X0, int n, int F, int K, double *dscratch,
+                                 int *iscratch, int *labels, double *inertia);
+
 }  // namespace mprg

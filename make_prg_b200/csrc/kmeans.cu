@@ -1,0 +1,622 @@
+// Kernel (c): KMeans exactly as make_prg calls it
+//     KMeans(n_clusters=K, random_state=2, algorithm="elkan").fit(X); .predict(X)
+// (make_prg/from_msa/cluster_sequences.py:262-266) with the semantics of the pinned scikit-learn 1.3.0
+// (n_init=10, k-means++ seeding from one RandomState(2), Elkan iterations, best-of-10 by strict
+// inertia, labels from predict).  float64 throughout, compiled with -fmad=false and written with
+// explicit __dadd_rn/__dmul_rn so that every sum that scikit-learn evaluates sequentially
+// (_euclidean_dense_dense in blocks of four features, centre accumulation in sample order, inertia in
+// sample order, numpy's pairwise summation for the tolerance and the centre-shift total) is evaluated
+// in the same order here.  The three places where scikit-learn goes through BLAS/einsum (k-means++
+// candidate distances, centre-centre distances used for pruning, predict) use a plain left-to-right
+// dot product; results can differ from scikit-learn there only by rounding of quantities that are
+// mathematically tied ("KMeans parity").
+//
+// One CTA per problem; samples (or features, for the centre update) are spread over the threads.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mprg {
+
+constexpr int KM_THREADS = 128;
+constexpr int KM_MAXK = 10;
+constexpr int KM_NINIT = 10;
+constexpr int KM_MAXITER = 300;
+
+__constant__ double c_rand[KM_RAND_COUNT];  // RandomState(2).random_sample stream
+
+__device__ __forceinline__ double sqdist(const double *a, const double *b, int F) {
+    // _euclidean_dense_dense (sklearn/cluster/_k_means_common.pyx): 4-way unrolled, then remainder
+    double res = 0.0;
+    const int m = F >> 2;
+    int i = 0;
+    for (int q = 0; q < m; ++q, i += 4) {
+        const double d0 = __dsub_rn(a[i], b[i]), d1 = __dsub_rn(a[i + 1], b[i + 1]);
+        const double d2 = __dsub_rn(a[i + 2], b[i + 2]), d3 = __dsub_rn(a[i + 3], b[i + 3]);
+        const double s = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)),
+                                             __dmul_rn(d2, d2)), __dmul_rn(d3, d3));
+        res = __dadd_rn(res, s);
+    }
+    for (; i < F; ++i) {
+        const double d = __dsub_rn(a[i], b[i]);
+        res = __dadd_rn(res, __dmul_rn(d, d));
+    }
+    return res;
+}
+
+__device__ __forceinline__ double dot_seq(const double *a, const double *b, int F) {
+    double acc = 0.0;
+    for (int i = 0; i < F; ++i) acc = __dadd_rn(acc, __dmul_rn(a[i], b[i]));
+    return acc;
+}
+
+// numpy's pairwise summation of a contiguous float64 vector (numpy/core/src/umath/loops_utils.h)
+__device__ double np_pairwise_sum(const double *a, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int k = 0; k < 8; ++k) r[k] = a[k];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], a[i + k]);
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(np_pairwise_sum(a, n2), np_pairwise_sum(a + n2, n - n2));
+}
+
+// numpy pairwise summation of (x[f] - c[f])^2 over f in [lo, lo + cnt), evaluated on the fly
+__device__ double np_pairwise_sqdiff(const double *x, const double *c, int lo, int cnt) {
+    if (cnt < 8) {
+        double r0 = 0.0;
+        for (int f = 0; f < cnt; ++f) {
+            const double d = __dsub_rn(x[lo + f], c[lo + f]);
+            r0 = __dadd_rn(r0, __dmul_rn(d, d));
+        }
+        return r0;
+    }
+    if (cnt <= 128) {
+        double r[8];
+        for (int q = 0; q < 8; ++q) {
+            const double d = __dsub_rn(x[lo + q], c[lo + q]);
+            r[q] = __dmul_rn(d, d);
+        }
+        int i = 8;
+        for (; i < cnt - (cnt % 8); i += 8)
+            for (int q = 0; q < 8; ++q) {
+                const double d = __dsub_rn(x[lo + i + q], c[lo + i + q]);
+                r[q] = __dadd_rn(r[q], __dmul_rn(d, d));
+            }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < cnt; ++i) {
+            const double d = __dsub_rn(x[lo + i], c[lo + i]);
+            res = __dadd_rn(res, __dmul_rn(d, d));
+        }
+        return res;
+    }
+    int n2 = cnt / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(np_pairwise_sqdiff(x, c, lo, n2), np_pairwise_sqdiff(x, c, lo + n2, cnt - n2));
+}
+
+struct KM {
+    int n, F, K;
+    const double *X0;
+    double *Xc, *mean, *tmpF, *xx, *ca, *cb, *best_c, *lb, *ub, *closest, *cum, *D, *half, *nxt, *shift,
+        *wts, *cc, *dist;
+    int *labels, *labels_old, *best_labels;
+};
+
+// squared distance candidate -> sample through  -2 x.y + |x|^2 + |y|^2  clamped at 0
+__device__ __forceinline__ double eucl_sq(const KM &k, int cand, int i) {
+    const double d = dot_seq(k.Xc + (long long)cand * k.F, k.Xc + (long long)i * k.F, k.F);
+    double v = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, d), k.xx[cand]), k.xx[i]);
+    return v > 0.0 ? v : 0.0;
+}
+
+__device__ void center_half_distances(const KM &k, const double *C) {
+    const int K = k.K, F = k.F;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) k.cc[j] = dot_seq(C + (long long)j * F, C + (long long)j * F, F);
+    __syncthreads();
+    for (int p = threadIdx.x; p < K * K; p += blockDim.x) {
+        const int a = p / K, b = p % K;
+        double v = 0.0;
+        if (a != b) {
+            const double d = dot_seq(C + (long long)a * F, C + (long long)b * F, F);
+            v = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, d), k.cc[a]), k.cc[b]);
+            v = v > 0.0 ? v : 0.0;
+            v = sqrt(v) / 2.0;
+        }
+        k.half[p] = v;
+    }
+    __syncthreads();
+    // distance_next_center = np.partition(half, kth=1, axis=0)[1]: second smallest per column
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        double m1 = 1e300, m2 = 1e300;
+        for (int a = 0; a < K; ++a) {
+            const double v = k.half[a * K + j];
+            if (v < m1) { m2 = m1; m1 = v; }
+            else if (v < m2) m2 = v;
+        }
+        k.nxt[j] = m2;
+    }
+    __syncthreads();
+}
+
+// E step of _update_chunk_dense (sklearn/cluster/_k_means_elkan.pyx) for every sample
+__device__ void elkan_e_step(const KM &k, const double *C) {
+    const int K = k.K, F = k.F;
+    for (int i = threadIdx.x; i < k.n; i += blockDim.x) {
+        double u = k.ub[i];
+        bool tight = false;
+        int lab = k.labels[i];
+        const double *x = k.Xc + (long long)i * F;
+        double *lbi = k.lb + (long long)i * K;
+        if (!(k.nxt[lab] >= u)) {
+            for (int j = 0; j < K; ++j) {
+                if (j != lab && u > lbi[j] && u > k.half[lab * K + j]) {
+                    if (!tight) {
+                        u = sqrt(sqdist(x, C + (long long)lab * F, F));
+                        lbi[lab] = u;
+                        tight = true;
+                    }
+                    if (u > lbi[j] || u > k.half[lab * K + j]) {
+                        const double d = sqrt(sqdist(x, C + (long long)j * F, F));
+                        lbi[j] = d;
+                        if (d < u) {
+                            lab = j;
+                            u = d;
+                        }
+                    }
+                }
+            }
+            k.labels[i] = lab;
+            k.ub[i] = u;
+        }
+    }
+    __syncthreads();
+}
+
+// one k-means run from k-means++ seeds; returns inertia in *out_inertia (thread 0 valid), final
+// centres in *out_C
+__device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar, int *s_int,
+                              const double **out_C) {
+    const int n = k.n, F = k.F, K = k.K;
+    double *C = k.ca, *Cn = k.cb;
+    const int trials = 2 + (int)log((double)K);
+    // ---- k-means++ (_kmeans_plusplus, sklearn/cluster/_kmeans.py) ----
+    if (threadIdx.x == 0) {
+        // random_state.choice(n, p=1/n): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
+        const double p = 1.0 / (double)n;
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) {
+            acc = __dadd_rn(acc, p);
+            k.cum[i] = acc;
+        }
+        const double total = k.cum[n - 1], u = c_rand[rand_pos];
+        int idx = 0;
+        while (idx < n && k.cum[idx] / total <= u) ++idx;
+        s_int[0] = idx < n ? idx : n - 1;
+    }
+    rand_pos += 1;
+    __syncthreads();
+    const int c0 = s_int[0];
+    for (int f = threadIdx.x; f < F; f += blockDim.x) C[f] = k.Xc[(long long)c0 * F + f];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) k.closest[i] = eucl_sq(k, c0, i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double pot = 0.0;
+        for (int i = 0; i < n; ++i) pot = __dadd_rn(pot, k.closest[i]);
+        s_scalar[0] = pot;
+    }
+    __syncthreads();
+    for (int c = 1; c < K; ++c) {
+        if (threadIdx.x == 0) {
+            const double pot = s_scalar[0];
+            double acc = 0.0;
+            for (int i = 0; i < n; ++i) {
+                acc = __dadd_rn(acc, k.closest[i]);
+                k.cum[i] = acc;
+            }
+            for (int t = 0; t < trials; ++t) {
+                const double val = __dmul_rn(c_rand[rand_pos + t], pot);
+                int lo = 0, hi = n;  // first index with cum[idx] >= val  (searchsorted 'left')
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (k.cum[mid] < val) lo = mid + 1; else hi = mid;
+                }
+                s_int[1 + t] = lo < n - 1 ? lo : n - 1;
+            }
+        }
+        rand_pos += trials;
+        __syncthreads();
+        for (int p = threadIdx.x; p < trials * n; p += blockDim.x) {
+            const int t = p / n, i = p % n;
+            const double d = eucl_sq(k, s_int[1 + t], i);
+            const double cl = k.closest[i];
+            k.D[p] = cl < d ? cl : d;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int best = 0;
+            double best_pot = 0.0;
+            for (int t = 0; t < trials; ++t) {
+                double s = 0.0;
+                for (int i = 0; i < n; ++i) s = __dadd_rn(s, k.D[t * n + i]);
+                if (t == 0 || s < best_pot) {
+                    best = t;
+                    best_pot = s;
+                }
+            }
+            s_scalar[0] = best_pot;
+            s_int[0] = best;
+        }
+        __syncthreads();
+        const int best = s_int[0], cand = s_int[1 + best];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) k.closest[i] = k.D[best * n + i];
+        for (int f = threadIdx.x; f < F; f += blockDim.x) C[(long long)c * F + f] = k.Xc[(long long)cand * F + f];
+        __syncthreads();
+    }
+
+    // ---- Elkan (_kmeans_single_elkan) ----
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        k.labels[i] = -1;
+        k.labels_old[i] = -1;
+        k.ub[i] = 0.0;
+    }
+    for (long long p = threadIdx.x; p < (long long)n * K; p += blockDim.x) k.lb[p] = 0.0;
+    for (long long p = threadIdx.x; p < (long long)K * F; p += blockDim.x) Cn[p] = 0.0;
+    __syncthreads();
+    center_half_distances(k, C);
+    // init_bounds_dense
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double *x = k.Xc + (long long)i * F;
+        int best = 0;
+        double md = sqrt(sqdist(x, C, F));
+        k.lb[(long long)i * K] = md;
+        for (int j = 1; j < K; ++j) {
+            if (md > k.half[best * K + j]) {
+                const double d = sqrt(sqdist(x, C + (long long)j * F, F));
+                k.lb[(long long)i * K + j] = d;
+                if (d < md) {
+                    md = d;
+                    best = j;
+                }
+            }
+        }
+        k.labels[i] = best;
+        k.ub[i] = md;
+    }
+    __syncthreads();
+    bool strict = false;
+    for (int it = 0; it < KM_MAXITER; ++it) {
+        elkan_e_step(k, C);
+        // M step: member sums in sample order (thread per feature), weights
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            double acc[KM_MAXK];
+#pragma unroll
+            for (int j = 0; j < KM_MAXK; ++j) acc[j] = 0.0;
+            for (int i = 0; i < n; ++i) {
+                const int lab = k.labels[i];
+                const double x = k.Xc[(long long)i * F + f];
+#pragma unroll
+                for (int j = 0; j < KM_MAXK; ++j)
+                    if (j == lab) acc[j] = __dadd_rn(acc[j], x);
+            }
+#pragma unroll
+            for (int j = 0; j < KM_MAXK; ++j)
+                if (j < K) Cn[(long long)j * F + f] = acc[j];
+        }
+        if (threadIdx.x == 0) {
+            for (int j = 0; j < K; ++j) k.wts[j] = 0.0;
+            for (int i = 0; i < n; ++i) k.wts[k.labels[i]] += 1.0;
+            int emask = 0;
+            for (int j = 0; j < K; ++j)
+                if (k.wts[j] == 0.0) emask |= 1 << j;
+            s_int[0] = emask;
+        }
+        __syncthreads();
+        const int emask = s_int[0];
+        if (emask != 0) {
+            // _relocate_empty_clusters_dense: farthest samples re-seed the empty clusters
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const double *x = k.Xc + (long long)i * F;
+                const double *c = C + (long long)k.labels[i] * F;
+                // ((X - C[labels])**2).sum(axis=1): numpy pairwise summation over the features
+                const double res = np_pairwise_sqdiff(x, c, 0, F);
+                k.dist[i] = res;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double mx = 0.0;
+                for (int i = 0; i < n; ++i) mx = k.dist[i] > mx ? k.dist[i] : mx;
+                s_int[1] = mx != 0.0;
+            }
+            __syncthreads();
+            if (s_int[1]) {
+                // one empty cluster at a time (ascending id), farthest remaining sample first
+                for (int e = 0; e < K; ++e) {
+                    if (!((emask >> e) & 1)) continue;  // the empty set is fixed before relocating
+                    if (threadIdx.x == 0) {
+                        int far = 0;
+                        double best = -1.0;
+                        for (int i = 0; i < n; ++i)
+                            if (k.dist[i] > best) {
+                                best = k.dist[i];
+                                far = i;
+                            }
+                        k.dist[far] = -2.0;  // taken
+                        s_int[2] = far;
+                    }
+                    __syncthreads();
+                    const int far = s_int[2], old = k.labels[far];
+                    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+                        const double x = k.Xc[(long long)far * F + f];
+                        Cn[(long long)old * F + f] = __dsub_rn(Cn[(long long)old * F + f], x);
+                        Cn[(long long)e * F + f] = x;
+                    }
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        k.wts[e] = 1.0;
+                        k.wts[old] -= 1.0;
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        // _average_centers (thread per feature, clusters in ascending order as the reference loop)
+        if (threadIdx.x == 0) {
+            int amax = 0;
+            for (int j = 1; j < K; ++j)
+                if (k.wts[j] > k.wts[amax]) amax = j;
+            s_int[0] = amax;
+        }
+        __syncthreads();
+        {
+            const int amax = s_int[0];
+            for (int f = threadIdx.x; f < F; f += blockDim.x) {
+                for (int j = 0; j < K; ++j) {
+                    if (k.wts[j] > 0.0) {
+                        const double alpha = 1.0 / k.wts[j];
+                        Cn[(long long)j * F + f] = __dmul_rn(Cn[(long long)j * F + f], alpha);
+                    } else {
+                        Cn[(long long)j * F + f] = Cn[(long long)amax * F + f];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // _center_shift, bounds update
+        for (int j = threadIdx.x; j < K; j += blockDim.x)
+            k.shift[j] = sqrt(sqdist(Cn + (long long)j * F, C + (long long)j * F, F));
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            k.ub[i] = __dadd_rn(k.ub[i], k.shift[k.labels[i]]);
+            for (int j = 0; j < K; ++j) {
+                double v = __dsub_rn(k.lb[(long long)i * K + j], k.shift[j]);
+                k.lb[(long long)i * K + j] = v < 0.0 ? 0.0 : v;
+            }
+        }
+        __syncthreads();
+        center_half_distances(k, Cn);
+        {
+            double *t = C;
+            C = Cn;
+            Cn = t;
+        }
+        // convergence
+        if (threadIdx.x == 0) {
+            bool same = true;
+            for (int i = 0; i < n && same; ++i) same = k.labels[i] == k.labels_old[i];
+            int stop = 0;
+            if (same) stop = 1;
+            else {
+                double sq[KM_MAXK];
+                for (int j = 0; j < K; ++j) sq[j] = __dmul_rn(k.shift[j], k.shift[j]);
+                if (np_pairwise_sum(sq, K) <= tol) stop = 2;
+            }
+            s_int[0] = stop;
+        }
+        __syncthreads();
+        const int stop = s_int[0];
+        if (stop == 1) {
+            strict = true;
+            break;
+        }
+        if (stop == 2) break;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) k.labels_old[i] = k.labels[i];
+        __syncthreads();
+    }
+    if (!strict) elkan_e_step(k, C);
+    // _inertia_dense: sequential over samples
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        k.dist[i] = sqdist(k.Xc + (long long)i * F, C + (long long)k.labels[i] * F, F);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double inertia = 0.0;
+        for (int i = 0; i < n; ++i) inertia = __dadd_rn(inertia, k.dist[i]);
+        s_scalar[1] = inertia;
+    }
+    __syncthreads();
+    *out_C = C;
+}
+
+__device__ void kmeans_fit_predict(KM &k, double *s_scalar, int *s_int, int *out_labels,
+                                   double *out_inertia) {
+    const int n = k.n, F = k.F, K = k.K;
+    // tolerance on the un-centred data, mean, centring, squared norms
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s = __dadd_rn(s, k.X0[(long long)i * F + f]);
+        const double m = s / (double)n;
+        double v = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double d = __dsub_rn(k.X0[(long long)i * F + f], m);
+            v = __dadd_rn(v, __dmul_rn(d, d));
+            k.Xc[(long long)i * F + f] = d;
+        }
+        k.mean[f] = m;
+        k.tmpF[f] = v / (double)n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_scalar[2] = __dmul_rn(np_pairwise_sum(k.tmpF, F) / (double)F, 1e-4);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        k.xx[i] = dot_seq(k.Xc + (long long)i * F, k.Xc + (long long)i * F, F);
+    __syncthreads();
+    const double tol = s_scalar[2];
+    int rand_pos = 0;
+    bool have_best = false;
+    double best_inertia = 0.0;
+    for (int init = 0; init < KM_NINIT; ++init) {
+        const double *C = nullptr;
+        kmeans_single(k, rand_pos, tol, s_scalar, s_int, &C);
+        const double inertia = s_scalar[1];
+        if (threadIdx.x == 0) {
+            int take = 0;
+            if (!have_best) take = 1;
+            else if (inertia < best_inertia) {
+                // _is_same_clustering(labels, best_labels, K)
+                int mapping[KM_MAXK];
+                for (int j = 0; j < KM_MAXK; ++j) mapping[j] = -1;
+                bool same = true;
+                for (int i = 0; i < n && same; ++i) {
+                    const int a = k.labels[i], b = k.best_labels[i];
+                    if (mapping[a] == -1) mapping[a] = b;
+                    else if (mapping[a] != b) same = false;
+                }
+                take = same ? 0 : 1;
+            }
+            s_int[0] = take;
+        }
+        __syncthreads();
+        if (s_int[0]) {
+            have_best = true;
+            best_inertia = inertia;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) k.best_labels[i] = k.labels[i];
+            for (long long p = threadIdx.x; p < (long long)K * F; p += blockDim.x) k.best_c[p] = C[p];
+        }
+        __syncthreads();
+    }
+    // predict on the un-centred data: argmin_j |c_j|^2 - 2 x.c_j  (lloyd _update_chunk_dense)
+    for (long long p = threadIdx.x; p < (long long)K * F; p += blockDim.x)
+        k.best_c[p] = __dadd_rn(k.best_c[p], k.mean[p % F]);
+    __syncthreads();
+    for (int j = threadIdx.x; j < K; j += blockDim.x)
+        k.cc[j] = dot_seq(k.best_c + (long long)j * F, k.best_c + (long long)j * F, F);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double *x = k.X0 + (long long)i * F;
+        int lab = 0;
+        double best = 0.0;
+        for (int j = 0; j < K; ++j) {
+            const double v = __dadd_rn(k.cc[j], __dmul_rn(-2.0, dot_seq(x, k.best_c + (long long)j * F, F)));
+            if (j == 0 || v < best) {
+                best = v;
+                lab = j;
+            }
+        }
+        out_labels[i] = lab;
+    }
+    if (threadIdx.x == 0 && out_inertia) *out_inertia = best_inertia;
+    __syncthreads();
+}
+
+__device__ void km_bind(KM &k, int n, int F, int K, const double *X0, double *d, int *ii) {
+    k.n = n; k.F = F; k.K = K; k.X0 = X0;
+    const long long nF = (long long)n * F;
+    k.Xc = d; d += nF;
+    k.mean = d; d += F;
+    k.tmpF = d; d += F;
+    k.xx = d; d += n;
+    k.ca = d; d += (long long)KM_MAXK * F;
+    k.cb = d; d += (long long)KM_MAXK * F;
+    k.best_c = d; d += (long long)KM_MAXK * F;
+    k.lb = d; d += (long long)n * KM_MAXK;
+    k.ub = d; d += n;
+    k.closest = d; d += n;
+    k.cum = d; d += n;
+    k.D = d; d += 4LL * n;
+    k.dist = d; d += n;
+    k.half = d; d += KM_MAXK * KM_MAXK;
+    k.nxt = d; d += KM_MAXK;
+    k.shift = d; d += KM_MAXK;
+    k.wts = d; d += KM_MAXK;
+    k.cc = d; d += KM_MAXK;
+    k.labels = ii; ii += n;
+    k.labels_old = ii; ii += n;
+    k.best_labels = ii; ii += n;
+}
+
+// one CTA per clustering problem of the level; runs only where refcheck_kernel asked for it
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_kernel(ClusterState *__restrict__ states, const double *__restrict__ X_all,
+              double *__restrict__ dscratch, int *__restrict__ iscratch, int *__restrict__ assign_all,
+              int *__restrict__ newlab_all) {
+    __shared__ double s_scalar[4];
+    __shared__ int s_int[8];
+    ClusterState &st = states[blockIdx.x];
+    if (st.status != 0 || !st.run_kmeans) return;
+    KM k;
+    km_bind(k, st.n, st.F, st.K, X_all + st.x_off, dscratch + st.kmd_off, iscratch + st.kmi_off);
+    int *newlab = newlab_all + st.assign_off;
+    int *assign = assign_all + st.assign_off;
+    kmeans_fit_predict(k, s_scalar, s_int, newlab, nullptr);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // cluster_sequences.py:267-274: fewer distinct labels than K => keep the previous assignment
+        unsigned seen = 0;
+        for (int i = 0; i < st.n; ++i) seen |= 1u << newlab[i];
+        const int distinct = __popc(seen);
+        if (distinct < st.K) {
+            st.K -= 1;
+            st.status = 1;
+        } else {
+            for (int i = 0; i < st.n; ++i) assign[i] = newlab[i];
+        }
+        st.run_kmeans = 0;
+    }
+}
+
+// stand-alone problem (mprg_kmeans)
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_single_problem_kernel(const double *X0, int n, int F, int K, double *dscratch, int *iscratch,
+                             int *labels, double *inertia) {
+    __shared__ double s_scalar[4];
+    __shared__ int s_int[8];
+    KM k;
+    km_bind(k, n, F, K, X0, dscratch, iscratch);
+    kmeans_fit_predict(k, s_scalar, s_int, labels, inertia);
+}
+
+long long kmeans_dscratch_doubles(long long n, long long F) {
+    return n * F + 2 * F + n + 3LL * KM_MAXK * F + n * KM_MAXK + 3 * n + 4 * n + n + KM_MAXK * KM_MAXK +
+           4 * KM_MAXK + 16;
+}
+long long kmeans_iscratch_ints(long long n) { return 3 * n + 8; }
+
+cudaError_t kmeans_upload_rand(const double *h_rand) {
+    return cudaMemcpyToSymbol(c_rand, h_rand, sizeof(double) * KM_RAND_COUNT);
+}
+
+cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, const double *X,
+                          double *dscratch, int *iscratch, int *assign, int *newlab) {
+    if (n_probs <= 0) return cudaSuccess;
+    kmeans_kernel<<<n_probs, KM_THREADS, 0, s>>>(states, X, dscratch, iscratch, assign, newlab);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kmeans_single(cudaStream_t s, const double *X0, int n, int F, int K, double *dscratch,
+                                 int *iscratch, int *labels, double *inertia) {
+    kmeans_single_problem_kernel<<<1, KM_THREADS, 0, s>>>(X0, n, F, K, dscratch, iscratch, labels, inertia);
+    return cudaGetLastError();
+}
+
+}  // namespace mprg

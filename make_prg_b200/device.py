@@ -161,6 +161,132 @@ class Context:
                                                       C.byref(cnt)))
         return iv[:cnt.value].copy()
 
+    # ---- clustering ----------------------------------------------------------------------------
+    def _row_offsets(self, arr):
+        offs = np.zeros(len(arr), np.int64)
+        if len(arr):
+            offs[1:] = np.cumsum(arr["n_rows"].astype(np.int64))[:-1]
+        return offs, int(arr["n_rows"].astype(np.int64).sum())
+
+    def dedupe_rows(self, batch, tasks):
+        """-> per task (group int32[], ungapped_len int32[], n_unique_ungapped, n_unique_gapped)."""
+        arr, arena = self.make_tasks(batch, tasks)
+        offs, total = self._row_offsets(arr)
+        group = np.zeros(max(total, 1), np.int32)
+        ulen = np.zeros(max(total, 1), np.int32)
+        nu = np.zeros(max(len(arr), 1), np.int32)
+        ng = np.zeros(max(len(arr), 1), np.int32)
+        self._check(self.lib.mprg_dedupe_rows(self.handle, batch.handle, ptr(arr), len(arr),
+                                              ptr(arena) if arena.size else None, arena.size,
+                                              ptr(offs), ptr(group), ptr(ulen), ptr(nu), ptr(ng)))
+        return [(group[o:o + n].copy(), ulen[o:o + n].copy(), int(nu[i]), int(ng[i]))
+                for i, (o, n) in enumerate(zip(offs, arr["n_rows"]))]
+
+    def kmer_counts(self, batch, task, kmer_size):
+        """-> float64[n_distinct_long, n_kmers] (kernel (b))."""
+        arr, arena = self.make_tasks(batch, [task])
+        n, F = C.c_int32(0), C.c_int32(0)
+        rows = ptr(arena) if arena.size else None
+        self._check(self.lib.mprg_kmer_counts(self.handle, batch.handle, ptr(arr), rows, kmer_size,
+                                              C.byref(n), C.byref(F), None, 0))
+        X = np.zeros((n.value, F.value), np.float64)
+        if X.size:
+            self._check(self.lib.mprg_kmer_counts(self.handle, batch.handle, ptr(arr), rows, kmer_size,
+                                                  C.byref(n), C.byref(F), ptr(X), X.size))
+        return X
+
+    def kmeans(self, X, K):
+        """KMeans(K, random_state=2, elkan, n_init=10).fit(X).predict(X) -> (labels, inertia)."""
+        X = np.ascontiguousarray(X, np.float64)
+        labels = np.zeros(X.shape[0], np.int32)
+        inertia = C.c_double(0)
+        self._check(self.lib.mprg_kmeans(self.handle, ptr(X), X.shape[0], X.shape[1], K, ptr(labels),
+                                         C.byref(inertia)))
+        return labels, inertia.value
+
+    def one_ref_like(self, batch, task, cluster_of_row, n_clusters):
+        arr, arena = self.make_tasks(batch, [task])
+        cl = np.ascontiguousarray(cluster_of_row, np.int32)
+        flags = np.zeros(n_clusters, np.int32)
+        self._check(self.lib.mprg_one_ref_like(self.handle, batch.handle, ptr(arr),
+                                               ptr(arena) if arena.size else None, ptr(cl), n_clusters,
+                                               ptr(flags)))
+        return flags.astype(bool)
+
+    def cluster_tasks(self, batch, tasks, kmer_size):
+        """kmeans_cluster_seqs per task -> list of clustered row positions (ClusteringResult order)."""
+        arr, arena = self.make_tasks(batch, tasks)
+        offs, total = self._row_offsets(arr)
+        cluster = np.zeros(max(total, 1), np.int32)
+        ncl = np.zeros(max(len(arr), 1), np.int32)
+        self._check(self.lib.mprg_cluster_tasks(self.handle, batch.handle, ptr(arr), len(arr),
+                                                ptr(arena) if arena.size else None, arena.size,
+                                                kmer_size, ptr(offs), ptr(cluster), ptr(ncl)))
+        out = []
+        for i, (o, n) in enumerate(zip(offs, arr["n_rows"])):
+            c = cluster[o:o + n]
+            out.append([np.nonzero(c == k)[0].tolist() for k in range(int(ncl[i]))])
+        return out
+
+    # ---- the whole path ------------------------------------------------------------------------
+    def build(self, batch, max_nesting, min_match_length):
+        h = C.c_void_p()
+        self._check(self.lib.mprg_build(self.handle, batch.handle, max_nesting, min_match_length,
+                                        C.byref(h)))
+        return BuildResult(self, h)
+
+
+class BuildResult:
+    """Trees and PRG strings of one mprg_build call."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+        self.n_loci = ctx.lib.mprg_result_n_loci(handle)
+
+    def status(self, locus):
+        return int(self.ctx.lib.mprg_result_status(self.handle, locus))
+
+    def prg(self, locus):
+        n = C.c_int64(0)
+        p = self.ctx.lib.mprg_result_prg(self.handle, locus, C.byref(n))
+        return C.string_at(p, n.value).decode() if p and n.value else ""
+
+    def n_nodes(self, locus):
+        return int(self.ctx.lib.mprg_result_n_nodes(self.handle, locus))
+
+    def n_sites(self, locus):
+        return int(self.ctx.lib.mprg_result_n_sites(self.handle, locus))
+
+    def nodes(self, locus):
+        """Pre-order node table: dict of arrays + the locus row pool."""
+        n = self.n_nodes(locus)
+        cols = {k: np.zeros(max(n, 1), np.int32) for k in
+                ("kind", "parent", "nesting_level", "c0", "c1", "n_rows", "n_children")}
+        row_off = np.zeros(max(n, 1), np.int64)
+        lib = self.ctx.lib
+        self.ctx._check(lib.mprg_result_nodes(self.handle, locus, ptr(cols["kind"]), ptr(cols["parent"]),
+                                              ptr(cols["nesting_level"]), ptr(cols["c0"]), ptr(cols["c1"]),
+                                              ptr(cols["n_rows"]), ptr(row_off), ptr(cols["n_children"])))
+        size = int(lib.mprg_result_row_pool_size(self.handle, locus))
+        pool = np.zeros(max(size, 1), np.int32)
+        if size:
+            self.ctx._check(lib.mprg_result_row_pool(self.handle, locus, ptr(pool)))
+        out = {k: v[:n] for k, v in cols.items()}
+        out["row_off"] = row_off[:n]
+        out["row_pool"] = pool[:size]
+        return out
+
+    def free(self):
+        if self.handle is not None:
+            self.ctx.lib.mprg_result_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
 
 _default = {}
 

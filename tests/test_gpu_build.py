@@ -1,0 +1,91 @@
+"""-m gpu parity of the whole path (mprg_build through the C ABI): byte-identical PRG strings and
+identical recursion trees against the reference's golden outputs and reference runs on synthetic MSAs."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import make_prg_oracle as mo
+from helpers import REF, SMALL_CASES, synthetic_cases, truth_multi, truth_prg
+from make_prg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from make_prg_b200 import device
+
+    return device.Context(0)
+
+
+def _build(ctx, mats, N, L):
+    batch = ctx.upload(mats)
+    res = ctx.build(batch, N, L)
+    return batch, res
+
+
+def _tree_dump(res, locus, M):
+    t = res.nodes(locus)
+    names = {0: "LeafNode", 1: "MultiIntervalNode", 2: "MultiClusterNode"}
+    out = []
+    for i in range(len(t["kind"])):
+        rows = (np.arange(M.shape[0]) if t["row_off"][i] < 0
+                else t["row_pool"][t["row_off"][i]:t["row_off"][i] + t["n_rows"][i]])
+        S = M[rows, t["c0"][i]:t["c1"][i]]
+        keep = int((~(S == ord("-")).all(axis=0)).sum())
+        out.append([names[int(t["kind"][i])], i, int(t["nesting_level"][i]), len(rows), keep,
+                    int(t["n_children"][i])])
+    return out
+
+
+def test_small_cases(ctx):
+    for L in sorted(set(SMALL_CASES.values())):
+        names = [c for c, l in SMALL_CASES.items() if l == L]
+        mats = [mo.load_msa(REF / f"{c}.fa")[1] for c in names]
+        _, res = _build(ctx, mats, 5, L)
+        for i, c in enumerate(names):
+            assert res.status(i) == 0
+            assert res.prg(i) == truth_prg(c), c
+
+
+def test_disallowed_base_marks_locus_only(ctx):
+    mats = [mo.load_msa(REF / "match.fa")[1]]
+    ids, bad = mo.parse_fasta((REF / "fails_2.fa").read_text())
+    mats.append(np.frombuffer("".join(bad).upper().encode(), np.uint8).reshape(len(bad), -1))
+    _, res = _build(ctx, mats, 5, 7)
+    assert res.status(0) == 0 and res.prg(0) == truth_prg("match")
+    assert res.status(1) == 1 and res.prg(1) == ""
+
+
+def test_sample_example_and_amira(ctx):
+    for setname, files in (("sample_example", ["GC00006032.fa", "GC00010897.fa"]),
+                           ("amira_MSAs", ["alsB.fasta.gz", "glpG.fasta.gz", "group_18516.fasta.gz"])):
+        mats = [mo.load_msa(REF / setname / f)[1] for f in files]
+        _, res = _build(ctx, mats, 5, 7)
+        truth = truth_multi(setname)
+        for i, f in enumerate(files):
+            name = f.split(".")[0]
+            assert res.prg(i) == truth[name], name
+
+
+def test_synthetic_prg_and_tree(ctx):
+    recs = synthetic_cases()
+    groups = {}
+    for r in recs:
+        groups.setdefault((r["N"], r["L"]), []).append(r)
+    for (N, L), rs in groups.items():
+        mats = [synth.config_msa(r["config"], r["index"], r.get("rows"), r.get("cols")) for r in rs]
+        _, res = _build(ctx, mats, N, L)
+        for i, r in enumerate(rs):
+            assert res.prg(i) == r["prg"], (r["config"], r["index"], N, L)
+            assert res.n_nodes(i) == r["n_nodes"] and res.n_sites(i) == r["n_sites"]
+            assert _tree_dump(res, i, mats[i]) == [list(t) for t in r["tree"]]
+
+
+def test_batch_order_invariance(ctx):
+    mats = [synth.config_msa(2, i) for i in range(4)]
+    _, a = _build(ctx, mats, 5, 7)
+    _, b = _build(ctx, mats[::-1], 5, 7)
+    for i in range(4):
+        assert a.prg(i) == b.prg(3 - i)
