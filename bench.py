@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- `from_msa` hot path on B200: MSA loci/sec with byte-identical-PRG semantics.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): synthetic 1,000-locus set, 200 seqs x 1 kb MSAs, -N 5 -L 7, per
+GPU.  A step = one pass of the whole hot path (level-synchronous scan / partition / clustering /
+KMeans / PRG emission, `mprg_build`) over that batch.
+  value     loci/sec with the packed batch already resident in HBM when the timed region starts
+  e2e       loci/sec through the public API from pinned HOST ASCII buffers: H2D copy + device packing
+            + build + PRG strings back on the host, every step
+  roofline  the dominant kernel (column scan, root level launch): algorithmic bytes / CUDA-event time
+  cpu_baseline  the oracle port (oracle/make_prg_oracle.py) on a bounded sample, 1 core
+`--impl reference` times the reference's CPU algorithm (the oracle port; the Python reference cannot
+travel to the GPU box) with all host cores on a bounded sample per step.
+N > 1: launched by torchrun, one rank per GPU, loci sharded (weak scaling: 1,000 loci per GPU, no
+data-path collective), time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+LOCI_PER_GPU = 1000
+ROWS, COLS = 200, 1000
+MAX_NESTING, MIN_MATCH = 5, 7
+CACHE = Path(os.environ.get("MPRG_BENCH_CACHE", "/tmp/mprg_bench_cache"))
+
+
+def workload(rank, n_loci=LOCI_PER_GPU):
+    """Config #2 loci [rank*n_loci, (rank+1)*n_loci) as one uint8[n_loci, ROWS, COLS] array (cached)."""
+    from make_prg_b200 import synth
+
+    CACHE.mkdir(parents=True, exist_ok=True)
+    f = CACHE / f"config2_{rank}_{n_loci}.npy"
+    if f.exists():
+        return np.load(f)
+    out = np.empty((n_loci, ROWS, COLS), np.uint8)
+    for i in range(n_loci):
+        out[i] = synth.config_msa(2, rank * n_loci + i)
+    tmp = f.with_suffix(f".{os.getpid()}.tmp.npy")
+    np.save(tmp, out)
+    os.replace(tmp, f)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def hbm_peak():
+    f = REPO / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def oracle_loci_per_sec(mats, n_workers):
+    """Times the oracle port (CPU restatement of the reference algorithm) on `mats`."""
+    sys.path.insert(0, str(REPO / "oracle"))
+    t0 = time.perf_counter()
+    if n_workers <= 1:
+        import make_prg_oracle as mo
+
+        for M in mats:
+            mo.build_prg_from_matrix([f"s{i}" for i in range(M.shape[0])], M, MAX_NESTING, MIN_MATCH)
+    else:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(n_workers) as pool:
+            pool.map(_oracle_one, list(mats), chunksize=1)
+    dt = time.perf_counter() - t0
+    return len(mats) / dt, dt
+
+
+def _oracle_one(M):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    sys.path.insert(0, str(REPO / "oracle"))
+    import make_prg_oracle as mo
+
+    mo.build_prg_from_matrix([f"s{i}" for i in range(M.shape[0])], M, MAX_NESTING, MIN_MATCH)
+    return 0
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = max(cores * 2, 8)
+    data = workload(0)[:sample]
+    mats = [data[i] for i in range(sample)]
+    for _ in range(args.warmup):
+        oracle_loci_per_sec(mats[:cores], cores)
+    t_total = 0.0
+    for _ in range(args.steps):
+        _, dt = oracle_loci_per_sec(mats, cores)
+        t_total += dt
+    value = sample * args.steps / t_total
+    line = {
+        "impl": "reference", "metric": "MSA loci/sec (from_msa, byte-identical PRG)", "value": value,
+        "unit": "loci/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": config_dict(sample_note=f"{sample} loci per step"),
+        "cpu_baseline": {"value": value, "unit": "loci/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} loci of the workload per step, multiprocessing over loci"},
+        "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(sample_note=None):
+    c = {"workload": "BASELINE configs[1]: synthetic 1,000-locus set, 200 seqs x 1 kb MSAs, -N 5 -L 7, "
+                     "per GPU (make_prg_b200.synth seeds 1000+i)",
+         "loci_per_gpu": LOCI_PER_GPU, "rows": ROWS, "cols": COLS, "max_nesting": MAX_NESTING,
+         "min_match_length": MIN_MATCH,
+         "l2": "L2 flushed between steps by writing a 256 MiB device buffer (packed batch is 100 MB < L2)"}
+    if sample_note:
+        c["sample"] = sample_note
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--loci", type=int, default=LOCI_PER_GPU)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from make_prg_b200 import device
+
+    ctx = device.Context(local_rank)
+    n_loci = args.loci
+    data = workload(rank, n_loci)
+    shapes = [(ROWS, COLS)] * n_loci
+    host = torch.from_numpy(data.reshape(-1)).pin_memory()  # pinned host ASCII
+    host_np = host.numpy()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(batch):
+        res = ctx.build(batch, MAX_NESTING, MIN_MATCH)
+        n_ok = sum(1 for i in range(n_loci) if res.status(i) == 0)
+        total_len = sum(len(res.prg(i)) for i in range(0, n_loci, 97))
+        res.free()
+        return n_ok, total_len
+
+    def step_e2e():
+        batch = ctx.upload((host_np, shapes))
+        out = step_resident(batch)
+        batch.free()
+        return out
+
+    # ---- kernel-side number: batch resident in HBM ----
+    batch = ctx.upload((host_np, shapes))
+    for _ in range(args.warmup):
+        step_resident(batch)
+        flush.zero_()
+    barrier()
+    ctx.scan_log(reset=True)
+    launches0 = ctx.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        t_dev = 0.0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.timer_start()
+            n_ok, _ = step_resident(batch)
+            t_dev += ctx.timer_stop()
+            flush.zero_()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    barrier()
+    launches = ctx.launch_count() - launches0
+    log_bytes, log_ms = ctx.scan_log(reset=True)
+    batch.free()
+
+    # ---- end to end: host buffers in, PRG strings out ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ctx.copy_stats(reset=True)
+    t_e2e = 0.0
+    for _ in range(args.steps):
+        ctx.timer_start()
+        step_e2e()
+        t_e2e += ctx.timer_stop()
+        flush.zero_()
+    barrier()
+    copies = ctx.copy_stats(reset=True)
+
+    t_dev_s, t_e2e_s = t_dev / 1e3, t_e2e / 1e3
+    if dist is not None:
+        tt = torch.tensor([t_dev_s, t_e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev_s, t_e2e_s = float(tt[0]), float(tt[1])
+        ok = torch.tensor([n_ok], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ok)
+        n_ok_total = int(ok[0])
+    else:
+        n_ok_total = n_ok
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    total_loci = n_loci * world
+    value = total_loci * args.steps / t_dev_s
+    e2e_value = total_loci * args.steps / t_e2e_s
+    # roofline of the dominant launch: the root-level scan (largest algorithmic byte count per step)
+    peak, peak_src = hbm_peak()
+    roof = None
+    if len(log_bytes):
+        top = log_bytes >= 0.5 * log_bytes.max()
+        achieved = float(log_bytes[top].sum() / (log_ms[top].sum() * 1e-3) / 1e9)
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "scan_kernel<false> (root level launch)",
+                "bytes_per_launch": float(log_bytes[top].mean()), "ms_per_launch": float(log_ms[top].mean()),
+                "peak_source": peak_src,
+                "all_scan_launches": {"per_step": len(log_bytes) / args.steps,
+                                      "achieved_gbs": float(log_bytes.sum() / (log_ms.sum() * 1e-3) / 1e9)}}
+    # CPU baseline: oracle port, 1 core, bounded sample
+    sample = 100
+    cpu_v, cpu_dt = oracle_loci_per_sec([data[i] for i in range(sample)], 1)
+    line = {
+        "metric": "MSA loci/sec (from_msa, byte-identical PRG)", "value": value, "unit": "loci/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_dict(),
+        "columns_per_sec": value * COLS, "loci_ok": n_ok_total,
+        "e2e": {"value": e2e_value, "unit": "loci/s",
+                "h2d_bytes_per_step": copies["h2d_bytes"] // args.steps,
+                "d2h_bytes_per_step": copies["d2h_bytes"] // args.steps,
+                "ms_per_step": 1e3 * t_e2e_s / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "cpu_baseline": {"value": cpu_v, "unit": "loci/s", "cores": 1, "kind": "port",
+                         "sample": f"first {sample} loci of the workload, oracle/make_prg_oracle.py, "
+                                   f"{cpu_dt:.1f} s"},
+        "clocks": clocks.summary(),
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -80,6 +80,14 @@ int64_t mprg_launch_count(const mprg_ctx *ctx);
  * kernel accumulated since the last reset; used by bench.py for the roofline object */
 int mprg_scan_stats(mprg_ctx *ctx, double *ms, double *bytes, int64_t *launches, int reset);
 
+/* host<->device bytes copied by this context since the last reset (bench.py's e2e object) */
+int mprg_copy_stats(mprg_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes, int reset);
+/* CUDA-event stopwatch on the context's stream: op 0 records the start, op 1 records the stop,
+ * waits for it and returns the elapsed device time in ms */
+int mprg_timer(mprg_ctx *ctx, int op, double *ms);
+/* per-launch log of the column-scan kernel (algorithmic bytes, device ms), newest last */
+int mprg_scan_log(mprg_ctx *ctx, double *bytes, double *ms, int32_t capacity, int32_t *n, int reset);
+
 /* ---- loader -> HBM (replaces the in-memory Biopython MSA of io_utils.py:17-49) --------------- */
 /* h_ascii: concatenated row-major ASCII matrices (upper or lower case, N already replaced by the
  * host loader); locus i occupies n_rows[i]*n_cols[i] bytes starting at h_offsets[i].

@@ -8,15 +8,6 @@
 
 using namespace mprg;
 
-static void account_scan(mprg_ctx *ctx, const Level &lv) {
-    float ms = 0;
-    if (!lv.units.empty() && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) {
-        ctx->scan_ms += ms;
-        ctx->scan_bytes += lv.algo_bytes;
-        ctx->scan_launches += 1;
-    }
-}
-
 extern "C" int mprg_scan_tasks(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks,
                                int32_t n_tasks, const int32_t *h_rows, int64_t n_row_entries,
                                const int64_t *h_col_offsets, uint8_t *h_consensus,
@@ -29,9 +20,8 @@ extern "C" int mprg_scan_tasks(mprg_ctx *ctx, const mprg_batch *batch, const mpr
     if (n_tasks == 0) return MPRG_OK;
     std::vector<uint8_t> cls((size_t)lv.total_cols);
     std::vector<int> reach((size_t)lv.total_cols);
-    MPRG_CUDA(ctx, cudaMemcpyAsync(cls.data(), ctx->d_cls.p, cls.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(reach.data(), ctx->d_reach.p, sizeof(int) * reach.size(),
-                                   cudaMemcpyDeviceToHost, ctx->stream));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, cls.data(), ctx->d_cls.p, cls.size(), ctx->stream));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, reach.data(), ctx->d_reach.p, sizeof(int) * reach.size(), ctx->stream));
     MPRG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     account_scan(ctx, lv);
     for (int i = 0; i < n_tasks; ++i) {
@@ -57,10 +47,8 @@ extern "C" int mprg_partition_tasks(mprg_ctx *ctx, const mprg_batch *batch, cons
     if (n_tasks == 0) return MPRG_OK;
     std::vector<DInterval> iv((size_t)lv.total_iv);
     std::vector<int> cnt(n_tasks + 1);
-    MPRG_CUDA(ctx, cudaMemcpyAsync(iv.data(), ctx->d_iv.p, sizeof(DInterval) * iv.size(),
-                                   cudaMemcpyDeviceToHost, ctx->stream));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(cnt.data(), ctx->d_ivcnt.p, sizeof(int) * cnt.size(),
-                                   cudaMemcpyDeviceToHost, ctx->stream));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, iv.data(), ctx->d_iv.p, sizeof(DInterval) * iv.size(), ctx->stream));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, cnt.data(), ctx->d_ivcnt.p, sizeof(int) * cnt.size(), ctx->stream));
     MPRG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     account_scan(ctx, lv);
     if (cnt[n_tasks]) MPRG_FAIL(ctx, MPRG_E_PARTITION, "Failed interval partitioning");
@@ -89,9 +77,9 @@ extern "C" int mprg_partition_consensus(mprg_ctx *ctx, const uint8_t *h_consensu
     MPRG_CUDA(ctx, ctx->d_misc.reserve(sizeof(uint32_t) * (n / 32 + 2)));
     MPRG_CUDA(ctx, ctx->d_iv.reserve(sizeof(DInterval) * ivcap));
     MPRG_CUDA(ctx, ctx->d_ivcnt.reserve(sizeof(int) * 2));
-    if (n) MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_cls.p, h_consensus, n, cudaMemcpyHostToDevice, s));
+    if (n) MPRG_CUDA(ctx, mprg::copy_h2d(ctx, ctx->d_cls.p, h_consensus, n, s));
     if (n && h_gap_reach)
-        MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_reach.p, h_gap_reach, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, ctx->d_reach.p, h_gap_reach, sizeof(int) * n, s));
     MPRG_CUDA(ctx, cudaMemsetAsync(ctx->d_ivcnt.p, 0, sizeof(int) * 2, s));
     int *cnt = ctx->d_ivcnt.as<int>();
     MPRG_CUDA(ctx, launch_partition_consensus(s, ctx->d_cls.as<uint8_t>(),
@@ -101,12 +89,52 @@ extern "C" int mprg_partition_consensus(mprg_ctx *ctx, const uint8_t *h_consensu
     ctx->launches++;
     int hc[2] = {0, 0};
     std::vector<DInterval> iv(ivcap);
-    MPRG_CUDA(ctx, cudaMemcpyAsync(hc, cnt, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(iv.data(), ctx->d_iv.p, sizeof(DInterval) * ivcap, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, hc, cnt, sizeof(int) * 2, s));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, iv.data(), ctx->d_iv.p, sizeof(DInterval) * ivcap, s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
     if (hc[1]) MPRG_FAIL(ctx, MPRG_E_PARTITION, "Failed interval partitioning");
     if (hc[0] > capacity) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "interval capacity too small");
     *h_count = hc[0];
     for (int k = 0; k < hc[0]; ++k) h_intervals[k] = mprg_interval{iv[k].start, iv[k].stop, iv[k].type};
+    return MPRG_OK;
+}
+
+extern "C" int mprg_copy_stats(mprg_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes, int reset) {
+    if (!ctx) return MPRG_E_BAD_ARG;
+    if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+    if (reset) ctx->h2d_bytes = ctx->d2h_bytes = 0;
+    return MPRG_OK;
+}
+
+extern "C" int mprg_timer(mprg_ctx *ctx, int op, double *ms) {
+    if (!ctx) return MPRG_E_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    if (op == 0) {
+        MPRG_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    } else {
+        MPRG_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+        MPRG_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
+        float f = 0;
+        MPRG_CUDA(ctx, cudaEventElapsedTime(&f, ctx->ev_t0, ctx->ev_t1));
+        if (ms) *ms = f;
+    }
+    return MPRG_OK;
+}
+
+extern "C" int mprg_scan_log(mprg_ctx *ctx, double *bytes, double *ms, int32_t capacity, int32_t *n,
+                             int reset) {
+    if (!ctx || !n) return MPRG_E_BAD_ARG;
+    const int have = (int)ctx->scan_log_bytes.size();
+    const int take = have < capacity ? have : capacity;
+    for (int i = 0; i < take; ++i) {
+        if (bytes) bytes[i] = ctx->scan_log_bytes[have - take + i];
+        if (ms) ms[i] = ctx->scan_log_ms[have - take + i];
+    }
+    *n = take;
+    if (reset) {
+        ctx->scan_log_bytes.clear();
+        ctx->scan_log_ms.clear();
+    }
     return MPRG_OK;
 }

@@ -84,7 +84,8 @@ extern "C" int mprg_create(int device_ordinal, mprg_ctx **out) {
     ctx->cc_major = prop.major;
     ctx->cc_minor = prop.minor;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_t0) != cudaSuccess || cudaEventCreate(&ctx->ev_t1) != cudaSuccess) {
         delete ctx;
         return MPRG_E_CUDA;
     }
@@ -114,6 +115,8 @@ extern "C" void mprg_destroy(mprg_ctx *ctx) {
     ctx->h_d.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -201,23 +204,21 @@ extern "C" int mprg_batch_upload(mprg_ctx *ctx, const uint8_t *h_ascii, const in
         bool contiguous = true;
         for (int l = 0; l < n_loci; ++l) contiguous &= (h_offsets[l] == h_offsets[0] + aoff[l]);
         if (contiguous) {
-            if ((e = cudaMemcpyAsync(d + o_ascii, h_ascii + h_offsets[0], (size_t)ascii_total,
-                                     cudaMemcpyHostToDevice, s)) != cudaSuccess)
+            if ((e = mprg::copy_h2d(ctx, d + o_ascii, h_ascii + h_offsets[0], (size_t)ascii_total, s)) != cudaSuccess)
                 return fail(e, "H2D ascii");
         } else {
             for (int l = 0; l < n_loci; ++l) {
                 const size_t nbytes = (size_t)n_rows[l] * n_cols[l];
                 if (!nbytes) continue;
-                if ((e = cudaMemcpyAsync(d + o_ascii + aoff[l], h_ascii + h_offsets[l], nbytes,
-                                         cudaMemcpyHostToDevice, s)) != cudaSuccess)
+                if ((e = mprg::copy_h2d(ctx, d + o_ascii + aoff[l], h_ascii + h_offsets[l], nbytes, s)) != cudaSuccess)
                     return fail(e, "H2D ascii");
             }
         }
-        cudaMemcpyAsync(d + o_aoff, aoff.data(), sizeof(long long) * n_loci, cudaMemcpyHostToDevice, s);
-        cudaMemcpyAsync(d + o_rp, row_prefix.data(), sizeof(long long) * (n_loci + 1), cudaMemcpyHostToDevice, s);
-        cudaMemcpyAsync(d + o_base, b->base.data(), sizeof(long long) * n_loci, cudaMemcpyHostToDevice, s);
-        cudaMemcpyAsync(d + o_nc, b->n_cols.data(), sizeof(int) * n_loci, cudaMemcpyHostToDevice, s);
-        cudaMemcpyAsync(d + o_st, b->stride.data(), sizeof(int) * n_loci, cudaMemcpyHostToDevice, s);
+        mprg::copy_h2d(ctx, d + o_aoff, aoff.data(), sizeof(long long) * n_loci, s);
+        mprg::copy_h2d(ctx, d + o_rp, row_prefix.data(), sizeof(long long) * (n_loci + 1), s);
+        mprg::copy_h2d(ctx, d + o_base, b->base.data(), sizeof(long long) * n_loci, s);
+        mprg::copy_h2d(ctx, d + o_nc, b->n_cols.data(), sizeof(int) * n_loci, s);
+        mprg::copy_h2d(ctx, d + o_st, b->stride.data(), sizeof(int) * n_loci, s);
         cudaMemsetAsync(d + o_fl, 0, sizeof(int) * n_loci, s);
         const int warps_per_block = 8;
         const long long blocks = (total_rows + warps_per_block - 1) / warps_per_block;
@@ -227,8 +228,7 @@ extern "C" int mprg_batch_upload(mprg_ctx *ctx, const uint8_t *h_ascii, const in
             total_rows, b->d_packed, (int *)(d + o_fl));
         ctx->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "pack_rows_kernel");
-        if ((e = cudaMemcpyAsync(b->flags.data(), d + o_fl, sizeof(int) * n_loci,
-                                 cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+        if ((e = mprg::copy_d2h(ctx, b->flags.data(), d + o_fl, sizeof(int) * n_loci, s)) != cudaSuccess)
             return fail(e, "D2H flags");
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, "sync upload");
     }
@@ -259,8 +259,7 @@ extern "C" int mprg_batch_download_packed(mprg_ctx *ctx, const mprg_batch *batch
     if (!h_out) return MPRG_OK;
     if (capacity < nbytes) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "download buffer too small");
     if (nbytes) {
-        MPRG_CUDA(ctx, cudaMemcpyAsync(h_out, batch->d_packed + batch->base[locus], (size_t)nbytes,
-                                       cudaMemcpyDeviceToHost, ctx->stream));
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_out, batch->d_packed + batch->base[locus], (size_t)nbytes, ctx->stream));
         MPRG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return MPRG_OK;

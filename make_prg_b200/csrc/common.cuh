@@ -110,6 +110,10 @@ struct mprg_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     long long launches = 0;
+    long long h2d_bytes = 0, d2h_bytes = 0;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // mprg_timer
+    // per-launch log of the scan kernel (algorithmic bytes, device ms), newest last
+    std::vector<double> scan_log_bytes, scan_log_ms;
     // scan-kernel accounting for the roofline object
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double scan_ms = 0, scan_bytes = 0;
@@ -122,6 +126,17 @@ struct mprg_ctx {
     // scratch (pinned host)
     mprg::PinnedBuf h_a, h_b, h_c, h_d;
 };
+
+namespace mprg {
+inline cudaError_t copy_h2d(mprg_ctx *c, void *dst, const void *src, size_t n, cudaStream_t st) {
+    c->h2d_bytes += (long long)n;
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st);
+}
+inline cudaError_t copy_d2h(mprg_ctx *c, void *dst, const void *src, size_t n, cudaStream_t st) {
+    c->d2h_bytes += (long long)n;
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st);
+}
+}  // namespace mprg
 
 #define MPRG_CUDA(ctx, call)                                                                   \
     do {                                                                                       \

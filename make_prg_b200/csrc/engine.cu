@@ -162,11 +162,11 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
     const long long n_int = 4 * row_total + 2LL * n_tasks + 1;
     MPRG_CUDA(ctx, B[5].reserve(sizeof(int) * n_int));
     MPRG_CUDA(ctx, ctx->d_rows.reserve(sizeof(int) * std::max<long long>(n_row_entries, 1)));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(B[0].p, tasks.data(), sizeof(DTask) * n_tasks, cudaMemcpyHostToDevice, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(B[1].p, g_off.data(), sizeof(long long) * n_tasks, cudaMemcpyHostToDevice, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(B[2].p, row_off.data(), sizeof(long long) * n_tasks, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[0].p, tasks.data(), sizeof(DTask) * n_tasks, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[1].p, g_off.data(), sizeof(long long) * n_tasks, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[2].p, row_off.data(), sizeof(long long) * n_tasks, s));
     if (n_row_entries > 0)
-        MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_rows.p, h_rows, sizeof(int) * n_row_entries, cudaMemcpyHostToDevice, s));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, ctx->d_rows.p, h_rows, sizeof(int) * n_row_entries, s));
     int *d_leader_u = B[5].as<int>();
     int *d_leader_g = d_leader_u + row_total;
     int *d_group = d_leader_g + row_total;
@@ -183,7 +183,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
     ctx->launches += 2;
     std::vector<int> h_ints((size_t)(2 * row_total + 2LL * n_tasks + 1));
     // group|ulen|nu|ng|err are contiguous
-    MPRG_CUDA(ctx, cudaMemcpyAsync(h_ints.data(), d_group, sizeof(int) * h_ints.size(), cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_ints.data(), d_group, sizeof(int) * h_ints.size(), s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
     const int *h_group = h_ints.data();
     const int *h_ulen = h_group + row_total;
@@ -305,8 +305,8 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
     MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * tab_total));
     MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * x_total));
     MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * np + 64));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(B[6].p, kp.data(), sizeof(KmerProb) * np, cudaMemcpyHostToDevice, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(B[7].p, seq_rows.data(), sizeof(int) * seq_rows.size(), cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[6].p, kp.data(), sizeof(KmerProb) * np, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[7].p, seq_rows.data(), sizeof(int) * seq_rows.size(), s));
     ClusterState *d_states = B[13].as<ClusterState>();
     int *d_F = reinterpret_cast<int *>(d_states + np);
     MPRG_CUDA(ctx, launch_kmer(s, B[6].p, np, B[7].as<int>(), B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
@@ -314,8 +314,8 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
                                d_err));
     ctx->launches++;
     std::vector<int> h_F(np + 1);
-    MPRG_CUDA(ctx, cudaMemcpyAsync(h_F.data(), d_F, sizeof(int) * np, cudaMemcpyDeviceToHost, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(&h_F[np], d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_F.data(), d_F, sizeof(int) * np, s));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &h_F[np], d_err, sizeof(int), s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
     if (h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
 
@@ -343,9 +343,9 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
     uint8_t *d_maj = b14 + o_maj;
     double *d_kmd = B[15].as<double>();
     int *d_kmi = reinterpret_cast<int *>(d_kmd + kmd_total);
-    MPRG_CUDA(ctx, cudaMemcpyAsync(d_states, st.data(), sizeof(ClusterState) * np, cudaMemcpyHostToDevice, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(d_memoff, mem_off.data(), sizeof(int) * mem_off.size(), cudaMemcpyHostToDevice, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(d_memrows, mem_rows.data(), sizeof(int) * mem_rows.size(), cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_states, st.data(), sizeof(ClusterState) * np, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_memoff, mem_off.data(), sizeof(int) * mem_off.size(), s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_memrows, mem_rows.data(), sizeof(int) * mem_rows.size(), s));
     MPRG_CUDA(ctx, cudaMemsetAsync(d_assign, 0, sizeof(int) * assign_total, s));
     const int MAX_CLUSTERS = 10;
     MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
@@ -356,8 +356,8 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         ctx->launches += 2;
     }
     std::vector<int> h_assign((size_t)assign_total);
-    MPRG_CUDA(ctx, cudaMemcpyAsync(st.data(), d_states, sizeof(ClusterState) * np, cudaMemcpyDeviceToHost, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(h_assign.data(), d_assign, sizeof(int) * assign_total, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, st.data(), d_states, sizeof(ClusterState) * np, s));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_assign.data(), d_assign, sizeof(int) * assign_total, s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
 
     for (int q = 0; q < np; ++q) {
@@ -451,12 +451,12 @@ extern "C" int mprg_kmeans(mprg_ctx *ctx, const double *h_X, int32_t n, int32_t 
     double *d_inertia = d_d + nd;
     int *d_i = reinterpret_cast<int *>(d_inertia + 1);
     int *d_labels = d_i + ni;
-    MPRG_CUDA(ctx, cudaMemcpyAsync(B[12].p, h_X, sizeof(double) * (size_t)n * F, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[12].p, h_X, sizeof(double) * (size_t)n * F, s));
     MPRG_CUDA(ctx, launch_kmeans_single(s, B[12].as<double>(), n, F, K, d_d, d_i, d_labels, d_inertia));
     ctx->launches++;
-    MPRG_CUDA(ctx, cudaMemcpyAsync(h_labels, d_labels, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_labels, d_labels, sizeof(int) * n, s));
     double inertia = 0;
-    MPRG_CUDA(ctx, cudaMemcpyAsync(&inertia, d_inertia, sizeof(double), cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &inertia, d_inertia, sizeof(double), s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
     if (h_inertia) *h_inertia = inertia;
     return MPRG_OK;
@@ -513,20 +513,20 @@ extern "C" int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mp
     MPRG_CUDA(ctx, B[13].reserve(sizeof(int) * 2));
     int *d_F = B[13].as<int>();
     MPRG_CUDA(ctx, cudaMemsetAsync(d_F, 0, sizeof(int) * 2, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(B[6].p, &k, sizeof(k), cudaMemcpyHostToDevice, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(B[7].p, leaders.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[6].p, &k, sizeof(k), s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[7].p, leaders.data(), sizeof(int) * n, s));
     MPRG_CUDA(ctx, launch_kmer(s, B[6].p, 1, B[7].as<int>(), B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
                                B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), B[12].as<double>(), d_F,
                                d_F + 1));
     ctx->launches++;
     int hF[2] = {0, 0};
-    MPRG_CUDA(ctx, cudaMemcpyAsync(hF, d_F, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, hF, d_F, sizeof(int) * 2, s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
     if (hF[1]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
     *n_kmers = hF[0];
     if (h_counts) {
         if (capacity < (int64_t)n * hF[0]) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "count matrix capacity too small");
-        MPRG_CUDA(ctx, cudaMemcpyAsync(h_counts, B[12].p, sizeof(double) * (size_t)n * hF[0], cudaMemcpyDeviceToHost, s));
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_counts, B[12].p, sizeof(double) * (size_t)n * hF[0], s));
         MPRG_CUDA(ctx, cudaStreamSynchronize(s));
     }
     return MPRG_OK;
@@ -563,14 +563,14 @@ extern "C" int mprg_one_ref_like(mprg_ctx *ctx, const mprg_batch *batch, const m
     MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState)));
     MPRG_CUDA(ctx, B[14].reserve(o_maj + w + 16));
     uint8_t *b = B[14].as<uint8_t>();
-    MPRG_CUDA(ctx, cudaMemcpyAsync(B[13].p, &c, sizeof(c), cudaMemcpyHostToDevice, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(b, mem_off.data(), sizeof(int) * (R + 1), cudaMemcpyHostToDevice, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(b + o_memrows, mem_rows.data(), sizeof(int) * R, cudaMemcpyHostToDevice, s));
-    MPRG_CUDA(ctx, cudaMemcpyAsync(b + o_assign, h_cluster_of_row, sizeof(int) * R, cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[13].p, &c, sizeof(c), s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, b, mem_off.data(), sizeof(int) * (R + 1), s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, b + o_memrows, mem_rows.data(), sizeof(int) * R, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, b + o_assign, h_cluster_of_row, sizeof(int) * R, s));
     MPRG_CUDA(ctx, launch_refcheck(s, B[13].as<ClusterState>(), 1, B[3].as<uint8_t>(), (int *)b, (int *)(b + o_memrows),
                                    (int *)(b + o_assign), b + o_maj, 10, (int *)(b + o_flags)));
     ctx->launches++;
-    MPRG_CUDA(ctx, cudaMemcpyAsync(h_flags, b + o_flags, sizeof(int) * n_clusters, cudaMemcpyDeviceToHost, s));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_flags, b + o_flags, sizeof(int) * n_clusters, s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
     return MPRG_OK;
 }
@@ -734,20 +734,13 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
         iv.resize((size_t)lv.total_iv);
         cnt.resize(nt + 1);
         cudaError_t e;
-        if ((e = cudaMemcpyAsync(iv.data(), ctx->d_iv.p, sizeof(DInterval) * iv.size(), cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
-            (e = cudaMemcpyAsync(cnt.data(), ctx->d_ivcnt.p, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+        if ((e = mprg::copy_d2h(ctx, iv.data(), ctx->d_iv.p, sizeof(DInterval) * iv.size(), s)) != cudaSuccess ||
+            (e = mprg::copy_d2h(ctx, cnt.data(), ctx->d_ivcnt.p, sizeof(int) * cnt.size(), s)) != cudaSuccess ||
             (e = cudaStreamSynchronize(s)) != cudaSuccess) {
             ctx->err = std::string("level D2H: ") + cudaGetErrorString(e);
             return fail(MPRG_E_CUDA);
         }
-        {
-            float ms = 0;
-            if (!lv.units.empty() && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) {
-                ctx->scan_ms += ms;
-                ctx->scan_bytes += lv.algo_bytes;
-                ctx->scan_launches += 1;
-            }
-        }
+        account_scan(ctx, lv);
         if (cnt[nt]) {
             ctx->err = "Failed interval partitioning";
             return fail(MPRG_E_PARTITION);
@@ -868,7 +861,7 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
         if ((e = B[0].reserve(sizeof(ExtractItem) * na)) != cudaSuccess ||
             (e = B[3].reserve((size_t)std::max<long long>(out_total, 1))) != cudaSuccess ||
             (e = B[5].reserve(sizeof(int) * na)) != cudaSuccess ||
-            (e = cudaMemcpyAsync(B[0].p, items.data(), sizeof(ExtractItem) * na, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
+            (e = mprg::copy_h2d(ctx, B[0].p, items.data(), sizeof(ExtractItem) * na, s)) != cudaSuccess) {
             ctx->err = std::string("extract setup: ") + cudaGetErrorString(e);
             return fail(MPRG_E_CUDA);
         }
@@ -876,8 +869,8 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
                                                     B[5].as<int>());
         ctx->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess ||
-            (e = cudaMemcpyAsync(h_out.data(), B[3].p, (size_t)out_total, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
-            (e = cudaMemcpyAsync(h_len.data(), B[5].p, sizeof(int) * na, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+            (e = mprg::copy_d2h(ctx, h_out.data(), B[3].p, (size_t)out_total, s)) != cudaSuccess ||
+            (e = mprg::copy_d2h(ctx, h_len.data(), B[5].p, sizeof(int) * na, s)) != cudaSuccess ||
             (e = cudaStreamSynchronize(s)) != cudaSuccess) {
             ctx->err = std::string("extract: ") + cudaGetErrorString(e);
             return fail(MPRG_E_CUDA);

@@ -34,6 +34,7 @@ struct Level {
 // Builds the level (device task table, scan units), uploads it together with the row-index arena,
 // and runs scan -> classify [-> partition -> demote].  Results stay in the context's device buffers:
 //   d_cls (uint8 per aligned column), d_reach (int per aligned column), d_iv / d_ivcnt.
+void account_scan(mprg_ctx *ctx, const Level &lv);
 int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, int n_tasks,
               const int32_t *h_rows, long long n_row_entries, int mml, bool do_partition, Level &lv);
 

@@ -12,8 +12,10 @@
 // mathematically tied ("KMeans parity").
 //
 // One CTA per problem; samples (or features, for the centre update) are spread over the threads.
+#ifndef MPRG_HOST_EMU  // tests/hostemu compiles the device functions below as plain C++
 #include "common.cuh"
 #include "kernels.cuh"
+#endif
 
 namespace mprg {
 
@@ -43,10 +45,35 @@ __device__ __forceinline__ double sqdist(const double *a, const double *b, int F
     return res;
 }
 
+// Dot product as OpenBLAS dgemm evaluates one output element for the small operands met here: a
+// left-to-right chain of fused multiply-adds (checked bit-for-bit against numpy matmul for
+// inner dimensions below 32; beyond that OpenBLAS blocks the sum and only the value, not the last
+// bits, agrees).
 __device__ __forceinline__ double dot_seq(const double *a, const double *b, int F) {
     double acc = 0.0;
-    for (int i = 0; i < F; ++i) acc = __dadd_rn(acc, __dmul_rn(a[i], b[i]));
+    for (int i = 0; i < F; ++i) acc = fma(a[i], b[i], acc);
     return acc;
+}
+
+// row_norms(X, squared=True) == np.einsum("ij,ij->i", X, X): numpy's two-lane SIMD inner loop
+// (einsum_sumprod.c.src, contig_contig_outstride0_two, 128-bit baseline, separate multiply and add):
+// blocks of 8 elements processed back to front per lane, tail two at a time, lanes added at the end.
+// Bit-identical to numpy for every length.
+__device__ __forceinline__ double einsum_self(const double *a, int n) {
+    double acc0 = 0.0, acc1 = 0.0;
+    int i = 0;
+    for (; n - i >= 8; i += 8) {
+#pragma unroll
+        for (int q = 3; q >= 0; --q) {
+            acc0 = __dadd_rn(__dmul_rn(a[i + 2 * q], a[i + 2 * q]), acc0);
+            acc1 = __dadd_rn(__dmul_rn(a[i + 2 * q + 1], a[i + 2 * q + 1]), acc1);
+        }
+    }
+    for (; i < n; i += 2) {
+        acc0 = __dadd_rn(__dmul_rn(a[i], a[i]), acc0);
+        if (i + 1 < n) acc1 = __dadd_rn(__dmul_rn(a[i + 1], a[i + 1]), acc1);
+    }
+    return __dadd_rn(acc0, acc1);
 }
 
 // numpy's pairwise summation of a contiguous float64 vector (numpy/core/src/umath/loops_utils.h)
@@ -124,7 +151,7 @@ __device__ __forceinline__ double eucl_sq(const KM &k, int cand, int i) {
 
 __device__ void center_half_distances(const KM &k, const double *C) {
     const int K = k.K, F = k.F;
-    for (int j = threadIdx.x; j < K; j += blockDim.x) k.cc[j] = dot_seq(C + (long long)j * F, C + (long long)j * F, F);
+    for (int j = threadIdx.x; j < K; j += blockDim.x) k.cc[j] = einsum_self(C + (long long)j * F, F);
     __syncthreads();
     for (int p = threadIdx.x; p < K * K; p += blockDim.x) {
         const int a = p / K, b = p % K;
@@ -209,6 +236,9 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
     rand_pos += 1;
     __syncthreads();
     const int c0 = s_int[0];
+#ifdef MPRG_HOST_EMU_DEBUG
+    printf("  kpp first %d (u=%.17g)\n", c0, c_rand[rand_pos - 1]);
+#endif
     for (int f = threadIdx.x; f < F; f += blockDim.x) C[f] = k.Xc[(long long)c0 * F + f];
     for (int i = threadIdx.x; i < n; i += blockDim.x) k.closest[i] = eucl_sq(k, c0, i);
     __syncthreads();
@@ -258,6 +288,11 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
             }
             s_scalar[0] = best_pot;
             s_int[0] = best;
+#ifdef MPRG_HOST_EMU_DEBUG
+            printf("  kpp c=%d cands", c);
+            for (int t = 0; t < trials; ++t) printf(" %d", s_int[1 + t]);
+            printf(" best %d pot %.17g\n", best, best_pot);
+#endif
         }
         __syncthreads();
         const int best = s_int[0], cand = s_int[1 + best];
@@ -469,7 +504,7 @@ __device__ void kmeans_fit_predict(KM &k, double *s_scalar, int *s_int, int *out
     __syncthreads();
     if (threadIdx.x == 0) s_scalar[2] = __dmul_rn(np_pairwise_sum(k.tmpF, F) / (double)F, 1e-4);
     for (int i = threadIdx.x; i < n; i += blockDim.x)
-        k.xx[i] = dot_seq(k.Xc + (long long)i * F, k.Xc + (long long)i * F, F);
+        k.xx[i] = einsum_self(k.Xc + (long long)i * F, F);
     __syncthreads();
     const double tol = s_scalar[2];
     int rand_pos = 0;
@@ -479,6 +514,11 @@ __device__ void kmeans_fit_predict(KM &k, double *s_scalar, int *s_int, int *out
         const double *C = nullptr;
         kmeans_single(k, rand_pos, tol, s_scalar, s_int, &C);
         const double inertia = s_scalar[1];
+#ifdef MPRG_HOST_EMU_DEBUG
+        printf("emu init %d inertia %.17g labels", init, inertia);
+        for (int i = 0; i < n; ++i) printf(" %d", k.labels[i]);
+        printf("\n");
+#endif
         if (threadIdx.x == 0) {
             int take = 0;
             if (!have_best) take = 1;
@@ -510,7 +550,7 @@ __device__ void kmeans_fit_predict(KM &k, double *s_scalar, int *s_int, int *out
         k.best_c[p] = __dadd_rn(k.best_c[p], k.mean[p % F]);
     __syncthreads();
     for (int j = threadIdx.x; j < K; j += blockDim.x)
-        k.cc[j] = dot_seq(k.best_c + (long long)j * F, k.best_c + (long long)j * F, F);
+        k.cc[j] = einsum_self(k.best_c + (long long)j * F, F);
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double *x = k.X0 + (long long)i * F;
@@ -602,6 +642,7 @@ long long kmeans_dscratch_doubles(long long n, long long F) {
 }
 long long kmeans_iscratch_ints(long long n) { return 3 * n + 8; }
 
+#ifndef MPRG_HOST_EMU
 cudaError_t kmeans_upload_rand(const double *h_rand) {
     return cudaMemcpyToSymbol(c_rand, h_rand, sizeof(double) * KM_RAND_COUNT);
 }
@@ -618,5 +659,7 @@ cudaError_t launch_kmeans_single(cudaStream_t s, const double *X0, int n, int F,
     kmeans_single_problem_kernel<<<1, KM_THREADS, 0, s>>>(X0, n, F, K, dscratch, iscratch, labels, inertia);
     return cudaGetLastError();
 }
+
+#endif  // MPRG_HOST_EMU
 
 }  // namespace mprg

@@ -8,6 +8,20 @@ namespace mprg {
 
 constexpr int MAX_UNIT_ROWS = 1024;  // rows of one task handled by one CTA
 
+// call after the stream has been synchronised: device time of the level's scan launch
+void account_scan(mprg_ctx *ctx, const Level &lv) {
+    float ms = 0;
+    if (!lv.units.empty() && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) {
+        ctx->scan_ms += ms;
+        ctx->scan_bytes += lv.algo_bytes;
+        ctx->scan_launches += 1;
+        if (ctx->scan_log_bytes.size() < (1u << 20)) {
+            ctx->scan_log_bytes.push_back(lv.algo_bytes);
+            ctx->scan_log_ms.push_back(ms);
+        }
+    }
+}
+
 int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, int n_tasks,
               const int32_t *h_rows, long long n_row_entries, int mml, bool do_partition, Level &lv) {
     cudaSetDevice(ctx->device);
@@ -76,14 +90,11 @@ int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, 
     MPRG_CUDA(ctx, ctx->d_iv.reserve(sizeof(DInterval) * lv.total_iv));
     MPRG_CUDA(ctx, ctx->d_ivcnt.reserve(sizeof(int) * (n_tasks + 1)));
 
-    MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_tasks.p, lv.tasks.data(), sizeof(DTask) * n_tasks,
-                                   cudaMemcpyHostToDevice, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, ctx->d_tasks.p, lv.tasks.data(), sizeof(DTask) * n_tasks, s));
     if (n_units)
-        MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_units.p, lv.units.data(), sizeof(ScanUnit) * n_units,
-                                       cudaMemcpyHostToDevice, s));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, ctx->d_units.p, lv.units.data(), sizeof(ScanUnit) * n_units, s));
     if (n_row_entries > 0)
-        MPRG_CUDA(ctx, cudaMemcpyAsync(ctx->d_rows.p, h_rows, sizeof(int) * n_row_entries,
-                                       cudaMemcpyHostToDevice, s));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, ctx->d_rows.p, h_rows, sizeof(int) * n_row_entries, s));
     MPRG_CUDA(ctx, cudaMemsetAsync(ctx->d_colwords.p, 0, sizeof(uint32_t) * 2 * words, s));
     MPRG_CUDA(ctx, cudaMemsetAsync(ctx->d_colB.p, 0, sizeof(unsigned) * lv.total_cols, s));
     // last int of d_ivcnt is the partition error flag

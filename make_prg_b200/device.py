@@ -80,6 +80,26 @@ class Context:
         self._check(self.lib.mprg_scan_stats(self.handle, C.byref(ms), C.byref(by), C.byref(n), int(reset)))
         return {"ms": ms.value, "bytes": by.value, "launches": n.value}
 
+    def copy_stats(self, reset=False):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.mprg_copy_stats(self.handle, C.byref(a), C.byref(b), int(reset)))
+        return {"h2d_bytes": a.value, "d2h_bytes": b.value}
+
+    def timer_start(self):
+        self._check(self.lib.mprg_timer(self.handle, 0, None))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self.lib.mprg_timer(self.handle, 1, C.byref(ms)))
+        return ms.value
+
+    def scan_log(self, reset=False, capacity=65536):
+        by = np.zeros(capacity, np.float64)
+        ms = np.zeros(capacity, np.float64)
+        n = C.c_int32()
+        self._check(self.lib.mprg_scan_log(self.handle, ptr(by), ptr(ms), capacity, C.byref(n), int(reset)))
+        return by[:n.value].copy(), ms[:n.value].copy()
+
     # ---- loader -> HBM ------------------------------------------------------------------------
     def upload(self, matrices):
         """matrices: list of uint8[rows, cols] ASCII arrays (or one flat buffer + shapes tuple)."""

@@ -56,3 +56,45 @@ def rows_to_matrix(rows):
     if not rows or len(rows[0]) == 0:
         return np.zeros((len(rows), 0), np.uint8)
     return np.frombuffer("".join(rows).encode(), np.uint8).reshape(len(rows), -1).copy()
+
+
+def prg_to_regex(prg):
+    """A PRG string as a regular expression over ACGT: site ` s a1 s+1 a2 ... s ` -> (?:a1|a2|...).
+    Every path through the PRG is a match; used for the size-independent property
+    'each input sequence is spelled by the PRG'."""
+    import re
+
+    tokens = re.findall(r" \d+ |[ACGT]+", prg)
+    out = []
+    stack = []  # open odd markers
+    for tok in tokens:
+        if tok[0] == " ":
+            m = int(tok)
+            if m % 2 == 1:
+                if stack and stack[-1] == m:
+                    stack.pop()
+                    out.append(")")
+                else:
+                    stack.append(m)
+                    out.append("(?:")
+            else:
+                out.append("|")
+        else:
+            out.append(tok)
+    assert not stack, "unbalanced PRG"
+    return "".join(out)
+
+
+def prg_spells_all_rows(prg, M):
+    import re
+
+    pat = re.compile(prg_to_regex(prg))
+    seen = set()
+    for row in M:
+        s = bytes(row[row != ord("-")]).decode()
+        if s in seen:
+            continue
+        seen.add(s)
+        if not pat.fullmatch(s):
+            return False
+    return True
