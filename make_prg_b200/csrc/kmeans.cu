@@ -45,14 +45,172 @@ __device__ __forceinline__ double sqdist(const double *a, const double *b, int F
     return res;
 }
 
-// Dot product as OpenBLAS dgemm evaluates one output element for the small operands met here: a
-// left-to-right chain of fused multiply-adds (checked bit-for-bit against numpy matmul for
-// inner dimensions below 32; beyond that OpenBLAS blocks the sum and only the value, not the last
-// bits, agrees).
-__device__ __forceinline__ double dot_seq(const double *a, const double *b, int F) {
+// ---- dot products exactly as numpy's matmul (OpenBLAS 0.3.30 dgemm, "TN" operand layout) rounds them
+// One output element C[i, j] = sum_k a[k] * b[k] of a product with inner dimension F, `mi`/`M` the
+// index/extent along the operand that OpenBLAS sees as M and `ni`/`N` along N:
+//   F < 32                      left-to-right chain of fused multiply-adds
+//   F >= 32 and M * N <= 1200   small-matrix kernel: eight lanes (k mod 8), each a chain of fused
+//                               multiply-adds, masked tail, then a horizontal reduction whose shape
+//                               depends on the 4x4 tile the element falls in
+//   otherwise                   blocked driver: chains of fused multiply-adds over K blocks of at most
+//                               384 (OpenBLAS level-3 split rule), block results added in order
+// Checked bit-for-bit against numpy matmul over thousands of random shapes (DESIGN.md "KMeans parity");
+// odd inner dimensions above 384 in the blocked regime are the one known gap.
+__device__ __forceinline__ double dot_fma_range(const double *a, const double *b, int lo, int hi) {
     double acc = 0.0;
-    for (int i = 0; i < F; ++i) acc = fma(a[i], b[i], acc);
+    for (int i = lo; i < hi; ++i) acc = fma(a[i], b[i], acc);
     return acc;
+}
+
+__device__ double gemm_dot(const double *a, const double *b, int F, int mi, int M, int ni, int N) {
+    if (F < 32) return dot_fma_range(a, b, 0, F);
+    if ((long long)M * N <= 1200) {
+        double l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int full = F & ~7;
+        for (int k = 0; k < full; k += 8) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) l[q] = fma(a[k + q], b[k + q], l[q]);
+        }
+        for (int k = full; k < F; ++k) l[k - full] = fma(a[k], b[k], l[k - full]);
+        if (mi < (M & ~3) || ni < (N & ~3)) {
+            // adjacent pairs
+            const double p0 = __dadd_rn(l[0], l[1]), p1 = __dadd_rn(l[2], l[3]);
+            const double p2 = __dadd_rn(l[4], l[5]), p3 = __dadd_rn(l[6], l[7]);
+            return __dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3));
+        }
+        // halves (_mm512_reduce_add_pd)
+        const double h0 = __dadd_rn(l[0], l[4]), h1 = __dadd_rn(l[1], l[5]);
+        const double h2 = __dadd_rn(l[2], l[6]), h3 = __dadd_rn(l[3], l[7]);
+        return __dadd_rn(__dadd_rn(h0, h2), __dadd_rn(h1, h3));
+    }
+    double tot = 0.0;
+    int ls = 0;
+    while (ls < F) {
+        int m = F - ls;
+        if (m >= 768) m = 384;
+        else if (m > 384) m = ((m / 2 + 3) / 4) * 4;
+        tot = __dadd_rn(tot, dot_fma_range(a, b, ls, ls + m));
+        ls += m;
+    }
+    return tot;
+}
+
+// c0 + alpha * dot as dgemm(alpha, beta = 1) leaves it in C: identical to gemm_dot except in the
+// blocked regime, where every K block is scaled and added to C separately
+__device__ double gemm_axpy(const double *a, const double *b, int F, int mi, int M, int ni, int N,
+                            double alpha, double c0) {
+    if (F < 32 || (long long)M * N <= 1200 || F <= 384)
+        return __dadd_rn(c0, __dmul_rn(alpha, gemm_dot(a, b, F, mi, M, ni, N)));
+    double v = c0;
+    int ls = 0;
+    while (ls < F) {
+        int m = F - ls;
+        if (m >= 768) m = 384;
+        else if (m > 384) m = ((m / 2 + 3) / 4) * 4;
+        v = __dadd_rn(v, __dmul_rn(alpha, dot_fma_range(a, b, ls, ls + m)));
+        ls += m;
+    }
+    return v;
+}
+
+// ---- OpenBLAS dgemv_t (numpy matmul with a single row / a single column operand) -------------
+// Output j of nout, dot length len (x86_64 dgemv_t_4.c + Haswell/SkylakeX micro-kernel): outputs are
+// produced four at a time by a 4-lane fused-multiply-add kernel; the 1-3 trailing outputs go through
+// the 2-output (two lanes, separate multiply and add) and 1-output (four lanes, separate multiply and
+// add) kernels; the len % 4 trailing elements are added as one expression.  Bit-identical to numpy on
+// every shape tried (DESIGN.md "KMeans parity").
+__device__ __forceinline__ double gemv_tail_expr(const double *a, const double *b, int m3) {
+    if (m3 == 1) return __dmul_rn(a[0], b[0]);
+    const double p = __dmul_rn(a[1], b[1]);
+    const double s = fma(a[0], b[0], p);
+    return m3 == 2 ? s : fma(a[2], b[2], s);
+}
+
+__device__ double gemv_t_dot(const double *a, const double *b, int len, int j, int nout) {
+    const int m3 = len & 3, main_n = len - m3;
+    if (main_n == 0) return m3 ? gemv_tail_expr(a, b, m3) : 0.0;
+    const int n4 = nout & ~3, rem = nout & 3;
+    int kind = 0;  // 0: four lanes fused, 1: two lanes unfused, 2: four lanes unfused
+    if (j >= n4) kind = (rem >= 2 && j - n4 < 2) ? 1 : 2;
+    double s;
+    if (kind == 1) {
+        double l0 = 0.0, l1 = 0.0;
+        for (int i = 0; i < main_n; i += 2) {
+            l0 = __dadd_rn(__dmul_rn(a[i], b[i]), l0);
+            l1 = __dadd_rn(__dmul_rn(a[i + 1], b[i + 1]), l1);
+        }
+        s = __dadd_rn(l0, l1);
+    } else {
+        double l[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < main_n; i += 4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                l[q] = kind == 0 ? fma(a[i + q], b[i + q], l[q]) : __dadd_rn(__dmul_rn(a[i + q], b[i + q]), l[q]);
+        }
+        s = __dadd_rn(__dadd_rn(l[0], l[2]), __dadd_rn(l[1], l[3]));
+    }
+    if (m3 == 1) return fma(a[main_n], b[main_n], s);
+    if (m3) return __dadd_rn(s, gemv_tail_expr(a + main_n, b + main_n, m3));
+    return s;
+}
+
+// the same kernel with b == 1 everywhere: row sums `D @ sample_weight.reshape(-1, 1)`
+__device__ double gemv_t_sum(const double *a, int len, int j, int nout) {
+    const int m3 = len & 3, main_n = len - m3;
+    auto tail = [&](const double *p) {
+        if (m3 == 1) return p[0];
+        const double s2 = __dadd_rn(p[0], p[1]);
+        return m3 == 2 ? s2 : __dadd_rn(p[2], s2);
+    };
+    if (main_n == 0) return m3 ? tail(a) : 0.0;
+    const int n4 = nout & ~3, rem = nout & 3;
+    const bool two_lanes = j >= n4 && rem >= 2 && j - n4 < 2;
+    double s;
+    if (two_lanes) {
+        double l0 = 0.0, l1 = 0.0;
+        for (int i = 0; i < main_n; i += 2) {
+            l0 = __dadd_rn(a[i], l0);
+            l1 = __dadd_rn(a[i + 1], l1);
+        }
+        s = __dadd_rn(l0, l1);
+    } else {
+        double l[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < main_n; i += 4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) l[q] = __dadd_rn(a[i + q], l[q]);
+        }
+        s = __dadd_rn(__dadd_rn(l[0], l[2]), __dadd_rn(l[1], l[3]));
+    }
+    if (m3 == 1) return __dadd_rn(a[main_n], s);
+    if (m3) return __dadd_rn(s, tail(a + main_n));
+    return s;
+}
+
+// OpenBLAS ddot (SkylakeX micro-kernel) with y == 1: `closest_dist_sq @ sample_weight`
+__device__ double ddot_ones(const double *x, int n) {
+    const int n1 = n & -16;
+    double dot = 0.0;
+    if (n1) {
+        double z[4][8], a[4][4];
+        for (int k = 0; k < 4; ++k)
+            for (int l = 0; l < 8; ++l) z[k][l] = 0.0;
+        const int n32 = n1 & ~31;
+        int i = 0;
+        for (; i < n32; i += 32)
+            for (int k = 0; k < 4; ++k)
+                for (int l = 0; l < 8; ++l) z[k][l] = __dadd_rn(x[i + 8 * k + l], z[k][l]);
+        for (int k = 0; k < 4; ++k)
+            for (int l = 0; l < 4; ++l) a[k][l] = __dadd_rn(z[k][l], z[k][l + 4]);
+        for (; i < n1; i += 16)
+            for (int k = 0; k < 4; ++k)
+                for (int l = 0; l < 4; ++l) a[k][l] = __dadd_rn(x[i + 4 * k + l], a[k][l]);
+        double t[4];
+        for (int l = 0; l < 4; ++l)
+            t[l] = __dadd_rn(__dadd_rn(__dadd_rn(a[0][l], a[1][l]), a[2][l]), a[3][l]);
+        dot = __dadd_rn(__dadd_rn(t[0], t[2]), __dadd_rn(t[1], t[3]));
+    }
+    for (int i = n1; i < n; ++i) dot = __dadd_rn(x[i], dot);
+    return dot;
 }
 
 // row_norms(X, squared=True) == np.einsum("ij,ij->i", X, X): numpy's two-lane SIMD inner loop
@@ -143,8 +301,11 @@ struct KM {
 };
 
 // squared distance candidate -> sample through  -2 x.y + |x|^2 + |y|^2  clamped at 0
-__device__ __forceinline__ double eucl_sq(const KM &k, int cand, int i) {
-    const double d = dot_seq(k.Xc + (long long)cand * k.F, k.Xc + (long long)i * k.F, k.F);
+__device__ __forceinline__ double eucl_sq(const KM &k, int cand, int i, int t, int trials) {
+    // numpy: X[candidate_ids] @ X.T  ->  M = n samples (index i), N = trials (index t); a single
+    // candidate row (the first centre) goes through dgemv instead of dgemm
+    const double *a = k.Xc + (long long)cand * k.F, *b = k.Xc + (long long)i * k.F;
+    const double d = trials == 1 ? gemv_t_dot(a, b, k.F, i, k.n) : gemm_dot(a, b, k.F, i, k.n, t, trials);
     double v = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, d), k.xx[cand]), k.xx[i]);
     return v > 0.0 ? v : 0.0;
 }
@@ -157,7 +318,7 @@ __device__ void center_half_distances(const KM &k, const double *C) {
         const int a = p / K, b = p % K;
         double v = 0.0;
         if (a != b) {
-            const double d = dot_seq(C + (long long)a * F, C + (long long)b * F, F);
+            const double d = gemm_dot(C + (long long)a * F, C + (long long)b * F, F, b, K, a, K);
             v = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, d), k.cc[a]), k.cc[b]);
             v = v > 0.0 ? v : 0.0;
             v = sqrt(v) / 2.0;
@@ -240,12 +401,10 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
     printf("  kpp first %d (u=%.17g)\n", c0, c_rand[rand_pos - 1]);
 #endif
     for (int f = threadIdx.x; f < F; f += blockDim.x) C[f] = k.Xc[(long long)c0 * F + f];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) k.closest[i] = eucl_sq(k, c0, i);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) k.closest[i] = eucl_sq(k, c0, i, 0, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        double pot = 0.0;
-        for (int i = 0; i < n; ++i) pot = __dadd_rn(pot, k.closest[i]);
-        s_scalar[0] = pot;
+        s_scalar[0] = ddot_ones(k.closest, n);
     }
     __syncthreads();
     for (int c = 1; c < K; ++c) {
@@ -270,7 +429,7 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
         __syncthreads();
         for (int p = threadIdx.x; p < trials * n; p += blockDim.x) {
             const int t = p / n, i = p % n;
-            const double d = eucl_sq(k, s_int[1 + t], i);
+            const double d = eucl_sq(k, s_int[1 + t], i, t, trials);
             const double cl = k.closest[i];
             k.D[p] = cl < d ? cl : d;
         }
@@ -279,8 +438,7 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
             int best = 0;
             double best_pot = 0.0;
             for (int t = 0; t < trials; ++t) {
-                double s = 0.0;
-                for (int i = 0; i < n; ++i) s = __dadd_rn(s, k.D[t * n + i]);
+                const double s = gemv_t_sum(k.D + (long long)t * n, n, t, trials);
                 if (t == 0 || s < best_pot) {
                     best = t;
                     best_pot = s;
@@ -557,7 +715,9 @@ __device__ void kmeans_fit_predict(KM &k, double *s_scalar, int *s_int, int *out
         int lab = 0;
         double best = 0.0;
         for (int j = 0; j < K; ++j) {
-            const double v = __dadd_rn(k.cc[j], __dmul_rn(-2.0, dot_seq(x, k.best_c + (long long)j * F, F)));
+            const int chunk = n > 256 ? 256 : n;
+            const int ci = i % chunk, cn = (i / chunk) * chunk + chunk <= n ? chunk : n % chunk;
+            const double v = gemm_axpy(x, k.best_c + (long long)j * F, F, j, K, ci, cn, -2.0, k.cc[j]);
             if (j == 0 || v < best) {
                 best = v;
                 lab = j;

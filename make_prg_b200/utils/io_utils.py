@@ -1,0 +1,80 @@
+"""Loader: FASTA (optionally .gz) -> MSA, upper-cased, N replaced by the per-column majority symbol.
+Mirrors make_prg/utils/io_utils.py:17-49 and make_prg/utils/seq_utils.py:242-290 (the private RNG is
+seeded with sha256 of the concatenated rows and `choice` is drawn once per column, in column order,
+so the stream position is identical to the reference's)."""
+import gzip
+import hashlib
+import random
+from collections import Counter
+from io import StringIO
+from pathlib import Path
+
+from ..msa import MSA, SeqRecord
+
+
+def parse_fasta(handle):
+    titles, chunks = [], []
+    for raw in handle:
+        line = raw.rstrip("\r\n")
+        if line.startswith(">"):
+            titles.append(line[1:])
+            chunks.append([])
+        elif titles:
+            chunks[-1].append(line.replace(" ", ""))
+    if not titles:
+        raise ValueError("No records found in handle")
+    records = []
+    for title, parts in zip(titles, chunks):
+        tokens = title.split(None, 1)
+        rid = tokens[0] if tokens else ""
+        records.append(SeqRecord("".join(parts), rid, rid, title))
+    return MSA(records)
+
+
+def get_majority_consensus_from_MSA(alignment):
+    seqs = [r.seq.upper() for r in alignment]
+    rng = random.Random()
+    rng.seed(hashlib.sha256("".join(seqs).encode()).digest())
+    consensus = []
+    for i in range(alignment.get_alignment_length()):
+        counts = Counter(s[i] for s in seqs if s[i] != "-" and s[i] != "N")
+        if not counts:
+            consensus.append(rng.choice("ACGT"))
+            continue
+        top = counts.most_common(1)[0][1]
+        consensus.append(rng.choice([res for res, c in counts.items() if c == top]))
+    return "".join(consensus)
+
+
+def load_alignment_file(msa_file, alignment_format="fasta"):
+    if alignment_format != "fasta":
+        raise ValueError(f"only the fasta alignment format is supported, got {alignment_format}")
+    if isinstance(msa_file, StringIO):
+        alignment = parse_fasta(msa_file)
+    else:
+        path = str(msa_file)
+        opener = gzip.open if path.endswith(".gz") else open
+        with opener(path, "rt") as handle:
+            alignment = parse_fasta(handle)
+    for record in alignment:
+        record.seq = record.seq.upper()
+    if any("N" in record.seq for record in alignment):
+        consensus = get_majority_consensus_from_MSA(alignment)
+        for record in alignment:
+            if "N" in record.seq:
+                record.seq = "".join(consensus[i] if ch == "N" else ch for i, ch in enumerate(record.seq))
+    alignment._matrix = None
+    return alignment
+
+
+def locus_name_of(path):
+    """input_output_files.py:234-235: file name minus .fa/.fasta(.gz)."""
+    name = Path(path).name
+    for suffix in (".gz",):
+        if name.endswith(suffix):
+            name = name[: -len(suffix)]
+    for suffix in (".fasta", ".fa"):
+        if name.endswith(suffix):
+            name = name[: -len(suffix)]
+            break
+    return name

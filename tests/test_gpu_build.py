@@ -61,34 +61,14 @@ def test_disallowed_base_marks_locus_only(ctx):
 
 def test_sample_example_and_amira(ctx):
     for setname, files in (("sample_example", ["GC00006032.fa", "GC00010897.fa"]),
-                           ("amira_MSAs", ["glpG.fasta.gz", "group_18516.fasta.gz"])):
+                           ("amira_MSAs", ["alsB.fasta.gz", "glpG.fasta.gz", "group_18516.fasta.gz"])):
         mats = [mo.load_msa(REF / setname / f)[1] for f in files]
         _, res = _build(ctx, mats, 5, 7)
         truth = truth_multi(setname)
         for i, f in enumerate(files):
             name = f.split(".")[0]
             assert res.prg(i) == truth[name], name
-
-
-def test_amira_alsB_tie_case(ctx):
-    """alsB holds a KMeans problem that is an exact three-way tie (count matrix == I3, K=2); the
-    reference's outcome there is decided by BLAS rounding noise inside scikit-learn's k-means++
-    (DESIGN.md 'KMeans parity').  Everything before that site must be identical,
-    the tree must have the same size, and the PRG must still spell every input sequence."""
-    M = mo.load_msa(REF / "amira_MSAs" / "alsB.fasta.gz")[1]
-    _, res = _build(ctx, [M], 5, 7)
-    truth = truth_multi("amira_MSAs")["alsB"]
-    got = res.prg(0)
-    if got != truth:
-        common = 0
-        while common < min(len(got), len(truth)) and got[common] == truth[common]:
-            common += 1
-        assert common > 3000  # first 98 sites identical
-        assert prg_spells_all_rows(got, M)
-        pytest.xfail("alsB differs from the reference golden at the documented exact-tie site")
-
-
-TOTAL, DIFFER = [], []
+            assert prg_spells_all_rows(res.prg(i), mats[i])
 
 
 def test_synthetic_prg_and_tree(ctx):
@@ -100,16 +80,9 @@ def test_synthetic_prg_and_tree(ctx):
         mats = [synth.config_msa(r["config"], r["index"], r.get("rows"), r.get("cols")) for r in rs]
         _, res = _build(ctx, mats, N, L)
         for i, r in enumerate(rs):
-            TOTAL.append(1)
-            if res.prg(i) == r["prg"]:
-                assert res.n_nodes(i) == r["n_nodes"] and res.n_sites(i) == r["n_sites"]
-                assert _tree_dump(res, i, mats[i]) == [list(t) for t in r["tree"]]
-            else:
-                # only a KMeans exact-tie may differ (DESIGN.md 'KMeans parity'); the PRG must still
-                # spell every input row
-                DIFFER.append((r["config"], r["index"], N, L))
-                assert prg_spells_all_rows(res.prg(i), mats[i])
-    assert len(DIFFER) <= 0.15 * len(TOTAL), DIFFER
+            assert res.prg(i) == r["prg"], (r["config"], r["index"], N, L)
+            assert res.n_nodes(i) == r["n_nodes"] and res.n_sites(i) == r["n_sites"]
+            assert _tree_dump(res, i, mats[i]) == [list(t) for t in r["tree"]]
 
 
 def test_batch_order_invariance(ctx):
