@@ -71,8 +71,9 @@ __global__ void __launch_bounds__(256)
 dedupe_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ g_off,
               const uint8_t *__restrict__ G, const long long *__restrict__ row_off,
               RowSig *__restrict__ sig, int *__restrict__ leader_u, int *__restrict__ leader_g,
-              int *__restrict__ group, int *__restrict__ ulen, int *__restrict__ n_ungapped,
-              int *__restrict__ n_gapped, int *__restrict__ err) {
+              int *__restrict__ group, int *__restrict__ ulen, int *__restrict__ leaders,
+              int *__restrict__ leader_len, int *__restrict__ n_ungapped, int *__restrict__ n_gapped,
+              int *__restrict__ err) {
     const int ti = blockIdx.x;
     const DTask t = tasks[ti];
     const int w = t.c1 - t.c0, R = t.n_rows;
@@ -122,8 +123,13 @@ dedupe_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ g_o
     if (threadIdx.x == 0) {
         int nu = 0, ng = 0;
         for (int r = 0; r < R; ++r) {
-            if (lu[r] == r) group[ro + r] = nu++;
-            else group[ro + r] = group[ro + lu[r]];
+            if (lu[r] == r) {
+                leaders[ro + nu] = r;
+                leader_len[ro + nu] = ulen[ro + r];
+                group[ro + r] = nu++;
+            } else {
+                group[ro + r] = group[ro + lu[r]];
+            }
             ng += lg[r] == r;
         }
         n_ungapped[ti] = nu;
@@ -364,6 +370,106 @@ refcheck_kernel(ClusterState *__restrict__ states, const uint8_t *__restrict__ G
     }
 }
 
+// ---- small device-side bookkeeping so that only O(#distinct) data crosses PCIe ---------------------
+// exclusive scan of counts[0..n) into offs[0..n] (single CTA)
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int *__restrict__ counts, int n,
+                                                           int *__restrict__ offs) {
+    __shared__ int s_warp[33];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? counts[i] : 0;
+        int x = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += o;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int y = lane < nw ? s_warp[lane] : 0;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, y, d);
+                if (lane >= d) y += o;
+            }
+            s_warp[lane] = y;
+        }
+        __syncthreads();
+        if (i < n) offs[i] = carry + (warp ? s_warp[warp - 1] : 0) + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += s_warp[nw - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offs[n] = carry;
+}
+
+// dst[dst_off[t] + i] = src[src_off[t] + i] for i < counts[t], two int arrays at once; one warp per t
+__global__ void __launch_bounds__(256)
+gather2_kernel(const long long *__restrict__ src_off, const int *__restrict__ counts,
+               const int *__restrict__ dst_off, int n, const int *__restrict__ src_a,
+               const int *__restrict__ src_b, int *__restrict__ dst_a, int *__restrict__ dst_b) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= n) return;
+    const long long so = src_off[t];
+    const int d = dst_off[t], c = counts[t];
+    for (int i = lane; i < c; i += 32) {
+        dst_a[d + i] = src_a[so + i];
+        if (src_b) dst_b[d + i] = src_b[so + i];
+    }
+}
+
+// member lists of a clustering problem: rows of every distinct long sequence, in row order
+__global__ void __launch_bounds__(32)
+members_kernel(const MemberProb *__restrict__ probs, const int *__restrict__ group,
+               const int *__restrict__ leader_len, int *__restrict__ long_of_group,
+               int *__restrict__ mem_off_all, int *__restrict__ mem_rows_all) {
+    if (threadIdx.x != 0) return;
+    const MemberProb p = probs[blockIdx.x];
+    const int *grp = group + p.row_off;
+    const int *ll = leader_len + p.row_off;
+    int *lg = long_of_group + p.row_off;
+    int *mem_off = mem_off_all + p.mem_off;
+    int *mem_rows = mem_rows_all + p.mem_rows_off;
+    int n = 0;
+    for (int g = 0; g < p.n_groups; ++g) lg[g] = ll[g] >= p.k ? n++ : -1;
+    for (int j = 0; j <= n; ++j) mem_off[j] = 0;
+    for (int r = 0; r < p.R; ++r) {
+        const int j = lg[grp[r]];
+        if (j >= 0) mem_off[j + 1]++;
+    }
+    for (int j = 0; j < n; ++j) mem_off[j + 1] += mem_off[j];
+    // stable placement in row order: advance mem_off[j] as a cursor, then shift the offsets back
+    for (int r = 0; r < p.R; ++r) {
+        const int j = lg[grp[r]];
+        if (j >= 0) mem_rows[mem_off[j]++] = r;
+    }
+    for (int j = n; j > 0; --j) mem_off[j] = mem_off[j - 1];
+    mem_off[0] = 0;
+}
+
+cudaError_t launch_scan_counts(cudaStream_t s, const int *counts, int n, int *offs) {
+    scan_counts_kernel<<<1, 1024, 0, s>>>(counts, n, offs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather2(cudaStream_t s, const long long *src_off, const int *counts, const int *dst_off,
+                           int n, const int *src_a, const int *src_b, int *dst_a, int *dst_b) {
+    if (n <= 0) return cudaSuccess;
+    gather2_kernel<<<(n + 7) / 8, 256, 0, s>>>(src_off, counts, dst_off, n, src_a, src_b, dst_a, dst_b);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_members(cudaStream_t s, const MemberProb *probs, int n, const int *group,
+                           const int *leader_len, int *long_of_group, int *mem_off, int *mem_rows) {
+    if (n <= 0) return cudaSuccess;
+    members_kernel<<<n, 32, 0, s>>>(probs, group, leader_len, long_of_group, mem_off, mem_rows);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_unpack(cudaStream_t s, const uint8_t *packed, const DTask *d_tasks, int n_tasks,
                           const int *d_rows, const long long *g_off, uint8_t *G) {
     if (n_tasks <= 0) return cudaSuccess;
@@ -373,11 +479,11 @@ cudaError_t launch_unpack(cudaStream_t s, const uint8_t *packed, const DTask *d_
 
 cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, const long long *g_off,
                           const uint8_t *G, const long long *row_off, void *sig, int *leader_u,
-                          int *leader_g, int *group, int *ulen, int *n_ungapped, int *n_gapped,
-                          int *err) {
+                          int *leader_g, int *group, int *ulen, int *leaders, int *leader_len,
+                          int *n_ungapped, int *n_gapped, int *err) {
     if (n_tasks <= 0) return cudaSuccess;
     dedupe_kernel<<<n_tasks, 256, 0, s>>>(d_tasks, g_off, G, row_off, (RowSig *)sig, leader_u, leader_g,
-                                          group, ulen, n_ungapped, n_gapped, err);
+                                          group, ulen, leaders, leader_len, n_ungapped, n_gapped, err);
     return cudaGetLastError();
 }
 

@@ -9,7 +9,10 @@
 // The host only keeps the tree bookkeeping (nodes, row subsets, child tasks), the cluster-merge
 // ordering rules and the string assembly.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_set>
@@ -20,6 +23,35 @@
 using namespace mprg;
 
 namespace mprg {
+
+// ---- optional wall-clock phase trace (MPRG_TRACE=1) ------------------------------------------------
+struct PhaseTrace {
+    bool on;
+    std::vector<std::pair<std::string, double>> acc;
+    std::chrono::steady_clock::time_point t;
+    PhaseTrace() : on(getenv("MPRG_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void mark(const char *name) {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        const double ms = std::chrono::duration<double, std::milli>(now - t).count();
+        t = now;
+        for (auto &p : acc)
+            if (p.first == name) {
+                p.second += ms;
+                return;
+            }
+        acc.emplace_back(name, ms);
+    }
+    void report(const char *title) {
+        if (!on) return;
+        double tot = 0;
+        for (auto &p : acc) tot += p.second;
+        fprintf(stderr, "[mprg trace] %s total %.2f ms\n", title, tot);
+        for (auto &p : acc) fprintf(stderr, "    %-28s %8.2f ms\n", p.first.c_str(), p.second);
+    }
+};
+static PhaseTrace *g_trace = nullptr;
+#define TRACE(name) do { if (g_trace) g_trace->mark(name); } while (0)
 
 // ---- MT19937 as numpy's RandomState(seed) / random_sample ---------------------------------------
 static void randomstate_doubles(uint32_t seed, double *out, int count) {
@@ -94,34 +126,77 @@ extract_kernel(const uint8_t *__restrict__ packed, const ExtractItem *__restrict
 // ---- clustering of a level ------------------------------------------------------------------------
 struct ClusterOut {
     int n_ungapped = 0, n_gapped = 0;
-    std::vector<int> group;  // per task row: distinct ungapped sequence (first-seen order)
-    std::vector<int> ulen;   // per task row: ungapped length
-    bool no_clustering = true;
-    std::vector<std::vector<int>> clusters;  // ClusteringResult.clustered_ids as task-local row positions
+    std::vector<int> leaders;     // task-local row position of each distinct ungapped sequence (first-seen order)
+    std::vector<int> leader_len;  // its ungapped length
+    bool no_clustering = true;    // ClusteringResult.no_clustering
+    bool clustered = false;       // kmeans_cluster_seqs was evaluated for this task
+    int n_labels = 0;             // KMeans clusters (labels 0..n_labels-1) when !no_clustering
+    std::vector<int> assign;      // label of each distinct LONG sequence, in first-seen order
+    std::vector<int> group;       // per task row: distinct ungapped sequence index (only when requested)
+    std::vector<int> ulen;        // per task row: ungapped length (only when requested)
 };
 
-static void single_cluster(const std::vector<std::vector<int>> &long_ids,
-                           const std::vector<std::vector<int>> &small_ids, ClusterOut &o) {
-    // cluster_sequences.py:237-246 / 276-285 + merge_clusters (:194-208): everything in one cluster,
-    // the first record moved to the front
-    std::vector<int> all;
-    for (auto &v : long_ids) all.insert(all.end(), v.begin(), v.end());
-    for (auto &v : small_ids) all.insert(all.end(), v.begin(), v.end());
-    auto it = std::find(all.begin(), all.end(), 0);
-    if (it != all.end()) {
-        all.erase(it);
-        all.insert(all.begin(), 0);
+// ClusteringResult.clustered_ids as task-local row positions, from the per-row groups:
+// extract_clusters (cluster_sequences.py:114-133) + one cluster per distinct small sequence +
+// merge_clusters (:194-208).  Needs o.group.
+static void clusters_from_rows(const ClusterOut &o, int kmer_size, std::vector<std::vector<int>> &out) {
+    out.clear();
+    const int R = (int)o.group.size();
+    std::vector<int> long_index(o.n_ungapped, -1), small_index(o.n_ungapped, -1);
+    int n_long = 0, n_small = 0;
+    for (int g = 0; g < o.n_ungapped; ++g) {
+        if (o.leader_len[g] >= kmer_size) long_index[g] = n_long++;
+        else small_index[g] = n_small++;
     }
-    o.no_clustering = true;
-    o.clusters.clear();
-    o.clusters.push_back(std::move(all));
+    if (o.no_clustering) {
+        // all long ids in distinct-sequence order, then all small ones; first record moved to the front
+        std::vector<std::vector<int>> lg(n_long), sg(n_small);
+        for (int r = 0; r < R; ++r) {
+            const int g = o.group[r];
+            if (long_index[g] >= 0) lg[long_index[g]].push_back(r);
+            else sg[small_index[g]].push_back(r);
+        }
+        std::vector<int> all;
+        for (auto &v : lg) all.insert(all.end(), v.begin(), v.end());
+        for (auto &v : sg) all.insert(all.end(), v.begin(), v.end());
+        auto it = std::find(all.begin(), all.end(), 0);
+        if (it != all.end()) {
+            all.erase(it);
+            all.insert(all.begin(), 0);
+        }
+        out.push_back(std::move(all));
+        return;
+    }
+    std::vector<std::vector<std::vector<int>>> per_label(o.n_labels);  // label -> long seq -> rows
+    std::vector<std::vector<int>> cl(o.n_labels + n_small);
+    // rows inside a KMeans cluster are ordered by (distinct sequence, row)
+    std::vector<std::vector<int>> lg(n_long), sg(n_small);
+    for (int r = 0; r < R; ++r) {
+        const int g = o.group[r];
+        if (long_index[g] >= 0) lg[long_index[g]].push_back(r);
+        else sg[small_index[g]].push_back(r);
+    }
+    for (int j = 0; j < n_long; ++j) cl[o.assign[j]].insert(cl[o.assign[j]].end(), lg[j].begin(), lg[j].end());
+    for (int j = 0; j < n_small; ++j) cl[o.n_labels + j] = sg[j];
+    size_t fi = 0;
+    for (size_t a = 0; a < cl.size(); ++a)
+        if (std::find(cl[a].begin(), cl[a].end(), 0) != cl[a].end()) fi = a;
+    std::vector<int> first = cl[fi];
+    first.erase(std::find(first.begin(), first.end(), 0));
+    first.insert(first.begin(), 0);
+    out.push_back(std::move(first));
+    for (size_t a = 0; a < cl.size(); ++a)
+        if (a != fi) out.push_back(std::move(cl[a]));
 }
 
-// want_clusters[t] == 0: only the de-duplication outputs are needed for task t
+// Runs kmeans_cluster_seqs for every task of a level.
+//   want_clusters[t] == 0   only the de-duplication outputs are needed
+//   want_rows[t] != 0       also return the per-row group / ungapped length (O(rows) over PCIe)
+//   rows_if_clustered       return the per-row groups of every task that ends up clustered
 static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, int n_tasks,
                          const int32_t *h_rows, long long n_row_entries, int kmer_size,
-                         const uint8_t *want_clusters, std::vector<ClusterOut> &out,
-                         bool skip_if_issues = false) {
+                         const uint8_t *want_clusters, const uint8_t *want_rows, bool rows_if_clustered,
+                         std::vector<ClusterOut> &out, bool skip_if_issues = false) {
     out.assign(n_tasks, ClusterOut());
     if (n_tasks == 0) return MPRG_OK;
     cudaSetDevice(ctx->device);
@@ -129,9 +204,9 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
     int rc = ensure_rand(ctx);
     if (rc != MPRG_OK) return rc;
 
-    // device task table (only base/stride/rows/window are used by these kernels)
     std::vector<DTask> tasks(n_tasks);
     std::vector<long long> g_off(n_tasks), row_off(n_tasks);
+    std::vector<int> h_R(n_tasks);
     long long g_total = 0, row_total = 0;
     for (int i = 0; i < n_tasks; ++i) {
         const mprg_task &ht = h_tasks[i];
@@ -150,16 +225,20 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         t.col_off = t.iv_off = t.flags = 0;
         g_off[i] = g_total;
         row_off[i] = row_total;
+        h_R[i] = ht.n_rows;
         g_total += (long long)ht.n_rows * (ht.c1 - ht.c0);
         row_total += ht.n_rows;
     }
-    DevBuf *B = ctx->d_c;  // 0 tasks, 1 g_off, 2 row_off, 3 G, 4 sig, 5 ints(leader_u|leader_g|group|ulen|nu|ng|err)
+    if (row_total > 0x7fffffffLL) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "too many rows in one clustering level");
+    DevBuf *B = ctx->d_c;
+    // 0 tasks, 1 g_off, 2 row_off, 3 G, 4 sig,
+    // 5 ints: leader_u | leader_g | group | ulen | leaders | leader_len | nu | ng | lead_off(n+1) | err | R(n)
     MPRG_CUDA(ctx, B[0].reserve(sizeof(DTask) * n_tasks));
     MPRG_CUDA(ctx, B[1].reserve(sizeof(long long) * n_tasks));
     MPRG_CUDA(ctx, B[2].reserve(sizeof(long long) * n_tasks));
     MPRG_CUDA(ctx, B[3].reserve((size_t)std::max<long long>(g_total, 1)));
     MPRG_CUDA(ctx, B[4].reserve(rowsig_bytes() * std::max<long long>(row_total, 1)));
-    const long long n_int = 4 * row_total + 2LL * n_tasks + 1;
+    const long long n_int = 6 * row_total + 4LL * n_tasks + 2;
     MPRG_CUDA(ctx, B[5].reserve(sizeof(int) * n_int));
     MPRG_CUDA(ctx, ctx->d_rows.reserve(sizeof(int) * std::max<long long>(n_row_entries, 1)));
     MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[0].p, tasks.data(), sizeof(DTask) * n_tasks, s));
@@ -171,226 +250,257 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
     int *d_leader_g = d_leader_u + row_total;
     int *d_group = d_leader_g + row_total;
     int *d_ulen = d_group + row_total;
-    int *d_nu = d_ulen + row_total;
+    int *d_leaders = d_ulen + row_total;
+    int *d_leadlen = d_leaders + row_total;
+    int *d_nu = d_leadlen + row_total;
     int *d_ng = d_nu + n_tasks;
-    int *d_err = d_ng + n_tasks;
+    int *d_leadoff = d_ng + n_tasks;  // n_tasks + 1
+    int *d_err = d_leadoff + n_tasks + 1;
+    int *d_R = d_err + 1;
     MPRG_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(int), s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_R, h_R.data(), sizeof(int) * n_tasks, s));
     MPRG_CUDA(ctx, launch_unpack(s, batch->d_packed, B[0].as<DTask>(), n_tasks, ctx->d_rows.as<int>(),
                                  B[1].as<long long>(), B[3].as<uint8_t>()));
     MPRG_CUDA(ctx, launch_dedupe(s, B[0].as<DTask>(), n_tasks, B[1].as<long long>(), B[3].as<uint8_t>(),
                                  B[2].as<long long>(), B[4].p, d_leader_u, d_leader_g, d_group, d_ulen,
-                                 d_nu, d_ng, d_err));
-    ctx->launches += 2;
-    std::vector<int> h_ints((size_t)(2 * row_total + 2LL * n_tasks + 1));
-    // group|ulen|nu|ng|err are contiguous
-    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_ints.data(), d_group, sizeof(int) * h_ints.size(), s));
+                                 d_leaders, d_leadlen, d_nu, d_ng, d_err));
+    MPRG_CUDA(ctx, launch_scan_counts(s, d_nu, n_tasks, d_leadoff));
+    ctx->launches += 3;
+    TRACE("cl: setup+launch dedupe");
+    // nu | ng | lead_off | err are contiguous: one small copy
+    std::vector<int> h_small((size_t)(3LL * n_tasks + 2));
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_small.data(), d_nu, sizeof(int) * h_small.size(), s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
-    const int *h_group = h_ints.data();
-    const int *h_ulen = h_group + row_total;
-    const int *h_nu = h_ulen + row_total;
+    const int *h_nu = h_small.data();
     const int *h_ng = h_nu + n_tasks;
-    if (h_ng[n_tasks]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while de-duplicating rows");
+    const int *h_leadoff = h_ng + n_tasks;
+    if (h_leadoff[n_tasks + 1]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while de-duplicating rows");
+    const long long lead_total = h_leadoff[n_tasks];
+    // dense leaders | leader lengths
+    MPRG_CUDA(ctx, B[6].reserve(sizeof(int) * 2 * std::max<long long>(lead_total, 1)));
+    int *d_dense = B[6].as<int>();
+    MPRG_CUDA(ctx, launch_gather2(s, B[2].as<long long>(), d_nu, d_leadoff, n_tasks, d_leaders, d_leadlen,
+                                  d_dense, d_dense + lead_total));
+    ctx->launches++;
+    MPRG_CUDA(ctx, ctx->h_a.reserve(sizeof(int) * 2 * std::max<long long>(lead_total, 1)));
+    int *h_dense = ctx->h_a.as<int>();
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_dense, d_dense, sizeof(int) * 2 * lead_total, s));
+    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    TRACE("cl: dedupe sync+D2H");
 
-    // host: long / short distinct sequences per task, trivial outcomes, KMeans problems
+    // host: distinct sequences per task, trivial outcomes, KMeans problems -- O(#distinct)
     struct Prob {
-        int task;
-        int n;
+        int task, n;
         long long P;
-        std::vector<int> leaders;               // task-local row position of each distinct long sequence
-        std::vector<std::vector<int>> long_ids; // rows of each distinct long sequence
-        std::vector<std::vector<int>> small_ids;
     };
     std::vector<Prob> probs;
+    std::vector<int> seq_rows;  // leader rows of the long sequences of every problem
     for (int i = 0; i < n_tasks; ++i) {
         ClusterOut &o = out[i];
-        const int R = h_tasks[i].n_rows;
         o.n_ungapped = h_nu[i];
         o.n_gapped = h_ng[i];
-        o.group.assign(h_group + row_off[i], h_group + row_off[i] + R);
-        o.ulen.assign(h_ulen + row_off[i], h_ulen + row_off[i] + R);
+        o.leaders.assign(h_dense + h_leadoff[i], h_dense + h_leadoff[i] + o.n_ungapped);
+        o.leader_len.assign(h_dense + lead_total + h_leadoff[i], h_dense + lead_total + h_leadoff[i] + o.n_ungapped);
         if (want_clusters && !want_clusters[i]) continue;
-        if (R == 0) continue;
+        if (h_R[i] == 0) continue;
         // NodeFactory._alignment_has_issues (recursion_tree.py:475-494) discards the clustering anyway
         if (skip_if_issues && (o.n_ungapped <= 2 || o.n_ungapped < o.n_gapped)) continue;
-        // distinct sequences in first-seen order; long ones (len >= k) keep their own numbering
-        std::vector<int> long_index(o.n_ungapped, -1), small_index(o.n_ungapped, -1);
-        Prob p;
-        p.task = i;
-        for (int r = 0; r < R; ++r) {
-            const int gidx = o.group[r];
-            if (o.ulen[r] >= kmer_size) {
-                if (long_index[gidx] < 0) {
-                    long_index[gidx] = (int)p.long_ids.size();
-                    p.long_ids.emplace_back();
-                    p.leaders.push_back(r);
-                }
-                p.long_ids[long_index[gidx]].push_back(r);
-            } else {
-                if (small_index[gidx] < 0) {
-                    small_index[gidx] = (int)p.small_ids.size();
-                    p.small_ids.emplace_back();
-                }
-                p.small_ids[small_index[gidx]].push_back(r);
+        o.clustered = true;
+        int n = 0;
+        long long P = 0;
+        for (int g = 0; g < o.n_ungapped; ++g)
+            if (o.leader_len[g] >= kmer_size) {
+                ++n;
+                P += o.leader_len[g] - kmer_size + 1;
             }
-        }
-        p.n = (int)p.long_ids.size();
-        if (p.n <= 2) {
-            single_cluster(p.long_ids, p.small_ids, o);
-            continue;
-        }
-        p.P = 0;
-        for (int r : p.leaders) p.P += o.ulen[r] - kmer_size + 1;
-        probs.push_back(std::move(p));
+        if (n <= 2) continue;  // too few sequences: single cluster (no_clustering stays true)
+        probs.push_back(Prob{i, n, P});
     }
     const int np = (int)probs.size();
-    if (np == 0) return MPRG_OK;
+    TRACE("cl: host grouping");
 
-    // ---- k-mer count matrices ----
-    std::vector<KmerProb> kp(np);
-    std::vector<int> seq_rows, mem_off, mem_rows;
-    long long useq_total = 0, ints_total = 0, tab_total = 0, x_total = 0;
     std::vector<ClusterState> st(np);
-    long long maj_total = 0, assign_total = 0;
-    for (int q = 0; q < np; ++q) {
-        const Prob &p = probs[q];
-        const mprg_task &ht = h_tasks[p.task];
-        const int w = ht.c1 - ht.c0;
-        if (p.P > 0x3fffffffLL) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "clustering problem too large");
-        KmerProb &k = kp[q];
-        k.g_off = g_off[p.task];
-        k.w = w;
-        k.n = p.n;
-        k.seq_off = (int)seq_rows.size();
-        seq_rows.insert(seq_rows.end(), p.leaders.begin(), p.leaders.end());
-        k.useq_off = useq_total;
-        useq_total += (long long)p.n * w;
-        k.pos_off = ints_total;
-        ints_total += 2LL * p.n + 1 + 2 * p.P;
-        int T = 64;
-        while (T < 2 * p.P) T <<= 1;
-        k.T = T;
-        k.tab_off = tab_total;
-        tab_total += T;
-        k.Pmax = (int)p.P;
-        k.x_off = x_total;
-        x_total += (long long)p.n * p.P;
-        ClusterState &c = st[q];
-        memset(&c, 0, sizeof(c));
-        c.K = 1;
-        c.n = p.n;
-        c.w = w;
-        c.g_off = g_off[p.task];
-        c.mem_off = (int)mem_off.size();
-        c.mem_rows_off = (int)mem_rows.size();
-        int acc = 0;
-        for (auto &v : p.long_ids) {
-            mem_off.push_back(acc);
-            acc += (int)v.size();
-            mem_rows.insert(mem_rows.end(), v.begin(), v.end());
+    std::vector<int> h_assign;
+    if (np > 0) {
+        // ---- member lists + k-mer count matrices ----
+        std::vector<KmerProb> kp(np);
+        std::vector<MemberProb> mp(np);
+        long long useq_total = 0, ints_total = 0, tab_total = 0, x_total = 0;
+        long long maj_total = 0, assign_total = 0, memoff_total = 0, memrows_total = 0;
+        for (int q = 0; q < np; ++q) {
+            const Prob &p = probs[q];
+            const mprg_task &ht = h_tasks[p.task];
+            const ClusterOut &o = out[p.task];
+            const int w = ht.c1 - ht.c0;
+            if (p.P > 0x3fffffffLL) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "clustering problem too large");
+            KmerProb &k = kp[q];
+            k.g_off = g_off[p.task];
+            k.w = w;
+            k.n = p.n;
+            k.seq_off = (int)seq_rows.size();
+            for (int g = 0; g < o.n_ungapped; ++g)
+                if (o.leader_len[g] >= kmer_size) seq_rows.push_back(o.leaders[g]);
+            k.useq_off = useq_total;
+            useq_total += (long long)p.n * w;
+            k.pos_off = ints_total;
+            ints_total += 2LL * p.n + 1 + 2 * p.P;
+            int T = 64;
+            while (T < 2 * p.P) T <<= 1;
+            k.T = T;
+            k.tab_off = tab_total;
+            tab_total += T;
+            k.Pmax = (int)p.P;
+            k.x_off = x_total;
+            x_total += (long long)p.n * p.P;
+            MemberProb &m = mp[q];
+            m.row_off = row_off[p.task];
+            m.R = ht.n_rows;
+            m.n_groups = o.n_ungapped;
+            m.k = kmer_size;
+            m.mem_off = (int)memoff_total;
+            m.mem_rows_off = (int)memrows_total;
+            ClusterState &c = st[q];
+            memset(&c, 0, sizeof(c));
+            c.K = 1;
+            c.n = p.n;
+            c.w = w;
+            c.g_off = g_off[p.task];
+            c.mem_off = m.mem_off;
+            c.mem_rows_off = m.mem_rows_off;
+            memoff_total += p.n + 1;
+            memrows_total += ht.n_rows;
+            c.assign_off = (int)assign_total;
+            assign_total += p.n;
+            c.maj_off = maj_total;
+            maj_total += w;
+            c.x_off = k.x_off;
         }
-        mem_off.push_back(acc);
-        c.assign_off = (int)assign_total;
-        assign_total += p.n;
-        c.maj_off = maj_total;
-        maj_total += w;
-        c.x_off = k.x_off;
-    }
-    if (x_total * 8 > (24LL << 30)) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "k-mer count matrices exceed the 24 GiB scratch budget");
-    // 6 kprobs, 7 seq_rows, 8 useq, 9 ints, 10 keys, 11 ming, 12 X, 13 states|F, 14 mem|assign|newlab|maj, 15 kmeans scratch
-    MPRG_CUDA(ctx, B[6].reserve(sizeof(KmerProb) * np));
-    MPRG_CUDA(ctx, B[7].reserve(sizeof(int) * seq_rows.size()));
-    MPRG_CUDA(ctx, B[8].reserve((size_t)useq_total));
-    MPRG_CUDA(ctx, B[9].reserve(sizeof(int) * ints_total));
-    MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * tab_total));
-    MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * tab_total));
-    MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * x_total));
-    MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * np + 64));
-    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[6].p, kp.data(), sizeof(KmerProb) * np, s));
-    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[7].p, seq_rows.data(), sizeof(int) * seq_rows.size(), s));
-    ClusterState *d_states = B[13].as<ClusterState>();
-    int *d_F = reinterpret_cast<int *>(d_states + np);
-    MPRG_CUDA(ctx, launch_kmer(s, B[6].p, np, B[7].as<int>(), B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
-                               B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), B[12].as<double>(), d_F,
-                               d_err));
-    ctx->launches++;
-    std::vector<int> h_F(np + 1);
-    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_F.data(), d_F, sizeof(int) * np, s));
-    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &h_F[np], d_err, sizeof(int), s));
-    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
-    if (h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
-
-    // ---- KMeans loop (cluster_sequences.py:256-274) ----
-    long long kmd_total = 0, kmi_total = 0;
-    for (int q = 0; q < np; ++q) {
-        st[q].F = h_F[q];
-        st[q].kmd_off = kmd_total;
-        st[q].kmi_off = kmi_total;
-        kmd_total += kmeans_dscratch_doubles(st[q].n, st[q].F);
-        kmi_total += kmeans_iscratch_ints(st[q].n);
-    }
-    const size_t o_memoff = 0;
-    const size_t o_memrows = o_memoff + sizeof(int) * mem_off.size();
-    const size_t o_assign = o_memrows + sizeof(int) * mem_rows.size();
-    const size_t o_newlab = o_assign + sizeof(int) * assign_total;
-    const size_t o_maj = o_newlab + sizeof(int) * assign_total;
-    MPRG_CUDA(ctx, B[14].reserve(o_maj + (size_t)maj_total + 16));
-    MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * kmd_total + sizeof(int) * kmi_total + 64));
-    uint8_t *b14 = B[14].as<uint8_t>();
-    int *d_memoff = reinterpret_cast<int *>(b14 + o_memoff);
-    int *d_memrows = reinterpret_cast<int *>(b14 + o_memrows);
-    int *d_assign = reinterpret_cast<int *>(b14 + o_assign);
-    int *d_newlab = reinterpret_cast<int *>(b14 + o_newlab);
-    uint8_t *d_maj = b14 + o_maj;
-    double *d_kmd = B[15].as<double>();
-    int *d_kmi = reinterpret_cast<int *>(d_kmd + kmd_total);
-    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_states, st.data(), sizeof(ClusterState) * np, s));
-    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_memoff, mem_off.data(), sizeof(int) * mem_off.size(), s));
-    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_memrows, mem_rows.data(), sizeof(int) * mem_rows.size(), s));
-    MPRG_CUDA(ctx, cudaMemsetAsync(d_assign, 0, sizeof(int) * assign_total, s));
-    const int MAX_CLUSTERS = 10;
-    MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
-    ctx->launches++;
-    for (int round = 2; round <= MAX_CLUSTERS; ++round) {
-        MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab));
-        MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
+        if (x_total * 8 > (24LL << 30)) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "k-mer count matrices exceed the 24 GiB scratch budget");
+        // 7 kprobs|mprobs, 8 useq, 9 ints, 10 keys, 11 ming, 12 X, 13 states|F, 14 seq_rows|mem|assign|newlab|maj, 15 kmeans scratch
+        MPRG_CUDA(ctx, B[7].reserve(sizeof(KmerProb) * np + sizeof(MemberProb) * np));
+        MPRG_CUDA(ctx, B[8].reserve((size_t)useq_total));
+        MPRG_CUDA(ctx, B[9].reserve(sizeof(int) * ints_total));
+        MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * tab_total));
+        MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * tab_total));
+        MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * x_total));
+        MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * np + 64));
+        const size_t o_seqrows = 0;
+        const size_t o_memoff = o_seqrows + sizeof(int) * seq_rows.size();
+        const size_t o_memrows = o_memoff + sizeof(int) * memoff_total;
+        const size_t o_assign = o_memrows + sizeof(int) * memrows_total;
+        const size_t o_newlab = o_assign + sizeof(int) * assign_total;
+        const size_t o_maj = o_newlab + sizeof(int) * assign_total;
+        MPRG_CUDA(ctx, B[14].reserve(o_maj + (size_t)maj_total + 16));
+        uint8_t *b14 = B[14].as<uint8_t>();
+        int *d_seqrows = reinterpret_cast<int *>(b14 + o_seqrows);
+        int *d_memoff = reinterpret_cast<int *>(b14 + o_memoff);
+        int *d_memrows = reinterpret_cast<int *>(b14 + o_memrows);
+        int *d_assign = reinterpret_cast<int *>(b14 + o_assign);
+        int *d_newlab = reinterpret_cast<int *>(b14 + o_newlab);
+        uint8_t *d_maj = b14 + o_maj;
+        KmerProb *d_kp = B[7].as<KmerProb>();
+        MemberProb *d_mp = reinterpret_cast<MemberProb *>(d_kp + np);
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_kp, kp.data(), sizeof(KmerProb) * np, s));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_mp, mp.data(), sizeof(MemberProb) * np, s));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_seqrows, seq_rows.data(), sizeof(int) * seq_rows.size(), s));
+        ClusterState *d_states = B[13].as<ClusterState>();
+        int *d_F = reinterpret_cast<int *>(d_states + np);
+        // d_leader_u is free after dedupe: scratch for the group -> long-sequence map
+        MPRG_CUDA(ctx, launch_members(s, d_mp, np, d_group, d_leadlen, d_leader_u, d_memoff, d_memrows));
+        MPRG_CUDA(ctx, launch_kmer(s, d_kp, np, d_seqrows, B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
+                                   B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), B[12].as<double>(), d_F,
+                                   d_err));
         ctx->launches += 2;
-    }
-    std::vector<int> h_assign((size_t)assign_total);
-    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, st.data(), d_states, sizeof(ClusterState) * np, s));
-    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_assign.data(), d_assign, sizeof(int) * assign_total, s));
-    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        std::vector<int> h_F(np + 1);
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_F.data(), d_F, sizeof(int) * np, s));
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &h_F[np], d_err, sizeof(int), s));
+        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        if (h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
+        TRACE("cl: kmer setup+run+sync");
 
-    for (int q = 0; q < np; ++q) {
-        const Prob &p = probs[q];
-        ClusterOut &o = out[p.task];
-        const ClusterState &c = st[q];
-        if (c.status != 1) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "clustering loop did not terminate");
-        const int K = c.K;
-        if (K == 1 || K == p.n) {
-            single_cluster(p.long_ids, p.small_ids, o);
-            continue;
+        // ---- KMeans loop (cluster_sequences.py:256-274) ----
+        long long kmd_total = 0, kmi_total = 0;
+        for (int q = 0; q < np; ++q) {
+            st[q].F = h_F[q];
+            st[q].kmd_off = kmd_total;
+            st[q].kmi_off = kmi_total;
+            kmd_total += kmeans_dscratch_doubles(st[q].n, st[q].F);
+            kmi_total += kmeans_iscratch_ints(st[q].n);
         }
-        const int *assign = h_assign.data() + c.assign_off;
-        const int n_lab = std::min(K, MAX_CLUSTERS);  // K == 11 keeps the 10-cluster assignment
-        std::vector<std::vector<int>> cl(n_lab);
-        for (int j = 0; j < p.n; ++j) {
-            if (assign[j] < 0 || assign[j] >= n_lab) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "label out of range");
-            cl[assign[j]].insert(cl[assign[j]].end(), p.long_ids[j].begin(), p.long_ids[j].end());
+        MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * kmd_total + sizeof(int) * kmi_total + 64));
+        double *d_kmd = B[15].as<double>();
+        int *d_kmi = reinterpret_cast<int *>(d_kmd + kmd_total);
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_states, st.data(), sizeof(ClusterState) * np, s));
+        MPRG_CUDA(ctx, cudaMemsetAsync(d_assign, 0, sizeof(int) * assign_total, s));
+        const int MAX_CLUSTERS = 10;
+        MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
+        ctx->launches++;
+        for (int round = 2; round <= MAX_CLUSTERS; ++round) {
+            MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab));
+            MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
+            ctx->launches += 2;
         }
-        for (auto &v : p.small_ids) cl.push_back(v);
-        // merge_clusters: the cluster holding the first record goes first, that record first in it
-        size_t fi = 0;
-        for (size_t a = 0; a < cl.size(); ++a)
-            if (std::find(cl[a].begin(), cl[a].end(), 0) != cl[a].end()) fi = a;
-        std::vector<int> first = cl[fi];
-        first.erase(std::find(first.begin(), first.end(), 0));
-        first.insert(first.begin(), 0);
-        o.clusters.clear();
-        o.clusters.push_back(std::move(first));
-        for (size_t a = 0; a < cl.size(); ++a)
-            if (a != fi) o.clusters.push_back(std::move(cl[a]));
-        o.no_clustering = o.clusters.size() == 1;
+        h_assign.resize((size_t)assign_total);
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, st.data(), d_states, sizeof(ClusterState) * np, s));
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_assign.data(), d_assign, sizeof(int) * assign_total, s));
+        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        TRACE("cl: kmeans loop+sync");
+        for (int q = 0; q < np; ++q) {
+            const Prob &p = probs[q];
+            ClusterOut &o = out[p.task];
+            const ClusterState &c = st[q];
+            if (c.status != 1) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "clustering loop did not terminate");
+            const int K = c.K;
+            if (K == 1 || K == p.n) continue;  // no_clustering (cluster_sequences.py:276)
+            o.no_clustering = false;
+            o.n_labels = std::min(K, MAX_CLUSTERS);  // K == 11 keeps the 10-cluster assignment
+            o.assign.assign(h_assign.begin() + c.assign_off, h_assign.begin() + c.assign_off + p.n);
+            for (int a : o.assign)
+                if (a < 0 || a >= o.n_labels) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "label out of range");
+        }
     }
+    // a task that is clustered but has small sequences only next to <= 2 long ones keeps no_clustering;
+    // clusters made only of small-sequence groups are not produced by the reference in that branch
+
+    // ---- per-row groups for the tasks that need them ----
+    std::vector<int> need;
+    for (int i = 0; i < n_tasks; ++i) {
+        const bool w = (want_rows && want_rows[i]) || (rows_if_clustered && out[i].clustered && !out[i].no_clustering);
+        if (w && h_R[i] > 0) need.push_back(i);
+    }
+    if (!need.empty()) {
+        const int nn = (int)need.size();
+        std::vector<long long> src(nn);
+        std::vector<int> cnt(nn), dst(nn);
+        long long total = 0;
+        for (int q = 0; q < nn; ++q) {
+            src[q] = row_off[need[q]];
+            cnt[q] = h_R[need[q]];
+            dst[q] = (int)total;
+            total += cnt[q];
+        }
+        MPRG_CUDA(ctx, B[6].reserve(sizeof(int) * 2 * total + sizeof(long long) * nn + sizeof(int) * 2 * nn + 64));
+        uint8_t *b6 = B[6].as<uint8_t>();
+        long long *d_src = reinterpret_cast<long long *>(b6);
+        int *d_cnt = reinterpret_cast<int *>(d_src + nn);
+        int *d_dst = d_cnt + nn;
+        int *d_out = d_dst + nn + ((nn & 1) ? 1 : 0);
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_src, src.data(), sizeof(long long) * nn, s));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_cnt, cnt.data(), sizeof(int) * nn, s));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_dst, dst.data(), sizeof(int) * nn, s));
+        MPRG_CUDA(ctx, launch_gather2(s, d_src, d_cnt, d_dst, nn, d_group, d_ulen, d_out, d_out + total));
+        ctx->launches++;
+        MPRG_CUDA(ctx, ctx->h_b.reserve(sizeof(int) * 2 * total));
+        int *h_out = ctx->h_b.as<int>();
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_out, d_out, sizeof(int) * 2 * total, s));
+        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        for (int q = 0; q < nn; ++q) {
+            ClusterOut &o = out[need[q]];
+            o.group.assign(h_out + dst[q], h_out + dst[q] + cnt[q]);
+            o.ulen.assign(h_out + total + dst[q], h_out + total + dst[q] + cnt[q]);
+        }
+    }
+    TRACE("cl: rows D2H");
     return MPRG_OK;
 }
 
@@ -405,8 +515,9 @@ extern "C" int mprg_dedupe_rows(mprg_ctx *ctx, const mprg_batch *batch, const mp
                                 int32_t *h_n_ungapped, int32_t *h_n_gapped) {
     if (!ctx || !batch || n_tasks < 0 || (n_tasks > 0 && (!h_tasks || !h_row_offsets))) return MPRG_E_BAD_ARG;
     std::vector<ClusterOut> out;
-    std::vector<uint8_t> want(std::max(n_tasks, 1), 0);
-    int rc = cluster_level(ctx, batch, h_tasks, n_tasks, h_rows, n_row_entries, 1, want.data(), out);
+    std::vector<uint8_t> want(std::max(n_tasks, 1), 0), rows(std::max(n_tasks, 1), 1);
+    int rc = cluster_level(ctx, batch, h_tasks, n_tasks, h_rows, n_row_entries, 1, want.data(), rows.data(),
+                           false, out);
     if (rc != MPRG_OK) return rc;
     for (int i = 0; i < n_tasks; ++i) {
         const int R = h_tasks[i].n_rows;
@@ -426,12 +537,20 @@ extern "C" int mprg_cluster_tasks(mprg_ctx *ctx, const mprg_batch *batch, const 
         (n_tasks > 0 && (!h_tasks || !h_row_offsets || !h_cluster || !h_n_clusters)))
         return MPRG_E_BAD_ARG;
     std::vector<ClusterOut> out;
-    int rc = cluster_level(ctx, batch, h_tasks, n_tasks, h_rows, n_row_entries, kmer_size, nullptr, out);
+    std::vector<uint8_t> rows(std::max(n_tasks, 1), 1);
+    int rc = cluster_level(ctx, batch, h_tasks, n_tasks, h_rows, n_row_entries, kmer_size, nullptr, rows.data(),
+                           false, out);
     if (rc != MPRG_OK) return rc;
+    std::vector<std::vector<int>> clusters;
     for (int i = 0; i < n_tasks; ++i) {
-        h_n_clusters[i] = (int)out[i].clusters.size();
-        for (size_t c = 0; c < out[i].clusters.size(); ++c)
-            for (int r : out[i].clusters[c]) h_cluster[h_row_offsets[i] + r] = (int)c;
+        if (h_tasks[i].n_rows == 0) {
+            h_n_clusters[i] = 0;
+            continue;
+        }
+        clusters_from_rows(out[i], kmer_size, clusters);
+        h_n_clusters[i] = (int)clusters.size();
+        for (size_t c = 0; c < clusters.size(); ++c)
+            for (int r : clusters[c]) h_cluster[h_row_offsets[i] + r] = (int)c;
     }
     return MPRG_OK;
 }
@@ -470,19 +589,17 @@ extern "C" int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mp
     uint8_t want = 0;
     mprg_task t = *h_task;
     const long long n_row_entries = t.rows_off >= 0 ? (long long)t.rows_off + t.n_rows : 0;
-    int rc = cluster_level(ctx, batch, &t, 1, h_rows, n_row_entries, kmer_size, &want, out);
+    int rc = cluster_level(ctx, batch, &t, 1, h_rows, n_row_entries, kmer_size, &want, nullptr, false, out);
     if (rc != MPRG_OK) return rc;
     cudaStream_t s = ctx->stream;
     DevBuf *B = ctx->d_c;
     const ClusterOut &o = out[0];
     std::vector<int> leaders;
-    std::vector<char> seen(o.n_ungapped, 0);
     long long P = 0;
-    for (int r = 0; r < t.n_rows; ++r)
-        if (o.ulen[r] >= kmer_size && !seen[o.group[r]]) {
-            seen[o.group[r]] = 1;
-            leaders.push_back(r);
-            P += o.ulen[r] - kmer_size + 1;
+    for (int g = 0; g < o.n_ungapped; ++g)
+        if (o.leader_len[g] >= kmer_size) {
+            leaders.push_back(o.leaders[g]);
+            P += o.leader_len[g] - kmer_size + 1;
         }
     const int n = (int)leaders.size();
     *n_seqs = n;
@@ -503,8 +620,8 @@ extern "C" int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mp
     k.T = T;
     k.Pmax = (int)P;
     k.x_off = 0;
-    MPRG_CUDA(ctx, B[6].reserve(sizeof(KmerProb)));
-    MPRG_CUDA(ctx, B[7].reserve(sizeof(int) * n));
+    MPRG_CUDA(ctx, B[7].reserve(sizeof(KmerProb)));
+    MPRG_CUDA(ctx, B[14].reserve(sizeof(int) * n));
     MPRG_CUDA(ctx, B[8].reserve((size_t)n * w + 1));
     MPRG_CUDA(ctx, B[9].reserve(sizeof(int) * (2LL * n + 1 + 2 * P)));
     MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * T));
@@ -513,9 +630,9 @@ extern "C" int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mp
     MPRG_CUDA(ctx, B[13].reserve(sizeof(int) * 2));
     int *d_F = B[13].as<int>();
     MPRG_CUDA(ctx, cudaMemsetAsync(d_F, 0, sizeof(int) * 2, s));
-    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[6].p, &k, sizeof(k), s));
-    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[7].p, leaders.data(), sizeof(int) * n, s));
-    MPRG_CUDA(ctx, launch_kmer(s, B[6].p, 1, B[7].as<int>(), B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[7].p, &k, sizeof(k), s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[14].p, leaders.data(), sizeof(int) * n, s));
+    MPRG_CUDA(ctx, launch_kmer(s, B[7].p, 1, B[14].as<int>(), B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
                                B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), B[12].as<double>(), d_F,
                                d_F + 1));
     ctx->launches++;
@@ -540,7 +657,7 @@ extern "C" int mprg_one_ref_like(mprg_ctx *ctx, const mprg_batch *batch, const m
     uint8_t want = 0;
     mprg_task t = *h_task;
     const long long n_row_entries = t.rows_off >= 0 ? (long long)t.rows_off + t.n_rows : 0;
-    int rc = cluster_level(ctx, batch, &t, 1, h_rows, n_row_entries, 1, &want, out);
+    int rc = cluster_level(ctx, batch, &t, 1, h_rows, n_row_entries, 1, &want, nullptr, false, out);
     if (rc != MPRG_OK) return rc;
     cudaStream_t s = ctx->stream;
     DevBuf *B = ctx->d_c;
@@ -701,8 +818,8 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
 
     std::vector<mprg_task> tasks;
     std::vector<int32_t> arena;
-    std::vector<DInterval> iv;
-    std::vector<int> cnt;
+    PhaseTrace trace;
+    g_trace = trace.on ? &trace : nullptr;
     while (!pending.empty()) {
         const int nt = (int)pending.size();
         tasks.resize(nt);
@@ -727,19 +844,26 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
                              L.row_pool.begin() + nd.row_off + nd.n_rows);
             }
         }
+        TRACE("build: task table");
         Level lv;
         int rc = level_run(ctx, batch, tasks.data(), nt, arena.data(), (long long)arena.size(),
                            min_match_length, true, lv);
         if (rc != MPRG_OK) return fail(rc);
-        iv.resize((size_t)lv.total_iv);
-        cnt.resize(nt + 1);
+        TRACE("build: level_run (host+launch)");
         cudaError_t e;
-        if ((e = mprg::copy_d2h(ctx, iv.data(), ctx->d_iv.p, sizeof(DInterval) * iv.size(), s)) != cudaSuccess ||
-            (e = mprg::copy_d2h(ctx, cnt.data(), ctx->d_ivcnt.p, sizeof(int) * cnt.size(), s)) != cudaSuccess ||
+        if ((e = ctx->h_d.reserve(sizeof(DInterval) * (size_t)lv.total_iv + sizeof(int) * (nt + 1))) != cudaSuccess) {
+            ctx->err = std::string("pinned alloc: ") + cudaGetErrorString(e);
+            return fail(MPRG_E_CUDA);
+        }
+        DInterval *iv = ctx->h_d.as<DInterval>();
+        int *cnt = reinterpret_cast<int *>(iv + lv.total_iv);
+        if ((e = mprg::copy_d2h(ctx, iv, ctx->d_iv.p, sizeof(DInterval) * (size_t)lv.total_iv, s)) != cudaSuccess ||
+            (e = mprg::copy_d2h(ctx, cnt, ctx->d_ivcnt.p, sizeof(int) * (nt + 1), s)) != cudaSuccess ||
             (e = cudaStreamSynchronize(s)) != cudaSuccess) {
             ctx->err = std::string("level D2H: ") + cudaGetErrorString(e);
             return fail(MPRG_E_CUDA);
         }
+        TRACE("build: level sync+D2H");
         account_scan(ctx, lv);
         if (cnt[nt]) {
             ctx->err = "Failed interval partitioning";
@@ -751,7 +875,7 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
             const int l = pending[i].locus;
             LocusResult &L = res->loci[l];
             const int ni = pending[i].node;
-            const DInterval *ivs = iv.data() + lv.tasks[i].iv_off;
+            const DInterval *ivs = iv + lv.tasks[i].iv_off;
             const int c = cnt[i];
             const bool is_root = L.nodes[ni].parent < 0;
             if (c == 1 && ivs[0].type != MPRG_IV_NONMATCH) {
@@ -781,6 +905,7 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
                 cluster_idx.push_back(i);
             }
         }
+        TRACE("build: host nodes");
         if (!cluster_idx.empty()) {
             const int nc = (int)cluster_idx.size();
             std::vector<mprg_task> ctasks(nc);
@@ -793,25 +918,26 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
             }
             std::vector<ClusterOut> cout_;
             rc = cluster_level(ctx, batch, ctasks.data(), nc, arena.data(), (long long)arena.size(),
-                               min_match_length, want.data(), cout_, true);
+                               min_match_length, want.data(), nullptr, true, cout_, true);
             if (rc != MPRG_OK) return fail(rc);
+            TRACE("cl: finalize");
+            std::vector<std::vector<int>> clusters;
             for (int q = 0; q < nc; ++q) {
                 const int i = cluster_idx[q];
                 const int l = pending[i].locus, ni = pending[i].node;
                 LocusResult &L = res->loci[l];
                 const ClusterOut &o = cout_[q];
                 const bool has_issues = o.n_ungapped <= 2 || o.n_ungapped < o.n_gapped;
-                const bool further = want[q] && !has_issues && !o.no_clustering && !o.clusters.empty();
-                const int R = L.nodes[ni].n_rows;
+                const bool further = want[q] && !has_issues && o.clustered && !o.no_clustering;
                 auto row_id = [&](int pos) {
                     const HNode &nd = L.nodes[ni];
                     return nd.row_off < 0 ? pos : L.row_pool[nd.row_off + pos];
                 };
                 if (further) {
+                    clusters_from_rows(o, min_match_length, clusters);
                     L.nodes[ni].kind = MPRG_NODE_CLUSTER;
                     L.nodes[ni].level += 1;
-                    for (const std::vector<int> &cl : o.clusters) {
-                        std::vector<int> pos(cl);
+                    for (std::vector<int> &pos : clusters) {
                         std::sort(pos.begin(), pos.end());  // sub-alignments keep the input row order
                         HNode ch;
                         ch.parent = ni;
@@ -831,16 +957,13 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
                     HNode &nd = L.nodes[ni];
                     nd.kind = MPRG_NODE_LEAF;
                     nd.allele_first = (int)alleles.size();
-                    std::vector<char> seen(o.n_ungapped, 0);
-                    for (int r = 0; r < R; ++r)
-                        if (!seen[o.group[r]]) {
-                            seen[o.group[r]] = 1;
-                            alleles.push_back(Allele{l, row_id(r), nd.c0, nd.c1});
-                        }
-                    nd.allele_count = (int)alleles.size() - nd.allele_first;
+                    for (int g = 0; g < o.n_ungapped; ++g)
+                        alleles.push_back(Allele{l, row_id(o.leaders[g]), nd.c0, nd.c1});
+                    nd.allele_count = o.n_ungapped;
                 }
             }
         }
+        TRACE("build: host cluster nodes");
         pending.swap(next);
     }
 
@@ -853,8 +976,15 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
         items[a] = ExtractItem{batch->base[al.locus], batch->stride[al.locus], al.row, al.c0, al.c1, out_total};
         out_total += al.c1 - al.c0;
     }
-    std::vector<uint8_t> h_out((size_t)std::max<long long>(out_total, 1));
-    std::vector<int> h_len(std::max(na, 1));
+    {
+        cudaError_t e1 = ctx->h_c.reserve((size_t)std::max<long long>(out_total, 1) + sizeof(int) * (size_t)std::max(na, 1) + 16);
+        if (e1 != cudaSuccess) {
+            ctx->err = std::string("pinned alloc: ") + cudaGetErrorString(e1);
+            return fail(MPRG_E_CUDA);
+        }
+    }
+    int *h_len = ctx->h_c.as<int>();
+    uint8_t *h_out = reinterpret_cast<uint8_t *>(h_len + std::max(na, 1));
     if (na > 0) {
         DevBuf *B = ctx->d_c;
         cudaError_t e;
@@ -869,19 +999,21 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
                                                     B[5].as<int>());
         ctx->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess ||
-            (e = mprg::copy_d2h(ctx, h_out.data(), B[3].p, (size_t)out_total, s)) != cudaSuccess ||
-            (e = mprg::copy_d2h(ctx, h_len.data(), B[5].p, sizeof(int) * na, s)) != cudaSuccess ||
+            (e = mprg::copy_d2h(ctx, h_out, B[3].p, (size_t)out_total, s)) != cudaSuccess ||
+            (e = mprg::copy_d2h(ctx, h_len, B[5].p, sizeof(int) * na, s)) != cudaSuccess ||
             (e = cudaStreamSynchronize(s)) != cudaSuccess) {
             ctx->err = std::string("extract: ") + cudaGetErrorString(e);
             return fail(MPRG_E_CUDA);
         }
     }
 
+    TRACE("build: allele extraction");
     // ---- pre-order numbering and PRG strings (recursion_tree.py:194-300, prg_builder.py:100-110) ----
     std::vector<std::string> raw, expanded;
     for (int l = 0; l < n_loci; ++l) {
         LocusResult &L = res->loci[l];
         if (L.status != MPRG_LOCUS_OK) continue;
+        L.prg.reserve((size_t)batch->n_cols[l] * 2 + 64);
         int site = 5;
         struct Frame {
             int node;
@@ -900,11 +1032,30 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
             HNode &nd = L.nodes[f.node];
             if (f.next_child == 0) {
                 L.preorder.push_back(f.node);
+                if (nd.kind == MPRG_NODE_LEAF && !(batch->flags[l] & 4)) {
+                    // no RYKMSW anywhere in the locus: the distinct ungapped rows are the alleles
+                    if (nd.allele_count == 1) {
+                        const ExtractItem &it = items[nd.allele_first];
+                        L.prg.append(reinterpret_cast<const char *>(h_out + it.out_off), (size_t)h_len[nd.allele_first]);
+                    } else {
+                        const int sn = site;
+                        site += 2;
+                        emit_marker(sn);
+                        for (int a = 0; a < nd.allele_count; ++a) {
+                            const ExtractItem &it = items[nd.allele_first + a];
+                            L.prg.append(reinterpret_cast<const char *>(h_out + it.out_off),
+                                         (size_t)h_len[nd.allele_first + a]);
+                            emit_marker(a + 1 < nd.allele_count ? sn + 1 : sn);
+                        }
+                    }
+                    stack.pop_back();
+                    continue;
+                }
                 if (nd.kind == MPRG_NODE_LEAF) {
                     raw.clear();
                     for (int a = 0; a < nd.allele_count; ++a) {
                         const ExtractItem &it = items[nd.allele_first + a];
-                        raw.emplace_back(reinterpret_cast<const char *>(h_out.data() + it.out_off),
+                        raw.emplace_back(reinterpret_cast<const char *>(h_out + it.out_off),
                                          (size_t)h_len[nd.allele_first + a]);
                     }
                     if (!expand_sequences(raw, expanded)) {
@@ -948,6 +1099,9 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
             L.preorder.clear();
         }
     }
+    TRACE("build: prg strings");
+    trace.report("mprg_build");
+    g_trace = nullptr;
     *out_res = res;
     return MPRG_OK;
 }

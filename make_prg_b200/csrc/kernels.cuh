@@ -77,8 +77,22 @@ cudaError_t launch_unpack(cudaStream_t s, const uint8_t *packed, const DTask *d_
                           const int *d_rows, const long long *g_off, uint8_t *G);
 cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, const long long *g_off,
                           const uint8_t *G, const long long *row_off, void *sig, int *leader_u,
-                          int *leader_g, int *group, int *ulen, int *n_ungapped, int *n_gapped,
-                          int *err);
+                          int *leader_g, int *group, int *ulen, int *leaders, int *leader_len,
+                          int *n_ungapped, int *n_gapped, int *err);
+// member lists (rows of each distinct long sequence) of one clustering problem
+struct MemberProb {
+    long long row_off;  // per-row arrays of the task
+    int R;              // rows of the task
+    int n_groups;       // distinct ungapped sequences of the task
+    int k;              // kmer size: sequences shorter than k are "small"
+    int mem_off;        // n + 1 ints
+    int mem_rows_off;   // up to R ints
+};
+cudaError_t launch_scan_counts(cudaStream_t s, const int *counts, int n, int *offs);
+cudaError_t launch_gather2(cudaStream_t s, const long long *src_off, const int *counts, const int *dst_off,
+                           int n, const int *src_a, const int *src_b, int *dst_a, int *dst_b);
+cudaError_t launch_members(cudaStream_t s, const MemberProb *probs, int n, const int *group,
+                           const int *leader_len, int *long_of_group, int *mem_off, int *mem_rows);
 size_t rowsig_bytes();
 cudaError_t launch_kmer(cudaStream_t s, const void *d_probs, int n_probs, const int *seq_rows,
                         const uint8_t *G, int k, uint8_t *useq, int *ints, uint64_t *keys, int *ming,

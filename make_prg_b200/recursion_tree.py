@@ -1,0 +1,185 @@
+"""Recursion-tree node classes with the reference's fields and PRG framing
+(make_prg/recursion_tree.py:27-391).  Trees are not grown by Python recursion: NodeFactory.build sends
+the alignment through the level-synchronous engine and materialises the nodes from its pre-order node
+table (node ids are the pre-order positions, as in the reference where ids are handed out in the
+constructor before the children are built)."""
+from abc import ABC, abstractmethod
+from typing import List, Optional
+
+import numpy as np
+
+from . import engine
+from ._lib import NODE_CLUSTER, NODE_INTERVAL, NODE_LEAF
+from .msa import MSA
+from .utils.seq_utils import SequenceExpander, remove_columns_full_of_gaps_from_MSA
+
+
+def equal_msas(msa_1, msa_2):
+    return format(msa_1, "fasta") == format(msa_2, "fasta")
+
+
+class RecursiveTreeNode(ABC):
+    def __init__(self, nesting_level, alignment, parent, prg_builder, node_id):
+        self.nesting_level = nesting_level
+        self.alignment = remove_columns_full_of_gaps_from_MSA(alignment)
+        self.parent = parent
+        self.prg_builder = prg_builder
+        self._node_id = node_id
+        self._children: List["RecursiveTreeNode"] = []
+
+    @property
+    def node_id(self):
+        return self._node_id
+
+    @property
+    def children(self):
+        return self._children
+
+    def is_leaf(self):
+        return len(self.children) == 0
+
+    def is_root(self):
+        return self.parent is None
+
+    def replace_child(self, old_child, new_child):
+        assert old_child in self.children, f"Failure to replace a child, {old_child} does not exist"
+        self.children[self.children.index(old_child)] = new_child
+
+    def __eq__(self, other):
+        if (self.nesting_level, self.prg_builder.locus_name, self.node_id) != (
+                other.nesting_level, other.prg_builder.locus_name, other.node_id):
+            return False
+        if (self.parent is None) != (other.parent is None):
+            return False
+        if self.parent is not None and self.parent.node_id != other.parent.node_id:
+            return False
+        if not equal_msas(self.alignment, other.alignment):
+            return False
+        if len(self.children) != len(other.children):
+            return False
+        return all(a == b for a, b in zip(self.children, other.children))
+
+    def __hash__(self):
+        return hash((self.node_id, self.prg_builder.locus_name))
+
+    @abstractmethod
+    def preorder_traversal_to_build_prg(self, prg_as_list, delim_char=" "):
+        raise NotImplementedError
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}:\nId = {self.node_id}\nNesting level = {self.nesting_level}\n"
+                f"Parent = {'None' if self.parent is None else f'Id = {self.parent.node_id}'}\n"
+                f"Children = [{', '.join(f'Id = {c.node_id}' for c in self.children)}]\n"
+                f"Alignment:\n{format(self.alignment, 'fasta')}")
+
+
+class MultiIntervalNode(RecursiveTreeNode):
+    """Vertical partition of an MSA: the PRG is the concatenation of the children's PRGs."""
+
+    def preorder_traversal_to_build_prg(self, prg_as_list, delim_char=" "):
+        for child in self.children:
+            child.preorder_traversal_to_build_prg(prg_as_list, delim_char)
+
+
+class MultiClusterNode(RecursiveTreeNode):
+    """Horizontal partition (sequence clusters): opens a site, one allele per child."""
+
+    def preorder_traversal_to_build_prg(self, prg_as_list, delim_char=" "):
+        site_num = self.prg_builder.get_next_site_num()
+        prg_as_list.extend(f"{delim_char}{site_num}{delim_char}")
+        last = len(self.children) - 1
+        for child_index, child in enumerate(self.children):
+            child.preorder_traversal_to_build_prg(prg_as_list, delim_char)
+            marker = site_num + 1 if child_index < last else site_num
+            prg_as_list.extend(f"{delim_char}{marker}{delim_char}")
+
+
+class UpdateError(Exception):
+    pass
+
+
+class LeafNode(RecursiveTreeNode):
+    """MSAs that are never partitioned; the only nodes that get indexed."""
+
+    def __init__(self, nesting_level, alignment, parent, prg_builder, node_id):
+        super().__init__(nesting_level, alignment, parent, prg_builder, node_id)
+        self.new_sequences = set()
+        self.indexed_PRG_intervals = set()
+
+    def preorder_traversal_to_build_prg(self, prg_as_list, delim_char=" ", do_indexing=True):
+        expanded = SequenceExpander.get_expanded_sequences_from_MSA(self.alignment)
+        if len(expanded) == 1:
+            start = len(prg_as_list)
+            prg_as_list.extend(expanded[0])
+            if do_indexing:
+                self.prg_builder.update_PRG_index(start, len(prg_as_list), node=self)
+            return
+        site_num = self.prg_builder.get_next_site_num()
+        prg_as_list.extend(f"{delim_char}{site_num}{delim_char}")
+        last = len(expanded) - 1
+        for seq_index, seq in enumerate(expanded):
+            start = len(prg_as_list)
+            prg_as_list.extend(seq)
+            end = len(prg_as_list)
+            marker = site_num + 1 if seq_index < last else site_num
+            prg_as_list.extend(f"{delim_char}{marker}{delim_char}")
+            if do_indexing:
+                self.prg_builder.update_PRG_index(start, end, node=self)
+
+    def add_indexed_PRG_interval(self, interval):
+        self.indexed_PRG_intervals.add(interval)
+
+    def clear_PRG_interval_index(self):
+        self.indexed_PRG_intervals.clear()
+
+
+_CLASSES = {NODE_LEAF: LeafNode, NODE_INTERVAL: MultiIntervalNode, NODE_CLUSTER: MultiClusterNode}
+
+
+def nodes_from_table(alignment: MSA, table, prg_builder) -> RecursiveTreeNode:
+    """Materialise the tree of one locus from the engine's pre-order node table."""
+    n = len(table["kind"])
+    M = alignment.matrix
+    records = list(alignment)
+    built: List[Optional[RecursiveTreeNode]] = [None] * n
+    for i in range(n):
+        if table["row_off"][i] < 0:
+            rows = np.arange(len(records))
+        else:
+            o = int(table["row_off"][i])
+            rows = table["row_pool"][o:o + int(table["n_rows"][i])]
+        c0, c1 = int(table["c0"][i]), int(table["c1"][i])
+        sub = MSA([records[int(r)][c0:c1] for r in rows])
+        parent = built[int(table["parent"][i])] if table["parent"][i] >= 0 else None
+        node = _CLASSES[int(table["kind"][i])](int(table["nesting_level"][i]), sub, parent, prg_builder, i)
+        built[i] = node
+        if parent is not None:
+            parent._children.append(node)
+    del M
+    return built[0]
+
+
+class NodeFactory:
+    """NodeFactory.build(alignment, prg_builder, parent_node=None) (recursion_tree.py:401-471)."""
+
+    @staticmethod
+    def build(alignment, prg_builder, parent_node=None):
+        if parent_node is not None:
+            raise NotImplementedError("re-building below an existing node belongs to `make_prg update`, "
+                                      "which is outside the from_msa hot path")
+        result = engine.build_matrices([alignment.matrix], prg_builder.max_nesting,
+                                       prg_builder.min_match_length)[0]
+        result.raise_for_status(prg_builder.locus_name)
+        prg_builder.next_node_id = result.n_nodes
+        prg_builder.engine_prg = result.prg
+        return nodes_from_table(alignment, result.nodes, prg_builder)
+
+    @staticmethod
+    def _get_vertical_partition(alignment, min_match_length):
+        from .from_msa.interval_partition import IntervalPartitioner
+        from .utils.seq_utils import get_consensus_from_MSA
+
+        consensus = get_consensus_from_MSA(alignment)
+        match, _non_match, all_intervals = IntervalPartitioner(consensus, min_match_length,
+                                                               alignment).get_intervals()
+        return all_intervals, match
