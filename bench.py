@@ -145,7 +145,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = max(cores * 2, 8)
+    sample = max(cores * 8, 32)
     data = workload(0)[:sample]
     mats = [data[i] for i in range(sample)]
     for _ in range(args.warmup):

@@ -80,6 +80,10 @@ int64_t mprg_launch_count(const mprg_ctx *ctx);
  * kernel accumulated since the last reset; used by bench.py for the roofline object */
 int mprg_scan_stats(mprg_ctx *ctx, double *ms, double *bytes, int64_t *launches, int reset);
 
+/* host threads (each with its own stream and scratch) mprg_build may use to overlap the host
+ * bookkeeping of one range of loci with the kernels of the others; default min(4, cores) or
+ * the MPRG_WORKERS environment variable */
+int mprg_set_workers(mprg_ctx *ctx, int32_t n_workers);
 /* host<->device bytes copied by this context since the last reset (bench.py's e2e object) */
 int mprg_copy_stats(mprg_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes, int reset);
 /* CUDA-event stopwatch on the context's stream: op 0 records the start, op 1 records the stop,

@@ -1,6 +1,9 @@
 // Context management and the loader -> HBM step: ASCII MSAs are copied to the device and packed to
 // 4 bits per symbol there (two columns per byte, rows padded to 16 bytes).
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -96,12 +99,21 @@ extern "C" int mprg_create(int device_ordinal, mprg_ctx **out) {
         delete ctx;
         return MPRG_E_CUDA;
     }
+    if (const char *env = getenv("MPRG_WORKERS")) {
+        const int n = atoi(env);
+        if (n >= 1 && n <= 64) ctx->n_workers = n;
+    } else {
+        const unsigned hc = std::thread::hardware_concurrency();
+        ctx->n_workers = (int)std::max(1u, std::min(4u, hc ? hc : 1u));
+    }
     *out = ctx;
     return MPRG_OK;
 }
 
 extern "C" void mprg_destroy(mprg_ctx *ctx) {
     if (!ctx) return;
+    for (mprg_ctx *w : ctx->workers) mprg_destroy(w);
+    ctx->workers.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_tasks, &ctx->d_units, &ctx->d_rows, &ctx->d_colwords, &ctx->d_colB,

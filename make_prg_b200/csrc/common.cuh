@@ -110,6 +110,8 @@ struct mprg_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     long long launches = 0;
+    int n_workers = 1;                // host threads / streams mprg_build may use
+    std::vector<mprg_ctx *> workers;  // lazily created worker contexts (same device)
     long long h2d_bytes = 0, d2h_bytes = 0;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // mprg_timer
     // per-launch log of the scan kernel (algorithmic bytes, device ms), newest last

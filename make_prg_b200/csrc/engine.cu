@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_set>
 
 #include "common.cuh"
@@ -764,15 +765,11 @@ struct mprg_result {
     std::vector<LocusResult> loci;
 };
 
-extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
-                          int32_t min_match_length, mprg_result **out_res) {
-    if (!ctx || !batch || !out_res || min_match_length < 1) return MPRG_E_BAD_ARG;
-    *out_res = nullptr;
+// Builds loci [l_begin, l_end) of the batch on one context (one stream, one host thread).
+static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, int32_t max_nesting,
+                       int32_t min_match_length, mprg_result *res, bool allow_trace) {
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
-    const int n_loci = batch->n_loci;
-    mprg_result *res = new mprg_result();
-    res->loci.resize(n_loci);
     struct Pending {
         int locus, node;
     };
@@ -781,11 +778,8 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
     };
     std::vector<Pending> pending, next;
     std::vector<Allele> alleles;
-    auto fail = [&](int code) {
-        delete res;
-        return code;
-    };
-    for (int l = 0; l < n_loci; ++l) {
+    auto fail = [&](int code) { return code; };
+    for (int l = l_begin; l < l_end; ++l) {
         LocusResult &L = res->loci[l];
         if (batch->flags[l] & 1) {
             L.status = MPRG_LOCUS_CURATION_ERROR;
@@ -819,7 +813,7 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
     std::vector<mprg_task> tasks;
     std::vector<int32_t> arena;
     PhaseTrace trace;
-    g_trace = trace.on ? &trace : nullptr;
+    if (allow_trace) g_trace = trace.on ? &trace : nullptr;
     while (!pending.empty()) {
         const int nt = (int)pending.size();
         tasks.resize(nt);
@@ -1010,7 +1004,7 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
     TRACE("build: allele extraction");
     // ---- pre-order numbering and PRG strings (recursion_tree.py:194-300, prg_builder.py:100-110) ----
     std::vector<std::string> raw, expanded;
-    for (int l = 0; l < n_loci; ++l) {
+    for (int l = l_begin; l < l_end; ++l) {
         LocusResult &L = res->loci[l];
         if (L.status != MPRG_LOCUS_OK) continue;
         L.prg.reserve((size_t)batch->n_cols[l] * 2 + 64);
@@ -1100,8 +1094,98 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
         }
     }
     TRACE("build: prg strings");
-    trace.report("mprg_build");
-    g_trace = nullptr;
+    if (allow_trace) {
+        trace.report("mprg_build");
+        g_trace = nullptr;
+    }
+    return MPRG_OK;
+}
+
+extern "C" int mprg_set_workers(mprg_ctx *ctx, int32_t n_workers) {
+    if (!ctx || n_workers < 1 || n_workers > 64) return MPRG_E_BAD_ARG;
+    ctx->n_workers = n_workers;
+    return MPRG_OK;
+}
+
+// Loci are independent, so a batch is cut into contiguous, cost-balanced ranges that are built
+// concurrently: one host thread + one stream + one scratch set per range, all reading the same
+// packed batch.  This overlaps the host bookkeeping of one range with the kernels of the others.
+extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
+                          int32_t min_match_length, mprg_result **out_res) {
+    if (!ctx || !batch || !out_res || min_match_length < 1) return MPRG_E_BAD_ARG;
+    *out_res = nullptr;
+    cudaSetDevice(ctx->device);
+    const int n_loci = batch->n_loci;
+    mprg_result *res = new mprg_result();
+    res->loci.resize(n_loci);
+    int rc = ensure_rand(ctx);
+    if (rc != MPRG_OK) {
+        delete res;
+        return rc;
+    }
+    int W = std::max(1, std::min(ctx->n_workers, n_loci / 8));
+    if (W <= 1) {
+        rc = build_range(ctx, batch, 0, n_loci, max_nesting, min_match_length, res, true);
+        if (rc != MPRG_OK) {
+            delete res;
+            return rc;
+        }
+        *out_res = res;
+        return MPRG_OK;
+    }
+    while ((int)ctx->workers.size() < W - 1) {
+        mprg_ctx *w = nullptr;
+        rc = mprg_create(ctx->device, &w);
+        if (rc != MPRG_OK) {
+            delete res;
+            MPRG_FAIL(ctx, rc, "could not create a worker context");
+        }
+        ctx->workers.push_back(w);
+    }
+    // contiguous ranges of roughly equal rows x cols
+    std::vector<double> prefix(n_loci + 1, 0.0);
+    for (int l = 0; l < n_loci; ++l) prefix[l + 1] = prefix[l] + (double)batch->n_rows[l] * batch->n_cols[l] + 1.0;
+    std::vector<int> cut(W + 1, n_loci);
+    cut[0] = 0;
+    for (int w = 1; w < W; ++w) {
+        const double target = prefix[n_loci] * w / W;
+        cut[w] = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
+        cut[w] = std::max(cut[w], cut[w - 1]);
+    }
+    std::vector<int> rcs(W, MPRG_OK);
+    std::vector<std::thread> threads;
+    for (int w = 1; w < W; ++w) {
+        mprg_ctx *wc = ctx->workers[w - 1];
+        threads.emplace_back([&, w, wc]() {
+            rcs[w] = build_range(wc, batch, cut[w], cut[w + 1], max_nesting, min_match_length, res, false);
+        });
+    }
+    rcs[0] = build_range(ctx, batch, cut[0], cut[1], max_nesting, min_match_length, res, false);
+    for (auto &t : threads) t.join();
+    for (int w = 1; w < W; ++w) {
+        mprg_ctx *wc = ctx->workers[w - 1];
+        ctx->launches += wc->launches;
+        ctx->h2d_bytes += wc->h2d_bytes;
+        ctx->d2h_bytes += wc->d2h_bytes;
+        ctx->scan_ms += wc->scan_ms;
+        ctx->scan_bytes += wc->scan_bytes;
+        ctx->scan_launches += wc->scan_launches;
+        ctx->scan_log_bytes.insert(ctx->scan_log_bytes.end(), wc->scan_log_bytes.begin(), wc->scan_log_bytes.end());
+        ctx->scan_log_ms.insert(ctx->scan_log_ms.end(), wc->scan_log_ms.begin(), wc->scan_log_ms.end());
+        wc->launches = wc->h2d_bytes = wc->d2h_bytes = 0;
+        wc->scan_ms = wc->scan_bytes = 0;
+        wc->scan_launches = 0;
+        wc->scan_log_bytes.clear();
+        wc->scan_log_ms.clear();
+        if (rcs[w] != MPRG_OK && rcs[0] == MPRG_OK) {
+            rcs[0] = rcs[w];
+            ctx->err = wc->err;
+        }
+    }
+    if (rcs[0] != MPRG_OK) {
+        delete res;
+        return rcs[0];
+    }
     *out_res = res;
     return MPRG_OK;
 }

@@ -80,6 +80,9 @@ class Context:
         self._check(self.lib.mprg_scan_stats(self.handle, C.byref(ms), C.byref(by), C.byref(n), int(reset)))
         return {"ms": ms.value, "bytes": by.value, "launches": n.value}
 
+    def set_workers(self, n):
+        self._check(self.lib.mprg_set_workers(self.handle, int(n)))
+
     def copy_stats(self, reset=False):
         a, b = C.c_int64(), C.c_int64()
         self._check(self.lib.mprg_copy_stats(self.handle, C.byref(a), C.byref(b), int(reset)))

@@ -1,0 +1,157 @@
+"""-m gpu: the Python host layer that mirrors the reference's interface (PrgBuilder, node classes,
+IntervalPartitioner, kmeans_cluster_seqs, writers, CLI) on top of the C ABI; the expectations are
+the reference's own golden files and unit vectors, so these read like the reference's tests."""
+import hashlib
+import pickle
+import zipfile
+from argparse import Namespace
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import REF, SMALL_CASES, rows_to_matrix, truth_multi, truth_prg, unit_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def test_prg_builder_matches_truth_and_engine_string():
+    from make_prg_b200.prg_builder import PrgBuilder
+    from make_prg_b200.recursion_tree import LeafNode, MultiClusterNode, MultiIntervalNode
+
+    for case in ("match.nonmatch.match", "nested_snps_seq_backgrounds", "contains_n_and_RYKMSW",
+                 "nested_snps_deletion", "match.staggereddash"):
+        b = PrgBuilder(case, REF / f"{case}.fa", "fasta", 5, SMALL_CASES[case])
+        prg = b.build_prg()
+        assert prg == truth_prg(case) == b.engine_prg
+        assert b.root.node_id == 0 and b.root.parent is None
+        ids = []
+
+        def walk(n):
+            ids.append(n.node_id)
+            assert isinstance(n, (LeafNode, MultiClusterNode, MultiIntervalNode))
+            for c in n.children:
+                assert c.parent is n
+                walk(c)
+
+        walk(b.root)
+        assert ids == list(range(b.next_node_id))  # pre-order numbering
+        clone = pickle.loads(pickle.dumps(b, protocol=4))
+        assert clone == b and clone.build_prg() == prg
+
+
+def test_sample_example_builder():
+    from make_prg_b200.prg_builder import PrgBuilder
+
+    truth = truth_multi("sample_example")
+    for name in ("GC00006032", "GC00010897"):
+        b = PrgBuilder(name, REF / "sample_example" / f"{name}.fa", "fasta", 5, 7)
+        assert b.build_prg() == truth[name]
+        # prg_index keys are character offsets of the leaf alleles (recursion_tree.py:278-300)
+        for (s, e), leaf in b.prg_index.items():
+            assert set(truth[name][s:e]) <= set("ACGT") and (s, e) in leaf.indexed_PRG_intervals
+
+
+def test_disallowed_base_raises_curation_error():
+    from make_prg_b200.prg_builder import PrgBuilder
+    from make_prg_b200.utils.seq_utils import SequenceCurationError
+
+    with pytest.raises(SequenceCurationError):
+        PrgBuilder("fails_2", REF / "fails_2.fa", "fasta", 5, 7)
+
+
+def test_interval_partitioner_reference_vectors():
+    # tests/from_msa/test_interval_partition.py of the reference
+    from make_prg_b200.from_msa.interval_partition import Interval, IntervalPartitioner, IntervalType
+    from make_prg_b200.msa import MSA, SeqRecord
+
+    M, N = IntervalType.Match, IntervalType.NonMatch
+    empty = MSA([])
+    m, n, a = IntervalPartitioner("TTATT**AAAC*", 3, empty).get_intervals()
+    assert m == [Interval(M, 0, 4), Interval(M, 7, 10)] and n == [Interval(N, 5, 6), Interval(N, 11, 11)]
+    assert a == sorted(m + n)
+    m, n, _ = IntervalPartitioner("**AT*AAA", 3, empty).get_intervals()
+    assert m == [Interval(M, 5, 7)] and n == [Interval(N, 0, 4)]
+    m, n, _ = IntervalPartitioner("T*", 5, empty).get_intervals()
+    assert m == [] and n == [Interval(N, 0, 1)]
+    msa = MSA([SeqRecord("TTAAGGTTT-AATTTA", "s1"), SeqRecord("TTAAGGTTTTAATTTA", "s2")])
+    m, n, _ = IntervalPartitioner("TTAAGGTTT*AATTTA", 7, msa).get_intervals()
+    assert m == [Interval(M, 0, 7)] and n == [Interval(N, 8, 15)]
+
+
+def test_seq_utils_mirrors_on_unit_vectors():
+    from make_prg_b200.msa import MSA, SeqRecord
+    from make_prg_b200.utils.seq_utils import get_consensus_from_MSA, has_empty_sequence
+
+    for rec in unit_cases()[:60]:
+        if "N" in "".join(rec["rows"]) or len(rec["rows"][0]) == 0:
+            continue
+        msa = MSA([SeqRecord(s, f"s{i}") for i, s in enumerate(rec["rows"])])
+        assert get_consensus_from_MSA(msa) == rec["consensus"]
+        a, b, ans = rec["has_empty"][0]
+        assert has_empty_sequence(msa, (a, b)) == ans
+
+
+def test_kmeans_cluster_seqs_mirror_exact_id_order():
+    from make_prg_b200.from_msa.cluster_sequences import kmeans_cluster_seqs
+    from make_prg_b200.msa import MSA, SeqRecord
+
+    n = 0
+    for rec in unit_cases():
+        if rec["clustered_ids"] is None or "N" in "".join(rec["rows"]) or len(rec["rows"][0]) == 0:
+            continue
+        msa = MSA([SeqRecord(s, f"s{i}") for i, s in enumerate(rec["rows"])])
+        res = kmeans_cluster_seqs(msa, rec["L"])
+        assert res.clustered_ids == rec["clustered_ids"], (rec["rows"], rec["L"])
+        n += 1
+        if n >= 120:
+            break
+
+
+def _run_cli(tmp_path, input_path, name, **kw):
+    from make_prg_b200.subcommands import from_msa
+    from make_prg_b200.subcommands.output_type import OutputType
+
+    opts = Namespace(input=str(input_path), suffix="", output_prefix=str(tmp_path / name),
+                     alignment_format="fasta", max_nesting=5, min_match_length=7,
+                     output_type=OutputType("a"), force=False, threads=1, verbose=False, log=None, gpus=1)
+    for k, v in kw.items():
+        setattr(opts, k, v)
+    from_msa.run(opts)
+    return opts
+
+
+def test_cli_sample_example_outputs_equal_truth(tmp_path):
+    _run_cli(tmp_path, REF / "sample_example", "sample_example")
+    truth_dir = REF / "truth" / "sample_example"
+    assert (tmp_path / "sample_example.prg.fa").read_bytes() == (truth_dir / "sample_example.prg.fa").read_bytes()
+    for kind in ("bin", "gfa"):
+        with zipfile.ZipFile(tmp_path / f"sample_example.prg.{kind}.zip") as got, \
+                zipfile.ZipFile(truth_dir / f"sample_example.prg.{kind}.zip") as want:
+            assert sorted(got.namelist()) == sorted(want.namelist())
+            for member in want.namelist():
+                assert got.read(member) == want.read(member), member
+    with zipfile.ZipFile(tmp_path / "sample_example.update_DS.zip") as zf:
+        assert sorted(zf.namelist()) == ["GC00006032", "GC00010897"]
+        b = pickle.loads(zf.read("GC00006032"))
+        assert b.build_prg() == truth_multi("sample_example")["GC00006032"]
+
+
+def test_cli_single_msa_and_skip_semantics(tmp_path):
+    from make_prg_b200.subcommands.from_msa import EmptyMSAError
+
+    _run_cli(tmp_path, REF / "match.nonmatch.fa", "one")
+    t = REF / "truth" / "match.nonmatch"
+    assert (tmp_path / "one.prg.fa").read_text().split("\n")[1] == truth_prg("match.nonmatch")
+    assert (tmp_path / "one.prg.bin").read_bytes() == (t / "match.nonmatch.prg.bin").read_bytes()
+    assert (tmp_path / "one.prg.gfa").read_bytes() == (t / "match.nonmatch.prg.gfa").read_bytes()
+    # a locus with a disallowed base produces no output (tests/integration_tests/test_from_msa.py:183-187)
+    _run_cli(tmp_path, REF / "fails_2.fa", "bad")
+    assert not (tmp_path / "bad.prg.fa").exists()
+    # an empty MSA aborts the run (test_from_msa.py:256-277)
+    with pytest.raises(EmptyMSAError):
+        _run_cli(tmp_path, REF / "several_empty", "empty")
+    # existing outputs are protected unless --force
+    with pytest.raises(RuntimeError):
+        _run_cli(tmp_path, REF / "match.nonmatch.fa", "one")
+    _run_cli(tmp_path, REF / "match.nonmatch.fa", "one", force=True)
