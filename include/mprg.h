@@ -14,9 +14,10 @@
  *     context's stream; entry points that return host results synchronise that stream.
  *   - there is NO CPU fallback: without a CUDA device mprg_create fails with MPRG_E_NO_DEVICE.
  *
- * Symbol codes of the 4-bit packed MSA (two columns per byte, even column in the low nibble, rows
- * padded to 16 bytes with MPRG_SYM_PAD):
- *   A C G T = 0..3, '-' = 4, R Y K M S W = 5..10, N = 11, pad/disallowed = 15.
+ * Symbol codes of the 4-bit packed MSA (rows padded to 16 bytes = 32 columns with MPRG_SYM_PAD; inside
+ * a 32-column chunk, column c is nibble c / 4 of the 32-bit little-endian word c % 4):
+ *   '-' = 0, A C G T = 1..4, R Y K M S W = 5..10, N = 11, pad/disallowed = 15
+ *   (gap = 0 makes the scan kernel's "row holds a gap" test a two-instruction zero-nibble test).
  */
 #ifndef MPRG_H
 #define MPRG_H
@@ -34,7 +35,7 @@ extern "C" {
 #define MPRG_E_PARTITION (-4) /* PartitioningError (interval_partition.py:12) */
 #define MPRG_E_INTERNAL (-5)
 
-#define MPRG_SYM_GAP 4
+#define MPRG_SYM_GAP 0
 #define MPRG_SYM_N 11
 #define MPRG_SYM_PAD 15
 

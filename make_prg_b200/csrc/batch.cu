@@ -14,7 +14,7 @@ __constant__ uint8_t c_sym_lut[256];
 
 static void build_lut(uint8_t *lut) {
     for (int i = 0; i < 256; ++i) lut[i] = SYM_PAD;
-    const char *order = "ACGT-RYKMSWN";
+    const char *order = "-ACGTRYKMSWN";
     for (int i = 0; order[i]; ++i) {
         lut[(uint8_t)order[i]] = (uint8_t)i;
         if (order[i] >= 'A' && order[i] <= 'Z') lut[(uint8_t)(order[i] - 'A' + 'a')] = (uint8_t)i;
@@ -46,16 +46,17 @@ pack_rows_kernel(const uint8_t *__restrict__ ascii, const long long *__restrict_
     int f = 0;
     for (int w = lane; w < n_words; w += 32) {
         uint32_t word = 0;
-        const int c = w * 8;
+        // word-interleaved chunk layout: word (w & 3) of chunk (w >> 2) holds columns 4k + (w & 3)
+        const int cbase = (w >> 2) * 32 + (w & 3);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             uint32_t code = SYM_PAD;
-            if (c + j < C) {
-                const uint8_t ch = src[c + j];
+            if (cbase + 4 * j < C) {
+                const uint8_t ch = src[cbase + 4 * j];
                 code = c_sym_lut[ch];
                 if (code == SYM_PAD) f |= 1;
                 else if (code == SYM_N) f |= 2;
-                else if (code > SYM_GAP) f |= 4;
+                else if (code >= 5) f |= 4;
             }
             word |= code << (4 * j);
         }

@@ -16,8 +16,7 @@
 namespace mprg {
 
 __device__ __forceinline__ int sym_of(const uint8_t *row, int col) {
-    const uint8_t b = row[col >> 1];
-    return (col & 1) ? (b >> 4) : (b & 15);
+    return packed_sym(row, col);
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {

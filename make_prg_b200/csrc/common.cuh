@@ -17,6 +17,19 @@ constexpr int SYM_PAD = MPRG_SYM_PAD;
 constexpr int COLS_PER_CHUNK = 32;  // one 16-byte vector load = 32 columns of one row
 constexpr int CHUNK_BYTES = 16;
 
+// Position of a column inside a packed row.  A chunk (32 columns, 16 bytes) is stored word-interleaved:
+// column c of the chunk lives in 32-bit word (c & 3), nibble (c >> 2).  With this layout the four
+// per-word "which nibbles are gaps" indicators of a chunk interleave, by three shifts and ORs, into
+// one 32-bit mask whose bit c is column c (scan.cu).
+__host__ __device__ __forceinline__ int packed_byte_of(int col) {
+    const int c = col & 31;
+    return ((col >> 5) << 4) + ((c & 3) << 2) + (c >> 3);
+}
+__host__ __device__ __forceinline__ int packed_shift_of(int col) { return ((col >> 2) & 1) << 2; }
+__host__ __device__ __forceinline__ int packed_sym(const uint8_t *row, int col) {
+    return (row[packed_byte_of(col)] >> packed_shift_of(col)) & 15;
+}
+
 // Device-side task descriptor (one sub-alignment).
 struct DTask {
     long long base;   // byte offset of the locus in the packed arena
@@ -35,10 +48,17 @@ struct DInterval {
 };
 
 // A unit of scan work: a row range of one task (all its columns), handled by one CTA.
+// Self-contained (32 bytes, one vector load) so that a CTA needs a single dependent global load
+// before it can issue its first row loads.
 struct ScanUnit {
-    int task;
-    int row_begin;
+    long long base;  // byte offset of the locus in the packed arena
+    int stride;      // bytes per packed row
+    int rows_off;    // offset of the unit's first row index in the row arena, -1 => rows are consecutive
+    int row_begin;   // first row (when rows_off < 0)
     int row_count;
+    int c0, c1;      // column window
+    int col_off;     // per-column outputs of the task (see DTask)
+    int pad;
 };
 
 // Growable device buffer (never shrinks); all launches of a context share one stream, so reuse

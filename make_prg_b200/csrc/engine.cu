@@ -108,14 +108,13 @@ extract_kernel(const uint8_t *__restrict__ packed, const ExtractItem *__restrict
     if (it >= n_items) return;
     const ExtractItem e = items[it];
     const uint8_t *row = packed + e.base + (long long)e.row * e.stride;
-    const char *alphabet = "ACGT-RYKMSWN????";
+    const char *alphabet = "-ACGTRYKMSWN????";
     int len = 0;
     for (int c0 = e.c0; c0 < e.c1; c0 += 32) {
         const int c = c0 + lane;
         int sym = SYM_GAP;
         if (c < e.c1) {
-            const uint8_t b = row[c >> 1];
-            sym = (c & 1) ? (b >> 4) : (b & 15);
+            sym = packed_sym(row, c);
         }
         const unsigned keep = __ballot_sync(0xffffffffu, sym != SYM_GAP);
         if (sym != SYM_GAP) out[e.out_off + len + __popc(keep & ((1u << lane) - 1u))] = (uint8_t)alphabet[sym];

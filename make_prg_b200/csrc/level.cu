@@ -6,7 +6,8 @@
 
 namespace mprg {
 
-constexpr int MAX_UNIT_ROWS = 1024;  // rows of one task handled by one CTA
+constexpr int MAX_UNIT_ROWS = 1024;  // most rows of one task handled by one CTA (carry array in smem)
+constexpr int UNIT_ROW_QUANTUM = 16;  // rows one CTA consumes per trip (4 warps x 4 unrolled rows)
 
 // call after the stream has been synchronised: device time of the level's scan launch
 void account_scan(mprg_ctx *ctx, const Level &lv) {
@@ -31,6 +32,15 @@ int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, 
     lv.tasks.resize(n_tasks);
     lv.has_n = batch->any_n;
     long long col_off = 0, iv_off = 0;
+    // A CTA streams its rows with a bounded number of loads in flight, so a unit's duration grows with
+    // its row count whatever the load of the machine: cut the level into enough units to fill every SM
+    // for several waves (but never below one trip's worth of rows).
+    long long level_rows = 0;
+    for (int i = 0; i < n_tasks; ++i) level_rows += h_tasks[i].n_rows > 0 ? h_tasks[i].n_rows : 0;
+    const long long target_units = (long long)std::max(ctx->sm_count, 1) * 8 * 4;
+    int unit_rows = (int)((level_rows + target_units - 1) / target_units);
+    unit_rows = ((unit_rows + UNIT_ROW_QUANTUM - 1) / UNIT_ROW_QUANTUM) * UNIT_ROW_QUANTUM;
+    unit_rows = std::min(std::max(unit_rows, 2 * UNIT_ROW_QUANTUM), MAX_UNIT_ROWS);
     for (int i = 0; i < n_tasks; ++i) {
         const mprg_task &ht = h_tasks[i];
         if (ht.locus < 0 || ht.locus >= batch->n_loci) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "task locus out of range");
@@ -56,9 +66,14 @@ int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, 
         iv_off += std::max(ht.c1 - ht.c0, 1);
         const double r = ht.n_rows, c = ht.c1 - ht.c0;
         lv.algo_bytes += r * c / 2 + (ht.rows_off >= 0 ? 4.0 * r : 0.0) + 5.0 * c;
-        for (int rb = 0; rb < ht.n_rows; rb += MAX_UNIT_ROWS) {
-            const int cnt = std::min(MAX_UNIT_ROWS, ht.n_rows - rb);
-            lv.units.push_back(ScanUnit{i, rb, cnt});
+        // equal-sized units of at most unit_rows rows, sizes rounded to the trip quantum
+        const int n_units_t = (ht.n_rows + unit_rows - 1) / unit_rows;
+        int per = n_units_t ? (ht.n_rows + n_units_t - 1) / n_units_t : 0;
+        per = ((per + UNIT_ROW_QUANTUM - 1) / UNIT_ROW_QUANTUM) * UNIT_ROW_QUANTUM;
+        for (int rb = 0; rb < ht.n_rows; rb += per) {
+            const int cnt = std::min(per, ht.n_rows - rb);
+            lv.units.push_back(ScanUnit{t.base, t.stride, t.rows_off >= 0 ? t.rows_off + rb : -1, rb, cnt,
+                                        t.c0, t.c1, t.col_off, 0});
             lv.max_unit_rows = std::max(lv.max_unit_rows, cnt);
         }
     }

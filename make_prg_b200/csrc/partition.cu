@@ -15,8 +15,7 @@
 namespace mprg {
 
 __device__ __forceinline__ int sym_at(const uint8_t *row, int col) {
-    const uint8_t b = row[col >> 1];
-    return (col & 1) ? (b >> 4) : (b & 15);
+    return packed_sym(row, col);
 }
 
 // one warp per task
@@ -38,13 +37,15 @@ classify_kernel(const DTask *__restrict__ tasks, int n_tasks, const uint32_t *__
         uint32_t orw = 0, norw = 0;
         unsigned b = 0;
         if (in) {
-            const long long widx = ((long long)t.col_off + wi) >> 3;
-            orw = (colOR[widx] >> ((wi & 7) * 4)) & 15u;
-            norw = (colNOR[widx] >> ((wi & 7) * 4)) & 15u;
+            // column accumulators use the packed layout: chunk -> word (c & 3) -> nibble (c >> 2)
+            const int cc = wi & 31;
+            const long long widx = (((long long)t.col_off + wi) >> 5) * 4 + (cc & 3);
+            orw = (colOR[widx] >> ((cc >> 2) * 4)) & 15u;
+            norw = (colNOR[widx] >> ((cc >> 2) * 4)) & 15u;
             b = colB[(long long)t.col_off + wi];
         }
         const bool uniform = ((orw ^ norw) == 15u);
-        const bool is_match = in && uniform && orw < 4u;
+        const bool is_match = in && uniform && orw >= 1u && orw <= 4u;
         // inclusive prefix max over the warp, seeded with the running maximum
         unsigned m = b;
         for (int d = 1; d < 32; d <<= 1) {
@@ -55,7 +56,7 @@ classify_kernel(const DTask *__restrict__ tasks, int n_tasks, const uint32_t *__
         run_max = __shfl_sync(0xffffffffu, m, 31);
         const uint32_t star = __ballot_sync(0xffffffffu, in && !is_match);
         if (in) {
-            cls[(long long)t.col_off + wi] = is_match ? (uint8_t)("ACGT"[orw]) : (uint8_t)'*';
+            cls[(long long)t.col_off + wi] = is_match ? (uint8_t)("-ACGT"[orw]) : (uint8_t)'*';
             // end (c0-relative) of the furthest gap run covering column i, else i - 1
             reach[(long long)t.col_off + wi] = (m >= (unsigned)(wi + 1)) ? (int)m - 1 - shift : i - 1;
         }
@@ -241,7 +242,7 @@ demote_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ task
         bool bad = false;
         for (int c = s + lane; c <= e; c += 32) {
             const int sym = sym_at(row0, c);
-            bad |= sym > SYM_GAP;
+            bad |= sym >= 5;  // RYKMSW / N
         }
         bad = __any_sync(0xffffffffu, bad);
         bool differ = false;
