@@ -383,7 +383,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * tab_total));
         MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * tab_total));
         MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * x_total));
-        MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * np + 64));
+        MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * 2 * np + 64));
         const size_t o_seqrows = 0;
         const size_t o_memoff = o_seqrows + sizeof(int) * seq_rows.size();
         const size_t o_memrows = o_memoff + sizeof(int) * memoff_total;
@@ -405,6 +405,8 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_seqrows, seq_rows.data(), sizeof(int) * seq_rows.size(), s));
         ClusterState *d_states = B[13].as<ClusterState>();
         int *d_F = reinterpret_cast<int *>(d_states + np);
+        int *d_tickets = d_F + np;  // per-problem "initialisations finished" counters of kmeans_kernel
+        MPRG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, sizeof(int) * np, s));
         // d_leader_u is free after dedupe: scratch for the group -> long-sequence map
         MPRG_CUDA(ctx, launch_members(s, d_mp, np, d_group, d_leadlen, d_leader_u, d_memoff, d_memrows));
         MPRG_CUDA(ctx, launch_kmer(s, d_kp, np, d_seqrows, B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
@@ -436,7 +438,8 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
         ctx->launches++;
         for (int round = 2; round <= MAX_CLUSTERS; ++round) {
-            MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab));
+            MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab,
+                                         d_tickets));
             MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
             ctx->launches += 2;
         }
@@ -565,13 +568,15 @@ extern "C" int mprg_kmeans(mprg_ctx *ctx, const double *h_X, int32_t n, int32_t 
     DevBuf *B = ctx->d_c;
     const long long nd = kmeans_dscratch_doubles(n, F), ni = kmeans_iscratch_ints(n);
     MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * (size_t)n * F));
-    MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * (nd + 1) + sizeof(int) * (ni + n)));
+    MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * (nd + 1) + sizeof(int) * (ni + n + 2)));
     double *d_d = B[15].as<double>();
     double *d_inertia = d_d + nd;
     int *d_i = reinterpret_cast<int *>(d_inertia + 1);
     int *d_labels = d_i + ni;
+    int *d_ticket = d_labels + n;
+    MPRG_CUDA(ctx, cudaMemsetAsync(d_ticket, 0, sizeof(int), s));
     MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[12].p, h_X, sizeof(double) * (size_t)n * F, s));
-    MPRG_CUDA(ctx, launch_kmeans_single(s, B[12].as<double>(), n, F, K, d_d, d_i, d_labels, d_inertia));
+    MPRG_CUDA(ctx, launch_kmeans_single(s, B[12].as<double>(), n, F, K, d_d, d_i, d_labels, d_inertia, d_ticket));
     ctx->launches++;
     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_labels, d_labels, sizeof(int) * n, s));
     double inertia = 0;

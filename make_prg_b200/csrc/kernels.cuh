@@ -104,8 +104,8 @@ long long kmeans_dscratch_doubles(long long n, long long F);
 long long kmeans_iscratch_ints(long long n);
 cudaError_t kmeans_upload_rand(const double *h_rand);
 cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, const double *X,
-                          double *dscratch, int *iscratch, int *assign, int *newlab);
+                          double *dscratch, int *iscratch, int *assign, int *newlab, int *tickets);
 cudaError_t launch_kmeans_single(cudaStream_t s, const double *X0, int n, int F, int K, double *dscratch,
-                                 int *iscratch, int *labels, double *inertia);
+                                 int *iscratch, int *labels, double *inertia, int *ticket);
 
 }  // namespace mprg

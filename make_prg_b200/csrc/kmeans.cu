@@ -296,7 +296,7 @@ struct KM {
     int n, F, K;
     const double *X0;
     double *Xc, *mean, *tmpF, *xx, *ca, *cb, *best_c, *lb, *ub, *closest, *cum, *D, *half, *nxt, *shift,
-        *wts, *cc, *dist;
+        *wts, *cc, *dist, *res;
     int *labels, *labels_old, *best_labels;
 };
 
@@ -642,8 +642,45 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
     *out_C = C;
 }
 
-__device__ void kmeans_fit_predict(KM &k, double *s_scalar, int *s_int, int *out_labels,
-                                   double *out_inertia) {
+// ---- one fit = KM_NINIT independent initialisations + a sequential best-of selection -------------
+// Scratch of one problem: KM_NINIT per-initialisation blocks (each with its own centred copy of X, so
+// the initialisations share nothing and can run in different CTAs) followed by the problem block.
+__device__ __host__ inline long long km_init_doubles(long long n, long long F) {
+    return n * F + 2 * F + n + 2LL * KM_MAXK * F + n * KM_MAXK + 3 * n + 4 * n + n + KM_MAXK * KM_MAXK +
+           4 * KM_MAXK + 8;  // + [inertia, tol, final-centres selector] in the last 8
+}
+__device__ __host__ inline long long km_init_ints(long long n) { return 2 * n + 8; }
+
+__device__ void km_bind_init(KM &k, int n, int F, int K, const double *X0, double *d, int *ii) {
+    k.n = n; k.F = F; k.K = K; k.X0 = X0;
+    const long long nF = (long long)n * F;
+    k.Xc = d; d += nF;
+    k.mean = d; d += F;
+    k.tmpF = d; d += F;
+    k.xx = d; d += n;
+    k.ca = d; d += (long long)KM_MAXK * F;
+    k.cb = d; d += (long long)KM_MAXK * F;
+    k.lb = d; d += (long long)n * KM_MAXK;
+    k.ub = d; d += n;
+    k.closest = d; d += n;
+    k.cum = d; d += n;
+    k.D = d; d += 4LL * n;
+    k.dist = d; d += n;
+    k.half = d; d += KM_MAXK * KM_MAXK;
+    k.nxt = d; d += KM_MAXK;
+    k.shift = d; d += KM_MAXK;
+    k.wts = d; d += KM_MAXK;
+    k.cc = d; d += KM_MAXK;
+    k.res = d;  // res[0] = inertia, res[1] = 0/1: final centres in ca/cb
+    k.labels = ii; ii += n;
+    k.labels_old = ii; ii += n;
+    k.best_c = nullptr;
+    k.best_labels = nullptr;
+}
+
+// one initialisation: centring (private copy), k-means++ from the init-th slice of the RandomState(2)
+// stream, Elkan; leaves labels, inertia and the final centres in the init's block
+__device__ void kmeans_run_init(KM &k, int init, double *s_scalar, int *s_int) {
     const int n = k.n, F = k.F, K = k.K;
     // tolerance on the un-centred data, mean, centring, squared norms
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
@@ -661,63 +698,65 @@ __device__ void kmeans_fit_predict(KM &k, double *s_scalar, int *s_int, int *out
     }
     __syncthreads();
     if (threadIdx.x == 0) s_scalar[2] = __dmul_rn(np_pairwise_sum(k.tmpF, F) / (double)F, 1e-4);
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        k.xx[i] = einsum_self(k.Xc + (long long)i * F, F);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) k.xx[i] = einsum_self(k.Xc + (long long)i * F, F);
     __syncthreads();
     const double tol = s_scalar[2];
-    int rand_pos = 0;
-    bool have_best = false;
-    double best_inertia = 0.0;
-    for (int init = 0; init < KM_NINIT; ++init) {
-        const double *C = nullptr;
-        kmeans_single(k, rand_pos, tol, s_scalar, s_int, &C);
-        const double inertia = s_scalar[1];
-#ifdef MPRG_HOST_EMU_DEBUG
-        printf("emu init %d inertia %.17g labels", init, inertia);
-        for (int i = 0; i < n; ++i) printf(" %d", k.labels[i]);
-        printf("\n");
-#endif
-        if (threadIdx.x == 0) {
-            int take = 0;
-            if (!have_best) take = 1;
-            else if (inertia < best_inertia) {
+    // every initialisation consumes 1 + (K-1) * (2 + int(ln K)) doubles of the shared stream
+    const int trials = 2 + (int)log((double)K);
+    int rand_pos = init * (1 + (K - 1) * trials);
+    const double *C = nullptr;
+    kmeans_single(k, rand_pos, tol, s_scalar, s_int, &C);
+    if (threadIdx.x == 0) {
+        k.res[0] = s_scalar[1];
+        k.res[1] = (C == k.ca) ? 0.0 : 1.0;
+    }
+    __syncthreads();
+}
+
+// best-of-n_init selection (strict inertia improvement and not the same clustering), then predict on
+// the un-centred data: argmin_j |c_j|^2 - 2 x.c_j  (lloyd _update_chunk_dense, chunks of 256 samples)
+__device__ void kmeans_select_predict(int n, int F, int K, const double *X0, double *init_d, int *init_i,
+                                      double *best_c, double *cc, int *s_int, int *out_labels,
+                                      double *out_inertia) {
+    const long long dstride = km_init_doubles(n, F), istride = km_init_ints(n);
+    if (threadIdx.x == 0) {
+        int best = 0;
+        for (int init = 1; init < KM_NINIT; ++init) {
+            KM a, b;
+            km_bind_init(a, n, F, K, X0, init_d + init * dstride, init_i + init * istride);
+            km_bind_init(b, n, F, K, X0, init_d + best * dstride, init_i + best * istride);
+            if (a.res[0] < b.res[0]) {
                 // _is_same_clustering(labels, best_labels, K)
                 int mapping[KM_MAXK];
                 for (int j = 0; j < KM_MAXK; ++j) mapping[j] = -1;
                 bool same = true;
                 for (int i = 0; i < n && same; ++i) {
-                    const int a = k.labels[i], b = k.best_labels[i];
-                    if (mapping[a] == -1) mapping[a] = b;
-                    else if (mapping[a] != b) same = false;
+                    const int la = a.labels[i], lb = b.labels[i];
+                    if (mapping[la] == -1) mapping[la] = lb;
+                    else if (mapping[la] != lb) same = false;
                 }
-                take = same ? 0 : 1;
+                if (!same) best = init;
             }
-            s_int[0] = take;
         }
-        __syncthreads();
-        if (s_int[0]) {
-            have_best = true;
-            best_inertia = inertia;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) k.best_labels[i] = k.labels[i];
-            for (long long p = threadIdx.x; p < (long long)K * F; p += blockDim.x) k.best_c[p] = C[p];
-        }
-        __syncthreads();
+        s_int[0] = best;
     }
-    // predict on the un-centred data: argmin_j |c_j|^2 - 2 x.c_j  (lloyd _update_chunk_dense)
-    for (long long p = threadIdx.x; p < (long long)K * F; p += blockDim.x)
-        k.best_c[p] = __dadd_rn(k.best_c[p], k.mean[p % F]);
     __syncthreads();
-    for (int j = threadIdx.x; j < K; j += blockDim.x)
-        k.cc[j] = einsum_self(k.best_c + (long long)j * F, F);
+    KM w;
+    km_bind_init(w, n, F, K, X0, init_d + s_int[0] * dstride, init_i + s_int[0] * istride);
+    const double *C = (w.res[1] == 0.0) ? w.ca : w.cb;
+    for (long long p = threadIdx.x; p < (long long)K * F; p += blockDim.x)
+        best_c[p] = __dadd_rn(C[p], w.mean[p % F]);
+    __syncthreads();
+    for (int j = threadIdx.x; j < K; j += blockDim.x) cc[j] = einsum_self(best_c + (long long)j * F, F);
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double *x = k.X0 + (long long)i * F;
+        const double *x = X0 + (long long)i * F;
         int lab = 0;
         double best = 0.0;
+        const int chunk = n > 256 ? 256 : n;
+        const int ci = i % chunk, cn = (i / chunk) * chunk + chunk <= n ? chunk : n % chunk;
         for (int j = 0; j < K; ++j) {
-            const int chunk = n > 256 ? 256 : n;
-            const int ci = i % chunk, cn = (i / chunk) * chunk + chunk <= n ? chunk : n % chunk;
-            const double v = gemm_axpy(x, k.best_c + (long long)j * F, F, j, K, ci, cn, -2.0, k.cc[j]);
+            const double v = gemm_axpy(x, best_c + (long long)j * F, F, j, K, ci, cn, -2.0, cc[j]);
             if (j == 0 || v < best) {
                 best = v;
                 lab = j;
@@ -725,82 +764,98 @@ __device__ void kmeans_fit_predict(KM &k, double *s_scalar, int *s_int, int *out
         }
         out_labels[i] = lab;
     }
-    if (threadIdx.x == 0 && out_inertia) *out_inertia = best_inertia;
+    if (threadIdx.x == 0 && out_inertia) *out_inertia = w.res[0];
     __syncthreads();
 }
 
-__device__ void km_bind(KM &k, int n, int F, int K, const double *X0, double *d, int *ii) {
-    k.n = n; k.F = F; k.K = K; k.X0 = X0;
-    const long long nF = (long long)n * F;
-    k.Xc = d; d += nF;
-    k.mean = d; d += F;
-    k.tmpF = d; d += F;
-    k.xx = d; d += n;
-    k.ca = d; d += (long long)KM_MAXK * F;
-    k.cb = d; d += (long long)KM_MAXK * F;
-    k.best_c = d; d += (long long)KM_MAXK * F;
-    k.lb = d; d += (long long)n * KM_MAXK;
-    k.ub = d; d += n;
-    k.closest = d; d += n;
-    k.cum = d; d += n;
-    k.D = d; d += 4LL * n;
-    k.dist = d; d += n;
-    k.half = d; d += KM_MAXK * KM_MAXK;
-    k.nxt = d; d += KM_MAXK;
-    k.shift = d; d += KM_MAXK;
-    k.wts = d; d += KM_MAXK;
-    k.cc = d; d += KM_MAXK;
-    k.labels = ii; ii += n;
-    k.labels_old = ii; ii += n;
-    k.best_labels = ii; ii += n;
+// scratch per problem: KM_NINIT init blocks | best_c [KM_MAXK * F] | cc [KM_MAXK] ; ints: KM_NINIT init blocks
+long long kmeans_dscratch_doubles(long long n, long long F) {
+    return KM_NINIT * km_init_doubles(n, F) + KM_MAXK * F + KM_MAXK + 8;
 }
+long long kmeans_iscratch_ints(long long n) { return KM_NINIT * km_init_ints(n) + 8; }
 
-// one CTA per clustering problem of the level; runs only where refcheck_kernel asked for it
+#ifndef MPRG_HOST_EMU
+// grid (problems, KM_NINIT): every CTA runs one initialisation; the last CTA of a problem to finish
+// (ticket counter) does the selection, the prediction and the loop control of kmeans_cluster_seqs
 __global__ void __launch_bounds__(KM_THREADS)
 kmeans_kernel(ClusterState *__restrict__ states, const double *__restrict__ X_all,
               double *__restrict__ dscratch, int *__restrict__ iscratch, int *__restrict__ assign_all,
-              int *__restrict__ newlab_all) {
+              int *__restrict__ newlab_all, int *__restrict__ tickets) {
     __shared__ double s_scalar[4];
     __shared__ int s_int[8];
     ClusterState &st = states[blockIdx.x];
     if (st.status != 0 || !st.run_kmeans) return;
+    const int n = st.n, F = st.F, K = st.K, init = blockIdx.y;
+    const double *X0 = X_all + st.x_off;
+    double *d0 = dscratch + st.kmd_off;
+    int *i0 = iscratch + st.kmi_off;
     KM k;
-    km_bind(k, st.n, st.F, st.K, X_all + st.x_off, dscratch + st.kmd_off, iscratch + st.kmi_off);
+    km_bind_init(k, n, F, K, X0, d0 + init * km_init_doubles(n, F), i0 + init * km_init_ints(n));
+    kmeans_run_init(k, init, s_scalar, s_int);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_int[7] = atomicAdd(&tickets[blockIdx.x], 1);
+    __syncthreads();
+    if (s_int[7] != KM_NINIT - 1) return;
+    __threadfence();
     int *newlab = newlab_all + st.assign_off;
     int *assign = assign_all + st.assign_off;
-    kmeans_fit_predict(k, s_scalar, s_int, newlab, nullptr);
-    __syncthreads();
+    double *best_c = d0 + KM_NINIT * km_init_doubles(n, F);
+    kmeans_select_predict(n, F, K, X0, d0, i0, best_c, best_c + (long long)KM_MAXK * F, s_int, newlab, nullptr);
     if (threadIdx.x == 0) {
         // cluster_sequences.py:267-274: fewer distinct labels than K => keep the previous assignment
         unsigned seen = 0;
-        for (int i = 0; i < st.n; ++i) seen |= 1u << newlab[i];
+        for (int i = 0; i < n; ++i) seen |= 1u << newlab[i];
         const int distinct = __popc(seen);
-        if (distinct < st.K) {
+        if (distinct < K) {
             st.K -= 1;
             st.status = 1;
         } else {
-            for (int i = 0; i < st.n; ++i) assign[i] = newlab[i];
+            for (int i = 0; i < n; ++i) assign[i] = newlab[i];
         }
+        tickets[blockIdx.x] = 0;
+        __threadfence();
         st.run_kmeans = 0;
     }
 }
 
-// stand-alone problem (mprg_kmeans)
+// stand-alone problem (mprg_kmeans): same structure, grid (1, KM_NINIT)
 __global__ void __launch_bounds__(KM_THREADS)
 kmeans_single_problem_kernel(const double *X0, int n, int F, int K, double *dscratch, int *iscratch,
-                             int *labels, double *inertia) {
+                             int *labels, double *inertia, int *ticket) {
     __shared__ double s_scalar[4];
     __shared__ int s_int[8];
+    const int init = blockIdx.y;
     KM k;
-    km_bind(k, n, F, K, X0, dscratch, iscratch);
-    kmeans_fit_predict(k, s_scalar, s_int, labels, inertia);
+    km_bind_init(k, n, F, K, X0, dscratch + init * km_init_doubles(n, F), iscratch + init * km_init_ints(n));
+    kmeans_run_init(k, init, s_scalar, s_int);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_int[7] = atomicAdd(ticket, 1);
+    __syncthreads();
+    if (s_int[7] != KM_NINIT - 1) return;
+    __threadfence();
+    double *best_c = dscratch + KM_NINIT * km_init_doubles(n, F);
+    kmeans_select_predict(n, F, K, X0, dscratch, iscratch, best_c, best_c + (long long)KM_MAXK * F, s_int, labels,
+                          inertia);
+    if (threadIdx.x == 0) *ticket = 0;
 }
-
-long long kmeans_dscratch_doubles(long long n, long long F) {
-    return n * F + 2 * F + n + 3LL * KM_MAXK * F + n * KM_MAXK + 3 * n + 4 * n + n + KM_MAXK * KM_MAXK +
-           4 * KM_MAXK + 16;
+#else
+// host emulation (tests/hostemu): the same device functions, initialisations one after the other
+void kmeans_single_problem_kernel(const double *X0, int n, int F, int K, double *dscratch, int *iscratch,
+                                  int *labels, double *inertia) {
+    static double s_scalar[4];
+    static int s_int[8];
+    for (int init = 0; init < KM_NINIT; ++init) {
+        KM k;
+        km_bind_init(k, n, F, K, X0, dscratch + init * km_init_doubles(n, F), iscratch + init * km_init_ints(n));
+        kmeans_run_init(k, init, s_scalar, s_int);
+    }
+    double *best_c = dscratch + KM_NINIT * km_init_doubles(n, F);
+    kmeans_select_predict(n, F, K, X0, dscratch, iscratch, best_c, best_c + (long long)KM_MAXK * F, s_int, labels,
+                          inertia);
 }
-long long kmeans_iscratch_ints(long long n) { return 3 * n + 8; }
+#endif
 
 #ifndef MPRG_HOST_EMU
 cudaError_t kmeans_upload_rand(const double *h_rand) {
@@ -808,15 +863,17 @@ cudaError_t kmeans_upload_rand(const double *h_rand) {
 }
 
 cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, const double *X,
-                          double *dscratch, int *iscratch, int *assign, int *newlab) {
+                          double *dscratch, int *iscratch, int *assign, int *newlab, int *tickets) {
     if (n_probs <= 0) return cudaSuccess;
-    kmeans_kernel<<<n_probs, KM_THREADS, 0, s>>>(states, X, dscratch, iscratch, assign, newlab);
+    kmeans_kernel<<<dim3(n_probs, KM_NINIT), KM_THREADS, 0, s>>>(states, X, dscratch, iscratch, assign, newlab,
+                                                                 tickets);
     return cudaGetLastError();
 }
 
 cudaError_t launch_kmeans_single(cudaStream_t s, const double *X0, int n, int F, int K, double *dscratch,
-                                 int *iscratch, int *labels, double *inertia) {
-    kmeans_single_problem_kernel<<<1, KM_THREADS, 0, s>>>(X0, n, F, K, dscratch, iscratch, labels, inertia);
+                                 int *iscratch, int *labels, double *inertia, int *ticket) {
+    kmeans_single_problem_kernel<<<dim3(1, KM_NINIT), KM_THREADS, 0, s>>>(X0, n, F, K, dscratch, iscratch, labels,
+                                                                          inertia, ticket);
     return cudaGetLastError();
 }
 

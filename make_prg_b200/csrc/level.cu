@@ -1,5 +1,6 @@
 // Host side of one recursion level: task table, scan units, launches.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -41,6 +42,10 @@ int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, 
     int unit_rows = (int)((level_rows + target_units - 1) / target_units);
     unit_rows = ((unit_rows + UNIT_ROW_QUANTUM - 1) / UNIT_ROW_QUANTUM) * UNIT_ROW_QUANTUM;
     unit_rows = std::min(std::max(unit_rows, 2 * UNIT_ROW_QUANTUM), MAX_UNIT_ROWS);
+    if (const char *env = getenv("MPRG_UNIT_ROWS")) {  // tuning knob for profiling runs
+        const int v = atoi(env);
+        if (v >= UNIT_ROW_QUANTUM && v <= MAX_UNIT_ROWS) unit_rows = v;
+    }
     for (int i = 0; i < n_tasks; ++i) {
         const mprg_task &ht = h_tasks[i];
         if (ht.locus < 0 || ht.locus >= batch->n_loci) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "task locus out of range");
@@ -66,15 +71,15 @@ int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, 
         iv_off += std::max(ht.c1 - ht.c0, 1);
         const double r = ht.n_rows, c = ht.c1 - ht.c0;
         lv.algo_bytes += r * c / 2 + (ht.rows_off >= 0 ? 4.0 * r : 0.0) + 5.0 * c;
-        // equal-sized units of at most unit_rows rows, sizes rounded to the trip quantum
-        const int n_units_t = (ht.n_rows + unit_rows - 1) / unit_rows;
-        int per = n_units_t ? (ht.n_rows + n_units_t - 1) / n_units_t : 0;
-        per = ((per + UNIT_ROW_QUANTUM - 1) / UNIT_ROW_QUANTUM) * UNIT_ROW_QUANTUM;
-        for (int rb = 0; rb < ht.n_rows; rb += per) {
-            const int cnt = std::min(per, ht.n_rows - rb);
+        // units of unit_rows rows (a multiple of the trip quantum); a short remainder joins the last unit
+        for (int rb = 0; rb < ht.n_rows;) {
+            int cnt = std::min(unit_rows, ht.n_rows - rb);
+            const int left = ht.n_rows - rb - cnt;
+            if (left > 0 && left < unit_rows / 2 && cnt + left <= MAX_UNIT_ROWS) cnt += left;
             lv.units.push_back(ScanUnit{t.base, t.stride, t.rows_off >= 0 ? t.rows_off + rb : -1, rb, cnt,
                                         t.c0, t.c1, t.col_off, 0});
             lv.max_unit_rows = std::max(lv.max_unit_rows, cnt);
+            rb += cnt;
         }
     }
     lv.total_cols = col_off;

@@ -31,7 +31,6 @@ namespace mprg {
 constexpr int SCAN_THREADS = 128;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int SCAN_BLOCK_CHUNKS = 32;                                  // chunks per column block
-constexpr int SCAN_BLOCK_COLS = SCAN_BLOCK_CHUNKS * COLS_PER_CHUNK;    // 1024
 constexpr int SCAN_UNROLL = 4;
 
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
@@ -65,15 +64,14 @@ __device__ __forceinline__ uint32_t nibble_eq_maskF(uint32_t w, uint32_t pattern
 // Gap runs that stay inside the lane's chunk (neither its first nor its last column is a gap) need no
 // cooperation: the common case for short indels.  Returns the mask when the lane needs the
 // cooperative path (a run touches a chunk border), 0 otherwise.
-__device__ __forceinline__ uint32_t scan_gap_local(uint32_t g, int lane_chunk, int colbase, int a0,
-                                                   unsigned *B_s) {
+__device__ __forceinline__ uint32_t scan_gap_local(uint32_t g, int colbase, int a0, unsigned *B) {
     if (g & 0x80000001u) return g;
     uint32_t starts = g & ~(g << 1);
     while (starts) {
         const int i = __ffs(starts) - 1;
         starts &= starts - 1;
         const int ones = __ffs(~(g >> i)) - 1;
-        atomicMax(&B_s[(lane_chunk << 5) + i], (unsigned)(colbase + i + ones - a0));
+        atomicMax(&B[colbase - a0 + i], (unsigned)(colbase + i + ones - a0));
     }
     return 0u;
 }
@@ -84,7 +82,7 @@ __device__ __forceinline__ uint32_t scan_gap_local(uint32_t g, int lane_chunk, i
 __device__ __forceinline__ void scan_gap_rows(uint32_t g, int lane,
                                               int lane_chunk, int nchp, int colbase, int a0, int rl,
                                               int row_count, bool right_block_exists, bool multi_block,
-                                              uint32_t topmask, int *carry_s, unsigned *B_s) {
+                                              uint32_t topmask, int *carry_s, unsigned *B) {
     const uint32_t firstb = __ballot_sync(0xffffffffu, g & 1u);
     const uint32_t lastb = __ballot_sync(0xffffffffu, g >> 31);
     const uint32_t fullb = __ballot_sync(0xffffffffu, g == 0xffffffffu);
@@ -119,7 +117,7 @@ __device__ __forceinline__ void scan_gap_rows(uint32_t g, int lane,
         const int ones = x ? (__ffs(x) - 1) : 32;
         int end_col = colbase + i + ones - 1;
         if (i + ones == 32) end_col += ext;
-        atomicMax(&B_s[(lane_chunk << 5) + i], (unsigned)(end_col - a0 + 1));
+        atomicMax(&B[colbase - a0 + i], (unsigned)(end_col - a0 + 1));
     }
 }
 
@@ -129,7 +127,6 @@ scan_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks,
             const ScanUnit *__restrict__ units, const int *__restrict__ rows_arena,
             uint32_t *__restrict__ colOR, uint32_t *__restrict__ colNOR,
             unsigned *__restrict__ colB) {
-    __shared__ unsigned B_s[SCAN_BLOCK_COLS];
     __shared__ uint32_t acc_s[SCAN_WARPS][SCAN_BLOCK_CHUNKS][8];
     extern __shared__ int carry_s[];  // one int per row of the unit (only used when nblocks > 1)
 
@@ -151,8 +148,7 @@ scan_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks,
     for (int blk = nblocks - 1; blk >= 0; --blk) {
         const int bch0 = ch0 + blk * SCAN_BLOCK_CHUNKS;
         const int bn = min(SCAN_BLOCK_CHUNKS, ch1 - bch0);
-        int lg = 0;
-        while ((1 << lg) < bn) ++lg;
+        const int lg = bn > 1 ? 32 - __clz(bn - 1) : 0;
         const int nchp = 1 << lg;       // lanes per row
         const int rpw = 32 >> lg;       // rows per warp iteration
         const int lane_chunk = lane & (nchp - 1);
@@ -188,10 +184,9 @@ scan_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks,
         int it0 = warp;
         uint4 vnext[SCAN_UNROLL];
         if (it0 < n_iters) load_trip(it0, vnext);
-        // (the first loads are in flight while the shared B tile is cleared)
-        for (int i = threadIdx.x; i < bn * 32; i += SCAN_THREADS) B_s[i] = 0;
-        __syncthreads();
-        bool saw_gap = false;
+        // gap-run ends go straight to the task's (zero-initialised) B array with atomicMax: about one
+        // run per row, far cheaper than clearing and flushing a shared tile per CTA
+        unsigned *B = colB + (long long)t.col_off;
         // software pipelined by one trip: the loads of trip i+1 are in flight while trip i is processed
         for (; it0 < n_iters; it0 += SCAN_WARPS * SCAN_UNROLL) {
             uint4 v[SCAN_UNROLL];
@@ -226,10 +221,7 @@ scan_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks,
 #pragma unroll
             for (int u = 0; u < SCAN_UNROLL; ++u) {
                 gb[u] = 0u;
-                if (gm[u]) {
-                    saw_gap = true;
-                    gb[u] = scan_gap_local(gm[u], lane_chunk, colbase, a0, B_s);
-                }
+                if (gm[u]) gb[u] = scan_gap_local(gm[u], colbase, a0, B);
                 any_gb |= gb[u];
             }
             if (multi_block || __any_sync(0xffffffffu, any_gb != 0u)) {
@@ -238,7 +230,7 @@ scan_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks,
                     const int rl = min((it0 + u * SCAN_WARPS) * rpw + lane_slot, last_row);
                     if (multi_block || __any_sync(0xffffffffu, gb[u] != 0u))
                         scan_gap_rows(gb[u], lane, lane_chunk, nchp, colbase, a0, rl, row_count,
-                                      right_block_exists, multi_block, topmask, carry_s, B_s);
+                                      right_block_exists, multi_block, topmask, carry_s, B);
                 }
             }
         }
@@ -257,7 +249,7 @@ scan_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks,
                 acc_s[warp][lane_chunk][4 + j] = ~a_and[j];  // published as OR of complements
             }
         }
-        const int cta_saw_gap = __syncthreads_or(saw_gap ? 1 : 0);
+        __syncthreads();
         // merge warps, publish
         const long long word_base = ((long long)t.col_off >> 3) + (long long)(bch0 - ch0) * 4;
         for (int i = threadIdx.x; i < bn * 8; i += SCAN_THREADS) {
@@ -268,13 +260,6 @@ scan_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks,
             if (x) {
                 if (j < 4) atomicOr(&colOR[word_base + c * 4 + j], x);
                 else atomicOr(&colNOR[word_base + c * 4 + (j - 4)], x);
-            }
-        }
-        const long long col_base = (long long)t.col_off + (long long)(bch0 - ch0) * 32;
-        if (cta_saw_gap) {
-            for (int i = threadIdx.x; i < bn * 32; i += SCAN_THREADS) {
-                const unsigned b = B_s[i];
-                if (b) atomicMax(&colB[col_base + i], b);
             }
         }
         __syncthreads();

@@ -7,6 +7,7 @@
 #include <cstring>
 #define MPRG_HOST_EMU 1
 #define __device__
+#define __host__
 #define __global__
 #define __constant__ static
 #define __shared__ static
