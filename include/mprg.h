@@ -16,8 +16,11 @@
  *
  * Symbol codes of the 4-bit packed MSA (rows padded to 16 bytes = 32 columns with MPRG_SYM_PAD; inside
  * a 32-column chunk, column c is nibble c / 4 of the 32-bit little-endian word c % 4):
- *   '-' = 0, A C G T = 1..4, R Y K M S W = 5..10, N = 11, pad/disallowed = 15
- *   (gap = 0 makes the scan kernel's "row holds a gap" test a two-instruction zero-nibble test).
+ *   '-' = 0;  A C G T = 1 3 5 7;  R Y K = 9 11 13;  M S W = 2 4 6;  N = 8;  pad/disallowed = 15
+ *   (MPRG_ALPHABET[code] is the character).  The gap is the zero nibble and every common symbol --
+ *   the four bases and the padding -- is odd, so "these rows hold no gap in these columns" is one AND
+ *   over the words and a test of bit 0 of every nibble (scan kernel); the even codes (M S W N, rare)
+ *   only send the scan through its exact path.
  */
 #ifndef MPRG_H
 #define MPRG_H
@@ -36,7 +39,8 @@ extern "C" {
 #define MPRG_E_INTERNAL (-5)
 
 #define MPRG_SYM_GAP 0
-#define MPRG_SYM_N 11
+#define MPRG_SYM_N 8
+#define MPRG_ALPHABET "-AMCSGWTNR?Y?K??"
 #define MPRG_SYM_PAD 15
 
 #define MPRG_IV_MATCH 0

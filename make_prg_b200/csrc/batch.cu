@@ -14,10 +14,12 @@ __constant__ uint8_t c_sym_lut[256];
 
 static void build_lut(uint8_t *lut) {
     for (int i = 0; i < 256; ++i) lut[i] = SYM_PAD;
-    const char *order = "-ACGTRYKMSWN";
-    for (int i = 0; order[i]; ++i) {
-        lut[(uint8_t)order[i]] = (uint8_t)i;
-        if (order[i] >= 'A' && order[i] <= 'Z') lut[(uint8_t)(order[i] - 'A' + 'a')] = (uint8_t)i;
+    const char *alphabet = MPRG_ALPHABET;
+    for (int i = 0; i < 16; ++i) {
+        const char ch = alphabet[i];
+        if (ch == '?') continue;
+        lut[(uint8_t)ch] = (uint8_t)i;
+        if (ch >= 'A' && ch <= 'Z') lut[(uint8_t)(ch - 'A' + 'a')] = (uint8_t)i;
     }
 }
 
@@ -56,7 +58,7 @@ pack_rows_kernel(const uint8_t *__restrict__ ascii, const long long *__restrict_
                 code = c_sym_lut[ch];
                 if (code == SYM_PAD) f |= 1;
                 else if (code == SYM_N) f |= 2;
-                else if (code >= 5) f |= 4;
+                else if (sym_is_ambiguous(code)) f |= 4;
             }
             word |= code << (4 * j);
         }

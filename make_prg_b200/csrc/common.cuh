@@ -14,6 +14,12 @@ namespace mprg {
 constexpr int SYM_GAP = MPRG_SYM_GAP;
 constexpr int SYM_N = MPRG_SYM_N;
 constexpr int SYM_PAD = MPRG_SYM_PAD;
+// the four unambiguous bases are the odd codes below 8 (see mprg.h)
+__host__ __device__ __forceinline__ bool sym_is_base(int code) { return (code & 9) == 1; }
+// R Y K M S W: what is neither gap, base, N nor padding
+__host__ __device__ __forceinline__ bool sym_is_ambiguous(int code) {
+    return code != SYM_GAP && code != SYM_N && code != SYM_PAD && !sym_is_base(code);
+}
 constexpr int COLS_PER_CHUNK = 32;  // one 16-byte vector load = 32 columns of one row
 constexpr int CHUNK_BYTES = 16;
 
@@ -47,19 +53,22 @@ struct DInterval {
     int start, stop, type;
 };
 
-// A unit of scan work: a row range of one task (all its columns), handled by one CTA.
-// Self-contained (32 bytes, one vector load) so that a CTA needs a single dependent global load
-// before it can issue its first row loads.
+// A unit of scan work: a tile (row range x chunk range, at most 32 chunks) of one task, handled by
+// one warp.  Self-contained (48 bytes, three vector loads) so that a warp needs a single dependent
+// global load before it can issue its first row loads.
 struct ScanUnit {
     long long base;  // byte offset of the locus in the packed arena
     int stride;      // bytes per packed row
-    int rows_off;    // offset of the unit's first row index in the row arena, -1 => rows are consecutive
+    int rows_off;    // offset of the tile's first row index in the row arena, -1 => rows are consecutive
     int row_begin;   // first row (when rows_off < 0)
     int row_count;
-    int c0, c1;      // column window
+    int c0, c1;      // column window of the task
     int col_off;     // per-column outputs of the task (see DTask)
+    int ch_begin;    // first chunk of the tile (locus coordinates)
+    int ch_count;    // chunks of the tile, 1..32
     int pad;
 };
+static_assert(sizeof(ScanUnit) == 48, "ScanUnit is loaded as three 16-byte vectors");
 
 // Growable device buffer (never shrinks); all launches of a context share one stream, so reuse
 // across calls is ordered.

@@ -108,7 +108,7 @@ extract_kernel(const uint8_t *__restrict__ packed, const ExtractItem *__restrict
     if (it >= n_items) return;
     const ExtractItem e = items[it];
     const uint8_t *row = packed + e.base + (long long)e.row * e.stride;
-    const char *alphabet = "-ACGTRYKMSWN????";
+    const char *alphabet = MPRG_ALPHABET;
     int len = 0;
     for (int c0 = e.c0; c0 < e.c1; c0 += 32) {
         const int c = c0 + lane;

@@ -4,9 +4,8 @@
 
 namespace mprg {
 
-cudaError_t launch_scan(cudaStream_t stream, bool has_n, const uint8_t *packed, const DTask *d_tasks,
-                        const ScanUnit *d_units, int n_units, int max_unit_rows, const int *d_rows,
-                        uint32_t *colOR, uint32_t *colNOR, unsigned *colB);
+cudaError_t launch_scan(cudaStream_t stream, bool has_n, const uint8_t *packed, const ScanUnit *d_units,
+                        int n_units, const int *d_rows, uint32_t *colOR, uint32_t *colNOR, unsigned *colB);
 cudaError_t launch_classify(cudaStream_t stream, const DTask *d_tasks, int n_tasks,
                             const uint32_t *colOR, const uint32_t *colNOR, const unsigned *colB,
                             uint8_t *cls, int *reach, uint32_t *starbits);
@@ -24,7 +23,6 @@ struct Level {
     int n_tasks = 0;
     std::vector<DTask> tasks;
     std::vector<ScanUnit> units;
-    int max_unit_rows = 1;
     long long total_cols = 0;  // sum of chunk-aligned window widths (multiple of 32)
     long long total_iv = 0;    // interval arena entries
     double algo_bytes = 0;     // sum r*c/2 + 4*r (row subsets) + 5*c

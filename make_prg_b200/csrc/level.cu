@@ -7,8 +7,16 @@
 
 namespace mprg {
 
-constexpr int MAX_UNIT_ROWS = 1024;  // most rows of one task handled by one CTA (carry array in smem)
-constexpr int UNIT_ROW_QUANTUM = 16;  // rows one CTA consumes per trip (4 warps x 4 unrolled rows)
+constexpr int TILE_CHUNKS = 32;      // widest tile: one 512-byte row segment per warp load
+constexpr int TILE_ITER_QUANTUM = 4; // warp iterations one trip of the scan kernel consumes
+constexpr int MIN_TILE_ITERS = 16, MAX_TILE_ITERS = 1024;
+constexpr int SCAN_RESIDENT_WARPS_PER_SM = 28;  // 72 registers per thread
+
+static inline int pow2_ceil(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
 
 // call after the stream has been synchronised: device time of the level's scan launch
 void account_scan(mprg_ctx *ctx, const Level &lv) {
@@ -33,18 +41,26 @@ int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, 
     lv.tasks.resize(n_tasks);
     lv.has_n = batch->any_n;
     long long col_off = 0, iv_off = 0;
-    // A CTA streams its rows with a bounded number of loads in flight, so a unit's duration grows with
-    // its row count whatever the load of the machine: cut the level into enough units to fill every SM
-    // for several waves (but never below one trip's worth of rows).
-    long long level_rows = 0;
-    for (int i = 0; i < n_tasks; ++i) level_rows += h_tasks[i].n_rows > 0 ? h_tasks[i].n_rows : 0;
-    const long long target_units = (long long)std::max(ctx->sm_count, 1) * 8 * 4;
-    int unit_rows = (int)((level_rows + target_units - 1) / target_units);
-    unit_rows = ((unit_rows + UNIT_ROW_QUANTUM - 1) / UNIT_ROW_QUANTUM) * UNIT_ROW_QUANTUM;
-    unit_rows = std::min(std::max(unit_rows, 2 * UNIT_ROW_QUANTUM), MAX_UNIT_ROWS);
-    if (const char *env = getenv("MPRG_UNIT_ROWS")) {  // tuning knob for profiling runs
+    // A warp streams the rows of its tile with a bounded number of loads in flight, so a tile's
+    // duration grows with its height whatever the load of the machine: cut the level into enough tiles
+    // to fill every SM for a few waves (but never below a few trips' worth of rows).  Heights are
+    // counted in warp iterations: a tile of W (power of two) chunks takes 32 / W rows per iteration.
+    long long level_iters = 0;
+    for (int i = 0; i < n_tasks; ++i) {
+        const mprg_task &ht = h_tasks[i];
+        if (ht.n_rows <= 0 || ht.c1 < ht.c0) continue;
+        const int nch = std::max(((ht.c1 + 31) >> 5) - (ht.c0 >> 5), 1);
+        const int rem = nch % TILE_CHUNKS;
+        level_iters += (long long)(nch / TILE_CHUNKS) * ht.n_rows;
+        if (rem) level_iters += (ht.n_rows + (32 / pow2_ceil(rem)) - 1) / (32 / pow2_ceil(rem));
+    }
+    const long long target_tiles = (long long)std::max(ctx->sm_count, 1) * SCAN_RESIDENT_WARPS_PER_SM * 2;
+    int tile_iters = (int)((level_iters + target_tiles - 1) / target_tiles);
+    tile_iters = ((tile_iters + TILE_ITER_QUANTUM - 1) / TILE_ITER_QUANTUM) * TILE_ITER_QUANTUM;
+    tile_iters = std::min(std::max(tile_iters, MIN_TILE_ITERS), MAX_TILE_ITERS);
+    if (const char *env = getenv("MPRG_TILE_ITERS")) {  // tuning knob for profiling runs
         const int v = atoi(env);
-        if (v >= UNIT_ROW_QUANTUM && v <= MAX_UNIT_ROWS) unit_rows = v;
+        if (v >= TILE_ITER_QUANTUM && v <= MAX_TILE_ITERS) tile_iters = v;
     }
     for (int i = 0; i < n_tasks; ++i) {
         const mprg_task &ht = h_tasks[i];
@@ -71,15 +87,20 @@ int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, 
         iv_off += std::max(ht.c1 - ht.c0, 1);
         const double r = ht.n_rows, c = ht.c1 - ht.c0;
         lv.algo_bytes += r * c / 2 + (ht.rows_off >= 0 ? 4.0 * r : 0.0) + 5.0 * c;
-        // units of unit_rows rows (a multiple of the trip quantum); a short remainder joins the last unit
-        for (int rb = 0; rb < ht.n_rows;) {
-            int cnt = std::min(unit_rows, ht.n_rows - rb);
-            const int left = ht.n_rows - rb - cnt;
-            if (left > 0 && left < unit_rows / 2 && cnt + left <= MAX_UNIT_ROWS) cnt += left;
-            lv.units.push_back(ScanUnit{t.base, t.stride, t.rows_off >= 0 ? t.rows_off + rb : -1, rb, cnt,
-                                        t.c0, t.c1, t.col_off, 0});
-            lv.max_unit_rows = std::max(lv.max_unit_rows, cnt);
-            rb += cnt;
+        // tiles: full 32-chunk column strips, then the remainder strip; each strip cut into row ranges
+        // of tile_iters warp iterations (a short remainder joins the last tile)
+        const int ch0 = ht.c0 >> 5, ch1 = std::max((ht.c1 + 31) >> 5, ch0 + 1);
+        for (int cb = ch0; cb < ch1; cb += TILE_CHUNKS) {
+            const int bn = std::min(TILE_CHUNKS, ch1 - cb);
+            const int tile_rows = tile_iters * (32 / pow2_ceil(bn));
+            for (int rb = 0; rb < ht.n_rows;) {
+                int cnt = std::min(tile_rows, ht.n_rows - rb);
+                const int left = ht.n_rows - rb - cnt;
+                if (left > 0 && left < tile_rows / 2) cnt += left;
+                lv.units.push_back(ScanUnit{t.base, t.stride, t.rows_off >= 0 ? t.rows_off + rb : -1, rb, cnt,
+                                            t.c0, t.c1, t.col_off, cb, bn, 0});
+                rb += cnt;
+            }
         }
     }
     lv.total_cols = col_off;
@@ -123,8 +144,7 @@ int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, 
     uint32_t *colOR = ctx->d_colwords.as<uint32_t>();
     uint32_t *colNOR = colOR + words;
     MPRG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
-    MPRG_CUDA(ctx, launch_scan(s, lv.has_n, batch->d_packed, ctx->d_tasks.as<DTask>(),
-                               ctx->d_units.as<ScanUnit>(), (int)n_units, lv.max_unit_rows,
+    MPRG_CUDA(ctx, launch_scan(s, lv.has_n, batch->d_packed, ctx->d_units.as<ScanUnit>(), (int)n_units,
                                ctx->d_rows.as<int>(), colOR, colNOR, ctx->d_colB.as<unsigned>()));
     MPRG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     ctx->launches += n_units ? 1 : 0;

@@ -45,7 +45,7 @@ classify_kernel(const DTask *__restrict__ tasks, int n_tasks, const uint32_t *__
             b = colB[(long long)t.col_off + wi];
         }
         const bool uniform = ((orw ^ norw) == 15u);
-        const bool is_match = in && uniform && orw >= 1u && orw <= 4u;
+        const bool is_match = in && uniform && sym_is_base((int)orw);
         // inclusive prefix max over the warp, seeded with the running maximum
         unsigned m = b;
         for (int d = 1; d < 32; d <<= 1) {
@@ -56,7 +56,7 @@ classify_kernel(const DTask *__restrict__ tasks, int n_tasks, const uint32_t *__
         run_max = __shfl_sync(0xffffffffu, m, 31);
         const uint32_t star = __ballot_sync(0xffffffffu, in && !is_match);
         if (in) {
-            cls[(long long)t.col_off + wi] = is_match ? (uint8_t)("-ACGT"[orw]) : (uint8_t)'*';
+            cls[(long long)t.col_off + wi] = is_match ? (uint8_t)(MPRG_ALPHABET[orw]) : (uint8_t)'*';
             // end (c0-relative) of the furthest gap run covering column i, else i - 1
             reach[(long long)t.col_off + wi] = (m >= (unsigned)(wi + 1)) ? (int)m - 1 - shift : i - 1;
         }
@@ -242,7 +242,7 @@ demote_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ task
         bool bad = false;
         for (int c = s + lane; c <= e; c += 32) {
             const int sym = sym_at(row0, c);
-            bad |= sym >= 5;  // RYKMSW / N
+            bad |= sym != SYM_GAP && !sym_is_base(sym);  // RYKMSW / N
         }
         bad = __any_sync(0xffffffffu, bad);
         bool differ = false;

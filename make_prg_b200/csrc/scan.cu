@@ -15,14 +15,16 @@
 // Gap runs: for each row, each maximal run of '-' inside the window contributes
 //     B[run start] = max(B[run start], run end + 1)
 // (coordinates relative to the chunk-aligned window start).  The partition kernel turns B into
-// gap_reach by a prefix maximum: has_empty_sequence([s, e]) == (gap_reach[s] >= e).  Runs crossing a
-// 1024-column block are stitched with a per-row carry while the CTA walks the blocks right to left.
+// gap_reach by a prefix maximum: has_empty_sequence([s, e]) == (gap_reach[s] >= e).
 //
-// Work decomposition: one CTA per ScanUnit (a row range of one task, all of its columns).  Inside a
-// warp the 32 lanes cover (32 / nchp) rows x nchp chunks, nchp = chunks in the block rounded to a
-// power of two, so narrow windows still use all lanes.  Partial results are merged through shared
-// memory, then with atomicOr / atomicMax into the (zero-initialised) per-task column arrays, which
-// also merges units that split the rows of a very tall task.
+// Work decomposition: one WARP per ScanUnit = a tile (row range x up to 32 chunks) of one task; warps
+// never cooperate, there is no shared memory and no barrier.  Inside a warp the 32 lanes cover
+// (32 / W) rows x W chunks, W = chunks of the tile rounded up to a power of two, so narrow windows
+// (deep recursion levels) still use every lane and a wide tile reads 512 contiguous bytes per row.
+// A gap run that reaches the end of its chunk is continued by the warp reading on in that row (32
+// chunks per step), a run that starts in the first column of a chunk looks one column back: tiles need
+// no carry between them, so tall tasks are cut by rows and wide ones by columns freely.  Partial
+// results reach the (zero-initialised) per-task column arrays with atomicOr / atomicMax.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -30,7 +32,6 @@ namespace mprg {
 
 constexpr int SCAN_THREADS = 128;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
-constexpr int SCAN_BLOCK_CHUNKS = 32;                                  // chunks per column block
 constexpr int SCAN_UNROLL = 4;
 
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
@@ -44,6 +45,7 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
 // bit 4k+3 set iff nibble k of w is zero (the gap code), exact: no carry crosses a nibble
 __device__ __forceinline__ uint32_t zero_nibbles(uint32_t w) {
     static_assert(SYM_GAP == 0, "the zero-nibble test assumes gap == 0");
+    static_assert((SYM_PAD & 1) == 1, "padding must pass the odd-code (no gap) filter");
     return ~(((w & 0x77777777u) + 0x77777777u) | w) & 0x88888888u;
 }
 
@@ -61,222 +63,208 @@ __device__ __forceinline__ uint32_t nibble_eq_maskF(uint32_t w, uint32_t pattern
     return (~t & 0x11111111u) * 15u;
 }
 
-// Gap runs that stay inside the lane's chunk (neither its first nor its last column is a gap) need no
-// cooperation: the common case for short indels.  Returns the mask when the lane needs the
-// cooperative path (a run touches a chunk border), 0 otherwise.
-__device__ __forceinline__ uint32_t scan_gap_local(uint32_t g, int colbase, int a0, unsigned *B) {
-    if (g & 0x80000001u) return g;
-    uint32_t starts = g & ~(g << 1);
-    while (starts) {
-        const int i = __ffs(starts) - 1;
-        starts &= starts - 1;
-        const int ones = __ffs(~(g >> i)) - 1;
-        atomicMax(&B[colbase - a0 + i], (unsigned)(colbase + i + ones - a0));
+// The warp reads on in the row `rp` from chunk k0: number of consecutive gap columns that follow, up
+// to the end of the window (32 chunks per step; only runs longer than a chunk, or runs that leave the
+// tile, come here).  Warp-uniform call, every lane returns the count.
+__device__ __forceinline__ int scan_walk(const uint8_t *rp, int k0, int lane, int c1) {
+    int e = 0;
+    while (true) {
+        const int k = k0 + lane;
+        uint32_t m = 0u;
+        if ((k << 5) < c1) {
+            m = gap_mask32(ld_stream(reinterpret_cast<const uint4 *>(rp + ((long long)k << 4))));
+            const int hi = c1 - (k << 5);
+            if (hi < 32) m &= (1u << hi) - 1u;
+        }
+        const uint32_t fullb = __ballot_sync(0xffffffffu, m == 0xffffffffu);
+        if (fullb == 0xffffffffu) {
+            e += 1024;
+            k0 += 32;
+            continue;
+        }
+        const int nf = __ffs(~fullb) - 1;
+        const int lead = __ffs(~m) - 1;
+        return e + 32 * nf + __shfl_sync(0xffffffffu, lead, nf);
     }
-    return 0u;
 }
 
-// Slow path of one warp iteration (one row per `nchp` lanes) that holds at least one gap: record
-// B[run start] = run end + 1 for every gap run, stitching runs across lanes (ballots + one shuffle)
-// and across 1024-column blocks (carry_s).
-__device__ __forceinline__ void scan_gap_rows(uint32_t g, int lane,
-                                              int lane_chunk, int nchp, int colbase, int a0, int rl,
-                                              int row_count, bool right_block_exists, bool multi_block,
-                                              uint32_t topmask, int *carry_s, unsigned *B) {
-    const uint32_t firstb = __ballot_sync(0xffffffffu, g & 1u);
-    const uint32_t lastb = __ballot_sync(0xffffffffu, g >> 31);
-    const uint32_t fullb = __ballot_sync(0xffffffffu, g == 0xffffffffu);
-    const int seg_base = lane - lane_chunk;
-    const uint32_t seg_mask = (nchp == 32 ? 0xffffffffu : ((1u << nchp) - 1u)) << seg_base;
-    int carry_in = 0;
-    if (right_block_exists && rl < row_count) carry_in = carry_s[rl];
-    // does any run of this warp iteration continue past its chunk?  (warp-uniform: `topmask` marks the
-    // last lane of every row segment, whose right neighbour is the block to the right, not lane + 1)
-    const uint32_t cont = lastb & (((firstb >> 1) & ~topmask) | (right_block_exists ? topmask : 0u));
-    int ext = 0;  // gap columns that follow the end of my chunk in the same row
-    const int lead = (g == 0xffffffffu) ? 32 : (__ffs(~g) - 1);
-    if (cont != 0u || multi_block) {
-        // consecutive full chunks after mine (inside the row's lanes), then the partial lead of the next
-        const uint32_t after = (lane == 31) ? 0u : ((fullb & seg_mask) >> (lane + 1));
-        int nfull = (after == 0xffffffffu) ? 32 : (__ffs(~after) - 1);
-        const int remaining = nchp - 1 - lane_chunk;
-        nfull = min(nfull, remaining);
-        const int k = lane + 1 + nfull;  // first lane after the full ones
-        const bool k_in_seg = (nfull < remaining);
-        const int lead_k = __shfl_sync(0xffffffffu, lead, k_in_seg ? k : lane);
-        ext = 32 * nfull + (k_in_seg ? lead_k : carry_in);
-        if (multi_block && lane_chunk == 0 && rl < row_count)
-            carry_s[rl] = (g == 0xffffffffu) ? 32 + ext : lead;
+// Gap path of one warp iteration (warp-uniform call).  g = gap mask of the lane's chunk clipped to the
+// task window, todo = the lane has runs to record.  Records B[run start] = run end + 1 (columns
+// relative to a0) for every maximal gap run of the window that starts in the lane's chunk.  The masks
+// of the two neighbouring chunks come from the neighbouring lanes; only a run that covers the whole
+// next chunk, or leaves the tile, makes the warp read on in that row (scan_walk).
+struct ScanLane {
+    int chunk, lane, lane_chunk, bn, c0, c1, a0;
+};
+template <typename RowPtr>
+__device__ __forceinline__ void scan_gap_rows(uint32_t g, bool todo, const ScanLane &L, RowPtr row_ptr,
+                                              unsigned *B) {
+    const int colbase = L.chunk << 5;
+    uint32_t gn = __shfl_down_sync(0xffffffffu, g, 1);
+    uint32_t gp = __shfl_up_sync(0xffffffffu, g, 1);
+    // tile edges: the neighbour is not a lane of this row
+    if (L.lane_chunk >= L.bn - 1) gn = (colbase + 32 < L.c1) ? 0xffffffffu : 0u;  // unknown => "read on"
+    uint32_t prev = gp >> 31;
+    if (L.lane_chunk == 0) {
+        prev = 0u;
+        // first chunk of a tile that is not the first of the window: look one column back
+        // (column 31 of the previous chunk = high nibble of its last byte)
+        if (todo && (g & 1u) && colbase > L.c0)
+            prev = ((row_ptr()[(L.chunk << 4) - 1] >> 4) == SYM_GAP) ? 1u : 0u;
     }
-    const uint32_t prev = (lane_chunk == 0) ? 0u : ((lastb >> (lane - 1)) & 1u);
-    uint32_t starts = g & ~((g << 1) | prev);
-    while (starts) {
-        const int i = __ffs(starts) - 1;
-        starts &= starts - 1;
-        const uint32_t x = ~(g >> i);
-        const int ones = x ? (__ffs(x) - 1) : 32;
-        int end_col = colbase + i + ones - 1;
-        if (i + ones == 32) end_col += ext;
-        atomicMax(&B[colbase - a0 + i], (unsigned)(end_col - a0 + 1));
+    const uint32_t starts = g & ~((g << 1) | prev);
+    const bool reaches_end = (g >> 31) != 0u;
+    // gap columns that follow the end of my chunk in this row
+    int ext = reaches_end ? ((gn == 0xffffffffu) ? 32 : (__ffs(~gn) - 1)) : 0;
+    uint32_t need = __ballot_sync(0xffffffffu, todo && reaches_end && gn == 0xffffffffu && starts != 0u);
+    if (need) {
+        const uint8_t *mine = row_ptr();
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const uint8_t *rp = reinterpret_cast<const uint8_t *>(
+                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(mine), src));
+            const int k0 = __shfl_sync(0xffffffffu, L.chunk, src) + 1;
+            const int e = scan_walk(rp, k0, L.lane, L.c1);
+            if (L.lane == src) ext = e;
+        }
+    }
+    if (todo) {
+        uint32_t st = starts;
+        while (st) {
+            const int i = __ffs(st) - 1;
+            st &= st - 1;
+            const uint32_t x = ~(g >> i);
+            const int ones = x ? (__ffs(x) - 1) : 32;
+            int end = colbase + i + ones;  // exclusive
+            if (i + ones == 32) end += ext;
+            atomicMax(&B[colbase + i - L.a0], (unsigned)(end - L.a0));
+        }
     }
 }
 
 template <bool HAS_N>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks,
-            const ScanUnit *__restrict__ units, const int *__restrict__ rows_arena,
-            uint32_t *__restrict__ colOR, uint32_t *__restrict__ colNOR,
-            unsigned *__restrict__ colB) {
-    __shared__ uint32_t acc_s[SCAN_WARPS][SCAN_BLOCK_CHUNKS][8];
-    extern __shared__ int carry_s[];  // one int per row of the unit (only used when nblocks > 1)
-
-    const ScanUnit t = units[blockIdx.x];
-    const ScanUnit &unit = t;
+scan_kernel(const uint8_t *__restrict__ packed, const ScanUnit *__restrict__ units, int n_units,
+            const int *__restrict__ rows_arena, uint32_t *__restrict__ colOR,
+            uint32_t *__restrict__ colNOR, unsigned *__restrict__ colB) {
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int ch0 = t.c0 >> 5;
-    const int ch1 = (t.c1 + 31) >> 5;
-    const int nch = ch1 - ch0;
-    if (nch <= 0 || unit.row_count <= 0) return;
-    const int a0 = ch0 << 5;  // chunk-aligned window start (columns)
-    const int nblocks = (nch + SCAN_BLOCK_CHUNKS - 1) / SCAN_BLOCK_CHUNKS;
-    const bool multi_block = nblocks > 1;
+    const int ui = blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5);
+    if (ui >= n_units) return;
+    const ScanUnit t = units[ui];
+    const int bn = t.ch_count;
+    const int row_count = t.row_count;
+    if (bn <= 0 || row_count <= 0) return;
+    const int a0 = (t.c0 >> 5) << 5;  // chunk-aligned window start (columns)
     const int *rows = t.rows_off >= 0 ? rows_arena + t.rows_off : nullptr;
     const uint8_t *msa = packed + t.base;
-    const int row_count = unit.row_count;
 
-    for (int blk = nblocks - 1; blk >= 0; --blk) {
-        const int bch0 = ch0 + blk * SCAN_BLOCK_CHUNKS;
-        const int bn = min(SCAN_BLOCK_CHUNKS, ch1 - bch0);
-        const int lg = bn > 1 ? 32 - __clz(bn - 1) : 0;
-        const int nchp = 1 << lg;       // lanes per row
-        const int rpw = 32 >> lg;       // rows per warp iteration
-        const int lane_chunk = lane & (nchp - 1);
-        const int lane_slot = lane >> lg;
-        const bool chunk_valid = lane_chunk < bn;
-        const int chunk = bch0 + min(lane_chunk, bn - 1);  // lanes beyond the block re-read its last chunk
-        const int colbase = (bch0 + lane_chunk) << 5;
-        // window mask: bit i set iff c0 <= colbase + i < c1 (0 for lanes beyond the block)
-        uint32_t wmask = 0;
-        if (chunk_valid) {
-            const int lo = max(t.c0 - colbase, 0);
-            const int hi = min(t.c1 - colbase, 32);
-            if (hi > lo) wmask = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-        }
-        const bool right_block_exists = blk < nblocks - 1;
-        const uint32_t topmask = __ballot_sync(0xffffffffu, lane_chunk == nchp - 1);
-        const uint8_t *col_ptr = msa + (long long)chunk * CHUNK_BYTES;
+    const int lg = bn > 1 ? 32 - __clz(bn - 1) : 0;
+    const int rpw = 32 >> lg;  // rows per warp iteration
+    const int lane_chunk = lane & ((1 << lg) - 1);
+    const int lane_slot = lane >> lg;
+    const bool chunk_valid = lane_chunk < bn;
+    const int chunk = t.ch_begin + min(lane_chunk, bn - 1);  // lanes beyond the tile re-read its last chunk
+    const int colbase = chunk << 5;
+    // window mask: bit i set iff c0 <= colbase + i < c1 (0 for lanes beyond the tile)
+    uint32_t wmask = 0;
+    if (chunk_valid) {
+        const int lo = max(t.c0 - colbase, 0);
+        const int hi = min(t.c1 - colbase, 32);
+        if (hi > lo) wmask = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+    }
+    const uint8_t *col_ptr = msa + ((long long)chunk << 4);
+    unsigned *B = colB + (long long)t.col_off;
 
-        uint32_t a_or[4] = {0, 0, 0, 0};
-        uint32_t a_and[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-        const int n_iters = (row_count + rpw - 1) / rpw;
-        // Every reduction here is idempotent (OR, AND, max), so missing rows at the end of the unit are
-        // replaced by its last row: no tail code, and all lanes of every trip do useful, uniform work.
-        const int last_row = row_count - 1;
-        auto load_trip = [&](int first_it, uint4 *dst) {
+    uint32_t a_or[4] = {0, 0, 0, 0};
+    uint32_t a_and[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    const int n_iters = (row_count + rpw - 1) / rpw;
+    // Every reduction here is idempotent (OR, AND, max), so missing rows at the end of the tile are
+    // replaced by its last row: no tail code, and all lanes of every trip do useful, uniform work.
+    const int last_row = row_count - 1;
+    auto row_of = [&](int it) {
+        const int rl = min(it * rpw + lane_slot, last_row);
+        return rows ? rows[rl] : t.row_begin + rl;
+    };
+    auto load_trip = [&](int first_it, uint4 *dst) {
 #pragma unroll
-            for (int u = 0; u < SCAN_UNROLL; ++u) {
-                const int rl = min((first_it + u * SCAN_WARPS) * rpw + lane_slot, last_row);
-                const int row = rows ? rows[rl] : unit.row_begin + rl;
-                dst[u] = ld_stream(reinterpret_cast<const uint4 *>(col_ptr + (long long)row * t.stride));
-            }
-        };
-        int it0 = warp;
-        uint4 vnext[SCAN_UNROLL];
-        if (it0 < n_iters) load_trip(it0, vnext);
-        // gap-run ends go straight to the task's (zero-initialised) B array with atomicMax: about one
-        // run per row, far cheaper than clearing and flushing a shared tile per CTA
-        unsigned *B = colB + (long long)t.col_off;
-        // software pipelined by one trip: the loads of trip i+1 are in flight while trip i is processed
-        for (; it0 < n_iters; it0 += SCAN_WARPS * SCAN_UNROLL) {
-            uint4 v[SCAN_UNROLL];
+        for (int u = 0; u < SCAN_UNROLL; ++u)
+            dst[u] = ld_stream(reinterpret_cast<const uint4 *>(col_ptr + (long long)row_of(first_it + u) * t.stride));
+    };
+    const ScanLane L = {chunk, lane, lane_chunk, bn, t.c0, t.c1, a0};
+    uint32_t g_done = 0u;  // last gap mask (interior runs only) this lane has recorded
+    uint4 vnext[SCAN_UNROLL];
+    load_trip(0, vnext);
+    // software pipelined by one trip: the loads of trip i+1 are in flight while trip i is processed
+    for (int it0 = 0; it0 < n_iters; it0 += SCAN_UNROLL) {
+        uint4 v[SCAN_UNROLL];
 #pragma unroll
-            for (int u = 0; u < SCAN_UNROLL; ++u) v[u] = vnext[u];
-            const int nit = it0 + SCAN_WARPS * SCAN_UNROLL;
-            if (nit < n_iters) load_trip(nit, vnext);
-            uint32_t gm[SCAN_UNROLL];  // gap mask of my chunk in each of the rows (0 outside the window)
+        for (int u = 0; u < SCAN_UNROLL; ++u) v[u] = vnext[u];
+        if (it0 + SCAN_UNROLL < n_iters) load_trip(it0 + SCAN_UNROLL, vnext);
+        uint32_t gm[SCAN_UNROLL];  // gap mask of my chunk in each of the rows (0 outside the window)
 #pragma unroll
-            for (int u = 0; u < SCAN_UNROLL; u += 2) {
-                const uint32_t wa[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                const uint32_t wb[4] = {v[u + 1].x, v[u + 1].y, v[u + 1].z, v[u + 1].w};
+        for (int u = 0; u < SCAN_UNROLL; u += 2) {
+            const uint32_t wa[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            const uint32_t wb[4] = {v[u + 1].x, v[u + 1].y, v[u + 1].z, v[u + 1].w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (HAS_N) {
-                        const uint32_t ka = ~nibble_eq_maskF(wa[j], 0xBBBBBBBBu);
-                        const uint32_t kb = ~nibble_eq_maskF(wb[j], 0xBBBBBBBBu);
-                        a_or[j] |= (wa[j] & ka) | (wb[j] & kb);
-                        a_and[j] &= (wa[j] | ~ka) & (wb[j] | ~kb);
-                    } else {
-                        a_or[j] |= wa[j] | wb[j];   // one LOP3 for two rows
-                        a_and[j] &= wa[j] & wb[j];  // one LOP3 for two rows
-                    }
+            for (int j = 0; j < 4; ++j) {
+                if (HAS_N) {
+                    const uint32_t ka = ~nibble_eq_maskF(wa[j], SYM_N * 0x11111111u);
+                    const uint32_t kb = ~nibble_eq_maskF(wb[j], SYM_N * 0x11111111u);
+                    a_or[j] |= (wa[j] & ka) | (wb[j] & kb);
+                    a_and[j] &= (wa[j] | ~ka) & (wb[j] | ~kb);
+                } else {
+                    a_or[j] |= wa[j] | wb[j];   // one LOP3 for two rows
+                    a_and[j] &= wa[j] & wb[j];  // one LOP3 for two rows
                 }
+            }
+            // Bases and padding are odd codes and the gap is 0: a chunk whose 32 nibbles all have bit 0
+            // set holds no gap.  Three LOP3 and a compare per row; the exact mask is only built for the
+            // chunks that fail the test.
+            gm[u] = 0u;
+            gm[u + 1] = 0u;
+            if (((wa[0] & wa[1] & wa[2]) & wa[3] & 0x11111111u) != 0x11111111u)
                 gm[u] = gap_mask32(v[u]) & wmask;
+            if (((wb[0] & wb[1] & wb[2]) & wb[3] & 0x11111111u) != 0x11111111u)
                 gm[u + 1] = gap_mask32(v[u + 1]) & wmask;
-            }
-            // lanes that hold a gap resolve their interior runs on their own; only runs touching a chunk
-            // border (or multi-block rows, which must hand a carry to the next block) go cooperative
-            uint32_t gb[SCAN_UNROLL];
-            uint32_t any_gb = 0;
+        }
 #pragma unroll
-            for (int u = 0; u < SCAN_UNROLL; ++u) {
-                gb[u] = 0u;
-                if (gm[u]) gb[u] = scan_gap_local(gm[u], colbase, a0, B);
-                any_gb |= gb[u];
-            }
-            if (multi_block || __any_sync(0xffffffffu, any_gb != 0u)) {
-#pragma unroll
-                for (int u = 0; u < SCAN_UNROLL; ++u) {
-                    const int rl = min((it0 + u * SCAN_WARPS) * rpw + lane_slot, last_row);
-                    if (multi_block || __any_sync(0xffffffffu, gb[u] != 0u))
-                        scan_gap_rows(gb[u], lane, lane_chunk, nchp, colbase, a0, rl, row_count,
-                                      right_block_exists, multi_block, topmask, carry_s, B);
-                }
+        for (int u = 0; u < SCAN_UNROLL; ++u) {
+            // Rows of one clade share their deletions: a mask equal to the last one this lane recorded
+            // (runs strictly inside the chunk, so nothing depends on the neighbours) adds nothing.
+            const bool todo = gm[u] != 0u && gm[u] != g_done;
+            if (__any_sync(0xffffffffu, todo)) {
+                scan_gap_rows(gm[u], todo, L, [&]() { return msa + (long long)row_of(it0 + u) * t.stride; }, B);
+                if (todo && (gm[u] & 0x80000001u) == 0u) g_done = gm[u];
             }
         }
-        // merge row slots inside the warp
-        for (int d = nchp; d < 32; d <<= 1) {
+    }
+    // merge the row slots of the warp, publish
+    for (int d = 1 << lg; d < 32; d <<= 1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                a_or[j] |= __shfl_xor_sync(0xffffffffu, a_or[j], d);
-                a_and[j] &= __shfl_xor_sync(0xffffffffu, a_and[j], d);
-            }
+        for (int j = 0; j < 4; ++j) {
+            a_or[j] |= __shfl_xor_sync(0xffffffffu, a_or[j], d);
+            a_and[j] &= __shfl_xor_sync(0xffffffffu, a_and[j], d);
         }
-        if (lane_slot == 0 && chunk_valid) {
+    }
+    if (lane_slot == 0 && chunk_valid) {
+        const long long word = (((long long)t.col_off + (colbase - a0)) >> 3);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                acc_s[warp][lane_chunk][j] = a_or[j];
-                acc_s[warp][lane_chunk][4 + j] = ~a_and[j];  // published as OR of complements
-            }
+        for (int j = 0; j < 4; ++j) {
+            if (a_or[j]) atomicOr(&colOR[word + j], a_or[j]);
+            if (~a_and[j]) atomicOr(&colNOR[word + j], ~a_and[j]);  // published as OR of complements
         }
-        __syncthreads();
-        // merge warps, publish
-        const long long word_base = ((long long)t.col_off >> 3) + (long long)(bch0 - ch0) * 4;
-        for (int i = threadIdx.x; i < bn * 8; i += SCAN_THREADS) {
-            const int c = i >> 3, j = i & 7;
-            uint32_t x = 0;
-#pragma unroll
-            for (int w = 0; w < SCAN_WARPS; ++w) x |= acc_s[w][c][j];
-            if (x) {
-                if (j < 4) atomicOr(&colOR[word_base + c * 4 + j], x);
-                else atomicOr(&colNOR[word_base + c * 4 + (j - 4)], x);
-            }
-        }
-        __syncthreads();
     }
 }
 
-cudaError_t launch_scan(cudaStream_t stream, bool has_n, const uint8_t *packed, const DTask *d_tasks,
-                        const ScanUnit *d_units, int n_units, int max_unit_rows,
-                        const int *d_rows, uint32_t *colOR, uint32_t *colNOR, unsigned *colB) {
+cudaError_t launch_scan(cudaStream_t stream, bool has_n, const uint8_t *packed, const ScanUnit *d_units,
+                        int n_units, const int *d_rows, uint32_t *colOR, uint32_t *colNOR, unsigned *colB) {
     if (n_units <= 0) return cudaSuccess;
-    const size_t smem = sizeof(int) * (size_t)max_unit_rows;
+    const int grid = (n_units + SCAN_WARPS - 1) / SCAN_WARPS;
     if (has_n)
-        scan_kernel<true><<<n_units, SCAN_THREADS, smem, stream>>>(packed, d_tasks, d_units, d_rows,
-                                                                    colOR, colNOR, colB);
+        scan_kernel<true><<<grid, SCAN_THREADS, 0, stream>>>(packed, d_units, n_units, d_rows, colOR, colNOR, colB);
     else
-        scan_kernel<false><<<n_units, SCAN_THREADS, smem, stream>>>(packed, d_tasks, d_units, d_rows,
-                                                                     colOR, colNOR, colB);
+        scan_kernel<false><<<grid, SCAN_THREADS, 0, stream>>>(packed, d_units, n_units, d_rows, colOR, colNOR, colB);
     return cudaGetLastError();
 }
 

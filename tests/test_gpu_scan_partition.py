@@ -33,7 +33,7 @@ def test_pack_roundtrip(ctx):
     alphabet = np.frombuffer(b"ACGT-RYKMSWNacgtXZ", np.uint8)
     mats = [alphabet[rng.integers(0, len(alphabet), (r, c))] for r, c in [(3, 1), (5, 31), (4, 32), (7, 33), (2, 100)]]
     batch = ctx.upload(mats)
-    lut = {ch: i for i, ch in enumerate(b"-ACGTRYKMSWN")}
+    lut = {ch: i for i, ch in enumerate(b"-AMCSGWTNR?Y?K??") if ch != ord("?")}
     for l, M in enumerate(mats):
         P = batch.packed(l)
         for r in range(M.shape[0]):
