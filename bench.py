@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--loci", type=int, default=LOCI_PER_GPU)
+    ap.add_argument("--no-big", action="store_true", help="skip the 8x-size launch of the roofline pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -273,7 +274,41 @@ def main():
         torch.cuda.synchronize()
         ctx.partition_tasks(batch, root_tasks, MIN_MATCH)
     iso_bytes, iso_ms = ctx.scan_log(reset=True)
+    # yardstick: a bare streaming read of the same packed batch (same tile shape, no other work), same
+    # timing method -- what the HBM system delivers for a launch of this size
+    yard = []
+    for _ in range(max(args.steps, 5) + 2):
+        flush.zero_()
+        torch.cuda.synchronize()
+        yard.append(ctx.read_yardstick(batch))
+    yard = yard[2:]
     batch.free()
+    # the same kernel on a launch 8x the size (the batch repeated), to separate launch-size effects from
+    # kernel quality: 8,000 root tasks, 840 MB per launch
+    big = None
+    if rank == 0 and not args.no_big:
+        reps8 = 8
+        host8 = np.concatenate([host_np] * reps8)
+        batch8 = ctx.upload((host8, shapes * reps8))
+        tasks8 = [(i, None, 0, COLS) for i in range(n_loci * reps8)]
+        for _ in range(2):
+            ctx.partition_tasks(batch8, tasks8, MIN_MATCH)
+        ctx.scan_log(reset=True)
+        for _ in range(5):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ctx.partition_tasks(batch8, tasks8, MIN_MATCH)
+        b8, m8 = ctx.scan_log(reset=True)
+        y8 = []
+        for _ in range(5):
+            flush.zero_()
+            torch.cuda.synchronize()
+            y8.append(ctx.read_yardstick(batch8))
+        batch8.free()
+        del host8
+        big = {"loci": n_loci * reps8, "bytes_per_launch": float(b8.mean()), "ms_per_launch": float(m8.mean()),
+               "achieved": float(b8.sum() / (m8.sum() * 1e-3) / 1e9),
+               "bare_read_gbs": float(sum(b for b, _ in y8) / (sum(m for _, m in y8) * 1e-3) / 1e9)}
 
     # ---- end to end: host buffers in, PRG strings out ----
     for _ in range(2):
@@ -317,6 +352,13 @@ def main():
                 "kernel": "scan_kernel<false>, root-level launch over the whole batch, timed alone",
                 "bytes_per_launch": float(iso_bytes.mean()), "ms_per_launch": float(iso_ms.mean()),
                 "launches_timed": int(len(iso_bytes)), "peak_source": peak_src,
+                "bare_read_same_launch": {
+                    "note": "one bare streaming read of the same packed batch (mprg_read_yardstick), same "
+                            "timing method: the ceiling for a launch of this size",
+                    "gbs": float(sum(b for b, _ in yard) / (sum(m for _, m in yard) * 1e-3) / 1e9),
+                    "frac_of_peak": float(sum(b for b, _ in yard) / (sum(m for _, m in yard) * 1e-3) / 1e9) / peak},
+                "launch_8x": None if big is None else dict(big, frac=big["achieved"] / peak,
+                                                           bare_read_frac=big["bare_read_gbs"] / peak),
                 "in_step": {"note": "same kernel inside the timed steps: one launch per worker stream and "
                                     "recursion level, launches of different streams overlap",
                             "launches_per_step": len(log_bytes) / args.steps,

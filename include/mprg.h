@@ -96,6 +96,11 @@ int mprg_copy_stats(mprg_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes, int r
 int mprg_timer(mprg_ctx *ctx, int op, double *ms);
 /* per-launch log of the column-scan kernel (algorithmic bytes, device ms), newest last */
 int mprg_scan_log(mprg_ctx *ctx, double *bytes, double *ms, int32_t capacity, int32_t *n, int reset);
+/* Measurement aid for the roofline of the scan kernel: stream the packed batch once with the scan's
+ * own access pattern (one warp per 16-row x 512-byte tile, 128-bit ld.global.nc) and nothing else;
+ * *ms = device time of that one launch (CUDA events on the context's stream), *bytes = bytes read.
+ * What a bare read of the same bytes reaches at this launch size bounds what the scan can reach. */
+int mprg_read_yardstick(mprg_ctx *ctx, const mprg_batch *batch, double *bytes, double *ms);
 
 /* ---- loader -> HBM (replaces the in-memory Biopython MSA of io_utils.py:17-49) --------------- */
 /* h_ascii: concatenated row-major ASCII matrices (upper or lower case, N already replaced by the

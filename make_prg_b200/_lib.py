@@ -56,6 +56,7 @@ SIGNATURES = {
     "mprg_copy_stats": (C.c_int, [P, C.POINTER(I64), C.POINTER(I64), C.c_int]),
     "mprg_timer": (C.c_int, [P, C.c_int, C.POINTER(C.c_double)]),
     "mprg_scan_log": (C.c_int, [P, P, P, I32, C.POINTER(I32), C.c_int]),
+    "mprg_read_yardstick": (C.c_int, [P, P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mprg_batch_upload": (C.c_int, [P, P, P, P, P, I32, C.POINTER(P)]),
     "mprg_batch_free": (None, [P, P]),
     "mprg_batch_flags": (C.c_int, [P, P, P]),

@@ -122,6 +122,54 @@ extern "C" int mprg_timer(mprg_ctx *ctx, int op, double *ms) {
     return MPRG_OK;
 }
 
+namespace mprg {
+// bare streaming read with the scan kernel's tile shape (measurement aid, mprg_read_yardstick)
+__global__ void __launch_bounds__(128)
+read_yardstick_kernel(const uint4 *__restrict__ p, long long n_tiles, long long n_vec, unsigned *sink) {
+    const int lane = threadIdx.x & 31;
+    const long long tile = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    const long long first = tile * 16 * 32 + lane;  // 16 rows of 32 vectors
+    uint32_t a = 0;
+    uint4 v[8];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long i = first + (half * 8 + u) * 32;
+            v[u] = make_uint4(0, 0, 0, 0);
+            if (i < n_vec)
+                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(p + i));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a |= v[u].x | v[u].y | v[u].z | v[u].w;
+    }
+    if (a == 0x5A5A5A5Au) atomicOr(sink, a);  // never true for packed symbols in practice; keeps the loads
+}
+}  // namespace mprg
+
+extern "C" int mprg_read_yardstick(mprg_ctx *ctx, const mprg_batch *batch, double *bytes, double *ms) {
+    if (!ctx || !batch || !batch->d_packed) return MPRG_E_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    const long long n_vec = batch->packed_bytes / 16;
+    const long long n_tiles = (n_vec + 511) / 512;
+    if (n_tiles <= 0) return MPRG_E_BAD_ARG;
+    MPRG_CUDA(ctx, ctx->d_misc.reserve(64));
+    MPRG_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    mprg::read_yardstick_kernel<<<(unsigned)((n_tiles + 3) / 4), 128, 0, ctx->stream>>>(
+        reinterpret_cast<const uint4 *>(batch->d_packed), n_tiles, n_vec, ctx->d_misc.as<unsigned>());
+    MPRG_CUDA(ctx, cudaGetLastError());
+    MPRG_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+    MPRG_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
+    float f = 0;
+    MPRG_CUDA(ctx, cudaEventElapsedTime(&f, ctx->ev_t0, ctx->ev_t1));
+    ctx->launches++;
+    if (ms) *ms = f;
+    if (bytes) *bytes = (double)n_vec * 16.0;
+    return MPRG_OK;
+}
+
 extern "C" int mprg_scan_log(mprg_ctx *ctx, double *bytes, double *ms, int32_t capacity, int32_t *n,
                              int reset) {
     if (!ctx || !n) return MPRG_E_BAD_ARG;

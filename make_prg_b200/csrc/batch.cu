@@ -59,6 +59,7 @@ pack_rows_kernel(const uint8_t *__restrict__ ascii, const long long *__restrict_
                 if (code == SYM_PAD) f |= 1;
                 else if (code == SYM_N) f |= 2;
                 else if (sym_is_ambiguous(code)) f |= 4;
+                if (code != SYM_GAP && !(code & 1u)) f |= 8;  // even code: the scan needs its exact gap test
             }
             word |= code << (4 * j);
         }

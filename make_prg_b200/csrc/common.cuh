@@ -66,7 +66,7 @@ struct ScanUnit {
     int col_off;     // per-column outputs of the task (see DTask)
     int ch_begin;    // first chunk of the tile (locus coordinates)
     int ch_count;    // chunks of the tile, 1..32
-    int pad;
+    int flags;       // bit0: the locus holds even symbol codes (M S W N): exact gap test
 };
 static_assert(sizeof(ScanUnit) == 48, "ScanUnit is loaded as three 16-byte vectors");
 

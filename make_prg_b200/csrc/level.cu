@@ -9,7 +9,7 @@ namespace mprg {
 
 constexpr int TILE_CHUNKS = 32;      // widest tile: one 512-byte row segment per warp load
 constexpr int TILE_ITER_QUANTUM = 4; // warp iterations one trip of the scan kernel consumes
-constexpr int MIN_TILE_ITERS = 16, MAX_TILE_ITERS = 1024;
+constexpr int MIN_TILE_ITERS = 12, MAX_TILE_ITERS = 32;  // sweeps in DESIGN.md section 7
 constexpr int SCAN_RESIDENT_WARPS_PER_SM = 28;  // 72 registers per thread
 
 static inline int pow2_ceil(int x) {
@@ -54,13 +54,13 @@ int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, 
         level_iters += (long long)(nch / TILE_CHUNKS) * ht.n_rows;
         if (rem) level_iters += (ht.n_rows + (32 / pow2_ceil(rem)) - 1) / (32 / pow2_ceil(rem));
     }
-    const long long target_tiles = (long long)std::max(ctx->sm_count, 1) * SCAN_RESIDENT_WARPS_PER_SM * 2;
+    const long long target_tiles = (long long)std::max(ctx->sm_count, 1) * SCAN_RESIDENT_WARPS_PER_SM * 4;
     int tile_iters = (int)((level_iters + target_tiles - 1) / target_tiles);
     tile_iters = ((tile_iters + TILE_ITER_QUANTUM - 1) / TILE_ITER_QUANTUM) * TILE_ITER_QUANTUM;
     tile_iters = std::min(std::max(tile_iters, MIN_TILE_ITERS), MAX_TILE_ITERS);
     if (const char *env = getenv("MPRG_TILE_ITERS")) {  // tuning knob for profiling runs
         const int v = atoi(env);
-        if (v >= TILE_ITER_QUANTUM && v <= MAX_TILE_ITERS) tile_iters = v;
+        if (v >= TILE_ITER_QUANTUM && v <= 1024) tile_iters = v;
     }
     for (int i = 0; i < n_tasks; ++i) {
         const mprg_task &ht = h_tasks[i];
@@ -97,8 +97,8 @@ int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, 
                 int cnt = std::min(tile_rows, ht.n_rows - rb);
                 const int left = ht.n_rows - rb - cnt;
                 if (left > 0 && left < tile_rows / 2) cnt += left;
-                lv.units.push_back(ScanUnit{t.base, t.stride, t.rows_off >= 0 ? t.rows_off + rb : -1, rb, cnt,
-                                            t.c0, t.c1, t.col_off, cb, bn, 0});
+                lv.units.push_back(ScanUnit{t.base, t.stride, t.rows_off >= 0 ? t.rows_off + rb : -1, rb, cnt, t.c0,
+                                        t.c1, t.col_off, cb, bn, (batch->flags[ht.locus] & 8) ? 1 : 0});
                 rb += cnt;
             }
         }

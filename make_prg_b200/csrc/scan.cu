@@ -25,6 +25,11 @@
 // chunks per step), a run that starts in the first column of a chunk looks one column back: tiles need
 // no carry between them, so tall tasks are cut by rows and wide ones by columns freely.  Partial
 // results reach the (zero-initialised) per-task column arrays with atomicOr / atomicMax.
+//
+// Rows are fetched with 128-bit ld.global.nc (L1 no-allocate), four rows per trip, software pipelined
+// by one trip.  A TMA variant (per-warp shared-memory ring filled by cp.async.bulk on mbarriers) and a
+// persistent-grid variant with a global tile counter were built and measured slower on B200 for this
+// access pattern (profiles/r1_scan_variants.txt); they are not kept.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -32,7 +37,7 @@ namespace mprg {
 
 constexpr int SCAN_THREADS = 128;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
-constexpr int SCAN_UNROLL = 4;
+constexpr int SCAN_UNROLL = 4;  // warp iterations per trip
 
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
     uint4 r;
@@ -53,6 +58,15 @@ __device__ __forceinline__ uint32_t zero_nibbles(uint32_t w) {
 // word c & 3, nibble c >> 2) the four per-word indicators interleave with three shifts
 __device__ __forceinline__ uint32_t gap_mask32(const uint4 &v) {
     return (zero_nibbles(v.x) >> 3) | (zero_nibbles(v.y) >> 2) | (zero_nibbles(v.z) >> 1) | zero_nibbles(v.w);
+}
+
+// The same mask for a chunk without even symbol codes (M S W N): a nibble is the gap iff its bit 0 is
+// clear.  Bit 0 of every nibble of the four words is gathered with three bit-selects (LOP3) on
+// shifted words: 7 instructions instead of 17.
+__device__ __forceinline__ uint32_t gap_mask32_odd(const uint4 &v) {
+    const uint32_t z01 = (v.x & 0x11111111u) | ((v.y << 1) & ~0x11111111u);  // bit 0: word 0, bit 1: word 1
+    const uint32_t z23 = (v.z & 0x11111111u) | ((v.w << 1) & ~0x11111111u);  // bit 0: word 2, bit 1: word 3
+    return ~((z01 & 0x33333333u) | ((z23 << 2) & ~0x33333333u));
 }
 
 // nibble-wide (0xF) mask of the nibbles equal to `pattern`
@@ -154,7 +168,6 @@ scan_kernel(const uint8_t *__restrict__ packed, const ScanUnit *__restrict__ uni
     const ScanUnit t = units[ui];
     const int bn = t.ch_count;
     const int row_count = t.row_count;
-    if (bn <= 0 || row_count <= 0) return;
     const int a0 = (t.c0 >> 5) << 5;  // chunk-aligned window start (columns)
     const int *rows = t.rows_off >= 0 ? rows_arena + t.rows_off : nullptr;
     const uint8_t *msa = packed + t.base;
@@ -186,13 +199,24 @@ scan_kernel(const uint8_t *__restrict__ packed, const ScanUnit *__restrict__ uni
         const int rl = min(it * rpw + lane_slot, last_row);
         return rows ? rows[rl] : t.row_begin + rl;
     };
-    auto load_trip = [&](int first_it, uint4 *dst) {
-#pragma unroll
-        for (int u = 0; u < SCAN_UNROLL; ++u)
-            dst[u] = ld_stream(reinterpret_cast<const uint4 *>(col_ptr + (long long)row_of(first_it + u) * t.stride));
-    };
     const ScanLane L = {chunk, lane, lane_chunk, bn, t.c0, t.c1, a0};
     uint32_t g_done = 0u;  // last gap mask (interior runs only) this lane has recorded
+    const bool exact = HAS_N || (t.flags & 1);
+
+    // consecutive rows: one pointer per lane, advanced by whole iterations (no index arithmetic per row)
+    const uint8_t *lane_ptr = col_ptr + (long long)(t.row_begin + lane_slot) * t.stride;
+    const long long it_bytes = (long long)rpw * t.stride;
+    auto load_trip = [&](int first_it, uint4 *dst) {
+        if (rows == nullptr && (first_it + SCAN_UNROLL) * rpw <= row_count) {
+            const uint8_t *p = lane_ptr + first_it * it_bytes;
+#pragma unroll
+            for (int u = 0; u < SCAN_UNROLL; ++u) dst[u] = ld_stream(reinterpret_cast<const uint4 *>(p + u * it_bytes));
+        } else {
+#pragma unroll
+            for (int u = 0; u < SCAN_UNROLL; ++u)
+                dst[u] = ld_stream(reinterpret_cast<const uint4 *>(col_ptr + (long long)row_of(first_it + u) * t.stride));
+        }
+    };
     uint4 vnext[SCAN_UNROLL];
     load_trip(0, vnext);
     // software pipelined by one trip: the loads of trip i+1 are in flight while trip i is processed
@@ -218,15 +242,15 @@ scan_kernel(const uint8_t *__restrict__ packed, const ScanUnit *__restrict__ uni
                     a_and[j] &= wa[j] & wb[j];  // one LOP3 for two rows
                 }
             }
-            // Bases and padding are odd codes and the gap is 0: a chunk whose 32 nibbles all have bit 0
-            // set holds no gap.  Three LOP3 and a compare per row; the exact mask is only built for the
-            // chunks that fail the test.
-            gm[u] = 0u;
-            gm[u + 1] = 0u;
-            if (((wa[0] & wa[1] & wa[2]) & wa[3] & 0x11111111u) != 0x11111111u)
+            // Bases and padding are odd codes and the gap is 0: without even codes in the locus the gap
+            // mask is bit 0 of every nibble, complemented
+            if (exact) {
                 gm[u] = gap_mask32(v[u]) & wmask;
-            if (((wb[0] & wb[1] & wb[2]) & wb[3] & 0x11111111u) != 0x11111111u)
                 gm[u + 1] = gap_mask32(v[u + 1]) & wmask;
+            } else {
+                gm[u] = gap_mask32_odd(v[u]) & wmask;
+                gm[u + 1] = gap_mask32_odd(v[u + 1]) & wmask;
+            }
         }
 #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; ++u) {

@@ -103,6 +103,12 @@ class Context:
         self._check(self.lib.mprg_scan_log(self.handle, ptr(by), ptr(ms), capacity, C.byref(n), int(reset)))
         return by[:n.value].copy(), ms[:n.value].copy()
 
+    def read_yardstick(self, batch):
+        """(bytes, ms) of one bare streaming read of the packed batch (measurement aid, mprg.h)."""
+        by, ms = C.c_double(), C.c_double()
+        self._check(self.lib.mprg_read_yardstick(self.handle, batch.handle, C.byref(by), C.byref(ms)))
+        return by.value, ms.value
+
     # ---- loader -> HBM ------------------------------------------------------------------------
     def upload(self, matrices):
         """matrices: list of uint8[rows, cols] ASCII arrays (or one flat buffer + shapes tuple)."""

@@ -1,13 +1,15 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, scan-kernel tile-height sweep, ncu capture of the scan kernel, bench line.
+# One GPU-box visit: parity tests, scan timing, ncu capture + launch list, bench line.
 set -u
 mkdir -p gpurun_out
+TAG=${1:-r1}
 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest.log
-for ti in 0 16 20 24 32 48; do
-  echo "== MPRG_TILE_ITERS=$ti" | tee -a gpurun_out/sweep.log
-  if [ "$ti" = 0 ]; then python scripts/scan_only.py 1000 12 2>&1 | tail -2 | tee -a gpurun_out/sweep.log
-  else MPRG_TILE_ITERS=$ti python scripts/scan_only.py 1000 12 2>&1 | tail -2 | tee -a gpurun_out/sweep.log; fi
+for n in 1000 8000; do
+  echo "== n=$n" | tee -a gpurun_out/sweep.log
+  python scripts/scan_only.py $n 12 2>&1 | tail -1 | tee -a gpurun_out/sweep.log
 done
-ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 3 -c 1 -o gpurun_out/scan_r1_v8 -f python scripts/scan_only.py 1000 6 > gpurun_out/ncu_scan.log 2>&1
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench7.json 2> gpurun_out/bench7.err
-cat gpurun_out/bench7.json
+ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 3 -c 1 -o gpurun_out/scan_$TAG -f python scripts/scan_only.py 1000 6 > gpurun_out/ncu_scan.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-big > gpurun_out/ncu_bench.log 2>&1
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+cat gpurun_out/bench_$TAG.json
+tail -3 gpurun_out/bench_$TAG.err
