@@ -10,6 +10,8 @@
 //   refcheck_kernel    cluster_further / sequences_are_one_reference_like (majority string with
 //                      first-seen tie-break, Hamming distance, threshold; cluster_sequences.py:59-111)
 //                      plus the loop control of kmeans_cluster_seqs (:256-261)
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(256)
 kmer_kernel(const KmerProb *__restrict__ probs, const int *__restrict__ seq_rows,
             const uint8_t *__restrict__ G, int k, uint8_t *__restrict__ useq_all,
             int *__restrict__ ints_all, uint64_t *__restrict__ keys_all, int *__restrict__ ming_all,
-            double *__restrict__ X_all, int *__restrict__ out_F, int *__restrict__ err) {
+            int *__restrict__ out_F, int *__restrict__ err) {
     __shared__ int s_warp[33];
     const KmerProb p = probs[blockIdx.x];
     const uint8_t *g = G + p.g_off;
@@ -197,7 +199,6 @@ kmer_kernel(const KmerProb *__restrict__ probs, const int *__restrict__ seq_rows
     int *kid = mref + p.Pmax;
     uint64_t *keys = keys_all + p.tab_off;
     int *ming = ming_all + p.tab_off;
-    double *X = X_all + p.x_off;
     const int w = p.w, n = p.n;
 
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
@@ -270,9 +271,21 @@ kmer_kernel(const KmerProb *__restrict__ probs, const int *__restrict__ seq_rows
     __syncthreads();
     const int F = block_exclusive_scan(kid, P, s_warp);  // kid[g] = column id when g is a first occurrence
     if (threadIdx.x == 0) out_F[blockIdx.x] = F;
-    for (long long i = threadIdx.x; i < (long long)n * F; i += blockDim.x) X[i] = 0.0;
-    __syncthreads();
-    for (int gidx = threadIdx.x; gidx < P; gidx += blockDim.x) {
+}
+
+// Second phase, once the host has sized the count matrices exactly (n x F doubles per problem, zeroed):
+// X[sequence of position g][column of the k-mer at g] += 1.  grid (problems, stripes of positions).
+__global__ void __launch_bounds__(256)
+kmer_fill_kernel(const KmerProb *__restrict__ probs, const int *__restrict__ ints_all,
+                 const int *__restrict__ F_all, double *__restrict__ X_all) {
+    const KmerProb p = probs[blockIdx.x];
+    const int n = p.n, F = F_all[blockIdx.x];
+    const int *pos = ints_all + p.pos_off + p.n;
+    const int *mref = pos + p.n + 1;
+    const int *kid = mref + p.Pmax;
+    double *X = X_all + p.x_off;
+    const int P = pos[n];
+    for (int gidx = blockIdx.y * blockDim.x + threadIdx.x; gidx < P; gidx += gridDim.y * blockDim.x) {
         int lo = 0, hi = n;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
@@ -490,10 +503,19 @@ size_t rowsig_bytes() { return sizeof(RowSig); }
 
 cudaError_t launch_kmer(cudaStream_t s, const void *d_probs, int n_probs, const int *seq_rows,
                         const uint8_t *G, int k, uint8_t *useq, int *ints, uint64_t *keys, int *ming,
-                        double *X, int *out_F, int *err) {
+                        int *out_F, int *err) {
     if (n_probs <= 0) return cudaSuccess;
     kmer_kernel<<<n_probs, 256, 0, s>>>((const KmerProb *)d_probs, seq_rows, G, k, useq, ints, keys, ming,
-                                        X, out_F, err);
+                                        out_F, err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kmer_fill(cudaStream_t s, const void *d_probs, int n_probs, long long max_positions,
+                             const int *ints, const int *F, double *X) {
+    if (n_probs <= 0) return cudaSuccess;
+    const long long stripes = (max_positions + 256 * 16 - 1) / (256 * 16);
+    const dim3 grid(n_probs, (unsigned)std::min<long long>(std::max<long long>(stripes, 1), 256));
+    kmer_fill_kernel<<<grid, 256, 0, s>>>((const KmerProb *)d_probs, ints, F, X);
     return cudaGetLastError();
 }
 

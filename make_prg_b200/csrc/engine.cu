@@ -350,8 +350,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
             k.tab_off = tab_total;
             tab_total += T;
             k.Pmax = (int)p.P;
-            k.x_off = x_total;
-            x_total += (long long)p.n * p.P;
+            k.x_off = 0;  // set below, once the number of distinct k-mers is known
             MemberProb &m = mp[q];
             m.row_off = row_off[p.task];
             m.R = ht.n_rows;
@@ -373,16 +372,13 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
             assign_total += p.n;
             c.maj_off = maj_total;
             maj_total += w;
-            c.x_off = k.x_off;
         }
-        if (x_total * 8 > (24LL << 30)) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "k-mer count matrices exceed the 24 GiB scratch budget");
         // 7 kprobs|mprobs, 8 useq, 9 ints, 10 keys, 11 ming, 12 X, 13 states|F, 14 seq_rows|mem|assign|newlab|maj, 15 kmeans scratch
         MPRG_CUDA(ctx, B[7].reserve(sizeof(KmerProb) * np + sizeof(MemberProb) * np));
         MPRG_CUDA(ctx, B[8].reserve((size_t)useq_total));
         MPRG_CUDA(ctx, B[9].reserve(sizeof(int) * ints_total));
         MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * tab_total));
         MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * tab_total));
-        MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * x_total));
         MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * 2 * np + 64));
         const size_t o_seqrows = 0;
         const size_t o_memoff = o_seqrows + sizeof(int) * seq_rows.size();
@@ -410,8 +406,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         // d_leader_u is free after dedupe: scratch for the group -> long-sequence map
         MPRG_CUDA(ctx, launch_members(s, d_mp, np, d_group, d_leadlen, d_leader_u, d_memoff, d_memrows));
         MPRG_CUDA(ctx, launch_kmer(s, d_kp, np, d_seqrows, B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
-                                   B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), B[12].as<double>(), d_F,
-                                   d_err));
+                                   B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), d_F, d_err));
         ctx->launches += 2;
         std::vector<int> h_F(np + 1);
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_F.data(), d_F, sizeof(int) * np, s));
@@ -420,6 +415,13 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         if (h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
         TRACE("cl: kmer setup+run+sync");
 
+        // ---- count matrices, sized exactly now that every F is known ----
+        long long max_P = 0;
+        for (int q = 0; q < np; ++q) {
+            kp[q].x_off = st[q].x_off = x_total;
+            x_total += (long long)probs[q].n * h_F[q];
+            max_P = std::max(max_P, probs[q].P);
+        }
         // ---- KMeans loop (cluster_sequences.py:256-274) ----
         long long kmd_total = 0, kmi_total = 0;
         for (int q = 0; q < np; ++q) {
@@ -429,6 +431,19 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
             kmd_total += kmeans_dscratch_doubles(st[q].n, st[q].F);
             kmi_total += kmeans_iscratch_ints(st[q].n);
         }
+        {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const double want = 8.0 * (double)x_total + 8.0 * (double)kmd_total + 4.0 * (double)kmi_total;
+            const double have = (double)free_b + (double)B[12].cap + (double)B[15].cap;
+            if (want > 0.9 * have)
+                MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "k-mer count matrices and KMeans scratch of this level do not fit in device memory");
+        }
+        MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * std::max<long long>(x_total, 1)));
+        MPRG_CUDA(ctx, cudaMemsetAsync(B[12].p, 0, sizeof(double) * x_total, s));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_kp, kp.data(), sizeof(KmerProb) * np, s));
+        MPRG_CUDA(ctx, launch_kmer_fill(s, d_kp, np, max_P, B[9].as<int>(), d_F, B[12].as<double>()));
+        ctx->launches++;
         MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * kmd_total + sizeof(int) * kmi_total + 64));
         double *d_kmd = B[15].as<double>();
         int *d_kmi = reinterpret_cast<int *>(d_kmd + kmd_total);
@@ -436,6 +451,9 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         MPRG_CUDA(ctx, cudaMemsetAsync(d_assign, 0, sizeof(int) * assign_total, s));
         const int MAX_CLUSTERS = 10;
         MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
+        ctx->launches++;
+        // every problem that ever runs KMeans runs it in the K == 2 round: centre its data once, now
+        MPRG_CUDA(ctx, launch_kmeans_prepare(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi));
         ctx->launches++;
         for (int round = 2; round <= MAX_CLUSTERS; ++round) {
             MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab,
@@ -631,21 +649,23 @@ extern "C" int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mp
     MPRG_CUDA(ctx, B[9].reserve(sizeof(int) * (2LL * n + 1 + 2 * P)));
     MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * T));
     MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * T));
-    MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * (size_t)n * P));
     MPRG_CUDA(ctx, B[13].reserve(sizeof(int) * 2));
     int *d_F = B[13].as<int>();
     MPRG_CUDA(ctx, cudaMemsetAsync(d_F, 0, sizeof(int) * 2, s));
     MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[7].p, &k, sizeof(k), s));
     MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[14].p, leaders.data(), sizeof(int) * n, s));
     MPRG_CUDA(ctx, launch_kmer(s, B[7].p, 1, B[14].as<int>(), B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
-                               B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), B[12].as<double>(), d_F,
-                               d_F + 1));
+                               B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), d_F, d_F + 1));
     ctx->launches++;
     int hF[2] = {0, 0};
     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, hF, d_F, sizeof(int) * 2, s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
     if (hF[1]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
     *n_kmers = hF[0];
+    MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * std::max<size_t>((size_t)n * hF[0], 1)));
+    MPRG_CUDA(ctx, cudaMemsetAsync(B[12].p, 0, sizeof(double) * (size_t)n * hF[0], s));
+    MPRG_CUDA(ctx, launch_kmer_fill(s, B[7].p, 1, P, B[9].as<int>(), d_F, B[12].as<double>()));
+    ctx->launches++;
     if (h_counts) {
         if (capacity < (int64_t)n * hF[0]) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "count matrix capacity too small");
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_counts, B[12].p, sizeof(double) * (size_t)n * hF[0], s));

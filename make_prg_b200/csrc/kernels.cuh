@@ -50,7 +50,7 @@ struct KmerProb {
     long long tab_off;   // hash table slots (keys u64 / ming int), T entries
     int T;               // table size (power of two >= 2 * Pmax)
     int Pmax;            // upper bound on the number of k-mer positions
-    long long x_off;     // count matrix (doubles), capacity n * Pmax, stride F once known
+    long long x_off;     // count matrix (doubles), n * F, set by the host once F is known
 };
 
 // per clustering problem: loop state of kmeans_cluster_seqs (cluster_sequences.py:249-274)
@@ -94,13 +94,17 @@ cudaError_t launch_members(cudaStream_t s, const MemberProb *probs, int n, const
 size_t rowsig_bytes();
 cudaError_t launch_kmer(cudaStream_t s, const void *d_probs, int n_probs, const int *seq_rows,
                         const uint8_t *G, int k, uint8_t *useq, int *ints, uint64_t *keys, int *ming,
-                        double *X, int *out_F, int *err);
+                        int *out_F, int *err);
+cudaError_t launch_kmer_fill(cudaStream_t s, const void *d_probs, int n_probs, long long max_positions,
+                             const int *ints, const int *F, double *X);
 cudaError_t launch_refcheck(cudaStream_t s, ClusterState *states, int n_probs, const uint8_t *G,
                             const int *mem_off, const int *mem_rows, int *assign, uint8_t *maj,
                             int max_clusters, int *flags_out = nullptr);
 long long kmeans_dscratch_doubles(long long n, long long F);
 long long kmeans_iscratch_ints(long long n);
 cudaError_t kmeans_upload_rand(const double *h_rand);
+cudaError_t launch_kmeans_prepare(cudaStream_t s, const ClusterState *states, int n_probs, const double *X,
+                                  double *dscratch, int *iscratch);
 cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, const double *X,
                           double *dscratch, int *iscratch, int *assign, int *newlab, int *tickets);
 cudaError_t launch_kmeans_single(cudaStream_t s, const double *X0, int n, int F, int K, double *dscratch,

@@ -296,7 +296,7 @@ struct KM {
     int n, F, K;
     const double *X0;
     double *Xc, *mean, *tmpF, *xx, *ca, *cb, *best_c, *lb, *ub, *closest, *cum, *D, *half, *nxt, *shift,
-        *wts, *cc, *dist, *res;
+        *wts, *cc, *dist, *res, *tol;
     int *labels, *labels_old, *best_labels;
 };
 
@@ -642,22 +642,28 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
     *out_C = C;
 }
 
-// ---- one fit = KM_NINIT independent initialisations + a sequential best-of selection -------------
-// Scratch of one problem: KM_NINIT per-initialisation blocks (each with its own centred copy of X, so
-// the initialisations share nothing and can run in different CTAs) followed by the problem block.
+// ---- one fit = preparation + KM_NINIT independent initialisations + a best-of selection ----------
+// Scratch of one problem: the shared block (centred copy of X, column means, squared row norms,
+// tolerance: written once by kmeans_prepare, read-only afterwards, for every K the clustering loop
+// tries), then KM_NINIT per-initialisation blocks (so the initialisations can run in different CTAs),
+// then the selection block.
+__device__ __host__ inline long long km_shared_doubles(long long n, long long F) { return n * F + 2 * F + n + 8; }
 __device__ __host__ inline long long km_init_doubles(long long n, long long F) {
-    return n * F + 2 * F + n + 2LL * KM_MAXK * F + n * KM_MAXK + 3 * n + 4 * n + n + KM_MAXK * KM_MAXK +
-           4 * KM_MAXK + 8;  // + [inertia, tol, final-centres selector] in the last 8
+    return 2LL * KM_MAXK * F + n * KM_MAXK + 3 * n + 4 * n + n + KM_MAXK * KM_MAXK + 4 * KM_MAXK +
+           8;  // + [inertia, final-centres selector] in the last 8
 }
 __device__ __host__ inline long long km_init_ints(long long n) { return 2 * n + 8; }
 
-__device__ void km_bind_init(KM &k, int n, int F, int K, const double *X0, double *d, int *ii) {
+// d0 = scratch of the problem, init = which initialisation block to bind
+__device__ void km_bind_init(KM &k, int n, int F, int K, const double *X0, double *d0, int *i0, int init) {
     k.n = n; k.F = F; k.K = K; k.X0 = X0;
-    const long long nF = (long long)n * F;
-    k.Xc = d; d += nF;
+    double *d = d0;
+    k.Xc = d; d += (long long)n * F;
     k.mean = d; d += F;
     k.tmpF = d; d += F;
     k.xx = d; d += n;
+    k.tol = d;
+    d = d0 + km_shared_doubles(n, F) + init * km_init_doubles(n, F);
     k.ca = d; d += (long long)KM_MAXK * F;
     k.cb = d; d += (long long)KM_MAXK * F;
     k.lb = d; d += (long long)n * KM_MAXK;
@@ -672,17 +678,17 @@ __device__ void km_bind_init(KM &k, int n, int F, int K, const double *X0, doubl
     k.wts = d; d += KM_MAXK;
     k.cc = d; d += KM_MAXK;
     k.res = d;  // res[0] = inertia, res[1] = 0/1: final centres in ca/cb
+    int *ii = i0 + init * km_init_ints(n);
     k.labels = ii; ii += n;
     k.labels_old = ii; ii += n;
     k.best_c = nullptr;
     k.best_labels = nullptr;
 }
 
-// one initialisation: centring (private copy), k-means++ from the init-th slice of the RandomState(2)
-// stream, Elkan; leaves labels, inertia and the final centres in the init's block
-__device__ void kmeans_run_init(KM &k, int init, double *s_scalar, int *s_int) {
-    const int n = k.n, F = k.F, K = k.K;
-    // tolerance on the un-centred data, mean, centring, squared norms
+// once per problem: tolerance on the un-centred data, column means, centring, squared row norms
+// (KMeans._tolerance, X -= X.mean(axis=0), row_norms(X, squared=True) in sklearn/cluster/_kmeans.py)
+__device__ void kmeans_prepare(KM &k) {
+    const int n = k.n, F = k.F;
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
         double s = 0.0;
         for (int i = 0; i < n; ++i) s = __dadd_rn(s, k.X0[(long long)i * F + f]);
@@ -697,10 +703,16 @@ __device__ void kmeans_run_init(KM &k, int init, double *s_scalar, int *s_int) {
         k.tmpF[f] = v / (double)n;
     }
     __syncthreads();
-    if (threadIdx.x == 0) s_scalar[2] = __dmul_rn(np_pairwise_sum(k.tmpF, F) / (double)F, 1e-4);
+    if (threadIdx.x == 0) k.tol[0] = __dmul_rn(np_pairwise_sum(k.tmpF, F) / (double)F, 1e-4);
     for (int i = threadIdx.x; i < n; i += blockDim.x) k.xx[i] = einsum_self(k.Xc + (long long)i * F, F);
     __syncthreads();
-    const double tol = s_scalar[2];
+}
+
+// one initialisation: k-means++ from the init-th slice of the RandomState(2) stream, Elkan; leaves
+// labels, inertia and the final centres in the init's block
+__device__ void kmeans_run_init(KM &k, int init, double *s_scalar, int *s_int) {
+    const int K = k.K;
+    const double tol = k.tol[0];
     // every initialisation consumes 1 + (K-1) * (2 + int(ln K)) doubles of the shared stream
     const int trials = 2 + (int)log((double)K);
     int rand_pos = init * (1 + (K - 1) * trials);
@@ -715,16 +727,16 @@ __device__ void kmeans_run_init(KM &k, int init, double *s_scalar, int *s_int) {
 
 // best-of-n_init selection (strict inertia improvement and not the same clustering), then predict on
 // the un-centred data: argmin_j |c_j|^2 - 2 x.c_j  (lloyd _update_chunk_dense, chunks of 256 samples)
-__device__ void kmeans_select_predict(int n, int F, int K, const double *X0, double *init_d, int *init_i,
-                                      double *best_c, double *cc, int *s_int, int *out_labels,
-                                      double *out_inertia) {
-    const long long dstride = km_init_doubles(n, F), istride = km_init_ints(n);
+__device__ void kmeans_select_predict(int n, int F, int K, const double *X0, double *d0, int *i0,
+                                      int *s_int, int *out_labels, double *out_inertia) {
+    double *best_c = d0 + km_shared_doubles(n, F) + KM_NINIT * km_init_doubles(n, F);
+    double *cc = best_c + (long long)KM_MAXK * F;
     if (threadIdx.x == 0) {
         int best = 0;
         for (int init = 1; init < KM_NINIT; ++init) {
             KM a, b;
-            km_bind_init(a, n, F, K, X0, init_d + init * dstride, init_i + init * istride);
-            km_bind_init(b, n, F, K, X0, init_d + best * dstride, init_i + best * istride);
+            km_bind_init(a, n, F, K, X0, d0, i0, init);
+            km_bind_init(b, n, F, K, X0, d0, i0, best);
             if (a.res[0] < b.res[0]) {
                 // _is_same_clustering(labels, best_labels, K)
                 int mapping[KM_MAXK];
@@ -742,7 +754,7 @@ __device__ void kmeans_select_predict(int n, int F, int K, const double *X0, dou
     }
     __syncthreads();
     KM w;
-    km_bind_init(w, n, F, K, X0, init_d + s_int[0] * dstride, init_i + s_int[0] * istride);
+    km_bind_init(w, n, F, K, X0, d0, i0, s_int[0]);
     const double *C = (w.res[1] == 0.0) ? w.ca : w.cb;
     for (long long p = threadIdx.x; p < (long long)K * F; p += blockDim.x)
         best_c[p] = __dadd_rn(C[p], w.mean[p % F]);
@@ -768,13 +780,25 @@ __device__ void kmeans_select_predict(int n, int F, int K, const double *X0, dou
     __syncthreads();
 }
 
-// scratch per problem: KM_NINIT init blocks | best_c [KM_MAXK * F] | cc [KM_MAXK] ; ints: KM_NINIT init blocks
+// scratch per problem: shared block | KM_NINIT init blocks | best_c [KM_MAXK * F] | cc [KM_MAXK] ;
+// ints: KM_NINIT init blocks
 long long kmeans_dscratch_doubles(long long n, long long F) {
-    return KM_NINIT * km_init_doubles(n, F) + KM_MAXK * F + KM_MAXK + 8;
+    return km_shared_doubles(n, F) + KM_NINIT * km_init_doubles(n, F) + KM_MAXK * F + KM_MAXK + 8;
 }
 long long kmeans_iscratch_ints(long long n) { return KM_NINIT * km_init_ints(n) + 8; }
 
 #ifndef MPRG_HOST_EMU
+// one CTA per problem that is about to run KMeans for the first time (K == 2 round)
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_prepare_kernel(const ClusterState *__restrict__ states, const double *__restrict__ X_all,
+                      double *__restrict__ dscratch, int *__restrict__ iscratch) {
+    const ClusterState &st = states[blockIdx.x];
+    if (st.status != 0 || !st.run_kmeans) return;
+    KM k;
+    km_bind_init(k, st.n, st.F, st.K, X_all + st.x_off, dscratch + st.kmd_off, iscratch + st.kmi_off, 0);
+    kmeans_prepare(k);
+}
+
 // grid (problems, KM_NINIT): every CTA runs one initialisation; the last CTA of a problem to finish
 // (ticket counter) does the selection, the prediction and the loop control of kmeans_cluster_seqs
 __global__ void __launch_bounds__(KM_THREADS)
@@ -790,7 +814,7 @@ kmeans_kernel(ClusterState *__restrict__ states, const double *__restrict__ X_al
     double *d0 = dscratch + st.kmd_off;
     int *i0 = iscratch + st.kmi_off;
     KM k;
-    km_bind_init(k, n, F, K, X0, d0 + init * km_init_doubles(n, F), i0 + init * km_init_ints(n));
+    km_bind_init(k, n, F, K, X0, d0, i0, init);
     kmeans_run_init(k, init, s_scalar, s_int);
     __threadfence();
     __syncthreads();
@@ -800,8 +824,7 @@ kmeans_kernel(ClusterState *__restrict__ states, const double *__restrict__ X_al
     __threadfence();
     int *newlab = newlab_all + st.assign_off;
     int *assign = assign_all + st.assign_off;
-    double *best_c = d0 + KM_NINIT * km_init_doubles(n, F);
-    kmeans_select_predict(n, F, K, X0, d0, i0, best_c, best_c + (long long)KM_MAXK * F, s_int, newlab, nullptr);
+    kmeans_select_predict(n, F, K, X0, d0, i0, s_int, newlab, nullptr);
     if (threadIdx.x == 0) {
         // cluster_sequences.py:267-274: fewer distinct labels than K => keep the previous assignment
         unsigned seen = 0;
@@ -819,7 +842,13 @@ kmeans_kernel(ClusterState *__restrict__ states, const double *__restrict__ X_al
     }
 }
 
-// stand-alone problem (mprg_kmeans): same structure, grid (1, KM_NINIT)
+// stand-alone problem (mprg_kmeans): prepare <<<1>>> then grid (1, KM_NINIT)
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_single_prepare_kernel(const double *X0, int n, int F, int K, double *dscratch, int *iscratch) {
+    KM k;
+    km_bind_init(k, n, F, K, X0, dscratch, iscratch, 0);
+    kmeans_prepare(k);
+}
 __global__ void __launch_bounds__(KM_THREADS)
 kmeans_single_problem_kernel(const double *X0, int n, int F, int K, double *dscratch, int *iscratch,
                              int *labels, double *inertia, int *ticket) {
@@ -827,7 +856,7 @@ kmeans_single_problem_kernel(const double *X0, int n, int F, int K, double *dscr
     __shared__ int s_int[8];
     const int init = blockIdx.y;
     KM k;
-    km_bind_init(k, n, F, K, X0, dscratch + init * km_init_doubles(n, F), iscratch + init * km_init_ints(n));
+    km_bind_init(k, n, F, K, X0, dscratch, iscratch, init);
     kmeans_run_init(k, init, s_scalar, s_int);
     __threadfence();
     __syncthreads();
@@ -835,9 +864,7 @@ kmeans_single_problem_kernel(const double *X0, int n, int F, int K, double *dscr
     __syncthreads();
     if (s_int[7] != KM_NINIT - 1) return;
     __threadfence();
-    double *best_c = dscratch + KM_NINIT * km_init_doubles(n, F);
-    kmeans_select_predict(n, F, K, X0, dscratch, iscratch, best_c, best_c + (long long)KM_MAXK * F, s_int, labels,
-                          inertia);
+    kmeans_select_predict(n, F, K, X0, dscratch, iscratch, s_int, labels, inertia);
     if (threadIdx.x == 0) *ticket = 0;
 }
 #else
@@ -846,14 +873,14 @@ void kmeans_single_problem_kernel(const double *X0, int n, int F, int K, double 
                                   int *labels, double *inertia) {
     static double s_scalar[4];
     static int s_int[8];
+    KM k;
+    km_bind_init(k, n, F, K, X0, dscratch, iscratch, 0);
+    kmeans_prepare(k);
     for (int init = 0; init < KM_NINIT; ++init) {
-        KM k;
-        km_bind_init(k, n, F, K, X0, dscratch + init * km_init_doubles(n, F), iscratch + init * km_init_ints(n));
+        km_bind_init(k, n, F, K, X0, dscratch, iscratch, init);
         kmeans_run_init(k, init, s_scalar, s_int);
     }
-    double *best_c = dscratch + KM_NINIT * km_init_doubles(n, F);
-    kmeans_select_predict(n, F, K, X0, dscratch, iscratch, best_c, best_c + (long long)KM_MAXK * F, s_int, labels,
-                          inertia);
+    kmeans_select_predict(n, F, K, X0, dscratch, iscratch, s_int, labels, inertia);
 }
 #endif
 
@@ -870,8 +897,16 @@ cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, con
     return cudaGetLastError();
 }
 
+cudaError_t launch_kmeans_prepare(cudaStream_t s, const ClusterState *states, int n_probs, const double *X,
+                                  double *dscratch, int *iscratch) {
+    if (n_probs <= 0) return cudaSuccess;
+    kmeans_prepare_kernel<<<n_probs, KM_THREADS, 0, s>>>(states, X, dscratch, iscratch);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_kmeans_single(cudaStream_t s, const double *X0, int n, int F, int K, double *dscratch,
                                  int *iscratch, int *labels, double *inertia, int *ticket) {
+    kmeans_single_prepare_kernel<<<1, KM_THREADS, 0, s>>>(X0, n, F, K, dscratch, iscratch);
     kmeans_single_problem_kernel<<<dim3(1, KM_NINIT), KM_THREADS, 0, s>>>(X0, n, F, K, dscratch, iscratch, labels,
                                                                           inertia, ticket);
     return cudaGetLastError();
