@@ -35,7 +35,7 @@ ROWS, COLS = 200, 1000
 MAX_NESTING, MIN_MATCH = 5, 7
 # dram__bytes_read.sum + dram__bytes_write.sum of one root-level scan launch of this workload from the
 # ncu --set full capture committed under profiles/ (per launch, like `achieved`); None if not captured
-NCU_TRAFFIC_BYTES = None
+NCU_TRAFFIC_BYTES = 107.68e6  # profiles/r1_scan_kernel_ncu_v12.txt: 104.32 MB read + 3.36 MB written
 CACHE = Path(os.environ.get("MPRG_BENCH_CACHE", "/tmp/mprg_bench_cache"))
 
 
@@ -57,28 +57,71 @@ def workload(rank, n_loci=LOCI_PER_GPU):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), read through NVML in
+    a thread of this process every 20 ms (spawning nvidia-smi from every rank stalls the driver for
+    tens of milliseconds on a multi-GPU box and would land inside the timed steps); nvidia-smi is the
+    fallback when NVML cannot be loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                    0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.stop = threading.Event()
         self.thread = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML indexes physical GPUs: honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = gpu_index
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        for bit, name in self.NVML_REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+        for line in out.strip().splitlines():
+            r = [c.strip() for c in line.split(",")]
+            self.sm.append(float(r[1]))
+            self.mx.append(float(r[2]))
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.02 if self.nvml is not None else 0.2)
 
     def __enter__(self):
         self.thread.start()
@@ -89,21 +132,11 @@ class ClockSampler:
         self.thread.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for name, val in zip(names, r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)),
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def hbm_peak():
@@ -186,7 +219,7 @@ def config_dict(sample_note=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--loci", type=int, default=LOCI_PER_GPU)
@@ -236,10 +269,13 @@ def main():
         return n_ok, total_len
 
     def step_e2e():
-        batch = ctx.upload((host_np, shapes))
-        out = step_resident(batch)
+        # the public one-call path: pinned host ASCII in, PRG strings out (mprg_build_ascii)
+        batch, res = ctx.build_ascii((host_np, shapes), MAX_NESTING, MIN_MATCH)
+        n_ok = sum(1 for i in range(n_loci) if res.status(i) == 0)
+        total_len = sum(len(res.prg(i)) for i in range(0, n_loci, 97))
+        res.free()
         batch.free()
-        return out
+        return n_ok, total_len
 
     # ---- kernel-side number: batch resident in HBM ----
     batch = ctx.upload((host_np, shapes))
@@ -251,11 +287,13 @@ def main():
     launches0 = ctx.launch_count()
     with ClockSampler(local_rank) as clocks:
         t_dev = 0.0
+        dev_steps = []
         t0 = time.perf_counter()
         for _ in range(args.steps):
             ctx.timer_start()
             n_ok, _ = step_resident(batch)
-            t_dev += ctx.timer_stop()
+            dev_steps.append(ctx.timer_stop())
+            t_dev += dev_steps[-1]
             flush.zero_()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -316,10 +354,12 @@ def main():
     barrier()
     ctx.copy_stats(reset=True)
     t_e2e = 0.0
+    e2e_steps = []
     for _ in range(args.steps):
         ctx.timer_start()
         step_e2e()
-        t_e2e += ctx.timer_stop()
+        e2e_steps.append(ctx.timer_stop())
+        t_e2e += e2e_steps[-1]
         flush.zero_()
     barrier()
     copies = ctx.copy_stats(reset=True)
@@ -384,6 +424,11 @@ def main():
                                    f"{cpu_dt:.1f} s"},
         "clocks": clocks.summary(),
         "wall_ms_per_step": 1e3 * wall / args.steps,
+        "step_ms": {"resident": {"min": float(np.min(dev_steps)), "median": float(np.median(dev_steps)),
+                                 "max": float(np.max(dev_steps))},
+                    "e2e": {"min": float(np.min(e2e_steps)), "median": float(np.median(e2e_steps)),
+                            "max": float(np.max(e2e_steps))}, "note": "rank 0, device time per step"},
+        "host": {"cores": os.cpu_count(), "loadavg": list(os.getloadavg())},
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -179,6 +179,14 @@ int mprg_cluster_tasks(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *
  *      (prg_builder.py:24-42,100-110; NodeFactory.build recursion_tree.py:401-471) -------------- */
 int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, int32_t min_match_length,
                mprg_result **out);
+/* The same from HOST ASCII in one call: loader output in, batch + result out.  The loci are cut into
+ * the ranges mprg_build uses and every range is copied, packed and built by its own worker thread and
+ * stream, so the host-to-device copy of one range overlaps the kernels of the others (the end-to-end
+ * path of `make_prg from_msa`, from_msa.py:114-123 per locus).  Arguments as mprg_batch_upload; the
+ * caller frees *out_batch with mprg_batch_free and *out_res with mprg_result_free. */
+int mprg_build_ascii(mprg_ctx *ctx, const uint8_t *h_ascii, const int64_t *h_offsets,
+                     const int32_t *n_rows, const int32_t *n_cols, int32_t n_loci, int32_t max_nesting,
+                     int32_t min_match_length, mprg_batch **out_batch, mprg_result **out_res);
 void mprg_result_free(mprg_result *res);
 int32_t mprg_result_n_loci(const mprg_result *res);
 int32_t mprg_result_status(const mprg_result *res, int32_t locus);

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 #include "common.cuh"
@@ -108,7 +109,7 @@ extern "C" int mprg_create(int device_ordinal, mprg_ctx **out) {
         if (n >= 1 && n <= 64) ctx->n_workers = n;
     } else {
         const unsigned hc = std::thread::hardware_concurrency();
-        ctx->n_workers = (int)std::max(1u, std::min(4u, hc ? hc : 1u));
+        ctx->n_workers = (int)std::max(1u, std::min(4u, hc ? hc / 2 : 1u));  // more is faster on a quiet host but stalls on a shared one
     }
     *out = ctx;
     return MPRG_OK;
@@ -163,11 +164,10 @@ extern "C" int mprg_scan_stats(mprg_ctx *ctx, double *ms, double *bytes, int64_t
     return MPRG_OK;
 }
 
-extern "C" int mprg_batch_upload(mprg_ctx *ctx, const uint8_t *h_ascii, const int64_t *h_offsets,
-                                 const int32_t *n_rows, const int32_t *n_cols, int32_t n_loci,
-                                 mprg_batch **out) {
-    if (!ctx || !out || n_loci < 0 || (n_loci > 0 && (!h_ascii || !h_offsets || !n_rows || !n_cols)))
-        return MPRG_E_BAD_ARG;
+namespace mprg {
+
+// Host metadata of a batch and its (still empty) packed arena in HBM.
+int batch_prepare(mprg_ctx *ctx, const int32_t *n_rows, const int32_t *n_cols, int32_t n_loci, mprg_batch **out) {
     *out = nullptr;
     cudaSetDevice(ctx->device);
     mprg_batch *b = new mprg_batch();
@@ -177,8 +177,7 @@ extern "C" int mprg_batch_upload(mprg_ctx *ctx, const uint8_t *h_ascii, const in
     b->stride.resize(n_loci);
     b->base.resize(n_loci);
     b->flags.assign(n_loci, 0);
-    long long packed = 0, ascii_total = 0, total_rows = 0;
-    std::vector<long long> row_prefix(n_loci + 1, 0), aoff(n_loci);
+    long long packed = 0;
     for (int l = 0; l < n_loci; ++l) {
         if (n_rows[l] < 0 || n_cols[l] < 0) {
             delete b;
@@ -187,68 +186,103 @@ extern "C" int mprg_batch_upload(mprg_ctx *ctx, const uint8_t *h_ascii, const in
         b->stride[l] = ((n_cols[l] + COLS_PER_CHUNK - 1) / COLS_PER_CHUNK) * CHUNK_BYTES;
         b->base[l] = packed;
         packed += (long long)b->stride[l] * n_rows[l];
-        aoff[l] = ascii_total;
-        ascii_total += (long long)n_rows[l] * n_cols[l];
-        row_prefix[l] = total_rows;
-        total_rows += n_rows[l];
     }
-    row_prefix[n_loci] = total_rows;
     b->packed_bytes = packed;
-    auto fail = [&](cudaError_t e, const char *what) {
-        ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
-        if (b->d_packed) cudaFree(b->d_packed);
+    const cudaError_t e = cudaMalloc(&b->d_packed, (size_t)packed + 16);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc packed: ") + cudaGetErrorString(e);
         delete b;
         return MPRG_E_CUDA;
-    };
-    cudaError_t e;
-    if ((e = cudaMalloc(&b->d_packed, (size_t)packed + 16)) != cudaSuccess) return fail(e, "cudaMalloc packed");
-    if (total_rows > 0 && ascii_total > 0) {
-        // stage: ascii | ascii_off | row_prefix | base | n_cols | stride | flags
-        size_t o_ascii = 0;
-        size_t o_aoff = (ascii_total + 15) & ~15LL;
-        size_t o_rp = o_aoff + sizeof(long long) * n_loci;
-        size_t o_base = o_rp + sizeof(long long) * (n_loci + 1);
-        size_t o_nc = o_base + sizeof(long long) * n_loci;
-        size_t o_st = o_nc + sizeof(int) * n_loci;
-        size_t o_fl = o_st + sizeof(int) * n_loci;
-        size_t total = o_fl + sizeof(int) * n_loci;
-        if ((e = ctx->d_stage.reserve(total)) != cudaSuccess) return fail(e, "reserve stage");
-        uint8_t *d = ctx->d_stage.as<uint8_t>();
-        cudaStream_t s = ctx->stream;
-        // the ASCII copy goes straight from the caller's buffer locus by locus when the loci are
-        // contiguous in the caller's buffer this is one copy
-        bool contiguous = true;
-        for (int l = 0; l < n_loci; ++l) contiguous &= (h_offsets[l] == h_offsets[0] + aoff[l]);
-        if (contiguous) {
-            if ((e = mprg::copy_h2d(ctx, d + o_ascii, h_ascii + h_offsets[0], (size_t)ascii_total, s)) != cudaSuccess)
-                return fail(e, "H2D ascii");
-        } else {
-            for (int l = 0; l < n_loci; ++l) {
-                const size_t nbytes = (size_t)n_rows[l] * n_cols[l];
-                if (!nbytes) continue;
-                if ((e = mprg::copy_h2d(ctx, d + o_ascii + aoff[l], h_ascii + h_offsets[l], nbytes, s)) != cudaSuccess)
-                    return fail(e, "H2D ascii");
-            }
-        }
-        mprg::copy_h2d(ctx, d + o_aoff, aoff.data(), sizeof(long long) * n_loci, s);
-        mprg::copy_h2d(ctx, d + o_rp, row_prefix.data(), sizeof(long long) * (n_loci + 1), s);
-        mprg::copy_h2d(ctx, d + o_base, b->base.data(), sizeof(long long) * n_loci, s);
-        mprg::copy_h2d(ctx, d + o_nc, b->n_cols.data(), sizeof(int) * n_loci, s);
-        mprg::copy_h2d(ctx, d + o_st, b->stride.data(), sizeof(int) * n_loci, s);
-        cudaMemsetAsync(d + o_fl, 0, sizeof(int) * n_loci, s);
-        const int warps_per_block = 8;
-        const long long blocks = (total_rows + warps_per_block - 1) / warps_per_block;
-        pack_rows_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(
-            d + o_ascii, (const long long *)(d + o_aoff), (const long long *)(d + o_rp),
-            (const int *)(d + o_nc), (const long long *)(d + o_base), (const int *)(d + o_st), n_loci,
-            total_rows, b->d_packed, (int *)(d + o_fl));
-        ctx->launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "pack_rows_kernel");
-        if ((e = mprg::copy_d2h(ctx, b->flags.data(), d + o_fl, sizeof(int) * n_loci, s)) != cudaSuccess)
-            return fail(e, "D2H flags");
-        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, "sync upload");
     }
-    for (int f : b->flags) b->any_n |= (f & 2) != 0;
+    *out = b;
+    return MPRG_OK;
+}
+
+// Loci [l0, l1) of the batch: ASCII host -> device stage of `ctx` (its stream), packed on the device
+// into the batch arena, alphabet flags back.  Ranges are independent, so the worker contexts of
+// mprg_build_ascii upload theirs concurrently and the copies overlap the other workers' kernels.
+int batch_upload_range(mprg_ctx *ctx, mprg_batch *b, const uint8_t *h_ascii, const int64_t *h_offsets, int l0,
+                       int l1) {
+    const int n = l1 - l0;
+    if (n <= 0) return MPRG_OK;
+    cudaSetDevice(ctx->device);
+    long long ascii_total = 0, total_rows = 0;
+    std::vector<long long> row_prefix(n + 1, 0), aoff(n);
+    for (int i = 0; i < n; ++i) {
+        const int l = l0 + i;
+        aoff[i] = ascii_total;
+        ascii_total += (long long)b->n_rows[l] * b->n_cols[l];
+        row_prefix[i] = total_rows;
+        total_rows += b->n_rows[l];
+    }
+    row_prefix[n] = total_rows;
+    if (total_rows <= 0 || ascii_total <= 0) return MPRG_OK;
+    // stage: ascii | ascii_off | row_prefix | base | n_cols | stride | flags
+    const size_t o_ascii = 0;
+    const size_t o_aoff = (ascii_total + 15) & ~15LL;
+    const size_t o_rp = o_aoff + sizeof(long long) * n;
+    const size_t o_base = o_rp + sizeof(long long) * (n + 1);
+    const size_t o_nc = o_base + sizeof(long long) * n;
+    const size_t o_st = o_nc + sizeof(int) * n;
+    const size_t o_fl = o_st + sizeof(int) * n;
+    const size_t total = o_fl + sizeof(int) * n;
+    MPRG_CUDA(ctx, ctx->d_stage.reserve(total));
+    uint8_t *d = ctx->d_stage.as<uint8_t>();
+    cudaStream_t s = ctx->stream;
+    // One range at a time on the PCIe link: concurrent copies of several workers would share the
+    // bandwidth and finish together; in turn, the first range is being built while the next is copied.
+    std::unique_lock<std::mutex> link(b->copy_mutex);
+    // loci that are contiguous in the caller's buffer go in one copy
+    bool contiguous = true;
+    for (int i = 0; i < n; ++i) contiguous &= (h_offsets[l0 + i] == h_offsets[l0] + aoff[i]);
+    if (contiguous) {
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_ascii, h_ascii + h_offsets[l0], (size_t)ascii_total, s));
+    } else {
+        for (int i = 0; i < n; ++i) {
+            const size_t nbytes = (size_t)b->n_rows[l0 + i] * b->n_cols[l0 + i];
+            if (!nbytes) continue;
+            MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_ascii + aoff[i], h_ascii + h_offsets[l0 + i], nbytes, s));
+        }
+    }
+    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    link.unlock();
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_aoff, aoff.data(), sizeof(long long) * n, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_rp, row_prefix.data(), sizeof(long long) * (n + 1), s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_base, b->base.data() + l0, sizeof(long long) * n, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_nc, b->n_cols.data() + l0, sizeof(int) * n, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_st, b->stride.data() + l0, sizeof(int) * n, s));
+    MPRG_CUDA(ctx, cudaMemsetAsync(d + o_fl, 0, sizeof(int) * n, s));
+    const int warps_per_block = 8;
+    const long long blocks = (total_rows + warps_per_block - 1) / warps_per_block;
+    pack_rows_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(
+        d + o_ascii, (const long long *)(d + o_aoff), (const long long *)(d + o_rp), (const int *)(d + o_nc),
+        (const long long *)(d + o_base), (const int *)(d + o_st), n, total_rows, b->d_packed, (int *)(d + o_fl));
+    ctx->launches++;
+    MPRG_CUDA(ctx, cudaGetLastError());
+    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, b->flags.data() + l0, d + o_fl, sizeof(int) * n, s));
+    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    for (int l = l0; l < l1; ++l)
+        if (b->flags[l] & 2) b->any_n = true;
+    return MPRG_OK;
+}
+
+}  // namespace mprg
+
+extern "C" int mprg_batch_upload(mprg_ctx *ctx, const uint8_t *h_ascii, const int64_t *h_offsets,
+                                 const int32_t *n_rows, const int32_t *n_cols, int32_t n_loci,
+                                 mprg_batch **out) {
+    if (!ctx || !out || n_loci < 0 || (n_loci > 0 && (!h_ascii || !h_offsets || !n_rows || !n_cols)))
+        return MPRG_E_BAD_ARG;
+    mprg_batch *b = nullptr;
+    int rc = mprg::batch_prepare(ctx, n_rows, n_cols, n_loci, &b);
+    if (rc != MPRG_OK) return rc;
+    rc = mprg::batch_upload_range(ctx, b, h_ascii, h_offsets, 0, n_loci);
+    if (rc != MPRG_OK) {
+        cudaFree(b->d_packed);
+        delete b;
+        *out = nullptr;
+        return rc;
+    }
     *out = b;
     return MPRG_OK;
 }

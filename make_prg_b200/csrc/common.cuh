@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -129,7 +131,8 @@ struct mprg_batch {
     std::vector<int> flags;       // alphabet flags per locus (host copy)
     long long packed_bytes = 0;
     uint8_t *d_packed = nullptr;
-    bool any_n = false;
+    std::mutex copy_mutex;  // orders the host-to-device copies of the ranges of mprg_build_ascii
+    std::atomic<bool> any_n{false};  // set by whichever upload finds an N; a stale read only picks the slower scan variant
 };
 
 struct mprg_ctx {

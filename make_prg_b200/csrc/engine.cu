@@ -1134,9 +1134,10 @@ extern "C" int mprg_set_workers(mprg_ctx *ctx, int32_t n_workers) {
 // Loci are independent, so a batch is cut into contiguous, cost-balanced ranges that are built
 // concurrently: one host thread + one stream + one scratch set per range, all reading the same
 // packed batch.  This overlaps the host bookkeeping of one range with the kernels of the others.
-extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
-                          int32_t min_match_length, mprg_result **out_res) {
-    if (!ctx || !batch || !out_res || min_match_length < 1) return MPRG_E_BAD_ARG;
+// With h_ascii != nullptr every range is first uploaded and packed by its own worker, so the
+// host-to-device copies of some ranges overlap the kernels of the others (mprg_build_ascii).
+static int build_ranges(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, int32_t min_match_length,
+                        const uint8_t *h_ascii, const int64_t *h_offsets, mprg_result **out_res) {
     *out_res = nullptr;
     cudaSetDevice(ctx->device);
     const int n_loci = batch->n_loci;
@@ -1147,9 +1148,16 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
         delete res;
         return rc;
     }
+    auto run = [&](mprg_ctx *c, int l0, int l1, bool trace) {
+        if (h_ascii) {
+            const int r = batch_upload_range(c, batch, h_ascii, h_offsets, l0, l1);
+            if (r != MPRG_OK) return r;
+        }
+        return build_range(c, batch, l0, l1, max_nesting, min_match_length, res, trace);
+    };
     int W = std::max(1, std::min(ctx->n_workers, n_loci / 8));
     if (W <= 1) {
-        rc = build_range(ctx, batch, 0, n_loci, max_nesting, min_match_length, res, true);
+        rc = run(ctx, 0, n_loci, true);
         if (rc != MPRG_OK) {
             delete res;
             return rc;
@@ -1166,25 +1174,36 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
         }
         ctx->workers.push_back(w);
     }
-    // contiguous ranges of roughly equal rows x cols
+    // contiguous ranges of roughly equal rows x cols, dealt round-robin; from host ASCII there are
+    // two ranges per worker, so that copies (one range at a time) and kernels stay overlapped
+    const int R = h_ascii ? std::max(W, std::min(2 * W, n_loci / 8)) : W;
     std::vector<double> prefix(n_loci + 1, 0.0);
     for (int l = 0; l < n_loci; ++l) prefix[l + 1] = prefix[l] + (double)batch->n_rows[l] * batch->n_cols[l] + 1.0;
-    std::vector<int> cut(W + 1, n_loci);
+    std::vector<int> cut(R + 1, n_loci);
     cut[0] = 0;
-    for (int w = 1; w < W; ++w) {
-        const double target = prefix[n_loci] * w / W;
-        cut[w] = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
-        cut[w] = std::max(cut[w], cut[w - 1]);
+    for (int r = 1; r < R; ++r) {
+        const double target = prefix[n_loci] * r / R;
+        cut[r] = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
+        cut[r] = std::max(cut[r], cut[r - 1]);
     }
     std::vector<int> rcs(W, MPRG_OK);
+    // range r always goes to worker r % W: the same worker sees the same loci on every call, so its
+    // scratch buffers stop growing after the first call (a reallocation synchronises the device)
+    auto work = [&](mprg_ctx *c, int w) {
+        for (int r = w; r < R; r += W) {
+            const int rc_r = run(c, cut[r], cut[r + 1], false);
+            if (rc_r != MPRG_OK) {
+                rcs[w] = rc_r;
+                break;
+            }
+        }
+    };
     std::vector<std::thread> threads;
     for (int w = 1; w < W; ++w) {
         mprg_ctx *wc = ctx->workers[w - 1];
-        threads.emplace_back([&, w, wc]() {
-            rcs[w] = build_range(wc, batch, cut[w], cut[w + 1], max_nesting, min_match_length, res, false);
-        });
+        threads.emplace_back([&, w, wc]() { work(wc, w); });
     }
-    rcs[0] = build_range(ctx, batch, cut[0], cut[1], max_nesting, min_match_length, res, false);
+    work(ctx, 0);
     for (auto &t : threads) t.join();
     for (int w = 1; w < W; ++w) {
         mprg_ctx *wc = ctx->workers[w - 1];
@@ -1211,6 +1230,33 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
         return rcs[0];
     }
     *out_res = res;
+    return MPRG_OK;
+}
+
+extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
+                          int32_t min_match_length, mprg_result **out_res) {
+    if (!ctx || !batch || !out_res || min_match_length < 1) return MPRG_E_BAD_ARG;
+    return build_ranges(ctx, batch, max_nesting, min_match_length, nullptr, nullptr, out_res);
+}
+
+extern "C" int mprg_build_ascii(mprg_ctx *ctx, const uint8_t *h_ascii, const int64_t *h_offsets,
+                                const int32_t *n_rows, const int32_t *n_cols, int32_t n_loci,
+                                int32_t max_nesting, int32_t min_match_length, mprg_batch **out_batch,
+                                mprg_result **out_res) {
+    if (!ctx || !out_batch || !out_res || min_match_length < 1 || n_loci < 0 ||
+        (n_loci > 0 && (!h_ascii || !h_offsets || !n_rows || !n_cols)))
+        return MPRG_E_BAD_ARG;
+    *out_batch = nullptr;
+    *out_res = nullptr;
+    mprg_batch *b = nullptr;
+    int rc = batch_prepare(ctx, n_rows, n_cols, n_loci, &b);
+    if (rc != MPRG_OK) return rc;
+    rc = build_ranges(ctx, b, max_nesting, min_match_length, h_ascii, h_offsets, out_res);
+    if (rc != MPRG_OK) {
+        mprg_batch_free(ctx, b);
+        return rc;
+    }
+    *out_batch = b;
     return MPRG_OK;
 }
 

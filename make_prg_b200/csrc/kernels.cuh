@@ -18,6 +18,11 @@ cudaError_t launch_partition_consensus(cudaStream_t stream, const uint8_t *cons,
 cudaError_t launch_demote(cudaStream_t stream, const uint8_t *packed, const DTask *d_tasks, int n_tasks,
                           const int *d_rows, DInterval *intervals, const int *iv_count);
 
+// batch.cu: batch metadata + arena, and the upload of a range of its loci on a context's stream
+int batch_prepare(mprg_ctx *ctx, const int32_t *n_rows, const int32_t *n_cols, int32_t n_loci, mprg_batch **out);
+int batch_upload_range(mprg_ctx *ctx, mprg_batch *b, const uint8_t *h_ascii, const int64_t *h_offsets, int l0,
+                       int l1);
+
 // Host-side description of one level of tasks, resident on the device after level_upload().
 struct Level {
     int n_tasks = 0;

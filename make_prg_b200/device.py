@@ -110,8 +110,8 @@ class Context:
         return by.value, ms.value
 
     # ---- loader -> HBM ------------------------------------------------------------------------
-    def upload(self, matrices):
-        """matrices: list of uint8[rows, cols] ASCII arrays (or one flat buffer + shapes tuple)."""
+    @staticmethod
+    def _flatten(matrices):
         if isinstance(matrices, tuple):
             flat, shapes = matrices
             shapes = [tuple(s) for s in shapes]
@@ -127,6 +127,11 @@ class Context:
         n_cols = np.array([s[1] for s in shapes], np.int32)
         if flat.size == 0:
             flat = np.zeros(1, np.uint8)
+        return flat, shapes, offsets, n_rows, n_cols
+
+    def upload(self, matrices):
+        """matrices: list of uint8[rows, cols] ASCII arrays (or one flat buffer + shapes tuple)."""
+        flat, shapes, offsets, n_rows, n_cols = self._flatten(matrices)
         h = C.c_void_p()
         self._check(self.lib.mprg_batch_upload(self.handle, ptr(flat), ptr(offsets), ptr(n_rows),
                                                ptr(n_cols), len(shapes), C.byref(h)))
@@ -263,6 +268,16 @@ class Context:
         self._check(self.lib.mprg_build(self.handle, batch.handle, max_nesting, min_match_length,
                                         C.byref(h)))
         return BuildResult(self, h)
+
+    def build_ascii(self, matrices, max_nesting, min_match_length):
+        """Host ASCII in, (Batch, BuildResult) out in one call: every worker range is copied, packed and
+        built on its own stream, so the copies overlap the kernels (mprg_build_ascii)."""
+        flat, shapes, offsets, n_rows, n_cols = self._flatten(matrices)
+        hb, hr = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.mprg_build_ascii(self.handle, ptr(flat), ptr(offsets), ptr(n_rows), ptr(n_cols),
+                                              len(shapes), max_nesting, min_match_length, C.byref(hb),
+                                              C.byref(hr)))
+        return Batch(self, hb, shapes), BuildResult(self, hr)
 
 
 class BuildResult:

@@ -40,8 +40,7 @@ def build_matrices(matrices: List[np.ndarray], max_nesting: int, min_match_lengt
             size += matrices[stop].size
             stop += 1
         chunk = matrices[start:stop]
-        batch = ctx.upload(chunk)
-        res = ctx.build(batch, max_nesting, min_match_length)
+        batch, res = ctx.build_ascii(chunk, max_nesting, min_match_length)
         for i in range(len(chunk)):
             status = res.status(i)
             out.append(LocusBuild(status, res.prg(i) if status == LOCUS_OK else "", res.n_nodes(i),

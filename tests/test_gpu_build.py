@@ -91,3 +91,25 @@ def test_batch_order_invariance(ctx):
     _, b = _build(ctx, mats[::-1], 5, 7)
     for i in range(4):
         assert a.prg(i) == b.prg(3 - i)
+
+
+def test_build_ascii_equals_upload_then_build(ctx):
+    """mprg_build_ascii (every worker range copied, packed and built on its own stream) returns exactly
+    what mprg_batch_upload + mprg_build return, whatever the number of workers, including a locus with
+    a disallowed base and loci of different shapes."""
+    mats = [synth.synth_msa(30 + (i % 7) * 9, 120 + (i % 5) * 77, 900 + i, var_frac=0.06, n_dels=3) for i in range(40)]
+    bad = mats[11].copy()
+    bad[3, 17] = ord("Z")
+    mats[11] = bad
+    _, want = _build(ctx, mats, 5, 7)
+    for workers in (1, 3, 8):
+        ctx.set_workers(workers)
+        batch, got = ctx.build_ascii(mats, 5, 7)
+        for i in range(len(mats)):
+            assert got.status(i) == want.status(i), (workers, i)
+            assert got.prg(i) == want.prg(i), (workers, i)
+        assert got.status(11) == 1
+        assert batch.flags()[11] & 1
+        got.free()
+        batch.free()
+    ctx.set_workers(4)
