@@ -190,6 +190,7 @@ kmer_kernel(const KmerProb *__restrict__ probs, const int *__restrict__ seq_rows
             int *__restrict__ out_F, int *__restrict__ err) {
     __shared__ int s_warp[33];
     const KmerProb p = probs[blockIdx.x];
+    if (p.big & 1) return;  // launch_kmer_big
     const uint8_t *g = G + p.g_off;
     const int *srow = seq_rows + p.seq_off;
     uint8_t *useq = useq_all + p.useq_off;
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(256)
 kmer_fill_kernel(const KmerProb *__restrict__ probs, const int *__restrict__ ints_all,
                  const int *__restrict__ F_all, double *__restrict__ X_all) {
     const KmerProb p = probs[blockIdx.x];
+    if (p.big & 2) return;  // launch_kmer_fill_big
     const int n = p.n, F = F_all[blockIdx.x];
     const int *pos = ints_all + p.pos_off + p.n;
     const int *mref = pos + p.n + 1;
@@ -292,6 +294,182 @@ kmer_fill_kernel(const KmerProb *__restrict__ probs, const int *__restrict__ int
             if (pos[mid] <= gidx) lo = mid; else hi = mid;
         }
         atomicAdd(&X[(long long)lo * F + kid[mref[gidx]]], 1.0);
+    }
+}
+
+// ---- big problems: the same numbering and counting with the whole grid ---------------------------
+// One problem at a time (deep loci: 10^4 sequences x 2*10^4 columns = 2*10^8 k-mer positions).  Same
+// results as kmer_kernel: column ids in first-occurrence order, exact verification of every hash match.
+constexpr int KB_THREADS = 256;
+constexpr int KB_CHUNK = 4096;  // positions per CTA in the numbering passes
+
+__device__ __forceinline__ int kb_seq_of(const int *pos, int n, int gidx) {
+    int lo = 0, hi = n;  // pos[lo] <= gidx < pos[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pos[mid] <= gidx) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// one warp per sequence: ordered compaction of the non-gap symbols, 32 columns at a time
+__global__ void __launch_bounds__(KB_THREADS)
+kmer_big_ungap_kernel(const KmerProb *__restrict__ probs, int q, const int *__restrict__ seq_rows,
+                      const uint8_t *__restrict__ G, uint8_t *__restrict__ useq_all, int *__restrict__ ints_all) {
+    const KmerProb p = probs[q];
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (KB_THREADS / 32) + (threadIdx.x >> 5);
+    if (j >= p.n) return;
+    const uint8_t *row = G + p.g_off + (long long)seq_rows[p.seq_off + j] * p.w;
+    uint8_t *u = useq_all + p.useq_off + (long long)j * p.w;
+    int len = 0;
+    for (int c0 = 0; c0 < p.w; c0 += 32) {
+        const int c = c0 + lane;
+        const int sym = c < p.w ? row[c] : SYM_GAP;
+        const unsigned keep = __ballot_sync(0xffffffffu, sym != SYM_GAP);
+        if (sym != SYM_GAP) u[len + __popc(keep & ((1u << lane) - 1u))] = (uint8_t)sym;
+        len += __popc(keep);
+    }
+    if (lane == 0) (ints_all + p.pos_off)[j] = len;
+}
+
+// one CTA: pos = exclusive prefix of (ulen - k + 1), table reset is done by the host (memset)
+__global__ void __launch_bounds__(KB_THREADS)
+kmer_big_prefix_kernel(const KmerProb *__restrict__ probs, int q, int k, int *__restrict__ ints_all) {
+    __shared__ int s_warp[33];
+    const KmerProb p = probs[q];
+    int *ulen = ints_all + p.pos_off;
+    int *pos = ulen + p.n;
+    for (int j = threadIdx.x; j < p.n; j += blockDim.x) pos[j] = ulen[j] - k + 1;
+    __syncthreads();
+    const int total = block_exclusive_scan(pos, p.n, s_warp);
+    if (threadIdx.x == 0) pos[p.n] = total;
+}
+
+// every position: claim / find the slot of its k-mer, keep the smallest position per slot.  The table
+// is read before any atomic: once a k-mer is in and its first occurrence is known, later occurrences
+// cost two cached loads and no atomic (10^8 positions hit ~10^4 hot slots on a deep locus).
+__global__ void __launch_bounds__(KB_THREADS)
+kmer_big_insert_kernel(const KmerProb *__restrict__ probs, int q, int k, const uint8_t *__restrict__ useq_all,
+                       int *__restrict__ ints_all, uint64_t *__restrict__ keys_all, int *__restrict__ ming_all) {
+    const KmerProb p = probs[q];
+    const int *pos = ints_all + p.pos_off + p.n;
+    int *mref = ints_all + p.pos_off + 2 * p.n + 1;
+    const uint8_t *useq = useq_all + p.useq_off;
+    uint64_t *keys = keys_all + p.tab_off;
+    int *ming = ming_all + p.tab_off;
+    const int P = pos[p.n], mask = p.T - 1;
+    for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < P; gidx += gridDim.x * blockDim.x) {
+        const int j = kb_seq_of(pos, p.n, gidx);
+        const uint64_t key = kmer_hash(useq + (long long)j * p.w + (gidx - pos[j]), k);
+        int slot = (int)(key & mask);
+        while (true) {
+            uint64_t cur = __ldcg((const unsigned long long *)&keys[slot]);
+            if (cur == ~0ULL) cur = atomicCAS((unsigned long long *)&keys[slot], ~0ULL, key);
+            if (cur == ~0ULL || cur == key) break;
+            slot = (slot + 1) & mask;
+        }
+        if (__ldcg(&ming[slot]) > gidx) atomicMin(&ming[slot], gidx);
+        mref[gidx] = slot;
+    }
+}
+
+// mref[g] <- first position of g's k-mer (verified symbol by symbol); per chunk the number of first
+// occurrences
+__global__ void __launch_bounds__(KB_THREADS)
+kmer_big_first_kernel(const KmerProb *__restrict__ probs, int q, int k, const uint8_t *__restrict__ useq_all,
+                      int *__restrict__ ints_all, const int *__restrict__ ming_all, int *__restrict__ block_counts,
+                      int *__restrict__ err) {
+    __shared__ int s_count;
+    const KmerProb p = probs[q];
+    const int *pos = ints_all + p.pos_off + p.n;
+    int *mref = ints_all + p.pos_off + 2 * p.n + 1;
+    const uint8_t *useq = useq_all + p.useq_off;
+    const int *ming = ming_all + p.tab_off;
+    const int P = pos[p.n];
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    int mine = 0;
+    const int g0 = blockIdx.x * KB_CHUNK;
+    for (int gidx = g0 + threadIdx.x; gidx < min(g0 + KB_CHUNK, P); gidx += blockDim.x) {
+        const int first = ming[mref[gidx]];
+        mref[gidx] = first;
+        if (first == gidx) {
+            ++mine;
+        } else {
+            const int ja = kb_seq_of(pos, p.n, gidx), jb = kb_seq_of(pos, p.n, first);
+            const uint8_t *a = useq + (long long)ja * p.w + (gidx - pos[ja]);
+            const uint8_t *b = useq + (long long)jb * p.w + (first - pos[jb]);
+            bool eq = true;
+            for (int i = 0; i < k && eq; ++i) eq = a[i] == b[i];
+            if (!eq) atomicExch(err, 3);
+        }
+    }
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = s_count;
+}
+
+// one CTA: exclusive scan of the chunk counts, total = F
+__global__ void __launch_bounds__(KB_THREADS)
+kmer_big_scan_kernel(int *__restrict__ block_counts, int n_chunks, int *__restrict__ out_F) {
+    __shared__ int s_warp[33];
+    const int F = block_exclusive_scan(block_counts, n_chunks, s_warp);
+    if (threadIdx.x == 0) *out_F = F;
+}
+
+// kid[g] = column id for every first occurrence g (first-occurrence order = position order)
+__global__ void __launch_bounds__(KB_THREADS)
+kmer_big_number_kernel(const KmerProb *__restrict__ probs, int q, int *__restrict__ ints_all,
+                       const int *__restrict__ block_counts) {
+    __shared__ int s_warp[KB_THREADS / 32];
+    __shared__ int s_base;
+    const KmerProb p = probs[q];
+    const int *pos = ints_all + p.pos_off + p.n;
+    const int *mref = ints_all + p.pos_off + 2 * p.n + 1;
+    int *kid = ints_all + p.pos_off + 2 * p.n + 1 + p.Pmax;
+    const int P = pos[p.n];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = block_counts[blockIdx.x];
+    __syncthreads();
+    const int g0 = blockIdx.x * KB_CHUNK;
+    for (int base = g0; base < min(g0 + KB_CHUNK, P); base += KB_THREADS) {
+        const int gidx = base + threadIdx.x;
+        const bool first = gidx < P && gidx < g0 + KB_CHUNK && mref[gidx] == gidx;
+        const unsigned b = __ballot_sync(0xffffffffu, first);
+        if (lane == 0) s_warp[warp] = __popc(b);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w2 = 0; w2 < KB_THREADS / 32; ++w2) {
+            if (w2 < warp) before += s_warp[w2];
+            total += s_warp[w2];
+        }
+        if (first) kid[gidx] = s_base + before + __popc(b & ((1u << lane) - 1u));
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+}
+
+// counts of a big problem: one CTA per sequence, histogram in shared memory (F int counters), then the
+// row goes out as doubles in one coalesced sweep
+__global__ void __launch_bounds__(KB_THREADS)
+kmer_big_fill_kernel(const KmerProb *__restrict__ probs, int q, int F, const int *__restrict__ ints_all,
+                     double *__restrict__ X_all) {
+    extern __shared__ int s_hist[];
+    const KmerProb p = probs[q];
+    const int *pos = ints_all + p.pos_off + p.n;
+    const int *mref = ints_all + p.pos_off + 2 * p.n + 1;
+    const int *kid = mref + p.Pmax;
+    for (int j = blockIdx.x; j < p.n; j += gridDim.x) {
+        for (int f = threadIdx.x; f < F; f += blockDim.x) s_hist[f] = 0;
+        __syncthreads();
+        for (int gidx = pos[j] + threadIdx.x; gidx < pos[j + 1]; gidx += blockDim.x)
+            atomicAdd(&s_hist[kid[mref[gidx]]], 1);
+        __syncthreads();
+        double *x = X_all + p.x_off + (long long)j * F;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) x[f] = (double)s_hist[f];
+        __syncthreads();
     }
 }
 
@@ -507,6 +685,40 @@ cudaError_t launch_kmer(cudaStream_t s, const void *d_probs, int n_probs, const 
     if (n_probs <= 0) return cudaSuccess;
     kmer_kernel<<<n_probs, 256, 0, s>>>((const KmerProb *)d_probs, seq_rows, G, k, useq, ints, keys, ming,
                                         out_F, err);
+    return cudaGetLastError();
+}
+
+// h_prob: host copy of probs[q] (sizes for the grids)
+cudaError_t launch_kmer_big(cudaStream_t s, const void *d_probs, int q, const void *h_prob, const int *seq_rows,
+                            const uint8_t *G, int k, uint8_t *useq, int *ints, uint64_t *keys, int *ming,
+                            int *block_counts, int *out_F, int *err) {
+    const KmerProb &hp = *(const KmerProb *)h_prob;
+    const KmerProb *probs = (const KmerProb *)d_probs;
+    const int n_chunks = (hp.Pmax + KB_CHUNK - 1) / KB_CHUNK;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(keys + hp.tab_off, 0xff, sizeof(uint64_t) * (size_t)hp.T, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(ming + hp.tab_off, 0x7f, sizeof(int) * (size_t)hp.T, s)) != cudaSuccess) return e;
+    kmer_big_ungap_kernel<<<(hp.n + KB_THREADS / 32 - 1) / (KB_THREADS / 32), KB_THREADS, 0, s>>>(probs, q, seq_rows, G,
+                                                                                                  useq, ints);
+    kmer_big_prefix_kernel<<<1, KB_THREADS, 0, s>>>(probs, q, k, ints);
+    kmer_big_insert_kernel<<<std::min(n_chunks, 148 * 16), KB_THREADS, 0, s>>>(probs, q, k, useq, ints, keys, ming);
+    kmer_big_first_kernel<<<n_chunks, KB_THREADS, 0, s>>>(probs, q, k, useq, ints, ming, block_counts, err);
+    kmer_big_scan_kernel<<<1, KB_THREADS, 0, s>>>(block_counts, n_chunks, out_F);
+    kmer_big_number_kernel<<<n_chunks, KB_THREADS, 0, s>>>(probs, q, ints, block_counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kmer_fill_big(cudaStream_t s, const void *d_probs, int q, const void *h_prob, int F,
+                                 const int *ints, double *X) {
+    const KmerProb &hp = *(const KmerProb *)h_prob;
+    const size_t smem = sizeof(int) * (size_t)F;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;  // caller falls back to kmer_fill_kernel
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(kmer_big_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    kmer_big_fill_kernel<<<std::min(hp.n, 148 * 8), KB_THREADS, smem, s>>>((const KmerProb *)d_probs, q, F, ints, X);
     return cudaGetLastError();
 }
 

@@ -350,6 +350,8 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
             k.tab_off = tab_total;
             tab_total += T;
             k.Pmax = (int)p.P;
+            k.big = p.P >= KMER_BIG_POSITIONS ? 1 : 0;
+            k.pad = 0;
             k.x_off = 0;  // set below, once the number of distinct k-mers is known
             MemberProb &m = mp[q];
             m.row_off = row_off[p.task];
@@ -408,6 +410,16 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         MPRG_CUDA(ctx, launch_kmer(s, d_kp, np, d_seqrows, B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
                                    B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), d_F, d_err));
         ctx->launches += 2;
+        // deep loci: problems with very many k-mer positions go through the whole-grid kernels, one by one
+        for (int q = 0; q < np; ++q) {
+            if (!kp[q].big) continue;
+            const size_t n_chunks = ((size_t)kp[q].Pmax + 4095) / 4096;
+            MPRG_CUDA(ctx, B[6].reserve(sizeof(int) * (n_chunks + 1)));
+            MPRG_CUDA(ctx, launch_kmer_big(s, d_kp, q, &kp[q], d_seqrows, B[3].as<uint8_t>(), kmer_size,
+                                           B[8].as<uint8_t>(), B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(),
+                                           B[6].as<int>(), d_F + q, d_err));
+            ctx->launches += 6;
+        }
         std::vector<int> h_F(np + 1);
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_F.data(), d_F, sizeof(int) * np, s));
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &h_F[np], d_err, sizeof(int), s));
@@ -420,7 +432,18 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         for (int q = 0; q < np; ++q) {
             kp[q].x_off = st[q].x_off = x_total;
             x_total += (long long)probs[q].n * h_F[q];
-            max_P = std::max(max_P, probs[q].P);
+            if (kp[q].big && (size_t)h_F[q] * sizeof(int) <= 200 * 1024) kp[q].big |= 2;
+            if (!(kp[q].big & 2)) max_P = std::max(max_P, probs[q].P);
+        }
+        if (g_trace) {
+            long long big_n = 0, big_F = 0, big_P = 0;
+            for (int q = 0; q < np; ++q) {
+                big_n = std::max<long long>(big_n, probs[q].n);
+                big_F = std::max<long long>(big_F, h_F[q]);
+                big_P = std::max<long long>(big_P, probs[q].P);
+            }
+            fprintf(stderr, "[mprg trace] clustering level: %d problems, max n %lld, max F %lld, max positions %lld, X %.1f MB\n",
+                    np, big_n, big_F, big_P, 8e-6 * (double)x_total);
         }
         // ---- KMeans loop (cluster_sequences.py:256-274) ----
         long long kmd_total = 0, kmi_total = 0;
@@ -444,6 +467,11 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_kp, kp.data(), sizeof(KmerProb) * np, s));
         MPRG_CUDA(ctx, launch_kmer_fill(s, d_kp, np, max_P, B[9].as<int>(), d_F, B[12].as<double>()));
         ctx->launches++;
+        for (int q = 0; q < np; ++q)
+            if (kp[q].big & 2) {
+                MPRG_CUDA(ctx, launch_kmer_fill_big(s, d_kp, q, &kp[q], h_F[q], B[9].as<int>(), B[12].as<double>()));
+                ctx->launches++;
+            }
         MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * kmd_total + sizeof(int) * kmi_total + 64));
         double *d_kmd = B[15].as<double>();
         int *d_kmi = reinterpret_cast<int *>(d_kmd + kmd_total);
@@ -643,6 +671,7 @@ extern "C" int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mp
     k.T = T;
     k.Pmax = (int)P;
     k.x_off = 0;
+    k.big = P >= KMER_BIG_POSITIONS ? 1 : 0;
     MPRG_CUDA(ctx, B[7].reserve(sizeof(KmerProb)));
     MPRG_CUDA(ctx, B[14].reserve(sizeof(int) * n));
     MPRG_CUDA(ctx, B[8].reserve((size_t)n * w + 1));
@@ -654,9 +683,17 @@ extern "C" int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mp
     MPRG_CUDA(ctx, cudaMemsetAsync(d_F, 0, sizeof(int) * 2, s));
     MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[7].p, &k, sizeof(k), s));
     MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[14].p, leaders.data(), sizeof(int) * n, s));
-    MPRG_CUDA(ctx, launch_kmer(s, B[7].p, 1, B[14].as<int>(), B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
-                               B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), d_F, d_F + 1));
-    ctx->launches++;
+    if (k.big) {
+        MPRG_CUDA(ctx, B[6].reserve(sizeof(int) * ((size_t)(P + 4095) / 4096 + 1)));
+        MPRG_CUDA(ctx, launch_kmer_big(s, B[7].p, 0, &k, B[14].as<int>(), B[3].as<uint8_t>(), kmer_size,
+                                       B[8].as<uint8_t>(), B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(),
+                                       B[6].as<int>(), d_F, d_F + 1));
+        ctx->launches += 6;
+    } else {
+        MPRG_CUDA(ctx, launch_kmer(s, B[7].p, 1, B[14].as<int>(), B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
+                                   B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), d_F, d_F + 1));
+        ctx->launches++;
+    }
     int hF[2] = {0, 0};
     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, hF, d_F, sizeof(int) * 2, s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
@@ -664,7 +701,13 @@ extern "C" int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mp
     *n_kmers = hF[0];
     MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * std::max<size_t>((size_t)n * hF[0], 1)));
     MPRG_CUDA(ctx, cudaMemsetAsync(B[12].p, 0, sizeof(double) * (size_t)n * hF[0], s));
-    MPRG_CUDA(ctx, launch_kmer_fill(s, B[7].p, 1, P, B[9].as<int>(), d_F, B[12].as<double>()));
+    if (k.big && (size_t)hF[0] * sizeof(int) <= 200 * 1024) {
+        k.big |= 2;
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[7].p, &k, sizeof(k), s));
+        MPRG_CUDA(ctx, launch_kmer_fill_big(s, B[7].p, 0, &k, hF[0], B[9].as<int>(), B[12].as<double>()));
+    } else {
+        MPRG_CUDA(ctx, launch_kmer_fill(s, B[7].p, 1, P, B[9].as<int>(), d_F, B[12].as<double>()));
+    }
     ctx->launches++;
     if (h_counts) {
         if (capacity < (int64_t)n * hF[0]) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "count matrix capacity too small");

@@ -56,7 +56,11 @@ struct KmerProb {
     int T;               // table size (power of two >= 2 * Pmax)
     int Pmax;            // upper bound on the number of k-mer positions
     long long x_off;     // count matrix (doubles), n * F, set by the host once F is known
+    int big;             // bit0: numbered by the whole-grid kernels (launch_kmer_big), bit1: counted by
+                         // launch_kmer_fill_big (shared-memory histograms)
+    int pad;
 };
+constexpr long long KMER_BIG_POSITIONS = 1LL << 19;  // problems with at least this many k-mer positions are "big"
 
 // per clustering problem: loop state of kmeans_cluster_seqs (cluster_sequences.py:249-274)
 struct ClusterState {
@@ -100,6 +104,11 @@ size_t rowsig_bytes();
 cudaError_t launch_kmer(cudaStream_t s, const void *d_probs, int n_probs, const int *seq_rows,
                         const uint8_t *G, int k, uint8_t *useq, int *ints, uint64_t *keys, int *ming,
                         int *out_F, int *err);
+cudaError_t launch_kmer_big(cudaStream_t s, const void *d_probs, int q, const void *h_prob, const int *seq_rows,
+                            const uint8_t *G, int k, uint8_t *useq, int *ints, uint64_t *keys, int *ming,
+                            int *block_counts, int *out_F, int *err);
+cudaError_t launch_kmer_fill_big(cudaStream_t s, const void *d_probs, int q, const void *h_prob, int F,
+                                 const int *ints, double *X);
 cudaError_t launch_kmer_fill(cudaStream_t s, const void *d_probs, int n_probs, long long max_positions,
                              const int *ints, const int *F, double *X);
 cudaError_t launch_refcheck(cudaStream_t s, ClusterState *states, int n_probs, const uint8_t *G,

@@ -60,6 +60,22 @@ def test_kmer_count_matrix(ctx):
         assert got.shape == want.shape and np.array_equal(got, want)
 
 
+def test_kmer_count_matrix_big_problem(ctx):
+    """Problems with >= 2^19 k-mer positions take the whole-grid path (hash numbering over all CTAs,
+    shared-memory histograms): same first-occurrence column order and counts as the oracle, both for few
+    distinct k-mers (shared-memory fill) and for very many (global-atomic fill)."""
+    few = synth.synth_msa(320, 2000, 77, n_haps=300, var_frac=0.05, n_dels=5, private_snp=0.002)  # F ~ 10^4
+    many = synth.synth_msa(320, 2000, 78, n_haps=300, var_frac=0.05, n_dels=5, private_snp=0.05)
+    batch = ctx.upload([few, many])
+    for l, M, k in [(0, few, 7), (1, many, 9)]:
+        seqs = list(dict.fromkeys(u for u in mo.ungapped_rows(M) if len(u) >= k))
+        assert sum(len(u) - k + 1 for u in seqs) >= 1 << 19
+        want = mo.count_kmer_occurrences(seqs, mo.count_distinct_kmers(seqs, k))
+        got = ctx.kmer_counts(batch, (l, None, 0, M.shape[1]), k)
+        assert got.shape == want.shape and np.array_equal(got, want)
+        assert (want.shape[1] * 4 > 200 * 1024) == (l == 1)  # only the second case is past the smem histogram
+
+
 def test_kmeans_golden_cases(ctx):
     """Labels identical and inertia bit-identical to what scikit-learn returned inside the reference on
     every count matrix it was handed (north_star asks for identical labels, inertia within 1e-6)."""
