@@ -162,6 +162,11 @@ int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_
  * .fit(X).predict(X) as called at cluster_sequences.py:262-266.  X row-major [n, F] doubles. */
 int mprg_kmeans(mprg_ctx *ctx, const double *h_X, int32_t n, int32_t F, int32_t K,
                 int32_t *h_labels, double *h_inertia);
+/* The same with the execution shape chosen by the caller (tests): mode 0 = the engine's choice, 1 = one
+ * CTA per initialisation, 2 = every initialisation on a group of co-resident CTAs (deep loci).  All
+ * modes return bit-identical labels and inertia. */
+int mprg_kmeans_mode(mprg_ctx *ctx, const double *h_X, int32_t n, int32_t F, int32_t K,
+                     int32_t *h_labels, double *h_inertia, int32_t mode);
 /* sequences_are_one_reference_like over clusters of gapped rows (cluster_sequences.py:59-111):
  * cluster_of_row[i] in [0, n_clusters) for each row of the task (in member order = the order the
  * caller lists them in h_rows); out_flags[c] = 1 when cluster c is one-reference-like. */

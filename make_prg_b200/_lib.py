@@ -67,6 +67,7 @@ SIGNATURES = {
     "mprg_dedupe_rows": (C.c_int, [P, P, P, I32, P, I64, P, P, P, P, P]),
     "mprg_kmer_counts": (C.c_int, [P, P, P, P, I32, C.POINTER(I32), C.POINTER(I32), P, I64]),
     "mprg_kmeans": (C.c_int, [P, P, I32, I32, I32, P, C.POINTER(C.c_double)]),
+    "mprg_kmeans_mode": (C.c_int, [P, P, I32, I32, I32, P, C.POINTER(C.c_double), I32]),
     "mprg_one_ref_like": (C.c_int, [P, P, P, P, P, I32, P]),
     "mprg_cluster_tasks": (C.c_int, [P, P, P, I32, P, I64, I32, P, P, P]),
     "mprg_build": (C.c_int, [P, P, I32, I32, C.POINTER(P)]),

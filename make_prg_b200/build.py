@@ -13,10 +13,19 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 # the KMeans kernel restates scikit-learn's float64 operation order: no FMA contraction there
 PER_FILE = {"kmeans.cu": ["-fmad=false"]}
+# kmeans.cu is compiled a second time for deep loci: every initialisation on a group of CTAs that meet
+# at a global-memory barrier; -dlcm=cg makes every global load of that object an L2 (coherent) load
+EXTRA_OBJECTS = [("kmeans.cu", "kmeans_group", ["-fmad=false", "-DMPRG_KM_GROUP", "-Xptxas", "-dlcm=cg"])]
 
 
 def sources():
     return sorted(CSRC.glob("*.cu"))
+
+
+def compile_units():
+    units = [(src, src.stem, PER_FILE.get(src.name, [])) for src in sources()]
+    units += [(CSRC / name, stem, flags) for name, stem, flags in EXTRA_OBJECTS]
+    return units
 
 
 def needs_build():
@@ -34,19 +43,19 @@ def build_library(force=False, verbose=False):
     objdir.mkdir(exist_ok=True)
     objs = []
     procs = []
-    for src in sources():
-        obj = objdir / (src.stem + ".o")
-        cmd = [NVCC, *ARCH, *COMMON, *PER_FILE.get(src.name, []), "-c", str(src), "-o", str(obj)]
+    for src, stem, flags in compile_units():
+        obj = objdir / (stem + ".o")
+        cmd = [NVCC, *ARCH, *COMMON, *flags, "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((stem, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(obj))
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
             failed = True
-            sys.stderr.write(f"nvcc failed on {src.name}:\n{out}\n")
+            sys.stderr.write(f"nvcc failed on {src}:\n{out}\n")
         elif verbose or out.strip():
             sys.stderr.write(out)
     if failed:

@@ -381,7 +381,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         MPRG_CUDA(ctx, B[9].reserve(sizeof(int) * ints_total));
         MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * tab_total));
         MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * tab_total));
-        MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * 2 * np + 64));
+        MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * 2 * np + KM_GROUP_WORDS * sizeof(unsigned) + 64));
         const size_t o_seqrows = 0;
         const size_t o_memoff = o_seqrows + sizeof(int) * seq_rows.size();
         const size_t o_memrows = o_memoff + sizeof(int) * memoff_total;
@@ -404,7 +404,9 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         ClusterState *d_states = B[13].as<ClusterState>();
         int *d_F = reinterpret_cast<int *>(d_states + np);
         int *d_tickets = d_F + np;  // per-problem "initialisations finished" counters of kmeans_kernel
-        MPRG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, sizeof(int) * np, s));
+        // barriers and broadcast slots of launch_kmeans_group (8-byte aligned)
+        unsigned *d_bars = reinterpret_cast<unsigned *>(d_tickets + np);  // d_F + 2 * np: 8-byte aligned
+        MPRG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, sizeof(int) * (np + 1) + KM_GROUP_WORDS * sizeof(unsigned), s));
         // d_leader_u is free after dedupe: scratch for the group -> long-sequence map
         MPRG_CUDA(ctx, launch_members(s, d_mp, np, d_group, d_leadlen, d_leader_u, d_memoff, d_memrows));
         MPRG_CUDA(ctx, launch_kmer(s, d_kp, np, d_seqrows, B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
@@ -449,6 +451,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         long long kmd_total = 0, kmi_total = 0;
         for (int q = 0; q < np; ++q) {
             st[q].F = h_F[q];
+            st[q].big = (long long)st[q].n * st[q].F >= KMEANS_BIG_ELEMENTS ? 1 : 0;
             st[q].kmd_off = kmd_total;
             st[q].kmi_off = kmi_total;
             kmd_total += kmeans_dscratch_doubles(st[q].n, st[q].F);
@@ -483,7 +486,15 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         // every problem that ever runs KMeans runs it in the K == 2 round: centre its data once, now
         MPRG_CUDA(ctx, launch_kmeans_prepare(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi));
         ctx->launches++;
+        std::vector<int> big_q;  // deep loci: these problems get the whole GPU, one after the other
+        for (int q = 0; q < np; ++q)
+            if (st[q].big) big_q.push_back(q);
         for (int round = 2; round <= MAX_CLUSTERS; ++round) {
+            for (int q : big_q) {
+                MPRG_CUDA(ctx, launch_kmeans_group(s, d_states, q, B[12].as<double>(), d_kmd, d_kmi, d_assign,
+                                                   d_newlab, d_bars, round == 2, ctx->sm_count));
+                ctx->launches += round == 2 ? 2 : 1;
+            }
             MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab,
                                          d_tickets));
             MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
@@ -604,32 +615,59 @@ extern "C" int mprg_cluster_tasks(mprg_ctx *ctx, const mprg_batch *batch, const 
     return MPRG_OK;
 }
 
-extern "C" int mprg_kmeans(mprg_ctx *ctx, const double *h_X, int32_t n, int32_t F, int32_t K,
-                           int32_t *h_labels, double *h_inertia) {
-    if (!ctx || !h_X || !h_labels || n < 1 || F < 1 || K < 1 || K > 10 || K > n) return MPRG_E_BAD_ARG;
+// mode 0: the engine's choice (CTA groups from KMEANS_BIG_ELEMENTS on), 1: one CTA per initialisation,
+// 2: CTA groups
+extern "C" int mprg_kmeans_mode(mprg_ctx *ctx, const double *h_X, int32_t n, int32_t F, int32_t K,
+                                int32_t *h_labels, double *h_inertia, int32_t mode) {
+    if (!ctx || !h_X || !h_labels || n < 1 || F < 1 || K < 1 || K > 10 || K > n || mode < 0 || mode > 2)
+        return MPRG_E_BAD_ARG;
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     int rc = ensure_rand(ctx);
     if (rc != MPRG_OK) return rc;
     DevBuf *B = ctx->d_c;
     const long long nd = kmeans_dscratch_doubles(n, F), ni = kmeans_iscratch_ints(n);
+    const bool group = mode == 2 || (mode == 0 && (long long)n * F >= KMEANS_BIG_ELEMENTS);
     MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * (size_t)n * F));
-    MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * (nd + 1) + sizeof(int) * (ni + n + 2)));
+    MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * (nd + 1) + sizeof(int) * (ni + 2 * n + 4 + KM_GROUP_WORDS)));
     double *d_d = B[15].as<double>();
     double *d_inertia = d_d + nd;
     int *d_i = reinterpret_cast<int *>(d_inertia + 1);
     int *d_labels = d_i + ni;
-    int *d_ticket = d_labels + n;
-    MPRG_CUDA(ctx, cudaMemsetAsync(d_ticket, 0, sizeof(int), s));
+    int *d_assign = d_labels + n;
+    int *d_ticket = d_assign + n;  // 1 ticket (+ pad to 8 bytes) + the group communication area
+    int *d_comm = d_ticket + 1 + ((ni + 2 * n + 1) & 1);
+    MPRG_CUDA(ctx, cudaMemsetAsync(d_ticket, 0, sizeof(int) * (2 + KM_GROUP_WORDS), s));
     MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[12].p, h_X, sizeof(double) * (size_t)n * F, s));
-    MPRG_CUDA(ctx, launch_kmeans_single(s, B[12].as<double>(), n, F, K, d_d, d_i, d_labels, d_inertia, d_ticket));
-    ctx->launches++;
+    if (group) {
+        ClusterState c;
+        memset(&c, 0, sizeof(c));
+        c.run_kmeans = 1;
+        c.K = K;
+        c.n = n;
+        c.F = F;
+        c.big = 1;
+        MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState)));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, B[13].p, &c, sizeof(c), s));
+        MPRG_CUDA(ctx, launch_kmeans_group(s, B[13].as<ClusterState>(), 0, B[12].as<double>(), d_d, d_i, d_assign,
+                                           d_labels, reinterpret_cast<unsigned *>(d_comm), true,
+                                           ctx->sm_count, d_inertia));
+        ctx->launches += 2;
+    } else {
+        MPRG_CUDA(ctx, launch_kmeans_single(s, B[12].as<double>(), n, F, K, d_d, d_i, d_labels, d_inertia, d_ticket));
+        ctx->launches++;
+    }
     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_labels, d_labels, sizeof(int) * n, s));
     double inertia = 0;
     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &inertia, d_inertia, sizeof(double), s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
     if (h_inertia) *h_inertia = inertia;
     return MPRG_OK;
+}
+
+extern "C" int mprg_kmeans(mprg_ctx *ctx, const double *h_X, int32_t n, int32_t F, int32_t K,
+                           int32_t *h_labels, double *h_inertia) {
+    return mprg_kmeans_mode(ctx, h_X, n, F, K, h_labels, h_inertia, 0);
 }
 
 extern "C" int mprg_kmer_counts(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_task,

@@ -78,7 +78,10 @@ struct ClusterState {
     long long x_off;         // count matrix
     long long kmd_off;       // KMeans double scratch
     long long kmi_off;       // KMeans int scratch
+    int big;                 // KMeans of this problem runs on CTA groups (launch_kmeans_group)
+    int pad;
 };
+constexpr long long KMEANS_BIG_ELEMENTS = 1LL << 21;  // n * F from which a problem is "big"
 
 cudaError_t launch_unpack(cudaStream_t s, const uint8_t *packed, const DTask *d_tasks, int n_tasks,
                           const int *d_rows, const long long *g_off, uint8_t *G);
@@ -119,6 +122,13 @@ long long kmeans_iscratch_ints(long long n);
 cudaError_t kmeans_upload_rand(const double *h_rand);
 cudaError_t launch_kmeans_prepare(cudaStream_t s, const ClusterState *states, int n_probs, const double *X,
                                   double *dscratch, int *iscratch);
+// deep loci: one problem, every initialisation on a group of co-resident CTAs (kmeans.cu compiled a second
+// time with MPRG_KM_GROUP and L2-only loads); bars: KM_GROUP_WORDS zero-initialised unsigneds, 8-byte aligned
+constexpr int KM_GROUP_WORDS = 32 + 16 * 10;
+cudaError_t launch_kmeans_group(cudaStream_t s, ClusterState *states, int q, const double *X, double *dscratch,
+                                int *iscratch, int *assign, int *newlab, unsigned *bars, bool prepare, int sm_count,
+                                double *inertia_out = nullptr);
+cudaError_t kmeans_group_upload_rand(const double *h_rand);
 cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, const double *X,
                           double *dscratch, int *iscratch, int *assign, int *newlab, int *tickets);
 cudaError_t launch_kmeans_single(cudaStream_t s, const double *X0, int n, int F, int K, double *dscratch,

@@ -13,17 +13,30 @@
 //
 // One CTA per problem; samples (or features, for the centre update) are spread over the threads.
 #ifndef MPRG_HOST_EMU  // tests/hostemu compiles the device functions below as plain C++
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #endif
 
 namespace mprg {
+// the device functions of the two compilations of this file (single-CTA, CTA-group) must not collide
+#ifdef MPRG_KM_GROUP
+#define KM_NS km_group
+#else
+#define KM_NS km_single
+#endif
+namespace KM_NS {
 
 constexpr int KM_THREADS = 128;
 constexpr int KM_MAXK = 10;
 constexpr int KM_NINIT = 10;
 constexpr int KM_MAXITER = 300;
 
+#ifdef MPRG_KM_GROUP
+#define c_rand c_rand_group  // the second compilation of this file keeps its own copy
+#endif
 __constant__ double c_rand[KM_RAND_COUNT];  // RandomState(2).random_sample stream
 
 __device__ __forceinline__ double sqdist(const double *a, const double *b, int F) {
@@ -298,7 +311,35 @@ struct KM {
     double *Xc, *mean, *tmpF, *xx, *ca, *cb, *best_c, *lb, *ub, *closest, *cum, *D, *half, *nxt, *shift,
         *wts, *cc, *dist, *res, *tol;
     int *labels, *labels_old, *best_labels;
+    // the threads that work on this initialisation: one CTA (tid = threadIdx.x), or a group of G
+    // co-resident CTAs that meet at a barrier in global memory (deep loci, kmeans_group_kernel)
+    int tid, nthr, G;
+    unsigned *bar;
 };
+
+__device__ __forceinline__ void km_sync(const KM &k) {
+#if defined(MPRG_KM_GROUP)
+    __syncthreads();
+    if (k.G > 1) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            volatile unsigned *gen = k.bar + 1;
+            const unsigned g = *gen;
+            if (atomicAdd(k.bar, 1u) == (unsigned)k.G - 1u) {
+                *(volatile unsigned *)k.bar = 0u;
+                __threadfence();
+                atomicAdd(k.bar + 1, 1u);
+            } else {
+                while (*gen == g) __nanosleep(64);
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+#else
+    __syncthreads();
+#endif
+}
 
 // squared distance candidate -> sample through  -2 x.y + |x|^2 + |y|^2  clamped at 0
 __device__ __forceinline__ double eucl_sq(const KM &k, int cand, int i, int t, int trials) {
@@ -312,9 +353,9 @@ __device__ __forceinline__ double eucl_sq(const KM &k, int cand, int i, int t, i
 
 __device__ void center_half_distances(const KM &k, const double *C) {
     const int K = k.K, F = k.F;
-    for (int j = threadIdx.x; j < K; j += blockDim.x) k.cc[j] = einsum_self(C + (long long)j * F, F);
-    __syncthreads();
-    for (int p = threadIdx.x; p < K * K; p += blockDim.x) {
+    for (int j = k.tid; j < K; j += k.nthr) k.cc[j] = einsum_self(C + (long long)j * F, F);
+    km_sync(k);
+    for (int p = k.tid; p < K * K; p += k.nthr) {
         const int a = p / K, b = p % K;
         double v = 0.0;
         if (a != b) {
@@ -325,9 +366,9 @@ __device__ void center_half_distances(const KM &k, const double *C) {
         }
         k.half[p] = v;
     }
-    __syncthreads();
+    km_sync(k);
     // distance_next_center = np.partition(half, kth=1, axis=0)[1]: second smallest per column
-    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    for (int j = k.tid; j < K; j += k.nthr) {
         double m1 = 1e300, m2 = 1e300;
         for (int a = 0; a < K; ++a) {
             const double v = k.half[a * K + j];
@@ -336,13 +377,13 @@ __device__ void center_half_distances(const KM &k, const double *C) {
         }
         k.nxt[j] = m2;
     }
-    __syncthreads();
+    km_sync(k);
 }
 
 // E step of _update_chunk_dense (sklearn/cluster/_k_means_elkan.pyx) for every sample
 __device__ void elkan_e_step(const KM &k, const double *C) {
     const int K = k.K, F = k.F;
-    for (int i = threadIdx.x; i < k.n; i += blockDim.x) {
+    for (int i = k.tid; i < k.n; i += k.nthr) {
         double u = k.ub[i];
         bool tight = false;
         int lab = k.labels[i];
@@ -370,7 +411,7 @@ __device__ void elkan_e_step(const KM &k, const double *C) {
             k.ub[i] = u;
         }
     }
-    __syncthreads();
+    km_sync(k);
 }
 
 // one k-means run from k-means++ seeds; returns inertia in *out_inertia (thread 0 valid), final
@@ -381,7 +422,7 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
     double *C = k.ca, *Cn = k.cb;
     const int trials = 2 + (int)log((double)K);
     // ---- k-means++ (_kmeans_plusplus, sklearn/cluster/_kmeans.py) ----
-    if (threadIdx.x == 0) {
+    if (k.tid == 0) {
         // random_state.choice(n, p=1/n): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
         const double p = 1.0 / (double)n;
         double acc = 0.0;
@@ -395,20 +436,20 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
         s_int[0] = idx < n ? idx : n - 1;
     }
     rand_pos += 1;
-    __syncthreads();
+    km_sync(k);
     const int c0 = s_int[0];
 #ifdef MPRG_HOST_EMU_DEBUG
     printf("  kpp first %d (u=%.17g)\n", c0, c_rand[rand_pos - 1]);
 #endif
-    for (int f = threadIdx.x; f < F; f += blockDim.x) C[f] = k.Xc[(long long)c0 * F + f];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) k.closest[i] = eucl_sq(k, c0, i, 0, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    for (int f = k.tid; f < F; f += k.nthr) C[f] = k.Xc[(long long)c0 * F + f];
+    for (int i = k.tid; i < n; i += k.nthr) k.closest[i] = eucl_sq(k, c0, i, 0, 1);
+    km_sync(k);
+    if (k.tid == 0) {
         s_scalar[0] = ddot_ones(k.closest, n);
     }
-    __syncthreads();
+    km_sync(k);
     for (int c = 1; c < K; ++c) {
-        if (threadIdx.x == 0) {
+        if (k.tid == 0) {
             const double pot = s_scalar[0];
             double acc = 0.0;
             for (int i = 0; i < n; ++i) {
@@ -426,15 +467,15 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
             }
         }
         rand_pos += trials;
-        __syncthreads();
-        for (int p = threadIdx.x; p < trials * n; p += blockDim.x) {
+        km_sync(k);
+        for (int p = k.tid; p < trials * n; p += k.nthr) {
             const int t = p / n, i = p % n;
             const double d = eucl_sq(k, s_int[1 + t], i, t, trials);
             const double cl = k.closest[i];
             k.D[p] = cl < d ? cl : d;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        km_sync(k);
+        if (k.tid == 0) {
             int best = 0;
             double best_pot = 0.0;
             for (int t = 0; t < trials; ++t) {
@@ -452,25 +493,25 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
             printf(" best %d pot %.17g\n", best, best_pot);
 #endif
         }
-        __syncthreads();
+        km_sync(k);
         const int best = s_int[0], cand = s_int[1 + best];
-        for (int i = threadIdx.x; i < n; i += blockDim.x) k.closest[i] = k.D[best * n + i];
-        for (int f = threadIdx.x; f < F; f += blockDim.x) C[(long long)c * F + f] = k.Xc[(long long)cand * F + f];
-        __syncthreads();
+        for (int i = k.tid; i < n; i += k.nthr) k.closest[i] = k.D[best * n + i];
+        for (int f = k.tid; f < F; f += k.nthr) C[(long long)c * F + f] = k.Xc[(long long)cand * F + f];
+        km_sync(k);
     }
 
     // ---- Elkan (_kmeans_single_elkan) ----
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = k.tid; i < n; i += k.nthr) {
         k.labels[i] = -1;
         k.labels_old[i] = -1;
         k.ub[i] = 0.0;
     }
-    for (long long p = threadIdx.x; p < (long long)n * K; p += blockDim.x) k.lb[p] = 0.0;
-    for (long long p = threadIdx.x; p < (long long)K * F; p += blockDim.x) Cn[p] = 0.0;
-    __syncthreads();
+    for (long long p = k.tid; p < (long long)n * K; p += k.nthr) k.lb[p] = 0.0;
+    for (long long p = k.tid; p < (long long)K * F; p += k.nthr) Cn[p] = 0.0;
+    km_sync(k);
     center_half_distances(k, C);
     // init_bounds_dense
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = k.tid; i < n; i += k.nthr) {
         const double *x = k.Xc + (long long)i * F;
         int best = 0;
         double md = sqrt(sqdist(x, C, F));
@@ -488,12 +529,12 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
         k.labels[i] = best;
         k.ub[i] = md;
     }
-    __syncthreads();
+    km_sync(k);
     bool strict = false;
     for (int it = 0; it < KM_MAXITER; ++it) {
         elkan_e_step(k, C);
         // M step: member sums in sample order (thread per feature), weights
-        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        for (int f = k.tid; f < F; f += k.nthr) {
             double acc[KM_MAXK];
 #pragma unroll
             for (int j = 0; j < KM_MAXK; ++j) acc[j] = 0.0;
@@ -508,7 +549,7 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
             for (int j = 0; j < KM_MAXK; ++j)
                 if (j < K) Cn[(long long)j * F + f] = acc[j];
         }
-        if (threadIdx.x == 0) {
+        if (k.tid == 0) {
             for (int j = 0; j < K; ++j) k.wts[j] = 0.0;
             for (int i = 0; i < n; ++i) k.wts[k.labels[i]] += 1.0;
             int emask = 0;
@@ -516,29 +557,29 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
                 if (k.wts[j] == 0.0) emask |= 1 << j;
             s_int[0] = emask;
         }
-        __syncthreads();
+        km_sync(k);
         const int emask = s_int[0];
         if (emask != 0) {
             // _relocate_empty_clusters_dense: farthest samples re-seed the empty clusters
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            for (int i = k.tid; i < n; i += k.nthr) {
                 const double *x = k.Xc + (long long)i * F;
                 const double *c = C + (long long)k.labels[i] * F;
                 // ((X - C[labels])**2).sum(axis=1): numpy pairwise summation over the features
                 const double res = np_pairwise_sqdiff(x, c, 0, F);
                 k.dist[i] = res;
             }
-            __syncthreads();
-            if (threadIdx.x == 0) {
+            km_sync(k);
+            if (k.tid == 0) {
                 double mx = 0.0;
                 for (int i = 0; i < n; ++i) mx = k.dist[i] > mx ? k.dist[i] : mx;
                 s_int[1] = mx != 0.0;
             }
-            __syncthreads();
+            km_sync(k);
             if (s_int[1]) {
                 // one empty cluster at a time (ascending id), farthest remaining sample first
                 for (int e = 0; e < K; ++e) {
                     if (!((emask >> e) & 1)) continue;  // the empty set is fixed before relocating
-                    if (threadIdx.x == 0) {
+                    if (k.tid == 0) {
                         int far = 0;
                         double best = -1.0;
                         for (int i = 0; i < n; ++i)
@@ -549,33 +590,33 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
                         k.dist[far] = -2.0;  // taken
                         s_int[2] = far;
                     }
-                    __syncthreads();
+                    km_sync(k);
                     const int far = s_int[2], old = k.labels[far];
-                    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+                    for (int f = k.tid; f < F; f += k.nthr) {
                         const double x = k.Xc[(long long)far * F + f];
                         Cn[(long long)old * F + f] = __dsub_rn(Cn[(long long)old * F + f], x);
                         Cn[(long long)e * F + f] = x;
                     }
-                    __syncthreads();
-                    if (threadIdx.x == 0) {
+                    km_sync(k);
+                    if (k.tid == 0) {
                         k.wts[e] = 1.0;
                         k.wts[old] -= 1.0;
                     }
-                    __syncthreads();
+                    km_sync(k);
                 }
             }
         }
         // _average_centers (thread per feature, clusters in ascending order as the reference loop)
-        if (threadIdx.x == 0) {
+        if (k.tid == 0) {
             int amax = 0;
             for (int j = 1; j < K; ++j)
                 if (k.wts[j] > k.wts[amax]) amax = j;
-            s_int[0] = amax;
+            s_int[5] = amax;  // its own slot: slot 0 (emask) may still be unread by slower threads
         }
-        __syncthreads();
+        km_sync(k);
         {
-            const int amax = s_int[0];
-            for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            const int amax = s_int[5];
+            for (int f = k.tid; f < F; f += k.nthr) {
                 for (int j = 0; j < K; ++j) {
                     if (k.wts[j] > 0.0) {
                         const double alpha = 1.0 / k.wts[j];
@@ -586,19 +627,19 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
                 }
             }
         }
-        __syncthreads();
+        km_sync(k);
         // _center_shift, bounds update
-        for (int j = threadIdx.x; j < K; j += blockDim.x)
+        for (int j = k.tid; j < K; j += k.nthr)
             k.shift[j] = sqrt(sqdist(Cn + (long long)j * F, C + (long long)j * F, F));
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        km_sync(k);
+        for (int i = k.tid; i < n; i += k.nthr) {
             k.ub[i] = __dadd_rn(k.ub[i], k.shift[k.labels[i]]);
             for (int j = 0; j < K; ++j) {
                 double v = __dsub_rn(k.lb[(long long)i * K + j], k.shift[j]);
                 k.lb[(long long)i * K + j] = v < 0.0 ? 0.0 : v;
             }
         }
-        __syncthreads();
+        km_sync(k);
         center_half_distances(k, Cn);
         {
             double *t = C;
@@ -606,7 +647,7 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
             Cn = t;
         }
         // convergence
-        if (threadIdx.x == 0) {
+        if (k.tid == 0) {
             bool same = true;
             for (int i = 0; i < n && same; ++i) same = k.labels[i] == k.labels_old[i];
             int stop = 0;
@@ -616,29 +657,29 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
                 for (int j = 0; j < K; ++j) sq[j] = __dmul_rn(k.shift[j], k.shift[j]);
                 if (np_pairwise_sum(sq, K) <= tol) stop = 2;
             }
-            s_int[0] = stop;
+            s_int[6] = stop;
         }
-        __syncthreads();
-        const int stop = s_int[0];
+        km_sync(k);
+        const int stop = s_int[6];
         if (stop == 1) {
             strict = true;
             break;
         }
         if (stop == 2) break;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) k.labels_old[i] = k.labels[i];
-        __syncthreads();
+        for (int i = k.tid; i < n; i += k.nthr) k.labels_old[i] = k.labels[i];
+        km_sync(k);
     }
     if (!strict) elkan_e_step(k, C);
     // _inertia_dense: sequential over samples
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int i = k.tid; i < n; i += k.nthr)
         k.dist[i] = sqdist(k.Xc + (long long)i * F, C + (long long)k.labels[i] * F, F);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    km_sync(k);
+    if (k.tid == 0) {
         double inertia = 0.0;
         for (int i = 0; i < n; ++i) inertia = __dadd_rn(inertia, k.dist[i]);
         s_scalar[1] = inertia;
     }
-    __syncthreads();
+    km_sync(k);
     *out_C = C;
 }
 
@@ -683,13 +724,17 @@ __device__ void km_bind_init(KM &k, int n, int F, int K, const double *X0, doubl
     k.labels_old = ii; ii += n;
     k.best_c = nullptr;
     k.best_labels = nullptr;
+    k.tid = threadIdx.x;
+    k.nthr = blockDim.x;
+    k.G = 1;
+    k.bar = nullptr;
 }
 
 // once per problem: tolerance on the un-centred data, column means, centring, squared row norms
 // (KMeans._tolerance, X -= X.mean(axis=0), row_norms(X, squared=True) in sklearn/cluster/_kmeans.py)
 __device__ void kmeans_prepare(KM &k) {
     const int n = k.n, F = k.F;
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    for (int f = k.tid; f < F; f += k.nthr) {
         double s = 0.0;
         for (int i = 0; i < n; ++i) s = __dadd_rn(s, k.X0[(long long)i * F + f]);
         const double m = s / (double)n;
@@ -702,10 +747,10 @@ __device__ void kmeans_prepare(KM &k) {
         k.mean[f] = m;
         k.tmpF[f] = v / (double)n;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) k.tol[0] = __dmul_rn(np_pairwise_sum(k.tmpF, F) / (double)F, 1e-4);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) k.xx[i] = einsum_self(k.Xc + (long long)i * F, F);
-    __syncthreads();
+    km_sync(k);
+    if (k.tid == 0) k.tol[0] = __dmul_rn(np_pairwise_sum(k.tmpF, F) / (double)F, 1e-4);
+    for (int i = k.tid; i < n; i += k.nthr) k.xx[i] = einsum_self(k.Xc + (long long)i * F, F);
+    km_sync(k);
 }
 
 // one initialisation: k-means++ from the init-th slice of the RandomState(2) stream, Elkan; leaves
@@ -718,11 +763,11 @@ __device__ void kmeans_run_init(KM &k, int init, double *s_scalar, int *s_int) {
     int rand_pos = init * (1 + (K - 1) * trials);
     const double *C = nullptr;
     kmeans_single(k, rand_pos, tol, s_scalar, s_int, &C);
-    if (threadIdx.x == 0) {
+    if (k.tid == 0) {
         k.res[0] = s_scalar[1];
         k.res[1] = (C == k.ca) ? 0.0 : 1.0;
     }
-    __syncthreads();
+    km_sync(k);
 }
 
 // best-of-n_init selection (strict inertia improvement and not the same clustering), then predict on
@@ -780,20 +825,25 @@ __device__ void kmeans_select_predict(int n, int F, int K, const double *X0, dou
     __syncthreads();
 }
 
+}  // namespace KM_NS
+using namespace KM_NS;
+
+#ifndef MPRG_KM_GROUP
 // scratch per problem: shared block | KM_NINIT init blocks | best_c [KM_MAXK * F] | cc [KM_MAXK] ;
 // ints: KM_NINIT init blocks
 long long kmeans_dscratch_doubles(long long n, long long F) {
     return km_shared_doubles(n, F) + KM_NINIT * km_init_doubles(n, F) + KM_MAXK * F + KM_MAXK + 8;
 }
 long long kmeans_iscratch_ints(long long n) { return KM_NINIT * km_init_ints(n) + 8; }
+#endif
 
-#ifndef MPRG_HOST_EMU
+#if !defined(MPRG_HOST_EMU) && !defined(MPRG_KM_GROUP)
 // one CTA per problem that is about to run KMeans for the first time (K == 2 round)
 __global__ void __launch_bounds__(KM_THREADS)
 kmeans_prepare_kernel(const ClusterState *__restrict__ states, const double *__restrict__ X_all,
                       double *__restrict__ dscratch, int *__restrict__ iscratch) {
     const ClusterState &st = states[blockIdx.x];
-    if (st.status != 0 || !st.run_kmeans) return;
+    if (st.status != 0 || !st.run_kmeans || st.big) return;
     KM k;
     km_bind_init(k, st.n, st.F, st.K, X_all + st.x_off, dscratch + st.kmd_off, iscratch + st.kmi_off, 0);
     kmeans_prepare(k);
@@ -808,7 +858,7 @@ kmeans_kernel(ClusterState *__restrict__ states, const double *__restrict__ X_al
     __shared__ double s_scalar[4];
     __shared__ int s_int[8];
     ClusterState &st = states[blockIdx.x];
-    if (st.status != 0 || !st.run_kmeans) return;
+    if (st.status != 0 || !st.run_kmeans || st.big) return;
     const int n = st.n, F = st.F, K = st.K, init = blockIdx.y;
     const double *X0 = X_all + st.x_off;
     double *d0 = dscratch + st.kmd_off;
@@ -867,6 +917,79 @@ kmeans_single_problem_kernel(const double *X0, int n, int F, int K, double *dscr
     kmeans_select_predict(n, F, K, X0, dscratch, iscratch, s_int, labels, inertia);
     if (threadIdx.x == 0) *ticket = 0;
 }
+#elif defined(MPRG_KM_GROUP)
+// ---- deep loci: one problem on the whole GPU ----------------------------------------------------------
+// Every initialisation runs on a group of G co-resident CTAs (cooperative launch): the loops over
+// samples and over features are spread over the G * KM_THREADS threads of the group, the sequential
+// parts stay with its first thread, and __syncthreads becomes a barrier in global memory (km_sync).
+// Every dot product, sum and comparison is the one the single-CTA kernel does, in the same order, so
+// labels and inertia are bit-identical.  This object is compiled with -dlcm=cg: data written by one
+// CTA of the group is read by the others through L2, never from a stale L1 line.
+// bars (8-byte aligned, 32 + 16 * KM_NINIT zero-initialised words): [2 * init] barrier of initialisation
+// init | [2 * KM_NINIT] barrier of the preparation | [2 * KM_NINIT + 2] ticket | [32 + 16 * init]
+// broadcast slots of initialisation init (4 doubles, 8 ints)
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_group_prepare_kernel(const ClusterState *__restrict__ states, int q, const double *__restrict__ X_all,
+                            double *__restrict__ dscratch, int *__restrict__ iscratch, unsigned *bars) {
+    const ClusterState &st = states[q];
+    if (st.status != 0 || !st.run_kmeans) return;
+    KM k;
+    km_bind_init(k, st.n, st.F, st.K, X_all + st.x_off, dscratch + st.kmd_off, iscratch + st.kmi_off, 0);
+    k.tid = blockIdx.x * blockDim.x + threadIdx.x;
+    k.nthr = gridDim.x * blockDim.x;
+    k.G = gridDim.x;
+    k.bar = bars + 2 * KM_NINIT;
+    kmeans_prepare(k);
+}
+
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_group_kernel(ClusterState *__restrict__ states, int q, const double *__restrict__ X_all,
+                    double *__restrict__ dscratch, int *__restrict__ iscratch, int *__restrict__ assign_all,
+                    int *__restrict__ newlab_all, unsigned *bars, int G, double *inertia_out) {
+    __shared__ int s_last;
+    __shared__ int s_sel[8];
+    ClusterState &st = states[q];
+    if (st.status != 0 || !st.run_kmeans) return;
+    const int n = st.n, F = st.F, K = st.K;
+    const int init = blockIdx.x / G, rank = blockIdx.x % G;
+    const double *X0 = X_all + st.x_off;
+    double *d0 = dscratch + st.kmd_off;
+    int *i0 = iscratch + st.kmi_off;
+    KM k;
+    km_bind_init(k, n, F, K, X0, d0, i0, init);
+    k.tid = rank * blockDim.x + threadIdx.x;
+    k.nthr = G * blockDim.x;
+    k.G = G;
+    k.bar = bars + 2 * init;
+    // the broadcast slots of kmeans_single (thread 0 of the group writes, everybody reads after the
+    // barrier) live in the communication area next to the barriers: 16 words per initialisation
+    unsigned *slots = bars + 32 + 16 * init;
+    kmeans_run_init(k, init, reinterpret_cast<double *>(slots), reinterpret_cast<int *>(slots + 8));
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&bars[2 * KM_NINIT + 2], 1u) == (unsigned)(KM_NINIT * G - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    int *newlab = newlab_all + st.assign_off;
+    int *assign = assign_all + st.assign_off;
+    kmeans_select_predict(n, F, K, X0, d0, i0, s_sel, newlab, inertia_out);
+    if (threadIdx.x == 0) {
+        // cluster_sequences.py:267-274: fewer distinct labels than K => keep the previous assignment
+        unsigned seen = 0;
+        for (int i = 0; i < n; ++i) seen |= 1u << newlab[i];
+        const int distinct = __popc(seen);
+        if (distinct < K) {
+            st.K -= 1;
+            st.status = 1;
+        } else {
+            for (int i = 0; i < n; ++i) assign[i] = newlab[i];
+        }
+        bars[2 * KM_NINIT + 2] = 0u;
+        __threadfence();
+        st.run_kmeans = 0;
+    }
+}
 #else
 // host emulation (tests/hostemu): the same device functions, initialisations one after the other
 void kmeans_single_problem_kernel(const double *X0, int n, int F, int K, double *dscratch, int *iscratch,
@@ -884,8 +1007,51 @@ void kmeans_single_problem_kernel(const double *X0, int n, int F, int K, double 
 }
 #endif
 
-#ifndef MPRG_HOST_EMU
+#if defined(MPRG_KM_GROUP)
+cudaError_t kmeans_group_upload_rand(const double *h_rand) {
+    return cudaMemcpyToSymbol(c_rand, h_rand, sizeof(double) * KM_RAND_COUNT);
+}
+
+cudaError_t launch_kmeans_group(cudaStream_t s, ClusterState *states, int q, const double *X, double *dscratch,
+                                int *iscratch, int *assign, int *newlab, unsigned *bars, bool prepare, int sm_count,
+                                double *inertia_out) {
+    static int occ = 0, occ_prep = 0;
+    if (!occ) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kmeans_group_kernel, KM_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_prep, kmeans_group_prepare_kernel, KM_THREADS, 0);
+        occ = occ > 0 ? occ : 1;
+        occ_prep = occ_prep > 0 ? occ_prep : 1;
+    }
+    cudaError_t e;
+    if (prepare) {
+        int gp = std::max(1, std::min(sm_count * occ_prep, sm_count));
+        if (const char *env = getenv("MPRG_KM_G")) gp = std::max(1, std::min(atoi(env), gp));  // debugging knob
+        const dim3 grid((unsigned)gp);
+        void *args[] = {(void *)&states, (void *)&q, (void *)&X, (void *)&dscratch, (void *)&iscratch, (void *)&bars};
+        e = cudaLaunchCooperativeKernel((const void *)kmeans_group_prepare_kernel, grid, dim3(KM_THREADS), args, 0, s);
+        if (e != cudaSuccess) return e;
+        if (getenv("MPRG_DEBUG_SYNC")) {
+            e = cudaStreamSynchronize(s);
+            fprintf(stderr, "[mprg debug] group prepare grid %u: %s\n", grid.x, cudaGetErrorString(e));
+            if (e != cudaSuccess) return e;
+        }
+    }
+    int G = std::max(1, std::min((sm_count * occ) / KM_NINIT, 32));
+    if (const char *env = getenv("MPRG_KM_G")) G = std::max(1, std::min(atoi(env), G));  // debugging knob
+    const dim3 grid((unsigned)(KM_NINIT * G));
+    void *args[] = {(void *)&states, (void *)&q, (void *)&X, (void *)&dscratch, (void *)&iscratch,
+                    (void *)&assign, (void *)&newlab, (void *)&bars, (void *)&G, (void *)&inertia_out};
+    e = cudaLaunchCooperativeKernel((const void *)kmeans_group_kernel, grid, dim3(KM_THREADS), args, 0, s);
+    if (e == cudaSuccess && getenv("MPRG_DEBUG_SYNC")) {
+        e = cudaStreamSynchronize(s);
+        fprintf(stderr, "[mprg debug] group kernel grid %u (G %d): %s\n", grid.x, G, cudaGetErrorString(e));
+    }
+    return e;
+}
+#elif !defined(MPRG_HOST_EMU)
 cudaError_t kmeans_upload_rand(const double *h_rand) {
+    const cudaError_t e = kmeans_group_upload_rand(h_rand);
+    if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_rand, h_rand, sizeof(double) * KM_RAND_COUNT);
 }
 

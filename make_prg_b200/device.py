@@ -229,13 +229,14 @@ class Context:
                                                   C.byref(n), C.byref(F), ptr(X), X.size))
         return X
 
-    def kmeans(self, X, K):
-        """KMeans(K, random_state=2, elkan, n_init=10).fit(X).predict(X) -> (labels, inertia)."""
+    def kmeans(self, X, K, mode=0):
+        """KMeans(K, random_state=2, elkan, n_init=10).fit(X).predict(X) -> (labels, inertia).
+        mode 0: the engine's choice, 1: one CTA per initialisation, 2: CTA groups (deep loci)."""
         X = np.ascontiguousarray(X, np.float64)
         labels = np.zeros(X.shape[0], np.int32)
         inertia = C.c_double(0)
-        self._check(self.lib.mprg_kmeans(self.handle, ptr(X), X.shape[0], X.shape[1], K, ptr(labels),
-                                         C.byref(inertia)))
+        self._check(self.lib.mprg_kmeans_mode(self.handle, ptr(X), X.shape[0], X.shape[1], K, ptr(labels),
+                                              C.byref(inertia), mode))
         return labels, inertia.value
 
     def one_ref_like(self, batch, task, cluster_of_row, n_clusters):

@@ -25,6 +25,6 @@ namespace mprg {
 constexpr int KM_RAND_COUNT = 400;
 struct ClusterState {
     int status, run_kmeans, K, n, F, w;
-    long long g_off; int mem_off, mem_rows_off, assign_off; long long maj_off, x_off, kmd_off, kmi_off;
+    long long g_off; int mem_off, mem_rows_off, assign_off; long long maj_off, x_off, kmd_off, kmi_off; int big, pad;
 };
 }

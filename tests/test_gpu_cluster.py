@@ -76,6 +76,26 @@ def test_kmer_count_matrix_big_problem(ctx):
         assert (want.shape[1] * 4 > 200 * 1024) == (l == 1)  # only the second case is past the smem histogram
 
 
+def test_kmeans_cta_groups_equal_single_cta(ctx):
+    """Deep loci run every initialisation on a group of co-resident CTAs (global-memory barrier, loads
+    through L2).  Same operations in the same order: labels and inertia must be bit-identical to the
+    one-CTA kernel, which is pinned to scikit-learn by the golden cases -- on those cases, and on count
+    matrices of the size that takes the group path in the engine."""
+    n = 0
+    for X, K, labels, inertia in kmeans_cases():
+        if n % 9 == 0:
+            got, got_inertia = ctx.kmeans(X, K, mode=2)
+            assert np.array_equal(got, labels) and got_inertia == inertia, (X.shape, K)
+        n += 1
+    rng = np.random.default_rng(11)
+    for rows, F, K in [(700, 3100, 2), (1500, 1500, 5), (400, 6000, 10)]:
+        centres = rng.integers(0, 4, (K + 1, F))
+        X = (centres[rng.integers(0, K + 1, rows)] + (rng.random((rows, F)) < 0.02)).astype(np.float64)
+        a, ia = ctx.kmeans(X, K, mode=1)
+        b, ib = ctx.kmeans(X, K, mode=2)
+        assert np.array_equal(a, b) and ia == ib, (rows, F, K)
+
+
 def test_kmeans_golden_cases(ctx):
     """Labels identical and inertia bit-identical to what scikit-learn returned inside the reference on
     every count matrix it was handed (north_star asks for identical labels, inertia within 1e-6)."""
