@@ -483,7 +483,7 @@ refcheck_kernel(ClusterState *__restrict__ states, const uint8_t *__restrict__ G
     __shared__ int first_s[16][128];
     __shared__ int s_bad, s_bad_c;
     ClusterState &st = states[blockIdx.x];
-    if (st.status != 0) return;
+    if (st.status != 0 || (st.big_ref && !flags_out)) return;  // big problems: launch_refcheck_big
     const uint8_t *g = G + st.g_off;
     const int w = st.w, n = st.n, K = st.K;
     const int *mem_off = mem_off_all + st.mem_off;   // n + 1 entries, into mem_rows
@@ -558,6 +558,101 @@ refcheck_kernel(ClusterState *__restrict__ states, const uint8_t *__restrict__ G
             else st.run_kmeans = 1;
         }
     }
+}
+
+// ---- the same check for a deep locus, with the whole grid -----------------------------------------
+// grid (column strips of 128, clusters): majority symbol per column of cluster blockIdx.y, members in
+// member order, ties to the first-seen symbol -- the loop of refcheck_kernel, one strip per CTA
+__global__ void __launch_bounds__(128)
+refcheck_big_majority_kernel(const ClusterState *__restrict__ states, int q, const uint8_t *__restrict__ G,
+                             const int *__restrict__ mem_off_all, const int *__restrict__ mem_rows_all,
+                             const int *__restrict__ assign_all, uint8_t *__restrict__ maj_all) {
+    __shared__ int cnt_s[16][128];
+    __shared__ int first_s[16][128];
+    const ClusterState &st = states[q];
+    const int c = blockIdx.y;
+    if (st.status != 0 || c >= st.K) return;
+    const uint8_t *g = G + st.g_off;
+    const int w = st.w, n = st.n;
+    const int *mem_off = mem_off_all + st.mem_off;
+    const int *mem_rows = mem_rows_all + st.mem_rows_off;
+    const int *assign = assign_all + st.assign_off;
+    uint8_t *maj = maj_all + st.maj_off + (long long)c * w;
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col >= w) return;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) cnt_s[s][threadIdx.x] = 0;
+    int order = 0;
+    for (int j = 0; j < n; ++j) {
+        if (assign[j] != c) continue;
+        for (int m = mem_off[j]; m < mem_off[j + 1]; ++m) {
+            const int s = g[(long long)mem_rows[m] * w + col];
+            if (cnt_s[s][threadIdx.x]++ == 0) first_s[s][threadIdx.x] = order;
+            ++order;
+        }
+    }
+    int best = -1, best_cnt = 0, best_first = 0;
+    for (int s = 0; s < 16; ++s) {
+        const int cn = cnt_s[s][threadIdx.x];
+        if (cn == 0) continue;
+        const int fi = first_s[s][threadIdx.x];
+        if (cn > best_cnt || (cn == best_cnt && fi < best_first)) {
+            best = s;
+            best_cnt = cn;
+            best_first = fi;
+        }
+    }
+    maj[col] = (uint8_t)best;
+}
+
+// one warp per distinct sequence j: Hamming distance of each of its member rows to the majority string
+// of its cluster; a row further than the threshold marks the cluster (and the problem) as not
+// one-reference-like
+__global__ void __launch_bounds__(128)
+refcheck_big_hamming_kernel(const ClusterState *__restrict__ states, int q, const uint8_t *__restrict__ G,
+                            const int *__restrict__ mem_off_all, const int *__restrict__ mem_rows_all,
+                            const int *__restrict__ assign_all, const uint8_t *__restrict__ maj_all,
+                            int *__restrict__ flags) {
+    const ClusterState &st = states[q];
+    if (st.status != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (j >= st.n) return;
+    const uint8_t *g = G + st.g_off;
+    const int w = st.w;
+    const int *mem_off = mem_off_all + st.mem_off;
+    const int *mem_rows = mem_rows_all + st.mem_rows_off;
+    const int c = assign_all[st.assign_off + j];
+    const uint8_t *maj = maj_all + st.maj_off + (long long)c * w;
+    const int thr = w < 5 ? 1 : (int)(0.2 * (double)w);
+    for (int m = mem_off[j]; m < mem_off[j + 1]; ++m) {
+        const uint8_t *row = g + (long long)mem_rows[m] * w;
+        int d = 0;
+        for (int i = lane; i < w; i += 32) d += row[i] != maj[i];
+        d = __reduce_add_sync(0xffffffffu, d);
+        if (d > thr) {
+            if (lane == 0) {
+                flags[0] = 1;
+                flags[1 + c] = 1;
+            }
+            break;
+        }
+    }
+}
+
+// kmeans_cluster_seqs loop control (cluster_sequences.py:256-261), then the flags are reset
+__global__ void refcheck_big_control_kernel(ClusterState *__restrict__ states, int q, int max_clusters,
+                                            int *__restrict__ flags) {
+    ClusterState &st = states[q];
+    if (st.status != 0) return;
+    if (!flags[0]) {
+        st.status = 1;
+    } else {
+        st.K = st.K + 1;
+        if (st.K > max_clusters || st.K == st.n) st.status = 1;
+        else st.run_kmeans = 1;
+    }
+    for (int i = 0; i < REFCHECK_FLAG_INTS; ++i) flags[i] = 0;
 }
 
 // ---- small device-side bookkeeping so that only O(#distinct) data crosses PCIe ---------------------
@@ -737,6 +832,17 @@ cudaError_t launch_refcheck(cudaStream_t s, ClusterState *states, int n_probs, c
     if (n_probs <= 0) return cudaSuccess;
     refcheck_kernel<<<n_probs, 128, 0, s>>>(states, G, mem_off, mem_rows, assign, maj, max_clusters,
                                             flags_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_refcheck_big(cudaStream_t s, ClusterState *states, int q, int w, int rows, const uint8_t *G,
+                                const int *mem_off, const int *mem_rows, int *assign, uint8_t *maj, int max_clusters,
+                                int *flag_blocks) {
+    int *flags = flag_blocks;
+    refcheck_big_majority_kernel<<<dim3((w + 127) / 128, max_clusters), 128, 0, s>>>(states, q, G, mem_off, mem_rows,
+                                                                                     assign, maj);
+    refcheck_big_hamming_kernel<<<(rows + 3) / 4, 128, 0, s>>>(states, q, G, mem_off, mem_rows, assign, maj, flags);
+    refcheck_big_control_kernel<<<1, 1, 0, s>>>(states, q, max_clusters, flags);
     return cudaGetLastError();
 }
 

@@ -327,6 +327,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         std::vector<MemberProb> mp(np);
         long long useq_total = 0, ints_total = 0, tab_total = 0, x_total = 0;
         long long maj_total = 0, assign_total = 0, memoff_total = 0, memrows_total = 0;
+        std::vector<int> big_ref_q;  // deep loci: one-reference-like check with the whole grid
         for (int q = 0; q < np; ++q) {
             const Prob &p = probs[q];
             const mprg_task &ht = h_tasks[p.task];
@@ -373,7 +374,13 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
             c.assign_off = (int)assign_total;
             assign_total += p.n;
             c.maj_off = maj_total;
-            maj_total += w;
+            if ((long long)ht.n_rows * w >= REFCHECK_BIG_SYMBOLS) {
+                c.big_ref = 1 + (int)big_ref_q.size();
+                big_ref_q.push_back(q);
+                maj_total += 10LL * w;  // one majority string per cluster
+            } else {
+                maj_total += w;
+            }
         }
         // 7 kprobs|mprobs, 8 useq, 9 ints, 10 keys, 11 ming, 12 X, 13 states|F, 14 seq_rows|mem|assign|newlab|maj, 15 kmeans scratch
         MPRG_CUDA(ctx, B[7].reserve(sizeof(KmerProb) * np + sizeof(MemberProb) * np));
@@ -381,7 +388,8 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         MPRG_CUDA(ctx, B[9].reserve(sizeof(int) * ints_total));
         MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * tab_total));
         MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * tab_total));
-        MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * 2 * np + KM_GROUP_WORDS * sizeof(unsigned) + 64));
+        MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * 2 * np + KM_GROUP_WORDS * sizeof(unsigned) +
+                                      sizeof(int) * REFCHECK_FLAG_INTS * big_ref_q.size() + 64));
         const size_t o_seqrows = 0;
         const size_t o_memoff = o_seqrows + sizeof(int) * seq_rows.size();
         const size_t o_memrows = o_memoff + sizeof(int) * memoff_total;
@@ -406,7 +414,22 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         int *d_tickets = d_F + np;  // per-problem "initialisations finished" counters of kmeans_kernel
         // barriers and broadcast slots of launch_kmeans_group (8-byte aligned)
         unsigned *d_bars = reinterpret_cast<unsigned *>(d_tickets + np);  // d_F + 2 * np: 8-byte aligned
-        MPRG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, sizeof(int) * (np + 1) + KM_GROUP_WORDS * sizeof(unsigned), s));
+        int *d_refflags = reinterpret_cast<int *>(d_bars + KM_GROUP_WORDS);
+        MPRG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0,
+                                       sizeof(int) * np + KM_GROUP_WORDS * sizeof(unsigned) +
+                                           sizeof(int) * REFCHECK_FLAG_INTS * big_ref_q.size(),
+                                       s));
+        auto refcheck_all = [&]() -> cudaError_t {
+            cudaError_t e = launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, 10);
+            ctx->launches++;
+            for (size_t b = 0; b < big_ref_q.size() && e == cudaSuccess; ++b) {
+                const int q = big_ref_q[b];
+                e = launch_refcheck_big(s, d_states, q, st[q].w, st[q].n, B[3].as<uint8_t>(), d_memoff, d_memrows,
+                                        d_assign, d_maj, 10, d_refflags + REFCHECK_FLAG_INTS * b);
+                ctx->launches += 3;
+            }
+            return e;
+        };
         // d_leader_u is free after dedupe: scratch for the group -> long-sequence map
         MPRG_CUDA(ctx, launch_members(s, d_mp, np, d_group, d_leadlen, d_leader_u, d_memoff, d_memrows));
         MPRG_CUDA(ctx, launch_kmer(s, d_kp, np, d_seqrows, B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
@@ -481,8 +504,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_states, st.data(), sizeof(ClusterState) * np, s));
         MPRG_CUDA(ctx, cudaMemsetAsync(d_assign, 0, sizeof(int) * assign_total, s));
         const int MAX_CLUSTERS = 10;
-        MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
-        ctx->launches++;
+        MPRG_CUDA(ctx, refcheck_all());
         // every problem that ever runs KMeans runs it in the K == 2 round: centre its data once, now
         MPRG_CUDA(ctx, launch_kmeans_prepare(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi));
         ctx->launches++;
@@ -497,8 +519,8 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
             }
             MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab,
                                          d_tickets));
-            MPRG_CUDA(ctx, launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, MAX_CLUSTERS));
-            ctx->launches += 2;
+            MPRG_CUDA(ctx, refcheck_all());
+            ctx->launches++;
         }
         h_assign.resize((size_t)assign_total);
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, st.data(), d_states, sizeof(ClusterState) * np, s));

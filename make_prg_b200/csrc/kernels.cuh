@@ -79,8 +79,10 @@ struct ClusterState {
     long long kmd_off;       // KMeans double scratch
     long long kmi_off;       // KMeans int scratch
     int big;                 // KMeans of this problem runs on CTA groups (launch_kmeans_group)
-    int pad;
+    int big_ref;             // 1 + index of its flag block: checked by launch_refcheck_big (whole grid)
 };
+constexpr long long REFCHECK_BIG_SYMBOLS = 1LL << 22;  // rows * width from which the one-reference-like check is "big"
+constexpr int REFCHECK_FLAG_INTS = 16;                 // flag block of a big problem: [0] any bad, [1 + c] cluster c bad
 constexpr long long KMEANS_BIG_ELEMENTS = 1LL << 21;  // n * F from which a problem is "big"
 
 cudaError_t launch_unpack(cudaStream_t s, const uint8_t *packed, const DTask *d_tasks, int n_tasks,
@@ -117,6 +119,11 @@ cudaError_t launch_kmer_fill(cudaStream_t s, const void *d_probs, int n_probs, l
 cudaError_t launch_refcheck(cudaStream_t s, ClusterState *states, int n_probs, const uint8_t *G,
                             const int *mem_off, const int *mem_rows, int *assign, uint8_t *maj,
                             int max_clusters, int *flags_out = nullptr);
+// deep loci: the same check for one problem with the whole grid (majority per column strip and cluster, one warp
+// per member row for the Hamming distances); maj holds max_clusters * w bytes for such a problem
+cudaError_t launch_refcheck_big(cudaStream_t s, ClusterState *states, int q, int w, int rows, const uint8_t *G,
+                                const int *mem_off, const int *mem_rows, int *assign, uint8_t *maj, int max_clusters,
+                                int *flag_blocks);
 long long kmeans_dscratch_doubles(long long n, long long F);
 long long kmeans_iscratch_ints(long long n);
 cudaError_t kmeans_upload_rand(const double *h_rand);

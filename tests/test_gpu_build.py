@@ -113,3 +113,14 @@ def test_build_ascii_equals_upload_then_build(ctx):
         got.free()
         batch.free()
     ctx.set_workers(4)
+
+
+def test_deep_locus_takes_the_whole_grid_paths(ctx):
+    """One deep locus (every row distinct: private SNPs) sends a single huge clustering problem through
+    the whole-grid k-mer numbering, the CTA-group KMeans and the whole-grid one-reference-like check;
+    the PRG must still be the oracle's, byte for byte."""
+    M = synth.synth_msa(1500, 3000, 4_100_000, n_haps=300, var_frac=0.04, private_snp=0.01)
+    want, _ = mo.build_prg_from_matrix([f"s{r}" for r in range(M.shape[0])], M, 10, 7)
+    _, res = _build(ctx, [M], 10, 7)
+    assert res.status(0) == 0
+    assert hashlib.sha256(res.prg(0).encode()).hexdigest() == hashlib.sha256(want.encode()).hexdigest()
