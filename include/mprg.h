@@ -192,6 +192,9 @@ int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, int32_t mi
 int mprg_build_ascii(mprg_ctx *ctx, const uint8_t *h_ascii, const int64_t *h_offsets,
                      const int32_t *n_rows, const int32_t *n_cols, int32_t n_loci, int32_t max_nesting,
                      int32_t min_match_length, mprg_batch **out_batch, mprg_result **out_res);
+/* A result that only holds the given PRG strings (no trees): lets the writers below serve PRGs that
+ * did not come out of mprg_build, e.g. PrgBuilder.build_prg() of a host-side tree (prg_builder.py:100-105) */
+int mprg_result_from_prgs(const char *const *prgs, const int64_t *lengths, int32_t n, mprg_result **out);
 void mprg_result_free(mprg_result *res);
 int32_t mprg_result_n_loci(const mprg_result *res);
 int32_t mprg_result_status(const mprg_result *res, int32_t locus);
@@ -206,6 +209,57 @@ int mprg_result_nodes(const mprg_result *res, int32_t locus, int32_t *kind, int3
                       int64_t *row_off, int32_t *n_children);
 int64_t mprg_result_row_pool_size(const mprg_result *res, int32_t locus);
 int mprg_result_row_pool(const mprg_result *res, int32_t locus, int32_t *h_rows);
+
+/* ---- host-side I/O either side of the path (plain host threads) ---------
+ * Loader: load_alignment_file (io_utils.py:17-49) for FASTA / FASTA.gz files.  Every file becomes one
+ * locus of an mprg_msa_set: upper-cased row-major ASCII rows in ONE host buffer (pinned when pin != 0
+ * and a device is present) laid out exactly as mprg_build_ascii / mprg_batch_upload take it.  Record
+ * ids are the first whitespace token of each title (Biopython).  N replacement (io_utils.py:35-47,
+ * seq_utils.py:246-290; Python's random.Random) stays with the caller: loci holding N carry
+ * MPRG_LOAD_FLAG_HAS_N and their rows can be rewritten in place through the h_ascii pointer. */
+#define MPRG_LOAD_OK 0
+#define MPRG_LOAD_NO_RECORDS 1 /* ValueError("No records found in handle") => EmptyMSAError */
+#define MPRG_LOAD_RAGGED 2     /* ValueError("Sequences must all be the same length") */
+#define MPRG_LOAD_IO_ERROR 3   /* cannot open / read / inflate: the caller re-raises through Python's open */
+#define MPRG_LOAD_NOT_ASCII 4  /* bytes >= 0x80: left to the caller's text decoder */
+#define MPRG_LOAD_FLAG_HAS_N 1
+typedef struct mprg_msa_set mprg_msa_set;
+int mprg_fasta_load(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t pin,
+                    mprg_msa_set **out);
+void mprg_fasta_free(mprg_msa_set *set);
+/* Borrowed views, valid until mprg_fasta_free; any out pointer may be NULL.  Locus i occupies
+ * n_rows[i] * n_cols[i] bytes at h_ascii + h_offsets[i] (0 bytes unless status[i] == MPRG_LOAD_OK). */
+int mprg_fasta_info(const mprg_msa_set *set, int32_t *n_loci, uint8_t **h_ascii, int64_t *ascii_bytes,
+                    const int64_t **h_offsets, const int32_t **n_rows, const int32_t **n_cols,
+                    const int32_t **status, const int32_t **flags);
+/* the title lines of a locus (text after '>'), joined by '\n', not NUL-terminated */
+const char *mprg_fasta_titles(const mprg_msa_set *set, int32_t locus, int64_t *length);
+
+/* Writers.  mprg_encode_prg: PrgEncoder.encode (prg_encoder.py:44-91), the uint32 values that
+ * PrgEncoder.write stores little-endian.  mprg_prg_to_gfa: GFA_Output.write_gfa's text (gfa.py:39-109,
+ * header included).  Both return *n = elements / bytes needed and fill `out` only when capacity >= *n;
+ * > 0 return codes are the reference's exceptions. */
+#define MPRG_ENC_INVALID_UNIT 1         /* EncodeError / "Invalid prg sequence" */
+#define MPRG_ENC_ODD_MARKER_REPEATED 2  /* ValueError: odd site marker found > 2 times */
+#define MPRG_ENC_OVERFLOW 3             /* marker does not fit 4 bytes (OverflowError in to_bytes) */
+int mprg_encode_prg(const char *prg, int64_t length, uint32_t *out, int64_t capacity, int64_t *n);
+int mprg_prg_to_gfa(const char *prg, int64_t length, char *out, int64_t capacity, int64_t *n);
+/* Final files of a run as InputOutputFiles.create_final_files lays them out
+ * (input_output_files.py:70-135): <prefix>.prg.fa (records sorted by "<name>.prg.fa"), and for ONE
+ * locus <prefix>.prg.bin / <prefix>.prg.gfa, for several <prefix>.prg.bin.zip / <prefix>.prg.gfa.zip
+ * (stored archives of <name>.bin / <name>.gfa in the order added).  mprg_writer_add encodes loci
+ * h_loci[0..n) of a result on n_threads host threads and appends them; results can be freed afterwards. */
+#define MPRG_WRITE_PRG 1
+#define MPRG_WRITE_BIN 2
+#define MPRG_WRITE_GFA 4
+typedef struct mprg_writer mprg_writer;
+int mprg_writer_open(const char *output_prefix, int32_t what, mprg_writer **out);
+int mprg_writer_add(mprg_writer *w, const mprg_result *res, const int32_t *h_loci, const char *const *names,
+                    int32_t n, int32_t n_threads);
+/* finishes the files and frees the writer on success; on failure read mprg_writer_error, then abort */
+int mprg_writer_close(mprg_writer *w, int64_t *n_loci, int64_t *bytes_written);
+void mprg_writer_abort(mprg_writer *w);
+const char *mprg_writer_error(const mprg_writer *w);
 
 #ifdef __cplusplus
 }

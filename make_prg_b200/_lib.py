@@ -81,6 +81,19 @@ SIGNATURES = {
     "mprg_result_nodes": (C.c_int, [P, I32, P, P, P, P, P, P, P, P]),
     "mprg_result_row_pool_size": (I64, [P, I32]),
     "mprg_result_row_pool": (C.c_int, [P, I32, P]),
+    "mprg_result_from_prgs": (C.c_int, [P, P, I32, C.POINTER(P)]),
+    "mprg_fasta_load": (C.c_int, [P, I32, I32, I32, C.POINTER(P)]),
+    "mprg_fasta_free": (None, [P]),
+    "mprg_fasta_info": (C.c_int, [P, C.POINTER(I32), C.POINTER(P), C.POINTER(I64), C.POINTER(P), C.POINTER(P),
+                                  C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
+    "mprg_fasta_titles": (P, [P, I32, C.POINTER(I64)]),
+    "mprg_encode_prg": (C.c_int, [P, I64, P, I64, C.POINTER(I64)]),
+    "mprg_prg_to_gfa": (C.c_int, [P, I64, P, I64, C.POINTER(I64)]),
+    "mprg_writer_open": (C.c_int, [C.c_char_p, I32, C.POINTER(P)]),
+    "mprg_writer_add": (C.c_int, [P, P, P, P, I32, I32]),
+    "mprg_writer_close": (C.c_int, [P, C.POINTER(I64), C.POINTER(I64)]),
+    "mprg_writer_abort": (None, [P]),
+    "mprg_writer_error": (C.c_char_p, [P]),
 }
 
 

@@ -19,7 +19,8 @@ EXTRA_OBJECTS = [("kmeans.cu", "kmeans_group", ["-fmad=false", "-DMPRG_KM_GROUP"
 
 
 def sources():
-    return sorted(CSRC.glob("*.cu"))
+    # *.cu: kernels + engine; *.cpp: host-only code (loader / writers), compiled by nvcc's host compiler
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))
 
 
 def compile_units():
@@ -32,7 +33,7 @@ def needs_build():
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "mprg.h"]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "mprg.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -60,7 +61,7 @@ def build_library(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("libmprg build failed")
-    cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *objs]
+    cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *objs, "-lz"]
     subprocess.run(cmd, check=True)
     return LIB
 

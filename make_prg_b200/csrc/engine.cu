@@ -1363,6 +1363,15 @@ extern "C" int mprg_build_ascii(mprg_ctx *ctx, const uint8_t *h_ascii, const int
     return MPRG_OK;
 }
 
+extern "C" int mprg_result_from_prgs(const char *const *prgs, const int64_t *lengths, int32_t n, mprg_result **out) {
+    if (!out || n < 0 || (n > 0 && (!prgs || !lengths))) return MPRG_E_BAD_ARG;
+    mprg_result *res = new mprg_result();
+    res->loci.resize(n);
+    for (int i = 0; i < n; ++i) res->loci[i].prg.assign(prgs[i] ? prgs[i] : "", (size_t)std::max<int64_t>(lengths[i], 0));
+    *out = res;
+    return MPRG_OK;
+}
+
 extern "C" void mprg_result_free(mprg_result *res) { delete res; }
 extern "C" int32_t mprg_result_n_loci(const mprg_result *res) { return res ? (int32_t)res->loci.size() : 0; }
 extern "C" int32_t mprg_result_status(const mprg_result *res, int32_t l) {

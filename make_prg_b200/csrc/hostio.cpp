@@ -1,0 +1,931 @@
+// Host-side I/O either side of the hot path, plain C++ on host threads:
+//
+//   loader   load_alignment_file                 make_prg/utils/io_utils.py:17-49
+//            (FASTA / FASTA.gz -> upper-cased row-major ASCII matrices, ready for mprg_build_ascii)
+//   writers  PrgEncoder.encode / write           make_prg/utils/prg_encoder.py:44-91
+//            GFA_Output.build_gfa_string         make_prg/utils/gfa.py:39-109
+//            InputOutputFiles.create_final_files make_prg/utils/input_output_files.py:70-135
+//            (.prg.fa sorted by file name, .prg.bin / .prg.gfa for one locus, stored .zip archives
+//            of <locus>.bin / <locus>.gfa for several -- zipfile.ZipFile's default ZIP_STORED)
+//
+// Nothing here touches the GPU except the optional pinned allocation of the loader's output buffer.
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <string.h>
+#include <stdlib.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <immintrin.h>
+
+#include <algorithm>
+#include <memory>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/mprg.h"
+
+namespace {
+
+template <typename F>
+void parallel_for_t(int n, int n_threads, F fn) {  // fn(item, thread index)
+    n_threads = std::max(1, std::min(n_threads, n));
+    if (n_threads == 1) {
+        for (int i = 0; i < n; ++i) fn(i, 0);
+        return;
+    }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([&, t]() {
+            for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i, t);
+        });
+    for (auto &t : th) t.join();
+}
+
+template <typename F>
+void parallel_for(int n, int n_threads, F fn) {
+    n_threads = std::max(1, std::min(n_threads, n));
+    if (n_threads == 1) {
+        for (int i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([&]() {
+            for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+        });
+    for (auto &t : th) t.join();
+}
+
+// ------------------------------------------------------------------------------------------------
+// loader
+// ------------------------------------------------------------------------------------------------
+// Big host buffers come in 2 MB-aligned blocks advised as transparent huge pages: first-touch page
+// faults are what a loader of fresh memory otherwise spends most of its time in.
+uint8_t *huge_alloc(size_t bytes) {
+    const size_t two_mb = (size_t)2 << 20;
+    bytes = (bytes + two_mb - 1) & ~(two_mb - 1);
+    void *p = aligned_alloc(two_mb, bytes);
+    if (p) madvise(p, bytes, MADV_HUGEPAGE);
+    return (uint8_t *)p;
+}
+
+// bump allocator of one parsing thread; the blocks live until the matrices have been copied out
+struct Slab {
+    static constexpr size_t BLOCK = (size_t)32 << 20;
+    std::vector<uint8_t *> blocks;
+    size_t used = BLOCK;
+    uint8_t *take(size_t bytes) {
+        if (bytes > BLOCK / 4) {  // a big locus gets its own block
+            uint8_t *p = huge_alloc(bytes);
+            if (p) blocks.insert(blocks.begin(), p);
+            return p;
+        }
+        if (used + bytes > BLOCK) {
+            uint8_t *p = huge_alloc(BLOCK);
+            if (!p) return nullptr;
+            blocks.push_back(p);
+            used = 0;
+        }
+        uint8_t *p = blocks.back() + used;
+        used += (bytes + 63) & ~(size_t)63;
+        return p;
+    }
+    void give_back(uint8_t *p, size_t taken, size_t kept) {  // shrink the newest allocation
+        if (!blocks.empty() && p >= blocks.back() && p + ((taken + 63) & ~(size_t)63) == blocks.back() + used)
+            used = (size_t)(p - blocks.back()) + ((kept + 63) & ~(size_t)63);
+    }
+    ~Slab() {
+        for (uint8_t *b : blocks) free(b);
+    }
+};
+
+struct ParsedFile {
+    uint8_t *buf = nullptr;  // the matrix, row-major (in the parsing thread's slab)
+    std::string titles;        // header lines without '>', joined by '\n'
+    int64_t matrix_bytes = 0;
+    int32_t n_rows = 0, n_cols = 0, status = MPRG_LOAD_OK, flags = 0;
+};
+
+bool ends_with(const char *s, const char *suffix) {
+    const size_t n = strlen(s), m = strlen(suffix);
+    return n >= m && memcmp(s + n - m, suffix, m) == 0;
+}
+
+bool read_plain(const char *path, std::vector<uint8_t> &out) {
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+        close(fd);
+        return false;
+    }
+    out.resize((size_t)st.st_size);
+    size_t got = 0;
+    while (got < out.size()) {
+        const ssize_t r = read(fd, out.data() + got, out.size() - got);
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            close(fd);
+            return false;
+        }
+        if (r == 0) break;
+        got += (size_t)r;
+    }
+    close(fd);
+    out.resize(got);
+    return true;
+}
+
+bool read_gzip(const char *path, std::vector<uint8_t> &out) {
+    gzFile f = gzopen(path, "rb");
+    if (!f) return false;
+    gzbuffer(f, 1 << 20);
+    out.clear();
+    size_t cap = 1 << 22;
+    out.resize(cap);
+    size_t got = 0;
+    while (true) {
+        if (got == cap) {
+            cap *= 2;
+            out.resize(cap);
+        }
+        const int r = gzread(f, out.data() + got, (unsigned)std::min<size_t>(cap - got, 1u << 30));
+        if (r < 0) {
+            gzclose(f);
+            return false;
+        }
+        if (r == 0) break;
+        got += (size_t)r;
+    }
+    gzclose(f);
+    out.resize(got);
+    return true;
+}
+
+// One text line as Python's universal-newline reader cuts it: '\n', '\r\n' and a lone '\r' all end it.
+inline void next_line(const uint8_t *s, const uint8_t *end, const uint8_t *&line_end, const uint8_t *&next) {
+    const uint8_t *p = (const uint8_t *)memchr(s, '\n', (size_t)(end - s));
+    const uint8_t *lim = p ? p : end;
+    const uint8_t *q = (const uint8_t *)memchr(s, '\r', (size_t)(lim - s));
+    if (q) {
+        line_end = q;
+        next = q + 1;
+        if (next < end && *next == '\n') ++next;
+    } else {
+        line_end = lim;
+        next = p ? p + 1 : end;
+    }
+}
+
+// The sequence lines of one record: copies [s, ...) to w up to (not including) the next title line
+// (a '>' first in its line) or `end`, dropping line ends and blanks and upper-casing a-z.
+// bits |= 1 when a byte >= 0x80 was copied, |= 2 when an 'N' was.  Returns the read position.
+const uint8_t *copy_record_scalar(const uint8_t *s, const uint8_t *end, uint8_t *&w, int &bits) {
+    unsigned hi = 0, n_count = 0;
+    while (s < end) {
+        uint8_t c = *s++;
+        if (c == '\n' || c == '\r') {
+            if (c == '\r' && s < end && *s == '\n') ++s;
+            if (s < end && *s == '>') break;
+            continue;
+        }
+        if (c == ' ') continue;
+        c = (uint8_t)(c - (((uint8_t)(c - 'a') < 26) << 5));
+        hi |= c;
+        n_count += (c == 'N');
+        *w++ = c;
+    }
+    bits |= ((hi & 0x80u) ? 1 : 0) | (n_count ? 2 : 0);
+    return s;
+}
+
+alignas(32) const uint8_t LANE_MASK[64] = {
+    255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255,
+    255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255};
+
+// The same, 32 bytes per step (the output buffer has 32 bytes of slack: whole vectors are stored and
+// the write position advances by the bytes that count).
+__attribute__((target("avx2"))) const uint8_t *copy_record_avx2(const uint8_t *s, const uint8_t *end, uint8_t *&w,
+                                                                  int &bits) {
+    const __m256i v_nl = _mm256_set1_epi8('\n'), v_cr = _mm256_set1_epi8('\r'), v_sp = _mm256_set1_epi8(' ');
+    const __m256i v_lo = _mm256_set1_epi8('a' - 1), v_hi = _mm256_set1_epi8('z' + 1);
+    const __m256i v_case = _mm256_set1_epi8(0x20), v_n = _mm256_set1_epi8('N');
+    __m256i acc_hi = _mm256_setzero_si256(), acc_n = _mm256_setzero_si256();
+    while (s + 32 <= end) {
+        const __m256i v = _mm256_loadu_si256((const __m256i *)s);
+        const __m256i special = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, v_nl), _mm256_cmpeq_epi8(v, v_cr)),
+                                                _mm256_cmpeq_epi8(v, v_sp));
+        const __m256i lower = _mm256_and_si256(_mm256_cmpgt_epi8(v, v_lo), _mm256_cmpgt_epi8(v_hi, v));
+        const __m256i up = _mm256_xor_si256(v, _mm256_and_si256(lower, v_case));
+        const uint32_t m = (uint32_t)_mm256_movemask_epi8(special);
+        _mm256_storeu_si256((__m256i *)w, up);
+        if (m == 0) {
+            acc_hi = _mm256_or_si256(acc_hi, v);
+            acc_n = _mm256_or_si256(acc_n, _mm256_cmpeq_epi8(up, v_n));
+            w += 32;
+            s += 32;
+            continue;
+        }
+        const int k = __builtin_ctz(m);
+        const __m256i lanes = _mm256_loadu_si256((const __m256i *)(LANE_MASK + 32 - k));
+        acc_hi = _mm256_or_si256(acc_hi, _mm256_and_si256(v, lanes));
+        acc_n = _mm256_or_si256(acc_n, _mm256_and_si256(_mm256_cmpeq_epi8(up, v_n), lanes));
+        w += k;
+        const uint8_t c = s[k];
+        s += k + 1;
+        if (c == ' ') continue;
+        if (c == '\r' && s < end && *s == '\n') ++s;
+        if (s < end && *s == '>') {
+            bits |= (_mm256_movemask_epi8(acc_hi) ? 1 : 0) | (_mm256_movemask_epi8(acc_n) ? 2 : 0);
+            return s;
+        }
+    }
+    bits |= (_mm256_movemask_epi8(acc_hi) ? 1 : 0) | (_mm256_movemask_epi8(acc_n) ? 2 : 0);
+    return copy_record_scalar(s, end, w, bits);
+}
+
+// Mirrors make_prg_b200.utils.io_utils.parse_fasta + the upper-casing of load_alignment_file.
+void parse_file(const char *path, ParsedFile &pf, bool avx2, Slab &slab) {
+    static thread_local std::vector<uint8_t> raw;  // reused by the files of one thread: no fresh pages
+    const bool ok = ends_with(path, ".gz") ? read_gzip(path, raw) : read_plain(path, raw);
+    if (!ok) {
+        pf.status = MPRG_LOAD_IO_ERROR;
+        return;
+    }
+    pf.buf = slab.take(raw.size() + 32);
+    if (!pf.buf) {
+        pf.status = MPRG_LOAD_IO_ERROR;
+        return;
+    }
+    const uint8_t *s = raw.data(), *end = s + raw.size();
+    uint8_t *w = pf.buf;
+    bool ragged = false;
+    int bits = 0;
+    int64_t first_len = -1;
+    // text before the first title line is skipped
+    while (s < end && *s != '>') {
+        const uint8_t *le, *nx;
+        next_line(s, end, le, nx);
+        s = nx;
+    }
+    while (s < end) {  // *s == '>' : one record per trip
+        const uint8_t *le, *nx;
+        next_line(s, end, le, nx);
+        if (pf.n_rows > 0) pf.titles.push_back('\n');
+        pf.titles.append((const char *)s + 1, (size_t)(le - s - 1));
+        s = nx;
+        uint8_t *row_start = w;
+        if (s < end && *s != '>') s = avx2 ? copy_record_avx2(s, end, w, bits) : copy_record_scalar(s, end, w, bits);
+        const int64_t len = w - row_start;
+        if (first_len < 0)
+            first_len = len;
+        else if (len != first_len)
+            ragged = true;
+        pf.n_rows++;
+    }
+    slab.give_back(pf.buf, raw.size() + 32, (size_t)(w - pf.buf) + 32);
+    if (pf.n_rows == 0) {
+        pf.status = MPRG_LOAD_NO_RECORDS;
+        return;
+    }
+    for (char c : pf.titles)
+        if ((unsigned char)c >= 0x80) bits |= 1;
+    if (bits & 1) {
+        pf.status = MPRG_LOAD_NOT_ASCII;
+        return;
+    }
+    if (ragged) {
+        pf.status = MPRG_LOAD_RAGGED;
+        return;
+    }
+    pf.n_cols = (int32_t)first_len;
+    pf.matrix_bytes = (int64_t)pf.n_rows * first_len;
+    if (first_len > INT32_MAX) pf.status = MPRG_LOAD_IO_ERROR;
+    if (bits & 2) pf.flags |= MPRG_LOAD_FLAG_HAS_N;
+}
+
+}  // namespace
+
+struct mprg_msa_set {
+    int32_t n = 0;
+    uint8_t *ascii = nullptr;
+    int64_t ascii_bytes = 0;
+    bool pinned = false;
+    std::vector<int64_t> offsets;
+    std::vector<int32_t> n_rows, n_cols, status, flags;
+    std::vector<std::string> titles;
+};
+
+extern "C" int mprg_fasta_load(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t pin,
+                               mprg_msa_set **out) {
+    if (!out || n_files < 0 || (n_files > 0 && !paths)) return MPRG_E_BAD_ARG;
+    *out = nullptr;
+    std::vector<ParsedFile> files((size_t)n_files);
+    const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("MPRG_NO_AVX2");
+    n_threads = std::max(1, std::min(n_threads, std::max(n_files, 1)));
+    std::vector<Slab> slabs((size_t)n_threads);
+    parallel_for_t(n_files, n_threads, [&](int i, int t) { parse_file(paths[i], files[(size_t)i], avx2, slabs[(size_t)t]); });
+    mprg_msa_set *set = new mprg_msa_set();
+    set->n = n_files;
+    set->offsets.resize((size_t)n_files);
+    set->n_rows.resize((size_t)n_files);
+    set->n_cols.resize((size_t)n_files);
+    set->status.resize((size_t)n_files);
+    set->flags.resize((size_t)n_files);
+    set->titles.resize((size_t)n_files);
+    int64_t total = 0;
+    for (int i = 0; i < n_files; ++i) {
+        ParsedFile &pf = files[(size_t)i];
+        const bool good = pf.status == MPRG_LOAD_OK;
+        set->offsets[(size_t)i] = total;
+        set->n_rows[(size_t)i] = good ? pf.n_rows : 0;
+        set->n_cols[(size_t)i] = good ? pf.n_cols : 0;
+        set->status[(size_t)i] = pf.status;
+        set->flags[(size_t)i] = pf.flags;
+        set->titles[(size_t)i].swap(pf.titles);
+        if (good) total += pf.matrix_bytes;
+    }
+    set->ascii_bytes = total;
+    const size_t alloc = (size_t)std::max<int64_t>(total, 1);
+    if (pin && cudaHostAlloc((void **)&set->ascii, alloc, cudaHostAllocDefault) == cudaSuccess) {
+        set->pinned = true;
+    } else {
+        if (pin) cudaGetLastError();  // without a device the buffer is ordinary memory
+        set->ascii = huge_alloc(alloc);
+        if (!set->ascii) {
+            delete set;
+            return MPRG_E_INTERNAL;
+        }
+    }
+    parallel_for(n_files, n_threads, [&](int i) {
+        ParsedFile &pf = files[(size_t)i];
+        if (pf.status == MPRG_LOAD_OK && pf.matrix_bytes)
+            memcpy(set->ascii + set->offsets[(size_t)i], pf.buf, (size_t)pf.matrix_bytes);
+    });
+    *out = set;
+    return MPRG_OK;
+}
+
+extern "C" void mprg_fasta_free(mprg_msa_set *set) {
+    if (!set) return;
+    if (set->ascii) {
+        if (set->pinned)
+            cudaFreeHost(set->ascii);
+        else
+            free(set->ascii);
+    }
+    delete set;
+}
+
+extern "C" int mprg_fasta_info(const mprg_msa_set *set, int32_t *n_loci, uint8_t **h_ascii, int64_t *ascii_bytes,
+                               const int64_t **h_offsets, const int32_t **n_rows, const int32_t **n_cols,
+                               const int32_t **status, const int32_t **flags) {
+    if (!set) return MPRG_E_BAD_ARG;
+    if (n_loci) *n_loci = set->n;
+    if (h_ascii) *h_ascii = set->ascii;
+    if (ascii_bytes) *ascii_bytes = set->ascii_bytes;
+    if (h_offsets) *h_offsets = set->offsets.data();
+    if (n_rows) *n_rows = set->n_rows.data();
+    if (n_cols) *n_cols = set->n_cols.data();
+    if (status) *status = set->status.data();
+    if (flags) *flags = set->flags.data();
+    return MPRG_OK;
+}
+
+extern "C" const char *mprg_fasta_titles(const mprg_msa_set *set, int32_t locus, int64_t *length) {
+    if (!set || locus < 0 || locus >= set->n) return nullptr;
+    if (length) *length = (int64_t)set->titles[(size_t)locus].size();
+    return set->titles[(size_t)locus].data();
+}
+
+// ------------------------------------------------------------------------------------------------
+// writers
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+inline bool is_py_space(unsigned char c) {  // str.split() separators within ASCII
+    return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f);
+}
+
+inline int base_code(unsigned char c) {
+    switch (c) {
+        case 'A': case 'a': return 1;
+        case 'C': case 'c': return 2;
+        case 'G': case 'g': return 3;
+        case 'T': case 't': return 4;
+        default: return 0;
+    }
+}
+
+// prg_encoder.py:44-91.  Returns 0, or MPRG_ENC_* on the reference's exceptions.
+int encode_prg(const char *prg, int64_t len, std::vector<uint32_t> &out) {
+    out.clear();
+    out.reserve((size_t)len);
+    std::unordered_map<uint64_t, int> seen;  // odd marker -> times seen
+    int64_t i = 0;
+    while (i < len) {
+        while (i < len && is_py_space((unsigned char)prg[i])) ++i;
+        if (i >= len) break;
+        const int64_t u0 = i;
+        bool all_bases = true, all_digits = true;
+        while (i < len && !is_py_space((unsigned char)prg[i])) {
+            const unsigned char c = (unsigned char)prg[i];
+            all_bases &= base_code(c) != 0;
+            all_digits &= (c >= '0' && c <= '9');
+            ++i;
+        }
+        if (all_bases) {
+            for (int64_t j = u0; j < i; ++j) out.push_back((uint32_t)base_code((unsigned char)prg[j]));
+        } else if (all_digits) {
+            uint64_t m = 0;
+            for (int64_t j = u0; j < i; ++j) {
+                m = m * 10 + (uint64_t)(prg[j] - '0');
+                if (m > 0xFFFFFFFFull) return MPRG_ENC_OVERFLOW;
+            }
+            if ((m & 1) == 0) {
+                out.push_back((uint32_t)m);
+            } else {
+                const int times = ++seen[m];
+                if (times > 2) return MPRG_ENC_ODD_MARKER_REPEATED;
+                if (times == 2 && m + 1 > 0xFFFFFFFFull) return MPRG_ENC_OVERFLOW;
+                out.push_back((uint32_t)(times == 1 ? m : m + 1));
+            }
+        } else {
+            return MPRG_ENC_INVALID_UNIT;
+        }
+    }
+    return 0;
+}
+
+inline void put_uint(std::string &s, uint64_t v) {
+    char tmp[24];
+    int n = 0;
+    do {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) s.push_back(tmp[--n]);
+}
+
+// gfa.py:39-109 as one recursive descent over the token stream (markers are " <digits> ", anything
+// else between spaces is sequence); segment / link ids come out in the reference's order.
+struct GfaBuilder {
+    const char *p;
+    int64_t len, i = 0;
+    std::string out;
+    uint64_t gfa_id = 0;
+    bool bad = false;
+
+    enum Tok { END, LITERAL, MARKER };
+    Tok tok = END;
+    int64_t lit0 = 0, lit1 = 0;
+    uint64_t marker = 0;
+
+    void advance() {
+        while (i < len) {
+            if (p[i] == ' ') {
+                int64_t j = i + 1;
+                uint64_t m = 0;
+                while (j < len && p[j] >= '0' && p[j] <= '9') {
+                    m = m * 10 + (uint64_t)(p[j] - '0');
+                    ++j;
+                }
+                if (j > i + 1 && j < len && p[j] == ' ') {
+                    tok = MARKER;
+                    marker = m;
+                    i = j + 1;
+                    return;
+                }
+                ++i;  // a space that is not part of a marker is skipped
+                continue;
+            }
+            lit0 = i;
+            while (i < len && p[i] != ' ') ++i;
+            lit1 = i;
+            tok = LITERAL;
+            return;
+        }
+        tok = END;
+    }
+    void segment(int64_t a, int64_t b, const std::string *extra) {
+        out += "S\t";
+        put_uint(out, gfa_id);
+        out.push_back('\t');
+        if (extra && !extra->empty())
+            out += *extra;
+        else if (b > a)
+            out.append(p + a, (size_t)(b - a));
+        else
+            out.push_back('*');
+        out += "\tRC:i:0\n";
+    }
+    void link(uint64_t a, uint64_t b) {
+        out += "L\t";
+        put_uint(out, a);
+        out += "\t+\t";
+        put_uint(out, b);
+        out += "\t+\t0M\n";
+    }
+    // One (sub)string of the PRG: literal? (site literal?)*.  open_marker = odd marker of the enclosing
+    // site (0 at top level).  Returns the id of the segment that ends it; on return `tok` is the token
+    // that ended the sequence (END, the closing odd marker, or the even separator).
+    uint64_t sequence(uint64_t open_marker, int depth) {
+        std::vector<uint64_t> end_ids;
+        int64_t a = 0, b = 0;     // pending literal as one slice of the input ...
+        std::string joined;       // ... or, when several literal tokens follow each other, their join
+        auto flush_segment = [&]() { segment(a, b, &joined); };
+        while (!bad) {
+            if (tok == LITERAL) {
+                if (b > a || !joined.empty()) {
+                    if (joined.empty()) joined.assign(p + a, (size_t)(b - a));
+                    joined.append(p + lit0, (size_t)(lit1 - lit0));
+                } else {
+                    a = lit0;
+                    b = lit1;
+                }
+                advance();
+                continue;
+            }
+            if (tok == MARKER && (marker & 1) && marker != open_marker) {
+                if (depth > 512) {
+                    bad = true;
+                    break;
+                }
+                const uint64_t site = marker;
+                flush_segment();
+                const uint64_t pre = gfa_id++;
+                for (uint64_t e : end_ids) link(e, pre);
+                end_ids.clear();
+                int alleles = 0;
+                advance();
+                while (!bad) {
+                    link(pre, gfa_id);
+                    end_ids.push_back(sequence(site, depth + 1));
+                    ++alleles;
+                    if (tok == MARKER && marker == site + 1) {  // next allele
+                        advance();
+                        continue;
+                    }
+                    if (tok == MARKER && marker == site) {  // site closed
+                        advance();
+                        break;
+                    }
+                    bad = true;  // unterminated site or a foreign even marker
+                }
+                if (alleles < 2) bad = true;
+                a = b = 0;
+                joined.clear();
+                continue;
+            }
+            if (tok == MARKER && !(marker & 1) && marker != open_marker + 1) bad = true;
+            if (tok == MARKER && open_marker == 0) bad = true;
+            break;  // END, my closing marker or my separator
+        }
+        flush_segment();
+        for (uint64_t e : end_ids) link(e, gfa_id);
+        return gfa_id++;
+    }
+};
+
+const char GFA_HEADER[] = "H\tVN:Z:1.0\tbn:Z:--linear --singlearr\n";
+
+int prg_to_gfa(const char *prg, int64_t len, std::string &out) {
+    GfaBuilder g;
+    g.p = prg;
+    g.len = len;
+    g.out.reserve((size_t)len * 3 + 64);
+    g.out = GFA_HEADER;
+    g.advance();
+    g.sequence(0, 0);
+    if (g.bad || g.tok != GfaBuilder::END) return MPRG_ENC_INVALID_UNIT;
+    out.swap(g.out);
+    return 0;
+}
+
+// ---- stored zip archive (what zipfile.ZipFile(path, "w") produces: ZIP_STORED) -------------------
+struct ZipEntry {
+    std::string name;
+    uint32_t crc, size;
+    uint64_t offset;
+};
+
+struct ZipFile {
+    FILE *f = nullptr;
+    uint64_t pos = 0;
+    std::vector<ZipEntry> entries;
+    uint16_t dos_time = 0, dos_date = 0;
+
+    static void le16(std::string &s, uint16_t v) {
+        s.push_back((char)(v & 0xff));
+        s.push_back((char)(v >> 8));
+    }
+    static void le32(std::string &s, uint32_t v) {
+        for (int k = 0; k < 4; ++k) s.push_back((char)((v >> (8 * k)) & 0xff));
+    }
+    static void le64(std::string &s, uint64_t v) {
+        for (int k = 0; k < 8; ++k) s.push_back((char)((v >> (8 * k)) & 0xff));
+    }
+    bool open_path(const std::string &path) {
+        f = fopen(path.c_str(), "wb");
+        if (!f) return false;
+        setvbuf(f, nullptr, _IOFBF, 1 << 20);
+        time_t now = time(nullptr);
+        struct tm tmv;
+        localtime_r(&now, &tmv);
+        const int year = std::max(tmv.tm_year + 1900, 1980);
+        dos_date = (uint16_t)(((year - 1980) << 9) | ((tmv.tm_mon + 1) << 5) | tmv.tm_mday);
+        dos_time = (uint16_t)((tmv.tm_hour << 11) | (tmv.tm_min << 5) | (tmv.tm_sec / 2));
+        return true;
+    }
+    bool put(const std::string &s) {
+        if (fwrite(s.data(), 1, s.size(), f) != s.size()) return false;
+        pos += s.size();
+        return true;
+    }
+    bool add(const std::string &name, const void *data, size_t n, uint32_t crc) {
+        if (n > 0xFFFFFFFEull || name.size() > 0xFFFF) return false;
+        std::string h;
+        le32(h, 0x04034b50u);
+        le16(h, 20);
+        le16(h, 0x0800);  // names are UTF-8
+        le16(h, 0);       // stored
+        le16(h, dos_time);
+        le16(h, dos_date);
+        le32(h, crc);
+        le32(h, (uint32_t)n);
+        le32(h, (uint32_t)n);
+        le16(h, (uint16_t)name.size());
+        le16(h, 0);
+        h += name;
+        entries.push_back({name, crc, (uint32_t)n, pos});
+        if (!put(h)) return false;
+        if (n && fwrite(data, 1, n, f) != n) return false;
+        pos += n;
+        return true;
+    }
+    bool finish() {
+        const uint64_t cd_offset = pos;
+        std::string cd;
+        for (const ZipEntry &e : entries) {
+            const bool big = e.offset >= 0xFFFFFFFFull;
+            le32(cd, 0x02014b50u);
+            le16(cd, (uint16_t)((3 << 8) | (big ? 45 : 20)));
+            le16(cd, big ? 45 : 20);
+            le16(cd, 0x0800);
+            le16(cd, 0);
+            le16(cd, dos_time);
+            le16(cd, dos_date);
+            le32(cd, e.crc);
+            le32(cd, e.size);
+            le32(cd, e.size);
+            le16(cd, (uint16_t)e.name.size());
+            le16(cd, big ? 12 : 0);
+            le16(cd, 0);
+            le16(cd, 0);
+            le16(cd, 0);
+            le32(cd, 0600u << 16);
+            le32(cd, big ? 0xFFFFFFFFu : (uint32_t)e.offset);
+            cd += e.name;
+            if (big) {
+                le16(cd, 1);
+                le16(cd, 8);
+                le64(cd, e.offset);
+            }
+        }
+        const uint64_t cd_size = cd.size(), n = entries.size();
+        if (n > 0xFFFE || cd_offset >= 0xFFFFFFFFull || cd_size >= 0xFFFFFFFFull) {
+            le32(cd, 0x06064b50u);  // zip64 end of central directory
+            le64(cd, 44);
+            le16(cd, 45);
+            le16(cd, 45);
+            le32(cd, 0);
+            le32(cd, 0);
+            le64(cd, n);
+            le64(cd, n);
+            le64(cd, cd_size);
+            le64(cd, cd_offset);
+            le32(cd, 0x07064b50u);  // locator
+            le32(cd, 0);
+            le64(cd, cd_offset + cd_size);
+            le32(cd, 1);
+        }
+        le32(cd, 0x06054b50u);
+        le16(cd, 0);
+        le16(cd, 0);
+        le16(cd, (uint16_t)std::min<uint64_t>(n, 0xFFFF));
+        le16(cd, (uint16_t)std::min<uint64_t>(n, 0xFFFF));
+        le32(cd, (uint32_t)std::min<uint64_t>(cd_size, 0xFFFFFFFFull));
+        le32(cd, (uint32_t)std::min<uint64_t>(cd_offset, 0xFFFFFFFFull));
+        le16(cd, 0);
+        bool ok = put(cd);
+        ok = (fclose(f) == 0) && ok;
+        f = nullptr;
+        return ok;
+    }
+};
+
+bool write_whole(const std::string &path, const void *data, size_t n) {
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    bool ok = n == 0 || fwrite(data, 1, n, f) == n;
+    ok = (fclose(f) == 0) && ok;
+    return ok;
+}
+
+struct Encoded {
+    std::string name;
+    std::vector<uint32_t> bin;
+    std::string gfa;
+    uint32_t crc_bin = 0, crc_gfa = 0;
+    int rc = 0;
+};
+
+}  // namespace
+
+struct mprg_writer {
+    std::string prefix, err;
+    int what = 0;
+    std::vector<std::pair<std::string, std::string>> fa;  // (name, prg) for the sorted .prg.fa
+    Encoded first;  // kept back until a second locus shows up: one locus => plain files, no archive
+    int64_t n_added = 0, bytes = 0;
+    ZipFile zbin, zgfa;
+    bool zips_open = false;
+};
+
+extern "C" int mprg_encode_prg(const char *prg, int64_t length, uint32_t *out, int64_t capacity, int64_t *n) {
+    if ((!prg && length > 0) || length < 0 || !n) return MPRG_E_BAD_ARG;
+    std::vector<uint32_t> v;
+    const int rc = encode_prg(prg, length, v);
+    if (rc) return rc;
+    *n = (int64_t)v.size();
+    if (out && capacity >= (int64_t)v.size() && !v.empty()) memcpy(out, v.data(), v.size() * sizeof(uint32_t));
+    return MPRG_OK;
+}
+
+extern "C" int mprg_prg_to_gfa(const char *prg, int64_t length, char *out, int64_t capacity, int64_t *n) {
+    if ((!prg && length > 0) || length < 0 || !n) return MPRG_E_BAD_ARG;
+    std::string s;
+    const int rc = prg_to_gfa(prg, length, s);
+    if (rc) return rc;
+    *n = (int64_t)s.size();
+    if (out && capacity >= (int64_t)s.size()) memcpy(out, s.data(), s.size());
+    return MPRG_OK;
+}
+
+extern "C" int mprg_writer_open(const char *output_prefix, int32_t what, mprg_writer **out) {
+    if (!output_prefix || !out || (what & ~7) || what == 0) return MPRG_E_BAD_ARG;
+    mprg_writer *w = new mprg_writer();
+    w->prefix = output_prefix;
+    w->what = what;
+    *out = w;
+    return MPRG_OK;
+}
+
+extern "C" const char *mprg_writer_error(const mprg_writer *w) { return w ? w->err.c_str() : ""; }
+
+static int writer_flush_entry(mprg_writer *w, const Encoded &e) {
+    if ((w->what & MPRG_WRITE_BIN) &&
+        !w->zbin.add(e.name + ".bin", e.bin.data(), e.bin.size() * sizeof(uint32_t), e.crc_bin)) {
+        w->err = "cannot write " + w->prefix + ".prg.bin.zip: " + strerror(errno);
+        return MPRG_E_INTERNAL;
+    }
+    if ((w->what & MPRG_WRITE_GFA) && !w->zgfa.add(e.name + ".gfa", e.gfa.data(), e.gfa.size(), e.crc_gfa)) {
+        w->err = "cannot write " + w->prefix + ".prg.gfa.zip: " + strerror(errno);
+        return MPRG_E_INTERNAL;
+    }
+    return MPRG_OK;
+}
+
+extern "C" int mprg_writer_add(mprg_writer *w, const mprg_result *res, const int32_t *h_loci,
+                               const char *const *names, int32_t n, int32_t n_threads) {
+    if (!w || !res || n < 0 || (n > 0 && (!h_loci || !names))) return MPRG_E_BAD_ARG;
+    std::vector<Encoded> enc((size_t)n);
+    const int what = w->what;
+    parallel_for(n, n_threads, [&](int i) {
+        Encoded &e = enc[(size_t)i];
+        e.name = names[i];
+        int64_t len = 0;
+        const char *prg = mprg_result_prg(res, h_loci[i], &len);
+        if (!prg) {
+            e.rc = MPRG_E_BAD_ARG;
+            return;
+        }
+        if (what & MPRG_WRITE_BIN) {
+            e.rc = encode_prg(prg, len, e.bin);
+            if (e.rc) return;
+            e.crc_bin = (uint32_t)crc32(0L, (const Bytef *)e.bin.data(), (uInt)(e.bin.size() * sizeof(uint32_t)));
+        }
+        if (what & MPRG_WRITE_GFA) {
+            e.rc = prg_to_gfa(prg, len, e.gfa);
+            if (e.rc) return;
+            e.crc_gfa = (uint32_t)crc32(0L, (const Bytef *)e.gfa.data(), (uInt)e.gfa.size());
+        }
+    });
+    for (int i = 0; i < n; ++i) {
+        Encoded &e = enc[(size_t)i];
+        if (e.rc) {
+            w->err = "PRG of " + e.name + " cannot be encoded";
+            return e.rc;
+        }
+        if (what & MPRG_WRITE_PRG) {
+            int64_t len = 0;
+            const char *prg = mprg_result_prg(res, h_loci[i], &len);
+            w->fa.emplace_back(e.name, std::string(prg, (size_t)len));
+        }
+        if (w->n_added == 0) {
+            w->first = std::move(e);
+        } else {
+            if (!w->zips_open) {
+                if ((what & MPRG_WRITE_BIN) && !w->zbin.open_path(w->prefix + ".prg.bin.zip")) {
+                    w->err = "cannot create " + w->prefix + ".prg.bin.zip: " + strerror(errno);
+                    return MPRG_E_INTERNAL;
+                }
+                if ((what & MPRG_WRITE_GFA) && !w->zgfa.open_path(w->prefix + ".prg.gfa.zip")) {
+                    w->err = "cannot create " + w->prefix + ".prg.gfa.zip: " + strerror(errno);
+                    return MPRG_E_INTERNAL;
+                }
+                w->zips_open = true;
+                const int rc = writer_flush_entry(w, w->first);
+                if (rc) return rc;
+                w->first = Encoded();
+            }
+            const int rc = writer_flush_entry(w, e);
+            if (rc) return rc;
+        }
+        w->n_added++;
+    }
+    return MPRG_OK;
+}
+
+extern "C" int mprg_writer_close(mprg_writer *w, int64_t *n_loci, int64_t *bytes_written) {
+    if (!w) return MPRG_E_BAD_ARG;
+    int rc = MPRG_OK;
+    int64_t bytes = 0;
+    if (w->n_added > 0) {
+        if (w->what & MPRG_WRITE_PRG) {
+            // input_output_files.py:86-92: the per-locus <name>.prg.fa files are concatenated in sorted order
+            std::vector<size_t> order(w->fa.size());
+            for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+            std::vector<std::string> keys(w->fa.size());
+            for (size_t i = 0; i < keys.size(); ++i) keys[i] = w->fa[i].first + ".prg.fa";
+            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+            std::string text;
+            for (size_t k : order) {
+                text.push_back('>');
+                text += w->fa[k].first;
+                text.push_back('\n');
+                text += w->fa[k].second;
+                text.push_back('\n');
+            }
+            if (!write_whole(w->prefix + ".prg.fa", text.data(), text.size())) {
+                w->err = "cannot write " + w->prefix + ".prg.fa: " + strerror(errno);
+                rc = MPRG_E_INTERNAL;
+            }
+            bytes += (int64_t)text.size();
+        }
+        if (w->n_added == 1) {
+            const Encoded &e = w->first;
+            if ((w->what & MPRG_WRITE_BIN) &&
+                !write_whole(w->prefix + ".prg.bin", e.bin.data(), e.bin.size() * sizeof(uint32_t))) {
+                w->err = "cannot write " + w->prefix + ".prg.bin: " + strerror(errno);
+                rc = MPRG_E_INTERNAL;
+            }
+            if ((w->what & MPRG_WRITE_GFA) && !write_whole(w->prefix + ".prg.gfa", e.gfa.data(), e.gfa.size())) {
+                w->err = "cannot write " + w->prefix + ".prg.gfa: " + strerror(errno);
+                rc = MPRG_E_INTERNAL;
+            }
+            bytes += (int64_t)(e.bin.size() * sizeof(uint32_t) + e.gfa.size());
+        } else {
+            if (w->what & MPRG_WRITE_BIN) {
+                if (!w->zbin.finish()) rc = MPRG_E_INTERNAL;
+                bytes += (int64_t)w->zbin.pos;
+            }
+            if (w->what & MPRG_WRITE_GFA) {
+                if (!w->zgfa.finish()) rc = MPRG_E_INTERNAL;
+                bytes += (int64_t)w->zgfa.pos;
+            }
+            if (rc && w->err.empty()) w->err = "cannot finish the archives of " + w->prefix;
+        }
+    }
+    if (n_loci) *n_loci = w->n_added;
+    if (bytes_written) *bytes_written = bytes;
+    if (rc == MPRG_OK) delete w;  // on failure the caller reads mprg_writer_error, then mprg_writer_abort
+    return rc;
+}
+
+extern "C" void mprg_writer_abort(mprg_writer *w) {
+    if (!w) return;
+    if (w->zbin.f) fclose(w->zbin.f);
+    if (w->zgfa.f) fclose(w->zgfa.f);
+    delete w;
+}

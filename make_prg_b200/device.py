@@ -281,6 +281,15 @@ class Context:
         return Batch(self, hb, shapes), BuildResult(self, hr)
 
 
+    def build_msa_set(self, msas, max_nesting, min_match_length):
+        """The same straight from the native loader's buffers (hostio.MsaSet): no copy on the host."""
+        hb, hr = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.mprg_build_ascii(self.handle, ptr(msas.ascii), ptr(msas.offsets), ptr(msas.n_rows),
+                                              ptr(msas.n_cols), msas.n_loci, max_nesting, min_match_length,
+                                              C.byref(hb), C.byref(hr)))
+        return Batch(self, hb, msas.shapes()), BuildResult(self, hr)
+
+
 class BuildResult:
     """Trees and PRG strings of one mprg_build call."""
 

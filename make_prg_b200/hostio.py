@@ -1,0 +1,257 @@
+"""Python face of libmprg's host-side I/O (include/mprg.h, csrc/hostio.cu): the native FASTA loader
+in front of the hot path and the native .prg.fa / .bin / .gfa writers behind it.
+
+    load_fasta_files  ~ load_alignment_file per file      make_prg/utils/io_utils.py:17-49
+    encode_prg        ~ PrgEncoder.encode                 make_prg/utils/prg_encoder.py:74-91
+    prg_to_gfa        ~ GFA_Output.write_gfa's text       make_prg/utils/gfa.py:39-109
+    OutputWriter      ~ InputOutputFiles.create_final_files  make_prg/utils/input_output_files.py:70-135
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import MprgError, ptr
+from .msa import MSA
+from .utils import io_utils
+
+LOAD_OK, LOAD_NO_RECORDS, LOAD_RAGGED, LOAD_IO_ERROR, LOAD_NOT_ASCII = 0, 1, 2, 3, 4
+FLAG_HAS_N = 1
+WRITE_PRG, WRITE_BIN, WRITE_GFA = 1, 2, 4
+
+
+def default_threads():
+    return max(1, min(32, os.cpu_count() or 1))
+
+
+def _c_strings(strings):
+    raw = [s.encode() if isinstance(s, str) else bytes(s) for s in strings]
+    arr = (C.c_char_p * max(len(raw), 1))(*raw)
+    return arr, raw
+
+
+def _view(pointer, ctype, n):
+    if n == 0 or not pointer:
+        return np.zeros(0, np.dtype(ctype))
+    return np.ctypeslib.as_array(C.cast(pointer, C.POINTER(ctype)), shape=(n,))
+
+
+class MsaSet:
+    """The loci of a list of FASTA files in one host buffer (pinned when a device is present), laid out
+    as mprg_build_ascii takes them.  Views are valid until free()."""
+
+    def __init__(self, handle, paths):
+        self.lib = _lib.load()
+        self.handle = handle
+        self.paths = [str(p) for p in paths]
+        n, ascii_p, nbytes = C.c_int32(), C.c_void_p(), C.c_int64()
+        offs, nr, nc, st, fl = (C.c_void_p() for _ in range(5))
+        rc = self.lib.mprg_fasta_info(handle, C.byref(n), C.byref(ascii_p), C.byref(nbytes), C.byref(offs),
+                                      C.byref(nr), C.byref(nc), C.byref(st), C.byref(fl))
+        if rc != 0:
+            raise MprgError(rc, "mprg_fasta_info failed")
+        self.n_loci = n.value
+        self.ascii = _view(ascii_p, C.c_uint8, max(nbytes.value, 1))
+        self.ascii_bytes = nbytes.value
+        self.offsets = _view(offs, C.c_int64, self.n_loci)
+        self.n_rows = _view(nr, C.c_int32, self.n_loci)
+        self.n_cols = _view(nc, C.c_int32, self.n_loci)
+        self.status = _view(st, C.c_int32, self.n_loci)
+        self.flags = _view(fl, C.c_int32, self.n_loci)
+
+    def matrix(self, locus):
+        """uint8[rows, cols] view (writable) of one locus."""
+        r, c, o = int(self.n_rows[locus]), int(self.n_cols[locus]), int(self.offsets[locus])
+        return self.ascii[o:o + r * c].reshape(r, c)
+
+    def titles(self, locus):
+        n = C.c_int64()
+        p = self.lib.mprg_fasta_titles(self.handle, locus, C.byref(n))
+        text = C.string_at(p, n.value).decode() if p and n.value else ""
+        rows = int(self.n_rows[locus]) if self.status[locus] == LOAD_OK else None
+        out = text.split("\n")
+        return out if rows is None or len(out) == rows else out + [""] * (rows - len(out))
+
+    def ids(self, locus):
+        """Record ids as Biopython cuts them: the first whitespace-separated token of the title."""
+        out = []
+        for title in self.titles(locus):
+            tokens = title.split(None, 1)
+            out.append(tokens[0] if tokens else "")
+        return out
+
+    def alignment(self, locus):
+        """The locus as an MSA object (ids, descriptions, rows) for the host-side node classes."""
+        return MSA.from_matrix(self.ids(locus), self.matrix(locus), descriptions=self.titles(locus))
+
+    def shapes(self):
+        return [(int(r), int(c)) for r, c in zip(self.n_rows, self.n_cols)]
+
+    def free(self):
+        if self.handle is not None:
+            self.ascii = self.offsets = self.n_rows = self.n_cols = self.status = self.flags = None
+            self.lib.mprg_fasta_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def replace_n_in_place(matrix):
+    """io_utils.py:35-47 on a uint8 matrix: every N becomes the column's majority symbol, drawn with
+    the reference's sha256-seeded random.Random (one `choice` per column, in column order)."""
+    seqs = [row.tobytes().decode("ascii") for row in matrix]
+    consensus = io_utils.majority_consensus_of_rows(seqs)
+    cons = np.frombuffer(consensus.encode("ascii"), np.uint8)
+    mask = matrix == ord("N")
+    matrix[mask] = np.broadcast_to(cons, matrix.shape)[mask]
+
+
+def load_fasta_files(paths, threads=None, pin=True):
+    """Parses every file on host threads.  Loci whose status is not LOAD_OK are left to the caller
+    (`raise_for_load_status` re-creates the reference's exception); N is replaced in place."""
+    lib = _lib.load()
+    arr, _keep = _c_strings([os.fspath(p) for p in paths])
+    h = C.c_void_p()
+    rc = lib.mprg_fasta_load(C.cast(arr, C.c_void_p), len(paths), threads or default_threads(), int(bool(pin)),
+                             C.byref(h))
+    if rc != 0:
+        raise MprgError(rc, "mprg_fasta_load failed")
+    msas = MsaSet(h, paths)
+    for i in np.nonzero((msas.flags & FLAG_HAS_N) != 0)[0]:
+        if msas.status[i] == LOAD_OK:
+            replace_n_in_place(msas.matrix(int(i)))
+    return msas
+
+
+def raise_for_load_status(msas, locus):
+    """The exception load_alignment_file raises for this file (io_utils.py:17-29 through Biopython)."""
+    status = int(msas.status[locus])
+    if status == LOAD_OK:
+        return
+    if status == LOAD_NO_RECORDS:
+        raise ValueError("No records found in handle")
+    if status == LOAD_RAGGED:
+        raise ValueError("Sequences must all be the same length")
+    # unreadable or not plain ASCII: the Python loader raises (or decodes) exactly as before
+    io_utils.load_alignment_file(msas.paths[locus], "fasta")
+    raise ValueError(f"{msas.paths[locus]} could not be loaded")
+
+
+# ---- writers ------------------------------------------------------------------------------------
+class EncodeError(Exception):
+    pass
+
+
+def _raise_encoding(rc, what):
+    if rc == 1:
+        raise EncodeError(f"{what} contains invalid characters")
+    if rc == 2:
+        raise ValueError("Prg error: odd site marker found >2 times")
+    if rc == 3:
+        raise OverflowError("int too big to convert")
+    raise MprgError(rc, f"{what} failed")
+
+
+def encode_prg(prg):
+    """PRG string -> uint32 array (what PrgEncoder.write stores little-endian)."""
+    lib = _lib.load()
+    raw = prg.encode() if isinstance(prg, str) else bytes(prg)
+    n = C.c_int64()
+    out = np.zeros(max(len(raw), 1), np.uint32)  # one value per base or marker: never more than bytes
+    rc = lib.mprg_encode_prg(raw, len(raw), ptr(out), out.size, C.byref(n))
+    if rc != 0:
+        _raise_encoding(rc, "Unit")
+    return out[:n.value].copy()
+
+
+def prg_to_gfa(prg):
+    """PRG string -> GFA text, header included."""
+    lib = _lib.load()
+    raw = prg.encode() if isinstance(prg, str) else bytes(prg)
+    n = C.c_int64()
+    rc = lib.mprg_prg_to_gfa(raw, len(raw), None, 0, C.byref(n))
+    if rc != 0:
+        raise AssertionError("Invalid prg sequence")
+    out = np.zeros(max(n.value, 1), np.uint8)
+    lib.mprg_prg_to_gfa(raw, len(raw), ptr(out), out.size, C.byref(n))
+    return out[:n.value].tobytes().decode()
+
+
+class PrgStrings:
+    """A result handle over plain PRG strings (mprg_result_from_prgs), for OutputWriter.add."""
+
+    def __init__(self, prgs):
+        self.lib = _lib.load()
+        raw = [p.encode() if isinstance(p, str) else bytes(p) for p in prgs]
+        arr = (C.c_char_p * max(len(raw), 1))(*raw)
+        lens = np.array([len(r) for r in raw], np.int64)
+        h = C.c_void_p()
+        rc = self.lib.mprg_result_from_prgs(C.cast(arr, C.c_void_p), ptr(lens) if len(raw) else None, len(raw),
+                                            C.byref(h))
+        if rc != 0:
+            raise MprgError(rc, "mprg_result_from_prgs failed")
+        self.handle = h
+
+    def free(self):
+        if self.handle is not None:
+            self.lib.mprg_result_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class OutputWriter:
+    """<prefix>.prg.fa / .prg.bin(.zip) / .prg.gfa(.zip) written by host threads of the library."""
+
+    def __init__(self, output_prefix, prg=True, binary=True, gfa=True, threads=None):
+        self.lib = _lib.load()
+        what = (WRITE_PRG if prg else 0) | (WRITE_BIN if binary else 0) | (WRITE_GFA if gfa else 0)
+        self.threads = threads or default_threads()
+        h = C.c_void_p()
+        rc = self.lib.mprg_writer_open(os.fspath(output_prefix).encode(), what, C.byref(h))
+        if rc != 0:
+            raise MprgError(rc, "mprg_writer_open failed")
+        self.handle = h
+
+    def add(self, result, loci, names):
+        """result: BuildResult or PrgStrings; loci: indices into it; names: locus names (archive order)."""
+        loci = np.ascontiguousarray(loci, np.int32)
+        arr, _keep = _c_strings(names)
+        rc = self.lib.mprg_writer_add(self.handle, result.handle, ptr(loci), C.cast(arr, C.c_void_p), len(loci),
+                                      self.threads)
+        if rc != 0:
+            message = self.lib.mprg_writer_error(self.handle).decode()
+            self.abort()
+            if rc > 0:
+                _raise_encoding(rc, message)
+            raise OSError(message)
+
+    def close(self):
+        n, nbytes = C.c_int64(), C.c_int64()
+        rc = self.lib.mprg_writer_close(self.handle, C.byref(n), C.byref(nbytes))
+        if rc != 0:
+            message = self.lib.mprg_writer_error(self.handle).decode()
+            self.abort()
+            raise OSError(message)
+        self.handle = None
+        return n.value, nbytes.value
+
+    def abort(self):
+        if self.handle is not None:
+            self.lib.mprg_writer_abort(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.abort()
+        except Exception:
+            pass

@@ -10,9 +10,10 @@ import tempfile
 import zipfile
 from pathlib import Path
 
+import numpy as np
 from loguru import logger
 
-from .. import engine
+from .. import engine, hostio
 from .._lib import LOCUS_CURATION_ERROR, LOCUS_OK
 from ..from_msa import MIN_MATCH_LEN, NESTING_LVL
 from ..prg_builder import PrgBuilder
@@ -47,6 +48,9 @@ def register_parser(subparsers):
                         "Default: %(default)d")
     p.add_argument("--gpus", dest="gpus", action="store", type=int, default=1,
                    help="Number of GPUs of this node to shard the loci over. Default: %(default)d")
+    p.add_argument("--skip-update-ds", dest="skip_update_ds", action="store_true",
+                   help="Do not write <prefix>.update_DS.zip (the pickled PrgBuilders `make_prg update` "
+                        "reads); everything else of -O p is still written")
     p.set_defaults(func=run)
     return p
 
@@ -88,70 +92,178 @@ def _bin_bytes(prg):
     return buf.getvalue()
 
 
-def build_loci(input_files, options, device_ordinal=0):
-    """Loads, builds and returns [(locus_name, alignment, LocusBuild)] for the successful loci, in
-    input order.  Errors follow from_msa.py:142-151: an empty MSA aborts the run, a locus with a
-    disallowed base is skipped with a warning."""
+def cut_chunks(input_files, max_bytes=None, max_loci=4096):
+    """Consecutive runs of input files of about max_bytes each: one chunk = one loader call + one device
+    batch, so that loading chunk k+1, building chunk k and writing chunk k-1 overlap."""
+    if max_bytes is None:
+        max_bytes = int(float(os.environ.get("MPRG_CHUNK_MB", "64")) * (1 << 20))
+    chunks, cur, size = [], [], 0
+    for path in input_files:
+        try:
+            nbytes = os.path.getsize(path)
+        except OSError:
+            nbytes = 0
+        if cur and (size + nbytes > max_bytes or len(cur) >= max_loci):
+            chunks.append(cur)
+            cur, size = [], 0
+        cur.append(path)
+        size += nbytes
+    if cur:
+        chunks.append(cur)
+    return chunks
+
+
+def _load_chunk(paths, alignment_format):
+    if alignment_format != "fasta":
+        raise ValueError(f"only the fasta alignment format is supported, got {alignment_format}")
+    return hostio.load_fasta_files(paths)
+
+
+def iter_built_chunks(input_files, options, device_ordinal=0):
+    """Loads (native loader, one chunk ahead on a host thread) and builds (mprg_build_ascii) the input
+    files chunk by chunk.  Yields (names, msas, result, ok) with ok = indices of the chunk's loci that
+    were built; the consumer frees result and msas.  Errors follow from_msa.py:142-151: an empty MSA
+    aborts the run, a locus with a disallowed base is skipped with a warning."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from .. import device
 
-    loci = []
-    for path in input_files:
-        name = remove_known_input_extensions(Path(path).name)
-        logger.info(f"Generating PRG for {name}...")
-        try:
-            alignment = load_alignment_file(str(path), options.alignment_format)
-        except ValueError as err:
-            if "No records found in handle" in str(err.args[0]):
-                raise EmptyMSAError(f"No records found in MSA of locus {name}")
-            raise
-        loci.append((name, alignment))
     ctx = device.default_context(device_ordinal)
-    want_nodes = options.output_type.prg  # the update_DS pickles need the trees
-    builds = engine.build_matrices([a.matrix for _, a in loci], options.max_nesting,
-                                   options.min_match_length, ctx=ctx, want_nodes=want_nodes)
+    chunks = cut_chunks(input_files)
+    with ThreadPoolExecutor(1) as pool:
+        future = pool.submit(_load_chunk, chunks[0], options.alignment_format) if chunks else None
+        for k, paths in enumerate(chunks):
+            msas = future.result()
+            future = (pool.submit(_load_chunk, chunks[k + 1], options.alignment_format)
+                      if k + 1 < len(chunks) else None)
+            names = [remove_known_input_extensions(Path(path).name) for path in paths]
+            logger.info(f"Generating PRGs for {names[0]} ... {names[-1]} ({len(names)} loci)...")
+            for i in np.nonzero(msas.status != hostio.LOAD_OK)[0]:
+                try:
+                    hostio.raise_for_load_status(msas, int(i))
+                except ValueError as err:
+                    if "No records found in handle" in str(err.args[0]):
+                        raise EmptyMSAError(f"No records found in MSA of locus {names[int(i)]}")
+                    raise
+            batch, res = ctx.build_msa_set(msas, options.max_nesting, options.min_match_length)
+            batch.free()
+            ok = []
+            for i, name in enumerate(names):
+                status = res.status(i)
+                if status == LOCUS_OK:
+                    ok.append(i)
+                elif status == LOCUS_CURATION_ERROR:
+                    logger.warning(f"Skipping building PRG for {name}. Error: a slice of a sequence has a "
+                                   "disallowed base. Redo sequence curation.")
+                else:
+                    engine.LocusBuild(status, "", 0, 0, None).raise_for_status(name)
+            yield names, msas, res, ok
+
+
+def _update_ds_pickles(names, msas, res, ok, options):
+    """(name, pickled PrgBuilder) for the update_DS archive (prg_builder.py:145-147)."""
+    import pickle
+
+    out = []
+    for i in ok:
+        build = engine.LocusBuild(LOCUS_OK, res.prg(i), res.n_nodes(i), res.n_sites(i), res.nodes(i))
+        builder = PrgBuilder.from_engine(names[i], msas.alignment(i), build, options.max_nesting,
+                                         options.min_match_length)
+        assert builder.build_prg() == build.prg, f"PRG emission mismatch for {names[i]}"
+        out.append((names[i], pickle.dumps(builder, protocol=4)))
+    return out
+
+
+def build_and_write(input_files, options, device_ordinal=0, output_prefix=None):
+    """One GPU: the whole run, files in -> final files out.  Returns the number of PRGs written.
+    The update_DS archive (Python PrgBuilder pickles) is written unless options.skip_update_ds."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    prefix = output_prefix or options.output_prefix
+    ot = options.output_type
+    want_ds = ot.prg and not getattr(options, "skip_update_ds", False)
+    writer = hostio.OutputWriter(prefix, prg=ot.prg, binary=ot.binary, gfa=ot.gfa)
+    ds_zip = None
+    n_ok = 0
+    pending = None  # (future, msas, res): the chunk being encoded / written on the writer thread
+
+    def finish(p):
+        fut, msas, res = p
+        try:
+            fut.result()
+        finally:
+            res.free()
+            msas.free()
+
+    try:
+        with ThreadPoolExecutor(1) as pool:
+            for names, msas, res, ok in iter_built_chunks(input_files, options, device_ordinal):
+                if pending is not None:
+                    finish(pending)
+                    pending = None
+                if want_ds and ok:
+                    if ds_zip is None:
+                        ds_zip = zipfile.ZipFile(prefix + ".update_DS.zip", "w")
+                    for name, blob in _update_ds_pickles(names, msas, res, ok, options):
+                        ds_zip.writestr(name, blob)
+                n_ok += len(ok)
+                pending = (pool.submit(writer.add, res, ok, [names[i] for i in ok]), msas, res)
+            if pending is not None:
+                finish(pending)
+                pending = None
+        writer.close()
+    except BaseException:
+        if pending is not None:
+            try:
+                finish(pending)
+            except Exception:
+                pass
+        writer.abort()
+        raise
+    finally:
+        if ds_zip is not None:
+            ds_zip.close()
+    return n_ok
+
+
+def build_loci(input_files, options, device_ordinal=0, want_nodes=None):
+    """Loads, builds and returns [(locus_name, alignment, LocusBuild)] for the successful loci, in
+    input order (the in-memory form of a run, used by the multi-GPU shards)."""
+    if want_nodes is None:
+        want_nodes = options.output_type.prg and not getattr(options, "skip_update_ds", False)
     good = []
-    for (name, alignment), b in zip(loci, builds):
-        if b.status == LOCUS_OK:
-            good.append((name, alignment, b))
-        elif b.status == LOCUS_CURATION_ERROR:
-            logger.warning(f"Skipping building PRG for {name}. Error: a slice of a sequence has a "
-                           "disallowed base. Redo sequence curation.")
-        else:
-            b.raise_for_status(name)
+    for names, msas, res, ok in iter_built_chunks(input_files, options, device_ordinal):
+        for i in ok:
+            build = engine.LocusBuild(LOCUS_OK, res.prg(i), res.n_nodes(i), res.n_sites(i),
+                                      res.nodes(i) if want_nodes else None)
+            good.append((names[i], msas.alignment(i) if want_nodes else None, build))
+        res.free()
+        msas.free()
     return good
 
 
 def write_outputs(good, options):
-    """Final files exactly as InputOutputFiles.create_final_files lays them out."""
+    """Final files exactly as InputOutputFiles.create_final_files lays them out, from in-memory builds
+    (the native writers take the PRG strings; the update_DS pickles are Python objects)."""
     prefix = options.output_prefix
     ot = options.output_type
-    single = len(good) == 1
-    if ot.prg:
-        with open(prefix + ".prg.fa", "w") as fh:
-            for name, _a, b in sorted(good, key=lambda t: t[0] + ".prg.fa"):
-                fh.write(f">{name}\n{b.prg}\n")
+    strings = hostio.PrgStrings([b.prg for _n, _a, b in good])
+    writer = hostio.OutputWriter(prefix, prg=ot.prg, binary=ot.binary, gfa=ot.gfa)
+    try:
+        writer.add(strings, np.arange(len(good), dtype=np.int32), [name for name, _a, _b in good])
+        writer.close()
+    finally:
+        writer.abort()
+        strings.free()
+    if ot.prg and not getattr(options, "skip_update_ds", False):
+        import pickle
+
         with zipfile.ZipFile(prefix + ".update_DS.zip", "w") as zf:
             for name, alignment, b in good:
                 builder = PrgBuilder.from_engine(name, alignment, b, options.max_nesting,
                                                  options.min_match_length)
                 assert builder.build_prg() == b.prg, f"PRG emission mismatch for {name}"
-                import pickle
-
                 zf.writestr(name, pickle.dumps(builder, protocol=4))
-    if ot.binary:
-        if single:
-            Path(prefix + ".prg.bin").write_bytes(_bin_bytes(good[0][2].prg))
-        else:
-            with zipfile.ZipFile(prefix + ".prg.bin.zip", "w") as zf:
-                for name, _a, b in good:
-                    zf.writestr(f"{name}.bin", _bin_bytes(b.prg))
-    if ot.gfa:
-        if single:
-            Path(prefix + ".prg.gfa").write_text(_gfa_text(good[0][2].prg))
-        else:
-            with zipfile.ZipFile(prefix + ".prg.gfa.zip", "w") as zf:
-                for name, _a, b in good:
-                    zf.writestr(f"{name}.gfa", _gfa_text(b.prg))
 
 
 def run(options):
@@ -165,14 +277,17 @@ def run(options):
     gpus = max(1, int(getattr(options, "gpus", 1) or 1))
     logger.info(f"Using {gpus} GPU(s) to generate PRGs...")
     if gpus == 1:
-        good = build_loci(input_files, options)
+        n_ok = build_and_write(input_files, options)
+        logger.success("All PRGs generated!")
+        if n_ok == 0:
+            logger.error("No PRGs were built, please check errors")
     else:
         good = _run_sharded(input_files, options, gpus)
-    logger.success("All PRGs generated!")
-    if len(good) == 0:
-        logger.error("No PRGs were built, please check errors")
-    else:
-        write_outputs(good, options)
+        logger.success("All PRGs generated!")
+        if len(good) == 0:
+            logger.error("No PRGs were built, please check errors")
+        else:
+            write_outputs(good, options)
     logger.success("All done!")
 
 

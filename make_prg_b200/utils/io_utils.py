@@ -31,12 +31,12 @@ def parse_fasta(handle):
     return MSA(records)
 
 
-def get_majority_consensus_from_MSA(alignment):
-    seqs = [r.seq.upper() for r in alignment]
+def majority_consensus_of_rows(seqs):
+    """seq_utils.py:246-290 on upper-cased row strings."""
     rng = random.Random()
     rng.seed(hashlib.sha256("".join(seqs).encode()).digest())
     consensus = []
-    for i in range(alignment.get_alignment_length()):
+    for i in range(len(seqs[0]) if seqs else 0):
         counts = Counter(s[i] for s in seqs if s[i] != "-" and s[i] != "N")
         if not counts:
             consensus.append(rng.choice("ACGT"))
@@ -44,6 +44,10 @@ def get_majority_consensus_from_MSA(alignment):
         top = counts.most_common(1)[0][1]
         consensus.append(rng.choice([res for res, c in counts.items() if c == top]))
     return "".join(consensus)
+
+
+def get_majority_consensus_from_MSA(alignment):
+    return majority_consensus_of_rows([r.seq.upper() for r in alignment])
 
 
 def load_alignment_file(msa_file, alignment_format="fasta"):

@@ -1,0 +1,216 @@
+"""CPU: the native loader and writers of libmprg (csrc/hostio.cpp) against the
+host-side mirrors of the reference (utils/io_utils.py, utils/gfa.py, utils/prg_encoder.py) and against
+the reference's golden output files.  No device is needed: these entry points are plain host code."""
+import gzip
+import zipfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import REF, truth_multi
+
+from make_prg_b200 import hostio
+from make_prg_b200.utils import gfa as gfa_py
+from make_prg_b200.utils import io_utils
+from make_prg_b200.utils.prg_encoder import PrgEncoder
+
+
+def fixture_fastas():
+    files = sorted(p for p in REF.glob("*.fa*") if p.is_file())
+    for sub in ("sample_example", "amira_MSAs", "several", "several_compressed"):
+        files += sorted(p for p in (REF / sub).rglob("*") if p.is_file())
+    return files
+
+
+def all_truth_prgs():
+    out = []
+    for f in sorted((REF / "truth").glob("*/*.prg.fa")):
+        lines = f.read_text().split("\n")
+        out += [lines[i + 1] for i in range(0, len(lines) - 1, 2)]
+    return out
+
+
+def test_loader_equals_python_loader_on_every_fixture():
+    files = fixture_fastas()
+    assert len(files) >= 30 and any(str(f).endswith(".gz") for f in files)
+    msas = hostio.load_fasta_files(files, threads=3, pin=False)
+    assert msas.n_loci == len(files)
+    with_n = 0
+    for i, f in enumerate(files):
+        want = io_utils.load_alignment_file(str(f))
+        assert msas.status[i] == hostio.LOAD_OK, f
+        assert np.array_equal(msas.matrix(i), want.matrix), f
+        assert msas.ids(i) == want.ids, f
+        assert [r.description for r in msas.alignment(i)] == [r.description for r in want], f
+        with_n += int(msas.flags[i] & hostio.FLAG_HAS_N)
+    assert with_n >= 4  # the contains_n* fixtures went through the in-place N replacement
+    # the loci sit back to back, as mprg_build_ascii wants them
+    sizes = msas.n_rows.astype(np.int64) * msas.n_cols
+    assert np.array_equal(msas.offsets, np.concatenate([[0], np.cumsum(sizes)[:-1]]))
+    assert msas.ascii_bytes == int(sizes.sum())
+    msas.free()
+
+
+def test_loader_text_edge_cases(tmp_path):
+    cases = {
+        "crlf.fa": b">a desc one\r\nACgt\r\nAC\r\n>b\r\nAC-TNC\r\n",
+        "lone_cr.fa": b">a\rACGT\r>b\rAC-T\r",
+        "blank_and_spaces.fa": b"; comment\n\n>a  two  spaces \nAC GT\n\n  \nAC\n>b\tTab\n\nACGTAC\n",
+        "no_trailing_newline.fa": b">a\nACGT\n>b\nAC-T",
+        "long_lines.fa": b">a\n" + b"ACGT" * 300 + b"\n>b\n" + b"acgt" * 150 + b"\n" + b"AC-T" * 150 + b"\n",
+        "empty_title.fa": b">\nAC\n>x\nAG\n",
+        "zero_columns.fa": b">a\n>b\n",
+        "wrapped_gt.fa": b">a\nAC\n>b\nA\n>\n",
+    }
+    paths = []
+    for name, blob in cases.items():
+        (tmp_path / name).write_bytes(blob)
+        paths.append(tmp_path / name)
+    with gzip.open(tmp_path / "multi.fa.gz", "wb") as fh:
+        fh.write(b">a\nACGT\n")
+    with gzip.open(tmp_path / "multi.fa.gz", "ab") as fh:  # second gzip member, as `cat a.gz b.gz`
+        fh.write(b">b\nACGA\n")
+    paths.append(tmp_path / "multi.fa.gz")
+    msas = hostio.load_fasta_files(paths, threads=2, pin=False)
+    for i, p in enumerate(paths):
+        try:
+            want = io_utils.load_alignment_file(str(p))
+        except ValueError as err:
+            assert msas.status[i] in (hostio.LOAD_NO_RECORDS, hostio.LOAD_RAGGED), p
+            with pytest.raises(ValueError, match=str(err.args[0])[:20]):
+                hostio.raise_for_load_status(msas, i)
+            continue
+        assert msas.status[i] == hostio.LOAD_OK, p
+        assert np.array_equal(msas.matrix(i), want.matrix), p
+        assert msas.ids(i) == want.ids, p
+        assert msas.titles(i) == [r.description for r in want], p
+    msas.free()
+
+
+def test_loader_statuses(tmp_path):
+    (tmp_path / "empty.fa").write_bytes(b"")
+    (tmp_path / "ragged.fa").write_bytes(b">a\nACGT\n>b\nACG\n")
+    (tmp_path / "latin.fa").write_bytes(">a café\nACGT\n".encode("utf-8"))
+    (tmp_path / "broken.fa.gz").write_bytes(b"not a gzip stream at all")
+    paths = [tmp_path / "empty.fa", tmp_path / "ragged.fa", tmp_path / "latin.fa", tmp_path / "missing.fa",
+             tmp_path / "broken.fa.gz"]
+    msas = hostio.load_fasta_files(paths, threads=2, pin=False)
+    assert list(msas.status[:4]) == [hostio.LOAD_NO_RECORDS, hostio.LOAD_RAGGED, hostio.LOAD_NOT_ASCII,
+                                     hostio.LOAD_IO_ERROR]
+    assert list(msas.n_rows) == [0] * 5 and msas.ascii_bytes == 0
+    with pytest.raises(ValueError, match="No records found in handle"):
+        hostio.raise_for_load_status(msas, 0)
+    with pytest.raises(ValueError, match="same length"):
+        hostio.raise_for_load_status(msas, 1)
+    with pytest.raises(FileNotFoundError):
+        hostio.raise_for_load_status(msas, 3)
+    msas.free()
+
+
+def test_loader_vector_and_scalar_paths_agree(tmp_path, monkeypatch):
+    rng = np.random.default_rng(5)
+    paths = []
+    for k in range(6):
+        rows, cols, wrap = int(rng.integers(1, 40)), int(rng.integers(0, 700)), int(rng.integers(1, 130))
+        M = rng.choice(np.frombuffer(b"ACGTacgtRYKMSW-N", np.uint8), size=(rows, cols))
+        with open(tmp_path / f"r{k}.fa", "wb") as fh:
+            for r in range(rows):
+                s = M[r].tobytes()
+                fh.write(b">row%d x\n" % r)
+                for c in range(0, cols, wrap):
+                    fh.write(s[c:c + wrap] + (b"\r\n" if k % 2 else b"\n"))
+        paths.append(tmp_path / f"r{k}.fa")
+    fast = hostio.load_fasta_files(paths, threads=2, pin=False)
+    monkeypatch.setenv("MPRG_NO_AVX2", "1")
+    slow = hostio.load_fasta_files(paths, threads=1, pin=False)
+    for i, p in enumerate(paths):
+        want = io_utils.load_alignment_file(str(p))
+        assert np.array_equal(fast.matrix(i), want.matrix) and np.array_equal(slow.matrix(i), want.matrix), p
+        assert b"N" not in fast.matrix(i).tobytes() or fast.n_cols[i] == 0
+    fast.free()
+    slow.free()
+
+
+def test_gfa_and_bin_equal_python_mirrors_and_golden_files():
+    prgs = all_truth_prgs()
+    assert len(prgs) >= 25
+    for prg in prgs:
+        g = gfa_py.GFA_Output(gfa_py.HEADER)
+        g.build_gfa_string(prg_string=prg)
+        assert hostio.prg_to_gfa(prg) == g.gfa_string
+        assert hostio.encode_prg(prg).tolist() == PrgEncoder().encode(prg)
+    t = REF / "truth" / "match.nonmatch"
+    prg = (t / "match.nonmatch.prg.fa").read_text().split("\n")[1]
+    assert hostio.encode_prg(prg).astype("<u4").tobytes() == (t / "match.nonmatch.prg.bin").read_bytes()
+    assert hostio.prg_to_gfa(prg).encode() == (t / "match.nonmatch.prg.gfa").read_bytes()
+
+
+def test_encoder_reference_unit_vectors_and_errors():
+    # tests/test_prg_encoder.py of the reference
+    assert hostio.encode_prg("").tolist() == []
+    assert hostio.encode_prg("ACGT").tolist() == [1, 2, 3, 4]
+    assert hostio.encode_prg("a 5 g 6 t 5 c").tolist() == [1, 5, 3, 6, 4, 6, 2]
+    assert hostio.encode_prg("TC 5 ACTC 7 TAGTCA 8 TTGTGA 7  6 AACTAG 5 AG").tolist() == PrgEncoder().encode(
+        "TC 5 ACTC 7 TAGTCA 8 TTGTGA 7  6 AACTAG 5 AG")
+    with pytest.raises(hostio.EncodeError):
+        hostio.encode_prg("AC 5 AX 6 T 5 ")
+    with pytest.raises(ValueError):
+        hostio.encode_prg("A 5 C 6 T 5 A 5 ")
+    with pytest.raises(AssertionError):
+        hostio.prg_to_gfa("A 5 C 5 ")  # a site with one allele (gfa.py:64-66)
+    with pytest.raises(AssertionError):
+        hostio.prg_to_gfa("A 5 C 6 T")  # unterminated site
+
+
+def test_writer_final_files(tmp_path):
+    truth = truth_multi("sample_example")
+    names = sorted(truth, reverse=True)  # archive order = order added, .prg.fa = sorted
+    strings = hostio.PrgStrings([truth[n] for n in names])
+    w = hostio.OutputWriter(tmp_path / "out", threads=2)
+    w.add(strings, [0, 1], names)
+    n, nbytes = w.close()
+    assert n == 2 and nbytes > 0
+    tdir = REF / "truth" / "sample_example"
+    assert (tmp_path / "out.prg.fa").read_bytes() == (tdir / "sample_example.prg.fa").read_bytes()
+    for kind in ("bin", "gfa"):
+        with zipfile.ZipFile(tmp_path / f"out.prg.{kind}.zip") as got, \
+                zipfile.ZipFile(tdir / f"sample_example.prg.{kind}.zip") as want:
+            assert got.testzip() is None
+            assert got.namelist() == [f"{n}.{kind}" for n in names]
+            assert got.infolist()[0].compress_type == zipfile.ZIP_STORED
+            for member in want.namelist():
+                assert got.read(member) == want.read(member), member
+    # one locus: plain files, no archives (input_output_files.py:107-112,122-126)
+    w = hostio.OutputWriter(tmp_path / "one", threads=1)
+    w.add(strings, [1], [names[1]])
+    assert w.close()[0] == 1
+    assert (tmp_path / "one.prg.bin").read_bytes() == hostio.encode_prg(truth[names[1]]).astype("<u4").tobytes()
+    assert (tmp_path / "one.prg.gfa").read_text() == hostio.prg_to_gfa(truth[names[1]])
+    assert not (tmp_path / "one.prg.bin.zip").exists()
+    # nothing added: nothing written; only some outputs asked for
+    assert hostio.OutputWriter(tmp_path / "none").close() == (0, 0)
+    assert not list(tmp_path.glob("none*"))
+    w = hostio.OutputWriter(tmp_path / "g", prg=False, binary=False, gfa=True)
+    w.add(strings, [0, 1], names)
+    w.add(strings, [0], ["again"])
+    w.close()
+    assert sorted(p.name for p in tmp_path.glob("g.*")) == ["g.prg.gfa.zip"]
+    with zipfile.ZipFile(tmp_path / "g.prg.gfa.zip") as z:
+        assert z.namelist() == [f"{names[0]}.gfa", f"{names[1]}.gfa", "again.gfa"]
+    with pytest.raises(hostio.EncodeError):
+        bad = hostio.PrgStrings(["AC 5 AX 6 T 5 "])
+        hostio.OutputWriter(tmp_path / "bad").add(bad, [0], ["bad"])
+    strings.free()
+
+
+def test_writer_many_entries_zip64(tmp_path):
+    n = 66000  # > 65535 entries: the archive needs the zip64 end-of-central-directory records
+    strings = hostio.PrgStrings(["A 5 C 6 G 5 T"])
+    w = hostio.OutputWriter(tmp_path / "big", prg=False, binary=True, gfa=False, threads=2)
+    names = [f"locus{i}" for i in range(n)]
+    w.add(strings, np.zeros(n, np.int32), names)
+    assert w.close()[0] == n
+    with zipfile.ZipFile(tmp_path / "big.prg.bin.zip") as z:
+        assert len(z.namelist()) == n
+        assert z.read("locus65999.bin") == np.array([1, 5, 2, 6, 3, 6, 4], "<u4").tobytes()
