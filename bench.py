@@ -10,6 +10,8 @@ KMeans / PRG emission, `mprg_build`) over that batch.
   e2e       loci/sec through the public API from pinned HOST ASCII buffers: H2D copy + device packing
             + build + PRG strings back on the host, every step
   roofline  the dominant kernel (column scan, root level launch): algorithmic bytes / CUDA-event time
+  files     the same metric file to file (FASTA files in page cache -> .prg.fa/.bin.zip/.gfa.zip on tmpfs)
+            through the native loader and writers (scripts/files_e2e.py), host wall clock
   cpu_baseline  the oracle port (oracle/make_prg_oracle.py) on a bounded sample, 1 core
 `--impl reference` times the reference's CPU algorithm (the oracle port; the Python reference cannot
 travel to the GPU box) with all host cores on a bounded sample per step.
@@ -224,6 +226,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--loci", type=int, default=LOCI_PER_GPU)
     ap.add_argument("--no-big", action="store_true", help="skip the 8x-size launch of the roofline pass")
+    ap.add_argument("--no-files", action="store_true", help="skip the file-to-file (FASTA in, PRG files out) pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -404,6 +407,18 @@ def main():
                             "launches_per_step": len(log_bytes) / args.steps,
                             "achieved_gbs_sum_over_launches": float(log_bytes.sum() / (log_ms.sum() * 1e-3) / 1e9)
                             if len(log_bytes) else None}}
+    # file to file: FASTA files in -> .prg.fa / .prg.bin.zip / .prg.gfa.zip out through the
+    # native loader and writers, one batch (1,000 loci) and a pipelined run (4 x the loci, chunked)
+    files = None
+    if not args.no_files and n_loci == LOCI_PER_GPU:
+        try:
+            sys.path.insert(0, str(REPO / "scripts"))
+            import files_e2e
+
+            files = {"one_batch": files_e2e.measure(n_loci, reps=5),
+                     "pipelined_x4": files_e2e.measure(n_loci, reps=3, copies=4)}
+        except Exception as err:  # the headline numbers above do not depend on this pass
+            files = {"error": repr(err)}
     # CPU baseline: oracle port, 1 core, bounded sample
     sample = 100
     cpu_v, cpu_dt = oracle_loci_per_sec([data[i] for i in range(sample)], 1)
@@ -422,6 +437,7 @@ def main():
         "cpu_baseline": {"value": cpu_v, "unit": "loci/s", "cores": 1, "kind": "port",
                          "sample": f"first {sample} loci of the workload, oracle/make_prg_oracle.py, "
                                    f"{cpu_dt:.1f} s"},
+        "files": files,
         "clocks": clocks.summary(),
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "step_ms": {"resident": {"min": float(np.min(dev_steps)), "median": float(np.median(dev_steps)),

@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <memory>
+#include <mutex>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -77,6 +78,56 @@ uint8_t *huge_alloc(size_t bytes) {
     void *p = aligned_alloc(two_mb, bytes);
     if (p) madvise(p, bytes, MADV_HUGEPAGE);
     return (uint8_t *)p;
+}
+
+// Pinned host buffers are expensive to create and to destroy (tens of ms per 100 MB): the loader's
+// output buffers are recycled through a small process-wide pool (at most MPRG_PINNED_POOL_MB, default
+// 1024, are kept when idle).
+struct PinnedPool {
+    std::mutex m;
+    std::vector<std::pair<uint8_t *, size_t>> idle;
+    size_t idle_bytes = 0;
+    uint8_t *acquire(size_t bytes, size_t &capacity) {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            int best = -1;
+            for (int i = 0; i < (int)idle.size(); ++i)
+                if (idle[i].second >= bytes && (best < 0 || idle[i].second < idle[best].second)) best = i;
+            if (best >= 0 && idle[best].second <= 4 * bytes + ((size_t)16 << 20)) {
+                uint8_t *p = idle[best].first;
+                capacity = idle[best].second;
+                idle_bytes -= capacity;
+                idle.erase(idle.begin() + best);
+                return p;
+            }
+        }
+        capacity = ((bytes + bytes / 8) + ((size_t)8 << 20) - 1) & ~(((size_t)8 << 20) - 1);
+        uint8_t *p = nullptr;
+        if (cudaHostAlloc((void **)&p, capacity, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return p;
+    }
+    void release(uint8_t *p, size_t capacity) {
+        static const size_t limit = []() {
+            const char *e = getenv("MPRG_PINNED_POOL_MB");
+            return (size_t)(e ? atoll(e) : 1024) << 20;
+        }();
+        {
+            std::lock_guard<std::mutex> lock(m);
+            if (idle_bytes + capacity <= limit) {
+                idle.emplace_back(p, capacity);
+                idle_bytes += capacity;
+                return;
+            }
+        }
+        cudaFreeHost(p);
+    }
+};
+PinnedPool &pinned_pool() {
+    static PinnedPool *pool = new PinnedPool();  // never destroyed: no CUDA calls at process exit
+    return *pool;
 }
 
 // bump allocator of one parsing thread; the blocks live until the matrices have been copied out
@@ -321,6 +372,7 @@ struct mprg_msa_set {
     uint8_t *ascii = nullptr;
     int64_t ascii_bytes = 0;
     bool pinned = false;
+    size_t capacity = 0;
     std::vector<int64_t> offsets;
     std::vector<int32_t> n_rows, n_cols, status, flags;
     std::vector<std::string> titles;
@@ -357,10 +409,10 @@ extern "C" int mprg_fasta_load(const char *const *paths, int32_t n_files, int32_
     }
     set->ascii_bytes = total;
     const size_t alloc = (size_t)std::max<int64_t>(total, 1);
-    if (pin && cudaHostAlloc((void **)&set->ascii, alloc, cudaHostAllocDefault) == cudaSuccess) {
+    if (pin) set->ascii = pinned_pool().acquire(alloc, set->capacity);
+    if (set->ascii) {
         set->pinned = true;
-    } else {
-        if (pin) cudaGetLastError();  // without a device the buffer is ordinary memory
+    } else {  // without a device the buffer is ordinary memory
         set->ascii = huge_alloc(alloc);
         if (!set->ascii) {
             delete set;
@@ -380,7 +432,7 @@ extern "C" void mprg_fasta_free(mprg_msa_set *set) {
     if (!set) return;
     if (set->ascii) {
         if (set->pinned)
-            cudaFreeHost(set->ascii);
+            pinned_pool().release(set->ascii, set->capacity);
         else
             free(set->ascii);
     }

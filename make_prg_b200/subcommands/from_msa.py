@@ -92,11 +92,11 @@ def _bin_bytes(prg):
     return buf.getvalue()
 
 
-def cut_chunks(input_files, max_bytes=None, max_loci=4096):
+def cut_chunks(input_files, max_bytes=None, max_loci=16384):
     """Consecutive runs of input files of about max_bytes each: one chunk = one loader call + one device
     batch, so that loading chunk k+1, building chunk k and writing chunk k-1 overlap."""
     if max_bytes is None:
-        max_bytes = int(float(os.environ.get("MPRG_CHUNK_MB", "64")) * (1 << 20))
+        max_bytes = int(float(os.environ.get("MPRG_CHUNK_MB", "256")) * (1 << 20))
     chunks, cur, size = [], [], 0
     for path in input_files:
         try:
