@@ -215,8 +215,8 @@ int mprg_result_row_pool(const mprg_result *res, int32_t locus, int32_t *h_rows)
  * locus of an mprg_msa_set: upper-cased row-major ASCII rows in ONE host buffer (pinned when pin != 0
  * and a device is present) laid out exactly as mprg_build_ascii / mprg_batch_upload take it.  Record
  * ids are the first whitespace token of each title (Biopython).  N replacement (io_utils.py:35-47,
- * seq_utils.py:246-290; Python's random.Random) stays with the caller: loci holding N carry
- * MPRG_LOAD_FLAG_HAS_N and their rows can be rewritten in place through the h_ascii pointer. */
+ * seq_utils.py:246-290) is done by the loader, bit for bit as the reference's sha256-seeded
+ * random.Random does it (mprg_replace_n); loci that held N carry MPRG_LOAD_FLAG_HAS_N. */
 #define MPRG_LOAD_OK 0
 #define MPRG_LOAD_NO_RECORDS 1 /* ValueError("No records found in handle") => EmptyMSAError */
 #define MPRG_LOAD_RAGGED 2     /* ValueError("Sequences must all be the same length") */
@@ -224,6 +224,8 @@ int mprg_result_row_pool(const mprg_result *res, int32_t locus, int32_t *h_rows)
 #define MPRG_LOAD_NOT_ASCII 4  /* bytes >= 0x80: left to the caller's text decoder */
 #define MPRG_LOAD_FLAG_HAS_N 1
 typedef struct mprg_msa_set mprg_msa_set;
+/* N replacement alone on one upper-cased row-major matrix, in place */
+int mprg_replace_n(uint8_t *h_ascii, int32_t n_rows, int32_t n_cols);
 int mprg_fasta_load(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t pin,
                     mprg_msa_set **out);
 void mprg_fasta_free(mprg_msa_set *set);

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mprg_result_row_pool_size": (I64, [P, I32]),
     "mprg_result_row_pool": (C.c_int, [P, I32, P]),
     "mprg_result_from_prgs": (C.c_int, [P, P, I32, C.POINTER(P)]),
+    "mprg_replace_n": (C.c_int, [P, I32, I32]),
     "mprg_fasta_load": (C.c_int, [P, I32, I32, I32, C.POINTER(P)]),
     "mprg_fasta_free": (None, [P]),
     "mprg_fasta_info": (C.c_int, [P, C.POINTER(I32), C.POINTER(P), C.POINTER(I64), C.POINTER(P), C.POINTER(P),

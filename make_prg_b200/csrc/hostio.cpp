@@ -305,6 +305,228 @@ __attribute__((target("avx2"))) const uint8_t *copy_record_avx2(const uint8_t *s
     return copy_record_scalar(s, end, w, bits);
 }
 
+// ------------------------------------------------------------------------------------------------
+// N replacement (io_utils.py:35-47, seq_utils.py:246-290): every N becomes the majority symbol of its
+// column among the non-gap, non-N symbols; ties and empty columns are resolved by a private
+// random.Random seeded with sha256 of the concatenated rows, one `choice` per column in column order.
+// CPython's random.seed(bytes) (version 2) and random.choice are restated here: SHA-256 / SHA-512,
+// MT19937 init_by_array, getrandbits-based _randbelow.
+// ------------------------------------------------------------------------------------------------
+struct Sha256 {
+    uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    static inline uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+    void block(const uint8_t *p) {
+        static const uint32_t K[64] = {
+            0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+            0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+            0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+            0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+            0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+            0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+            0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+            0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+        uint32_t w[64];
+        for (int i = 0; i < 16; ++i)
+            w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | p[4 * i + 3];
+        for (int i = 16; i < 64; ++i) {
+            const uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+            const uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+        for (int i = 0; i < 64; ++i) {
+            const uint32_t t1 = hh + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+            const uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+    void digest(const uint8_t *data, uint64_t n, uint8_t out[32]) {
+        uint64_t i = 0;
+        for (; i + 64 <= n; i += 64) block(data + i);
+        uint8_t tail[128] = {0};
+        const uint64_t rem = n - i;
+        memcpy(tail, data + i, (size_t)rem);
+        tail[rem] = 0x80;
+        const size_t total = rem + 9 <= 64 ? 64 : 128;
+        const uint64_t bits = n * 8;
+        for (int k = 0; k < 8; ++k) tail[total - 1 - k] = (uint8_t)(bits >> (8 * k));
+        block(tail);
+        if (total == 128) block(tail + 64);
+        for (int k = 0; k < 8; ++k)
+            for (int j = 0; j < 4; ++j) out[4 * k + j] = (uint8_t)(h[k] >> (24 - 8 * j));
+    }
+};
+
+struct Sha512 {
+    uint64_t h[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
+                     0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
+    static inline uint64_t rotr(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+    void block(const uint8_t *p) {
+        static const uint64_t K[80] = {
+            0x428a2f98d728ae22ull, 0x7137449123ef65cdull, 0xb5c0fbcfec4d3b2full, 0xe9b5dba58189dbbcull, 0x3956c25bf348b538ull,
+            0x59f111f1b605d019ull, 0x923f82a4af194f9bull, 0xab1c5ed5da6d8118ull, 0xd807aa98a3030242ull, 0x12835b0145706fbeull,
+            0x243185be4ee4b28cull, 0x550c7dc3d5ffb4e2ull, 0x72be5d74f27b896full, 0x80deb1fe3b1696b1ull, 0x9bdc06a725c71235ull,
+            0xc19bf174cf692694ull, 0xe49b69c19ef14ad2ull, 0xefbe4786384f25e3ull, 0x0fc19dc68b8cd5b5ull, 0x240ca1cc77ac9c65ull,
+            0x2de92c6f592b0275ull, 0x4a7484aa6ea6e483ull, 0x5cb0a9dcbd41fbd4ull, 0x76f988da831153b5ull, 0x983e5152ee66dfabull,
+            0xa831c66d2db43210ull, 0xb00327c898fb213full, 0xbf597fc7beef0ee4ull, 0xc6e00bf33da88fc2ull, 0xd5a79147930aa725ull,
+            0x06ca6351e003826full, 0x142929670a0e6e70ull, 0x27b70a8546d22ffcull, 0x2e1b21385c26c926ull, 0x4d2c6dfc5ac42aedull,
+            0x53380d139d95b3dfull, 0x650a73548baf63deull, 0x766a0abb3c77b2a8ull, 0x81c2c92e47edaee6ull, 0x92722c851482353bull,
+            0xa2bfe8a14cf10364ull, 0xa81a664bbc423001ull, 0xc24b8b70d0f89791ull, 0xc76c51a30654be30ull, 0xd192e819d6ef5218ull,
+            0xd69906245565a910ull, 0xf40e35855771202aull, 0x106aa07032bbd1b8ull, 0x19a4c116b8d2d0c8ull, 0x1e376c085141ab53ull,
+            0x2748774cdf8eeb99ull, 0x34b0bcb5e19b48a8ull, 0x391c0cb3c5c95a63ull, 0x4ed8aa4ae3418acbull, 0x5b9cca4f7763e373ull,
+            0x682e6ff3d6b2b8a3ull, 0x748f82ee5defb2fcull, 0x78a5636f43172f60ull, 0x84c87814a1f0ab72ull, 0x8cc702081a6439ecull,
+            0x90befffa23631e28ull, 0xa4506cebde82bde9ull, 0xbef9a3f7b2c67915ull, 0xc67178f2e372532bull, 0xca273eceea26619cull,
+            0xd186b8c721c0c207ull, 0xeada7dd6cde0eb1eull, 0xf57d4f7fee6ed178ull, 0x06f067aa72176fbaull, 0x0a637dc5a2c898a6ull,
+            0x113f9804bef90daeull, 0x1b710b35131c471bull, 0x28db77f523047d84ull, 0x32caab7b40c72493ull, 0x3c9ebe0a15c9bebcull,
+            0x431d67c49c100d4cull, 0x4cc5d4becb3e42b6ull, 0x597f299cfc657e2aull, 0x5fcb6fab3ad6faecull, 0x6c44198c4a475817ull};
+        uint64_t w[80];
+        for (int i = 0; i < 16; ++i) {
+            w[i] = 0;
+            for (int j = 0; j < 8; ++j) w[i] = (w[i] << 8) | p[8 * i + j];
+        }
+        for (int i = 16; i < 80; ++i) {
+            const uint64_t s0 = rotr(w[i - 15], 1) ^ rotr(w[i - 15], 8) ^ (w[i - 15] >> 7);
+            const uint64_t s1 = rotr(w[i - 2], 19) ^ rotr(w[i - 2], 61) ^ (w[i - 2] >> 6);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        uint64_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+        for (int i = 0; i < 80; ++i) {
+            const uint64_t t1 = hh + (rotr(e, 14) ^ rotr(e, 18) ^ rotr(e, 41)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+            const uint64_t t2 = (rotr(a, 28) ^ rotr(a, 34) ^ rotr(a, 39)) + ((a & b) ^ (a & c) ^ (b & c));
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+    void digest_short(const uint8_t *data, size_t n, uint8_t out[64]) {  // n <= 111: one block
+        uint8_t blk[128] = {0};
+        memcpy(blk, data, n);
+        blk[n] = 0x80;
+        const uint64_t bits = (uint64_t)n * 8;
+        for (int k = 0; k < 8; ++k) blk[127 - k] = (uint8_t)(bits >> (8 * k));
+        block(blk);
+        for (int k = 0; k < 8; ++k)
+            for (int j = 0; j < 8; ++j) out[8 * k + j] = (uint8_t)(h[k] >> (56 - 8 * j));
+    }
+};
+
+struct PyRandom {  // CPython's _random.Random (MT19937)
+    uint32_t mt[624];
+    int idx = 624;
+    void init_genrand(uint32_t s) {
+        mt[0] = s;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    void init_by_array(const uint32_t *key, size_t len) {
+        init_genrand(19650218u);
+        size_t i = 1, j = 0;
+        for (size_t k = std::max<size_t>(624, len); k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+            if (++i >= 624) {
+                mt[0] = mt[623];
+                i = 1;
+            }
+            if (++j >= len) j = 0;
+        }
+        for (size_t k = 623; k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+            if (++i >= 624) {
+                mt[0] = mt[623];
+                i = 1;
+            }
+        }
+        mt[0] = 0x80000000u;
+    }
+    // random.seed(a: bytes), version 2: the integer int.from_bytes(a + sha512(a).digest(), "big")
+    void seed_bytes(const uint8_t *a, size_t n) {  // n <= 47
+        uint8_t big[47 + 64];
+        memcpy(big, a, n);
+        Sha512().digest_short(a, n, big + n);
+        const size_t total = n + 64;
+        size_t lead = 0;
+        while (lead < total && big[lead] == 0) ++lead;
+        const size_t nbytes = total - lead;
+        size_t words = std::max<size_t>(1, (nbytes + 3) / 4);
+        std::vector<uint32_t> key(words, 0u);
+        for (size_t k = 0; k < nbytes; ++k) key[k / 4] |= (uint32_t)big[total - 1 - k] << (8 * (k % 4));
+        init_by_array(key.data(), words);
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            static const uint32_t mag01[2] = {0u, 0x9908b0dfu};
+            int kk = 0;
+            for (; kk < 624 - 397; ++kk) {
+                const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + 397] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            for (; kk < 623; ++kk) {
+                const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            const uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+            mt[623] = mt[396] ^ (y >> 1) ^ mag01[y & 1u];
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    uint32_t randbelow(uint32_t n) {  // Random._randbelow_with_getrandbits, n in [1, 2^31)
+        const int k = 32 - __builtin_clz(n);
+        uint32_t r = next() >> (32 - k);
+        while (r >= n) r = next() >> (32 - k);
+        return r;
+    }
+};
+
+void replace_n(uint8_t *m, int64_t n_rows, int64_t n_cols) {
+    if (n_rows <= 0 || n_cols <= 0) return;
+    uint8_t digest[32];
+    Sha256().digest(m, (uint64_t)(n_rows * n_cols), digest);
+    PyRandom rng;
+    rng.seed_bytes(digest, 32);
+    std::vector<uint8_t> consensus((size_t)n_cols);
+    constexpr int BLOCK = 32;
+    std::vector<uint32_t> counts((size_t)BLOCK * 256);
+    uint8_t order[BLOCK][256];
+    int n_order[BLOCK];
+    for (int64_t c0 = 0; c0 < n_cols; c0 += BLOCK) {
+        const int w = (int)std::min<int64_t>(BLOCK, n_cols - c0);
+        std::fill(counts.begin(), counts.end(), 0u);
+        for (int b = 0; b < w; ++b) n_order[b] = 0;
+        for (int64_t r = 0; r < n_rows; ++r) {
+            const uint8_t *row = m + r * n_cols + c0;
+            for (int b = 0; b < w; ++b) {
+                const uint8_t ch = row[b];
+                if (ch == '-' || ch == 'N') continue;
+                if (counts[(size_t)b * 256 + ch]++ == 0) order[b][n_order[b]++] = ch;  // Counter keeps first-seen order
+            }
+        }
+        for (int b = 0; b < w; ++b) {
+            if (n_order[b] == 0) {
+                consensus[(size_t)(c0 + b)] = (uint8_t)"ACGT"[rng.randbelow(4)];
+                continue;
+            }
+            uint32_t top = 0;
+            for (int k = 0; k < n_order[b]; ++k) top = std::max(top, counts[(size_t)b * 256 + order[b][k]]);
+            uint8_t cand[256];
+            uint32_t n_cand = 0;
+            for (int k = 0; k < n_order[b]; ++k)
+                if (counts[(size_t)b * 256 + order[b][k]] == top) cand[n_cand++] = order[b][k];
+            consensus[(size_t)(c0 + b)] = cand[rng.randbelow(n_cand)];
+        }
+    }
+    for (int64_t r = 0; r < n_rows; ++r) {
+        uint8_t *row = m + r * n_cols;
+        for (int64_t c = 0; c < n_cols; ++c)
+            if (row[c] == 'N') row[c] = consensus[(size_t)c];
+    }
+}
+
 // Mirrors make_prg_b200.utils.io_utils.parse_fasta + the upper-casing of load_alignment_file.
 void parse_file(const char *path, ParsedFile &pf, bool avx2, Slab &slab) {
     static thread_local std::vector<uint8_t> raw;  // reused by the files of one thread: no fresh pages
@@ -362,10 +584,19 @@ void parse_file(const char *path, ParsedFile &pf, bool avx2, Slab &slab) {
     pf.n_cols = (int32_t)first_len;
     pf.matrix_bytes = (int64_t)pf.n_rows * first_len;
     if (first_len > INT32_MAX) pf.status = MPRG_LOAD_IO_ERROR;
-    if (bits & 2) pf.flags |= MPRG_LOAD_FLAG_HAS_N;
+    if ((bits & 2) && pf.status == MPRG_LOAD_OK) {
+        pf.flags |= MPRG_LOAD_FLAG_HAS_N;
+        replace_n(pf.buf, pf.n_rows, pf.n_cols);
+    }
 }
 
 }  // namespace
+
+extern "C" int mprg_replace_n(uint8_t *h_ascii, int32_t n_rows, int32_t n_cols) {
+    if (!h_ascii || n_rows < 0 || n_cols < 0) return MPRG_E_BAD_ARG;
+    replace_n(h_ascii, n_rows, n_cols);
+    return MPRG_OK;
+}
 
 struct mprg_msa_set {
     int32_t n = 0;

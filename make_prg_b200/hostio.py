@@ -101,9 +101,17 @@ class MsaSet:
             pass
 
 
+def replace_n(matrix):
+    """io_utils.py:35-47 on an upper-cased uint8 matrix, in place, by the library (mprg_replace_n)."""
+    assert matrix.dtype == np.uint8 and matrix.flags["C_CONTIGUOUS"]
+    rc = _lib.load().mprg_replace_n(ptr(matrix), matrix.shape[0], matrix.shape[1])
+    if rc != 0:
+        raise MprgError(rc, "mprg_replace_n failed")
+
+
 def replace_n_in_place(matrix):
-    """io_utils.py:35-47 on a uint8 matrix: every N becomes the column's majority symbol, drawn with
-    the reference's sha256-seeded random.Random (one `choice` per column, in column order)."""
+    """The same through the Python mirror (random.Random itself): every N becomes the column's majority
+    symbol, one `choice` per column in column order.  Kept as the checker of mprg_replace_n."""
     seqs = [row.tobytes().decode("ascii") for row in matrix]
     consensus = io_utils.majority_consensus_of_rows(seqs)
     cons = np.frombuffer(consensus.encode("ascii"), np.uint8)
@@ -112,8 +120,8 @@ def replace_n_in_place(matrix):
 
 
 def load_fasta_files(paths, threads=None, pin=True):
-    """Parses every file on host threads.  Loci whose status is not LOAD_OK are left to the caller
-    (`raise_for_load_status` re-creates the reference's exception); N is replaced in place."""
+    """Parses every file on host threads (N replaced by the loader).  Loci whose status is not LOAD_OK
+    are left to the caller (`raise_for_load_status` re-creates the reference's exception)."""
     lib = _lib.load()
     arr, _keep = _c_strings([os.fspath(p) for p in paths])
     h = C.c_void_p()
@@ -121,11 +129,7 @@ def load_fasta_files(paths, threads=None, pin=True):
                              C.byref(h))
     if rc != 0:
         raise MprgError(rc, "mprg_fasta_load failed")
-    msas = MsaSet(h, paths)
-    for i in np.nonzero((msas.flags & FLAG_HAS_N) != 0)[0]:
-        if msas.status[i] == LOAD_OK:
-            replace_n_in_place(msas.matrix(int(i)))
-    return msas
+    return MsaSet(h, paths)
 
 
 def raise_for_load_status(msas, locus):

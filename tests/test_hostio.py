@@ -214,3 +214,21 @@ def test_writer_many_entries_zip64(tmp_path):
     with zipfile.ZipFile(tmp_path / "big.prg.bin.zip") as z:
         assert len(z.namelist()) == n
         assert z.read("locus65999.bin") == np.array([1, 5, 2, 6, 3, 6, 4], "<u4").tobytes()
+
+
+def test_native_n_replacement_equals_python_random():
+    rng = np.random.default_rng(11)
+    alphabet = np.frombuffer(b"ACGTACGTACGT--NNRYKMSW", np.uint8)
+    for k in range(40):
+        rows, cols = int(rng.integers(1, 30)), int(rng.integers(1, 400))
+        M = rng.choice(alphabet, size=(rows, cols))
+        if k % 5 == 0:
+            M[:, : cols // 3] = ord("N")  # columns full of N: choice("ACGT")
+        if k % 7 == 0:
+            M[:] = rng.choice(np.frombuffer(b"AC", np.uint8), size=(rows, cols))  # ties everywhere
+            M[0, 0] = ord("N")
+        a, b = M.copy(), M.copy()
+        hostio.replace_n(a)
+        hostio.replace_n_in_place(b)
+        assert np.array_equal(a, b), k
+        assert ord("N") not in a
