@@ -109,7 +109,7 @@ extern "C" int mprg_create(int device_ordinal, mprg_ctx **out) {
         if (n >= 1 && n <= 64) ctx->n_workers = n;
     } else {
         const unsigned hc = std::thread::hardware_concurrency();
-        ctx->n_workers = (int)std::max(1u, std::min(4u, hc ? hc / 2 : 1u));  // more is faster on a quiet host but stalls on a shared one
+        ctx->n_workers = (int)std::max(1u, std::min(8u, hc ? hc / 2 : 1u));  // more is faster on a quiet host but stalls on a shared one
     }
     *out = ctx;
     return MPRG_OK;

@@ -9,6 +9,7 @@
 // The host only keeps the tree bookkeeping (nodes, row subsets, child tasks), the cluster-merge
 // ordering rules and the string assembly.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -51,7 +52,7 @@ struct PhaseTrace {
         for (auto &p : acc) fprintf(stderr, "    %-28s %8.2f ms\n", p.first.c_str(), p.second);
     }
 };
-static PhaseTrace *g_trace = nullptr;
+static thread_local PhaseTrace *g_trace = nullptr;
 #define TRACE(name) do { if (g_trace) g_trace->mark(name); } while (0)
 
 // ---- MT19937 as numpy's RandomState(seed) / random_sample ---------------------------------------
@@ -187,6 +188,35 @@ static void clusters_from_rows(const ClusterOut &o, int kmer_size, std::vector<s
     out.push_back(std::move(first));
     for (size_t a = 0; a < cl.size(); ++a)
         if (a != fi) out.push_back(std::move(cl[a]));
+}
+
+// The same partition as clusters_from_rows, as one cluster index per row (cluster 0 holds row 0, the
+// others keep the order of ClusteringResult.clustered_ids); no per-cluster row lists are built.  The
+// order of the rows inside a cluster is not represented: sub-alignments keep the input row order
+// (recursion_tree.py:558-572).  Returns the number of clusters.
+static int cluster_of_rows(const ClusterOut &o, int kmer_size, std::vector<int> &index_of_group,
+                           std::vector<int> &cluster_of_row) {
+    const int R = (int)o.group.size();
+    cluster_of_row.resize(R);
+    if (o.no_clustering) {
+        std::fill(cluster_of_row.begin(), cluster_of_row.end(), 0);
+        return R > 0 ? 1 : 0;
+    }
+    index_of_group.resize(o.n_ungapped);
+    int n_long = 0, n_small = 0;
+    for (int g = 0; g < o.n_ungapped; ++g) {
+        if (o.leader_len[g] >= kmer_size) index_of_group[g] = o.assign[n_long++];
+        else index_of_group[g] = o.n_labels + n_small++;
+    }
+    const int n_cl = o.n_labels + n_small;
+    // the cluster of row 0 moves to the front (merge_clusters), the others keep their order
+    const int first = R > 0 ? index_of_group[o.group[0]] : 0;
+    for (int g = 0; g < o.n_ungapped; ++g) {
+        const int c = index_of_group[g];
+        index_of_group[g] = c == first ? 0 : (c < first ? c + 1 : c);
+    }
+    for (int r = 0; r < R; ++r) cluster_of_row[r] = index_of_group[o.group[r]];
+    return n_cl;
 }
 
 // Runs kmeans_cluster_seqs for every task of a level.
@@ -480,10 +510,10 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
             kmd_total += kmeans_dscratch_doubles(st[q].n, st[q].F);
             kmi_total += kmeans_iscratch_ints(st[q].n);
         }
-        {
+        const double want = 8.0 * (double)x_total + 8.0 * (double)kmd_total + 4.0 * (double)kmi_total;
+        if (want > 1e9) {  // cudaMemGetInfo is a slow, serialising driver call: only deep loci ask
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
-            const double want = 8.0 * (double)x_total + 8.0 * (double)kmd_total + 4.0 * (double)kmi_total;
             const double have = (double)free_b + (double)B[12].cap + (double)B[15].cap;
             if (want > 0.9 * have)
                 MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "k-mer count matrices and KMeans scratch of this level do not fit in device memory");
@@ -940,7 +970,8 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
     std::vector<mprg_task> tasks;
     std::vector<int32_t> arena;
     PhaseTrace trace;
-    if (allow_trace) g_trace = trace.on ? &trace : nullptr;
+    const bool trace_all = getenv("MPRG_TRACE_ALL") != nullptr;
+    if (allow_trace || trace_all) g_trace = trace.on ? &trace : nullptr;
     while (!pending.empty()) {
         const int nt = (int)pending.size();
         tasks.resize(nt);
@@ -1042,7 +1073,7 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
                                min_match_length, want.data(), nullptr, true, cout_, true);
             if (rc != MPRG_OK) return fail(rc);
             TRACE("cl: finalize");
-            std::vector<std::vector<int>> clusters;
+            std::vector<int> index_of_group, cl_of_row, cl_count, cl_start;
             for (int q = 0; q < nc; ++q) {
                 const int i = cluster_idx[q];
                 const int l = pending[i].locus, ni = pending[i].node;
@@ -1055,19 +1086,42 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
                     return nd.row_off < 0 ? pos : L.row_pool[nd.row_off + pos];
                 };
                 if (further) {
-                    clusters_from_rows(o, min_match_length, clusters);
+                    // counting sort of the rows by cluster: every child keeps the input row order
+                    const int n_cl = cluster_of_rows(o, min_match_length, index_of_group, cl_of_row);
+                    const int R = (int)cl_of_row.size();
+                    cl_count.assign(n_cl, 0);
+                    for (int r = 0; r < R; ++r) cl_count[cl_of_row[r]]++;
+                    cl_start.resize(n_cl);
+                    const long long pool0 = (long long)L.row_pool.size();
+                    long long at = pool0;
+                    for (int c = 0; c < n_cl; ++c) {
+                        cl_start[c] = (int)(at - pool0);
+                        at += cl_count[c];
+                    }
+                    L.row_pool.resize((size_t)at);
+                    {
+                        const HNode &nd = L.nodes[ni];
+                        int *dst = L.row_pool.data() + pool0;
+                        if (nd.row_off < 0) {
+                            for (int r = 0; r < R; ++r) dst[cl_start[cl_of_row[r]]++] = r;
+                        } else {
+                            const int *src = L.row_pool.data() + nd.row_off;
+                            for (int r = 0; r < R; ++r) dst[cl_start[cl_of_row[r]]++] = src[r];
+                        }
+                    }
                     L.nodes[ni].kind = MPRG_NODE_CLUSTER;
                     L.nodes[ni].level += 1;
-                    for (std::vector<int> &pos : clusters) {
-                        std::sort(pos.begin(), pos.end());  // sub-alignments keep the input row order
+                    long long off = pool0;
+                    for (int c = 0; c < n_cl; ++c) {
+                        if (cl_count[c] == 0) continue;
                         HNode ch;
                         ch.parent = ni;
                         ch.level = L.nodes[ni].level;
                         ch.c0 = L.nodes[ni].c0;
                         ch.c1 = L.nodes[ni].c1;
-                        ch.row_off = (long long)L.row_pool.size();
-                        ch.n_rows = (int)pos.size();
-                        for (int p : pos) L.row_pool.push_back(row_id(p));
+                        ch.row_off = off;
+                        ch.n_rows = cl_count[c];
+                        off += cl_count[c];
                         const int ci = (int)L.nodes.size();
                         L.nodes.push_back(ch);
                         L.nodes[ni].children.push_back(ci);
@@ -1221,7 +1275,7 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
         }
     }
     TRACE("build: prg strings");
-    if (allow_trace) {
+    if (allow_trace || trace_all) {
         trace.report("mprg_build");
         g_trace = nullptr;
     }
@@ -1279,7 +1333,13 @@ static int build_ranges(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, i
     }
     // contiguous ranges of roughly equal rows x cols, dealt round-robin; from host ASCII there are
     // two ranges per worker, so that copies (one range at a time) and kernels stay overlapped
-    const int R = h_ascii ? std::max(W, std::min(2 * W, n_loci / 8)) : W;
+    static const int ranges_per_worker = []() {
+        const char *e = getenv("MPRG_RANGES_PER_WORKER");
+        return e ? std::max(1, atoi(e)) : 0;
+    }();
+    static const bool dynamic = getenv("MPRG_DYNAMIC_RANGES") != nullptr;
+    const int rpw = ranges_per_worker ? ranges_per_worker : 1;  // sweeps: profiles/r1_ranges_sweep.txt
+    const int R = std::max(W, std::min(rpw * W, n_loci / 8));
     std::vector<double> prefix(n_loci + 1, 0.0);
     for (int l = 0; l < n_loci; ++l) prefix[l + 1] = prefix[l] + (double)batch->n_rows[l] * batch->n_cols[l] + 1.0;
     std::vector<int> cut(R + 1, n_loci);
@@ -1292,8 +1352,10 @@ static int build_ranges(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, i
     std::vector<int> rcs(W, MPRG_OK);
     // range r always goes to worker r % W: the same worker sees the same loci on every call, so its
     // scratch buffers stop growing after the first call (a reallocation synchronises the device)
+    std::atomic<int> next_range{0};
     auto work = [&](mprg_ctx *c, int w) {
-        for (int r = w; r < R; r += W) {
+        // static: range r goes to worker r % W; dynamic: the next range goes to whichever worker is free
+        for (int r = dynamic ? next_range.fetch_add(1) : w; r < R; r = dynamic ? next_range.fetch_add(1) : r + W) {
             const int rc_r = run(c, cut[r], cut[r + 1], false);
             if (rc_r != MPRG_OK) {
                 rcs[w] = rc_r;
