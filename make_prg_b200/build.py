@@ -37,16 +37,19 @@ def needs_build():
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not needs_build():
+def build_library(force=False, verbose=False, extra_flags=(), lib_out=None):
+    """extra_flags / lib_out: experiment builds (e.g. -DMPRG_SCAN_MIN_BLOCKS=8 into libmprg_x.so, picked up
+    through the MPRG_LIB environment variable); the default build is what ships."""
+    variant = bool(extra_flags) or lib_out is not None
+    if not variant and not force and not needs_build():
         return LIB
-    objdir = CSRC / "build"
+    objdir = CSRC / ("build_variant" if variant else "build")
     objdir.mkdir(exist_ok=True)
     objs = []
     procs = []
     for src, stem, flags in compile_units():
         obj = objdir / (stem + ".o")
-        cmd = [NVCC, *ARCH, *COMMON, *flags, "-c", str(src), "-o", str(obj)]
+        cmd = [NVCC, *ARCH, *COMMON, *flags, *extra_flags, "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((stem, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -61,10 +64,14 @@ def build_library(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("libmprg build failed")
-    cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *objs, "-lz"]
+    lib = Path(lib_out) if lib_out is not None else LIB
+    cmd = [NVCC, *ARCH, "-shared", "-o", str(lib), *objs, "-lz"]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[len("--out="):] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_flags=extra,
+                        lib_out=outs[0] if outs else None))

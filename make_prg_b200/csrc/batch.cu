@@ -126,6 +126,8 @@ extern "C" void mprg_destroy(mprg_ctx *ctx) {
                       &ctx->d_stage};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : ctx->d_c) b.release();
+    for (auto &a : ctx->idle_arenas) cudaFree(a.first);
+    ctx->idle_arenas.clear();
     ctx->h_a.release();
     ctx->h_b.release();
     ctx->h_c.release();
@@ -188,7 +190,23 @@ int batch_prepare(mprg_ctx *ctx, const int32_t *n_rows, const int32_t *n_cols, i
         packed += (long long)b->stride[l] * n_rows[l];
     }
     b->packed_bytes = packed;
-    const cudaError_t e = cudaMalloc(&b->d_packed, (size_t)packed + 16);
+    const size_t need = (size_t)packed + 16;
+    {
+        std::lock_guard<std::mutex> lock(ctx->arena_mutex);
+        int best = -1;
+        for (int i = 0; i < (int)ctx->idle_arenas.size(); ++i)
+            if (ctx->idle_arenas[i].second >= need && (best < 0 || ctx->idle_arenas[i].second < ctx->idle_arenas[best].second))
+                best = i;
+        if (best >= 0 && ctx->idle_arenas[best].second <= 2 * need + ((size_t)64 << 20)) {
+            b->d_packed = ctx->idle_arenas[best].first;
+            b->packed_capacity = ctx->idle_arenas[best].second;
+            ctx->idle_arenas.erase(ctx->idle_arenas.begin() + best);
+            *out = b;
+            return MPRG_OK;
+        }
+    }
+    b->packed_capacity = need + need / 16;
+    const cudaError_t e = cudaMalloc(&b->d_packed, b->packed_capacity);
     if (e != cudaSuccess) {
         ctx->err = std::string("cudaMalloc packed: ") + cudaGetErrorString(e);
         delete b;
@@ -290,6 +308,14 @@ extern "C" int mprg_batch_upload(mprg_ctx *ctx, const uint8_t *h_ascii, const in
 extern "C" void mprg_batch_free(mprg_ctx *ctx, mprg_batch *batch) {
     if (!batch) return;
     if (ctx) cudaSetDevice(ctx->device);
+    if (batch->d_packed && ctx && batch->packed_capacity <= ((size_t)8 << 30)) {
+        // every launch that read the arena has been waited for (mprg_build returns host results)
+        std::lock_guard<std::mutex> lock(ctx->arena_mutex);
+        if (ctx->idle_arenas.size() < 2) {
+            ctx->idle_arenas.emplace_back(batch->d_packed, batch->packed_capacity);
+            batch->d_packed = nullptr;
+        }
+    }
     if (batch->d_packed) cudaFree(batch->d_packed);
     delete batch;
 }

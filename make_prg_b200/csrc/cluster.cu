@@ -31,7 +31,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 }
 
 // ---- unpack -------------------------------------------------------------------------------------
-// one CTA per task, warps over rows, lanes over columns
+// one CTA (or, for deep tasks, gridDim.y CTAs) per task, warps over rows, lanes over columns
 __global__ void __launch_bounds__(256)
 unpack_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks,
               const int *__restrict__ rows_arena, const long long *__restrict__ g_off,
@@ -41,7 +41,7 @@ unpack_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ task
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int *rows = t.rows_off >= 0 ? rows_arena + t.rows_off : nullptr;
     uint8_t *out = G + g_off[blockIdx.x];
-    for (int r = warp; r < t.n_rows; r += nw) {
+    for (int r = warp + nw * blockIdx.y; r < t.n_rows; r += nw * gridDim.y) {
         const uint8_t *row = packed + t.base + (long long)(rows ? rows[r] : r) * t.stride;
         for (int i = lane; i < w; i += 32) out[(long long)r * w + i] = (uint8_t)sym_of(row, t.c0 + i);
     }
@@ -181,6 +181,137 @@ __device__ int block_exclusive_scan(int *a, int n, int *s_warp /* >= 33 ints */)
         __syncthreads();
     }
     return carry;
+}
+
+// ---- dedupe of deep tasks -------------------------------------------------------------------------
+// The same outputs as dedupe_kernel from four launches that spread every task over the grid (one CTA
+// per task is the wrong shape for a 10,000 x 20,000 task): signatures with one warp per row (the hashes
+// are sums of mixed (position, symbol) words, so the lanes of a warp add up their columns in any order;
+// the ungapped sequence of the row is compacted next to it for the exact check), first-seen search
+// with one thread per row, exact verification of every merge with one warp per row, and the
+// first-seen numbering of the distinct rows by a block-wide prefix sum.
+constexpr uint64_t SALT_U = 0x9e3779b97f4a7c15ULL, SALT_G = 0x2545f4914f6cdd1dULL;
+
+__global__ void __launch_bounds__(256)
+dedupe_big_sig_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ g_off,
+                      const uint8_t *__restrict__ G, const long long *__restrict__ row_off,
+                      RowSig *__restrict__ sig, int *__restrict__ ulen, uint8_t *__restrict__ U) {
+    const int ti = blockIdx.y;
+    const DTask t = tasks[ti];
+    const int w = t.c1 - t.c0, R = t.n_rows;
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < R; r += gridDim.x * 8) {  // warp-uniform
+        const uint8_t *row = G + g_off[ti] + (long long)r * w;
+        uint8_t *urow = U + g_off[ti] + (long long)r * w;
+        uint64_t hu = 0, hg = 0;
+        int base = 0;
+        for (int i0 = 0; i0 < w; i0 += 32) {
+            const int i = i0 + lane;
+            const bool in = i < w;
+            const uint32_t c = in ? row[i] : (uint32_t)SYM_GAP;
+            if (in) hg += mix64((((uint64_t)i << 8) | c) ^ SALT_G);
+            const bool solid = in && c != SYM_GAP;
+            const uint32_t m = __ballot_sync(0xffffffffu, solid);
+            if (solid) {
+                const int u = base + __popc(m & ((1u << lane) - 1u));
+                hu += mix64((((uint64_t)u << 8) | c) ^ SALT_U);
+                urow[u] = (uint8_t)c;
+            }
+            base += __popc(m);
+        }
+        for (int d = 16; d; d >>= 1) {
+            hu += __shfl_xor_sync(0xffffffffu, hu, d);
+            hg += __shfl_xor_sync(0xffffffffu, hg, d);
+        }
+        if (lane == 0) {
+            sig[row_off[ti] + r] = RowSig{mix64(hu ^ SALT_U), mix64(hg ^ SALT_G), base, 0};
+            ulen[row_off[ti] + r] = base;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dedupe_big_match_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ row_off,
+                        const RowSig *__restrict__ sig, int *__restrict__ leader_u, int *__restrict__ leader_g) {
+    const int ti = blockIdx.y;
+    const int R = tasks[ti].n_rows;
+    const long long ro = row_off[ti];
+    const RowSig *s = sig + ro;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+        const RowSig me = s[r];
+        int a = r, b = r;
+        for (int q = 0; q < r; ++q) {
+            const RowSig o = s[q];
+            if (a == r && o.hu == me.hu && o.len == me.len) a = q;
+            if (b == r && o.hg == me.hg) b = q;
+            if (a != r && b != r) break;
+        }
+        leader_u[ro + r] = a;
+        leader_g[ro + r] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dedupe_big_verify_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ g_off,
+                         const uint8_t *__restrict__ G, const uint8_t *__restrict__ U,
+                         const long long *__restrict__ row_off, const int *__restrict__ leader_u,
+                         const int *__restrict__ leader_g, const int *__restrict__ ulen, int *__restrict__ err) {
+    const int ti = blockIdx.y;
+    const DTask t = tasks[ti];
+    const int w = t.c1 - t.c0, R = t.n_rows;
+    const int lane = threadIdx.x & 31;
+    const long long ro = row_off[ti];
+    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < R; r += gridDim.x * 8) {
+        const int a = leader_u[ro + r], b = leader_g[ro + r];
+        bool bad = false;
+        if (a != r) {
+            const int len = ulen[ro + r];
+            const uint8_t *x = U + g_off[ti] + (long long)a * w, *y = U + g_off[ti] + (long long)r * w;
+            bad |= ulen[ro + a] != len;
+            for (int i = lane; i < len && !bad; i += 32) bad |= x[i] != y[i];
+        }
+        if (b != r) {
+            const uint8_t *x = G + g_off[ti] + (long long)b * w, *y = G + g_off[ti] + (long long)r * w;
+            for (int i = lane; i < w && !bad; i += 32) bad |= x[i] != y[i];
+        }
+        if (bad) atomicExch(err, 2);  // hash equality is only a filter: a false merge fails the call
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dedupe_big_number_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ row_off,
+                         const int *__restrict__ leader_u, const int *__restrict__ leader_g,
+                         const int *__restrict__ ulen, int *__restrict__ group, int *__restrict__ leaders,
+                         int *__restrict__ leader_len, int *__restrict__ n_ungapped, int *__restrict__ n_gapped) {
+    __shared__ int s_warp[33];
+    __shared__ int s_ng;
+    const int ti = blockIdx.x;
+    const int R = tasks[ti].n_rows;
+    const long long ro = row_off[ti];
+    if (threadIdx.x == 0) s_ng = 0;
+    int ng = 0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        group[ro + r] = leader_u[ro + r] == r ? 1 : 0;
+        ng += leader_g[ro + r] == r;
+    }
+    __syncthreads();
+    atomicAdd(&s_ng, ng);
+    const int nu = block_exclusive_scan(group + ro, R, s_warp);  // leaders: their first-seen index
+    for (int r = threadIdx.x; r < R; r += blockDim.x)
+        if (leader_u[ro + r] == r) {
+            leaders[ro + group[ro + r]] = r;
+            leader_len[ro + group[ro + r]] = ulen[ro + r];
+        }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int a = leader_u[ro + r];
+        if (a != r) group[ro + r] = group[ro + a];  // leaders come first (a < r) and are never rewritten
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        n_ungapped[ti] = nu;
+        n_gapped[ti] = s_ng;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -756,9 +887,27 @@ cudaError_t launch_members(cudaStream_t s, const MemberProb *probs, int n, const
 }
 
 cudaError_t launch_unpack(cudaStream_t s, const uint8_t *packed, const DTask *d_tasks, int n_tasks,
-                          const int *d_rows, const long long *g_off, uint8_t *G) {
+                          const int *d_rows, const long long *g_off, uint8_t *G, int row_split) {
     if (n_tasks <= 0) return cudaSuccess;
-    unpack_kernel<<<n_tasks, 256, 0, s>>>(packed, d_tasks, d_rows, g_off, G);
+    unpack_kernel<<<dim3(n_tasks, std::max(1, std::min(row_split, 4096))), 256, 0, s>>>(packed, d_tasks, d_rows,
+                                                                                     g_off, G);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dedupe_big(cudaStream_t s, const DTask *d_tasks, int n_tasks, int max_rows, const long long *g_off,
+                              const uint8_t *G, uint8_t *U, const long long *row_off, void *sig, int *leader_u,
+                              int *leader_g, int *group, int *ulen, int *leaders, int *leader_len, int *n_ungapped,
+                              int *n_gapped, int *err) {
+    if (n_tasks <= 0 || n_tasks > 65535) return n_tasks <= 0 ? cudaSuccess : cudaErrorInvalidValue;
+    const int by_warp = std::max(1, std::min((max_rows + 7) / 8, 8192));
+    const int by_thread = std::max(1, std::min((max_rows + 255) / 256, 8192));
+    dedupe_big_sig_kernel<<<dim3(by_warp, n_tasks), 256, 0, s>>>(d_tasks, g_off, G, row_off, (RowSig *)sig, ulen, U);
+    dedupe_big_match_kernel<<<dim3(by_thread, n_tasks), 256, 0, s>>>(d_tasks, row_off, (const RowSig *)sig, leader_u,
+                                                                     leader_g);
+    dedupe_big_verify_kernel<<<dim3(by_warp, n_tasks), 256, 0, s>>>(d_tasks, g_off, G, U, row_off, leader_u, leader_g,
+                                                                    ulen, err);
+    dedupe_big_number_kernel<<<n_tasks, 256, 0, s>>>(d_tasks, row_off, leader_u, leader_g, ulen, group, leaders,
+                                                     leader_len, n_ungapped, n_gapped);
     return cudaGetLastError();
 }
 

@@ -131,6 +131,7 @@ struct mprg_batch {
     std::vector<int> flags;       // alphabet flags per locus (host copy)
     long long packed_bytes = 0;
     uint8_t *d_packed = nullptr;
+    size_t packed_capacity = 0;
     std::mutex copy_mutex;  // orders the host-to-device copies of the ranges of mprg_build_ascii
     std::atomic<bool> any_n{false};  // set by whichever upload finds an N; a stale read only picks the slower scan variant
 };
@@ -159,6 +160,10 @@ struct mprg_ctx {
     mprg::DevBuf d_c[16];
     // scratch (pinned host)
     mprg::PinnedBuf h_a, h_b, h_c, h_d;
+    // packed arenas of freed batches, kept for the next batch of about the same size: cudaMalloc and
+    // cudaFree of 100 MB cost more than a millisecond each and cudaFree synchronises the device
+    std::mutex arena_mutex;
+    std::vector<std::pair<uint8_t *, size_t>> idle_arenas;
 };
 
 namespace mprg {

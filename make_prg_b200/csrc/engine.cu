@@ -289,11 +289,28 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
     int *d_R = d_err + 1;
     MPRG_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(int), s));
     MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_R, h_R.data(), sizeof(int) * n_tasks, s));
+    // a level that holds a deep task (config #4: 10,000 x 20,000) spreads every task over the grid
+    long long biggest = 0;
+    int max_rows = 0;
+    for (int i = 0; i < n_tasks; ++i) {
+        biggest = std::max(biggest, (long long)h_R[i] * (tasks[i].c1 - tasks[i].c0));
+        max_rows = std::max(max_rows, h_R[i]);
+    }
+    const bool deep = (biggest >= DEDUPE_BIG_SYMBOLS || getenv("MPRG_FORCE_BIG_DEDUPE")) && n_tasks <= 65535;
     MPRG_CUDA(ctx, launch_unpack(s, batch->d_packed, B[0].as<DTask>(), n_tasks, ctx->d_rows.as<int>(),
-                                 B[1].as<long long>(), B[3].as<uint8_t>()));
-    MPRG_CUDA(ctx, launch_dedupe(s, B[0].as<DTask>(), n_tasks, B[1].as<long long>(), B[3].as<uint8_t>(),
-                                 B[2].as<long long>(), B[4].p, d_leader_u, d_leader_g, d_group, d_ulen,
-                                 d_leaders, d_leadlen, d_nu, d_ng, d_err));
+                                 B[1].as<long long>(), B[3].as<uint8_t>(), deep ? (max_rows + 7) / 8 : 1));
+    if (deep) {
+        MPRG_CUDA(ctx, B[15].reserve((size_t)std::max<long long>(g_total, 1)));  // compacted rows; free again below
+        MPRG_CUDA(ctx, launch_dedupe_big(s, B[0].as<DTask>(), n_tasks, max_rows, B[1].as<long long>(),
+                                         B[3].as<uint8_t>(), B[15].as<uint8_t>(), B[2].as<long long>(), B[4].p,
+                                         d_leader_u, d_leader_g, d_group, d_ulen, d_leaders, d_leadlen, d_nu, d_ng,
+                                         d_err));
+        ctx->launches += 3;
+    } else {
+        MPRG_CUDA(ctx, launch_dedupe(s, B[0].as<DTask>(), n_tasks, B[1].as<long long>(), B[3].as<uint8_t>(),
+                                     B[2].as<long long>(), B[4].p, d_leader_u, d_leader_g, d_group, d_ulen,
+                                     d_leaders, d_leadlen, d_nu, d_ng, d_err));
+    }
     MPRG_CUDA(ctx, launch_scan_counts(s, d_nu, n_tasks, d_leadoff));
     ctx->launches += 3;
     TRACE("cl: setup+launch dedupe");
@@ -1146,10 +1163,12 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
     const int na = (int)alleles.size();
     std::vector<ExtractItem> items(na);
     long long out_total = 0;
+    std::vector<long long> prg_bound((size_t)std::max(l_end - l_begin, 1), 0);
     for (int a = 0; a < na; ++a) {
         const Allele &al = alleles[a];
         items[a] = ExtractItem{batch->base[al.locus], batch->stride[al.locus], al.row, al.c0, al.c1, out_total};
         out_total += al.c1 - al.c0;
+        prg_bound[al.locus - l_begin] += (al.c1 - al.c0) + 12;
     }
     {
         cudaError_t e1 = ctx->h_c.reserve((size_t)std::max<long long>(out_total, 1) + sizeof(int) * (size_t)std::max(na, 1) + 16);
@@ -1188,7 +1207,9 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
     for (int l = l_begin; l < l_end; ++l) {
         LocusResult &L = res->loci[l];
         if (L.status != MPRG_LOCUS_OK) continue;
-        L.prg.reserve((size_t)batch->n_cols[l] * 2 + 64);
+        // upper bound of the string: gapped width of every allele + one marker per allele and node, so
+        // that a 200 MB PRG (deep locus) is not grown by doubling
+        L.prg.reserve((size_t)prg_bound[l - l_begin] + 12 * L.nodes.size() + 64);
         int site = 5;
         struct Frame {
             int node;

@@ -85,8 +85,15 @@ constexpr long long REFCHECK_BIG_SYMBOLS = 1LL << 22;  // rows * width from whic
 constexpr int REFCHECK_FLAG_INTS = 16;                 // flag block of a big problem: [0] any bad, [1 + c] cluster c bad
 constexpr long long KMEANS_BIG_ELEMENTS = 1LL << 21;  // n * F from which a problem is "big"
 
+constexpr long long DEDUPE_BIG_SYMBOLS = 1LL << 22;  // rows * width from which a level de-duplicates with the whole grid
+// row_split: CTAs per task (deep tasks); 1 for the many small tasks of a pangenome level
 cudaError_t launch_unpack(cudaStream_t s, const uint8_t *packed, const DTask *d_tasks, int n_tasks,
-                          const int *d_rows, const long long *g_off, uint8_t *G);
+                          const int *d_rows, const long long *g_off, uint8_t *G, int row_split);
+// dedupe_kernel's outputs for levels that hold a deep task; U: scratch of the size of G
+cudaError_t launch_dedupe_big(cudaStream_t s, const DTask *d_tasks, int n_tasks, int max_rows, const long long *g_off,
+                              const uint8_t *G, uint8_t *U, const long long *row_off, void *sig, int *leader_u,
+                              int *leader_g, int *group, int *ulen, int *leaders, int *leader_len, int *n_ungapped,
+                              int *n_gapped, int *err);
 cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, const long long *g_off,
                           const uint8_t *G, const long long *row_off, void *sig, int *leader_u,
                           int *leader_g, int *group, int *ulen, int *leaders, int *leader_len,

@@ -10,7 +10,7 @@ namespace mprg {
 constexpr int TILE_CHUNKS = 32;      // widest tile: one 512-byte row segment per warp load
 constexpr int TILE_ITER_QUANTUM = 4; // warp iterations one trip of the scan kernel consumes
 constexpr int MIN_TILE_ITERS = 12, MAX_TILE_ITERS = 32;  // sweeps in DESIGN.md section 7
-constexpr int SCAN_RESIDENT_WARPS_PER_SM = 28;  // 72 registers per thread
+constexpr int SCAN_RESIDENT_WARPS_PER_SM = 32;  // 64 registers per thread (__launch_bounds__(128, 8))
 
 static inline int pow2_ceil(int x) {
     int p = 1;
@@ -54,7 +54,9 @@ int level_run(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *h_tasks, 
         level_iters += (long long)(nch / TILE_CHUNKS) * ht.n_rows;
         if (rem) level_iters += (ht.n_rows + (32 / pow2_ceil(rem)) - 1) / (32 / pow2_ceil(rem));
     }
-    const long long target_tiles = (long long)std::max(ctx->sm_count, 1) * SCAN_RESIDENT_WARPS_PER_SM * 4;
+    // 3.5 waves of resident warps: 16 iterations for the 1,000 x (200 x 1,000) root level (sweep: 12: 3.00, 16: 3.18,
+    // 20: 3.06, 24: 2.94 TB/s), 32 for launches 8x that size (12: 4.2, 20: 5.1, 28-32: 5.3 TB/s)
+    const long long target_tiles = (long long)std::max(ctx->sm_count, 1) * SCAN_RESIDENT_WARPS_PER_SM * 7 / 2;
     int tile_iters = (int)((level_iters + target_tiles - 1) / target_tiles);
     tile_iters = ((tile_iters + TILE_ITER_QUANTUM - 1) / TILE_ITER_QUANTUM) * TILE_ITER_QUANTUM;
     tile_iters = std::min(std::max(tile_iters, MIN_TILE_ITERS), MAX_TILE_ITERS);

@@ -110,8 +110,16 @@ __device__ __forceinline__ int scan_walk(const uint8_t *rp, int k0, int lane, in
 struct ScanLane {
     int chunk, lane, lane_chunk, bn, c0, c1, a0;
 };
+// Inlined four times (once per row of a trip).  A single out-of-line copy (smaller loop, fewer
+// instruction-cache misses) was measured at 2.1 instead of 3.2 TB/s: the call pins the accumulators
+// to the ABI's registers (profiles/r1_scan_variants.txt).
+#ifdef MPRG_SCAN_NOINLINE_GAPS
+#define MPRG_GAP_INLINE __noinline__
+#else
+#define MPRG_GAP_INLINE __forceinline__
+#endif
 template <typename RowPtr>
-__device__ __forceinline__ void scan_gap_rows(uint32_t g, bool todo, const ScanLane &L, RowPtr row_ptr,
+__device__ MPRG_GAP_INLINE void scan_gap_rows(uint32_t g, bool todo, const ScanLane &L, RowPtr row_ptr,
                                               unsigned *B) {
     const int colbase = L.chunk << 5;
     uint32_t gn = __shfl_down_sync(0xffffffffu, g, 1);
@@ -158,7 +166,10 @@ __device__ __forceinline__ void scan_gap_rows(uint32_t g, bool todo, const ScanL
 }
 
 template <bool HAS_N>
-__global__ void __launch_bounds__(SCAN_THREADS)
+#ifndef MPRG_SCAN_MIN_BLOCKS
+#define MPRG_SCAN_MIN_BLOCKS 8  // 64 registers (11 words spilled): 32 resident warps per SM instead of 28, +6..11 % measured
+#endif
+__global__ void __launch_bounds__(SCAN_THREADS, MPRG_SCAN_MIN_BLOCKS)
 scan_kernel(const uint8_t *__restrict__ packed, const ScanUnit *__restrict__ units, int n_units,
             const int *__restrict__ rows_arena, uint32_t *__restrict__ colOR,
             uint32_t *__restrict__ colNOR, unsigned *__restrict__ colB) {

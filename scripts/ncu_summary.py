@@ -19,8 +19,17 @@ keep = ['Kernel Name', 'Block Size', 'Grid Size', 'gpu__time_duration.sum', 'dra
         'smsp__pcsamp_warps_issue_stalled_branch_resolving', 'smsp__pcsamp_warps_issue_stalled_no_instructions',
         'smsp__pcsamp_warps_issue_stalled_dispatch_stall', 'smsp__pcsamp_warps_issue_stalled_membar',
         'smsp__pcsamp_warps_issue_stalled_mio_throttle', 'smsp__pcsamp_warps_issue_stalled_drain']
+import re
+extra = re.compile(r"^(l1tex__data_pipe_lsu_wavefronts_mem_shared(_op_(atom|ld|st))?\.sum(\.pct_of_peak_sustained_elapsed)?|"
+                   r"l1tex__data_bank_conflicts_pipe_lsu_mem_shared(_op_atom)?\.sum|"
+                   r"smsp__inst_executed_op_shared_atom[a-z_]*\.sum|smsp__inst_executed_op_global_(red|atom)\.sum|"
+                   r"lts__t_sectors_op_(atom|red)\.sum|launch__shared_mem_per_block_(static|dynamic)|"
+                   r"launch__occupancy_limit_[a-z_]+|launch__grid_size|launch__block_size|"
+                   r"sm__inst_executed_pipe_fp64\.sum|smsp__inst_executed_pipe_fp64[a-z_]*\.sum|"
+                   r"sm__pipe_fp64_cycles_active\.avg\.pct_of_peak_sustained_active|"
+                   r"sm__inst_executed_pipe_tensor[a-z_0-9]*\.sum)$")
 for vals in rows[2:]:
     for i, h in enumerate(hdr):
-        if h in keep:
+        if h in keep or extra.search(h):
             print(f"{h}\t{vals[i]}\t{units[i]}")
     print()
