@@ -113,10 +113,20 @@ def cut_chunks(input_files, max_bytes=None, max_loci=16384):
     return chunks
 
 
-def _load_chunk(paths, alignment_format):
+def side_threads(n_chunks, writer=False):
+    """Host threads of the loader and of the writers.  With one chunk nothing overlaps and each stage may
+    use every core; with several, loading chunk k+1 and writing chunk k-1 run beside the build of chunk
+    k, whose worker threads drive the device and must not be starved of cores."""
+    cores = os.cpu_count() or 1
+    if n_chunks <= 1:
+        return max(1, min(32, cores))
+    return max(1, min(4, cores // 8)) if writer else max(1, min(12, cores // 3))
+
+
+def _load_chunk(paths, alignment_format, threads=None):
     if alignment_format != "fasta":
         raise ValueError(f"only the fasta alignment format is supported, got {alignment_format}")
-    return hostio.load_fasta_files(paths)
+    return hostio.load_fasta_files(paths, threads=threads)
 
 
 def iter_built_chunks(input_files, options, device_ordinal=0):
@@ -131,10 +141,11 @@ def iter_built_chunks(input_files, options, device_ordinal=0):
     ctx = device.default_context(device_ordinal)
     chunks = cut_chunks(input_files)
     with ThreadPoolExecutor(1) as pool:
-        future = pool.submit(_load_chunk, chunks[0], options.alignment_format) if chunks else None
+        threads = side_threads(len(chunks))
+        future = pool.submit(_load_chunk, chunks[0], options.alignment_format, threads) if chunks else None
         for k, paths in enumerate(chunks):
             msas = future.result()
-            future = (pool.submit(_load_chunk, chunks[k + 1], options.alignment_format)
+            future = (pool.submit(_load_chunk, chunks[k + 1], options.alignment_format, threads)
                       if k + 1 < len(chunks) else None)
             names = [remove_known_input_extensions(Path(path).name) for path in paths]
             logger.info(f"Generating PRGs for {names[0]} ... {names[-1]} ({len(names)} loci)...")
@@ -182,7 +193,8 @@ def build_and_write(input_files, options, device_ordinal=0, output_prefix=None):
     prefix = output_prefix or options.output_prefix
     ot = options.output_type
     want_ds = ot.prg and not getattr(options, "skip_update_ds", False)
-    writer = hostio.OutputWriter(prefix, prg=ot.prg, binary=ot.binary, gfa=ot.gfa)
+    writer = hostio.OutputWriter(prefix, prg=ot.prg, binary=ot.binary, gfa=ot.gfa,
+                                 threads=side_threads(len(cut_chunks(input_files)), writer=True))
     ds_zip = None
     n_ok = 0
     pending = None  # (future, msas, res): the chunk being encoded / written on the writer thread

@@ -46,6 +46,37 @@ def test_dedupe_rows(ctx):
         assert group.tolist() == g and ulen.tolist() == ul and (nu, ng) == (n_u, n_g)
 
 
+def test_dedupe_rows_whole_grid_path(ctx, monkeypatch):
+    """Deep tasks de-duplicate with the whole grid (dedupe_big_* kernels): same outputs as the one-CTA
+    kernel, on the forced path for small windows and on a task that takes it by size."""
+    rng = np.random.default_rng(8)
+    mats = [synth.synth_msa(70, 260, 21, var_frac=0.1, n_dels=12), rows_to_matrix(["A--C", "AC--", "-A-C", "----", "----"]),
+            synth.synth_msa(2500, 1800, 22, n_haps=300, var_frac=0.05, n_dels=6, private_snp=0.0005)]
+    mats[2][5] = mats[2][3]  # exact duplicates far apart
+    mats[2][2400] = mats[2][3]
+    batch = ctx.upload(mats)
+    tasks = [(0, None, 0, 260), (1, None, 0, 4), (1, np.array([3, 4]), 1, 3)]
+    for _ in range(25):
+        c0 = int(rng.integers(0, 259))
+        c1 = int(rng.integers(c0 + 1, min(260, c0 + 70) + 1))
+        tasks.append((0, np.sort(rng.choice(70, int(rng.integers(1, 71)), replace=False)), c0, c1))
+    plain = ctx.dedupe_rows(batch, tasks)
+    monkeypatch.setenv("MPRG_FORCE_BIG_DEDUPE", "1")
+    forced = ctx.dedupe_rows(batch, tasks)
+    monkeypatch.delenv("MPRG_FORCE_BIG_DEDUPE")
+    for (l, rows, c0, c1), a, b in zip(tasks, plain, forced):
+        S = mats[l][:, c0:c1] if rows is None else mats[l][rows, c0:c1]
+        g, ul, n_u, n_g = _oracle_dedupe(S)
+        for group, ulen, nu, ng in (a, b):
+            assert group.tolist() == g and ulen.tolist() == ul and (nu, ng) == (n_u, n_g)
+    # 2,500 x 1,800 = 4.5 M symbols: above DEDUPE_BIG_SYMBOLS, next to a small task of the same level
+    (group, ulen, nu, ng), small = ctx.dedupe_rows(batch, [(2, None, 0, 1800), (0, None, 10, 40)])
+    g, ul, n_u, n_g = _oracle_dedupe(mats[2])
+    assert group.tolist() == g and ulen.tolist() == ul and (nu, ng) == (n_u, n_g)
+    g, ul, n_u, n_g = _oracle_dedupe(mats[0][:, 10:40])
+    assert small[0].tolist() == g and small[1].tolist() == ul and small[2:] == (n_u, n_g)
+
+
 def test_kmer_count_matrix(ctx):
     rng = np.random.default_rng(4)
     mats = [synth.synth_msa(50, 120, 15, var_frac=0.15, n_dels=6),
