@@ -184,6 +184,13 @@ int mprg_cluster_tasks(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task *
  *      (prg_builder.py:24-42,100-110; NodeFactory.build recursion_tree.py:401-471) -------------- */
 int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, int32_t min_match_length,
                mprg_result **out);
+/* The same for alignments that are built BELOW an existing node, NodeFactory.build(alignment, builder,
+ * parent_node) as LeafNode._update_leaf calls it (recursion_tree.py:373-376, 431-432): h_parent_level[l]
+ * is parent_node.nesting_level for locus l, or -1 to build it as a root.  A non-root alignment is never
+ * forced into a MultiIntervalNode and its nesting starts at the parent's level; node ids in the result
+ * count from 0 (the caller adds PrgBuilder.next_node_id).  h_parent_level == NULL is mprg_build. */
+int mprg_build_sub(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, int32_t min_match_length,
+                   const int32_t *h_parent_level, mprg_result **out);
 /* The same from HOST ASCII in one call: loader output in, batch + result out.  The loci are cut into
  * the ranges mprg_build uses and every range is copied, packed and built by its own worker thread and
  * stream, so the host-to-device copy of one range overlaps the kernels of the others (the end-to-end

@@ -71,6 +71,7 @@ SIGNATURES = {
     "mprg_one_ref_like": (C.c_int, [P, P, P, P, P, I32, P]),
     "mprg_cluster_tasks": (C.c_int, [P, P, P, I32, P, I64, I32, P, P, P]),
     "mprg_build": (C.c_int, [P, P, I32, I32, C.POINTER(P)]),
+    "mprg_build_sub": (C.c_int, [P, P, I32, I32, P, C.POINTER(P)]),
     "mprg_build_ascii": (C.c_int, [P, P, P, P, P, I32, I32, I32, C.POINTER(P), C.POINTER(P)]),
     "mprg_result_free": (None, [P]),
     "mprg_result_n_loci": (I32, [P]),

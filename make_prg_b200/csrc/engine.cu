@@ -885,6 +885,7 @@ struct HNode {
 
 struct LocusResult {
     int status = MPRG_LOCUS_OK;
+    bool as_root = true;            // false: built below an existing node (mprg_build_sub)
     std::vector<HNode> nodes;       // creation (level) order; node 0 is the root
     std::vector<int> row_pool;
     std::vector<int> preorder;      // node indices in pre-order == node_id order
@@ -940,8 +941,11 @@ struct mprg_result {
 };
 
 // Builds loci [l_begin, l_end) of the batch on one context (one stream, one host thread).
+// root_levels (may be null): per locus -1 = the alignment is a locus root (from_msa), >= 0 = it is built
+// below an existing node of that nesting level, NodeFactory.build(alignment, builder, parent_node)
+// (recursion_tree.py:431-432: no forced MultiIntervalNode, nesting starts at the parent's level).
 static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, int32_t max_nesting,
-                       int32_t min_match_length, mprg_result *res, bool allow_trace) {
+                       int32_t min_match_length, mprg_result *res, bool allow_trace, const int32_t *root_levels) {
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     struct Pending {
@@ -965,7 +969,8 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
         }
         HNode root;
         root.parent = -1;
-        root.level = 0;
+        root.level = (root_levels && root_levels[l] >= 0) ? root_levels[l] : 0;
+        L.as_root = !(root_levels && root_levels[l] >= 0);
         root.c0 = 0;
         root.c1 = batch->n_cols[l];
         root.row_off = -1;
@@ -1046,7 +1051,7 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
             const int ni = pending[i].node;
             const DInterval *ivs = iv + lv.tasks[i].iv_off;
             const int c = cnt[i];
-            const bool is_root = L.nodes[ni].parent < 0;
+            const bool is_root = L.nodes[ni].parent < 0 && L.as_root;
             if (c == 1 && ivs[0].type != MPRG_IV_NONMATCH) {
                 make_match_leaf(l, L.nodes[ni]);
             } else if (c > 1 || is_root) {
@@ -1315,7 +1320,8 @@ extern "C" int mprg_set_workers(mprg_ctx *ctx, int32_t n_workers) {
 // With h_ascii != nullptr every range is first uploaded and packed by its own worker, so the
 // host-to-device copies of some ranges overlap the kernels of the others (mprg_build_ascii).
 static int build_ranges(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, int32_t min_match_length,
-                        const uint8_t *h_ascii, const int64_t *h_offsets, mprg_result **out_res) {
+                        const uint8_t *h_ascii, const int64_t *h_offsets, mprg_result **out_res,
+                        const int32_t *root_levels = nullptr) {
     *out_res = nullptr;
     cudaSetDevice(ctx->device);
     const int n_loci = batch->n_loci;
@@ -1331,7 +1337,7 @@ static int build_ranges(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, i
             const int r = batch_upload_range(c, batch, h_ascii, h_offsets, l0, l1);
             if (r != MPRG_OK) return r;
         }
-        return build_range(c, batch, l0, l1, max_nesting, min_match_length, res, trace);
+        return build_range(c, batch, l0, l1, max_nesting, min_match_length, res, trace, root_levels);
     };
     int W = std::max(1, std::min(ctx->n_workers, n_loci / 8));
     if (W <= 1) {
@@ -1423,6 +1429,12 @@ extern "C" int mprg_build(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting,
                           int32_t min_match_length, mprg_result **out_res) {
     if (!ctx || !batch || !out_res || min_match_length < 1) return MPRG_E_BAD_ARG;
     return build_ranges(ctx, batch, max_nesting, min_match_length, nullptr, nullptr, out_res);
+}
+
+extern "C" int mprg_build_sub(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, int32_t min_match_length,
+                              const int32_t *h_parent_level, mprg_result **out_res) {
+    if (!ctx || !batch || !out_res || min_match_length < 1) return MPRG_E_BAD_ARG;
+    return build_ranges(ctx, batch, max_nesting, min_match_length, nullptr, nullptr, out_res, h_parent_level);
 }
 
 extern "C" int mprg_build_ascii(mprg_ctx *ctx, const uint8_t *h_ascii, const int64_t *h_offsets,

@@ -270,6 +270,16 @@ class Context:
                                         C.byref(h)))
         return BuildResult(self, h)
 
+    def build_sub(self, batch, max_nesting, min_match_length, parent_levels):
+        """Every locus of the batch built below a node of nesting level parent_levels[l] (-1: as a root):
+        NodeFactory.build(alignment, builder, parent_node) for a batch of re-builds (mprg_build_sub)."""
+        levels = np.ascontiguousarray(parent_levels, np.int32)
+        assert len(levels) == batch.n_loci
+        h = C.c_void_p()
+        self._check(self.lib.mprg_build_sub(self.handle, batch.handle, max_nesting, min_match_length,
+                                            ptr(levels), C.byref(h)))
+        return BuildResult(self, h)
+
     def build_ascii(self, matrices, max_nesting, min_match_length):
         """Host ASCII in, (Batch, BuildResult) out in one call: every worker range is copied, packed and
         built on its own stream, so the copies overlap the kernels (mprg_build_ascii)."""

@@ -29,8 +29,10 @@ class LocusBuild:
 
 def build_matrices(matrices: List[np.ndarray], max_nesting: int, min_match_length: int,
                    ctx: Optional[device.Context] = None, want_nodes: bool = True,
-                   max_batch_bytes: int = 8 << 30) -> List[LocusBuild]:
-    """Runs the whole hot path on a list of uint8[rows, cols] ASCII matrices."""
+                   max_batch_bytes: int = 8 << 30, parent_levels=None) -> List[LocusBuild]:
+    """Runs the whole hot path on a list of uint8[rows, cols] ASCII matrices.  parent_levels[i] >= 0
+    builds matrix i below an existing node of that nesting level (NodeFactory.build with a parent_node,
+    recursion_tree.py:431-432), -1 / None as a locus root."""
     ctx = ctx or device.default_context()
     out: List[LocusBuild] = []
     start = 0
@@ -40,7 +42,11 @@ def build_matrices(matrices: List[np.ndarray], max_nesting: int, min_match_lengt
             size += matrices[stop].size
             stop += 1
         chunk = matrices[start:stop]
-        batch, res = ctx.build_ascii(chunk, max_nesting, min_match_length)
+        if parent_levels is None:
+            batch, res = ctx.build_ascii(chunk, max_nesting, min_match_length)
+        else:
+            batch = ctx.upload(chunk)
+            res = ctx.build_sub(batch, max_nesting, min_match_length, list(parent_levels[start:stop]))
         for i in range(len(chunk)):
             status = res.status(i)
             out.append(LocusBuild(status, res.prg(i) if status == LOCUS_OK else "", res.n_nodes(i),

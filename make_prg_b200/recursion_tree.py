@@ -136,8 +136,9 @@ class LeafNode(RecursiveTreeNode):
 _CLASSES = {NODE_LEAF: LeafNode, NODE_INTERVAL: MultiIntervalNode, NODE_CLUSTER: MultiClusterNode}
 
 
-def nodes_from_table(alignment: MSA, table, prg_builder) -> RecursiveTreeNode:
-    """Materialise the tree of one locus from the engine's pre-order node table."""
+def nodes_from_table(alignment: MSA, table, prg_builder, parent_node=None, first_node_id=0) -> RecursiveTreeNode:
+    """Materialise the tree of one locus from the engine's pre-order node table.  With parent_node the
+    tree hangs below that node and its ids count on from first_node_id."""
     n = len(table["kind"])
     M = alignment.matrix
     records = list(alignment)
@@ -150,10 +151,11 @@ def nodes_from_table(alignment: MSA, table, prg_builder) -> RecursiveTreeNode:
             rows = table["row_pool"][o:o + int(table["n_rows"][i])]
         c0, c1 = int(table["c0"][i]), int(table["c1"][i])
         sub = MSA([records[int(r)][c0:c1] for r in rows])
-        parent = built[int(table["parent"][i])] if table["parent"][i] >= 0 else None
-        node = _CLASSES[int(table["kind"][i])](int(table["nesting_level"][i]), sub, parent, prg_builder, i)
+        parent = built[int(table["parent"][i])] if table["parent"][i] >= 0 else parent_node
+        node = _CLASSES[int(table["kind"][i])](int(table["nesting_level"][i]), sub, parent, prg_builder,
+                                               first_node_id + i)
         built[i] = node
-        if parent is not None:
+        if parent is not None and table["parent"][i] >= 0:
             parent._children.append(node)
     del M
     return built[0]
@@ -165,8 +167,15 @@ class NodeFactory:
     @staticmethod
     def build(alignment, prg_builder, parent_node=None):
         if parent_node is not None:
-            raise NotImplementedError("re-building below an existing node belongs to `make_prg update`, "
-                                      "which is outside the from_msa hot path")
+            # LeafNode._update_leaf (recursion_tree.py:373-376): the updated alignment is re-built below
+            # the leaf's parent; the caller swaps the new node in (replace_child) and re-emits the PRG
+            result = engine.build_matrices([alignment.matrix], prg_builder.max_nesting,
+                                           prg_builder.min_match_length,
+                                           parent_levels=[parent_node.nesting_level])[0]
+            result.raise_for_status(prg_builder.locus_name)
+            first = prg_builder.next_node_id
+            prg_builder.next_node_id += result.n_nodes
+            return nodes_from_table(alignment, result.nodes, prg_builder, parent_node, first)
         result = engine.build_matrices([alignment.matrix], prg_builder.max_nesting,
                                        prg_builder.min_match_length)[0]
         result.raise_for_status(prg_builder.locus_name)

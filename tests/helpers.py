@@ -40,6 +40,13 @@ def synthetic_cases():
         return json.load(fh)
 
 
+def sub_build_cases():
+    """NodeFactory.build(alignment, builder, parent_node) vectors from the unmodified reference
+    (oracle/gen_golden_sub.py)."""
+    with open(GOLDEN / "sub_builds.json") as fh:
+        return json.load(fh)
+
+
 def unit_cases():
     with open(GOLDEN / "units.json") as fh:
         return json.load(fh)

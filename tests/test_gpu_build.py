@@ -85,6 +85,31 @@ def test_synthetic_prg_and_tree(ctx):
             assert _tree_dump(res, i, mats[i]) == [list(t) for t in r["tree"]]
 
 
+def test_build_below_a_parent_node(ctx):
+    """mprg_build_sub against the unmodified reference's NodeFactory.build(alignment, builder, parent_node):
+    PRG strings and trees of 216 re-builds below nodes of nesting level 0 / 2 / 4, one batch per (N, L)."""
+    from helpers import rows_to_matrix, sub_build_cases
+
+    recs = sub_build_cases()
+    groups = {}
+    for r in recs:
+        groups.setdefault((r["N"], r["L"]), []).append(r)
+    for (N, L), rs in groups.items():
+        mats = [rows_to_matrix(r["rows"]) for r in rs]
+        batch = ctx.upload(mats)
+        res = ctx.build_sub(batch, N, L, [r["parent_level"] for r in rs])
+        for i, r in enumerate(rs):
+            assert res.status(i) == 0
+            assert res.prg(i) == r["prg"], (r["rows"], L, r["parent_level"])
+            want = [[t[0], t[1] - r["first_node_id"]] + list(t[2:]) for t in r["tree"]]
+            assert _tree_dump(res, i, mats[i]) == want
+        # the same loci as roots differ wherever the reference would force a MultiIntervalNode
+        roots = ctx.build_sub(batch, N, L, [-1] * len(rs))
+        plain = ctx.build(batch, N, L)
+        for i in range(len(rs)):
+            assert roots.prg(i) == plain.prg(i)
+
+
 def test_batch_order_invariance(ctx):
     mats = [synth.config_msa(2, i) for i in range(4)]
     _, a = _build(ctx, mats, 5, 7)

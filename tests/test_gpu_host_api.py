@@ -155,3 +155,70 @@ def test_cli_single_msa_and_skip_semantics(tmp_path):
     with pytest.raises(RuntimeError):
         _run_cli(tmp_path, REF / "match.nonmatch.fa", "one")
     _run_cli(tmp_path, REF / "match.nonmatch.fa", "one", force=True)
+
+
+def test_cli_chunked_pipeline_equals_one_batch(tmp_path, monkeypatch):
+    """The load -> build -> write pipeline cuts a run into chunks of MPRG_CHUNK_MB of input: the final files
+    do not depend on the cut (amira_MSAs + sample_example + the small cases, one file per chunk vs one chunk)."""
+    import shutil
+
+    src = tmp_path / "msas"
+    src.mkdir()
+    for f in sorted((REF / "amira_MSAs").iterdir()) + sorted((REF / "sample_example").iterdir()):
+        if f.is_file():
+            shutil.copy(f, src / f.name)
+    for case in ("match.nonmatch.match", "nested_snps_deletion", "contains_n_and_RYKMSW", "fails_2"):
+        shutil.copy(REF / f"{case}.fa", src / f"{case}.fa")
+    _run_cli(tmp_path, src, "one", skip_update_ds=True)
+    monkeypatch.setenv("MPRG_CHUNK_MB", "0.000001")
+    from make_prg_b200.subcommands import from_msa
+
+    files = from_msa.get_all_input_files(str(src), "")
+    assert len(from_msa.cut_chunks(files)) == len(files) >= 8
+    _run_cli(tmp_path, src, "many", skip_update_ds=True)
+    assert (tmp_path / "one.prg.fa").read_bytes() == (tmp_path / "many.prg.fa").read_bytes()
+    assert (tmp_path / "one.prg.fa").read_text().count(">") == len(files) - 1  # fails_2 is skipped
+    assert not (tmp_path / "one.update_DS.zip").exists()
+    for kind in ("bin", "gfa"):
+        with zipfile.ZipFile(tmp_path / f"one.prg.{kind}.zip") as a, zipfile.ZipFile(tmp_path / f"many.prg.{kind}.zip") as b:
+            assert a.namelist() == b.namelist() and a.testzip() is None and b.testzip() is None
+            for member in a.namelist():
+                assert a.read(member) == b.read(member), member
+    truth = truth_multi("amira_MSAs")
+    lines = (tmp_path / "many.prg.fa").read_text().split("\n")
+    got = {lines[i][1:]: lines[i + 1] for i in range(0, len(lines) - 1, 2)}
+    for name, prg in truth.items():
+        assert got[name] == prg, name
+
+
+def test_node_factory_build_below_parent(tmp_path):
+    """NodeFactory.build(alignment, prg_builder, parent_node) of the host mirror: node ids count on from
+    PrgBuilder.next_node_id and the new node can be swapped in as LeafNode._update_leaf does."""
+    from helpers import sub_build_cases
+    from make_prg_b200.msa import MSA, SeqRecord
+    from make_prg_b200.prg_builder import PrgBuilder
+    from make_prg_b200.recursion_tree import NodeFactory
+
+    builder = PrgBuilder("match.nonmatch.match", REF / "match.nonmatch.match.fa", "fasta", 5, 7)
+    for r in [c for c in sub_build_cases() if c["L"] == 7][:12]:
+        builder.next_node_id = r["first_node_id"]
+        parent = builder.root
+        parent.nesting_level = r["parent_level"]
+        msa = MSA([SeqRecord(s, f"s{i}") for i, s in enumerate(r["rows"])])
+        node = NodeFactory.build(msa, builder, parent)
+        assert node.parent is parent and node.node_id == r["first_node_id"]
+        assert builder.next_node_id == r["next_node_id"]
+        builder.site_num = 5
+        parts = []
+        node.preorder_traversal_to_build_prg(parts)
+        assert "".join(parts) == r["prg"]
+        dump = []
+
+        def walk(n):
+            dump.append([type(n).__name__, n.node_id, n.nesting_level, len(n.alignment),
+                         n.alignment.get_alignment_length(), len(n.children)])
+            for c in n.children:
+                walk(c)
+
+        walk(node)
+        assert dump == [list(t) for t in r["tree"]]

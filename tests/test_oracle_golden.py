@@ -6,7 +6,8 @@ import hashlib
 import pytest
 
 import make_prg_oracle as mo
-from helpers import REF, SMALL_CASES, locus_name, synthetic_cases, truth_multi, truth_prg
+from helpers import (REF, SMALL_CASES, locus_name, rows_to_matrix, sub_build_cases, synthetic_cases, truth_multi,
+                     truth_prg)
 from make_prg_b200 import synth
 
 
@@ -58,3 +59,17 @@ def test_synthetic_against_reference_run(rec):
     assert [list(t) for t in b.dump_tree()] == [list(t) for t in rec["tree"]]
     assert hashlib.sha256(mo.prg_gfa(prg).encode()).hexdigest() == rec["gfa_sha256"]
     assert hashlib.sha256(mo.prg_bin(prg)).hexdigest() == rec["bin_sha256"]
+
+
+def test_build_below_a_parent_node_against_reference_run():
+    """NodeFactory.build(alignment, builder, parent_node) (recursion_tree.py:431-432): the re-build of an
+    updated leaf is not a root -- no forced MultiIntervalNode, nesting starts at the parent's level."""
+    recs = sub_build_cases()
+    assert len(recs) >= 200 and {r["tree"][0][0] for r in recs} == {"LeafNode", "MultiIntervalNode", "MultiClusterNode"}
+    for r in recs:
+        M = rows_to_matrix(r["rows"])
+        b = mo.OracleBuilder([f"s{i}" for i in range(M.shape[0])], M, r["N"], r["L"],
+                             parent_level=r["parent_level"], first_node_id=r["first_node_id"])
+        assert b.build_prg() == r["prg"]
+        assert [list(t) for t in b.dump_tree()] == [list(t) for t in r["tree"]]
+        assert b.next_node_id == r["next_node_id"]
