@@ -246,6 +246,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION/INFO) must not join it
+        # (it is printed at NCCL_DEBUG=WARN too)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from make_prg_b200 import device

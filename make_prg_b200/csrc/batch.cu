@@ -108,8 +108,16 @@ extern "C" int mprg_create(int device_ordinal, mprg_ctx **out) {
         const int n = atoi(env);
         if (n >= 1 && n <= 64) ctx->n_workers = n;
     } else {
+        // at most 8 (sweeps in DESIGN.md section 4): half of the host cores for one process, the whole
+        // share of this process when torchrun says several ranks drive their GPUs from this host
+        // (4 ranks on 32 cores: 8 workers each 447 k loci/s, 4 each 404 k)
         const unsigned hc = std::thread::hardware_concurrency();
-        ctx->n_workers = (int)std::max(1u, std::min(8u, hc ? hc / 2 : 1u));  // more is faster on a quiet host but stalls on a shared one
+        unsigned share = hc / 2;
+        if (const char *lw = getenv("LOCAL_WORLD_SIZE")) {
+            const int n = atoi(lw);
+            if (n > 1) share = hc / (unsigned)n;
+        }
+        ctx->n_workers = (int)std::max(hc >= 4 ? 2u : 1u, std::min(8u, share));
     }
     *out = ctx;
     return MPRG_OK;

@@ -303,7 +303,9 @@ def run(options):
     logger.success("All done!")
 
 
-def _shard_worker(rank, shard_files, options, queue):
+def _shard_worker(rank, shard_files, options, queue, n_shards=1):
+    # every shard process drives its own GPU from this host: share the cores (mprg_create reads this)
+    os.environ.setdefault("LOCAL_WORLD_SIZE", str(n_shards))
     try:
         queue.put((rank, build_loci(shard_files, options, device_ordinal=rank), None))
     except Exception as err:  # propagated to the parent like a Pool worker's exception
@@ -321,7 +323,7 @@ def _run_sharded(input_files, options, gpus):
     queue = ctx.Queue()
     procs = []
     for rank, idx in enumerate(parts):
-        p = ctx.Process(target=_shard_worker, args=(rank, [input_files[i] for i in idx], options, queue))
+        p = ctx.Process(target=_shard_worker, args=(rank, [input_files[i] for i in idx], options, queue, gpus))
         p.start()
         procs.append(p)
     results = {}
