@@ -83,7 +83,8 @@ class MsaSet:
 
     def alignment(self, locus):
         """The locus as an MSA object (ids, descriptions, rows) for the host-side node classes."""
-        return MSA.from_matrix(self.ids(locus), self.matrix(locus), descriptions=self.titles(locus))
+        # a private copy of the rows: the set's buffer goes back to the pinned pool on free()
+        return MSA.from_matrix(self.ids(locus), self.matrix(locus).copy(), descriptions=self.titles(locus))
 
     def shapes(self):
         return [(int(r), int(c)) for r, c in zip(self.n_rows, self.n_cols)]

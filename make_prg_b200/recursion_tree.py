@@ -10,7 +10,7 @@ import numpy as np
 
 from . import engine
 from ._lib import NODE_CLUSTER, NODE_INTERVAL, NODE_LEAF
-from .msa import MSA
+from .msa import MSA, SeqRecord
 from .utils.seq_utils import SequenceExpander, remove_columns_full_of_gaps_from_MSA
 
 
@@ -18,14 +18,75 @@ def equal_msas(msa_1, msa_2):
     return format(msa_1, "fasta") == format(msa_2, "fasta")
 
 
+class RootAlignment:
+    """The root MSA of a locus as one uint8 matrix + record labels: what every node of the locus' tree
+    slices.  One object per locus, shared by its nodes (so a pickled PrgBuilder stores the rows once)."""
+
+    def __init__(self, alignment: MSA):
+        self.matrix = np.ascontiguousarray(alignment.matrix, np.uint8)
+        self.ids = [r.id for r in alignment]
+        self.names = [r.name for r in alignment]
+        self.descriptions = [r.description for r in alignment]
+
+
+class SubAlignment:
+    """(row subset, column window) of a RootAlignment: the sub-alignment of a tree node, kept as indices
+    and materialised as an MSA (columns full of gaps removed, recursion_tree.py:45) on first use.  Every
+    sub-alignment the reference builds is such a slice."""
+
+    __slots__ = ("root", "rows", "c0", "c1")
+
+    def __init__(self, root, rows, c0, c1):
+        self.root, self.rows, self.c0, self.c1 = root, rows, int(c0), int(c1)
+
+    def matrix(self):
+        M = self.root.matrix
+        return M[:, self.c0:self.c1] if self.rows is None else M[self.rows, self.c0:self.c1]
+
+    def row_numbers(self):
+        return range(self.root.matrix.shape[0]) if self.rows is None else [int(r) for r in self.rows]
+
+    def ungapped_sequences(self):
+        """Ungapped rows in row order (the input of SequenceExpander, seq_utils.py:155-158)."""
+        return [row.tobytes().replace(b"-", b"").decode() for row in self.matrix()]
+
+    def materialise(self):
+        S = self.matrix()
+        root = self.root
+        if S.size:
+            S = S[:, ~(S == ord("-")).all(axis=0)]
+        texts = [row.tobytes().decode() for row in S] if S.size else [""] * S.shape[0]
+        return MSA([SeqRecord(text, root.ids[r], root.names[r], root.descriptions[r])
+                    for text, r in zip(texts, self.row_numbers())])
+
+
 class RecursiveTreeNode(ABC):
     def __init__(self, nesting_level, alignment, parent, prg_builder, node_id):
         self.nesting_level = nesting_level
-        self.alignment = remove_columns_full_of_gaps_from_MSA(alignment)
+        if isinstance(alignment, SubAlignment):
+            self._sub, self._alignment = alignment, None
+        else:
+            self._sub, self._alignment = None, remove_columns_full_of_gaps_from_MSA(alignment)
         self.parent = parent
         self.prg_builder = prg_builder
         self._node_id = node_id
         self._children: List["RecursiveTreeNode"] = []
+
+    @property
+    def alignment(self):
+        if self._alignment is None:
+            self._alignment = self._sub.materialise()
+        return self._alignment
+
+    @alignment.setter
+    def alignment(self, value):
+        self._sub, self._alignment = None, value
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        if state.get("_sub") is not None:
+            state["_alignment"] = None  # re-materialised from the shared root matrix after loading
+        return state
 
     @property
     def node_id(self):
@@ -107,7 +168,10 @@ class LeafNode(RecursiveTreeNode):
         self.indexed_PRG_intervals = set()
 
     def preorder_traversal_to_build_prg(self, prg_as_list, delim_char=" ", do_indexing=True):
-        expanded = SequenceExpander.get_expanded_sequences_from_MSA(self.alignment)
+        if self._sub is not None:  # straight from the root matrix: no MSA objects for the leaf
+            expanded = SequenceExpander.get_expanded_sequences(self._sub.ungapped_sequences())
+        else:
+            expanded = SequenceExpander.get_expanded_sequences_from_MSA(self.alignment)
         if len(expanded) == 1:
             start = len(prg_as_list)
             prg_as_list.extend(expanded[0])
@@ -140,24 +204,21 @@ def nodes_from_table(alignment: MSA, table, prg_builder, parent_node=None, first
     """Materialise the tree of one locus from the engine's pre-order node table.  With parent_node the
     tree hangs below that node and its ids count on from first_node_id."""
     n = len(table["kind"])
-    M = alignment.matrix
-    records = list(alignment)
+    root = RootAlignment(alignment)
     built: List[Optional[RecursiveTreeNode]] = [None] * n
     for i in range(n):
         if table["row_off"][i] < 0:
-            rows = np.arange(len(records))
+            rows = None
         else:
             o = int(table["row_off"][i])
-            rows = table["row_pool"][o:o + int(table["n_rows"][i])]
-        c0, c1 = int(table["c0"][i]), int(table["c1"][i])
-        sub = MSA([records[int(r)][c0:c1] for r in rows])
+            rows = np.array(table["row_pool"][o:o + int(table["n_rows"][i])], np.int32)
+        sub = SubAlignment(root, rows, table["c0"][i], table["c1"][i])
         parent = built[int(table["parent"][i])] if table["parent"][i] >= 0 else parent_node
         node = _CLASSES[int(table["kind"][i])](int(table["nesting_level"][i]), sub, parent, prg_builder,
                                                first_node_id + i)
         built[i] = node
         if parent is not None and table["parent"][i] >= 0:
             parent._children.append(node)
-    del M
     return built[0]
 
 
