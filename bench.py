@@ -246,10 +246,20 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION/INFO) must not join it
-        # (it is printed at NCCL_DEBUG=WARN too)
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries exactly one JSON line: this image exports NCCL_DEBUG=VERSION and NCCL prints its
+        # version banner on stdout (NCCL_DEBUG_FILE does not move it) when the first communicator is made,
+        # so file descriptor 1 points at stderr while the process group comes up
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     from make_prg_b200 import device
 

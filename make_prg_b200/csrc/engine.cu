@@ -311,28 +311,45 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
                                      B[2].as<long long>(), B[4].p, d_leader_u, d_leader_g, d_group, d_ulen,
                                      d_leaders, d_leadlen, d_nu, d_ng, d_err));
     }
-    MPRG_CUDA(ctx, launch_scan_counts(s, d_nu, n_tasks, d_leadoff));
-    ctx->launches += 3;
+    // Results of the de-duplication in ONE trip when the level is small (nu | ng | err and the per-row
+    // leader arrays as they are, O(rows)); big levels first fetch the counts, compact the leaders on the
+    // device and fetch O(#distinct) -- a second synchronisation that a pangenome level does not need.
+    const bool one_trip = 2LL * row_total * (long long)sizeof(int) <= (8LL << 20);
+    if (!one_trip) MPRG_CUDA(ctx, launch_scan_counts(s, d_nu, n_tasks, d_leadoff));
+    ctx->launches += one_trip ? 2 : 3;
     TRACE("cl: setup+launch dedupe");
     // nu | ng | lead_off | err are contiguous: one small copy
     std::vector<int> h_small((size_t)(3LL * n_tasks + 2));
+    std::vector<int> lead_base(n_tasks);  // where task i's leaders start in h_dense
+    long long lead_total = 0;
+    int *h_dense = nullptr;
+    if (one_trip) {
+        MPRG_CUDA(ctx, ctx->h_a.reserve(sizeof(int) * 2 * std::max<long long>(row_total, 1)));
+        h_dense = ctx->h_a.as<int>();
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_dense, d_leaders, sizeof(int) * 2 * row_total, s));
+        lead_total = row_total;  // leader lengths follow the leaders at this distance
+        for (int i = 0; i < n_tasks; ++i) lead_base[i] = (int)row_off[i];
+    }
     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_small.data(), d_nu, sizeof(int) * h_small.size(), s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
     const int *h_nu = h_small.data();
     const int *h_ng = h_nu + n_tasks;
     const int *h_leadoff = h_ng + n_tasks;
     if (h_leadoff[n_tasks + 1]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while de-duplicating rows");
-    const long long lead_total = h_leadoff[n_tasks];
-    // dense leaders | leader lengths
-    MPRG_CUDA(ctx, B[6].reserve(sizeof(int) * 2 * std::max<long long>(lead_total, 1)));
-    int *d_dense = B[6].as<int>();
-    MPRG_CUDA(ctx, launch_gather2(s, B[2].as<long long>(), d_nu, d_leadoff, n_tasks, d_leaders, d_leadlen,
-                                  d_dense, d_dense + lead_total));
-    ctx->launches++;
-    MPRG_CUDA(ctx, ctx->h_a.reserve(sizeof(int) * 2 * std::max<long long>(lead_total, 1)));
-    int *h_dense = ctx->h_a.as<int>();
-    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_dense, d_dense, sizeof(int) * 2 * lead_total, s));
-    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    if (!one_trip) {
+        lead_total = h_leadoff[n_tasks];
+        for (int i = 0; i < n_tasks; ++i) lead_base[i] = h_leadoff[i];
+        // dense leaders | leader lengths
+        MPRG_CUDA(ctx, B[6].reserve(sizeof(int) * 2 * std::max<long long>(lead_total, 1)));
+        int *d_dense = B[6].as<int>();
+        MPRG_CUDA(ctx, launch_gather2(s, B[2].as<long long>(), d_nu, d_leadoff, n_tasks, d_leaders, d_leadlen,
+                                      d_dense, d_dense + lead_total));
+        ctx->launches++;
+        MPRG_CUDA(ctx, ctx->h_a.reserve(sizeof(int) * 2 * std::max<long long>(lead_total, 1)));
+        h_dense = ctx->h_a.as<int>();
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_dense, d_dense, sizeof(int) * 2 * lead_total, s));
+        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    }
     TRACE("cl: dedupe sync+D2H");
 
     // host: distinct sequences per task, trivial outcomes, KMeans problems -- O(#distinct)
@@ -346,8 +363,8 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         ClusterOut &o = out[i];
         o.n_ungapped = h_nu[i];
         o.n_gapped = h_ng[i];
-        o.leaders.assign(h_dense + h_leadoff[i], h_dense + h_leadoff[i] + o.n_ungapped);
-        o.leader_len.assign(h_dense + lead_total + h_leadoff[i], h_dense + lead_total + h_leadoff[i] + o.n_ungapped);
+        o.leaders.assign(h_dense + lead_base[i], h_dense + lead_base[i] + o.n_ungapped);
+        o.leader_len.assign(h_dense + lead_total + lead_base[i], h_dense + lead_total + lead_base[i] + o.n_ungapped);
         if (want_clusters && !want_clusters[i]) continue;
         if (h_R[i] == 0) continue;
         // NodeFactory._alignment_has_issues (recursion_tree.py:475-494) discards the clustering anyway
