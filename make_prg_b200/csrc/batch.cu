@@ -70,6 +70,74 @@ pack_rows_kernel(const uint8_t *__restrict__ ascii, const long long *__restrict_
     if (lane == 0 && f) atomicOr(&flags[l], f);
 }
 
+// The same packing with the ASCII rows read straight from PINNED HOST memory (zero copy, opt-in): a big
+// cudaMemcpyAsync sits in the copy engine's queue in front of the small task-table and result copies of
+// the ranges that are already being built (a saturating stream of 26 MB copies beside mprg_build slows
+// it from 7.5 to 110 ms), and the staged copy is read once more from HBM.  Each warp stages the aligned
+// 16-byte vectors that cover 512 columns of its row in shared memory with coalesced 128-bit loads over
+// PCIe (an aligned vector that holds one valid byte lies in a mapped page), then packs from there; here
+// ascii_off are offsets into the caller's buffer.
+__global__ void __launch_bounds__(256)
+pack_rows_hostmem_kernel(const uint8_t *__restrict__ ascii, const long long *__restrict__ ascii_off,
+                         const long long *__restrict__ row_prefix, const int *__restrict__ n_cols,
+                         const long long *__restrict__ base, const int *__restrict__ stride, int n_loci,
+                         long long total_rows, uint8_t *__restrict__ packed, int *__restrict__ flags) {
+    __shared__ uint4 s_stage[8][34];
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (warp >= total_rows) return;
+    int lo = 0, hi = n_loci;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (row_prefix[mid] <= warp) lo = mid; else hi = mid;
+    }
+    const int l = lo;
+    const int r = (int)(warp - row_prefix[l]);
+    const int C = n_cols[l];
+    const uint8_t *src = ascii + ascii_off[l] + (long long)r * C;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(packed + base[l] + (long long)r * stride[l]);
+    const int n_words = stride[l] >> 2;
+    uint4 *stage = s_stage[threadIdx.x >> 5];
+    int f = 0;
+    for (int c0 = 0; c0 < n_words * 8; c0 += 512) {
+        const int len = min(512, C - c0);  // valid columns of this span (<= 0: padding words only)
+        const uint8_t *first = src + c0;
+        const int lead = (int)(reinterpret_cast<unsigned long long>(first) & 15ull);
+        if (len > 0) {
+            const uint4 *aligned = reinterpret_cast<const uint4 *>(first - lead);
+            const int n_vec = (lead + len + 15) >> 4;  // <= 33
+            for (int k = lane; k < n_vec; k += 32) stage[k] = aligned[k];
+        }
+        __syncwarp();
+        const uint8_t *sb = reinterpret_cast<const uint8_t *>(stage) + lead;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int ws = lane + 32 * half;  // word of the span
+            const int w = (c0 >> 3) + ws;
+            if (w < n_words) {
+                const int cbase = (ws >> 2) * 32 + (ws & 3);
+                uint32_t word = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t code = SYM_PAD;
+                    if (cbase + 4 * j < len) {
+                        code = c_sym_lut[sb[cbase + 4 * j]];
+                        if (code == SYM_PAD) f |= 1;
+                        else if (code == SYM_N) f |= 2;
+                        else if (sym_is_ambiguous(code)) f |= 4;
+                        if (code != SYM_GAP && !(code & 1u)) f |= 8;
+                    }
+                    word |= code << (4 * j);
+                }
+                dst[w] = word;
+            }
+        }
+        __syncwarp();
+    }
+    f = __reduce_or_sync(0xffffffffu, f);
+    if (lane == 0 && f) atomicOr(&flags[l], f);
+}
+
 }  // namespace mprg
 
 using namespace mprg;
@@ -255,23 +323,40 @@ int batch_upload_range(mprg_ctx *ctx, mprg_batch *b, const uint8_t *h_ascii, con
     MPRG_CUDA(ctx, ctx->d_stage.reserve(total));
     uint8_t *d = ctx->d_stage.as<uint8_t>();
     cudaStream_t s = ctx->stream;
+    // The rows are staged in HBM with cudaMemcpyAsync and packed from there.  With MPRG_ZEROCOPY=1 pinned
+    // (device-visible) host memory is read by the pack kernel itself instead; measured slower here (11.7
+    // against 10.8 ms per 1,000 loci end to end: SM reads over PCIe do not reach the copy engine's rate),
+    // kept as a checked alternative for hosts where the copy engines are the contended resource.
+    const uint8_t *d_host_view = nullptr;
+    if (getenv("MPRG_ZEROCOPY")) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, h_ascii) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer != nullptr)
+            d_host_view = static_cast<const uint8_t *>(attr.devicePointer);
+        else
+            cudaGetLastError();
+    }
     // One range at a time on the PCIe link: concurrent copies of several workers would share the
     // bandwidth and finish together; in turn, the first range is being built while the next is copied.
     std::unique_lock<std::mutex> link(b->copy_mutex);
-    // loci that are contiguous in the caller's buffer go in one copy
-    bool contiguous = true;
-    for (int i = 0; i < n; ++i) contiguous &= (h_offsets[l0 + i] == h_offsets[l0] + aoff[i]);
-    if (contiguous) {
-        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_ascii, h_ascii + h_offsets[l0], (size_t)ascii_total, s));
+    if (d_host_view) {
+        for (int i = 0; i < n; ++i) aoff[i] = h_offsets[l0 + i];  // offsets into the caller's buffer
     } else {
-        for (int i = 0; i < n; ++i) {
-            const size_t nbytes = (size_t)b->n_rows[l0 + i] * b->n_cols[l0 + i];
-            if (!nbytes) continue;
-            MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_ascii + aoff[i], h_ascii + h_offsets[l0 + i], nbytes, s));
+        // loci that are contiguous in the caller's buffer go in one copy
+        bool contiguous = true;
+        for (int i = 0; i < n; ++i) contiguous &= (h_offsets[l0 + i] == h_offsets[l0] + aoff[i]);
+        if (contiguous) {
+            MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_ascii, h_ascii + h_offsets[l0], (size_t)ascii_total, s));
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const size_t nbytes = (size_t)b->n_rows[l0 + i] * b->n_cols[l0 + i];
+                if (!nbytes) continue;
+                MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_ascii + aoff[i], h_ascii + h_offsets[l0 + i], nbytes, s));
+            }
         }
+        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        link.unlock();
     }
-    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
-    link.unlock();
     MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_aoff, aoff.data(), sizeof(long long) * n, s));
     MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_rp, row_prefix.data(), sizeof(long long) * (n + 1), s));
     MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d + o_base, b->base.data() + l0, sizeof(long long) * n, s));
@@ -280,13 +365,21 @@ int batch_upload_range(mprg_ctx *ctx, mprg_batch *b, const uint8_t *h_ascii, con
     MPRG_CUDA(ctx, cudaMemsetAsync(d + o_fl, 0, sizeof(int) * n, s));
     const int warps_per_block = 8;
     const long long blocks = (total_rows + warps_per_block - 1) / warps_per_block;
-    pack_rows_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(
-        d + o_ascii, (const long long *)(d + o_aoff), (const long long *)(d + o_rp), (const int *)(d + o_nc),
-        (const long long *)(d + o_base), (const int *)(d + o_st), n, total_rows, b->d_packed, (int *)(d + o_fl));
+    if (d_host_view) {
+        pack_rows_hostmem_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(
+            d_host_view, (const long long *)(d + o_aoff), (const long long *)(d + o_rp), (const int *)(d + o_nc),
+            (const long long *)(d + o_base), (const int *)(d + o_st), n, total_rows, b->d_packed, (int *)(d + o_fl));
+        ctx->h2d_bytes += ascii_total;  // read over PCIe by the kernel
+    } else {
+        pack_rows_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(
+            d + o_ascii, (const long long *)(d + o_aoff), (const long long *)(d + o_rp), (const int *)(d + o_nc),
+            (const long long *)(d + o_base), (const int *)(d + o_st), n, total_rows, b->d_packed, (int *)(d + o_fl));
+    }
     ctx->launches++;
     MPRG_CUDA(ctx, cudaGetLastError());
     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, b->flags.data() + l0, d + o_fl, sizeof(int) * n, s));
     MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    if (link.owns_lock()) link.unlock();
     for (int l = l0; l < l1; ++l)
         if (b->flags[l] & 2) b->any_n = true;
     return MPRG_OK;

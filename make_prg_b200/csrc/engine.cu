@@ -1349,12 +1349,21 @@ static int build_ranges(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, i
         delete res;
         return rc;
     }
+    const auto t_call = std::chrono::steady_clock::now();
+    const bool trace_all = getenv("MPRG_TRACE") && getenv("MPRG_TRACE_ALL");
+    auto since_call = [&]() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
+    };
     auto run = [&](mprg_ctx *c, int l0, int l1, bool trace) {
         if (h_ascii) {
+            const double t0 = since_call();
             const int r = batch_upload_range(c, batch, h_ascii, h_offsets, l0, l1);
             if (r != MPRG_OK) return r;
+            if (trace_all) fprintf(stderr, "[mprg trace] range %d..%d: upload %.2f -> %.2f ms after the call\n", l0, l1, t0, since_call());
         }
-        return build_range(c, batch, l0, l1, max_nesting, min_match_length, res, trace, root_levels);
+        const int rc_b = build_range(c, batch, l0, l1, max_nesting, min_match_length, res, trace, root_levels);
+        if (trace_all) fprintf(stderr, "[mprg trace] range %d..%d: built %.2f ms after the call\n", l0, l1, since_call());
+        return rc_b;
     };
     int W = std::max(1, std::min(ctx->n_workers, n_loci / 8));
     if (W <= 1) {

@@ -140,6 +140,39 @@ def test_build_ascii_equals_upload_then_build(ctx):
     ctx.set_workers(4)
 
 
+def test_build_ascii_from_pinned_memory_equals_pageable(ctx, monkeypatch):
+    """Pinned host buffers copied and packed, pinned buffers read in place by the pack kernel
+    (MPRG_ZEROCOPY=1) and pageable buffers: same packed rows, flags and PRGs for odd widths, unaligned
+    locus offsets, widths around the 512-column staging span and a locus with a disallowed base."""
+    import torch
+
+    widths = [1, 7, 31, 32, 33, 511, 512, 513, 1000, 1023, 1025, 1531]
+    mats = [synth.synth_msa(3 + (i * 5) % 17, w, 700 + i, var_frac=0.1, n_dels=2) for i, w in enumerate(widths)]
+    mats[4][1, 3] = ord("Z")
+    mats[6][2, 500:512] = np.frombuffer(b"RYKMSWRYKMSW", np.uint8)
+    flat = np.concatenate([np.zeros(3, np.uint8)] + [m.reshape(-1) for m in mats])  # every offset is odd-ish
+    shapes = [m.shape for m in mats]
+    pinned = torch.from_numpy(flat.copy()).pin_memory().numpy()[3:]
+    pageable = flat[3:].copy()
+    results = []
+    for buf, zero_copy in ((pinned, True), (pageable, False), (pinned, False)):
+        if zero_copy:
+            monkeypatch.setenv("MPRG_ZEROCOPY", "1")
+        else:
+            monkeypatch.delenv("MPRG_ZEROCOPY", raising=False)
+        batch, res = ctx.build_ascii((buf, shapes), 5, 7)
+        results.append((batch.flags().tolist(), [batch.packed(i).tobytes() for i in range(len(mats))],
+                        [res.status(i) for i in range(len(mats))], [res.prg(i) for i in range(len(mats))]))
+        res.free()
+        batch.free()
+    assert results[0] == results[1] == results[2]
+    assert results[0][2][4] == 1 and all(st == 0 for i, st in enumerate(results[0][2]) if i != 4)
+    for i, M in enumerate(mats):
+        if i != 4:
+            want, _ = mo.build_prg_from_matrix([f"s{r}" for r in range(M.shape[0])], M, 5, 7)
+            assert results[0][3][i] == want, widths[i]
+
+
 def test_deep_locus_takes_the_whole_grid_paths(ctx):
     """One deep locus (every row distinct: private SNPs) sends a single huge clustering problem through
     the whole-grid k-mer numbering, the CTA-group KMeans and the whole-grid one-reference-like check;
