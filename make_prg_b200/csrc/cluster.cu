@@ -38,13 +38,71 @@ unpack_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ task
               uint8_t *__restrict__ G) {
     const DTask t = tasks[blockIdx.x];
     const int w = t.c1 - t.c0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int *rows = t.rows_off >= 0 ? rows_arena + t.rows_off : nullptr;
     uint8_t *out = G + g_off[blockIdx.x];
-    for (int r = warp + nw * blockIdx.y; r < t.n_rows; r += nw * gridDim.y) {
-        const uint8_t *row = packed + t.base + (long long)(rows ? rows[r] : r) * t.stride;
-        for (int i = lane; i < w; i += 32) out[(long long)r * w + i] = (uint8_t)sym_of(row, t.c0 + i);
+    if (w >= 64) {
+        // wide windows: warps over rows, lanes over columns
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int r = warp + nw * blockIdx.y; r < t.n_rows; r += nw * gridDim.y) {
+            const uint8_t *row = packed + t.base + (long long)(rows ? rows[r] : r) * t.stride;
+            for (int i = lane; i < w; i += 32) out[(long long)r * w + i] = (uint8_t)sym_of(row, t.c0 + i);
+        }
+    } else {
+        // narrow windows (the non-match intervals of a pangenome level are a few columns wide): the
+        // threads stride over the (row, column) pairs, so every lane has a symbol to fetch
+        const long long total = (long long)t.n_rows * w;
+        for (long long e = threadIdx.x + (long long)blockDim.x * blockIdx.y; e < total;
+             e += (long long)blockDim.x * gridDim.y) {
+            const int r = (int)(e / w), i = (int)(e - (long long)r * w);
+            const uint8_t *row = packed + t.base + (long long)(rows ? rows[r] : r) * t.stride;
+            out[e] = (uint8_t)sym_of(row, t.c0 + i);
+        }
     }
+}
+
+// ---- helpers shared by the kernels below ----
+// Per clustering problem (one CTA): the n distinct long sequences are rows seq_rows[0..n) (task-local
+// row positions) of the task's unpacked block G.
+
+__device__ __forceinline__ uint64_t kmer_hash(const uint8_t *p, int k) {
+    uint64_t h = 0x243f6a8885a308d3ULL;
+    for (int i = 0; i < k; ++i) h = (h ^ (uint64_t)(p[i] + 1)) * 0x9e3779b97f4a7c15ULL + (h >> 32);
+    h = mix64(h);
+    return h == ~0ULL ? 0 : h;  // ~0 marks an empty slot
+}
+
+// block-wide exclusive prefix sum over `n` ints in place (values small); returns the total
+__device__ int block_exclusive_scan(int *a, int n, int *s_warp /* >= 33 ints */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? a[i] : 0;
+        int x = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += o;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int y = lane < nw ? s_warp[lane] : 0;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, y, d);
+                if (lane >= d) y += o;
+            }
+            s_warp[lane] = y;  // inclusive over warps
+        }
+        __syncthreads();
+        const int warp_excl = warp ? s_warp[warp - 1] : 0;
+        if (i < n) a[i] = carry + warp_excl + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += s_warp[nw - 1];
+        __syncthreads();
+    }
+    return carry;
 }
 
 // ---- dedupe ---------------------------------------------------------------------------------------
@@ -121,66 +179,33 @@ dedupe_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ g_o
         lg[r] = b;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int nu = 0, ng = 0;
-        for (int r = 0; r < R; ++r) {
-            if (lu[r] == r) {
-                leaders[ro + nu] = r;
-                leader_len[ro + nu] = ulen[ro + r];
-                group[ro + r] = nu++;
-            } else {
-                group[ro + r] = group[ro + lu[r]];
-            }
-            ng += lg[r] == r;
-        }
-        n_ungapped[ti] = nu;
-        n_gapped[ti] = ng;
+    // first-seen numbering of the distinct rows: exclusive prefix sum of the leader flags
+    __shared__ int s_warp[33];
+    __shared__ int s_ng;
+    if (threadIdx.x == 0) s_ng = 0;
+    int ng = 0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        group[ro + r] = lu[r] == r ? 1 : 0;
+        ng += lg[r] == r;
     }
-}
-
-// ---- k-mer counting -------------------------------------------------------------------------------
-// Per clustering problem (one CTA): the n distinct long sequences are rows seq_rows[0..n) (task-local
-// row positions) of the task's unpacked block G.
-
-__device__ __forceinline__ uint64_t kmer_hash(const uint8_t *p, int k) {
-    uint64_t h = 0x243f6a8885a308d3ULL;
-    for (int i = 0; i < k; ++i) h = (h ^ (uint64_t)(p[i] + 1)) * 0x9e3779b97f4a7c15ULL + (h >> 32);
-    h = mix64(h);
-    return h == ~0ULL ? 0 : h;  // ~0 marks an empty slot
-}
-
-// block-wide exclusive prefix sum over `n` ints in place (values small); returns the total
-__device__ int block_exclusive_scan(int *a, int n, int *s_warp /* >= 33 ints */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        const int v = i < n ? a[i] : 0;
-        int x = v;
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= d) x += o;
+    if (ng) atomicAdd(&s_ng, ng);
+    const int nu = block_exclusive_scan(group + ro, R, s_warp);
+    for (int r = threadIdx.x; r < R; r += blockDim.x)
+        if (lu[r] == r) {
+            leaders[ro + group[ro + r]] = r;
+            leader_len[ro + group[ro + r]] = ulen[ro + r];
         }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            int y = lane < nw ? s_warp[lane] : 0;
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, y, d);
-                if (lane >= d) y += o;
-            }
-            s_warp[lane] = y;  // inclusive over warps
-        }
-        __syncthreads();
-        const int warp_excl = warp ? s_warp[warp - 1] : 0;
-        if (i < n) a[i] = carry + warp_excl + x - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += s_warp[nw - 1];
-        __syncthreads();
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int a = lu[r];
+        if (a != r) group[ro + r] = group[ro + a];  // a is a leader (a < r): its entry is final
     }
-    return carry;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        n_ungapped[ti] = nu;
+        n_gapped[ti] = s_ng;
+    }
 }
 
 // ---- dedupe of deep tasks -------------------------------------------------------------------------

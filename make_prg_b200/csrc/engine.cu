@@ -575,14 +575,24 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         std::vector<int> big_q;  // deep loci: these problems get the whole GPU, one after the other
         for (int q = 0; q < np; ++q)
             if (st[q].big) big_q.push_back(q);
-        for (int round = 2; round <= MAX_CLUSTERS; ++round) {
+        // A problem with n distinct sequences stops at K == n (cluster_sequences.py:257-259), so its last
+        // KMeans round is K = n - 1: the level needs rounds 2 .. max n - 1, not always 2 .. 10 (a deep level
+        // of a pangenome batch has max n = 3 or 4: one or two rounds instead of nine)
+        int max_n = 0;
+        long long max_elements = 0;
+        for (int q = 0; q < np; ++q) {
+            max_n = std::max(max_n, probs[q].n);
+            if (!st[q].big) max_elements = std::max(max_elements, (long long)st[q].n * st[q].F);
+        }
+        const int last_round = std::min(MAX_CLUSTERS, max_n - 1);
+        for (int round = 2; round <= last_round; ++round) {
             for (int q : big_q) {
                 MPRG_CUDA(ctx, launch_kmeans_group(s, d_states, q, B[12].as<double>(), d_kmd, d_kmi, d_assign,
                                                    d_newlab, d_bars, round == 2, ctx->sm_count));
                 ctx->launches += round == 2 ? 2 : 1;
             }
             MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab,
-                                         d_tickets));
+                                         d_tickets, max_elements));
             MPRG_CUDA(ctx, refcheck_all());
             ctx->launches++;
         }

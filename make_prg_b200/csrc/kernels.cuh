@@ -144,7 +144,8 @@ cudaError_t launch_kmeans_group(cudaStream_t s, ClusterState *states, int q, con
                                 double *inertia_out = nullptr);
 cudaError_t kmeans_group_upload_rand(const double *h_rand);
 cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, const double *X,
-                          double *dscratch, int *iscratch, int *assign, int *newlab, int *tickets);
+                          double *dscratch, int *iscratch, int *assign, int *newlab, int *tickets,
+                          long long max_elements);
 cudaError_t launch_kmeans_single(cudaStream_t s, const double *X0, int n, int F, int K, double *dscratch,
                                  int *iscratch, int *labels, double *inertia, int *ticket);
 

@@ -1055,11 +1055,18 @@ cudaError_t kmeans_upload_rand(const double *h_rand) {
     return cudaMemcpyToSymbol(c_rand, h_rand, sizeof(double) * KM_RAND_COUNT);
 }
 
+// max_elements: the largest n * F of the level.  The loops of an initialisation stride over whatever
+// threads it has (the results do not depend on their number: test_kmeans_cta_groups_equal_single_cta),
+// so the many tiny problems of a pangenome level (n <= 8, F <= 70) get one warp per CTA: four times as
+// many initialisations resident per SM at 128 registers per thread, cheaper barriers.
 cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, const double *X,
-                          double *dscratch, int *iscratch, int *assign, int *newlab, int *tickets) {
+                          double *dscratch, int *iscratch, int *assign, int *newlab, int *tickets,
+                          long long max_elements) {
     if (n_probs <= 0) return cudaSuccess;
-    kmeans_kernel<<<dim3(n_probs, KM_NINIT), KM_THREADS, 0, s>>>(states, X, dscratch, iscratch, assign, newlab,
-                                                                 tickets);
+    int threads = max_elements <= 1024 ? 32 : (max_elements <= 8192 ? 64 : KM_THREADS);
+    if (const char *e = getenv("MPRG_KM_THREADS")) threads = std::max(32, std::min(atoi(e) & ~31, KM_THREADS));
+    kmeans_kernel<<<dim3(n_probs, KM_NINIT), threads, 0, s>>>(states, X, dscratch, iscratch, assign, newlab,
+                                                              tickets);
     return cudaGetLastError();
 }
 
