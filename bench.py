@@ -279,16 +279,18 @@ def main():
 
     def step_resident(batch):
         res = ctx.build(batch, MAX_NESTING, MIN_MATCH)
-        n_ok = sum(1 for i in range(n_loci) if res.status(i) == 0)
-        total_len = sum(len(res.prg(i)) for i in range(0, n_loci, 97))
+        status, lengths = res.statuses()
+        n_ok = int((status == 0).sum())
+        total_len = int(lengths.sum()) + sum(len(res.prg(i)) for i in range(0, n_loci, 97))
         res.free()
         return n_ok, total_len
 
     def step_e2e():
         # the public one-call path: pinned host ASCII in, PRG strings out (mprg_build_ascii)
         batch, res = ctx.build_ascii((host_np, shapes), MAX_NESTING, MIN_MATCH)
-        n_ok = sum(1 for i in range(n_loci) if res.status(i) == 0)
-        total_len = sum(len(res.prg(i)) for i in range(0, n_loci, 97))
+        status, lengths = res.statuses()
+        n_ok = int((status == 0).sum())
+        total_len = int(lengths.sum()) + sum(len(res.prg(i)) for i in range(0, n_loci, 97))
         res.free()
         batch.free()
         return n_ok, total_len

@@ -205,6 +205,8 @@ int mprg_result_from_prgs(const char *const *prgs, const int64_t *lengths, int32
 void mprg_result_free(mprg_result *res);
 int32_t mprg_result_n_loci(const mprg_result *res);
 int32_t mprg_result_status(const mprg_result *res, int32_t locus);
+/* all loci at once: status and PRG length per locus (either array may be NULL) */
+int mprg_result_statuses(const mprg_result *res, int32_t *h_status, int64_t *h_prg_length);
 /* PRG string of a locus (not NUL-terminated); valid until mprg_result_free */
 const char *mprg_result_prg(const mprg_result *res, int32_t locus, int64_t *length);
 int32_t mprg_result_n_nodes(const mprg_result *res, int32_t locus);

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mprg_result_free": (None, [P]),
     "mprg_result_n_loci": (I32, [P]),
     "mprg_result_status": (I32, [P, I32]),
+    "mprg_result_statuses": (C.c_int, [P, P, P]),
     "mprg_result_prg": (P, [P, I32, C.POINTER(I64)]),
     "mprg_result_n_nodes": (I32, [P, I32]),
     "mprg_result_n_sites": (I32, [P, I32]),

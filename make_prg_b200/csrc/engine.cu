@@ -127,8 +127,11 @@ extract_kernel(const uint8_t *__restrict__ packed, const ExtractItem *__restrict
 // ---- clustering of a level ------------------------------------------------------------------------
 struct ClusterOut {
     int n_ungapped = 0, n_gapped = 0;
-    std::vector<int> leaders;     // task-local row position of each distinct ungapped sequence (first-seen order)
-    std::vector<int> leader_len;  // its ungapped length
+    // task-local row position of each distinct ungapped sequence (first-seen order) and its ungapped
+    // length: n_ungapped entries each, views into the context's pinned result buffer (valid until the next
+    // clustering level on that context) -- a level has tens of thousands of tasks, no vector per task
+    const int *leaders = nullptr;
+    const int *leader_len = nullptr;
     bool no_clustering = true;    // ClusteringResult.no_clustering
     bool clustered = false;       // kmeans_cluster_seqs was evaluated for this task
     int n_labels = 0;             // KMeans clusters (labels 0..n_labels-1) when !no_clustering
@@ -314,7 +317,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
     // Results of the de-duplication in ONE trip when the level is small (nu | ng | err and the per-row
     // leader arrays as they are, O(rows)); big levels first fetch the counts, compact the leaders on the
     // device and fetch O(#distinct) -- a second synchronisation that a pangenome level does not need.
-    const bool one_trip = 2LL * row_total * (long long)sizeof(int) <= (8LL << 20);
+    const bool one_trip = 2LL * row_total * (long long)sizeof(int) <= (256LL << 10);  // root levels: 30 tasks of 200 rows per locus
     if (!one_trip) MPRG_CUDA(ctx, launch_scan_counts(s, d_nu, n_tasks, d_leadoff));
     ctx->launches += one_trip ? 2 : 3;
     TRACE("cl: setup+launch dedupe");
@@ -363,8 +366,8 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         ClusterOut &o = out[i];
         o.n_ungapped = h_nu[i];
         o.n_gapped = h_ng[i];
-        o.leaders.assign(h_dense + lead_base[i], h_dense + lead_base[i] + o.n_ungapped);
-        o.leader_len.assign(h_dense + lead_total + lead_base[i], h_dense + lead_total + lead_base[i] + o.n_ungapped);
+        o.leaders = h_dense + lead_base[i];
+        o.leader_len = h_dense + lead_total + lead_base[i];
         if (want_clusters && !want_clusters[i]) continue;
         if (h_R[i] == 0) continue;
         // NodeFactory._alignment_has_issues (recursion_tree.py:475-494) discards the clustering anyway
@@ -906,7 +909,8 @@ struct HNode {
     int c0 = 0, c1 = 0;
     long long row_off = -1;  // into the locus row pool, -1 = all rows
     int n_rows = 0;
-    std::vector<int> children;
+    // the children of a node are created one after the other: nodes [first_child, first_child + n_children)
+    int first_child = -1, n_children = 0;
     int allele_first = -1, allele_count = 0;  // extract items of a leaf
 };
 
@@ -1097,7 +1101,7 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
                     ch.n_rows = L.nodes[ni].n_rows;
                     const int ci = (int)L.nodes.size();
                     L.nodes.push_back(ch);
-                    L.nodes[ni].children.push_back(ci);
+                    if (L.nodes[ni].n_children++ == 0) L.nodes[ni].first_child = ci;
                     // a pure match interval re-partitions to itself: leaf without another scan
                     if (ivs[k].type == MPRG_IV_MATCH) make_match_leaf(l, L.nodes[ci]);
                     else next.push_back(Pending{l, ci});
@@ -1173,7 +1177,7 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
                         off += cl_count[c];
                         const int ci = (int)L.nodes.size();
                         L.nodes.push_back(ch);
-                        L.nodes[ni].children.push_back(ci);
+                        if (L.nodes[ni].n_children++ == 0) L.nodes[ni].first_child = ci;
                         next.push_back(Pending{l, ci});
                     }
                 } else {
@@ -1311,10 +1315,10 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
                 }
             } else if (nd.kind == MPRG_NODE_CLUSTER) {
                 // separator after child (next_child - 1)
-                emit_marker(f.next_child < (int)nd.children.size() ? f.site + 1 : f.site);
+                emit_marker(f.next_child < nd.n_children ? f.site + 1 : f.site);
             }
-            if (f.next_child < (int)nd.children.size()) {
-                const int ch = nd.children[f.next_child];
+            if (f.next_child < nd.n_children) {
+                const int ch = nd.first_child + f.next_child;
                 f.next_child++;
                 stack.push_back(Frame{ch, 0, 0});
             } else {
@@ -1508,6 +1512,14 @@ extern "C" int32_t mprg_result_n_loci(const mprg_result *res) { return res ? (in
 extern "C" int32_t mprg_result_status(const mprg_result *res, int32_t l) {
     return (res && l >= 0 && l < (int)res->loci.size()) ? res->loci[l].status : -1;
 }
+extern "C" int mprg_result_statuses(const mprg_result *res, int32_t *h_status, int64_t *h_prg_length) {
+    if (!res) return MPRG_E_BAD_ARG;
+    for (size_t l = 0; l < res->loci.size(); ++l) {
+        if (h_status) h_status[l] = res->loci[l].status;
+        if (h_prg_length) h_prg_length[l] = (int64_t)res->loci[l].prg.size();
+    }
+    return MPRG_OK;
+}
 extern "C" const char *mprg_result_prg(const mprg_result *res, int32_t l, int64_t *length) {
     if (!res || l < 0 || l >= (int)res->loci.size()) return nullptr;
     if (length) *length = (int64_t)res->loci[l].prg.size();
@@ -1535,7 +1547,7 @@ extern "C" int mprg_result_nodes(const mprg_result *res, int32_t l, int32_t *kin
         if (c1) c1[i] = nd.c1;
         if (n_rows) n_rows[i] = nd.n_rows;
         if (row_off) row_off[i] = nd.row_off;
-        if (n_children) n_children[i] = (int)nd.children.size();
+        if (n_children) n_children[i] = nd.n_children;
     }
     return MPRG_OK;
 }

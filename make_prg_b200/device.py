@@ -114,20 +114,21 @@ class Context:
     def _flatten(matrices):
         if isinstance(matrices, tuple):
             flat, shapes = matrices
-            shapes = [tuple(s) for s in shapes]
+            shape_arr = np.asarray(shapes, np.int64).reshape(-1, 2)
         else:
-            shapes = [tuple(m.shape) for m in matrices]
+            shape_arr = np.array([m.shape for m in matrices], np.int64).reshape(-1, 2)
             flat = (np.concatenate([np.ascontiguousarray(m, np.uint8).reshape(-1) for m in matrices])
                     if matrices else np.zeros(0, np.uint8))
-        sizes = np.array([r * c for r, c in shapes], np.int64)
-        offsets = np.zeros(len(shapes), np.int64)
-        if len(shapes):
+        sizes = shape_arr[:, 0] * shape_arr[:, 1]
+        offsets = np.zeros(len(shape_arr), np.int64)
+        if len(shape_arr):
             offsets[1:] = np.cumsum(sizes)[:-1]
-        n_rows = np.array([s[0] for s in shapes], np.int32)
-        n_cols = np.array([s[1] for s in shapes], np.int32)
+        n_rows = np.ascontiguousarray(shape_arr[:, 0], np.int32)
+        n_cols = np.ascontiguousarray(shape_arr[:, 1], np.int32)
         if flat.size == 0:
             flat = np.zeros(1, np.uint8)
-        return flat, shapes, offsets, n_rows, n_cols
+        # shapes: indexable per locus as (rows, cols); an int64[n, 2] array, no per-locus Python objects
+        return flat, shape_arr, offsets, n_rows, n_cols
 
     def upload(self, matrices):
         """matrices: list of uint8[rows, cols] ASCII arrays (or one flat buffer + shapes tuple)."""
@@ -309,6 +310,13 @@ class BuildResult:
 
     def status(self, locus):
         return int(self.ctx.lib.mprg_result_status(self.handle, locus))
+
+    def statuses(self):
+        """(status int32[n_loci], PRG length int64[n_loci]) in one call."""
+        st = np.zeros(max(self.n_loci, 1), np.int32)
+        ln = np.zeros(max(self.n_loci, 1), np.int64)
+        self.ctx._check(self.ctx.lib.mprg_result_statuses(self.handle, ptr(st), ptr(ln)))
+        return st[:self.n_loci], ln[:self.n_loci]
 
     def prg(self, locus):
         n = C.c_int64(0)

@@ -87,7 +87,8 @@ class MsaSet:
         return MSA.from_matrix(self.ids(locus), self.matrix(locus).copy(), descriptions=self.titles(locus))
 
     def shapes(self):
-        return [(int(r), int(c)) for r, c in zip(self.n_rows, self.n_cols)]
+        """int64[n_loci, 2] (rows, cols)."""
+        return np.stack([self.n_rows.astype(np.int64), self.n_cols.astype(np.int64)], axis=1)
 
     def free(self):
         if self.handle is not None:

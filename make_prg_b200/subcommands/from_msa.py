@@ -159,8 +159,9 @@ def iter_built_chunks(input_files, options, device_ordinal=0):
             batch, res = ctx.build_msa_set(msas, options.max_nesting, options.min_match_length)
             batch.free()
             ok = []
+            statuses, _lengths = res.statuses()
             for i, name in enumerate(names):
-                status = res.status(i)
+                status = int(statuses[i])
                 if status == LOCUS_OK:
                     ok.append(i)
                 elif status == LOCUS_CURATION_ERROR:

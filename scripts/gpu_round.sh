@@ -13,3 +13,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 cat gpurun_out/bench_$TAG.json
 tail -3 gpurun_out/bench_$TAG.err
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee gpurun_out/smoke_$TAG.log
+python scripts/run_configs.py 3,5,4r,4 2>&1 | tail -10 > gpurun_out/configs_$TAG.jsonl
+python scripts/ncu_summary.py gpurun_out/scan_$TAG.ncu-rep > gpurun_out/scan_$TAG.txt 2>&1
+python scripts/launch_summary.py gpurun_out/launches_$TAG.csv > gpurun_out/launches_${TAG}_summary.txt 2>&1
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err
+cut -c1-300 gpurun_out/configs_$TAG.jsonl
