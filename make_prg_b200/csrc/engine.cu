@@ -1240,6 +1240,12 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
     TRACE("build: allele extraction");
     // ---- pre-order numbering and PRG strings (recursion_tree.py:194-300, prg_builder.py:100-110) ----
     std::vector<std::string> raw, expanded;
+    struct Frame {
+        int node;
+        int next_child;
+        int site;
+    };
+    std::vector<Frame> stack;
     for (int l = l_begin; l < l_end; ++l) {
         LocusResult &L = res->loci[l];
         if (L.status != MPRG_LOCUS_OK) continue;
@@ -1247,17 +1253,19 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
         // that a 200 MB PRG (deep locus) is not grown by doubling
         L.prg.reserve((size_t)prg_bound[l - l_begin] + 12 * L.nodes.size() + 64);
         int site = 5;
-        struct Frame {
-            int node;
-            int next_child;
-            int site;
-        };
-        std::vector<Frame> stack;
+        L.preorder.reserve(L.nodes.size());
+        stack.clear();
         stack.push_back(Frame{0, 0, 0});
         auto emit_marker = [&](int m) {
-            L.prg.push_back(' ');
-            L.prg += std::to_string(m);
-            L.prg.push_back(' ');
+            char buf[16];
+            int k = 15;
+            buf[k] = ' ';
+            do {
+                buf[--k] = (char)('0' + m % 10);
+                m /= 10;
+            } while (m);
+            buf[--k] = ' ';
+            L.prg.append(buf + k, (size_t)(16 - k));
         };
         while (!stack.empty() && L.status == MPRG_LOCUS_OK) {
             Frame &f = stack.back();
