@@ -100,7 +100,7 @@ def cut_chunks(input_files, max_bytes=None, max_loci=16384):
     chunks, cur, size = [], [], 0
     for path in input_files:
         try:
-            nbytes = os.path.getsize(path)
+            nbytes = os.stat(path).st_size
         except OSError:
             nbytes = 0
         if cur and (size + nbytes > max_bytes or len(cur) >= max_loci):
@@ -129,7 +129,19 @@ def _load_chunk(paths, alignment_format, threads=None):
     return hostio.load_fasta_files(paths, threads=threads)
 
 
-def iter_built_chunks(input_files, options, device_ordinal=0):
+_EXTENSIONS = (".fasta.gz", ".fa.gz", ".fasta", ".fa")
+
+
+def locus_name_of(path):
+    """remove_known_input_extensions(Path(path).name) without the Path object and the regular expression."""
+    name = os.path.basename(os.fspath(path))
+    for ext in _EXTENSIONS:
+        if name.endswith(ext):
+            return name[:-len(ext)]
+    return name
+
+
+def iter_built_chunks(input_files, options, device_ordinal=0, chunks=None):
     """Loads (native loader, one chunk ahead on a host thread) and builds (mprg_build_ascii) the input
     files chunk by chunk.  Yields (names, msas, result, ok) with ok = indices of the chunk's loci that
     were built; the consumer frees result and msas.  Errors follow from_msa.py:142-151: an empty MSA
@@ -139,7 +151,8 @@ def iter_built_chunks(input_files, options, device_ordinal=0):
     from .. import device
 
     ctx = device.default_context(device_ordinal)
-    chunks = cut_chunks(input_files)
+    if chunks is None:
+        chunks = cut_chunks(input_files)
     with ThreadPoolExecutor(1) as pool:
         threads = side_threads(len(chunks))
         future = pool.submit(_load_chunk, chunks[0], options.alignment_format, threads) if chunks else None
@@ -147,7 +160,7 @@ def iter_built_chunks(input_files, options, device_ordinal=0):
             msas = future.result()
             future = (pool.submit(_load_chunk, chunks[k + 1], options.alignment_format, threads)
                       if k + 1 < len(chunks) else None)
-            names = [remove_known_input_extensions(Path(path).name) for path in paths]
+            names = [locus_name_of(path) for path in paths]
             logger.info(f"Generating PRGs for {names[0]} ... {names[-1]} ({len(names)} loci)...")
             for i in np.nonzero(msas.status != hostio.LOAD_OK)[0]:
                 try:
@@ -158,17 +171,14 @@ def iter_built_chunks(input_files, options, device_ordinal=0):
                     raise
             batch, res = ctx.build_msa_set(msas, options.max_nesting, options.min_match_length)
             batch.free()
-            ok = []
             statuses, _lengths = res.statuses()
-            for i, name in enumerate(names):
-                status = int(statuses[i])
-                if status == LOCUS_OK:
-                    ok.append(i)
-                elif status == LOCUS_CURATION_ERROR:
-                    logger.warning(f"Skipping building PRG for {name}. Error: a slice of a sequence has a "
+            ok = np.nonzero(statuses == LOCUS_OK)[0].tolist()
+            for i in np.nonzero(statuses != LOCUS_OK)[0].tolist():
+                if statuses[i] == LOCUS_CURATION_ERROR:
+                    logger.warning(f"Skipping building PRG for {names[i]}. Error: a slice of a sequence has a "
                                    "disallowed base. Redo sequence curation.")
                 else:
-                    engine.LocusBuild(status, "", 0, 0, None).raise_for_status(name)
+                    engine.LocusBuild(int(statuses[i]), "", 0, 0, None).raise_for_status(names[i])
             yield names, msas, res, ok
 
 
@@ -194,8 +204,9 @@ def build_and_write(input_files, options, device_ordinal=0, output_prefix=None):
     prefix = output_prefix or options.output_prefix
     ot = options.output_type
     want_ds = ot.prg and not getattr(options, "skip_update_ds", False)
+    chunks = cut_chunks(input_files)
     writer = hostio.OutputWriter(prefix, prg=ot.prg, binary=ot.binary, gfa=ot.gfa,
-                                 threads=side_threads(len(cut_chunks(input_files)), writer=True))
+                                 threads=side_threads(len(chunks), writer=True))
     ds_zip = None
     n_ok = 0
     pending = None  # (future, msas, res): the chunk being encoded / written on the writer thread
@@ -210,7 +221,7 @@ def build_and_write(input_files, options, device_ordinal=0, output_prefix=None):
 
     try:
         with ThreadPoolExecutor(1) as pool:
-            for names, msas, res, ok in iter_built_chunks(input_files, options, device_ordinal):
+            for names, msas, res, ok in iter_built_chunks(input_files, options, device_ordinal, chunks):
                 if pending is not None:
                     finish(pending)
                     pending = None
@@ -220,7 +231,8 @@ def build_and_write(input_files, options, device_ordinal=0, output_prefix=None):
                     for name, blob in _update_ds_pickles(names, msas, res, ok, options):
                         ds_zip.writestr(name, blob)
                 n_ok += len(ok)
-                pending = (pool.submit(writer.add, res, ok, [names[i] for i in ok]), msas, res)
+                ok_names = names if len(ok) == len(names) else [names[i] for i in ok]
+                pending = (pool.submit(writer.add, res, ok, ok_names), msas, res)
             if pending is not None:
                 finish(pending)
                 pending = None
