@@ -696,78 +696,111 @@ extern "C" const char *mprg_fasta_titles(const mprg_msa_set *set, int32_t locus,
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// output buffer of an encoder: allocated to an upper bound WITHOUT being zero-filled (the tail that is
+// never written is never touched, so never paged in), then cut to the length written
+template <typename T>
+struct RawBuf {
+    std::unique_ptr<T[]> p;
+    size_t n = 0;
+    void allocate(size_t capacity) {
+        p.reset(new T[capacity > 0 ? capacity : 1]);
+        n = 0;
+    }
+    T *data() { return p.get(); }
+    const T *data() const { return p.get(); }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+};
+
+const char GFA_HEADER[] = "H\tVN:Z:1.0\tbn:Z:--linear --singlearr\n";
+
 inline bool is_py_space(unsigned char c) {  // str.split() separators within ASCII
     return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f);
 }
 
-inline int base_code(unsigned char c) {
-    switch (c) {
-        case 'A': case 'a': return 1;
-        case 'C': case 'c': return 2;
-        case 'G': case 'g': return 3;
-        case 'T': case 't': return 4;
-        default: return 0;
+// character classes of a PRG string: 1..4 = A C G T (either case), 5 = digit, 6 = separator, 0 = other
+struct PrgClasses {
+    uint8_t of[256];
+    PrgClasses() {
+        memset(of, 0, sizeof(of));
+        const char *bases = "ACGT";
+        for (int k = 0; k < 4; ++k) {
+            of[(unsigned char)bases[k]] = (uint8_t)(k + 1);
+            of[(unsigned char)(bases[k] + 32)] = (uint8_t)(k + 1);
+        }
+        for (int c = '0'; c <= '9'; ++c) of[c] = 5;
+        for (int c = 0; c < 256; ++c)
+            if (is_py_space((unsigned char)c)) of[c] = 6;
     }
-}
+};
+const PrgClasses PRG_CLASSES;
 
 // prg_encoder.py:44-91.  Returns 0, or MPRG_ENC_* on the reference's exceptions.
-int encode_prg(const char *prg, int64_t len, std::vector<uint32_t> &out) {
-    out.clear();
-    out.reserve((size_t)len);
-    std::unordered_map<uint64_t, int> seen;  // odd marker -> times seen
+int encode_prg(const char *prg, int64_t len, RawBuf<uint32_t> &out) {
+    out.allocate((size_t)len);  // one value per base or marker: never more than characters
+    uint32_t *o = out.data();
+    const uint8_t *cls = PRG_CLASSES.of;
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(prg);
+    // odd marker -> times seen; sites close in LIFO order, so the search runs from the back
+    std::vector<std::pair<uint64_t, int>> seen;
     int64_t i = 0;
     while (i < len) {
-        while (i < len && is_py_space((unsigned char)prg[i])) ++i;
-        if (i >= len) break;
+        if (cls[p[i]] == 6) {
+            ++i;
+            continue;
+        }
         const int64_t u0 = i;
-        bool all_bases = true, all_digits = true;
-        while (i < len && !is_py_space((unsigned char)prg[i])) {
-            const unsigned char c = (unsigned char)prg[i];
-            all_bases &= base_code(c) != 0;
-            all_digits &= (c >= '0' && c <= '9');
+        uint32_t *o0 = o;
+        unsigned all = 0xff, any = 0;
+        while (i < len) {  // written as bases while scanning; rewound if the unit is something else
+            const unsigned c = cls[p[i]];
+            if (c == 6) break;
+            *o++ = c;
+            all &= (c >= 1 && c <= 4) ? 1u : (c == 5 ? 2u : 0u);
+            any = 1;
             ++i;
         }
-        if (all_bases) {
-            for (int64_t j = u0; j < i; ++j) out.push_back((uint32_t)base_code((unsigned char)prg[j]));
-        } else if (all_digits) {
-            uint64_t m = 0;
-            for (int64_t j = u0; j < i; ++j) {
-                m = m * 10 + (uint64_t)(prg[j] - '0');
-                if (m > 0xFFFFFFFFull) return MPRG_ENC_OVERFLOW;
-            }
-            if ((m & 1) == 0) {
-                out.push_back((uint32_t)m);
-            } else {
-                const int times = ++seen[m];
-                if (times > 2) return MPRG_ENC_ODD_MARKER_REPEATED;
-                if (times == 2 && m + 1 > 0xFFFFFFFFull) return MPRG_ENC_OVERFLOW;
-                out.push_back((uint32_t)(times == 1 ? m : m + 1));
-            }
-        } else {
-            return MPRG_ENC_INVALID_UNIT;
+        (void)any;
+        if (all & 1u) continue;  // a unit of bases
+        o = o0;
+        if (!(all & 2u)) return MPRG_ENC_INVALID_UNIT;
+        uint64_t m = 0;
+        for (int64_t j = u0; j < i; ++j) {
+            m = m * 10 + (uint64_t)(p[j] - '0');
+            if (m > 0xFFFFFFFFull) return MPRG_ENC_OVERFLOW;
         }
+        if ((m & 1) == 0) {
+            *o++ = (uint32_t)m;
+            continue;
+        }
+        int times = 0;
+        for (size_t k = seen.size(); k-- > 0;)
+            if (seen[k].first == m) {
+                times = ++seen[k].second;
+                break;
+            }
+        if (times == 0) {
+            seen.emplace_back(m, 1);
+            times = 1;
+        }
+        if (times > 2) return MPRG_ENC_ODD_MARKER_REPEATED;
+        if (times == 2 && m + 1 > 0xFFFFFFFFull) return MPRG_ENC_OVERFLOW;
+        *o++ = (uint32_t)(times == 1 ? m : m + 1);
     }
+    out.n = (size_t)(o - out.data());
     return 0;
 }
 
-inline void put_uint(std::string &s, uint64_t v) {
-    char tmp[24];
-    int n = 0;
-    do {
-        tmp[n++] = (char)('0' + v % 10);
-        v /= 10;
-    } while (v);
-    while (n) s.push_back(tmp[--n]);
-}
-
 // gfa.py:39-109 as one recursive descent over the token stream (markers are " <digits> ", anything
-// else between spaces is sequence); segment / link ids come out in the reference's order.
+// else between spaces is sequence); segment / link ids come out in the reference's order.  The text is
+// written through a raw pointer into a buffer sized to its upper bound.
 struct GfaBuilder {
     const char *p;
     int64_t len, i = 0;
-    std::string out;
+    char *w = nullptr;
     uint64_t gfa_id = 0;
     bool bad = false;
+    std::vector<uint64_t> ids;  // ends of the alleles of the open sites (a stack shared by the recursion)
 
     enum Tok { END, LITERAL, MARKER };
     Tok tok = END;
@@ -793,40 +826,53 @@ struct GfaBuilder {
                 continue;
             }
             lit0 = i;
-            while (i < len && p[i] != ' ') ++i;
+            const void *sp = memchr(p + i, ' ', (size_t)(len - i));
+            i = sp ? (int64_t)((const char *)sp - p) : len;
             lit1 = i;
             tok = LITERAL;
             return;
         }
         tok = END;
     }
+    inline void put(const char *s, size_t n) {
+        memcpy(w, s, n);
+        w += n;
+    }
+    inline void put_uint(uint64_t v) {
+        char tmp[24];
+        int n = 0;
+        do {
+            tmp[n++] = (char)('0' + v % 10);
+            v /= 10;
+        } while (v);
+        while (n) *w++ = tmp[--n];
+    }
     void segment(int64_t a, int64_t b, const std::string *extra) {
-        out += "S\t";
-        put_uint(out, gfa_id);
-        out.push_back('\t');
+        put("S\t", 2);
+        put_uint(gfa_id);
+        *w++ = '\t';
         if (extra && !extra->empty())
-            out += *extra;
+            put(extra->data(), extra->size());
         else if (b > a)
-            out.append(p + a, (size_t)(b - a));
+            put(p + a, (size_t)(b - a));
         else
-            out.push_back('*');
-        out += "\tRC:i:0\n";
+            *w++ = '*';
+        put("\tRC:i:0\n", 8);
     }
     void link(uint64_t a, uint64_t b) {
-        out += "L\t";
-        put_uint(out, a);
-        out += "\t+\t";
-        put_uint(out, b);
-        out += "\t+\t0M\n";
+        put("L\t", 2);
+        put_uint(a);
+        put("\t+\t", 3);
+        put_uint(b);
+        put("\t+\t0M\n", 6);
     }
     // One (sub)string of the PRG: literal? (site literal?)*.  open_marker = odd marker of the enclosing
     // site (0 at top level).  Returns the id of the segment that ends it; on return `tok` is the token
     // that ended the sequence (END, the closing odd marker, or the even separator).
     uint64_t sequence(uint64_t open_marker, int depth) {
-        std::vector<uint64_t> end_ids;
-        int64_t a = 0, b = 0;     // pending literal as one slice of the input ...
-        std::string joined;       // ... or, when several literal tokens follow each other, their join
-        auto flush_segment = [&]() { segment(a, b, &joined); };
+        const size_t base = ids.size();  // ids[base..) = ends of the alleles of the site just closed
+        int64_t a = 0, b = 0;            // pending literal as one slice of the input ...
+        std::string joined;              // ... or, when several literal tokens follow each other, their join
         while (!bad) {
             if (tok == LITERAL) {
                 if (b > a || !joined.empty()) {
@@ -845,15 +891,16 @@ struct GfaBuilder {
                     break;
                 }
                 const uint64_t site = marker;
-                flush_segment();
+                segment(a, b, &joined);
                 const uint64_t pre = gfa_id++;
-                for (uint64_t e : end_ids) link(e, pre);
-                end_ids.clear();
+                for (size_t k = base; k < ids.size(); ++k) link(ids[k], pre);
+                ids.resize(base);
                 int alleles = 0;
                 advance();
                 while (!bad) {
                     link(pre, gfa_id);
-                    end_ids.push_back(sequence(site, depth + 1));
+                    const uint64_t last = sequence(site, depth + 1);
+                    ids.push_back(last);
                     ++alleles;
                     if (tok == MARKER && marker == site + 1) {  // next allele
                         advance();
@@ -874,24 +921,29 @@ struct GfaBuilder {
             if (tok == MARKER && open_marker == 0) bad = true;
             break;  // END, my closing marker or my separator
         }
-        flush_segment();
-        for (uint64_t e : end_ids) link(e, gfa_id);
+        segment(a, b, &joined);
+        for (size_t k = base; k < ids.size(); ++k) link(ids[k], gfa_id);
+        ids.resize(base);
         return gfa_id++;
     }
 };
 
-const char GFA_HEADER[] = "H\tVN:Z:1.0\tbn:Z:--linear --singlearr\n";
-
-int prg_to_gfa(const char *prg, int64_t len, std::string &out) {
+int prg_to_gfa(const char *prg, int64_t len, RawBuf<char> &out) {
     GfaBuilder g;
     g.p = prg;
     g.len = len;
-    g.out.reserve((size_t)len * 3 + 64);
-    g.out = GFA_HEADER;
+    // upper bound of the text: every input character once, and per marker token at most two segment
+    // lines and three link lines (each id < 2 * markers + 2, so at most 20 digits)
+    size_t spaces = 0;
+    for (int64_t k = 0; k < len; ++k) spaces += prg[k] == ' ';
+    const size_t tokens = spaces / 2 + 2;
+    out.allocate(sizeof(GFA_HEADER) + (size_t)len + tokens * (2 * 36 + 3 * 56) + 64);
+    g.w = out.data();
+    g.put(GFA_HEADER, sizeof(GFA_HEADER) - 1);
     g.advance();
     g.sequence(0, 0);
     if (g.bad || g.tok != GfaBuilder::END) return MPRG_ENC_INVALID_UNIT;
-    out.swap(g.out);
+    out.n = (size_t)(g.w - out.data());
     return 0;
 }
 
@@ -1027,8 +1079,8 @@ bool write_whole(const std::string &path, const void *data, size_t n) {
 
 struct Encoded {
     std::string name;
-    std::vector<uint32_t> bin;
-    std::string gfa;
+    RawBuf<uint32_t> bin;
+    RawBuf<char> gfa;
     uint32_t crc_bin = 0, crc_gfa = 0;
     int rc = 0;
 };
@@ -1047,7 +1099,7 @@ struct mprg_writer {
 
 extern "C" int mprg_encode_prg(const char *prg, int64_t length, uint32_t *out, int64_t capacity, int64_t *n) {
     if ((!prg && length > 0) || length < 0 || !n) return MPRG_E_BAD_ARG;
-    std::vector<uint32_t> v;
+    RawBuf<uint32_t> v;
     const int rc = encode_prg(prg, length, v);
     if (rc) return rc;
     *n = (int64_t)v.size();
@@ -1057,7 +1109,7 @@ extern "C" int mprg_encode_prg(const char *prg, int64_t length, uint32_t *out, i
 
 extern "C" int mprg_prg_to_gfa(const char *prg, int64_t length, char *out, int64_t capacity, int64_t *n) {
     if ((!prg && length > 0) || length < 0 || !n) return MPRG_E_BAD_ARG;
-    std::string s;
+    RawBuf<char> s;
     const int rc = prg_to_gfa(prg, length, s);
     if (rc) return rc;
     *n = (int64_t)s.size();
@@ -1114,39 +1166,86 @@ extern "C" int mprg_writer_add(mprg_writer *w, const mprg_result *res, const int
             e.crc_gfa = (uint32_t)crc32(0L, (const Bytef *)e.gfa.data(), (uInt)e.gfa.size());
         }
     });
-    for (int i = 0; i < n; ++i) {
-        Encoded &e = enc[(size_t)i];
-        if (e.rc) {
-            w->err = "PRG of " + e.name + " cannot be encoded";
-            return e.rc;
+    for (int i = 0; i < n; ++i)
+        if (enc[(size_t)i].rc) {
+            w->err = "PRG of " + enc[(size_t)i].name + " cannot be encoded";
+            return enc[(size_t)i].rc;
         }
+    if (n == 0) return MPRG_OK;
+    // the only locus of a run is kept back: one locus => plain files, no archives
+    int begin = 0;
+    if (w->n_added == 0 && n == 1) {
         if (what & MPRG_WRITE_PRG) {
             int64_t len = 0;
-            const char *prg = mprg_result_prg(res, h_loci[i], &len);
-            w->fa.emplace_back(e.name, std::string(prg, (size_t)len));
+            const char *prg = mprg_result_prg(res, h_loci[0], &len);
+            w->fa.emplace_back(enc[0].name, std::string(prg, (size_t)len));
         }
-        if (w->n_added == 0) {
-            w->first = std::move(e);
-        } else {
-            if (!w->zips_open) {
-                if ((what & MPRG_WRITE_BIN) && !w->zbin.open_path(w->prefix + ".prg.bin.zip")) {
-                    w->err = "cannot create " + w->prefix + ".prg.bin.zip: " + strerror(errno);
-                    return MPRG_E_INTERNAL;
-                }
-                if ((what & MPRG_WRITE_GFA) && !w->zgfa.open_path(w->prefix + ".prg.gfa.zip")) {
-                    w->err = "cannot create " + w->prefix + ".prg.gfa.zip: " + strerror(errno);
-                    return MPRG_E_INTERNAL;
-                }
-                w->zips_open = true;
-                const int rc = writer_flush_entry(w, w->first);
-                if (rc) return rc;
-                w->first = Encoded();
-            }
-            const int rc = writer_flush_entry(w, e);
-            if (rc) return rc;
-        }
-        w->n_added++;
+        w->first = std::move(enc[0]);
+        w->n_added = 1;
+        return MPRG_OK;
     }
+    if (!w->zips_open) {
+        if ((what & MPRG_WRITE_BIN) && !w->zbin.open_path(w->prefix + ".prg.bin.zip")) {
+            w->err = "cannot create " + w->prefix + ".prg.bin.zip: " + strerror(errno);
+            return MPRG_E_INTERNAL;
+        }
+        if ((what & MPRG_WRITE_GFA) && !w->zgfa.open_path(w->prefix + ".prg.gfa.zip")) {
+            w->err = "cannot create " + w->prefix + ".prg.gfa.zip: " + strerror(errno);
+            return MPRG_E_INTERNAL;
+        }
+        w->zips_open = true;
+        if (w->n_added == 1) {
+            const int rc = writer_flush_entry(w, w->first);
+            if (rc) return rc;
+            w->first = Encoded();
+        }
+    }
+    // the two archives and the .prg.fa records are independent streams: one host thread each
+    int rc_bin = MPRG_OK, rc_gfa = MPRG_OK;
+    std::string err_bin, err_gfa;
+    auto append_bin = [&]() {
+        for (int i = begin; i < n && rc_bin == MPRG_OK; ++i) {
+            const Encoded &e = enc[(size_t)i];
+            if (!w->zbin.add(e.name + ".bin", e.bin.data(), e.bin.size() * sizeof(uint32_t), e.crc_bin)) {
+                err_bin = "cannot write " + w->prefix + ".prg.bin.zip: " + strerror(errno);
+                rc_bin = MPRG_E_INTERNAL;
+            }
+        }
+    };
+    auto append_gfa = [&]() {
+        for (int i = begin; i < n && rc_gfa == MPRG_OK; ++i) {
+            const Encoded &e = enc[(size_t)i];
+            if (!w->zgfa.add(e.name + ".gfa", e.gfa.data(), e.gfa.size(), e.crc_gfa)) {
+                err_gfa = "cannot write " + w->prefix + ".prg.gfa.zip: " + strerror(errno);
+                rc_gfa = MPRG_E_INTERNAL;
+            }
+        }
+    };
+    std::thread t_bin, t_gfa;
+    const bool threaded = n_threads > 1 && n >= 64;
+    if (what & MPRG_WRITE_BIN) {
+        if (threaded) t_bin = std::thread(append_bin);
+        else append_bin();
+    }
+    if (what & MPRG_WRITE_GFA) {
+        if (threaded) t_gfa = std::thread(append_gfa);
+        else append_gfa();
+    }
+    if (what & MPRG_WRITE_PRG) {
+        w->fa.reserve(w->fa.size() + (size_t)n);
+        for (int i = begin; i < n; ++i) {
+            int64_t len = 0;
+            const char *prg = mprg_result_prg(res, h_loci[i], &len);
+            w->fa.emplace_back(enc[(size_t)i].name, std::string(prg, (size_t)len));
+        }
+    }
+    if (t_bin.joinable()) t_bin.join();
+    if (t_gfa.joinable()) t_gfa.join();
+    if (rc_bin != MPRG_OK || rc_gfa != MPRG_OK) {
+        w->err = rc_bin != MPRG_OK ? err_bin : err_gfa;
+        return MPRG_E_INTERNAL;
+    }
+    w->n_added += n;
     return MPRG_OK;
 }
 
