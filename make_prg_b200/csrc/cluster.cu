@@ -635,8 +635,10 @@ refcheck_kernel(ClusterState *__restrict__ states, const uint8_t *__restrict__ G
                 const int *__restrict__ mem_off_all, const int *__restrict__ mem_rows_all,
                 int *__restrict__ assign_all, uint8_t *__restrict__ maj_all, int max_clusters,
                 int *__restrict__ flags_out) {
+    constexpr int REF_ROWS = 1024;
     __shared__ int cnt_s[16][128];
     __shared__ int first_s[16][128];
+    __shared__ int s_rows[REF_ROWS];
     __shared__ int s_bad, s_bad_c;
     ClusterState &st = states[blockIdx.x];
     if (st.status != 0 || (st.big_ref && !flags_out)) return;  // big problems: launch_refcheck_big
@@ -651,47 +653,120 @@ refcheck_kernel(ClusterState *__restrict__ states, const uint8_t *__restrict__ G
     __syncthreads();
     for (int c = 0; c < K; ++c) {
         if (threadIdx.x == 0) s_bad_c = 0;
-        // majority symbol per column over the members of cluster c in member order
-        for (int col0 = 0; col0 < w; col0 += blockDim.x) {
-            const int col = col0 + threadIdx.x;
-            if (col < w) {
-#pragma unroll
-                for (int s = 0; s < 16; ++s) cnt_s[s][threadIdx.x] = 0;
-                int order = 0;
-                for (int j = 0; j < n; ++j) {
-                    if (assign[j] != c) continue;
-                    for (int m = mem_off[j]; m < mem_off[j + 1]; ++m) {
-                        const int s = g[(long long)mem_rows[m] * w + col];
-                        if (cnt_s[s][threadIdx.x]++ == 0) first_s[s][threadIdx.x] = order;
-                        ++order;
-                    }
+        // the member rows of cluster c in member order (sequence j = threadIdx.x copies its rows behind
+        // those of the earlier sequences of the cluster); clusters of more than REF_ROWS rows take the
+        // plain loops below
+        int my_start = 0, total_rows = 0;
+        for (int j = 0; j < n; ++j) {
+            if (assign[j] != c) continue;
+            const int cnt = mem_off[j + 1] - mem_off[j];
+            if (j < (int)threadIdx.x) my_start += cnt;
+            total_rows += cnt;
+        }
+        const bool listed = total_rows <= REF_ROWS;
+        if (listed) {
+            for (int j = threadIdx.x; j < n; j += blockDim.x) {
+                if (assign[j] != c) continue;
+                int start = 0;
+                if (j == (int)threadIdx.x) {
+                    start = my_start;
+                } else {
+                    for (int q = 0; q < j; ++q)
+                        if (assign[q] == c) start += mem_off[q + 1] - mem_off[q];
                 }
+                for (int m = mem_off[j]; m < mem_off[j + 1]; ++m) s_rows[start + (m - mem_off[j])] = mem_rows[m];
+            }
+        }
+        __syncthreads();
+        // majority symbol per column over the members of cluster c in member order
+        if (listed && w <= (int)blockDim.x / 2) {
+            // narrow windows: the threads are (row slice, column) pairs; slice s counts rows s, s + S, ...,
+            // then the first slice of each column adds the slices up (first-seen = smallest row position)
+            const int S = blockDim.x / w;
+            const int col = threadIdx.x % w, slice = threadIdx.x / w;
+            if (slice < S) {
+#pragma unroll
+                for (int sy = 0; sy < 16; ++sy) cnt_s[sy][threadIdx.x] = 0;
+                for (int k = slice; k < total_rows; k += S) {
+                    const int sy = g[(long long)s_rows[k] * w + col];
+                    if (cnt_s[sy][threadIdx.x]++ == 0) first_s[sy][threadIdx.x] = k;
+                }
+            }
+            __syncthreads();
+            if (slice == 0) {
                 int best = -1, best_cnt = 0, best_first = 0;
-                for (int s = 0; s < 16; ++s) {
-                    const int cn = cnt_s[s][threadIdx.x];
+                for (int sy = 0; sy < 16; ++sy) {
+                    int cn = 0, fi = 0x7fffffff;
+                    for (int q = 0; q < S; ++q) {
+                        const int cq = cnt_s[sy][q * w + col];
+                        if (cq) {
+                            cn += cq;
+                            fi = min(fi, first_s[sy][q * w + col]);
+                        }
+                    }
                     if (cn == 0) continue;
-                    const int fi = first_s[s][threadIdx.x];
                     if (cn > best_cnt || (cn == best_cnt && fi < best_first)) {
-                        best = s;
+                        best = sy;
                         best_cnt = cn;
                         best_first = fi;
                     }
                 }
                 maj[col] = (uint8_t)best;
             }
+        } else {
+            for (int col0 = 0; col0 < w; col0 += blockDim.x) {
+                const int col = col0 + threadIdx.x;
+                if (col < w) {
+#pragma unroll
+                    for (int sy = 0; sy < 16; ++sy) cnt_s[sy][threadIdx.x] = 0;
+                    int order = 0;
+                    for (int j = 0; j < n; ++j) {
+                        if (assign[j] != c) continue;
+                        for (int m = mem_off[j]; m < mem_off[j + 1]; ++m) {
+                            const int sy = g[(long long)mem_rows[m] * w + col];
+                            if (cnt_s[sy][threadIdx.x]++ == 0) first_s[sy][threadIdx.x] = order;
+                            ++order;
+                        }
+                    }
+                    int best = -1, best_cnt = 0, best_first = 0;
+                    for (int sy = 0; sy < 16; ++sy) {
+                        const int cn = cnt_s[sy][threadIdx.x];
+                        if (cn == 0) continue;
+                        const int fi = first_s[sy][threadIdx.x];
+                        if (cn > best_cnt || (cn == best_cnt && fi < best_first)) {
+                            best = sy;
+                            best_cnt = cn;
+                            best_first = fi;
+                        }
+                    }
+                    maj[col] = (uint8_t)best;
+                }
+            }
         }
         __syncthreads();
         // Hamming distance of every member to the majority string
-        for (int j = 0; j < n; ++j) {
-            if (assign[j] != c) continue;
-            const int m0 = mem_off[j], m1 = mem_off[j + 1];
-            for (int m = m0 + threadIdx.x; m < m1; m += blockDim.x) {
-                const uint8_t *row = g + (long long)mem_rows[m] * w;
+        if (listed) {
+            for (int k = threadIdx.x; k < total_rows; k += blockDim.x) {
+                const uint8_t *row = g + (long long)s_rows[k] * w;
                 int d = 0;
                 for (int i = 0; i < w; ++i) d += row[i] != maj[i];
                 if (d > thr) {
                     s_bad = 1;
                     s_bad_c = 1;
+                }
+            }
+        } else {
+            for (int j = 0; j < n; ++j) {
+                if (assign[j] != c) continue;
+                const int m0 = mem_off[j], m1 = mem_off[j + 1];
+                for (int m = m0 + threadIdx.x; m < m1; m += blockDim.x) {
+                    const uint8_t *row = g + (long long)mem_rows[m] * w;
+                    int d = 0;
+                    for (int i = 0; i < w; ++i) d += row[i] != maj[i];
+                    if (d > thr) {
+                        s_bad = 1;
+                        s_bad_c = 1;
+                    }
                 }
             }
         }
