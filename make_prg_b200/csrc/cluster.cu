@@ -972,6 +972,20 @@ cudaError_t launch_scan_counts(cudaStream_t s, const int *counts, int n, int *of
     return cudaGetLastError();
 }
 
+// the number of distinct k-mers of every problem goes from the numbering kernel's output straight into the
+// loop state (levels of small problems do not wait for it on the host: their matrices are laid out for
+// the upper bound "every k-mer position is distinct")
+__global__ void set_features_kernel(ClusterState *__restrict__ states, const int *__restrict__ F, int n) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) states[q].F = F[q];
+}
+
+cudaError_t launch_set_features(cudaStream_t s, ClusterState *states, const int *F, int n) {
+    if (n <= 0) return cudaSuccess;
+    set_features_kernel<<<(n + 127) / 128, 128, 0, s>>>(states, F, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gather2(cudaStream_t s, const long long *src_off, const int *counts, const int *dst_off,
                            int n, const int *src_a, const int *src_b, int *dst_a, int *dst_b) {
     if (n <= 0) return cudaSuccess;

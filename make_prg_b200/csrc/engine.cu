@@ -512,11 +512,28 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
                                            B[6].as<int>(), d_F + q, d_err));
             ctx->launches += 6;
         }
-        std::vector<int> h_F(np + 1);
-        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_F.data(), d_F, sizeof(int) * np, s));
-        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &h_F[np], d_err, sizeof(int), s));
-        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
-        if (h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
+        // The number of distinct k-mers F of a problem sizes its count matrix and KMeans scratch.  A level
+        // of small problems (a pangenome level: n <= 8, <= 241 positions) does not wait for it: it lays its
+        // matrices out for the upper bound F <= P (every k-mer position distinct) and the device passes the
+        // real F from the numbering kernel to the loop state; levels with a big problem fetch F first.
+        bool bounded = !getenv("MPRG_EXACT_F");
+        {
+            long long bound_elems = 0;
+            for (int q = 0; q < np && bounded; ++q) {
+                if (kp[q].big || (long long)probs[q].n * probs[q].P >= KMEANS_BIG_ELEMENTS) bounded = false;
+                bound_elems += (long long)probs[q].n * probs[q].P;
+            }
+            if (bound_elems > (16LL << 20)) bounded = false;  // 128 MB of doubles for the level
+        }
+        std::vector<int> h_F(np + 1, 0);
+        if (bounded) {
+            for (int q = 0; q < np; ++q) h_F[q] = (int)probs[q].P;
+        } else {
+            MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_F.data(), d_F, sizeof(int) * np, s));
+            MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &h_F[np], d_err, sizeof(int), s));
+            MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+            if (h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
+        }
         TRACE("cl: kmer setup+run+sync");
 
         // ---- count matrices, sized exactly now that every F is known ----
@@ -569,6 +586,10 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         double *d_kmd = B[15].as<double>();
         int *d_kmi = reinterpret_cast<int *>(d_kmd + kmd_total);
         MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_states, st.data(), sizeof(ClusterState) * np, s));
+        if (bounded) {
+            MPRG_CUDA(ctx, launch_set_features(s, d_states, d_F, np));
+            ctx->launches++;
+        }
         MPRG_CUDA(ctx, cudaMemsetAsync(d_assign, 0, sizeof(int) * assign_total, s));
         const int MAX_CLUSTERS = 10;
         MPRG_CUDA(ctx, refcheck_all());
@@ -602,7 +623,9 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         h_assign.resize((size_t)assign_total);
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, st.data(), d_states, sizeof(ClusterState) * np, s));
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_assign.data(), d_assign, sizeof(int) * assign_total, s));
+        if (bounded) MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &h_F[np], d_err, sizeof(int), s));
         MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        if (bounded && h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
         TRACE("cl: kmeans loop+sync");
         for (int q = 0; q < np; ++q) {
             const Prob &p = probs[q];

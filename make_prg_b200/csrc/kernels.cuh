@@ -121,6 +121,7 @@ cudaError_t launch_kmer_big(cudaStream_t s, const void *d_probs, int q, const vo
                             int *block_counts, int *out_F, int *err);
 cudaError_t launch_kmer_fill_big(cudaStream_t s, const void *d_probs, int q, const void *h_prob, int F,
                                  const int *ints, double *X);
+cudaError_t launch_set_features(cudaStream_t s, ClusterState *states, const int *F, int n);
 cudaError_t launch_kmer_fill(cudaStream_t s, const void *d_probs, int n_probs, long long max_positions,
                              const int *ints, const int *F, double *X);
 cudaError_t launch_refcheck(cudaStream_t s, ClusterState *states, int n_probs, const uint8_t *G,
