@@ -232,3 +232,26 @@ def test_native_n_replacement_equals_python_random():
         hostio.replace_n_in_place(b)
         assert np.array_equal(a, b), k
         assert ord("N") not in a
+
+
+def test_pipeline_helpers(tmp_path, monkeypatch):
+    """Host logic of the from_msa pipeline that needs no device: locus names (input_output_files.py:234-235),
+    chunk cutting, thread split between the stages."""
+    from pathlib import Path
+
+    from make_prg_b200.subcommands import from_msa as fm
+
+    for name in ["a/b/x.fa", "x.fasta.gz", "y.fa.gz", "z.fasta", "w.txt", "q.fa.fa", "/p/GC0001.fa", "n.fa.gz.fa"]:
+        assert fm.locus_name_of(name) == fm.remove_known_input_extensions(Path(name).name), name
+    files = []
+    for i, size in enumerate([10, 300, 5, 5, 400, 1]):
+        p = tmp_path / f"l{i}.fa"
+        p.write_bytes(b"A" * size)
+        files.append(p)
+    chunks = fm.cut_chunks(files, max_bytes=310)
+    assert [[f.name for f in c] for c in chunks] == [["l0.fa", "l1.fa"], ["l2.fa", "l3.fa"], ["l4.fa"], ["l5.fa"]]
+    assert sum(len(c) for c in fm.cut_chunks(files + [tmp_path / "missing.fa"], max_bytes=10 ** 9)) == 7
+    assert fm.cut_chunks(files, max_bytes=10 ** 9, max_loci=4) == [files[:4], files[4:]]
+    monkeypatch.setenv("MPRG_CHUNK_MB", "0.0001")  # ~105 bytes
+    assert len(fm.cut_chunks(files)) == 5
+    assert fm.side_threads(1) >= fm.side_threads(4) >= 1 and fm.side_threads(4, writer=True) >= 1
