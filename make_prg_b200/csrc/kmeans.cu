@@ -1063,7 +1063,8 @@ cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, con
                           double *dscratch, int *iscratch, int *assign, int *newlab, int *tickets,
                           long long max_elements) {
     if (n_probs <= 0) return cudaSuccess;
-    int threads = max_elements <= 1024 ? 32 : (max_elements <= 8192 ? 64 : KM_THREADS);
+    // (max_elements is counted with the bound F <= positions when the level does not wait for F: 8 x 241)
+    int threads = max_elements <= 2048 ? 32 : (max_elements <= 16384 ? 64 : KM_THREADS);
     if (const char *e = getenv("MPRG_KM_THREADS")) threads = std::max(32, std::min(atoi(e) & ~31, KM_THREADS));
     kmeans_kernel<<<dim3(n_probs, KM_NINIT), threads, 0, s>>>(states, X, dscratch, iscratch, assign, newlab,
                                                               tickets);
