@@ -13,8 +13,9 @@ KMeans / PRG emission, `mprg_build`) over that batch.
   files     the same metric file to file (FASTA files in page cache -> .prg.fa/.bin.zip/.gfa.zip on tmpfs)
             through the native loader and writers (scripts/files_e2e.py), host wall clock
   cpu_baseline  the oracle port (oracle/make_prg_oracle.py) on a bounded sample, 1 core
-`--impl reference` times the reference's CPU algorithm (the oracle port; the Python reference cannot
-travel to the GPU box) with all host cores on a bounded sample per step.
+`--impl reference` times the UNMODIFIED reference (`make_prg from_msa -t <all host cores>`, staged into
+git-ignored oracle/_ref by oracle/stage_reference.py so that it travels to the GPU box) on a bounded sample
+of the same loci per step; the oracle port is the fallback when nothing is staged.
 N > 1: launched by torchrun, one rank per GPU, loci sharded (weak scaling: 1,000 loci per GPU, no
 data-path collective), time = max over ranks.
 """
@@ -39,6 +40,7 @@ MAX_NESTING, MIN_MATCH = 5, 7
 # ncu --set full capture committed under profiles/ (per launch, like `achieved`); None if not captured
 NCU_TRAFFIC_BYTES = 107.68e6  # profiles/r1_scan_kernel_ncu_v12.txt: 104.32 MB read + 3.36 MB written
 CACHE = Path(os.environ.get("MPRG_BENCH_CACHE", "/tmp/mprg_bench_cache"))
+CPU_BASELINE_SAMPLE = 100
 
 
 def workload(rank, n_loci=LOCI_PER_GPU):
@@ -151,15 +153,18 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def oracle_loci_per_sec(mats, n_workers):
-    """Times the oracle port (CPU restatement of the reference algorithm) on `mats`."""
+def oracle_loci_per_sec(mats, n_workers, keep=None):
+    """Times the oracle port (CPU restatement of the reference algorithm) on `mats`; keep: list that
+    receives the PRG strings (single-core run only)."""
     sys.path.insert(0, str(REPO / "oracle"))
     t0 = time.perf_counter()
     if n_workers <= 1:
         import make_prg_oracle as mo
 
         for M in mats:
-            mo.build_prg_from_matrix([f"s{i}" for i in range(M.shape[0])], M, MAX_NESTING, MIN_MATCH)
+            prg, _ = mo.build_prg_from_matrix([f"s{i}" for i in range(M.shape[0])], M, MAX_NESTING, MIN_MATCH)
+            if keep is not None:
+                keep.append(prg)
     else:
         import multiprocessing as mp
 
@@ -178,44 +183,115 @@ def _oracle_one(M):
     return 0
 
 
+def reference_sample_size(cores):
+    """Loci per step of the reference arm: the unmodified reference does about 0.5-1 locus/s/core on this
+    workload, so 2 loci per core keep a step at a few seconds and a 25-step run at a few minutes."""
+    return max(2 * cores, 16)
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    """--impl reference: the UNMODIFIED reference (`make_prg from_msa -t <all host cores>`, staged under
+    oracle/_ref by oracle/stage_reference.py, driven through its own CLI entry under the harness of
+    oracle/run_reference.py) on the first loci of the same workload, FASTA files in -> PRG files out.
+    Falls back to the oracle port (kind "port") only when no staged reference is present."""
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = "1"
     cores = os.cpu_count() or 1
-    sample = max(cores * 8, 32)
+    sample = reference_sample_size(cores)
     data = workload(0)[:sample]
-    mats = [data[i] for i in range(sample)]
-    for _ in range(args.warmup):
-        oracle_loci_per_sec(mats[:cores], cores)
-    t_total = 0.0
-    for _ in range(args.steps):
-        _, dt = oracle_loci_per_sec(mats, cores)
-        t_total += dt
+    sys.path.insert(0, str(REPO / "oracle"))
+    import run_reference as rr
+
+    kind = "reference" if rr.reference_available() else "port"
+    checked = None
+    if kind == "reference":
+        import shutil
+        import tempfile
+
+        tmp = Path(tempfile.mkdtemp(prefix="mprg_ref_"))
+        (tmp / "msas").mkdir()
+        for i in range(sample):
+            with open(tmp / "msas" / f"locus{i:05d}.fa", "w") as f:
+                for r in range(data[i].shape[0]):
+                    f.write(f">s{r}\n{data[i][r].tobytes().decode()}\n")
+
+        def one_step(n):
+            src = tmp / "msas"
+            if n < sample:
+                src = tmp / "warm"
+                if not src.exists():
+                    src.mkdir()
+                    for i in range(n):
+                        shutil.copy(tmp / "msas" / f"locus{i:05d}.fa", src)
+            t0 = time.perf_counter()
+            saved = os.dup(1)  # stdout carries exactly one JSON line
+            os.dup2(2, 1)
+            try:
+                rr.ref_cli(["from_msa", "-i", src, "-o", tmp / "out", "-N", MAX_NESTING, "-L", MIN_MATCH,
+                            "-t", cores, "-F"])
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
+            return time.perf_counter() - t0
+
+        try:
+            for _ in range(args.warmup):
+                one_step(min(cores, sample))
+            t_total = sum(one_step(sample) for _ in range(args.steps))
+            # the reference's PRGs of the sample against the oracle port's (what the GPU arm is checked against)
+            import make_prg_oracle as mo
+
+            lines = (tmp / "out.prg.fa").read_text().split("\n")
+            ref_prgs = {lines[i][1:]: lines[i + 1] for i in range(0, len(lines) - 1, 2)}
+            n_chk = min(8, sample)
+            checked = all(
+                ref_prgs.get(f"locus{i:05d}") ==
+                mo.build_prg_from_matrix([f"s{r}" for r in range(data[i].shape[0])], data[i], MAX_NESTING, MIN_MATCH)[0]
+                for i in range(n_chk))
+            if not checked:
+                raise SystemExit("reference arm: the reference's PRGs differ from the oracle port's")
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        how = (f"{sample} loci of the workload per step as FASTA files through `make_prg from_msa -N {MAX_NESTING} "
+               f"-L {MIN_MATCH} -t {cores} -F` of the unmodified reference (oracle/_ref, Biopython stand-in, "
+               f"KMeans n_init=10, OMP_NUM_THREADS=1), files in -> .prg.fa/.bin/.gfa/update_DS out")
+    else:
+        mats = [data[i] for i in range(sample)]
+        for _ in range(args.warmup):
+            oracle_loci_per_sec(mats[:cores], cores)
+        t_total = 0.0
+        for _ in range(args.steps):
+            _, dt = oracle_loci_per_sec(mats, cores)
+            t_total += dt
+        how = f"{sample} loci of the workload per step, oracle port, multiprocessing over loci"
     value = sample * args.steps / t_total
     line = {
         "impl": "reference", "metric": "MSA loci/sec (from_msa, byte-identical PRG)", "value": value,
         "unit": "loci/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": config_dict(sample_note=f"{sample} loci per step"),
-        "cpu_baseline": {"value": value, "unit": "loci/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} loci of the workload per step, multiprocessing over loci"},
+        "config": config_dict(),
+        "cpu_baseline": {"value": value, "unit": "loci/s", "cores": cores, "kind": kind, "sample": how,
+                         "prgs_equal_oracle_port": checked},
         "e2e": {"value": value, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def config_dict(sample_note=None):
-    c = {"workload": "BASELINE configs[1]: synthetic 1,000-locus set, 200 seqs x 1 kb MSAs, -N 5 -L 7, "
-                     "per GPU (make_prg_b200.synth seeds 1000+i)",
-         "loci_per_gpu": LOCI_PER_GPU, "rows": ROWS, "cols": COLS, "max_nesting": MAX_NESTING,
-         "min_match_length": MIN_MATCH,
-         "l2": "L2 flushed between steps by writing a 256 MiB device buffer (packed batch is 100 MB < L2)"}
-    if sample_note:
-        c["sample"] = sample_note
-    return c
+def config_dict():
+    """The same object in both arms (the arms differ in what they time, not in the workload)."""
+    cores = os.cpu_count() or 1
+    return {"workload": "BASELINE configs[1]: synthetic 1,000-locus set, 200 seqs x 1 kb MSAs, -N 5 -L 7, "
+                        "per GPU (make_prg_b200.synth seeds 1000+i)",
+            "loci_per_gpu": LOCI_PER_GPU, "rows": ROWS, "cols": COLS, "max_nesting": MAX_NESTING,
+            "min_match_length": MIN_MATCH,
+            "l2": "L2 flushed between steps by writing a 256 MiB device buffer (packed batch is 100 MB < L2)",
+            "cpu_sample": f"CPU arms time a bounded sample of the same loci: --impl reference the first "
+                          f"{reference_sample_size(cores)} loci per step on {cores} cores, cpu_baseline the "
+                          f"first {CPU_BASELINE_SAMPLE} loci on 1 core"}
 
 
 def main():
@@ -277,11 +353,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident(batch):
+    seen_lengths = {}  # PRG lengths of the last step of each path, compared with the checked run below
+
+    def step_resident(batch, keep=None):
         res = ctx.build(batch, MAX_NESTING, MIN_MATCH)
         status, lengths = res.statuses()
         n_ok = int((status == 0).sum())
         total_len = int(lengths.sum()) + sum(len(res.prg(i)) for i in range(0, n_loci, 97))
+        seen_lengths["resident"] = lengths
+        if keep is not None:
+            keep.extend(res.prg(i) for i in range(min(CPU_BASELINE_SAMPLE, n_loci)))
         res.free()
         return n_ok, total_len
 
@@ -291,6 +372,7 @@ def main():
         status, lengths = res.statuses()
         n_ok = int((status == 0).sum())
         total_len = int(lengths.sum()) + sum(len(res.prg(i)) for i in range(0, n_loci, 97))
+        seen_lengths["e2e"] = lengths
         res.free()
         batch.free()
         return n_ok, total_len
@@ -338,6 +420,13 @@ def main():
         torch.cuda.synchronize()
         yard.append(ctx.read_yardstick(batch))
     yard = yard[2:]
+    # parity of the timed batch: one more (untimed) build whose PRG strings are kept for the oracle check
+    # below; the timed steps must have produced PRGs of exactly these lengths
+    timed_lengths = seen_lengths["resident"].copy()
+    gpu_prgs = []
+    step_resident(batch, keep=gpu_prgs)
+    if not np.array_equal(timed_lengths, seen_lengths["resident"]):
+        raise SystemExit("bench: PRG lengths differ between two builds of the same batch")
     batch.free()
     # the same kernel on a launch 8x the size (the batch repeated), to separate launch-size effects from
     # kernel quality: 8,000 root tasks, 840 MB per launch
@@ -435,14 +524,23 @@ def main():
         except Exception as err:  # the headline numbers above do not depend on this pass
             files = {"error": repr(err)}
     # CPU baseline: oracle port, 1 core, bounded sample
-    sample = 100
-    cpu_v, cpu_dt = oracle_loci_per_sec([data[i] for i in range(sample)], 1)
+    sample = min(CPU_BASELINE_SAMPLE, n_loci)
+    oracle_prgs = []
+    cpu_v, cpu_dt = oracle_loci_per_sec([data[i] for i in range(sample)], 1, keep=oracle_prgs)
+    # the oracle is the checker here: the PRGs of the timed batch must be the reference algorithm's
+    bad = [i for i in range(sample) if gpu_prgs[i] != oracle_prgs[i]]
+    if bad or not np.array_equal(timed_lengths, seen_lengths["e2e"]):
+        raise SystemExit(f"bench: PRG parity failure (loci {bad[:10]}, e2e lengths equal: "
+                         f"{np.array_equal(timed_lengths, seen_lengths['e2e'])})")
     line = {
         "metric": "MSA loci/sec (from_msa, byte-identical PRG)", "value": value, "unit": "loci/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_dict(),
         "columns_per_sec": value * COLS, "loci_ok": n_ok_total,
+        "parity": {"prgs_equal_oracle": sample, "of": sample,
+                   "note": "PRG strings of the first loci of the timed batch == oracle port; PRG lengths of "
+                           "every locus equal across resident / e2e / checked builds"},
         "e2e": {"value": e2e_value, "unit": "loci/s",
                 "h2d_bytes_per_step": copies["h2d_bytes"] // args.steps,
                 "d2h_bytes_per_step": copies["d2h_bytes"] // args.steps,

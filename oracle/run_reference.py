@@ -19,8 +19,12 @@ from pathlib import Path
 
 os.environ.setdefault("OMP_NUM_THREADS", "1")
 
-REFERENCE_ROOT = Path(os.environ.get("MAKE_PRG_REFERENCE", "/root/reference"))
 SHIM_ROOT = Path(__file__).resolve().parent / "refshim"
+# /root/reference in the build container; on the GPU box the copy staged by oracle/stage_reference.py
+_STAGED = Path(__file__).resolve().parent / "_ref"
+REFERENCE_ROOT = Path(os.environ.get(
+    "MAKE_PRG_REFERENCE",
+    "/root/reference" if Path("/root/reference/make_prg").exists() else str(_STAGED)))
 DATA = REFERENCE_ROOT / "tests" / "integration_tests" / "data"
 
 _loaded = False
