@@ -232,6 +232,9 @@ int mprg_result_row_pool(const mprg_result *res, int32_t locus, int32_t *h_rows)
 #define MPRG_LOAD_IO_ERROR 3   /* cannot open / read / inflate: the caller re-raises through Python's open */
 #define MPRG_LOAD_NOT_ASCII 4  /* bytes >= 0x80: left to the caller's text decoder */
 #define MPRG_LOAD_FLAG_HAS_N 1
+/* two records share an id (first token of the title): the reference selects cluster sub-alignments by id
+ * (recursion_tree.py:558-572), so its sub-alignments overlap on such a file; this engine cuts by row */
+#define MPRG_LOAD_FLAG_DUPLICATE_IDS 2
 typedef struct mprg_msa_set mprg_msa_set;
 /* N replacement alone on one upper-cased row-major matrix, in place */
 int mprg_replace_n(uint8_t *h_ascii, int32_t n_rows, int32_t n_cols);
@@ -263,6 +266,9 @@ int mprg_prg_to_gfa(const char *prg, int64_t length, char *out, int64_t capacity
 #define MPRG_WRITE_PRG 1
 #define MPRG_WRITE_BIN 2
 #define MPRG_WRITE_GFA 4
+/* this writer produces one PART of a run (one GPU shard): archives even for a single locus; the parts are
+ * turned into the final files by mprg_merge_outputs */
+#define MPRG_WRITE_PART 8
 typedef struct mprg_writer mprg_writer;
 int mprg_writer_open(const char *output_prefix, int32_t what, mprg_writer **out);
 int mprg_writer_add(mprg_writer *w, const mprg_result *res, const int32_t *h_loci, const char *const *names,
@@ -271,6 +277,12 @@ int mprg_writer_add(mprg_writer *w, const mprg_result *res, const int32_t *h_loc
 int mprg_writer_close(mprg_writer *w, int64_t *n_loci, int64_t *bytes_written);
 void mprg_writer_abort(mprg_writer *w);
 const char *mprg_writer_error(const mprg_writer *w);
+/* Final files of a run built as several parts (replaces the concatenation of per-process files in
+ * make_prg/utils/input_output_files.py:70-135): .prg.fa records merged in sorted order, archive members
+ * appended part by part, plain .prg.bin / .prg.gfa when the whole run holds one locus.  Missing parts hold no
+ * locus; the parts are removed.  Files appear under their final names only when complete. */
+int mprg_merge_outputs(const char *const *part_prefixes, int32_t n_parts, const char *output_prefix, int32_t what,
+                       int64_t *n_loci, char *err_buf, int64_t err_capacity);
 
 #ifdef __cplusplus
 }

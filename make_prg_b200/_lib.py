@@ -24,6 +24,10 @@ class MprgError(RuntimeError):
     def __init__(self, code, message):
         super().__init__(f"libmprg error {code} ({ERRORS.get(code, '?')}): {message}")
         self.code = code
+        self.message = message
+
+    def __reduce__(self):  # crosses process boundaries (shards of a multi-GPU run)
+        return (MprgError, (self.code, self.message))
 
 
 class Task(C.Structure):
@@ -97,6 +101,7 @@ SIGNATURES = {
     "mprg_writer_close": (C.c_int, [P, C.POINTER(I64), C.POINTER(I64)]),
     "mprg_writer_abort": (None, [P]),
     "mprg_writer_error": (C.c_char_p, [P]),
+    "mprg_merge_outputs": (C.c_int, [P, I32, C.c_char_p, I32, C.POINTER(I64), C.c_char_p, I64]),
 }
 
 

@@ -289,11 +289,45 @@ inline void next_line(const uint8_t *s, const uint8_t *end, const uint8_t *&line
 // The sequence lines of one record: copies [s, ...) to w up to (not including) the next title line
 // (a '>' first in its line) or `end`, dropping line ends and blanks and upper-casing a-z.
 // bits |= 1 when a byte >= 0x80 was copied, |= 2 when an 'N' was.  Returns the read position.
-const uint8_t *copy_record_scalar(const uint8_t *s, const uint8_t *end, uint8_t *&w, int &bits) {
+// Strict UTF-8 as Python's decoder accepts it (no overlong forms, no surrogates, nothing above U+10FFFF).
+bool valid_utf8(const uint8_t *p, size_t n) {
+    size_t i = 0;
+    while (i < n) {
+        const uint8_t c = p[i];
+        if (c < 0x80) {
+            ++i;
+            continue;
+        }
+        int len;
+        uint32_t cp, lo;
+        if ((c & 0xE0) == 0xC0) { len = 2; cp = c & 0x1F; lo = 0x80; }
+        else if ((c & 0xF0) == 0xE0) { len = 3; cp = c & 0x0F; lo = 0x800; }
+        else if ((c & 0xF8) == 0xF0) { len = 4; cp = c & 0x07; lo = 0x10000; }
+        else return false;
+        if (i + (size_t)len > n) return false;
+        for (int k = 1; k < len; ++k) {
+            if ((p[i + k] & 0xC0) != 0x80) return false;
+            cp = (cp << 6) | (p[i + k] & 0x3F);
+        }
+        if (cp < lo || cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) return false;
+        i += (size_t)len;
+    }
+    return true;
+}
+
+// What str.rstrip() removes at the end of a line besides blanks and line ends (Biopython's
+// SimpleFastaParser rstrips every line before joining them): \t \v \f and the separators 0x1c-0x1f.
+inline bool is_trailing_ws(uint8_t c) { return c == '\t' || c == 0x0b || c == 0x0c || (c >= 0x1c && c <= 0x1f); }
+inline void rstrip_line(uint8_t *row_start, uint8_t *&w) {
+    while (w > row_start && is_trailing_ws(w[-1])) --w;
+}
+
+const uint8_t *copy_record_scalar(const uint8_t *s, const uint8_t *end, uint8_t *&w, int &bits, uint8_t *row_start) {
     unsigned hi = 0, n_count = 0;
     while (s < end) {
         uint8_t c = *s++;
         if (c == '\n' || c == '\r') {
+            rstrip_line(row_start, w);
             if (c == '\r' && s < end && *s == '\n') ++s;
             if (s < end && *s == '>') break;
             continue;
@@ -304,6 +338,7 @@ const uint8_t *copy_record_scalar(const uint8_t *s, const uint8_t *end, uint8_t 
         n_count += (c == 'N');
         *w++ = c;
     }
+    rstrip_line(row_start, w);  // a last line without a line end
     bits |= ((hi & 0x80u) ? 1 : 0) | (n_count ? 2 : 0);
     return s;
 }
@@ -315,7 +350,7 @@ alignas(32) const uint8_t LANE_MASK[64] = {
 // The same, 32 bytes per step (the output buffer has 32 bytes of slack: whole vectors are stored and
 // the write position advances by the bytes that count).
 __attribute__((target("avx2"))) const uint8_t *copy_record_avx2(const uint8_t *s, const uint8_t *end, uint8_t *&w,
-                                                                  int &bits) {
+                                                                  int &bits, uint8_t *row_start) {
     const __m256i v_nl = _mm256_set1_epi8('\n'), v_cr = _mm256_set1_epi8('\r'), v_sp = _mm256_set1_epi8(' ');
     const __m256i v_lo = _mm256_set1_epi8('a' - 1), v_hi = _mm256_set1_epi8('z' + 1);
     const __m256i v_case = _mm256_set1_epi8(0x20), v_n = _mm256_set1_epi8('N');
@@ -343,6 +378,7 @@ __attribute__((target("avx2"))) const uint8_t *copy_record_avx2(const uint8_t *s
         const uint8_t c = s[k];
         s += k + 1;
         if (c == ' ') continue;
+        rstrip_line(row_start, w);
         if (c == '\r' && s < end && *s == '\n') ++s;
         if (s < end && *s == '>') {
             bits |= (_mm256_movemask_epi8(acc_hi) ? 1 : 0) | (_mm256_movemask_epi8(acc_n) ? 2 : 0);
@@ -350,7 +386,7 @@ __attribute__((target("avx2"))) const uint8_t *copy_record_avx2(const uint8_t *s
         }
     }
     bits |= (_mm256_movemask_epi8(acc_hi) ? 1 : 0) | (_mm256_movemask_epi8(acc_n) ? 2 : 0);
-    return copy_record_scalar(s, end, w, bits);
+    return copy_record_scalar(s, end, w, bits, row_start);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -614,10 +650,16 @@ void parse_file(const char *path, ParsedFile &pf, bool avx2, Slab &slab) {
         const uint8_t *le, *nx;
         next_line(s, end, le, nx);
         if (pf.n_rows > 0) pf.titles.push_back('\n');
-        pf.titles.append((const char *)s + 1, (size_t)(le - s - 1));
+        {
+            // title = line[1:].rstrip() (the ASCII whitespace here; Unicode blanks when the text is decoded)
+            const uint8_t *te = le;
+            while (te > s + 1 && (te[-1] == ' ' || is_trailing_ws(te[-1]))) --te;
+            pf.titles.append((const char *)s + 1, (size_t)(te - s - 1));
+        }
         s = nx;
         uint8_t *row_start = w;
-        if (s < end && *s != '>') s = avx2 ? copy_record_avx2(s, end, w, bits) : copy_record_scalar(s, end, w, bits);
+        if (s < end && *s != '>')
+            s = avx2 ? copy_record_avx2(s, end, w, bits, row_start) : copy_record_scalar(s, end, w, bits, row_start);
         const int64_t len = w - row_start;
         if (first_len < 0)
             first_len = len;
@@ -630,8 +672,9 @@ void parse_file(const char *path, ParsedFile &pf, bool avx2, Slab &slab) {
         pf.status = MPRG_LOAD_NO_RECORDS;
         return;
     }
-    for (char c : pf.titles)
-        if ((unsigned char)c >= 0x80) bits |= 1;
+    // titles may hold any valid UTF-8 (Biopython reads text); a title that does not decode makes the
+    // reference's read fail, so that file goes back to the Python loader for the exception
+    if (!valid_utf8((const uint8_t *)pf.titles.data(), pf.titles.size())) bits |= 1;
     if (bits & 1) {
         pf.status = MPRG_LOAD_NOT_ASCII;
         return;
@@ -639,6 +682,23 @@ void parse_file(const char *path, ParsedFile &pf, bool avx2, Slab &slab) {
     if (ragged) {
         pf.status = MPRG_LOAD_RAGGED;
         return;
+    }
+    {
+        // duplicate record ids (first whitespace-separated token of each title)
+        std::unordered_map<std::string, int> seen;
+        seen.reserve((size_t)pf.n_rows * 2);
+        size_t at = 0;
+        const std::string &t = pf.titles;
+        for (int r = 0; r < pf.n_rows; ++r) {
+            size_t e = t.find('\n', at);
+            if (e == std::string::npos) e = t.size();
+            size_t a = at;
+            while (a < e && (t[a] == ' ' || (t[a] >= '\t' && t[a] <= '\r') || (t[a] >= 0x1c && t[a] <= 0x1f))) ++a;
+            size_t b = a;
+            while (b < e && !(t[b] == ' ' || (t[b] >= '\t' && t[b] <= '\r') || (t[b] >= 0x1c && t[b] <= 0x1f))) ++b;
+            if (++seen[t.substr(a, b - a)] == 2) pf.flags |= MPRG_LOAD_FLAG_DUPLICATE_IDS;
+            at = e + 1;
+        }
     }
     pf.n_cols = (int32_t)first_len;
     pf.matrix_bytes = (int64_t)pf.n_rows * first_len;
@@ -1013,11 +1073,22 @@ struct ZipEntry {
     uint64_t offset;
 };
 
+// Output files are written under a temporary name next to their final one and renamed when complete, so
+// that an aborted run leaves no truncated archive behind (and nothing a rerun without -F would trip over).
+std::string temp_name_of(const std::string &path) { return path + ".tmp" + std::to_string((long long)getpid()); }
+
 struct ZipFile {
     FILE *f = nullptr;
     uint64_t pos = 0;
     std::vector<ZipEntry> entries;
     uint16_t dos_time = 0, dos_date = 0;
+    std::string final_path, tmp_path;
+    void discard() {
+        if (f) fclose(f);
+        f = nullptr;
+        if (!tmp_path.empty()) unlink(tmp_path.c_str());
+        tmp_path.clear();
+    }
 
     static void le16(std::string &s, uint16_t v) {
         s.push_back((char)(v & 0xff));
@@ -1030,8 +1101,13 @@ struct ZipFile {
         for (int k = 0; k < 8; ++k) s.push_back((char)((v >> (8 * k)) & 0xff));
     }
     bool open_path(const std::string &path) {
-        f = fopen(path.c_str(), "wb");
-        if (!f) return false;
+        final_path = path;
+        tmp_path = temp_name_of(path);
+        f = fopen(tmp_path.c_str(), "wb");
+        if (!f) {
+            tmp_path.clear();
+            return false;
+        }
         setvbuf(f, nullptr, _IOFBF, 1 << 20);
         time_t now = time(nullptr);
         struct tm tmv;
@@ -1124,16 +1200,124 @@ struct ZipFile {
         bool ok = put(cd);
         ok = (fclose(f) == 0) && ok;
         f = nullptr;
+        if (ok) ok = rename(tmp_path.c_str(), final_path.c_str()) == 0;
+        if (!ok) unlink(tmp_path.c_str());
+        tmp_path.clear();
         return ok;
     }
+    // appends the members of a finished stored archive written by this class (a shard's part): its data
+    // region is copied as one block, the directory entries move by the current position
+    bool append_archive(const std::string &part_path, std::string &err);
 };
 
 bool write_whole(const std::string &path, const void *data, size_t n) {
-    FILE *f = fopen(path.c_str(), "wb");
+    const std::string tmp = temp_name_of(path);
+    FILE *f = fopen(tmp.c_str(), "wb");
     if (!f) return false;
     bool ok = n == 0 || fwrite(data, 1, n, f) == n;
     ok = (fclose(f) == 0) && ok;
+    if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;
+    if (!ok) unlink(tmp.c_str());
     return ok;
+}
+
+bool read_whole(const std::string &path, std::string &out) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    out.clear();
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) out.append(buf, n);
+    const bool ok = !ferror(f);
+    fclose(f);
+    return ok;
+}
+
+inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint64_t rd64(const uint8_t *p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+// Central directory of a stored archive held in memory: entries with their local-header offsets and the
+// offset where the directory starts (= size of the data region).  False when the bytes are not such a file.
+bool parse_stored_zip(const std::string &z, std::vector<ZipEntry> &entries, uint64_t &cd_offset) {
+    entries.clear();
+    if (z.size() < 22) return false;
+    const uint8_t *b = (const uint8_t *)z.data();
+    const size_t eocd = z.size() - 22;  // archives written here carry no comment
+    if (rd32(b + eocd) != 0x06054b50u) return false;
+    uint64_t n = rd16(b + eocd + 10), cd_size = rd32(b + eocd + 12);
+    cd_offset = rd32(b + eocd + 16);
+    if (n == 0xFFFF || cd_size == 0xFFFFFFFFull || cd_offset == 0xFFFFFFFFull) {
+        if (eocd < 20 + 56 || rd32(b + eocd - 20) != 0x07064b50u) return false;
+        const uint64_t z64 = rd64(b + eocd - 20 + 8);
+        if (z64 + 56 > z.size() || rd32(b + z64) != 0x06064b50u) return false;
+        n = rd64(b + z64 + 32);
+        cd_size = rd64(b + z64 + 40);
+        cd_offset = rd64(b + z64 + 48);
+    }
+    if (cd_offset + cd_size > z.size()) return false;
+    size_t p = (size_t)cd_offset;
+    entries.reserve((size_t)n);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (p + 46 > z.size() || rd32(b + p) != 0x02014b50u) return false;
+        if (rd16(b + p + 10) != 0) return false;  // stored members only
+        ZipEntry e;
+        e.crc = rd32(b + p + 16);
+        e.size = rd32(b + p + 24);
+        const size_t nlen = rd16(b + p + 28), xlen = rd16(b + p + 30), clen = rd16(b + p + 32);
+        e.offset = rd32(b + p + 42);
+        if (p + 46 + nlen + xlen + clen > z.size()) return false;
+        e.name.assign(z.data() + p + 46, nlen);
+        if (e.offset == 0xFFFFFFFFull) {
+            size_t x = p + 46 + nlen;
+            const size_t xe = x + xlen;
+            bool found = false;
+            while (x + 4 <= xe) {
+                const uint16_t id = rd16(b + x), sz = rd16(b + x + 2);
+                if (id == 1 && sz >= 8) {
+                    e.offset = rd64(b + x + 4);
+                    found = true;
+                    break;
+                }
+                x += 4 + sz;
+            }
+            if (!found) return false;
+        }
+        entries.push_back(std::move(e));
+        p += 46 + nlen + xlen + clen;
+    }
+    return true;
+}
+
+bool ZipFile::append_archive(const std::string &part_path, std::string &err) {
+    std::string z;
+    std::vector<ZipEntry> part;
+    uint64_t cd_offset = 0;
+    if (!read_whole(part_path, z) || !parse_stored_zip(z, part, cd_offset)) {
+        err = "cannot read the archive part " + part_path;
+        return false;
+    }
+    if (cd_offset && fwrite(z.data(), 1, (size_t)cd_offset, f) != cd_offset) {
+        err = "cannot write " + final_path + ": " + strerror(errno);
+        return false;
+    }
+    for (ZipEntry &e : part) {
+        e.offset += pos;
+        entries.push_back(std::move(e));
+    }
+    pos += cd_offset;
+    return true;
+}
+
+// data of one member of a stored archive held in memory
+bool member_data(const std::string &z, const ZipEntry &e, const char *&data, size_t &n) {
+    const uint8_t *b = (const uint8_t *)z.data();
+    if (e.offset + 30 > z.size() || rd32(b + e.offset) != 0x04034b50u) return false;
+    const size_t start = (size_t)e.offset + 30 + rd16(b + e.offset + 26) + rd16(b + e.offset + 28);
+    if (start + e.size > z.size()) return false;
+    data = z.data() + start;
+    n = e.size;
+    return true;
 }
 
 struct Encoded {
@@ -1177,7 +1361,7 @@ extern "C" int mprg_prg_to_gfa(const char *prg, int64_t length, char *out, int64
 }
 
 extern "C" int mprg_writer_open(const char *output_prefix, int32_t what, mprg_writer **out) {
-    if (!output_prefix || !out || (what & ~7) || what == 0) return MPRG_E_BAD_ARG;
+    if (!output_prefix || !out || (what & ~15) || (what & 7) == 0) return MPRG_E_BAD_ARG;
     mprg_writer *w = new mprg_writer();
     w->prefix = output_prefix;
     w->what = what;
@@ -1233,7 +1417,7 @@ extern "C" int mprg_writer_add(mprg_writer *w, const mprg_result *res, const int
     if (n == 0) return MPRG_OK;
     // the only locus of a run is kept back: one locus => plain files, no archives
     int begin = 0;
-    if (w->n_added == 0 && n == 1) {
+    if (w->n_added == 0 && n == 1 && !(w->what & MPRG_WRITE_PART)) {
         if (what & MPRG_WRITE_PRG) {
             int64_t len = 0;
             const char *prg = mprg_result_prg(res, h_loci[0], &len);
@@ -1334,7 +1518,7 @@ extern "C" int mprg_writer_close(mprg_writer *w, int64_t *n_loci, int64_t *bytes
             }
             bytes += (int64_t)text.size();
         }
-        if (w->n_added == 1) {
+        if (w->n_added == 1 && !w->zips_open) {
             const Encoded &e = w->first;
             if ((w->what & MPRG_WRITE_BIN) &&
                 !write_whole(w->prefix + ".prg.bin", e.bin.data(), e.bin.size() * sizeof(uint32_t))) {
@@ -1366,7 +1550,107 @@ extern "C" int mprg_writer_close(mprg_writer *w, int64_t *n_loci, int64_t *bytes
 
 extern "C" void mprg_writer_abort(mprg_writer *w) {
     if (!w) return;
-    if (w->zbin.f) fclose(w->zbin.f);
-    if (w->zgfa.f) fclose(w->zgfa.f);
+    w->zbin.discard();  // closes and removes the unfinished archives
+    w->zgfa.discard();
     delete w;
+}
+
+// Final files of a run that was built as several parts (one per GPU shard, each written by its own
+// writer opened with MPRG_WRITE_PART): .prg.fa records merged in sorted order (input_output_files.py:86-92),
+// archive members concatenated part by part; a run of a single locus gets plain .prg.bin / .prg.gfa files
+// (input_output_files.py:113-135).  Parts that do not exist hold no locus.  The parts are removed afterwards.
+extern "C" int mprg_merge_outputs(const char *const *part_prefixes, int32_t n_parts, const char *output_prefix,
+                                  int32_t what, int64_t *n_loci, char *err_buf, int64_t err_capacity) {
+    if (!part_prefixes || n_parts < 0 || !output_prefix || (what & ~7) || what == 0) return MPRG_E_BAD_ARG;
+    std::string err;
+    auto fail = [&](const std::string &m) {
+        if (err_buf && err_capacity > 0) {
+            const size_t k = std::min<size_t>(m.size(), (size_t)err_capacity - 1);
+            memcpy(err_buf, m.data(), k);
+            err_buf[k] = 0;
+        }
+        return MPRG_E_INTERNAL;
+    };
+    auto exists = [](const std::string &p) { return access(p.c_str(), R_OK) == 0; };
+    const std::string out = output_prefix;
+    int64_t total = -1;
+    // ---- archives ----
+    struct Kind { int bit; const char *zip_ext, *plain_ext; };
+    const Kind kinds[2] = {{MPRG_WRITE_BIN, ".prg.bin.zip", ".prg.bin"}, {MPRG_WRITE_GFA, ".prg.gfa.zip", ".prg.gfa"}};
+    for (const Kind &k : kinds) {
+        if (!(what & k.bit)) continue;
+        std::vector<std::string> parts;
+        for (int i = 0; i < n_parts; ++i) {
+            const std::string p = std::string(part_prefixes[i]) + k.zip_ext;
+            if (exists(p)) parts.push_back(p);
+        }
+        // one member in all => plain file
+        int64_t members = 0;
+        std::string only_z;
+        std::vector<ZipEntry> only_e;
+        for (const std::string &p : parts) {
+            std::string z;
+            std::vector<ZipEntry> e;
+            uint64_t cd = 0;
+            if (!read_whole(p, z) || !parse_stored_zip(z, e, cd)) return fail("cannot read the archive part " + p);
+            members += (int64_t)e.size();
+            if (members == (int64_t)e.size() && e.size() == 1) {
+                only_z.swap(z);
+                only_e = e;
+            }
+            if (members > 1) break;
+        }
+        if (members == 1) {
+            const char *d = nullptr;
+            size_t n = 0;
+            if (!member_data(only_z, only_e[0], d, n) || !write_whole(out + k.plain_ext, d, n))
+                return fail("cannot write " + out + k.plain_ext);
+            total = 1;
+        } else if (members > 1) {
+            ZipFile zf;
+            if (!zf.open_path(out + k.zip_ext)) return fail("cannot create " + out + k.zip_ext + ": " + strerror(errno));
+            for (const std::string &p : parts)
+                if (!zf.append_archive(p, err)) {
+                    zf.discard();
+                    return fail(err);
+                }
+            total = (int64_t)zf.entries.size();
+            if (!zf.finish()) return fail("cannot finish " + out + k.zip_ext);
+        }
+        for (const std::string &p : parts) unlink(p.c_str());
+    }
+    // ---- .prg.fa: every part is sorted by "<name>.prg.fa"; merge ----
+    if (what & MPRG_WRITE_PRG) {
+        struct Rec { std::string key; const char *p; size_t n; };
+        std::vector<std::string> texts((size_t)n_parts);
+        std::vector<Rec> recs;
+        for (int i = 0; i < n_parts; ++i) {
+            const std::string p = std::string(part_prefixes[i]) + ".prg.fa";
+            if (!exists(p)) continue;
+            if (!read_whole(p, texts[(size_t)i])) return fail("cannot read " + p);
+            const std::string &t = texts[(size_t)i];
+            size_t at = 0;
+            while (at < t.size()) {  // ">name\nprg\n"
+                const size_t e1 = t.find('\n', at);
+                if (t[at] != '>' || e1 == std::string::npos) return fail("malformed part " + p);
+                size_t e2 = t.find('\n', e1 + 1);
+                if (e2 == std::string::npos) e2 = t.size() - 1;
+                recs.push_back(Rec{t.substr(at + 1, e1 - at - 1) + ".prg.fa", t.data() + at, e2 + 1 - at});
+                at = e2 + 1;
+            }
+        }
+        std::stable_sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.key < b.key; });
+        if (!recs.empty()) {
+            std::string text;
+            size_t bytes = 0;
+            for (const Rec &r : recs) bytes += r.n;
+            text.reserve(bytes);
+            for (const Rec &r : recs) text.append(r.p, r.n);
+            if (!write_whole(out + ".prg.fa", text.data(), text.size())) return fail("cannot write " + out + ".prg.fa");
+        }
+        total = (int64_t)recs.size();
+        for (int i = 0; i < n_parts; ++i) unlink((std::string(part_prefixes[i]) + ".prg.fa").c_str());
+    }
+    if (n_loci) *n_loci = std::max<int64_t>(total, 0);
+    return MPRG_OK;
 }

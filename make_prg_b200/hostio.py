@@ -17,8 +17,8 @@ from .msa import MSA
 from .utils import io_utils
 
 LOAD_OK, LOAD_NO_RECORDS, LOAD_RAGGED, LOAD_IO_ERROR, LOAD_NOT_ASCII = 0, 1, 2, 3, 4
-FLAG_HAS_N = 1
-WRITE_PRG, WRITE_BIN, WRITE_GFA = 1, 2, 4
+FLAG_HAS_N, FLAG_DUPLICATE_IDS = 1, 2
+WRITE_PRG, WRITE_BIN, WRITE_GFA, WRITE_PART = 1, 2, 4, 8
 
 
 def default_threads():
@@ -70,7 +70,7 @@ class MsaSet:
         p = self.lib.mprg_fasta_titles(self.handle, locus, C.byref(n))
         text = C.string_at(p, n.value).decode() if p and n.value else ""
         rows = int(self.n_rows[locus]) if self.status[locus] == LOAD_OK else None
-        out = text.split("\n")
+        out = [t.rstrip() for t in text.split("\n")]  # Unicode blanks too, as str.rstrip() in Biopython
         return out if rows is None or len(out) == rows else out + [""] * (rows - len(out))
 
     def ids(self, locus):
@@ -134,6 +134,10 @@ def load_fasta_files(paths, threads=None, pin=True):
     return MsaSet(h, paths)
 
 
+class NonAsciiSequenceError(ValueError):
+    """The file parses as text but its rows hold non-ASCII characters: a curation error of that locus."""
+
+
 def raise_for_load_status(msas, locus):
     """The exception load_alignment_file raises for this file (io_utils.py:17-29 through Biopython)."""
     status = int(msas.status[locus])
@@ -143,8 +147,13 @@ def raise_for_load_status(msas, locus):
         raise ValueError("No records found in handle")
     if status == LOAD_RAGGED:
         raise ValueError("Sequences must all be the same length")
-    # unreadable or not plain ASCII: the Python loader raises (or decodes) exactly as before
+    # unreadable, or bytes >= 0x80 among the sequences / a title that is not UTF-8: the Python loader raises
+    # what the reference's read raises (OSError, UnicodeDecodeError, ...).  If it loads, the rows hold
+    # characters outside the DNA alphabet: the reference skips such a locus (SequenceCurationError,
+    # from_msa.py:147-151), which is what LOAD_NOT_ASCII then means to the caller.
     io_utils.load_alignment_file(msas.paths[locus], "fasta")
+    if status == LOAD_NOT_ASCII:
+        raise NonAsciiSequenceError(f"{msas.paths[locus]}: a sequence has a disallowed (non-ASCII) character")
     raise ValueError(f"{msas.paths[locus]} could not be loaded")
 
 
@@ -215,12 +224,30 @@ class PrgStrings:
             pass
 
 
+def merge_outputs(part_prefixes, output_prefix, prg=True, binary=True, gfa=True):
+    """Final .prg.fa / .prg.bin(.zip) / .prg.gfa(.zip) from the parts of a sharded run (mprg_merge_outputs);
+    returns the number of loci.  The parts are removed."""
+    lib = _lib.load()
+    what = (WRITE_PRG if prg else 0) | (WRITE_BIN if binary else 0) | (WRITE_GFA if gfa else 0)
+    arr, _keep = _c_strings([os.fspath(p) for p in part_prefixes])
+    n = C.c_int64()
+    err = C.create_string_buffer(1024)
+    rc = lib.mprg_merge_outputs(C.cast(arr, C.c_void_p), len(part_prefixes), os.fspath(output_prefix).encode(), what,
+                                C.byref(n), err, len(err))
+    if rc != 0:
+        raise OSError(err.value.decode() or "mprg_merge_outputs failed")
+    return n.value
+
+
 class OutputWriter:
     """<prefix>.prg.fa / .prg.bin(.zip) / .prg.gfa(.zip) written by host threads of the library."""
 
-    def __init__(self, output_prefix, prg=True, binary=True, gfa=True, threads=None):
+    def __init__(self, output_prefix, prg=True, binary=True, gfa=True, threads=None, part=False):
+        """part: this writer produces one part of a sharded run (archives even for one locus); the parts
+        become the final files through merge_outputs."""
         self.lib = _lib.load()
         what = (WRITE_PRG if prg else 0) | (WRITE_BIN if binary else 0) | (WRITE_GFA if gfa else 0)
+        what |= WRITE_PART if part else 0
         self.threads = threads or default_threads()
         h = C.c_void_p()
         rc = self.lib.mprg_writer_open(os.fspath(output_prefix).encode(), what, C.byref(h))

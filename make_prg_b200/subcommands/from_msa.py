@@ -162,9 +162,16 @@ def iter_built_chunks(input_files, options, device_ordinal=0, chunks=None):
                       if k + 1 < len(chunks) else None)
             names = [locus_name_of(path) for path in paths]
             logger.info(f"Generating PRGs for {names[0]} ... {names[-1]} ({len(names)} loci)...")
+            for i in np.nonzero(msas.flags & hostio.FLAG_DUPLICATE_IDS)[0]:
+                logger.warning(f"{names[int(i)]}: duplicated record ids; clusters are cut by row here, the reference "
+                               "pulls every record with a clustered id (recursion_tree.py:558-572), so its PRG may "
+                               "differ for this locus")
+            curation = set()  # loci whose rows hold non-ASCII characters: skipped like any disallowed base
             for i in np.nonzero(msas.status != hostio.LOAD_OK)[0]:
                 try:
                     hostio.raise_for_load_status(msas, int(i))
+                except hostio.NonAsciiSequenceError:
+                    curation.add(int(i))
                 except ValueError as err:
                     if "No records found in handle" in str(err.args[0]):
                         raise EmptyMSAError(f"No records found in MSA of locus {names[int(i)]}")
@@ -174,7 +181,7 @@ def iter_built_chunks(input_files, options, device_ordinal=0, chunks=None):
             statuses, _lengths = res.statuses()
             ok = np.nonzero(statuses == LOCUS_OK)[0].tolist()
             for i in np.nonzero(statuses != LOCUS_OK)[0].tolist():
-                if statuses[i] == LOCUS_CURATION_ERROR:
+                if statuses[i] == LOCUS_CURATION_ERROR or i in curation:
                     logger.warning(f"Skipping building PRG for {names[i]}. Error: a slice of a sequence has a "
                                    "disallowed base. Redo sequence curation.")
                 else:
@@ -191,14 +198,19 @@ def _update_ds_pickles(names, msas, res, ok, options):
         build = engine.LocusBuild(LOCUS_OK, res.prg(i), res.n_nodes(i), res.n_sites(i), res.nodes(i))
         builder = PrgBuilder.from_engine(names[i], msas.alignment(i), build, options.max_nesting,
                                          options.min_match_length)
-        assert builder.build_prg() == build.prg, f"PRG emission mismatch for {names[i]}"
+        # build_prg() also fills prg_index and the leaves' indexed_PRG_intervals: a statement, not an assert
+        prg = builder.build_prg()
+        if prg != build.prg:
+            raise RuntimeError(f"PRG emission mismatch for {names[i]}")
         out.append((names[i], pickle.dumps(builder, protocol=4)))
     return out
 
 
-def build_and_write(input_files, options, device_ordinal=0, output_prefix=None):
+def build_and_write(input_files, options, device_ordinal=0, output_prefix=None, part=False):
     """One GPU: the whole run, files in -> final files out.  Returns the number of PRGs written.
-    The update_DS archive (Python PrgBuilder pickles) is written unless options.skip_update_ds."""
+    The update_DS archive (Python PrgBuilder pickles) is written unless options.skip_update_ds.
+    part: the files are one part of a sharded run (hostio.merge_outputs makes the final files).
+    Every file appears under its final name only when it is complete; an aborted run leaves none."""
     from concurrent.futures import ThreadPoolExecutor
 
     prefix = output_prefix or options.output_prefix
@@ -206,8 +218,9 @@ def build_and_write(input_files, options, device_ordinal=0, output_prefix=None):
     want_ds = ot.prg and not getattr(options, "skip_update_ds", False)
     chunks = cut_chunks(input_files)
     writer = hostio.OutputWriter(prefix, prg=ot.prg, binary=ot.binary, gfa=ot.gfa,
-                                 threads=side_threads(len(chunks), writer=True))
+                                 threads=side_threads(len(chunks), writer=True), part=part)
     ds_zip = None
+    ds_tmp = f"{prefix}.update_DS.zip.tmp{os.getpid()}"
     n_ok = 0
     pending = None  # (future, msas, res): the chunk being encoded / written on the writer thread
 
@@ -227,7 +240,7 @@ def build_and_write(input_files, options, device_ordinal=0, output_prefix=None):
                     pending = None
                 if want_ds and ok:
                     if ds_zip is None:
-                        ds_zip = zipfile.ZipFile(prefix + ".update_DS.zip", "w")
+                        ds_zip = zipfile.ZipFile(ds_tmp, "w")
                     for name, blob in _update_ds_pickles(names, msas, res, ok, options):
                         ds_zip.writestr(name, blob)
                 n_ok += len(ok)
@@ -237,6 +250,10 @@ def build_and_write(input_files, options, device_ordinal=0, output_prefix=None):
                 finish(pending)
                 pending = None
         writer.close()
+        if ds_zip is not None:
+            ds_zip.close()
+            ds_zip = None
+            os.replace(ds_tmp, prefix + ".update_DS.zip")
     except BaseException:
         if pending is not None:
             try:
@@ -244,16 +261,17 @@ def build_and_write(input_files, options, device_ordinal=0, output_prefix=None):
             except Exception:
                 pass
         writer.abort()
-        raise
-    finally:
         if ds_zip is not None:
             ds_zip.close()
+        if os.path.exists(ds_tmp):
+            os.unlink(ds_tmp)
+        raise
     return n_ok
 
 
 def build_loci(input_files, options, device_ordinal=0, want_nodes=None):
     """Loads, builds and returns [(locus_name, alignment, LocusBuild)] for the successful loci, in
-    input order (the in-memory form of a run, used by the multi-GPU shards)."""
+    input order (the in-memory form of a run)."""
     if want_nodes is None:
         want_nodes = options.output_type.prg and not getattr(options, "skip_update_ds", False)
     good = []
@@ -265,30 +283,6 @@ def build_loci(input_files, options, device_ordinal=0, want_nodes=None):
         res.free()
         msas.free()
     return good
-
-
-def write_outputs(good, options):
-    """Final files exactly as InputOutputFiles.create_final_files lays them out, from in-memory builds
-    (the native writers take the PRG strings; the update_DS pickles are Python objects)."""
-    prefix = options.output_prefix
-    ot = options.output_type
-    strings = hostio.PrgStrings([b.prg for _n, _a, b in good])
-    writer = hostio.OutputWriter(prefix, prg=ot.prg, binary=ot.binary, gfa=ot.gfa)
-    try:
-        writer.add(strings, np.arange(len(good), dtype=np.int32), [name for name, _a, _b in good])
-        writer.close()
-    finally:
-        writer.abort()
-        strings.free()
-    if ot.prg and not getattr(options, "skip_update_ds", False):
-        import pickle
-
-        with zipfile.ZipFile(prefix + ".update_DS.zip", "w") as zf:
-            for name, alignment, b in good:
-                builder = PrgBuilder.from_engine(name, alignment, b, options.max_nesting,
-                                                 options.min_match_length)
-                assert builder.build_prg() == b.prg, f"PRG emission mismatch for {name}"
-                zf.writestr(name, pickle.dumps(builder, protocol=4))
 
 
 def run(options):
@@ -303,52 +297,98 @@ def run(options):
     logger.info(f"Using {gpus} GPU(s) to generate PRGs...")
     if gpus == 1:
         n_ok = build_and_write(input_files, options)
-        logger.success("All PRGs generated!")
-        if n_ok == 0:
-            logger.error("No PRGs were built, please check errors")
     else:
-        good = _run_sharded(input_files, options, gpus)
-        logger.success("All PRGs generated!")
-        if len(good) == 0:
-            logger.error("No PRGs were built, please check errors")
-        else:
-            write_outputs(good, options)
+        n_ok = _run_sharded(input_files, options, gpus)
+    logger.success("All PRGs generated!")
+    if n_ok == 0:
+        logger.error("No PRGs were built, please check errors")
     logger.success("All done!")
 
 
-def _shard_worker(rank, shard_files, options, queue, n_shards=1):
+def _shard_worker(rank, shard_files, options, part_prefix, queue, n_shards=1):
     # every shard process drives its own GPU from this host: share the cores (mprg_create reads this)
     os.environ.setdefault("LOCAL_WORLD_SIZE", str(n_shards))
     try:
-        queue.put((rank, build_loci(shard_files, options, device_ordinal=rank), None))
-    except Exception as err:  # propagated to the parent like a Pool worker's exception
-        queue.put((rank, None, err))
+        n_ok = build_and_write(shard_files, options, device_ordinal=rank, output_prefix=part_prefix, part=True)
+        queue.put((rank, n_ok, None))
+    except BaseException as err:  # propagated to the parent like a Pool worker's exception
+        import traceback
+
+        queue.put((rank, None, (type(err).__name__, str(err), traceback.format_exc())))
+
+
+def shard_files_lpt(input_files, gpus):
+    """LPT partition of the loci by file size (a proxy of rows x cols), one shard per GPU."""
+    costs = [os.path.getsize(p) for p in input_files]
+    return engine.lpt_partition(costs, gpus)
+
+
+def merge_parts(part_prefixes, options):
+    """Final files from the shards' parts: native merge of .prg.fa / archives, update_DS members appended."""
+    ot = options.output_type
+    prefix = options.output_prefix
+    n = hostio.merge_outputs(part_prefixes, prefix, prg=ot.prg, binary=ot.binary, gfa=ot.gfa)
+    ds_parts = [p + ".update_DS.zip" for p in part_prefixes if os.path.exists(p + ".update_DS.zip")]
+    if ds_parts:
+        tmp = f"{prefix}.update_DS.zip.tmp{os.getpid()}"
+        with zipfile.ZipFile(tmp, "w") as out:
+            for part in ds_parts:
+                with zipfile.ZipFile(part) as zf:
+                    for info in zf.infolist():
+                        out.writestr(info.filename, zf.read(info))
+                os.unlink(part)
+        os.replace(tmp, prefix + ".update_DS.zip")
+    return n
 
 
 def _run_sharded(input_files, options, gpus):
-    """Loci are independent: LPT partition by file size (a proxy of rows x cols), one process per GPU,
-    no collective; results are gathered on the host and re-ordered to the input order."""
+    """Loci are independent: LPT partition by file size, one process per GPU, no collective.  Every shard
+    loads, builds and WRITES its own part (native writers); the parent only merges the parts -- nothing but
+    a locus count comes back through the queue.  Returns the number of PRGs written."""
     import multiprocessing as mp
+    import queue as queue_mod
 
-    costs = [os.path.getsize(p) for p in input_files]
-    parts = engine.lpt_partition(costs, gpus)
+    parts = shard_files_lpt(input_files, gpus)
+    tmp_dir = tempfile.mkdtemp(prefix=".mprg_parts_", dir=str(Path(options.output_prefix).parent.resolve()))
+    part_prefixes = [os.path.join(tmp_dir, f"part{rank}") for rank in range(len(parts))]
     ctx = mp.get_context("spawn")
     queue = ctx.Queue()
     procs = []
-    for rank, idx in enumerate(parts):
-        p = ctx.Process(target=_shard_worker, args=(rank, [input_files[i] for i in idx], options, queue, gpus))
-        p.start()
-        procs.append(p)
-    results = {}
-    for _ in procs:
-        rank, good, err = queue.get()
-        if err is not None:
-            for p in procs:
+    try:
+        for rank, idx in enumerate(parts):
+            p = ctx.Process(target=_shard_worker,
+                            args=(rank, [input_files[i] for i in idx], options, part_prefixes[rank], queue, gpus))
+            p.start()
+            procs.append(p)
+        counts = {}
+        while len(counts) < len(procs):
+            try:
+                rank, n_ok, err = queue.get(timeout=1.0)
+            except queue_mod.Empty:
+                # a shard that died without reporting (segfault, OOM killer, CUDA abort) must not hang the run
+                dead = [r for r, p in enumerate(procs) if p.exitcode not in (None, 0) and r not in counts]
+                if dead:
+                    raise RuntimeError(f"shard process of GPU {dead[0]} exited with code {procs[dead[0]].exitcode} "
+                                       "without a result")
+                if all(p.exitcode is not None for p in procs) and queue.empty():
+                    missing = [r for r in range(len(procs)) if r not in counts]
+                    if missing:
+                        raise RuntimeError(f"shard process of GPU {missing[0]} ended without a result")
+                continue
+            if err is not None:
+                name, message, trace = err
+                logger.error(f"shard of GPU {rank} failed:\n{trace}")
+                if name == "EmptyMSAError":
+                    raise EmptyMSAError(message)
+                raise RuntimeError(f"{name}: {message}")
+            counts[rank] = n_ok
+        for p in procs:
+            p.join()
+        return merge_parts(part_prefixes, options) if sum(counts.values()) else 0
+    finally:
+        for p in procs:
+            if p.is_alive():
                 p.terminate()
-            raise err
-        results[rank] = good
-    for p in procs:
-        p.join()
-    order = {remove_known_input_extensions(Path(f).name): i for i, f in enumerate(input_files)}
-    merged = [g for rank in sorted(results) for g in results[rank]]
-    return sorted(merged, key=lambda t: order[t[0]])
+        for p in procs:
+            p.join(timeout=10)
+        shutil.rmtree(tmp_dir, ignore_errors=True)

@@ -14,13 +14,14 @@ from ..msa import MSA, SeqRecord
 
 def parse_fasta(handle):
     titles, chunks = [], []
+    # Biopython 1.79 SimpleFastaParser: title = line[1:].rstrip(); every sequence line is rstripped,
+    # then blanks and carriage returns are removed from the joined sequence
     for raw in handle:
-        line = raw.rstrip("\r\n")
-        if line.startswith(">"):
-            titles.append(line[1:])
+        if raw.startswith(">"):
+            titles.append(raw[1:].rstrip())
             chunks.append([])
         elif titles:
-            chunks[-1].append(line.replace(" ", ""))
+            chunks[-1].append(raw.rstrip().replace(" ", "").replace("\r", ""))
     if not titles:
         raise ValueError("No records found in handle")
     records = []

@@ -44,6 +44,7 @@ def test_loader_equals_python_loader_on_every_fixture():
         assert msas.ids(i) == want.ids, f
         assert [r.description for r in msas.alignment(i)] == [r.description for r in want], f
         with_n += int(msas.flags[i] & hostio.FLAG_HAS_N)
+    assert not any(msas.flags & hostio.FLAG_DUPLICATE_IDS)
     assert with_n >= 4  # the contains_n* fixtures went through the in-place N replacement
     # the loci sit back to back, as mprg_build_ascii wants them
     sizes = msas.n_rows.astype(np.int64) * msas.n_cols
@@ -62,6 +63,10 @@ def test_loader_text_edge_cases(tmp_path):
         "empty_title.fa": b">\nAC\n>x\nAG\n",
         "zero_columns.fa": b">a\n>b\n",
         "wrapped_gt.fa": b">a\nAC\n>b\nA\n>\n",
+        # Biopython rstrips every line: trailing tabs / form feeds go, inner ones stay
+        "trailing_tabs.fa": b">a \t\nAC\t\nGT\t \n>b\x0c\nACGT\x0c\n>c\nAC\x1f\n\t\nGT",
+        "inner_tab.fa": b">a\nA\tC\nGT\n>b x\nACG\n-T\n",
+        "utf8_title.fa": ">s1 caf\u00e9 \u2003\nACGT\n>\u00e9\u00e8 second\nAC-T\n".encode("utf-8"),
     }
     paths = []
     for name, blob in cases.items():
@@ -91,14 +96,26 @@ def test_loader_text_edge_cases(tmp_path):
 def test_loader_statuses(tmp_path):
     (tmp_path / "empty.fa").write_bytes(b"")
     (tmp_path / "ragged.fa").write_bytes(b">a\nACGT\n>b\nACG\n")
-    (tmp_path / "latin.fa").write_bytes(">a café\nACGT\n".encode("utf-8"))
+    (tmp_path / "latin.fa").write_bytes(">a\nAC\u00e9T\n".encode("utf-8"))
     (tmp_path / "broken.fa.gz").write_bytes(b"not a gzip stream at all")
+    (tmp_path / "badtitle.fa").write_bytes(b">s\xff1\nACGT\n")
     paths = [tmp_path / "empty.fa", tmp_path / "ragged.fa", tmp_path / "latin.fa", tmp_path / "missing.fa",
-             tmp_path / "broken.fa.gz"]
+             tmp_path / "broken.fa.gz", tmp_path / "badtitle.fa"]
     msas = hostio.load_fasta_files(paths, threads=2, pin=False)
     assert list(msas.status[:4]) == [hostio.LOAD_NO_RECORDS, hostio.LOAD_RAGGED, hostio.LOAD_NOT_ASCII,
                                      hostio.LOAD_IO_ERROR]
-    assert list(msas.n_rows) == [0] * 5 and msas.ascii_bytes == 0
+    assert list(msas.n_rows) == [0] * 6 and msas.ascii_bytes == 0
+    (tmp_path / "dup.fa").write_bytes(b">a x\nAC\n>b\nAC\n>a y\nAG\n")
+    dup = hostio.load_fasta_files([tmp_path / "dup.fa"], threads=1, pin=False)
+    assert dup.status[0] == hostio.LOAD_OK and dup.flags[0] & hostio.FLAG_DUPLICATE_IDS
+    dup.free()
+    # non-ASCII among the sequences: the text loads, the locus is a curation error (skipped, not fatal)
+    with pytest.raises(hostio.NonAsciiSequenceError):
+        hostio.raise_for_load_status(msas, 2)
+    # a title that is not UTF-8: the reference's read fails with the decoder's error
+    assert msas.status[5] == hostio.LOAD_NOT_ASCII
+    with pytest.raises(UnicodeDecodeError):
+        hostio.raise_for_load_status(msas, 5)
     with pytest.raises(ValueError, match="No records found in handle"):
         hostio.raise_for_load_status(msas, 0)
     with pytest.raises(ValueError, match="same length"):
@@ -202,6 +219,61 @@ def test_writer_final_files(tmp_path):
         bad = hostio.PrgStrings(["AC 5 AX 6 T 5 "])
         hostio.OutputWriter(tmp_path / "bad").add(bad, [0], ["bad"])
     strings.free()
+
+
+def test_writer_parts_merge_and_abort(tmp_path):
+    """A sharded run: every shard writes a part, mprg_merge_outputs makes the final files -- byte-identical
+    .prg.fa and the same archive members as one writer; unfinished files never carry a final name."""
+    prgs = all_truth_prgs()[:7]
+    names = [f"locus{c}" for c in "dbagfce"]
+    strings = hostio.PrgStrings(prgs)
+    w = hostio.OutputWriter(tmp_path / "whole", threads=2)
+    w.add(strings, np.arange(7), names)
+    w.close()
+    shards = [[0, 3, 4], [1], [], [2, 5, 6]]
+    parts = []
+    for k, idx in enumerate(shards):
+        pw = hostio.OutputWriter(tmp_path / f"part{k}", threads=1, part=True)
+        if idx:
+            pw.add(strings, idx, [names[i] for i in idx])
+        pw.close()
+        parts.append(tmp_path / f"part{k}")
+    assert (tmp_path / "part1.prg.bin.zip").exists()  # a part of one locus is still an archive
+    assert hostio.merge_outputs(parts, tmp_path / "merged") == 7
+    assert (tmp_path / "merged.prg.fa").read_bytes() == (tmp_path / "whole.prg.fa").read_bytes()
+    for kind in ("bin", "gfa"):
+        with zipfile.ZipFile(tmp_path / f"merged.prg.{kind}.zip") as got, \
+                zipfile.ZipFile(tmp_path / f"whole.prg.{kind}.zip") as want:
+            assert got.testzip() is None
+            assert got.namelist() == [f"{names[i]}.{kind}" for idx in shards for i in idx]
+            for member in want.namelist():
+                assert got.read(member) == want.read(member), member
+    assert not list(tmp_path.glob("part*"))
+    # the whole run holds one locus: plain files
+    pw = hostio.OutputWriter(tmp_path / "p0", part=True)
+    pw.add(strings, [2], ["only"])
+    pw.close()
+    assert hostio.merge_outputs([tmp_path / "p0", tmp_path / "p1"], tmp_path / "single") == 1
+    assert (tmp_path / "single.prg.bin").read_bytes() == hostio.encode_prg(prgs[2]).astype("<u4").tobytes()
+    assert (tmp_path / "single.prg.gfa").read_text() == hostio.prg_to_gfa(prgs[2])
+    assert (tmp_path / "single.prg.fa").read_text() == f">only\n{prgs[2]}\n"
+    assert not (tmp_path / "single.prg.bin.zip").exists()
+    # an aborted writer leaves nothing behind (ADVICE r1: truncated archives blocked reruns)
+    aw = hostio.OutputWriter(tmp_path / "gone", threads=1)
+    aw.add(strings, [0, 1, 2], names[:3])
+    assert not (tmp_path / "gone.prg.bin.zip").exists()  # still under its temporary name
+    aw.abort()
+    assert not list(tmp_path.glob("gone*"))
+    strings.free()
+
+
+def test_mprg_error_crosses_process_boundaries():
+    import pickle
+
+    from make_prg_b200._lib import MprgError
+
+    err = pickle.loads(pickle.dumps(MprgError(-2, "kernel launch failed")))
+    assert isinstance(err, MprgError) and err.code == -2 and "kernel launch failed" in str(err)
 
 
 def test_writer_many_entries_zip64(tmp_path):
