@@ -81,6 +81,17 @@ const char *mprg_last_error(const mprg_ctx *ctx);
 int mprg_device_info(const mprg_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t mprg_launch_count(const mprg_ctx *ctx);
+/* Which kernel variants the engine picked since the last reset (tests pin the deep-locus paths with it):
+ * out[MPRG_PATH_x] = launches of that variant, worker contexts included. */
+#define MPRG_PATH_KMEANS_CTA 0        /* kmeans_kernel: one CTA (1-4 warps) per initialisation */
+#define MPRG_PATH_KMEANS_GROUP 1      /* kmeans_group_kernel: CTA groups per initialisation (deep loci) */
+#define MPRG_PATH_REFCHECK_CTA 2      /* refcheck_kernel: one CTA per problem */
+#define MPRG_PATH_REFCHECK_GRID 3     /* whole-grid one-reference-like check */
+#define MPRG_PATH_REFCHECK_GRID_MULTI 4 /* ... of which with more than one cluster */
+#define MPRG_PATH_KMER_GRID 5         /* whole-grid k-mer numbering */
+#define MPRG_PATH_DEDUPE_GRID 6       /* whole-grid de-duplication */
+#define MPRG_PATH_COUNT 8
+int mprg_path_counts(mprg_ctx *ctx, int64_t *out, int reset);
 /* device time (ms, CUDA events on the context's stream) and algorithmic bytes of the column-scan
  * kernel accumulated since the last reset; used by bench.py for the roofline object */
 int mprg_scan_stats(mprg_ctx *ctx, double *ms, double *bytes, int64_t *launches, int reset);

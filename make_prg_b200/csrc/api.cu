@@ -107,6 +107,21 @@ extern "C" int mprg_copy_stats(mprg_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_b
     return MPRG_OK;
 }
 
+extern "C" int mprg_path_counts(mprg_ctx *ctx, int64_t *out, int reset) {
+    if (!ctx || !out) return MPRG_E_BAD_ARG;
+    for (int k = 0; k < MPRG_PATH_COUNT; ++k) {
+        out[k] = ctx->path_counts[k];
+        for (mprg_ctx *w : ctx->workers) out[k] += w->path_counts[k];
+    }
+    if (reset) {
+        for (int k = 0; k < MPRG_PATH_COUNT; ++k) {
+            ctx->path_counts[k] = 0;
+            for (mprg_ctx *w : ctx->workers) w->path_counts[k] = 0;
+        }
+    }
+    return MPRG_OK;
+}
+
 extern "C" int mprg_timer(mprg_ctx *ctx, int op, double *ms) {
     if (!ctx) return MPRG_E_BAD_ARG;
     cudaSetDevice(ctx->device);

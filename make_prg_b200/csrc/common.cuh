@@ -146,6 +146,8 @@ struct mprg_ctx {
     int n_workers = 1;                // host threads / streams mprg_build may use
     std::vector<mprg_ctx *> workers;  // lazily created worker contexts (same device)
     long long h2d_bytes = 0, d2h_bytes = 0;
+    // which variants the engine chose (mprg_path_counts): see MPRG_PATH_* in mprg.h
+    long long path_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // mprg_timer
     // per-launch log of the scan kernel (algorithmic bytes, device ms), newest last
     std::vector<double> scan_log_bytes, scan_log_ms;

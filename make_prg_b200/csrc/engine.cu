@@ -309,6 +309,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
                                          d_leader_u, d_leader_g, d_group, d_ulen, d_leaders, d_leadlen, d_nu, d_ng,
                                          d_err));
         ctx->launches += 3;
+        ctx->path_counts[MPRG_PATH_DEDUPE_GRID]++;
     } else {
         MPRG_CUDA(ctx, launch_dedupe(s, B[0].as<DTask>(), n_tasks, B[1].as<long long>(), B[3].as<uint8_t>(),
                                      B[2].as<long long>(), B[4].p, d_leader_u, d_leader_g, d_group, d_ulen,
@@ -486,14 +487,18 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
                                        sizeof(int) * np + KM_GROUP_WORDS * sizeof(unsigned) +
                                            sizeof(int) * REFCHECK_FLAG_INTS * big_ref_q.size(),
                                        s));
+        int refcheck_round = 1;  // the check of round r sees up to r clusters
         auto refcheck_all = [&]() -> cudaError_t {
             cudaError_t e = launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, 10);
             ctx->launches++;
+            ctx->path_counts[MPRG_PATH_REFCHECK_CTA]++;
             for (size_t b = 0; b < big_ref_q.size() && e == cudaSuccess; ++b) {
                 const int q = big_ref_q[b];
                 e = launch_refcheck_big(s, d_states, q, st[q].w, st[q].n, B[3].as<uint8_t>(), d_memoff, d_memrows,
                                         d_assign, d_maj, 10, d_refflags + REFCHECK_FLAG_INTS * b);
                 ctx->launches += 3;
+                ctx->path_counts[MPRG_PATH_REFCHECK_GRID]++;
+                if (refcheck_round > 1) ctx->path_counts[MPRG_PATH_REFCHECK_GRID_MULTI]++;
             }
             return e;
         };
@@ -511,6 +516,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
                                            B[8].as<uint8_t>(), B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(),
                                            B[6].as<int>(), d_F + q, d_err));
             ctx->launches += 6;
+            ctx->path_counts[MPRG_PATH_KMER_GRID]++;
         }
         // The number of distinct k-mers F of a problem sizes its count matrix and KMeans scratch.  A level
         // of small problems (a pangenome level: n <= 8, <= 241 positions) does not wait for it: it lays its
@@ -614,7 +620,10 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
                 MPRG_CUDA(ctx, launch_kmeans_group(s, d_states, q, B[12].as<double>(), d_kmd, d_kmi, d_assign,
                                                    d_newlab, d_bars, round == 2, ctx->sm_count));
                 ctx->launches += round == 2 ? 2 : 1;
+                ctx->path_counts[MPRG_PATH_KMEANS_GROUP]++;
             }
+            refcheck_round = round;
+            ctx->path_counts[MPRG_PATH_KMEANS_CTA]++;
             MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab,
                                          d_tickets, max_elements));
             MPRG_CUDA(ctx, refcheck_all());

@@ -83,6 +83,15 @@ class Context:
     def set_workers(self, n):
         self._check(self.lib.mprg_set_workers(self.handle, int(n)))
 
+    PATHS = ("kmeans_cta", "kmeans_group", "refcheck_cta", "refcheck_grid", "refcheck_grid_multi", "kmer_grid",
+             "dedupe_grid")
+
+    def path_counts(self, reset=False):
+        """Launches per kernel variant since the last reset (mprg_path_counts)."""
+        out = np.zeros(8, np.int64)
+        self._check(self.lib.mprg_path_counts(self.handle, ptr(out), int(reset)))
+        return dict(zip(self.PATHS, out.tolist()))
+
     def copy_stats(self, reset=False):
         a, b = C.c_int64(), C.c_int64()
         self._check(self.lib.mprg_copy_stats(self.handle, C.byref(a), C.byref(b), int(reset)))

@@ -68,7 +68,9 @@ SYNTH_CASES = (
     + [dict(config=5, index=1, N=5, L=L) for L in (3, 7)]
     + [dict(config=2, index=7, N=2, L=7), dict(config=2, index=8, N=1, L=7),
        dict(config=2, index=9, N=10, L=5)]
-    + [dict(config=4, index=0, N=10, L=7, rows=300, cols=1500)]
+    # "4flat": round 1's config-#4 generator (no deep clades: the clustering loop ends before KMeans);
+    # the deep-clade config #4 has its own vectors (oracle/gen_golden_deep.py -> tests/golden/deep.json)
+    + [dict(config="4flat", index=0, N=10, L=7, rows=300, cols=1500)]
 )
 
 

@@ -278,3 +278,23 @@ def kmeans_fit_predict(X0, K):
     """Labels as the reference sees them: KMeans(...).fit(X) then .predict(X)."""
     fit_labels, inertia, centers = kmeans_fit(X0, K)
     return kmeans_predict(X0, centers), inertia, centers, fit_labels
+
+
+def sklearn_fit_predict(X0, K):
+    """The same call through the INSTALLED scikit-learn (>= 1.4) forced to the pinned 1.3.0 behaviour
+    (n_init=10; run with OMP_NUM_THREADS=1 for sequential reductions) -- the library the unmodified reference
+    itself runs on in this image (oracle/run_reference.py).  For clustering problems too large for the
+    pure-Python restatement above (deep loci: thousands of sequences x 4^k k-mers); the restatement is pinned
+    against this very function by tests/test_oracle_kmeans.py.  Same return shape as kmeans_fit_predict."""
+    from sklearn.cluster import KMeans
+
+    X = np.ascontiguousarray(X0, dtype=np.float64)
+    km = KMeans(n_clusters=K, random_state=SEED, algorithm="elkan", n_init=N_INIT).fit(X)
+    return km.predict(X), float(km.inertia_), km.cluster_centers_, km.labels_
+
+
+def hybrid_fit_predict(X0, K, limit=1 << 16):
+    """Restatement for small problems, installed scikit-learn above `limit` matrix elements."""
+    if X0.shape[0] * X0.shape[1] <= limit:
+        return kmeans_fit_predict(X0, K)
+    return sklearn_fit_predict(X0, K)

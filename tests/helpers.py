@@ -105,3 +105,64 @@ def prg_spells_all_rows(prg, M):
         if not pat.fullmatch(s):
             return False
     return True
+
+
+def deep_cases():
+    """Deep-clade loci (config #4 class) run through the unmodified reference (oracle/gen_golden_deep.py)."""
+    with open(GOLDEN / "deep.json") as fh:
+        return json.load(fh)
+
+
+def deep_msa(case):
+    """The MSA of a deep case, regenerated from its seed and pinned by the recorded sha256."""
+    import hashlib
+
+    from make_prg_b200 import synth
+
+    M = synth.synth_deep_msa(**case["gen"])
+    assert hashlib.sha256(M.tobytes()).hexdigest() == case["msa_sha256"], "synthetic generator drifted"
+    return M
+
+
+def deep_kmeans_problems(case, M):
+    """[(X, K, golden record)] for the big KMeans problems of a deep case: the count matrices come from the
+    oracle's own k-mer counting (checked against the sha256 of what the reference handed to scikit-learn),
+    the answers from the recorded scikit-learn results, so nothing slow runs."""
+    import hashlib
+
+    import make_prg_oracle as mo
+
+    golden = iter(case["kmeans"])
+    recorded = {}
+    out = []
+
+    def replay(X, K):
+        # replays the reference's answers in call order; small problems go to the restatement
+        if X.shape[0] * X.shape[1] < 4096:
+            return mo.kmeans13.kmeans_fit_predict(X, K)
+        g = next(golden)
+        assert (g["n"], g["F"], g["K"]) == (X.shape[0], X.shape[1], K)
+        assert hashlib.sha256(np.ascontiguousarray(X, np.float64).tobytes()).hexdigest() == g["x_sha256"]
+        out.append((np.ascontiguousarray(X, np.float64).copy(), K, g))
+        return np.array(g["labels"]), float.fromhex(g["inertia"]), None, None
+
+    ids = [f"s{i}" for i in range(M.shape[0])]
+    prg, builder = mo.build_prg_from_matrix(ids, M, case["N"], case["L"], kmeans=replay)
+    recorded["prg"] = prg
+    return out, prg
+
+
+def tree_dump(res, locus, M):
+    """Pre-order dump of a built locus in the shape of oracle/run_reference.dump_tree:
+    [class, node_id, nesting_level, rows, columns after all-gap removal, children]."""
+    t = res.nodes(locus)
+    names = {0: "LeafNode", 1: "MultiIntervalNode", 2: "MultiClusterNode"}
+    out = []
+    for i in range(len(t["kind"])):
+        rows = (np.arange(M.shape[0]) if t["row_off"][i] < 0
+                else t["row_pool"][t["row_off"][i]:t["row_off"][i] + t["n_rows"][i]])
+        S = M[rows, t["c0"][i]:t["c1"][i]]
+        keep = int((~(S == ord("-")).all(axis=0)).sum())
+        out.append([names[int(t["kind"][i])], i, int(t["nesting_level"][i]), len(rows), keep,
+                    int(t["n_children"][i])])
+    return out

@@ -174,9 +174,11 @@ def test_build_ascii_from_pinned_memory_equals_pageable(ctx, monkeypatch):
 
 
 def test_deep_locus_takes_the_whole_grid_paths(ctx):
-    """One deep locus (every row distinct: private SNPs) sends a single huge clustering problem through
-    the whole-grid k-mer numbering, the CTA-group KMeans and the whole-grid one-reference-like check;
-    the PRG must still be the oracle's, byte for byte."""
+    """One deep locus of the FLAT generator (every row distinct through private SNPs, but all within 20 % of
+    the majority string) sends a single huge clustering problem through the whole-grid de-duplication, k-mer
+    numbering and one-reference-like check with ONE cluster; the loop of cluster_sequences.py:256-274 ends
+    there, so no KMeans runs (the deep-clade loci of tests/test_gpu_deep.py do reach it).  The PRG must still
+    be the oracle's, byte for byte."""
     M = synth.synth_msa(1500, 3000, 4_100_000, n_haps=300, var_frac=0.04, private_snp=0.01)
     want, _ = mo.build_prg_from_matrix([f"s{r}" for r in range(M.shape[0])], M, 10, 7)
     _, res = _build(ctx, [M], 10, 7)
