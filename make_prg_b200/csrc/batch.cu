@@ -202,6 +202,8 @@ extern "C" void mprg_destroy(mprg_ctx *ctx) {
                       &ctx->d_stage};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : ctx->d_c) b.release();
+    for (DevBuf &b : ctx->d_dev) b.release();
+    ctx->h_cnt.release();
     for (auto &a : ctx->idle_arenas) cudaFree(a.first);
     ctx->idle_arenas.clear();
     ctx->h_a.release();

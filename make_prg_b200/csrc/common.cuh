@@ -160,6 +160,11 @@ struct mprg_ctx {
         d_stage;
     // scratch for clustering
     mprg::DevBuf d_c[16];
+    // buffers of the device-resident level loop (engine_dev.cu): tree, row pool, alleles, task / problem tables
+    mprg::DevBuf d_dev[32];
+    mprg::PinnedBuf h_cnt;  // the counter block the host reads twice per level
+    bool pending_scan = false;  // a scan launch whose events have not been read yet
+    double pending_scan_bytes = 0;
     // scratch (pinned host)
     mprg::PinnedBuf h_a, h_b, h_c, h_d;
     // packed arenas of freed batches, kept for the next batch of about the same size: cudaMalloc and

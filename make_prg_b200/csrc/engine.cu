@@ -19,41 +19,13 @@
 #include <thread>
 #include <unordered_set>
 
-#include "common.cuh"
-#include "kernels.cuh"
+#include "engine.cuh"
 
 using namespace mprg;
 
 namespace mprg {
 
-// ---- optional wall-clock phase trace (MPRG_TRACE=1) ------------------------------------------------
-struct PhaseTrace {
-    bool on;
-    std::vector<std::pair<std::string, double>> acc;
-    std::chrono::steady_clock::time_point t;
-    PhaseTrace() : on(getenv("MPRG_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
-    void mark(const char *name) {
-        if (!on) return;
-        auto now = std::chrono::steady_clock::now();
-        const double ms = std::chrono::duration<double, std::milli>(now - t).count();
-        t = now;
-        for (auto &p : acc)
-            if (p.first == name) {
-                p.second += ms;
-                return;
-            }
-        acc.emplace_back(name, ms);
-    }
-    void report(const char *title) {
-        if (!on) return;
-        double tot = 0;
-        for (auto &p : acc) tot += p.second;
-        fprintf(stderr, "[mprg trace] %s total %.2f ms\n", title, tot);
-        for (auto &p : acc) fprintf(stderr, "    %-28s %8.2f ms\n", p.first.c_str(), p.second);
-    }
-};
-static thread_local PhaseTrace *g_trace = nullptr;
-#define TRACE(name) do { if (g_trace) g_trace->mark(name); } while (0)
+thread_local PhaseTrace *g_trace = nullptr;
 
 // ---- MT19937 as numpy's RandomState(seed) / random_sample ---------------------------------------
 static void randomstate_doubles(uint32_t seed, double *out, int count) {
@@ -84,7 +56,7 @@ static void randomstate_doubles(uint32_t seed, double *out, int count) {
 }
 
 static bool g_rand_uploaded = false;
-static int ensure_rand(mprg_ctx *ctx) {
+int ensure_rand(mprg_ctx *ctx) {
     if (g_rand_uploaded) return MPRG_OK;
     double r[KM_RAND_COUNT];
     randomstate_doubles(2u, r, KM_RAND_COUNT);
@@ -94,12 +66,6 @@ static int ensure_rand(mprg_ctx *ctx) {
 }
 
 // ---- allele extraction ---------------------------------------------------------------------------
-struct ExtractItem {
-    long long base;
-    int stride, row, c0, c1;
-    long long out_off;
-};
-
 __global__ void __launch_bounds__(128)
 extract_kernel(const uint8_t *__restrict__ packed, const ExtractItem *__restrict__ items, int n_items,
                uint8_t *__restrict__ out, int *__restrict__ out_len) {
@@ -122,6 +88,13 @@ extract_kernel(const uint8_t *__restrict__ packed, const ExtractItem *__restrict
         len += __popc(keep);
     }
     if (lane == 0) out_len[it] = len;
+}
+
+cudaError_t launch_extract(cudaStream_t s, const uint8_t *packed, const ExtractItem *items, int n_items, uint8_t *out,
+                           int *out_len) {
+    if (n_items <= 0) return cudaSuccess;
+    extract_kernel<<<(n_items + 3) / 4, 128, 0, s>>>(packed, items, n_items, out, out_len);
+    return cudaGetLastError();
 }
 
 // ---- clustering of a level ------------------------------------------------------------------------
@@ -221,6 +194,271 @@ static int cluster_of_rows(const ClusterOut &o, int kmer_size, std::vector<int> 
     for (int r = 0; r < R; ++r) cluster_of_row[r] = index_of_group[o.group[r]];
     return n_cl;
 }
+
+// The clustering loop of kmeans_cluster_seqs (cluster_sequences.py:249-274) for the problems of one level,
+// driven from the host: member lists, k-mer numbering (whole-grid kernels for deep problems), count matrices
+// sized exactly (or by the bound F <= positions when every problem is small), then <= 9 rounds of
+// [KMeans, one-reference-like check] with the loop state on the device.  The unpacked rows (d_G), the
+// per-row groups and the leader lengths are the outputs of the de-duplication of the same level.
+// fetch: copy the final loop states and assignments back (the device-resident loop reads them in place).
+int run_problems_host(mprg_ctx *ctx, cudaStream_t s, const std::vector<HostProblem> &hp, const std::vector<int> &seq_rows,
+                      int kmer_size, const uint8_t *d_G, const int *d_group, const int *d_leadlen, int *d_leader_u,
+                      int *d_err, bool fetch, ProblemRun &run) {
+    const int np = (int)hp.size();
+    DevBuf *B = ctx->d_c;
+    std::vector<ClusterState> &st = run.st;
+    std::vector<int> &h_assign = run.h_assign;
+    st.assign(np, ClusterState());
+    long long seq_total = 0;
+    // ---- member lists + k-mer count matrices ----
+    std::vector<KmerProb> kp(np);
+    std::vector<MemberProb> mp(np);
+    long long useq_total = 0, ints_total = 0, tab_total = 0, x_total = 0;
+    long long maj_total = 0, assign_total = 0, memoff_total = 0, memrows_total = 0;
+    std::vector<int> big_ref_q;  // deep loci: one-reference-like check with the whole grid
+    for (int q = 0; q < np; ++q) {
+        const HostProblem &p = hp[q];
+        const int w = p.w;
+        if (p.P > 0x3fffffffLL) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "clustering problem too large");
+        KmerProb &k = kp[q];
+        k.g_off = p.g_off;
+        k.w = w;
+        k.n = p.n;
+        k.seq_off = (int)seq_total;
+        seq_total += p.n;
+        k.useq_off = useq_total;
+        useq_total += (long long)p.n * w;
+        k.pos_off = ints_total;
+        ints_total += 2LL * p.n + 1 + 2 * p.P;
+        int T = 64;
+        while (T < 2 * p.P) T <<= 1;
+        k.T = T;
+        k.tab_off = tab_total;
+        tab_total += T;
+        k.Pmax = (int)p.P;
+        k.big = p.P >= KMER_BIG_POSITIONS ? 1 : 0;
+        k.pad = 0;
+        k.x_off = 0;  // set below, once the number of distinct k-mers is known
+        MemberProb &m = mp[q];
+        m.row_off = p.row_off;
+        m.R = p.R;
+        m.n_groups = p.n_groups;
+        m.k = kmer_size;
+        m.mem_off = (int)memoff_total;
+        m.mem_rows_off = (int)memrows_total;
+        ClusterState &c = st[q];
+        memset(&c, 0, sizeof(c));
+        c.K = 1;
+        c.n = p.n;
+        c.w = w;
+        c.g_off = p.g_off;
+        c.mem_off = m.mem_off;
+        c.mem_rows_off = m.mem_rows_off;
+        memoff_total += p.n + 1;
+        memrows_total += p.R;
+        c.assign_off = (int)assign_total;
+        assign_total += p.n;
+        c.maj_off = maj_total;
+        if ((long long)p.R * w >= REFCHECK_BIG_SYMBOLS) {
+            c.big_ref = 1 + (int)big_ref_q.size();
+            big_ref_q.push_back(q);
+            maj_total += 10LL * w;  // one majority string per cluster
+        } else {
+            maj_total += w;
+        }
+    }
+    // 7 kprobs|mprobs, 8 useq, 9 ints, 10 keys, 11 ming, 12 X, 13 states|F, 14 seq_rows|mem|assign|newlab|maj, 15 kmeans scratch
+    MPRG_CUDA(ctx, B[7].reserve(sizeof(KmerProb) * np + sizeof(MemberProb) * np));
+    MPRG_CUDA(ctx, B[8].reserve((size_t)useq_total));
+    MPRG_CUDA(ctx, B[9].reserve(sizeof(int) * ints_total));
+    MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * tab_total));
+    MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * tab_total));
+    MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * 2 * np + KM_GROUP_WORDS * sizeof(unsigned) +
+                                  sizeof(int) * REFCHECK_FLAG_INTS * big_ref_q.size() + 64));
+    const size_t o_seqrows = 0;
+    const size_t o_memoff = o_seqrows + sizeof(int) * seq_rows.size();
+    const size_t o_memrows = o_memoff + sizeof(int) * memoff_total;
+    const size_t o_assign = o_memrows + sizeof(int) * memrows_total;
+    const size_t o_newlab = o_assign + sizeof(int) * assign_total;
+    const size_t o_maj = o_newlab + sizeof(int) * assign_total;
+    MPRG_CUDA(ctx, B[14].reserve(o_maj + (size_t)maj_total + 16));
+    uint8_t *b14 = B[14].as<uint8_t>();
+    int *d_seqrows = reinterpret_cast<int *>(b14 + o_seqrows);
+    int *d_memoff = reinterpret_cast<int *>(b14 + o_memoff);
+    int *d_memrows = reinterpret_cast<int *>(b14 + o_memrows);
+    int *d_assign = reinterpret_cast<int *>(b14 + o_assign);
+    int *d_newlab = reinterpret_cast<int *>(b14 + o_newlab);
+    uint8_t *d_maj = b14 + o_maj;
+    KmerProb *d_kp = B[7].as<KmerProb>();
+    MemberProb *d_mp = reinterpret_cast<MemberProb *>(d_kp + np);
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_kp, kp.data(), sizeof(KmerProb) * np, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_mp, mp.data(), sizeof(MemberProb) * np, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_seqrows, seq_rows.data(), sizeof(int) * seq_rows.size(), s));
+    ClusterState *d_states = B[13].as<ClusterState>();
+    int *d_F = reinterpret_cast<int *>(d_states + np);
+    int *d_tickets = d_F + np;  // per-problem "initialisations finished" counters of kmeans_kernel
+    // barriers and broadcast slots of launch_kmeans_group (8-byte aligned)
+    unsigned *d_bars = reinterpret_cast<unsigned *>(d_tickets + np);  // d_F + 2 * np: 8-byte aligned
+    int *d_refflags = reinterpret_cast<int *>(d_bars + KM_GROUP_WORDS);
+    MPRG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0,
+                                   sizeof(int) * np + KM_GROUP_WORDS * sizeof(unsigned) +
+                                       sizeof(int) * REFCHECK_FLAG_INTS * big_ref_q.size(),
+                                   s));
+    int refcheck_round = 1;  // the check of round r sees up to r clusters
+    auto refcheck_all = [&]() -> cudaError_t {
+        cudaError_t e = launch_refcheck(s, d_states, np, d_G, d_memoff, d_memrows, d_assign, d_maj, 10);
+        ctx->launches++;
+        ctx->path_counts[MPRG_PATH_REFCHECK_CTA]++;
+        for (size_t b = 0; b < big_ref_q.size() && e == cudaSuccess; ++b) {
+            const int q = big_ref_q[b];
+            e = launch_refcheck_big(s, d_states, q, st[q].w, st[q].n, d_G, d_memoff, d_memrows,
+                                    d_assign, d_maj, 10, d_refflags + REFCHECK_FLAG_INTS * b);
+            ctx->launches += 3;
+            ctx->path_counts[MPRG_PATH_REFCHECK_GRID]++;
+            if (refcheck_round > 1) ctx->path_counts[MPRG_PATH_REFCHECK_GRID_MULTI]++;
+        }
+        return e;
+    };
+    // d_leader_u is free after dedupe: scratch for the group -> long-sequence map
+    MPRG_CUDA(ctx, launch_members(s, d_mp, np, d_group, d_leadlen, d_leader_u, d_memoff, d_memrows));
+    MPRG_CUDA(ctx, launch_kmer(s, d_kp, np, d_seqrows, d_G, kmer_size, B[8].as<uint8_t>(),
+                               B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), d_F, d_err));
+    ctx->launches += 2;
+    // deep loci: problems with very many k-mer positions go through the whole-grid kernels, one by one
+    for (int q = 0; q < np; ++q) {
+        if (!kp[q].big) continue;
+        const size_t n_chunks = ((size_t)kp[q].Pmax + 4095) / 4096;
+        MPRG_CUDA(ctx, B[6].reserve(sizeof(int) * (n_chunks + 1)));
+        MPRG_CUDA(ctx, launch_kmer_big(s, d_kp, q, &kp[q], d_seqrows, d_G, kmer_size,
+                                       B[8].as<uint8_t>(), B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(),
+                                       B[6].as<int>(), d_F + q, d_err));
+        ctx->launches += 6;
+        ctx->path_counts[MPRG_PATH_KMER_GRID]++;
+    }
+    // The number of distinct k-mers F of a problem sizes its count matrix and KMeans scratch.  A level
+    // of small problems (a pangenome level: n <= 8, <= 241 positions) does not wait for it: it lays its
+    // matrices out for the upper bound F <= P (every k-mer position distinct) and the device passes the
+    // real F from the numbering kernel to the loop state; levels with a big problem fetch F first.
+    bool bounded = !getenv("MPRG_EXACT_F");
+    {
+        long long bound_elems = 0;
+        for (int q = 0; q < np && bounded; ++q) {
+            if (kp[q].big || (long long)hp[q].n * hp[q].P >= KMEANS_BIG_ELEMENTS) bounded = false;
+            bound_elems += (long long)hp[q].n * hp[q].P;
+        }
+        if (bound_elems > (16LL << 20)) bounded = false;  // 128 MB of doubles for the level
+    }
+    std::vector<int> h_F(np + 1, 0);
+    if (bounded) {
+        for (int q = 0; q < np; ++q) h_F[q] = (int)hp[q].P;
+    } else {
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_F.data(), d_F, sizeof(int) * np, s));
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &h_F[np], d_err, sizeof(int), s));
+        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        if (h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
+    }
+    TRACE("cl: kmer setup+run+sync");
+
+    // ---- count matrices, sized exactly now that every F is known ----
+    long long max_P = 0;
+    for (int q = 0; q < np; ++q) {
+        kp[q].x_off = st[q].x_off = x_total;
+        x_total += (long long)hp[q].n * h_F[q];
+        if (kp[q].big && (size_t)h_F[q] * sizeof(int) <= 200 * 1024) kp[q].big |= 2;
+        if (!(kp[q].big & 2)) max_P = std::max(max_P, hp[q].P);
+    }
+    if (g_trace) {
+        long long big_n = 0, big_F = 0, big_P = 0;
+        for (int q = 0; q < np; ++q) {
+            big_n = std::max<long long>(big_n, hp[q].n);
+            big_F = std::max<long long>(big_F, h_F[q]);
+            big_P = std::max<long long>(big_P, hp[q].P);
+        }
+        fprintf(stderr, "[mprg trace] clustering level: %d problems, max n %lld, max F %lld, max positions %lld, X %.1f MB\n",
+                np, big_n, big_F, big_P, 8e-6 * (double)x_total);
+    }
+    // ---- KMeans loop (cluster_sequences.py:256-274) ----
+    long long kmd_total = 0, kmi_total = 0;
+    for (int q = 0; q < np; ++q) {
+        st[q].F = h_F[q];
+        st[q].big = (long long)st[q].n * st[q].F >= KMEANS_BIG_ELEMENTS ? 1 : 0;
+        st[q].kmd_off = kmd_total;
+        st[q].kmi_off = kmi_total;
+        kmd_total += kmeans_dscratch_doubles(st[q].n, st[q].F);
+        kmi_total += kmeans_iscratch_ints(st[q].n);
+    }
+    const double want = 8.0 * (double)x_total + 8.0 * (double)kmd_total + 4.0 * (double)kmi_total;
+    if (want > 1e9) {  // cudaMemGetInfo is a slow, serialising driver call: only deep loci ask
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const double have = (double)free_b + (double)B[12].cap + (double)B[15].cap;
+        if (want > 0.9 * have)
+            MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "k-mer count matrices and KMeans scratch of this level do not fit in device memory");
+    }
+    MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * std::max<long long>(x_total, 1)));
+    MPRG_CUDA(ctx, cudaMemsetAsync(B[12].p, 0, sizeof(double) * x_total, s));
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_kp, kp.data(), sizeof(KmerProb) * np, s));
+    MPRG_CUDA(ctx, launch_kmer_fill(s, d_kp, np, max_P, B[9].as<int>(), d_F, B[12].as<double>()));
+    ctx->launches++;
+    for (int q = 0; q < np; ++q)
+        if (kp[q].big & 2) {
+            MPRG_CUDA(ctx, launch_kmer_fill_big(s, d_kp, q, &kp[q], h_F[q], B[9].as<int>(), B[12].as<double>()));
+            ctx->launches++;
+        }
+    MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * kmd_total + sizeof(int) * kmi_total + 64));
+    double *d_kmd = B[15].as<double>();
+    int *d_kmi = reinterpret_cast<int *>(d_kmd + kmd_total);
+    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_states, st.data(), sizeof(ClusterState) * np, s));
+    if (bounded) {
+        MPRG_CUDA(ctx, launch_set_features(s, d_states, d_F, np));
+        ctx->launches++;
+    }
+    MPRG_CUDA(ctx, cudaMemsetAsync(d_assign, 0, sizeof(int) * assign_total, s));
+    const int MAX_CLUSTERS = 10;
+    MPRG_CUDA(ctx, refcheck_all());
+    // every problem that ever runs KMeans runs it in the K == 2 round: centre its data once, now
+    MPRG_CUDA(ctx, launch_kmeans_prepare(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi));
+    ctx->launches++;
+    std::vector<int> big_q;  // deep loci: these problems get the whole GPU, one after the other
+    for (int q = 0; q < np; ++q)
+        if (st[q].big) big_q.push_back(q);
+    // A problem with n distinct sequences stops at K == n (cluster_sequences.py:257-259), so its last
+    // KMeans round is K = n - 1: the level needs rounds 2 .. max n - 1, not always 2 .. 10 (a deep level
+    // of a pangenome batch has max n = 3 or 4: one or two rounds instead of nine)
+    int max_n = 0;
+    long long max_elements = 0;
+    for (int q = 0; q < np; ++q) {
+        max_n = std::max(max_n, hp[q].n);
+        if (!st[q].big) max_elements = std::max(max_elements, (long long)st[q].n * st[q].F);
+    }
+    const int last_round = std::min(MAX_CLUSTERS, max_n - 1);
+    for (int round = 2; round <= last_round; ++round) {
+        for (int q : big_q) {
+            MPRG_CUDA(ctx, launch_kmeans_group(s, d_states, q, B[12].as<double>(), d_kmd, d_kmi, d_assign,
+                                               d_newlab, d_bars, round == 2, ctx->sm_count));
+            ctx->launches += round == 2 ? 2 : 1;
+            ctx->path_counts[MPRG_PATH_KMEANS_GROUP]++;
+        }
+        refcheck_round = round;
+        ctx->path_counts[MPRG_PATH_KMEANS_CTA]++;
+        MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab,
+                                     d_tickets, max_elements));
+        MPRG_CUDA(ctx, refcheck_all());
+        ctx->launches++;
+    }
+    run.d_states = d_states;
+    run.d_assign = d_assign;
+    if (fetch) {
+        h_assign.resize((size_t)assign_total);
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, st.data(), d_states, sizeof(ClusterState) * np, s));
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_assign.data(), d_assign, sizeof(int) * assign_total, s));
+        if (bounded) MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &h_F[np], d_err, sizeof(int), s));
+        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        if (bounded && h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
+    }
+    return MPRG_OK;
+}
+
 
 // Runs kmeans_cluster_seqs for every task of a level.
 //   want_clusters[t] == 0   only the de-duplication outputs are needed
@@ -387,254 +625,33 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
     const int np = (int)probs.size();
     TRACE("cl: host grouping");
 
-    std::vector<ClusterState> st(np);
+    std::vector<ClusterState> st;
     std::vector<int> h_assign;
     if (np > 0) {
-        // ---- member lists + k-mer count matrices ----
-        std::vector<KmerProb> kp(np);
-        std::vector<MemberProb> mp(np);
-        long long useq_total = 0, ints_total = 0, tab_total = 0, x_total = 0;
-        long long maj_total = 0, assign_total = 0, memoff_total = 0, memrows_total = 0;
-        std::vector<int> big_ref_q;  // deep loci: one-reference-like check with the whole grid
+        std::vector<HostProblem> hp(np);
         for (int q = 0; q < np; ++q) {
             const Prob &p = probs[q];
             const mprg_task &ht = h_tasks[p.task];
+            HostProblem &h = hp[q];
+            h.task = p.task;
+            h.n = p.n;
+            h.P = p.P;
+            h.w = ht.c1 - ht.c0;
+            h.R = ht.n_rows;
+            h.n_groups = out[p.task].n_ungapped;
+            h.g_off = g_off[p.task];
+            h.row_off = row_off[p.task];
             const ClusterOut &o = out[p.task];
-            const int w = ht.c1 - ht.c0;
-            if (p.P > 0x3fffffffLL) MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "clustering problem too large");
-            KmerProb &k = kp[q];
-            k.g_off = g_off[p.task];
-            k.w = w;
-            k.n = p.n;
-            k.seq_off = (int)seq_rows.size();
             for (int g = 0; g < o.n_ungapped; ++g)
                 if (o.leader_len[g] >= kmer_size) seq_rows.push_back(o.leaders[g]);
-            k.useq_off = useq_total;
-            useq_total += (long long)p.n * w;
-            k.pos_off = ints_total;
-            ints_total += 2LL * p.n + 1 + 2 * p.P;
-            int T = 64;
-            while (T < 2 * p.P) T <<= 1;
-            k.T = T;
-            k.tab_off = tab_total;
-            tab_total += T;
-            k.Pmax = (int)p.P;
-            k.big = p.P >= KMER_BIG_POSITIONS ? 1 : 0;
-            k.pad = 0;
-            k.x_off = 0;  // set below, once the number of distinct k-mers is known
-            MemberProb &m = mp[q];
-            m.row_off = row_off[p.task];
-            m.R = ht.n_rows;
-            m.n_groups = o.n_ungapped;
-            m.k = kmer_size;
-            m.mem_off = (int)memoff_total;
-            m.mem_rows_off = (int)memrows_total;
-            ClusterState &c = st[q];
-            memset(&c, 0, sizeof(c));
-            c.K = 1;
-            c.n = p.n;
-            c.w = w;
-            c.g_off = g_off[p.task];
-            c.mem_off = m.mem_off;
-            c.mem_rows_off = m.mem_rows_off;
-            memoff_total += p.n + 1;
-            memrows_total += ht.n_rows;
-            c.assign_off = (int)assign_total;
-            assign_total += p.n;
-            c.maj_off = maj_total;
-            if ((long long)ht.n_rows * w >= REFCHECK_BIG_SYMBOLS) {
-                c.big_ref = 1 + (int)big_ref_q.size();
-                big_ref_q.push_back(q);
-                maj_total += 10LL * w;  // one majority string per cluster
-            } else {
-                maj_total += w;
-            }
         }
-        // 7 kprobs|mprobs, 8 useq, 9 ints, 10 keys, 11 ming, 12 X, 13 states|F, 14 seq_rows|mem|assign|newlab|maj, 15 kmeans scratch
-        MPRG_CUDA(ctx, B[7].reserve(sizeof(KmerProb) * np + sizeof(MemberProb) * np));
-        MPRG_CUDA(ctx, B[8].reserve((size_t)useq_total));
-        MPRG_CUDA(ctx, B[9].reserve(sizeof(int) * ints_total));
-        MPRG_CUDA(ctx, B[10].reserve(sizeof(uint64_t) * tab_total));
-        MPRG_CUDA(ctx, B[11].reserve(sizeof(int) * tab_total));
-        MPRG_CUDA(ctx, B[13].reserve(sizeof(ClusterState) * np + sizeof(int) * 2 * np + KM_GROUP_WORDS * sizeof(unsigned) +
-                                      sizeof(int) * REFCHECK_FLAG_INTS * big_ref_q.size() + 64));
-        const size_t o_seqrows = 0;
-        const size_t o_memoff = o_seqrows + sizeof(int) * seq_rows.size();
-        const size_t o_memrows = o_memoff + sizeof(int) * memoff_total;
-        const size_t o_assign = o_memrows + sizeof(int) * memrows_total;
-        const size_t o_newlab = o_assign + sizeof(int) * assign_total;
-        const size_t o_maj = o_newlab + sizeof(int) * assign_total;
-        MPRG_CUDA(ctx, B[14].reserve(o_maj + (size_t)maj_total + 16));
-        uint8_t *b14 = B[14].as<uint8_t>();
-        int *d_seqrows = reinterpret_cast<int *>(b14 + o_seqrows);
-        int *d_memoff = reinterpret_cast<int *>(b14 + o_memoff);
-        int *d_memrows = reinterpret_cast<int *>(b14 + o_memrows);
-        int *d_assign = reinterpret_cast<int *>(b14 + o_assign);
-        int *d_newlab = reinterpret_cast<int *>(b14 + o_newlab);
-        uint8_t *d_maj = b14 + o_maj;
-        KmerProb *d_kp = B[7].as<KmerProb>();
-        MemberProb *d_mp = reinterpret_cast<MemberProb *>(d_kp + np);
-        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_kp, kp.data(), sizeof(KmerProb) * np, s));
-        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_mp, mp.data(), sizeof(MemberProb) * np, s));
-        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_seqrows, seq_rows.data(), sizeof(int) * seq_rows.size(), s));
-        ClusterState *d_states = B[13].as<ClusterState>();
-        int *d_F = reinterpret_cast<int *>(d_states + np);
-        int *d_tickets = d_F + np;  // per-problem "initialisations finished" counters of kmeans_kernel
-        // barriers and broadcast slots of launch_kmeans_group (8-byte aligned)
-        unsigned *d_bars = reinterpret_cast<unsigned *>(d_tickets + np);  // d_F + 2 * np: 8-byte aligned
-        int *d_refflags = reinterpret_cast<int *>(d_bars + KM_GROUP_WORDS);
-        MPRG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0,
-                                       sizeof(int) * np + KM_GROUP_WORDS * sizeof(unsigned) +
-                                           sizeof(int) * REFCHECK_FLAG_INTS * big_ref_q.size(),
-                                       s));
-        int refcheck_round = 1;  // the check of round r sees up to r clusters
-        auto refcheck_all = [&]() -> cudaError_t {
-            cudaError_t e = launch_refcheck(s, d_states, np, B[3].as<uint8_t>(), d_memoff, d_memrows, d_assign, d_maj, 10);
-            ctx->launches++;
-            ctx->path_counts[MPRG_PATH_REFCHECK_CTA]++;
-            for (size_t b = 0; b < big_ref_q.size() && e == cudaSuccess; ++b) {
-                const int q = big_ref_q[b];
-                e = launch_refcheck_big(s, d_states, q, st[q].w, st[q].n, B[3].as<uint8_t>(), d_memoff, d_memrows,
-                                        d_assign, d_maj, 10, d_refflags + REFCHECK_FLAG_INTS * b);
-                ctx->launches += 3;
-                ctx->path_counts[MPRG_PATH_REFCHECK_GRID]++;
-                if (refcheck_round > 1) ctx->path_counts[MPRG_PATH_REFCHECK_GRID_MULTI]++;
-            }
-            return e;
-        };
-        // d_leader_u is free after dedupe: scratch for the group -> long-sequence map
-        MPRG_CUDA(ctx, launch_members(s, d_mp, np, d_group, d_leadlen, d_leader_u, d_memoff, d_memrows));
-        MPRG_CUDA(ctx, launch_kmer(s, d_kp, np, d_seqrows, B[3].as<uint8_t>(), kmer_size, B[8].as<uint8_t>(),
-                                   B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(), d_F, d_err));
-        ctx->launches += 2;
-        // deep loci: problems with very many k-mer positions go through the whole-grid kernels, one by one
-        for (int q = 0; q < np; ++q) {
-            if (!kp[q].big) continue;
-            const size_t n_chunks = ((size_t)kp[q].Pmax + 4095) / 4096;
-            MPRG_CUDA(ctx, B[6].reserve(sizeof(int) * (n_chunks + 1)));
-            MPRG_CUDA(ctx, launch_kmer_big(s, d_kp, q, &kp[q], d_seqrows, B[3].as<uint8_t>(), kmer_size,
-                                           B[8].as<uint8_t>(), B[9].as<int>(), B[10].as<uint64_t>(), B[11].as<int>(),
-                                           B[6].as<int>(), d_F + q, d_err));
-            ctx->launches += 6;
-            ctx->path_counts[MPRG_PATH_KMER_GRID]++;
-        }
-        // The number of distinct k-mers F of a problem sizes its count matrix and KMeans scratch.  A level
-        // of small problems (a pangenome level: n <= 8, <= 241 positions) does not wait for it: it lays its
-        // matrices out for the upper bound F <= P (every k-mer position distinct) and the device passes the
-        // real F from the numbering kernel to the loop state; levels with a big problem fetch F first.
-        bool bounded = !getenv("MPRG_EXACT_F");
-        {
-            long long bound_elems = 0;
-            for (int q = 0; q < np && bounded; ++q) {
-                if (kp[q].big || (long long)probs[q].n * probs[q].P >= KMEANS_BIG_ELEMENTS) bounded = false;
-                bound_elems += (long long)probs[q].n * probs[q].P;
-            }
-            if (bound_elems > (16LL << 20)) bounded = false;  // 128 MB of doubles for the level
-        }
-        std::vector<int> h_F(np + 1, 0);
-        if (bounded) {
-            for (int q = 0; q < np; ++q) h_F[q] = (int)probs[q].P;
-        } else {
-            MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_F.data(), d_F, sizeof(int) * np, s));
-            MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &h_F[np], d_err, sizeof(int), s));
-            MPRG_CUDA(ctx, cudaStreamSynchronize(s));
-            if (h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
-        }
-        TRACE("cl: kmer setup+run+sync");
-
-        // ---- count matrices, sized exactly now that every F is known ----
-        long long max_P = 0;
-        for (int q = 0; q < np; ++q) {
-            kp[q].x_off = st[q].x_off = x_total;
-            x_total += (long long)probs[q].n * h_F[q];
-            if (kp[q].big && (size_t)h_F[q] * sizeof(int) <= 200 * 1024) kp[q].big |= 2;
-            if (!(kp[q].big & 2)) max_P = std::max(max_P, probs[q].P);
-        }
-        if (g_trace) {
-            long long big_n = 0, big_F = 0, big_P = 0;
-            for (int q = 0; q < np; ++q) {
-                big_n = std::max<long long>(big_n, probs[q].n);
-                big_F = std::max<long long>(big_F, h_F[q]);
-                big_P = std::max<long long>(big_P, probs[q].P);
-            }
-            fprintf(stderr, "[mprg trace] clustering level: %d problems, max n %lld, max F %lld, max positions %lld, X %.1f MB\n",
-                    np, big_n, big_F, big_P, 8e-6 * (double)x_total);
-        }
-        // ---- KMeans loop (cluster_sequences.py:256-274) ----
-        long long kmd_total = 0, kmi_total = 0;
-        for (int q = 0; q < np; ++q) {
-            st[q].F = h_F[q];
-            st[q].big = (long long)st[q].n * st[q].F >= KMEANS_BIG_ELEMENTS ? 1 : 0;
-            st[q].kmd_off = kmd_total;
-            st[q].kmi_off = kmi_total;
-            kmd_total += kmeans_dscratch_doubles(st[q].n, st[q].F);
-            kmi_total += kmeans_iscratch_ints(st[q].n);
-        }
-        const double want = 8.0 * (double)x_total + 8.0 * (double)kmd_total + 4.0 * (double)kmi_total;
-        if (want > 1e9) {  // cudaMemGetInfo is a slow, serialising driver call: only deep loci ask
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
-            const double have = (double)free_b + (double)B[12].cap + (double)B[15].cap;
-            if (want > 0.9 * have)
-                MPRG_FAIL(ctx, MPRG_E_BAD_ARG, "k-mer count matrices and KMeans scratch of this level do not fit in device memory");
-        }
-        MPRG_CUDA(ctx, B[12].reserve(sizeof(double) * std::max<long long>(x_total, 1)));
-        MPRG_CUDA(ctx, cudaMemsetAsync(B[12].p, 0, sizeof(double) * x_total, s));
-        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_kp, kp.data(), sizeof(KmerProb) * np, s));
-        MPRG_CUDA(ctx, launch_kmer_fill(s, d_kp, np, max_P, B[9].as<int>(), d_F, B[12].as<double>()));
-        ctx->launches++;
-        for (int q = 0; q < np; ++q)
-            if (kp[q].big & 2) {
-                MPRG_CUDA(ctx, launch_kmer_fill_big(s, d_kp, q, &kp[q], h_F[q], B[9].as<int>(), B[12].as<double>()));
-                ctx->launches++;
-            }
-        MPRG_CUDA(ctx, B[15].reserve(sizeof(double) * kmd_total + sizeof(int) * kmi_total + 64));
-        double *d_kmd = B[15].as<double>();
-        int *d_kmi = reinterpret_cast<int *>(d_kmd + kmd_total);
-        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_states, st.data(), sizeof(ClusterState) * np, s));
-        if (bounded) {
-            MPRG_CUDA(ctx, launch_set_features(s, d_states, d_F, np));
-            ctx->launches++;
-        }
-        MPRG_CUDA(ctx, cudaMemsetAsync(d_assign, 0, sizeof(int) * assign_total, s));
+        ProblemRun run;
+        rc = run_problems_host(ctx, s, hp, seq_rows, kmer_size, B[3].as<uint8_t>(), d_group, d_leadlen, d_leader_u, d_err,
+                               true, run);
+        if (rc != MPRG_OK) return rc;
+        st.swap(run.st);
+        h_assign.swap(run.h_assign);
         const int MAX_CLUSTERS = 10;
-        MPRG_CUDA(ctx, refcheck_all());
-        // every problem that ever runs KMeans runs it in the K == 2 round: centre its data once, now
-        MPRG_CUDA(ctx, launch_kmeans_prepare(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi));
-        ctx->launches++;
-        std::vector<int> big_q;  // deep loci: these problems get the whole GPU, one after the other
-        for (int q = 0; q < np; ++q)
-            if (st[q].big) big_q.push_back(q);
-        // A problem with n distinct sequences stops at K == n (cluster_sequences.py:257-259), so its last
-        // KMeans round is K = n - 1: the level needs rounds 2 .. max n - 1, not always 2 .. 10 (a deep level
-        // of a pangenome batch has max n = 3 or 4: one or two rounds instead of nine)
-        int max_n = 0;
-        long long max_elements = 0;
-        for (int q = 0; q < np; ++q) {
-            max_n = std::max(max_n, probs[q].n);
-            if (!st[q].big) max_elements = std::max(max_elements, (long long)st[q].n * st[q].F);
-        }
-        const int last_round = std::min(MAX_CLUSTERS, max_n - 1);
-        for (int round = 2; round <= last_round; ++round) {
-            for (int q : big_q) {
-                MPRG_CUDA(ctx, launch_kmeans_group(s, d_states, q, B[12].as<double>(), d_kmd, d_kmi, d_assign,
-                                                   d_newlab, d_bars, round == 2, ctx->sm_count));
-                ctx->launches += round == 2 ? 2 : 1;
-                ctx->path_counts[MPRG_PATH_KMEANS_GROUP]++;
-            }
-            refcheck_round = round;
-            ctx->path_counts[MPRG_PATH_KMEANS_CTA]++;
-            MPRG_CUDA(ctx, launch_kmeans(s, d_states, np, B[12].as<double>(), d_kmd, d_kmi, d_assign, d_newlab,
-                                         d_tickets, max_elements));
-            MPRG_CUDA(ctx, refcheck_all());
-            ctx->launches++;
-        }
-        h_assign.resize((size_t)assign_total);
-        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, st.data(), d_states, sizeof(ClusterState) * np, s));
-        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_assign.data(), d_assign, sizeof(int) * assign_total, s));
-        if (bounded) MPRG_CUDA(ctx, mprg::copy_d2h(ctx, &h_F[np], d_err, sizeof(int), s));
-        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
-        if (bounded && h_F[np]) MPRG_FAIL(ctx, MPRG_E_INTERNAL, "hash collision detected while numbering k-mers");
         TRACE("cl: kmeans loop+sync");
         for (int q = 0; q < np; ++q) {
             const Prob &p = probs[q];
@@ -934,28 +951,6 @@ extern "C" int mprg_one_ref_like(mprg_ctx *ctx, const mprg_batch *batch, const m
 // =================================================================================================
 namespace mprg {
 
-struct HNode {
-    int kind = -1;
-    int parent = -1;
-    int level = 0;
-    int c0 = 0, c1 = 0;
-    long long row_off = -1;  // into the locus row pool, -1 = all rows
-    int n_rows = 0;
-    // the children of a node are created one after the other: nodes [first_child, first_child + n_children)
-    int first_child = -1, n_children = 0;
-    int allele_first = -1, allele_count = 0;  // extract items of a leaf
-};
-
-struct LocusResult {
-    int status = MPRG_LOCUS_OK;
-    bool as_root = true;            // false: built below an existing node (mprg_build_sub)
-    std::vector<HNode> nodes;       // creation (level) order; node 0 is the root
-    std::vector<int> row_pool;
-    std::vector<int> preorder;      // node indices in pre-order == node_id order
-    std::string prg;
-    int n_sites = 0;
-};
-
 static const char *iupac_alternatives(char c) {
     switch (c) {
         case 'R': return "GA";
@@ -999,9 +994,143 @@ static bool expand_sequences(const std::vector<std::string> &seqs, std::vector<s
 
 }  // namespace mprg
 
-struct mprg_result {
-    std::vector<LocusResult> loci;
-};
+
+namespace mprg {
+static void assemble_prgs_range(const mprg_batch *batch, mprg_result *res, int l_begin, int lo, int hi,
+                                const long long *out_off, const int *h_len, const uint8_t *h_out,
+                                const long long *prg_bound) {
+    std::vector<std::string> raw, expanded;
+    struct Frame {
+        int node;
+        int next_child;
+        int site;
+    };
+    std::vector<Frame> stack;
+    for (int l = lo; l < hi; ++l) {
+        LocusResult &L = res->loci[l];
+        if (L.status != MPRG_LOCUS_OK) continue;
+        // upper bound of the string: gapped width of every allele + one marker per allele and node, so
+        // that a 200 MB PRG (deep locus) is not grown by doubling
+        L.prg.reserve((size_t)prg_bound[l - l_begin] + 12 * L.nodes.size() + 64);
+        int site = 5;
+        L.preorder.reserve(L.nodes.size());
+        stack.clear();
+        stack.push_back(Frame{0, 0, 0});
+        auto emit_marker = [&](int m) {
+            char buf[16];
+            int k = 15;
+            buf[k] = ' ';
+            do {
+                buf[--k] = (char)('0' + m % 10);
+                m /= 10;
+            } while (m);
+            buf[--k] = ' ';
+            L.prg.append(buf + k, (size_t)(16 - k));
+        };
+        while (!stack.empty() && L.status == MPRG_LOCUS_OK) {
+            Frame &f = stack.back();
+            HNode &nd = L.nodes[f.node];
+            if (f.next_child == 0) {
+                L.preorder.push_back(f.node);
+                if (nd.kind == MPRG_NODE_LEAF && !(batch->flags[l] & 4)) {
+                    // no RYKMSW anywhere in the locus: the distinct ungapped rows are the alleles
+                    if (nd.allele_count == 1) {
+                        const long long it_off = out_off[nd.allele_first];
+                        L.prg.append(reinterpret_cast<const char *>(h_out + it_off), (size_t)h_len[nd.allele_first]);
+                    } else {
+                        const int sn = site;
+                        site += 2;
+                        emit_marker(sn);
+                        for (int a = 0; a < nd.allele_count; ++a) {
+                            const long long it_off = out_off[nd.allele_first + a];
+                            L.prg.append(reinterpret_cast<const char *>(h_out + it_off),
+                                         (size_t)h_len[nd.allele_first + a]);
+                            emit_marker(a + 1 < nd.allele_count ? sn + 1 : sn);
+                        }
+                    }
+                    stack.pop_back();
+                    continue;
+                }
+                if (nd.kind == MPRG_NODE_LEAF) {
+                    raw.clear();
+                    for (int a = 0; a < nd.allele_count; ++a) {
+                        const long long it_off = out_off[nd.allele_first + a];
+                        raw.emplace_back(reinterpret_cast<const char *>(h_out + it_off),
+                                         (size_t)h_len[nd.allele_first + a]);
+                    }
+                    if (!expand_sequences(raw, expanded)) {
+                        L.status = MPRG_LOCUS_CURATION_ERROR;
+                        break;
+                    }
+                    if (expanded.size() == 1) {
+                        L.prg += expanded[0];
+                    } else {
+                        const int sn = site;
+                        site += 2;
+                        emit_marker(sn);
+                        for (size_t a = 0; a < expanded.size(); ++a) {
+                            L.prg += expanded[a];
+                            emit_marker(a + 1 < expanded.size() ? sn + 1 : sn);
+                        }
+                    }
+                    stack.pop_back();
+                    continue;
+                }
+                if (nd.kind == MPRG_NODE_CLUSTER) {
+                    f.site = site;
+                    site += 2;
+                    emit_marker(f.site);
+                }
+            } else if (nd.kind == MPRG_NODE_CLUSTER) {
+                // separator after child (next_child - 1)
+                emit_marker(f.next_child < nd.n_children ? f.site + 1 : f.site);
+            }
+            if (f.next_child < nd.n_children) {
+                const int ch = nd.first_child + f.next_child;
+                f.next_child++;
+                stack.push_back(Frame{ch, 0, 0});
+            } else {
+                stack.pop_back();
+            }
+        }
+        L.n_sites = (site - 5) / 2;
+        if (L.status != MPRG_LOCUS_OK) {
+            L.prg.clear();
+            L.preorder.clear();
+        }
+    }
+}
+
+void assemble_prgs(const mprg_batch *batch, mprg_result *res, int l_begin, int l_end, const long long *out_off,
+                   const int *h_len, const uint8_t *h_out, const long long *prg_bound, int n_threads) {
+    const int n = l_end - l_begin;
+    n_threads = std::max(1, std::min(n_threads, n / 16));
+    if (n_threads <= 1) {
+        assemble_prgs_range(batch, res, l_begin, l_begin, l_end, out_off, h_len, h_out, prg_bound);
+        return;
+    }
+    // contiguous ranges of about equal output size
+    std::vector<long long> prefix((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i) prefix[i + 1] = prefix[i] + prg_bound[i] + 64;
+    std::vector<std::thread> threads;
+    int lo = l_begin;
+    for (int t = 0; t < n_threads; ++t) {
+        int hi = l_end;
+        if (t + 1 < n_threads) {
+            const long long target = prefix[n] * (t + 1) / n_threads;
+            hi = l_begin + (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
+            hi = std::max(lo, std::min(hi, l_end));
+        }
+        if (t + 1 == n_threads) {
+            assemble_prgs_range(batch, res, l_begin, lo, hi, out_off, h_len, h_out, prg_bound);
+        } else {
+            threads.emplace_back(assemble_prgs_range, batch, res, l_begin, lo, hi, out_off, h_len, h_out, prg_bound);
+        }
+        lo = hi;
+    }
+    for (auto &t : threads) t.join();
+}
+}  // namespace mprg
 
 // Builds loci [l_begin, l_end) of the batch on one context (one stream, one host thread).
 // root_levels (may be null): per locus -1 = the alignment is a locus root (from_msa), >= 0 = it is built
@@ -1270,106 +1399,10 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
     }
 
     TRACE("build: allele extraction");
-    // ---- pre-order numbering and PRG strings (recursion_tree.py:194-300, prg_builder.py:100-110) ----
-    std::vector<std::string> raw, expanded;
-    struct Frame {
-        int node;
-        int next_child;
-        int site;
-    };
-    std::vector<Frame> stack;
-    for (int l = l_begin; l < l_end; ++l) {
-        LocusResult &L = res->loci[l];
-        if (L.status != MPRG_LOCUS_OK) continue;
-        // upper bound of the string: gapped width of every allele + one marker per allele and node, so
-        // that a 200 MB PRG (deep locus) is not grown by doubling
-        L.prg.reserve((size_t)prg_bound[l - l_begin] + 12 * L.nodes.size() + 64);
-        int site = 5;
-        L.preorder.reserve(L.nodes.size());
-        stack.clear();
-        stack.push_back(Frame{0, 0, 0});
-        auto emit_marker = [&](int m) {
-            char buf[16];
-            int k = 15;
-            buf[k] = ' ';
-            do {
-                buf[--k] = (char)('0' + m % 10);
-                m /= 10;
-            } while (m);
-            buf[--k] = ' ';
-            L.prg.append(buf + k, (size_t)(16 - k));
-        };
-        while (!stack.empty() && L.status == MPRG_LOCUS_OK) {
-            Frame &f = stack.back();
-            HNode &nd = L.nodes[f.node];
-            if (f.next_child == 0) {
-                L.preorder.push_back(f.node);
-                if (nd.kind == MPRG_NODE_LEAF && !(batch->flags[l] & 4)) {
-                    // no RYKMSW anywhere in the locus: the distinct ungapped rows are the alleles
-                    if (nd.allele_count == 1) {
-                        const ExtractItem &it = items[nd.allele_first];
-                        L.prg.append(reinterpret_cast<const char *>(h_out + it.out_off), (size_t)h_len[nd.allele_first]);
-                    } else {
-                        const int sn = site;
-                        site += 2;
-                        emit_marker(sn);
-                        for (int a = 0; a < nd.allele_count; ++a) {
-                            const ExtractItem &it = items[nd.allele_first + a];
-                            L.prg.append(reinterpret_cast<const char *>(h_out + it.out_off),
-                                         (size_t)h_len[nd.allele_first + a]);
-                            emit_marker(a + 1 < nd.allele_count ? sn + 1 : sn);
-                        }
-                    }
-                    stack.pop_back();
-                    continue;
-                }
-                if (nd.kind == MPRG_NODE_LEAF) {
-                    raw.clear();
-                    for (int a = 0; a < nd.allele_count; ++a) {
-                        const ExtractItem &it = items[nd.allele_first + a];
-                        raw.emplace_back(reinterpret_cast<const char *>(h_out + it.out_off),
-                                         (size_t)h_len[nd.allele_first + a]);
-                    }
-                    if (!expand_sequences(raw, expanded)) {
-                        L.status = MPRG_LOCUS_CURATION_ERROR;
-                        break;
-                    }
-                    if (expanded.size() == 1) {
-                        L.prg += expanded[0];
-                    } else {
-                        const int sn = site;
-                        site += 2;
-                        emit_marker(sn);
-                        for (size_t a = 0; a < expanded.size(); ++a) {
-                            L.prg += expanded[a];
-                            emit_marker(a + 1 < expanded.size() ? sn + 1 : sn);
-                        }
-                    }
-                    stack.pop_back();
-                    continue;
-                }
-                if (nd.kind == MPRG_NODE_CLUSTER) {
-                    f.site = site;
-                    site += 2;
-                    emit_marker(f.site);
-                }
-            } else if (nd.kind == MPRG_NODE_CLUSTER) {
-                // separator after child (next_child - 1)
-                emit_marker(f.next_child < nd.n_children ? f.site + 1 : f.site);
-            }
-            if (f.next_child < nd.n_children) {
-                const int ch = nd.first_child + f.next_child;
-                f.next_child++;
-                stack.push_back(Frame{ch, 0, 0});
-            } else {
-                stack.pop_back();
-            }
-        }
-        L.n_sites = (site - 5) / 2;
-        if (L.status != MPRG_LOCUS_OK) {
-            L.prg.clear();
-            L.preorder.clear();
-        }
+    {
+        std::vector<long long> off(std::max(na, 1));
+        for (int a = 0; a < na; ++a) off[a] = items[a].out_off;
+        assemble_prgs(batch, res, l_begin, l_end, off.data(), h_len, h_out, prg_bound.data(), 1);
     }
     TRACE("build: prg strings");
     if (allow_trace || trace_all) {
@@ -1415,11 +1448,27 @@ static int build_ranges(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, i
             if (r != MPRG_OK) return r;
             if (trace_all) fprintf(stderr, "[mprg trace] range %d..%d: upload %.2f -> %.2f ms after the call\n", l0, l1, t0, since_call());
         }
-        const int rc_b = build_range(c, batch, l0, l1, max_nesting, min_match_length, res, trace, root_levels);
+        // the device-resident level loop is the product path; MPRG_HOST_LOOP=1 keeps the host-driven one
+        // (the checked alternative: both must produce identical results)
+        static const bool host_loop = getenv("MPRG_HOST_LOOP") != nullptr;
+        const int rc_b = host_loop
+                             ? build_range(c, batch, l0, l1, max_nesting, min_match_length, res, trace, root_levels)
+                             : build_range_dev(c, batch, l0, l1, max_nesting, min_match_length, res, trace, root_levels);
         if (trace_all) fprintf(stderr, "[mprg trace] range %d..%d: built %.2f ms after the call\n", l0, l1, since_call());
         return rc_b;
     };
     int W = std::max(1, std::min(ctx->n_workers, n_loci / 8));
+    {
+        // The device-resident loop needs no host threads to hide bookkeeping: one range per build when the
+        // batch is resident, two from host buffers (the upload of one overlaps the kernels of the other).
+        // MPRG_DEV_RANGES overrides.
+        static const bool host_loop = getenv("MPRG_HOST_LOOP") != nullptr;
+        static const int dev_ranges = []() {
+            const char *e = getenv("MPRG_DEV_RANGES");
+            return e ? std::max(1, atoi(e)) : 0;
+        }();
+        if (!host_loop) W = std::min(W, dev_ranges ? dev_ranges : (h_ascii ? 2 : 1));
+    }
     if (W <= 1) {
         rc = run(ctx, 0, n_loci, true);
         if (rc != MPRG_OK) {

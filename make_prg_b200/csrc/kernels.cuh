@@ -1,6 +1,7 @@
 // Launchers of the device kernels (definitions in scan.cu, partition.cu, cluster.cu, kmeans.cu).
 #pragma once
 #include "common.cuh"
+#include "km_layout.cuh"
 
 namespace mprg {
 

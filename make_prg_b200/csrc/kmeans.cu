@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #endif
+#include "km_layout.cuh"
 
 namespace mprg {
 // the device functions of the two compilations of this file (single-CTA, CTA-group) must not collide
@@ -30,8 +31,6 @@ namespace mprg {
 namespace KM_NS {
 
 constexpr int KM_THREADS = 128;
-constexpr int KM_MAXK = 10;
-constexpr int KM_NINIT = 10;
 constexpr int KM_MAXITER = 300;
 
 #ifdef MPRG_KM_GROUP
@@ -688,12 +687,7 @@ __device__ void kmeans_single(KM &k, int &rand_pos, double tol, double *s_scalar
 // tolerance: written once by kmeans_prepare, read-only afterwards, for every K the clustering loop
 // tries), then KM_NINIT per-initialisation blocks (so the initialisations can run in different CTAs),
 // then the selection block.
-__device__ __host__ inline long long km_shared_doubles(long long n, long long F) { return n * F + 2 * F + n + 8; }
-__device__ __host__ inline long long km_init_doubles(long long n, long long F) {
-    return 2LL * KM_MAXK * F + n * KM_MAXK + 3 * n + 4 * n + n + KM_MAXK * KM_MAXK + 4 * KM_MAXK +
-           8;  // + [inertia, final-centres selector] in the last 8
-}
-__device__ __host__ inline long long km_init_ints(long long n) { return 2 * n + 8; }
+// (km_shared_doubles / km_init_doubles / km_init_ints: kernels.cuh, shared with the device-side problem builder)
 
 // d0 = scratch of the problem, init = which initialisation block to bind
 __device__ void km_bind_init(KM &k, int n, int F, int K, const double *X0, double *d0, int *i0, int init) {
@@ -831,10 +825,8 @@ using namespace KM_NS;
 #ifndef MPRG_KM_GROUP
 // scratch per problem: shared block | KM_NINIT init blocks | best_c [KM_MAXK * F] | cc [KM_MAXK] ;
 // ints: KM_NINIT init blocks
-long long kmeans_dscratch_doubles(long long n, long long F) {
-    return km_shared_doubles(n, F) + KM_NINIT * km_init_doubles(n, F) + KM_MAXK * F + KM_MAXK + 8;
-}
-long long kmeans_iscratch_ints(long long n) { return KM_NINIT * km_init_ints(n) + 8; }
+long long kmeans_dscratch_doubles(long long n, long long F) { return km_dscratch_doubles(n, F); }
+long long kmeans_iscratch_ints(long long n) { return km_iscratch_ints(n); }
 #endif
 
 #if !defined(MPRG_HOST_EMU) && !defined(MPRG_KM_GROUP)
