@@ -1596,6 +1596,121 @@ extern "C" int mprg_result_from_prgs(const char *const *prgs, const int64_t *len
     return MPRG_OK;
 }
 
+// ---- pinned blocks recycled across results -----------------------------------------------------------
+namespace mprg {
+static std::mutex g_pin_mutex;
+static std::vector<PinnedBlock> g_pin_free;
+
+PinnedBlock pinned_acquire(size_t bytes) {
+    bytes = std::max<size_t>(bytes, 64);
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mutex);
+        int best = -1;
+        for (int i = 0; i < (int)g_pin_free.size(); ++i)
+            if (g_pin_free[i].cap >= bytes && (best < 0 || g_pin_free[i].cap < g_pin_free[best].cap)) best = i;
+        if (best >= 0 && g_pin_free[best].cap <= 4 * bytes + ((size_t)1 << 20)) {
+            PinnedBlock b = g_pin_free[best];
+            g_pin_free.erase(g_pin_free.begin() + best);
+            return b;
+        }
+    }
+    PinnedBlock b;
+    const size_t want = bytes + bytes / 4 + 4096;
+    if (cudaMallocHost(&b.p, want) == cudaSuccess) b.cap = want;
+    else b.p = nullptr;
+    return b;
+}
+
+void pinned_release(PinnedBlock b) {
+    if (!b.p) return;
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mutex);
+        size_t held = 0;
+        for (const PinnedBlock &f : g_pin_free) held += f.cap;
+        if (g_pin_free.size() < 24 && held + b.cap <= ((size_t)4 << 30)) {
+            g_pin_free.push_back(b);
+            return;
+        }
+    }
+    cudaFreeHost(b.p);
+}
+
+void ensure_tables(mprg_result *res, int l) {
+    LocusResult &L = res->loci[l];
+    if (L.tables_ready) return;
+    std::lock_guard<std::mutex> lock(res->lazy_mutex);
+    if (L.tables_ready) return;
+    const RawTree &raw = res->raw[L.raw_index];
+    const DNode *nodes = static_cast<const DNode *>(raw.nodes.p);
+    const int *pool = static_cast<const int *>(raw.pool.p);
+    std::vector<int> order;  // raw node indices in local order: children of a node contiguous
+    order.push_back(L.raw_root);
+    L.nodes.clear();
+    L.row_pool.clear();
+    for (size_t k = 0; k < order.size(); ++k) {
+        const DNode &g = nodes[order[k]];
+        HNode h;
+        h.kind = g.kind;
+        h.parent = -1;
+        h.level = g.level;
+        h.c0 = g.c0;
+        h.c1 = g.c1;
+        h.row_off = -1;
+        h.n_rows = g.n_rows;
+        h.first_child = g.n_children ? (int)order.size() : -1;
+        h.n_children = g.n_children;
+        h.allele_first = g.allele_first;
+        h.allele_count = g.allele_count;
+        L.nodes.push_back(h);
+        for (int c = 0; c < g.n_children; ++c) order.push_back(g.first_child + c);
+    }
+    // parents and row subsets: interval children share their parent's rows, cluster children own theirs
+    for (size_t k = 0; k < order.size(); ++k) {
+        HNode &h = L.nodes[k];
+        const DNode &g = nodes[order[k]];
+        for (int c = 0; c < h.n_children; ++c) {
+            HNode &ch = L.nodes[h.first_child + c];
+            const DNode &gc = nodes[g.first_child + c];
+            ch.parent = (int)k;
+            if (gc.row_off < 0) {
+                ch.row_off = -1;
+            } else if (gc.row_off == g.row_off) {
+                ch.row_off = h.row_off;
+            } else {
+                ch.row_off = (long long)L.row_pool.size();
+                L.row_pool.insert(L.row_pool.end(), pool + gc.row_off, pool + gc.row_off + gc.n_rows);
+            }
+        }
+    }
+    // pre-order == node_id order
+    L.preorder.clear();
+    L.preorder.reserve(L.nodes.size());
+    std::vector<std::pair<int, int>> stack;
+    stack.emplace_back(0, 0);
+    L.preorder.push_back(0);
+    while (!stack.empty()) {
+        auto &f = stack.back();
+        const HNode &nd = L.nodes[f.first];
+        if (f.second < nd.n_children) {
+            const int ch = nd.first_child + f.second++;
+            L.preorder.push_back(ch);
+            stack.emplace_back(ch, 0);
+        } else {
+            stack.pop_back();
+        }
+    }
+    L.tables_ready = true;
+}
+}  // namespace mprg
+
+mprg_result::~mprg_result() {
+    for (mprg::RawTree &r : raw) {
+        mprg::pinned_release(r.nodes);
+        mprg::pinned_release(r.pool);
+    }
+    for (mprg::PinnedBlock &b : blobs) mprg::pinned_release(b);
+}
+
 extern "C" void mprg_result_free(mprg_result *res) { delete res; }
 extern "C" int32_t mprg_result_n_loci(const mprg_result *res) { return res ? (int32_t)res->loci.size() : 0; }
 extern "C" int32_t mprg_result_status(const mprg_result *res, int32_t l) {
@@ -1605,17 +1720,25 @@ extern "C" int mprg_result_statuses(const mprg_result *res, int32_t *h_status, i
     if (!res) return MPRG_E_BAD_ARG;
     for (size_t l = 0; l < res->loci.size(); ++l) {
         if (h_status) h_status[l] = res->loci[l].status;
-        if (h_prg_length) h_prg_length[l] = (int64_t)res->loci[l].prg.size();
+        if (h_prg_length)
+            h_prg_length[l] = res->loci[l].prg_data ? (int64_t)res->loci[l].prg_size : (int64_t)res->loci[l].prg.size();
     }
     return MPRG_OK;
 }
 extern "C" const char *mprg_result_prg(const mprg_result *res, int32_t l, int64_t *length) {
     if (!res || l < 0 || l >= (int)res->loci.size()) return nullptr;
-    if (length) *length = (int64_t)res->loci[l].prg.size();
-    return res->loci[l].prg.data();
+    const LocusResult &L = res->loci[l];
+    if (L.prg_data) {
+        if (length) *length = (int64_t)L.prg_size;
+        return L.prg_data;
+    }
+    if (length) *length = (int64_t)L.prg.size();
+    return L.prg.data();
 }
 extern "C" int32_t mprg_result_n_nodes(const mprg_result *res, int32_t l) {
-    return (res && l >= 0 && l < (int)res->loci.size()) ? (int32_t)res->loci[l].preorder.size() : 0;
+    if (!res || l < 0 || l >= (int)res->loci.size()) return 0;
+    const LocusResult &L = res->loci[l];
+    return L.n_nodes >= 0 ? L.n_nodes : (int32_t)L.preorder.size();
 }
 extern "C" int32_t mprg_result_n_sites(const mprg_result *res, int32_t l) {
     return (res && l >= 0 && l < (int)res->loci.size()) ? res->loci[l].n_sites : 0;
@@ -1624,6 +1747,7 @@ extern "C" int mprg_result_nodes(const mprg_result *res, int32_t l, int32_t *kin
                                  int32_t *nesting_level, int32_t *c0, int32_t *c1, int32_t *n_rows,
                                  int64_t *row_off, int32_t *n_children) {
     if (!res || l < 0 || l >= (int)res->loci.size()) return MPRG_E_BAD_ARG;
+    ensure_tables(const_cast<mprg_result *>(res), l);
     const LocusResult &L = res->loci[l];
     std::vector<int> new_id(L.nodes.size(), -1);
     for (size_t i = 0; i < L.preorder.size(); ++i) new_id[L.preorder[i]] = (int)i;
@@ -1641,10 +1765,13 @@ extern "C" int mprg_result_nodes(const mprg_result *res, int32_t l, int32_t *kin
     return MPRG_OK;
 }
 extern "C" int64_t mprg_result_row_pool_size(const mprg_result *res, int32_t l) {
-    return (res && l >= 0 && l < (int)res->loci.size()) ? (int64_t)res->loci[l].row_pool.size() : 0;
+    if (!res || l < 0 || l >= (int)res->loci.size()) return 0;
+    ensure_tables(const_cast<mprg_result *>(res), l);
+    return (int64_t)res->loci[l].row_pool.size();
 }
 extern "C" int mprg_result_row_pool(const mprg_result *res, int32_t l, int32_t *h_rows) {
     if (!res || l < 0 || l >= (int)res->loci.size() || !h_rows) return MPRG_E_BAD_ARG;
+    ensure_tables(const_cast<mprg_result *>(res), l);
     const LocusResult &L = res->loci[l];
     if (!L.row_pool.empty()) memcpy(h_rows, L.row_pool.data(), sizeof(int) * L.row_pool.size());
     return MPRG_OK;

@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,37 @@ struct LocusResult {
     std::vector<int> preorder;      // node indices in pre-order == node_id order
     std::string prg;
     int n_sites = 0;
+    // device-assembled results: the PRG lies in a blob of the result, the node table is made from the raw
+    // device tree (mprg_result::raw[raw_index]) the first time it is asked for
+    const char *prg_data = nullptr;
+    long long prg_size = 0;
+    int n_nodes = -1;
+    int raw_index = -1, raw_root = -1;
+    bool tables_ready = true;
+};
+
+// node and locus records of the device-resident loop (engine_dev.cu)
+struct DNode {
+    int locus, parent, level, kind;
+    int c0, c1;
+    long long row_off;  // into the device row pool, -1 = all rows of the locus
+    int n_rows, first_child, n_children, allele_first, allele_count, pad;
+};
+
+// pinned host memory recycled across results (cudaMallocHost / cudaFreeHost cost milliseconds)
+struct PinnedBlock {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+PinnedBlock pinned_acquire(size_t bytes);
+void pinned_release(PinnedBlock b);
+
+// what one range of the device-resident loop brought back: node table and row pool as the device made them
+struct RawTree {
+    int l_begin = 0, l_end = 0;
+    PinnedBlock nodes, pool;
+    int n_nodes = 0;
+    long long pool_size = 0;
 };
 
 // one allele of a leaf: ungapped symbols of (row, [c0, c1)) of a locus, written at out_off
@@ -76,6 +108,10 @@ cudaError_t launch_extract(cudaStream_t s, const uint8_t *packed, const ExtractI
 
 struct mprg_result {
     std::vector<mprg::LocusResult> loci;
+    std::vector<mprg::RawTree> raw;          // one per range of the device-resident loop
+    std::vector<mprg::PinnedBlock> blobs;    // PRG strings assembled on the device
+    std::mutex lazy_mutex, raw_mutex;
+    ~mprg_result();
 };
 
 namespace mprg {
@@ -84,6 +120,8 @@ namespace mprg {
 // n_threads > 1 spreads the loci over host threads.
 void assemble_prgs(const mprg_batch *batch, mprg_result *res, int l_begin, int l_end, const long long *out_off,
                    const int *h_len, const uint8_t *h_out, const long long *prg_bound, int n_threads);
+// node table, row pool and pre-order of one locus from the raw device tree (first use)
+void ensure_tables(mprg_result *res, int l);
 int ensure_rand(mprg_ctx *ctx);
 // one clustering problem as the host-driven clustering loop takes it: the n distinct long sequences of
 // cluster task `task` (w columns, R rows, n_groups distinct ungapped sequences), P k-mer positions

@@ -29,13 +29,6 @@ struct DLocus {
     int status;
 };
 
-struct DNode {
-    int locus, parent, level, kind;
-    int c0, c1;
-    long long row_off;  // into the device row pool, -1 = all rows of the locus
-    int n_rows, first_child, n_children, allele_first, allele_count, pad;
-};
-
 struct DevCounters {
     // whole build
     int n_nodes, n_alleles;
@@ -661,6 +654,161 @@ expand_clusters_kernel(DevCounters *C, ClusterTaskArrays ct, ProblemArrays pa, c
     }
 }
 
+// ---- PRG strings on the device (recursion_tree.py:194-300, prg_builder.py:100-110) -------------------------
+// Loci without RYKMSW: the distinct ungapped rows of a leaf are its alleles, so the PRG of a locus is the
+// pre-order concatenation of allele strings and site markers.  allele_len: ungapped length of every allele;
+// prg_measure: length / sites / nodes per locus (one thread per locus walks its tree); a prefix sum gives the
+// position of every locus in the blob; prg_write walks the tree again, writes the markers and tells every
+// allele where it goes; the extraction kernel then cuts the alleles straight into the blob.
+struct PrgInfo {
+    long long off, len;
+    int n_sites, n_nodes, status, pad;
+};
+
+__global__ void __launch_bounds__(128)
+allele_len_kernel(const uint8_t *__restrict__ packed, const ExtractItem *__restrict__ items, int n_items,
+                  int *__restrict__ len_out) {
+    const int lane = threadIdx.x & 31;
+    const int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (it >= n_items) return;
+    const ExtractItem e = items[it];
+    const uint8_t *row = packed + e.base + (long long)e.row * e.stride;
+    int len = 0;
+    for (int c0 = e.c0; c0 < e.c1; c0 += 32) {
+        const int c = c0 + lane;
+        const bool solid = c < e.c1 && packed_sym(row, c) != SYM_GAP;
+        len += __popc(__ballot_sync(0xffffffffu, solid));
+    }
+    if (lane == 0) len_out[it] = len;
+}
+
+__device__ __forceinline__ int marker_len(int m) {
+    int d = 1;
+    while (m >= 10) {
+        m /= 10;
+        ++d;
+    }
+    return d + 2;
+}
+__device__ __forceinline__ void marker_put(char *dst, int m) {
+    const int n = marker_len(m);
+    dst[0] = ' ';
+    dst[n - 1] = ' ';
+    for (int k = n - 2; k >= 1; --k) {
+        dst[k] = (char)('0' + m % 10);
+        m /= 10;
+    }
+}
+
+constexpr int PRG_STACK = 64;  // nesting depth of the tree: at most 2 * max_nesting + 2 in practice
+
+// WRITE == false: measure; WRITE == true: markers into the blob, items[a].out_off = where allele a goes
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+prg_walk_kernel(const DNode *__restrict__ nodes, const DLocus *__restrict__ loci, int nl,
+                const int *__restrict__ allele_len, PrgInfo *__restrict__ info, ExtractItem *__restrict__ items,
+                char *__restrict__ blob, int *__restrict__ err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nl) return;
+    if (loci[i].status != MPRG_LOCUS_OK) {
+        if (!WRITE) info[i] = PrgInfo{0, 0, 0, 0, loci[i].status, 0};
+        return;
+    }
+    int st_node[PRG_STACK], st_next[PRG_STACK], st_site[PRG_STACK];
+    int depth = 0;
+    st_node[0] = i;  // the root of locus i is node i
+    st_next[0] = 0;
+    st_site[0] = 0;
+    long long at = WRITE ? info[i].off : 0;
+    int site = 5, n_nodes = 0;
+    while (depth >= 0) {
+        const int ni = st_node[depth];
+        const DNode nd = nodes[ni];
+        if (st_next[depth] == 0) {
+            ++n_nodes;
+            if (nd.kind == MPRG_NODE_LEAF) {
+                if (nd.allele_count == 1) {
+                    if (WRITE) items[nd.allele_first].out_off = at;
+                    at += allele_len[nd.allele_first];
+                } else {
+                    const int sn = site;
+                    site += 2;
+                    if (WRITE) marker_put(blob + at, sn);
+                    at += marker_len(sn);
+                    for (int a = 0; a < nd.allele_count; ++a) {
+                        if (WRITE) items[nd.allele_first + a].out_off = at;
+                        at += allele_len[nd.allele_first + a];
+                        const int m = a + 1 < nd.allele_count ? sn + 1 : sn;
+                        if (WRITE) marker_put(blob + at, m);
+                        at += marker_len(m);
+                    }
+                }
+                --depth;
+                continue;
+            }
+            if (nd.kind == MPRG_NODE_CLUSTER) {
+                st_site[depth] = site;
+                site += 2;
+                if (WRITE) marker_put(blob + at, st_site[depth]);
+                at += marker_len(st_site[depth]);
+            }
+        } else if (nd.kind == MPRG_NODE_CLUSTER) {
+            const int m = st_next[depth] < nd.n_children ? st_site[depth] + 1 : st_site[depth];  // after a child
+            if (WRITE) marker_put(blob + at, m);
+            at += marker_len(m);
+        }
+        if (st_next[depth] < nd.n_children) {
+            const int ch = nd.first_child + st_next[depth];
+            st_next[depth]++;
+            if (depth + 1 >= PRG_STACK) {
+                atomicOr(err, ERR_OVERFLOW);
+                return;
+            }
+            ++depth;
+            st_node[depth] = ch;
+            st_next[depth] = 0;
+            st_site[depth] = 0;
+        } else {
+            --depth;
+        }
+    }
+    if (!WRITE) info[i] = PrgInfo{0, at, (site - 5) / 2, n_nodes, MPRG_LOCUS_OK, 0};
+}
+
+// exclusive prefix sum of the PRG lengths (single CTA); total -> *total_out
+__global__ void __launch_bounds__(1024) prg_offsets_kernel(PrgInfo *__restrict__ info, int nl, long long *total_out) {
+    __shared__ long long s_warp[33];
+    __shared__ long long carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nl; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const long long v = i < nl ? info[i].len : 0;
+        long long x = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += o;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            long long y = lane < nw ? s_warp[lane] : 0;
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long o = __shfl_up_sync(0xffffffffu, y, d);
+                if (lane >= d) y += o;
+            }
+            s_warp[lane] = y;
+        }
+        __syncthreads();
+        if (i < nl) info[i].off = carry + (warp ? s_warp[warp - 1] : 0) + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += s_warp[nw - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
 // ---- growable device buffers that keep their contents -----------------------------------------------------
 static cudaError_t reserve_keep(DevBuf &b, size_t bytes, size_t used, cudaStream_t s) {
     if (bytes <= b.cap) return cudaSuccess;
@@ -683,7 +831,7 @@ static cudaError_t reserve_keep(DevBuf &b, size_t bytes, size_t used, cudaStream
 // buffers of the device-resident loop (ctx->d_dev)
 enum {
     V_COUNTERS = 0, V_LOCI, V_NODES, V_POOL, V_ITEMS, V_PEND_A, V_PEND_B, V_CT_TASKS, V_CT_MISC, V_G, V_SIG, V_ROWINTS,
-    V_PROBS, V_PROB_MISC, V_SCRATCH, V_USEQ, V_INTS, V_KEYS, V_MING, V_X, V_STATE_MISC, V_B14, V_KM, V_OUT, V_OUTLEN, V_UNIT_OFF,
+    V_PROBS, V_PROB_MISC, V_SCRATCH, V_USEQ, V_INTS, V_KEYS, V_MING, V_X, V_STATE_MISC, V_B14, V_KM, V_OUT, V_OUTLEN, V_UNIT_OFF, V_PRGINFO,
     V_COUNT
 };
 
@@ -1066,6 +1214,88 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
     }
     const int n_nodes = cnt->n_nodes, na = cnt->n_alleles;
     const long long pool_size = cnt->pool_size, out_total = cnt->allele_bytes;
+    bool expansion = getenv("MPRG_HOST_ASSEMBLY") != nullptr;  // RYKMSW: the cartesian product is made on the host
+    for (int i = 0; i < nl && !expansion; ++i) expansion = h_loci[i].status == MPRG_LOCUS_OK && (h_loci[i].flags & 4);
+    if (!expansion) {
+        // ---- PRG strings assembled on the device: only the strings and the raw tree cross PCIe ----
+        MPRG_CUDA(ctx, V[V_OUTLEN].reserve(sizeof(int) * (size_t)std::max(na, 1)));
+        MPRG_CUDA(ctx, V[V_PRGINFO].reserve(sizeof(PrgInfo) * (size_t)nl + 64));
+        PrgInfo *d_info = V[V_PRGINFO].as<PrgInfo>();
+        long long *d_total = reinterpret_cast<long long *>(d_info + nl);
+        int *d_len = V[V_OUTLEN].as<int>();
+        ExtractItem *d_items = V[V_ITEMS].as<ExtractItem>();
+        int *d_errflag = &d_cnt->err;
+        if (na > 0) allele_len_kernel<<<(na + 3) / 4, 128, 0, s>>>(batch->d_packed, d_items, na, d_len);
+        prg_walk_kernel<false><<<(nl + 127) / 128, 128, 0, s>>>(V[V_NODES].as<DNode>(), d_loci, nl, d_len, d_info, d_items,
+                                                               nullptr, d_errflag);
+        prg_offsets_kernel<<<1, 1024, 0, s>>>(d_info, nl, d_total);
+        ctx->launches += 3;
+        MPRG_CUDA(ctx, cudaGetLastError());
+        // the raw tree travels while the strings are being laid out
+        RawTree raw;
+        raw.l_begin = l_begin;
+        raw.l_end = l_end;
+        raw.n_nodes = n_nodes;
+        raw.pool_size = pool_size;
+        raw.nodes = pinned_acquire(sizeof(DNode) * (size_t)std::max(n_nodes, 1));
+        raw.pool = pinned_acquire(sizeof(int) * (size_t)std::max<long long>(pool_size, 1));
+        MPRG_CUDA(ctx, ctx->h_d.reserve(sizeof(PrgInfo) * (size_t)nl + 64));
+        PrgInfo *h_info = ctx->h_d.as<PrgInfo>();
+        long long *h_total = reinterpret_cast<long long *>(h_info + nl);
+        if (!raw.nodes.p || !raw.pool.p) MPRG_FAIL(ctx, MPRG_E_CUDA, "pinned allocation for the result failed");
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_total, d_total, sizeof(long long), s));
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, raw.nodes.p, V[V_NODES].p, sizeof(DNode) * (size_t)n_nodes, s));
+        if (pool_size > 0) MPRG_CUDA(ctx, mprg::copy_d2h(ctx, raw.pool.p, V[V_POOL].p, sizeof(int) * (size_t)pool_size, s));
+        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        const long long blob_bytes = *h_total;
+        TRACE("dev: measure + raw tree D2H");
+        PinnedBlock blob = pinned_acquire((size_t)std::max<long long>(blob_bytes, 1));
+        if (!blob.p) MPRG_FAIL(ctx, MPRG_E_CUDA, "pinned allocation for the result failed");
+        MPRG_CUDA(ctx, V[V_OUT].reserve((size_t)std::max<long long>(blob_bytes, 1)));
+        prg_walk_kernel<true><<<(nl + 127) / 128, 128, 0, s>>>(V[V_NODES].as<DNode>(), d_loci, nl, d_len, d_info, d_items,
+                                                              V[V_OUT].as<char>(), d_errflag);
+        if (na > 0)
+            MPRG_CUDA(ctx, launch_extract(s, batch->d_packed, d_items, na, V[V_OUT].as<uint8_t>(), d_len));
+        ctx->launches += 2;
+        MPRG_CUDA(ctx, cudaGetLastError());
+        if (blob_bytes > 0) MPRG_CUDA(ctx, mprg::copy_d2h(ctx, blob.p, V[V_OUT].p, (size_t)blob_bytes, s));
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_info, d_info, sizeof(PrgInfo) * (size_t)nl, s));
+        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, cnt, d_cnt, sizeof(DevCounters), s));
+        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        TRACE("dev: strings D2H");
+        if (cnt->err & ERR_OVERFLOW) {
+            pinned_release(blob);
+            pinned_release(raw.nodes);
+            pinned_release(raw.pool);
+            MPRG_FAIL(ctx, MPRG_E_INTERNAL, "tree deeper than the PRG walk supports");
+        }
+        int raw_index;
+        {
+            std::lock_guard<std::mutex> lock(res->raw_mutex);
+            raw_index = (int)res->raw.size();
+            res->raw.push_back(raw);
+            res->blobs.push_back(blob);
+        }
+        const char *base = static_cast<const char *>(blob.p);
+        for (int i = 0; i < nl; ++i) {
+            LocusResult &L = res->loci[l_begin + i];
+            L.status = h_info[i].status;
+            if (L.status != MPRG_LOCUS_OK) continue;
+            L.prg_data = base + h_info[i].off;
+            L.prg_size = h_info[i].len;
+            L.n_sites = h_info[i].n_sites;
+            L.n_nodes = h_info[i].n_nodes;
+            L.raw_index = raw_index;
+            L.raw_root = i;
+            L.tables_ready = false;
+        }
+        TRACE("dev: result records");
+        if (allow_trace || trace_all) {
+            trace.report("mprg_build (device-resident loop)");
+            g_trace = nullptr;
+        }
+        return MPRG_OK;
+    }
     MPRG_CUDA(ctx, ctx->h_a.reserve(sizeof(DNode) * (size_t)std::max(n_nodes, 1)));
     MPRG_CUDA(ctx, ctx->h_c.reserve((size_t)std::max<long long>(out_total, 1) + 16));
     MPRG_CUDA(ctx, ctx->h_d.reserve((sizeof(int) + sizeof(ExtractItem)) * (size_t)std::max(na, 1) + 64));
