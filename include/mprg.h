@@ -210,6 +210,12 @@ int mprg_build_sub(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, int32_
 int mprg_build_ascii(mprg_ctx *ctx, const uint8_t *h_ascii, const int64_t *h_offsets,
                      const int32_t *n_rows, const int32_t *n_cols, int32_t n_loci, int32_t max_nesting,
                      int32_t min_match_length, mprg_batch **out_batch, mprg_result **out_res);
+/* The same from HOST rows that are already in the 4-bit device layout (mprg_fasta_packed / mprg_pack_rows):
+ * locus i occupies n_rows[i] * 16 * ceil(n_cols[i] / 32) bytes at h_packed + h_offsets[i]; h_flags[i] are
+ * its alphabet flags.  Half the bytes of mprg_build_ascii cross PCIe and no pack kernel runs. */
+int mprg_build_packed(mprg_ctx *ctx, const uint8_t *h_packed, const int64_t *h_offsets, const int32_t *n_rows,
+                      const int32_t *n_cols, const int32_t *h_flags, int32_t n_loci, int32_t max_nesting,
+                      int32_t min_match_length, mprg_batch **out_batch, mprg_result **out_res);
 /* A result that only holds the given PRG strings (no trees): lets the writers below serve PRGs that
  * did not come out of mprg_build, e.g. PrgBuilder.build_prg() of a host-side tree (prg_builder.py:100-105) */
 int mprg_result_from_prgs(const char *const *prgs, const int64_t *lengths, int32_t n, mprg_result **out);
@@ -249,11 +255,25 @@ int mprg_result_row_pool(const mprg_result *res, int32_t locus, int32_t *h_rows)
 typedef struct mprg_msa_set mprg_msa_set;
 /* N replacement alone on one upper-cased row-major matrix, in place */
 int mprg_replace_n(uint8_t *h_ascii, int32_t n_rows, int32_t n_cols);
-int mprg_fasta_load(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t pin,
+/* mode: MPRG_LOADMODE_PIN = the output buffer is pinned host memory (pooled); MPRG_LOADMODE_PACKED = the
+ * matrices come out in the 4-bit device layout (mprg_fasta_packed, for mprg_build_packed: half the bytes
+ * cross PCIe and no pack kernel runs) and the text is dropped unless MPRG_LOADMODE_KEEP_ASCII is set */
+#define MPRG_LOADMODE_PIN 1
+#define MPRG_LOADMODE_PACKED 2
+#define MPRG_LOADMODE_KEEP_ASCII 4
+int mprg_fasta_load(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t mode,
                     mprg_msa_set **out);
 void mprg_fasta_free(mprg_msa_set *set);
 /* Borrowed views, valid until mprg_fasta_free; any out pointer may be NULL.  Locus i occupies
  * n_rows[i] * n_cols[i] bytes at h_ascii + h_offsets[i] (0 bytes unless status[i] == MPRG_LOAD_OK). */
+/* packed mode: locus i occupies n_rows[i] * stride(n_cols[i]) bytes at h_packed + h_packed_offsets[i]
+ * (stride = 16 * ceil(cols / 32)); alphabet_flags[i] = what mprg_batch_flags reports after a device pack */
+int mprg_fasta_packed(const mprg_msa_set *set, uint8_t **h_packed, int64_t *packed_bytes,
+                      const int64_t **h_packed_offsets, const int32_t **alphabet_flags);
+/* ASCII rows (row-major, n_rows * n_cols bytes, either case) -> the packed layout on the host;
+ * h_packed holds n_rows * stride(n_cols) bytes; *flags = alphabet flags as the device pack reports them */
+int mprg_pack_rows(const uint8_t *h_ascii, int32_t n_rows, int32_t n_cols, uint8_t *h_packed, int64_t capacity,
+                   int32_t *flags);
 int mprg_fasta_info(const mprg_msa_set *set, int32_t *n_loci, uint8_t **h_ascii, int64_t *ascii_bytes,
                     const int64_t **h_offsets, const int32_t **n_rows, const int32_t **n_cols,
                     const int32_t **status, const int32_t **flags);

@@ -78,6 +78,7 @@ SIGNATURES = {
     "mprg_build": (C.c_int, [P, P, I32, I32, C.POINTER(P)]),
     "mprg_build_sub": (C.c_int, [P, P, I32, I32, P, C.POINTER(P)]),
     "mprg_build_ascii": (C.c_int, [P, P, P, P, P, I32, I32, I32, C.POINTER(P), C.POINTER(P)]),
+    "mprg_build_packed": (C.c_int, [P, P, P, P, P, P, I32, I32, I32, C.POINTER(P), C.POINTER(P)]),
     "mprg_result_free": (None, [P]),
     "mprg_result_n_loci": (I32, [P]),
     "mprg_result_status": (I32, [P, I32]),
@@ -92,6 +93,8 @@ SIGNATURES = {
     "mprg_replace_n": (C.c_int, [P, I32, I32]),
     "mprg_fasta_load": (C.c_int, [P, I32, I32, I32, C.POINTER(P)]),
     "mprg_fasta_free": (None, [P]),
+    "mprg_fasta_packed": (C.c_int, [P, C.POINTER(P), C.POINTER(I64), C.POINTER(P), C.POINTER(P)]),
+    "mprg_pack_rows": (C.c_int, [P, I32, I32, P, I64, C.POINTER(I32)]),
     "mprg_fasta_info": (C.c_int, [P, C.POINTER(I32), C.POINTER(P), C.POINTER(I64), C.POINTER(P), C.POINTER(P),
                                   C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
     "mprg_fasta_titles": (P, [P, I32, C.POINTER(I64)]),

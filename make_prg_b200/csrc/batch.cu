@@ -387,6 +387,34 @@ int batch_upload_range(mprg_ctx *ctx, mprg_batch *b, const uint8_t *h_ascii, con
     return MPRG_OK;
 }
 
+// Loci [l0, l1) from host rows in the packed layout: one copy per run of loci that are contiguous in the
+// caller's buffer, straight into the batch arena (the loader lays them out exactly like the arena).
+int batch_upload_range_packed(mprg_ctx *ctx, mprg_batch *b, const uint8_t *h_packed, const int64_t *h_offsets,
+                              const int32_t *h_flags, int l0, int l1) {
+    if (l1 <= l0) return MPRG_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    std::unique_lock<std::mutex> link(b->copy_mutex);  // one range at a time on the PCIe link
+    int run0 = l0;
+    for (int l = l0; l < l1; ++l) {
+        const long long bytes_l = (long long)b->stride[l] * b->n_rows[l];
+        const bool last = l + 1 == l1;
+        const bool joins = !last && h_offsets[l + 1] == h_offsets[l] + bytes_l && b->base[l + 1] == b->base[l] + bytes_l;
+        if (joins) continue;
+        const long long nbytes = b->base[l] + bytes_l - b->base[run0];
+        if (nbytes > 0)
+            MPRG_CUDA(ctx, mprg::copy_h2d(ctx, b->d_packed + b->base[run0], h_packed + h_offsets[run0], (size_t)nbytes, s));
+        run0 = l + 1;
+    }
+    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    link.unlock();
+    for (int l = l0; l < l1; ++l) {
+        b->flags[l] = h_flags ? h_flags[l] : 0;
+        if (b->flags[l] & 2) b->any_n = true;
+    }
+    return MPRG_OK;
+}
+
 }  // namespace mprg
 
 extern "C" int mprg_batch_upload(mprg_ctx *ctx, const uint8_t *h_ascii, const int64_t *h_offsets,

@@ -1425,7 +1425,8 @@ extern "C" int mprg_set_workers(mprg_ctx *ctx, int32_t n_workers) {
 // host-to-device copies of some ranges overlap the kernels of the others (mprg_build_ascii).
 static int build_ranges(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, int32_t min_match_length,
                         const uint8_t *h_ascii, const int64_t *h_offsets, mprg_result **out_res,
-                        const int32_t *root_levels = nullptr) {
+                        const int32_t *root_levels = nullptr, const int32_t *h_packed_flags = nullptr,
+                        bool host_is_packed = false) {
     *out_res = nullptr;
     cudaSetDevice(ctx->device);
     const int n_loci = batch->n_loci;
@@ -1444,7 +1445,8 @@ static int build_ranges(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, i
     auto run = [&](mprg_ctx *c, int l0, int l1, bool trace) {
         if (h_ascii) {
             const double t0 = since_call();
-            const int r = batch_upload_range(c, batch, h_ascii, h_offsets, l0, l1);
+            const int r = host_is_packed ? batch_upload_range_packed(c, batch, h_ascii, h_offsets, h_packed_flags, l0, l1)
+                                         : batch_upload_range(c, batch, h_ascii, h_offsets, l0, l1);
             if (r != MPRG_OK) return r;
             if (trace_all) fprintf(stderr, "[mprg trace] range %d..%d: upload %.2f -> %.2f ms after the call\n", l0, l1, t0, since_call());
         }
@@ -1579,6 +1581,27 @@ extern "C" int mprg_build_ascii(mprg_ctx *ctx, const uint8_t *h_ascii, const int
     int rc = batch_prepare(ctx, n_rows, n_cols, n_loci, &b);
     if (rc != MPRG_OK) return rc;
     rc = build_ranges(ctx, b, max_nesting, min_match_length, h_ascii, h_offsets, out_res);
+    if (rc != MPRG_OK) {
+        mprg_batch_free(ctx, b);
+        return rc;
+    }
+    *out_batch = b;
+    return MPRG_OK;
+}
+
+extern "C" int mprg_build_packed(mprg_ctx *ctx, const uint8_t *h_packed, const int64_t *h_offsets,
+                                 const int32_t *n_rows, const int32_t *n_cols, const int32_t *h_flags, int32_t n_loci,
+                                 int32_t max_nesting, int32_t min_match_length, mprg_batch **out_batch,
+                                 mprg_result **out_res) {
+    if (!ctx || !out_batch || !out_res || min_match_length < 1 || n_loci < 0 ||
+        (n_loci > 0 && (!h_packed || !h_offsets || !n_rows || !n_cols)))
+        return MPRG_E_BAD_ARG;
+    *out_batch = nullptr;
+    *out_res = nullptr;
+    mprg_batch *b = nullptr;
+    int rc = batch_prepare(ctx, n_rows, n_cols, n_loci, &b);
+    if (rc != MPRG_OK) return rc;
+    rc = build_ranges(ctx, b, max_nesting, min_match_length, h_packed, h_offsets, out_res, nullptr, h_flags, true);
     if (rc != MPRG_OK) {
         mprg_batch_free(ctx, b);
         return rc;

@@ -709,13 +709,137 @@ void parse_file(const char *path, ParsedFile &pf, bool avx2, Slab &slab) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// ASCII rows -> the 4-bit device layout, on the host (what pack_rows_kernel of batch.cu produces): rows
+// padded to 16 bytes = 32 columns with MPRG_SYM_PAD, column c of a chunk in nibble c / 4 of word c % 4.
+// The loader emits its matrices this way so that half the bytes cross PCIe and no pack kernel runs
+// (mprg_build_packed).  flags: bit0 a character outside the alphabet, bit1 N, bit2 RYKMSW, bit3 an even
+// symbol code (M S W N) -- exactly the flags of the pack kernel.
+// ------------------------------------------------------------------------------------------------
+struct PackTables {
+    uint8_t code[256], cls[16];
+    PackTables() {
+        memset(code, MPRG_SYM_PAD, sizeof(code));
+        const char *alphabet = MPRG_ALPHABET;
+        for (int i = 0; i < 16; ++i) {
+            const char ch = alphabet[i];
+            if (ch == '?') continue;
+            code[(uint8_t)ch] = (uint8_t)i;
+            if (ch >= 'A' && ch <= 'Z') code[(uint8_t)(ch - 'A' + 'a')] = (uint8_t)i;
+        }
+        for (int c = 0; c < 16; ++c) {
+            int f = 0;
+            if (c == MPRG_SYM_PAD) f |= 1;
+            else if (c == MPRG_SYM_N) f |= 2;
+            else if (c != MPRG_SYM_GAP && (c & 9) != 1) f |= 4;
+            if (c != MPRG_SYM_GAP && !(c & 1)) f |= 8;
+            cls[c] = (uint8_t)f;
+        }
+    }
+};
+const PackTables &pack_tables() {
+    static const PackTables t;
+    return t;
+}
+
+// one chunk (up to 32 valid columns at src) -> 16 bytes
+inline int pack_chunk_scalar(const uint8_t *src, int valid, uint8_t *dst) {
+    const PackTables &t = pack_tables();
+    uint32_t words[4] = {0, 0, 0, 0};
+    int f = 0;
+    for (int c = 0; c < 32; ++c) {
+        uint32_t code = MPRG_SYM_PAD;
+        if (c < valid) {
+            code = t.code[src[c]];
+            f |= t.cls[code];
+        }
+        words[c & 3] |= code << (4 * (c >> 2));
+    }
+    memcpy(dst, words, 16);
+    return f;
+}
+
+__attribute__((target("avx2"))) int pack_row_avx2(const uint8_t *src, int cols, uint8_t *dst) {
+    const PackTables &t = pack_tables();
+    // letters by their low five bits: two 16-entry tables ('@'..'O', 'P'..'_')
+    alignas(32) uint8_t lo[32], hi[32], cls[32];
+    for (int k = 0; k < 16; ++k) {
+        lo[k] = lo[k + 16] = t.code[0x40 + k];
+        hi[k] = hi[k + 16] = t.code[0x50 + k];
+        cls[k] = cls[k + 16] = t.cls[k];
+    }
+    lo[0] = lo[16] = MPRG_SYM_PAD;  // '@' / '`' are no letters
+    const __m256i t_lo = _mm256_load_si256((const __m256i *)lo), t_hi = _mm256_load_si256((const __m256i *)hi);
+    const __m256i t_cls = _mm256_load_si256((const __m256i *)cls);
+    const __m256i v_dash = _mm256_set1_epi8('-'), v_case = _mm256_set1_epi8(0x20), v_a = _mm256_set1_epi8('a' - 1);
+    const __m256i v_z = _mm256_set1_epi8('z' + 1), v_0f = _mm256_set1_epi8(0x0f), v_10 = _mm256_set1_epi8(0x10);
+    const __m256i v_pad = _mm256_set1_epi8(MPRG_SYM_PAD);
+    const __m256i shuf = _mm256_setr_epi8(0, 4, 8, 12, 1, 5, 9, 13, 2, 6, 10, 14, 3, 7, 11, 15, 0, 4, 8, 12, 1, 5, 9, 13, 2, 6,
+                                          10, 14, 3, 7, 11, 15);
+    const __m256i m1 = _mm256_set1_epi16(0x1001), m2 = _mm256_set1_epi32(0x01000001);
+    __m256i acc = _mm256_setzero_si256();
+    int c = 0;
+    for (; c + 32 <= cols; c += 32, dst += 16) {
+        const __m256i v = _mm256_loadu_si256((const __m256i *)(src + c));
+        const __m256i low = _mm256_or_si256(v, v_case);
+        const __m256i letter = _mm256_and_si256(_mm256_cmpgt_epi8(low, v_a), _mm256_cmpgt_epi8(v_z, low));
+        const __m256i idx = _mm256_and_si256(v, v_0f);
+        const __m256i upper_half = _mm256_cmpeq_epi8(_mm256_and_si256(v, v_10), v_10);
+        __m256i code = _mm256_blendv_epi8(_mm256_shuffle_epi8(t_lo, idx), _mm256_shuffle_epi8(t_hi, idx), upper_half);
+        code = _mm256_blendv_epi8(v_pad, code, letter);
+        code = _mm256_andnot_si256(_mm256_cmpeq_epi8(v, v_dash), code);  // '-' = 0
+        acc = _mm256_or_si256(acc, _mm256_shuffle_epi8(t_cls, code));
+        const __m256i x = _mm256_shuffle_epi8(code, shuf);
+        const __m256i q = _mm256_madd_epi16(_mm256_maddubs_epi16(x, m1), m2);
+        const __m128i out = _mm_or_si128(_mm256_castsi256_si128(q), _mm_slli_epi32(_mm256_extracti128_si256(q, 1), 16));
+        _mm_storeu_si128((__m128i *)dst, out);
+    }
+    alignas(32) uint8_t accb[32];
+    _mm256_store_si256((__m256i *)accb, acc);
+    int f = 0;
+    for (int k = 0; k < 32; ++k) f |= accb[k];
+    if (c < cols) f |= pack_chunk_scalar(src + c, cols - c, dst);
+    return f;
+}
+
+int pack_row_scalar(const uint8_t *src, int cols, uint8_t *dst) {
+    int f = 0;
+    for (int c = 0; c < cols; c += 32, dst += 16) f |= pack_chunk_scalar(src + c, std::min(32, cols - c), dst);
+    return f;
+}
+
+inline int64_t packed_stride(int32_t cols) { return ((int64_t)cols + 31) / 32 * 16; }
+
+int pack_matrix(const uint8_t *ascii, int32_t rows, int32_t cols, uint8_t *out, bool avx2) {
+    const int64_t stride = packed_stride(cols);
+    int f = 0;
+    for (int32_t r = 0; r < rows; ++r) {
+        const uint8_t *src = ascii + (int64_t)r * cols;
+        uint8_t *dst = out + (int64_t)r * stride;
+        f |= avx2 ? pack_row_avx2(src, cols, dst) : pack_row_scalar(src, cols, dst);
+    }
+    return f;
+}
 }  // namespace
+
+extern "C" int mprg_pack_rows(const uint8_t *h_ascii, int32_t n_rows, int32_t n_cols, uint8_t *h_packed,
+                              int64_t capacity, int32_t *flags) {
+    if (n_rows < 0 || n_cols < 0 || (!h_ascii && (int64_t)n_rows * n_cols > 0) || !h_packed) return MPRG_E_BAD_ARG;
+    if (capacity < packed_stride(n_cols) * n_rows) return MPRG_E_BAD_ARG;
+    const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("MPRG_NO_AVX2");
+    const int f = pack_matrix(h_ascii, n_rows, n_cols, h_packed, avx2);
+    if (flags) *flags = f;
+    return MPRG_OK;
+}
 
 extern "C" int mprg_replace_n(uint8_t *h_ascii, int32_t n_rows, int32_t n_cols) {
     if (!h_ascii || n_rows < 0 || n_cols < 0) return MPRG_E_BAD_ARG;
     replace_n(h_ascii, n_rows, n_cols);
     return MPRG_OK;
 }
+
+extern "C" void mprg_fasta_free(mprg_msa_set *set);
 
 struct mprg_msa_set {
     int32_t n = 0;
@@ -726,11 +850,21 @@ struct mprg_msa_set {
     std::vector<int64_t> offsets;
     std::vector<int32_t> n_rows, n_cols, status, flags;
     std::vector<std::string> titles;
+    // packed mode (MPRG_LOADMODE_PACKED): the matrices in the 4-bit device layout, loci back to back
+    uint8_t *packed = nullptr;
+    int64_t packed_bytes = 0;
+    bool packed_pinned = false;
+    size_t packed_capacity = 0;
+    std::vector<int64_t> packed_offsets;
+    std::vector<int32_t> alphabet_flags;  // per locus: the flags of the pack kernel (mprg_batch_flags)
 };
 
-extern "C" int mprg_fasta_load(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t pin,
+extern "C" int mprg_fasta_load(const char *const *paths, int32_t n_files, int32_t n_threads, int32_t mode,
                                mprg_msa_set **out) {
     if (!out || n_files < 0 || (n_files > 0 && !paths)) return MPRG_E_BAD_ARG;
+    const int pin = mode & MPRG_LOADMODE_PIN;
+    const bool want_packed = (mode & MPRG_LOADMODE_PACKED) != 0;
+    const bool want_ascii = !want_packed || (mode & MPRG_LOADMODE_KEEP_ASCII) != 0;
     *out = nullptr;
     std::vector<ParsedFile> files((size_t)n_files);
     const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("MPRG_NO_AVX2");
@@ -757,24 +891,61 @@ extern "C" int mprg_fasta_load(const char *const *paths, int32_t n_files, int32_
         set->titles[(size_t)i].swap(pf.titles);
         if (good) total += pf.matrix_bytes;
     }
-    set->ascii_bytes = total;
-    const size_t alloc = (size_t)std::max<int64_t>(total, 1);
-    if (pin) set->ascii = pinned_pool().acquire(alloc, set->capacity);
-    if (set->ascii) {
-        set->pinned = true;
-    } else {  // without a device the buffer is ordinary memory
-        set->ascii = huge_alloc(alloc);
-        if (!set->ascii) {
-            delete set;
-            return MPRG_E_INTERNAL;
+    set->ascii_bytes = want_ascii ? total : 0;
+    if (want_ascii) {
+        const size_t alloc = (size_t)std::max<int64_t>(total, 1);
+        // in packed mode the text is only kept for callers that want the rows back: ordinary memory
+        if (pin && !want_packed) set->ascii = pinned_pool().acquire(alloc, set->capacity);
+        if (set->ascii) {
+            set->pinned = true;
+        } else {  // without a device the buffer is ordinary memory
+            set->ascii = huge_alloc(alloc);
+            if (!set->ascii) {
+                delete set;
+                return MPRG_E_INTERNAL;
+            }
+        }
+    }
+    if (want_packed) {
+        set->packed_offsets.resize((size_t)n_files);
+        set->alphabet_flags.assign((size_t)n_files, 0);
+        int64_t ptotal = 0;
+        for (int i = 0; i < n_files; ++i) {
+            set->packed_offsets[(size_t)i] = ptotal;
+            ptotal += packed_stride(set->n_cols[(size_t)i]) * set->n_rows[(size_t)i];
+        }
+        set->packed_bytes = ptotal;
+        const size_t palloc = (size_t)std::max<int64_t>(ptotal, 1);
+        if (pin) set->packed = pinned_pool().acquire(palloc, set->packed_capacity);
+        if (set->packed) {
+            set->packed_pinned = true;
+        } else {
+            set->packed = huge_alloc(palloc);
+            if (!set->packed) {
+                mprg_fasta_free(set);
+                return MPRG_E_INTERNAL;
+            }
         }
     }
     parallel_for(n_files, n_threads, [&](int i) {
         ParsedFile &pf = files[(size_t)i];
-        if (pf.status == MPRG_LOAD_OK && pf.matrix_bytes)
-            memcpy(set->ascii + set->offsets[(size_t)i], pf.buf, (size_t)pf.matrix_bytes);
+        if (pf.status != MPRG_LOAD_OK || !pf.matrix_bytes) return;
+        if (want_packed)
+            set->alphabet_flags[(size_t)i] =
+                pack_matrix(pf.buf, pf.n_rows, pf.n_cols, set->packed + set->packed_offsets[(size_t)i], avx2);
+        if (want_ascii) memcpy(set->ascii + set->offsets[(size_t)i], pf.buf, (size_t)pf.matrix_bytes);
     });
     *out = set;
+    return MPRG_OK;
+}
+
+extern "C" int mprg_fasta_packed(const mprg_msa_set *set, uint8_t **h_packed, int64_t *packed_bytes,
+                                 const int64_t **h_packed_offsets, const int32_t **alphabet_flags) {
+    if (!set || !set->packed) return MPRG_E_BAD_ARG;
+    if (h_packed) *h_packed = set->packed;
+    if (packed_bytes) *packed_bytes = set->packed_bytes;
+    if (h_packed_offsets) *h_packed_offsets = set->packed_offsets.data();
+    if (alphabet_flags) *alphabet_flags = set->alphabet_flags.data();
     return MPRG_OK;
 }
 
@@ -785,6 +956,12 @@ extern "C" void mprg_fasta_free(mprg_msa_set *set) {
             pinned_pool().release(set->ascii, set->capacity);
         else
             free(set->ascii);
+    }
+    if (set->packed) {
+        if (set->packed_pinned)
+            pinned_pool().release(set->packed, set->packed_capacity);
+        else
+            free(set->packed);
     }
     delete set;
 }

@@ -23,6 +23,9 @@ cudaError_t launch_demote(cudaStream_t stream, const uint8_t *packed, const DTas
 int batch_prepare(mprg_ctx *ctx, const int32_t *n_rows, const int32_t *n_cols, int32_t n_loci, mprg_batch **out);
 int batch_upload_range(mprg_ctx *ctx, mprg_batch *b, const uint8_t *h_ascii, const int64_t *h_offsets, int l0,
                        int l1);
+// the same for host rows already in the packed layout: straight into the arena, flags from the caller
+int batch_upload_range_packed(mprg_ctx *ctx, mprg_batch *b, const uint8_t *h_packed, const int64_t *h_offsets,
+                              const int32_t *h_flags, int l0, int l1);
 
 // Host-side description of one level of tasks, resident on the device after level_upload().
 struct Level {

@@ -59,10 +59,23 @@ class MsaSet:
         self.n_cols = _view(nc, C.c_int32, self.n_loci)
         self.status = _view(st, C.c_int32, self.n_loci)
         self.flags = _view(fl, C.c_int32, self.n_loci)
+        # packed mode: the matrices in the 4-bit device layout (mprg_build_packed takes them as they are)
+        self.packed = self.packed_offsets = self.alphabet_flags = None
+        pk, pbytes, poffs, pflags = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_void_p()
+        if self.lib.mprg_fasta_packed(handle, C.byref(pk), C.byref(pbytes), C.byref(poffs), C.byref(pflags)) == 0:
+            self.packed = _view(pk, C.c_uint8, max(pbytes.value, 1))
+            self.packed_bytes = pbytes.value
+            self.packed_offsets = _view(poffs, C.c_int64, self.n_loci)
+            self.alphabet_flags = _view(pflags, C.c_int32, self.n_loci)
 
     def matrix(self, locus):
-        """uint8[rows, cols] view (writable) of one locus."""
+        """uint8[rows, cols] of one locus: a (writable) view of the text, or -- when the loader only kept the
+        packed rows -- the text unpacked from them."""
         r, c, o = int(self.n_rows[locus]), int(self.n_cols[locus]), int(self.offsets[locus])
+        if self.ascii_bytes == 0 and self.packed is not None:
+            stride = packed_stride(c)
+            po = int(self.packed_offsets[locus])
+            return unpack_rows(self.packed[po:po + r * stride].reshape(r, stride), c)
         return self.ascii[o:o + r * c].reshape(r, c)
 
     def titles(self, locus):
@@ -93,6 +106,7 @@ class MsaSet:
     def free(self):
         if self.handle is not None:
             self.ascii = self.offsets = self.n_rows = self.n_cols = self.status = self.flags = None
+            self.packed = self.packed_offsets = self.alphabet_flags = None
             self.lib.mprg_fasta_free(self.handle)
             self.handle = None
 
@@ -121,13 +135,51 @@ def replace_n_in_place(matrix):
     matrix[mask] = np.broadcast_to(cons, matrix.shape)[mask]
 
 
-def load_fasta_files(paths, threads=None, pin=True):
+ALPHABET = np.frombuffer(b"-AMCSGWTNR?Y?K??", np.uint8)  # MPRG_ALPHABET: character of every 4-bit code
+
+
+def packed_stride(cols):
+    """Bytes of a packed row: 16 per chunk of 32 columns."""
+    return (int(cols) + 31) // 32 * 16
+
+
+def pack_rows(matrix):
+    """uint8[rows, cols] ASCII -> (uint8[rows, stride] in the 4-bit device layout, alphabet flags), by the
+    library's host packer (mprg_pack_rows)."""
+    matrix = np.ascontiguousarray(matrix, np.uint8)
+    rows, cols = matrix.shape
+    out = np.empty((rows, packed_stride(cols)), np.uint8)
+    flags = C.c_int32()
+    rc = _lib.load().mprg_pack_rows(ptr(matrix) if matrix.size else None, rows, cols, ptr(out) if out.size else ptr(np.zeros(1, np.uint8)),
+                                    out.size, C.byref(flags))
+    if rc != 0:
+        raise MprgError(rc, "mprg_pack_rows failed")
+    return out, flags.value
+
+
+def unpack_rows(packed, cols):
+    """Inverse of the packing (numpy; test and archive helper): column c of a chunk is nibble c // 4 of the
+    little-endian 32-bit word c % 4."""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    rows = packed.shape[0]
+    if cols == 0 or rows == 0:
+        return np.zeros((rows, cols), np.uint8)
+    words = packed.view("<u4").reshape(rows, -1, 4)                      # [row, chunk, word]
+    shifts = (4 * np.arange(8, dtype=np.uint32)).reshape(1, 1, 8, 1)      # nibble j of every word
+    codes = (words[:, :, None, :] >> shifts) & 15                         # [row, chunk, nibble j, word w]: column 4j + w
+    return ALPHABET[codes.reshape(rows, -1)[:, :cols]]
+
+
+def load_fasta_files(paths, threads=None, pin=True, packed=False, keep_ascii=False):
     """Parses every file on host threads (N replaced by the loader).  Loci whose status is not LOAD_OK
-    are left to the caller (`raise_for_load_status` re-creates the reference's exception)."""
+    are left to the caller (`raise_for_load_status` re-creates the reference's exception).
+    packed: the matrices come out in the 4-bit device layout (for Context.build_msa_set / mprg_build_packed);
+    the text is dropped unless keep_ascii."""
     lib = _lib.load()
     arr, _keep = _c_strings([os.fspath(p) for p in paths])
     h = C.c_void_p()
-    rc = lib.mprg_fasta_load(C.cast(arr, C.c_void_p), len(paths), threads or default_threads(), int(bool(pin)),
+    mode = (1 if pin else 0) | (2 if packed else 0) | (4 if keep_ascii else 0)
+    rc = lib.mprg_fasta_load(C.cast(arr, C.c_void_p), len(paths), threads or default_threads(), mode,
                              C.byref(h))
     if rc != 0:
         raise MprgError(rc, "mprg_fasta_load failed")

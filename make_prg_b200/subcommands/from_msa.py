@@ -126,7 +126,9 @@ def side_threads(n_chunks, writer=False):
 def _load_chunk(paths, alignment_format, threads=None):
     if alignment_format != "fasta":
         raise ValueError(f"only the fasta alignment format is supported, got {alignment_format}")
-    return hostio.load_fasta_files(paths, threads=threads)
+    # the loader emits the matrices in the 4-bit device layout: half the bytes cross PCIe, no pack kernel
+    # (MPRG_TEXT_UPLOAD=1 keeps the text path: upload of ASCII rows + pack_rows_kernel)
+    return hostio.load_fasta_files(paths, threads=threads, packed=not os.environ.get("MPRG_TEXT_UPLOAD"))
 
 
 _EXTENSIONS = (".fasta.gz", ".fa.gz", ".fasta", ".fa")

@@ -93,7 +93,7 @@ def measure(n_loci=1000, reps=5, copies=1, python_io=False):
         return line
     # stages, one after the other
     t0 = time.perf_counter()
-    msas = hostio.load_fasta_files(paths)
+    msas = hostio.load_fasta_files(paths, packed=True)
     t_load = time.perf_counter() - t0
     t0 = time.perf_counter()
     batch, res = ctx.build_msa_set(msas, 5, 7)
@@ -103,7 +103,7 @@ def measure(n_loci=1000, reps=5, copies=1, python_io=False):
     w.add(res, np.arange(n_loci, dtype=np.int32), [p.stem for p in paths])
     w.close()
     t_write = time.perf_counter() - t0
-    line["stages_s"] = {"load": t_load, "build_ascii": t_build, "write": t_write}
+    line["stages_s"] = {"load": t_load, "build_packed": t_build, "write": t_write}
     if python_io:
         from make_prg_b200.utils.io_utils import load_alignment_file
 

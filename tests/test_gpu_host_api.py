@@ -222,3 +222,32 @@ def test_node_factory_build_below_parent(tmp_path):
 
         walk(node)
         assert dump == [list(t) for t in r["tree"]]
+
+
+def test_packed_host_rows_equal_device_pack_and_text_build():
+    """mprg_build_packed: the host packer produces what pack_rows_kernel produces (bytes and alphabet flags),
+    and a build from packed host rows equals the build from text (incl. N / RYKMSW / disallowed loci)."""
+    import numpy as np
+    from make_prg_b200 import device, hostio, synth
+
+    ctx = device.default_context(0)
+    rng = np.random.default_rng(21)
+    mats = [synth.synth_msa(3 + (i * 7) % 23, w, 900 + i, var_frac=0.08, n_dels=2)
+            for i, w in enumerate([1, 31, 32, 33, 100, 255, 1000, 64, 7, 513])]
+    mats[2][1, 3] = ord("Z")
+    mats[4][0, 5:9] = np.frombuffer(b"RYKM", np.uint8)
+    mats[6][2, 500:503] = np.frombuffer(b"SWR", np.uint8)
+    batch, res_text = ctx.build_ascii(mats, 5, 7)
+    packed, flags = zip(*(hostio.pack_rows(m) for m in mats))
+    for i, m in enumerate(mats):
+        assert np.array_equal(batch.packed(i), packed[i]), i
+    assert batch.flags().tolist() == list(flags)
+    flat = np.concatenate([p.reshape(-1) for p in packed])
+    offsets = np.cumsum([0] + [p.size for p in packed[:-1]])
+    b2, res_packed = ctx.build_packed(flat, offsets, [m.shape[0] for m in mats], [m.shape[1] for m in mats], flags, 5, 7)
+    assert b2.flags().tolist() == list(flags)
+    for i in range(len(mats)):
+        assert res_packed.status(i) == res_text.status(i)
+        assert res_packed.prg(i) == res_text.prg(i)
+        assert np.array_equal(b2.packed(i), packed[i])
+    assert res_text.status(2) == 1 and res_text.status(0) == 0

@@ -180,6 +180,56 @@ def test_encoder_reference_unit_vectors_and_errors():
         hostio.prg_to_gfa("A 5 C 6 T")  # unterminated site
 
 
+def test_host_packer_and_packed_loader(tmp_path, monkeypatch):
+    """The loader's packed mode: rows in the 4-bit device layout (what pack_rows_kernel produces on the device,
+    checked against it in tests/test_gpu_host_api.py), vector and scalar packers agree, the text comes back."""
+    rng = np.random.default_rng(11)
+    alphabet = np.frombuffer(b"ACGTacgtRYKMSWN-Z@`[{", np.uint8)
+    good = np.frombuffer(b"ACGTRYKMSWN-", np.uint8)
+    for rows, cols in [(5, 1), (3, 31), (4, 32), (7, 33), (2, 64), (9, 1000), (1, 0), (0, 5), (6, 257)]:
+        M = rng.choice(alphabet, size=(rows, cols))
+        P, flags = hostio.pack_rows(M)
+        assert P.shape == (rows, hostio.packed_stride(cols))
+        monkeypatch.setenv("MPRG_NO_AVX2", "1")
+        P2, flags2 = hostio.pack_rows(M)
+        monkeypatch.delenv("MPRG_NO_AVX2")
+        assert np.array_equal(P, P2) and flags == flags2
+        upper = np.where((M >= ord("a")) & (M <= ord("z")), M - 32, M)
+        want = np.where(np.isin(upper, good), upper, ord("?"))
+        assert np.array_equal(hostio.unpack_rows(P, cols), want)
+        if M.size:
+            assert bool(flags & 1) == bool((~np.isin(upper, good)).any())
+            assert bool(flags & 2) == bool((upper == ord("N")).any())
+            assert bool(flags & 4) == bool(np.isin(upper, np.frombuffer(b"RYKMSW", np.uint8)).any())
+            assert bool(flags & 8) == bool(np.isin(upper, np.frombuffer(b"MSWN", np.uint8)).any())
+        # padding columns are MPRG_SYM_PAD (15) and raise no flag
+        if cols % 32:
+            full = hostio.unpack_rows(P, hostio.packed_stride(cols) * 2)
+            assert (full[:, cols:] == ord("?")).all()
+    files = fixture_fastas()
+    text = hostio.load_fasta_files(files, threads=3, pin=False)
+    packed = hostio.load_fasta_files(files, threads=3, pin=False, packed=True)
+    both = hostio.load_fasta_files(files, threads=2, pin=False, packed=True, keep_ascii=True)
+    assert packed.ascii_bytes == 0 and both.ascii_bytes == text.ascii_bytes
+    at = 0
+    for i in range(text.n_loci):
+        M = text.matrix(i)
+        assert packed.packed_offsets[i] == at
+        at += M.shape[0] * hostio.packed_stride(M.shape[1])
+        want, flags = hostio.pack_rows(M)
+        po = int(packed.packed_offsets[i])
+        assert np.array_equal(packed.packed[po:po + want.size].reshape(want.shape), want)
+        assert packed.alphabet_flags[i] == flags == both.alphabet_flags[i]
+        if flags & 1:  # a disallowed character (the locus is skipped anyway): '?' in the unpacked text
+            assert ((packed.matrix(i) == M) | (packed.matrix(i) == ord("?"))).all()
+        else:
+            assert np.array_equal(packed.matrix(i), M)  # unpacked from the 4-bit rows
+        assert np.array_equal(both.matrix(i), M) and packed.ids(i) == text.ids(i)
+    assert packed.packed_bytes == at
+    for m in (text, packed, both):
+        m.free()
+
+
 def test_writer_final_files(tmp_path):
     truth = truth_multi("sample_example")
     names = sorted(truth, reverse=True)  # archive order = order added, .prg.fa = sorted
