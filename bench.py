@@ -538,9 +538,13 @@ def main():
                     "frac_of_peak": float(sum(b for b, _ in yard) / (sum(m for _, m in yard) * 1e-3) / 1e9) / peak},
                 "launch_8x": None if big is None else dict(big, frac=big["achieved"] / peak,
                                                            bare_read_frac=big["bare_read_gbs"] / peak),
-                "in_step": {"note": "same kernel inside the timed steps: one launch per worker stream and "
-                                    "recursion level, launches of different streams overlap",
+                "in_step": {"note": "same kernel inside the timed steps: one launch per recursion level over the "
+                                    "whole batch (device-resident level loop); root_level_launch_gbs = the "
+                                    "105 MB launch of the root level, as timed inside the steps",
                             "launches_per_step": len(log_bytes) / args.steps,
+                            "root_level_launch_gbs": float(
+                                log_bytes[log_bytes >= 0.99 * log_bytes.max()].sum() /
+                                (log_ms[log_bytes >= 0.99 * log_bytes.max()].sum() * 1e-3) / 1e9) if len(log_bytes) else None,
                             "achieved_gbs_sum_over_launches": float(log_bytes.sum() / (log_ms.sum() * 1e-3) / 1e9)
                             if len(log_bytes) else None}}
     # file to file: FASTA files in -> .prg.fa / .prg.bin.zip / .prg.gfa.zip out through the

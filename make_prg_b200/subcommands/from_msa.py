@@ -116,11 +116,13 @@ def cut_chunks(input_files, max_bytes=None, max_loci=16384):
 def side_threads(n_chunks, writer=False):
     """Host threads of the loader and of the writers.  With one chunk nothing overlaps and each stage may
     use every core; with several, loading chunk k+1 and writing chunk k-1 run beside the build of chunk
-    k, whose worker threads drive the device and must not be starved of cores."""
+    k.  The build itself needs two host threads (the level loop runs on the device), so the loader and the
+    writers share the rest of this process's cores."""
     cores = os.cpu_count() or 1
+    share = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)))
     if n_chunks <= 1:
-        return max(1, min(32, cores))
-    return max(1, min(4, cores // 8)) if writer else max(1, min(12, cores // 3))
+        return max(1, min(32, share))
+    return max(1, min(8, share // 4)) if writer else max(1, min(24, (share - 2) * 2 // 3))
 
 
 def _load_chunk(paths, alignment_format, threads=None):
