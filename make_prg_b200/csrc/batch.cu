@@ -204,6 +204,7 @@ extern "C" void mprg_destroy(mprg_ctx *ctx) {
     for (DevBuf &b : ctx->d_c) b.release();
     for (DevBuf &b : ctx->d_dev) b.release();
     ctx->h_cnt.release();
+    ctx->d_ref.release();
     for (auto &a : ctx->idle_arenas) cudaFree(a.first);
     ctx->idle_arenas.clear();
     ctx->h_a.release();

@@ -1109,4 +1109,9 @@ cudaError_t launch_refcheck_big(cudaStream_t s, ClusterState *states, int q, int
     return cudaGetLastError();
 }
 
+cudaError_t launch_refcheck_big_control(cudaStream_t s, ClusterState *states, int q, int max_clusters, int *flags) {
+    refcheck_big_control_kernel<<<1, 1, 0, s>>>(states, q, max_clusters, flags);
+    return cudaGetLastError();
+}
+
 }  // namespace mprg

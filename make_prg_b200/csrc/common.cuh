@@ -162,6 +162,7 @@ struct mprg_ctx {
     mprg::DevBuf d_c[16];
     // buffers of the device-resident level loop (engine_dev.cu): tree, row pool, alleles, task / problem tables
     mprg::DevBuf d_dev[32];
+    mprg::DevBuf d_ref;  // scratch of the whole-grid one-reference-like check (refcheck_grid.cu)
     mprg::PinnedBuf h_cnt;  // the counter block the host reads twice per level
     bool pending_scan = false;  // a scan launch whose events have not been read yet
     double pending_scan_bytes = 0;

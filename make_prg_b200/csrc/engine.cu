@@ -203,7 +203,7 @@ static int cluster_of_rows(const ClusterOut &o, int kmer_size, std::vector<int> 
 // fetch: copy the final loop states and assignments back (the device-resident loop reads them in place).
 int run_problems_host(mprg_ctx *ctx, cudaStream_t s, const std::vector<HostProblem> &hp, const std::vector<int> &seq_rows,
                       int kmer_size, const uint8_t *d_G, const int *d_group, const int *d_leadlen, int *d_leader_u,
-                      int *d_err, bool fetch, ProblemRun &run) {
+                      int *d_err, bool fetch, ProblemRun &run, const uint8_t *d_packed, const int *d_rows_arena) {
     const int np = (int)hp.size();
     DevBuf *B = ctx->d_c;
     std::vector<ClusterState> &st = run.st;
@@ -311,9 +311,32 @@ int run_problems_host(mprg_ctx *ctx, cudaStream_t s, const std::vector<HostProbl
         ctx->path_counts[MPRG_PATH_REFCHECK_CTA]++;
         for (size_t b = 0; b < big_ref_q.size() && e == cudaSuccess; ++b) {
             const int q = big_ref_q[b];
-            e = launch_refcheck_big(s, d_states, q, st[q].w, st[q].n, d_G, d_memoff, d_memrows,
-                                    d_assign, d_maj, 10, d_refflags + REFCHECK_FLAG_INTS * b);
-            ctx->launches += 3;
+            const HostProblem &p = hp[q];
+            // loci over ACGT- only (no N, no RYKMSW, no even code): bit-sliced counting on the packed rows;
+            // MPRG_REFCHECK_BYTES=1 keeps the byte-wise kernels (the checked alternative)
+            static const bool bytes_only = getenv("MPRG_REFCHECK_BYTES") != nullptr;
+            if (d_packed && !(p.alpha_flags & (2 | 4 | 8)) && !bytes_only) {
+                DTask t;
+                t.base = p.base;
+                t.stride = p.stride;
+                t.rows_off = p.rows_off;
+                t.n_rows = p.R;
+                t.c0 = p.c0;
+                t.c1 = p.c0 + p.w;
+                t.col_off = t.iv_off = t.flags = 0;
+                const int n_words = (((t.c1 + 31) >> 5) - (t.c0 >> 5)) * 4;
+                cudaError_t e2 = ctx->d_ref.reserve(sizeof(int) * (size_t)refgrid_scratch_ints(p.R, p.w, n_words, 10));
+                if (e2 != cudaSuccess) return e2;
+                int *flags = d_refflags + REFCHECK_FLAG_INTS * b;
+                e = launch_refcheck_grid(s, d_states, q, t, 10, d_packed, d_rows_arena, d_memoff, d_memrows, d_assign, d_maj,
+                                         ctx->d_ref.as<int>(), p.R, flags);
+                if (e == cudaSuccess) e = launch_refcheck_big_control(s, d_states, q, 10, flags);
+                ctx->launches += 6;
+            } else {
+                e = launch_refcheck_big(s, d_states, q, st[q].w, st[q].n, d_G, d_memoff, d_memrows,
+                                        d_assign, d_maj, 10, d_refflags + REFCHECK_FLAG_INTS * b);
+                ctx->launches += 3;
+            }
             ctx->path_counts[MPRG_PATH_REFCHECK_GRID]++;
             if (refcheck_round > 1) ctx->path_counts[MPRG_PATH_REFCHECK_GRID_MULTI]++;
         }
@@ -641,13 +664,18 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
             h.n_groups = out[p.task].n_ungapped;
             h.g_off = g_off[p.task];
             h.row_off = row_off[p.task];
+            h.base = batch->base[ht.locus];
+            h.stride = batch->stride[ht.locus];
+            h.rows_off = ht.rows_off;
+            h.c0 = ht.c0;
+            h.alpha_flags = batch->flags[ht.locus];
             const ClusterOut &o = out[p.task];
             for (int g = 0; g < o.n_ungapped; ++g)
                 if (o.leader_len[g] >= kmer_size) seq_rows.push_back(o.leaders[g]);
         }
         ProblemRun run;
         rc = run_problems_host(ctx, s, hp, seq_rows, kmer_size, B[3].as<uint8_t>(), d_group, d_leadlen, d_leader_u, d_err,
-                               true, run);
+                               true, run, batch->d_packed, ctx->d_rows.as<int>());
         if (rc != MPRG_OK) return rc;
         st.swap(run.st);
         h_assign.swap(run.h_assign);

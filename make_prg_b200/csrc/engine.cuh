@@ -130,6 +130,10 @@ struct HostProblem {
     long long P;
     int w, R, n_groups;
     long long g_off, row_off;  // unpacked rows / per-row arrays of the task
+    // the task in the packed arena (whole-grid one-reference-like check reads the 4-bit rows directly)
+    long long base = 0;
+    int stride = 0, rows_off = -1, c0 = 0;
+    int alpha_flags = 0;  // alphabet flags of its locus (mprg_batch_flags)
 };
 struct ProblemRun {
     ClusterState *d_states = nullptr;  // final loop states, in problem order
@@ -139,7 +143,7 @@ struct ProblemRun {
 };
 int run_problems_host(mprg_ctx *ctx, cudaStream_t s, const std::vector<HostProblem> &hp, const std::vector<int> &seq_rows,
                       int kmer_size, const uint8_t *d_G, const int *d_group, const int *d_leadlen, int *d_leader_u,
-                      int *d_err, bool fetch, ProblemRun &run);
+                      int *d_err, bool fetch, ProblemRun &run, const uint8_t *d_packed, const int *d_rows_arena);
 // engine_dev.cu: the device-resident level loop over loci [l_begin, l_end)
 int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, int32_t max_nesting,
                     int32_t min_match_length, mprg_result *res, bool allow_trace, const int32_t *root_levels);

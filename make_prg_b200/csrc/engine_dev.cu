@@ -1155,6 +1155,8 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
                     std::vector<MemberProb> mp(np);
                     std::vector<long long> Pq(np);
                     std::vector<int> task_of(np), seq_rows((size_t)cnt->seqrows_total);
+                    std::vector<DTask> h_ct((size_t)n_ct);
+                    MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_ct.data(), ct.tasks, sizeof(DTask) * (size_t)n_ct, s));
                     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, kp.data(), pa.kp, sizeof(KmerProb) * np, s));
                     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, mp.data(), pa.mp, sizeof(MemberProb) * np, s));
                     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, Pq.data(), pa.P_of_prob, sizeof(long long) * np, s));
@@ -1176,12 +1178,26 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
                         h.n_groups = mp[q].n_groups;
                         h.g_off = kp[q].g_off;
                         h.row_off = mp[q].row_off;
+                        {
+                            const DTask &t = h_ct[(size_t)h.task];
+                            h.base = t.base;
+                            h.stride = t.stride;
+                            h.rows_off = t.rows_off;
+                            h.c0 = t.c0;
+                            // the locus of the task: the last one whose arena offset is not above the task's
+                            int lo = 0, hi = nl;
+                            while (hi - lo > 1) {
+                                const int mid = (lo + hi) >> 1;
+                                if (h_loci[mid].base <= t.base) lo = mid; else hi = mid;
+                            }
+                            h.alpha_flags = h_loci[lo].flags;
+                        }
                         seq_sorted.insert(seq_sorted.end(), seq_rows.begin() + kp[q].seq_off,
                                           seq_rows.begin() + kp[q].seq_off + kp[q].n);
                     }
                     ProblemRun run;
                     rc = run_problems_host(ctx, s, hp, seq_sorted, min_match_length, V[V_G].as<uint8_t>(), d_group,
-                                           d_leadlen, d_leader_u, d_err, false, run);
+                                           d_leadlen, d_leader_u, d_err, false, run, batch->d_packed, d_pool);
                     if (rc != MPRG_OK) return rc;
                     d_states = run.d_states;
                     d_assign = run.d_assign;

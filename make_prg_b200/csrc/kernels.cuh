@@ -136,6 +136,13 @@ cudaError_t launch_refcheck(cudaStream_t s, ClusterState *states, int n_probs, c
 cudaError_t launch_refcheck_big(cudaStream_t s, ClusterState *states, int q, int w, int rows, const uint8_t *G,
                                 const int *mem_off, const int *mem_rows, int *assign, uint8_t *maj, int max_clusters,
                                 int *flag_blocks);
+// refcheck_grid.cu: the same check straight from the 4-bit packed rows (loci whose alphabet is ACGT-):
+// bit-sliced counting, bound by one read of the member rows per pass; scratch: refgrid_scratch_ints ints
+long long refgrid_scratch_ints(int R, int w, int n_words, int K_max);
+cudaError_t launch_refcheck_grid(cudaStream_t s, ClusterState *states, int q, const DTask &t, int K_max,
+                                 const uint8_t *packed, const int *rows_arena, const int *mem_off, const int *mem_rows,
+                                 int *assign, uint8_t *maj, int *scratch, int n_member_rows, int *flags);
+cudaError_t launch_refcheck_big_control(cudaStream_t s, ClusterState *states, int q, int max_clusters, int *flags);
 long long kmeans_dscratch_doubles(long long n, long long F);
 long long kmeans_iscratch_ints(long long n);
 cudaError_t kmeans_upload_rand(const double *h_rand);
