@@ -77,32 +77,42 @@ if "5" in which:
               "property_checked": 32, "property_fail": prop_bad})
     del mats
 
-for tag, rows, cols, n_haps in (("4r", 2000, 5000, 400), ("4", 10000, 20000, 2000)):
+# config #4: ONE deep-clade locus (8 clades at 30 % divergence, 1 % private SNPs): the clustering loop runs KMeans
+# on every distinct row (n = rows, F = 4^7 = 16,384 k-mers).  "4r" = reduced (oracle run on the box),
+# "4" = BASELINE size (sha256 of the oracle's PRG from the build container, tests/golden/config4_deep_oracle.json),
+# "4flat" = round 1's generator (no deep clades: the loop ends before KMeans).
+import hashlib
+for tag, rows, cols in (("4r", 1500, 4000), ("4", 10000, 20000), ("4flat", 10000, 20000)):
     if tag not in which:
         continue
     t0 = time.perf_counter()
-    M = synth.synth_msa(rows, cols, 4_000_000, n_haps=n_haps, var_frac=0.04, private_snp=0.01)
+    if tag == "4flat":
+        M = synth.config_msa("4flat", 0)
+    elif tag == "4r":
+        M = synth.synth_deep_msa(rows, cols, 4_000_000, n_clades=8, n_haps=300)
+    else:
+        M = synth.config_msa(4, 0)
     gen = time.perf_counter() - t0
     try:
+        ctx.path_counts(reset=True)
         prgs, stats, ms_res, ms_e2e = gpu_build([M], 10, 7, reps=2)
-        d = {"config": tag, "what": f"one deep locus {rows} x {cols}, n_haps={n_haps}, 1% private SNPs, -N 10 -L 7",
-             "ok": int(stats[0] == 0), "resident_ms": ms_res, "e2e_ms": ms_e2e, "prg_len": len(prgs[0]), "gen_s": gen}
-        import hashlib
+        d = {"config": tag, "what": f"one deep locus {rows} x {cols}, -N 10 -L 7", "ok": int(stats[0] == 0),
+             "resident_ms": ms_res, "e2e_ms": ms_e2e, "prg_len": len(prgs[0]), "gen_s": gen,
+             "paths": ctx.path_counts(reset=True)}
         d["prg_sha256"] = hashlib.sha256(prgs[0].encode()).hexdigest()
+        gname = {"4r": "deep.json", "4": "config4_deep_oracle.json", "4flat": "config4_oracle.json"}[tag]
+        gold = json.loads((REPO / "tests" / "golden" / gname).read_text())
         if tag == "4r":
-            bad, dt, _ = check([M], prgs, 10, 7, 1, 0)
-            d.update({"oracle_mismatch": bad, "oracle_s": dt})
+            gold = gold["deep_1500"]
+            d["reference_s"] = gold["reference_seconds"]
         else:
-            g = REPO / "tests" / "golden" / "config4_oracle.json"
-            if g.exists():  # oracle run of the full locus in the build container (sha256 of its PRG)
-                gold = json.loads(g.read_text())
-                d.update({"oracle_mismatch": int(gold["prg_sha256"] != d["prg_sha256"]),
-                          "oracle_s": gold["oracle_seconds_1core"]})
+            d["oracle_s"] = gold["oracle_seconds_1core"]
+        d["oracle_mismatch"] = int(gold["prg_sha256"] != d["prg_sha256"])
     except Exception as e:  # report, do not hide
         d = {"config": tag, "error": repr(e)[:500], "gen_s": gen}
     emit(d)
 
 (REPO / "gpurun_out").mkdir(exist_ok=True)
-with open(REPO / "gpurun_out" / "configs_r1.json", "a") as fh:
+with open(REPO / "gpurun_out" / "configs_r2.json", "a") as fh:
     for d in out:
         fh.write(json.dumps(d) + "\n")
