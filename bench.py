@@ -556,6 +556,7 @@ def main():
             import files_e2e
 
             files = {"one_batch": files_e2e.measure(n_loci, reps=5),
+                     "one_batch_with_update_ds": files_e2e.measure(n_loci, reps=3, update_ds=True),
                      "pipelined_x4": files_e2e.measure(n_loci, reps=3, copies=4)}
         except Exception as err:  # the headline numbers above do not depend on this pass
             files = {"error": repr(err)}

@@ -300,10 +300,20 @@ int mprg_prg_to_gfa(const char *prg, int64_t length, char *out, int64_t capacity
 /* this writer produces one PART of a run (one GPU shard): archives even for a single locus; the parts are
  * turned into the final files by mprg_merge_outputs */
 #define MPRG_WRITE_PART 8
+/* mprg_merge_outputs only: also merge the parts' <prefix>.update_DS.zip archives */
+#define MPRG_WRITE_DS 16
 typedef struct mprg_writer mprg_writer;
 int mprg_writer_open(const char *output_prefix, int32_t what, mprg_writer **out);
 int mprg_writer_add(mprg_writer *w, const mprg_result *res, const int32_t *h_loci, const char *const *names,
                     int32_t n, int32_t n_threads);
+/* <prefix>.update_DS.zip (prg_builder.py:145-147, input_output_files.py:95-104): one member per locus, named by
+ * the locus, holding what its PrgBuilder is made of as tables (pre-order node table, row subsets, record titles,
+ * the root alignment as 4-bit packed rows, the PRG string; layout "MPRGDS01" in csrc/hostio.cpp) instead of a
+ * pickle of Python objects -- the Python host builds the objects on load.  msas: the loader's set the result was
+ * built from; h_loci index both. */
+int mprg_writer_add_ds(mprg_writer *w, const mprg_result *res, const mprg_msa_set *msas, const int32_t *h_loci,
+                       const char *const *names, int32_t n, int32_t max_nesting, int32_t min_match_length,
+                       int32_t n_threads);
 /* finishes the files and frees the writer on success; on failure read mprg_writer_error, then abort */
 int mprg_writer_close(mprg_writer *w, int64_t *n_loci, int64_t *bytes_written);
 void mprg_writer_abort(mprg_writer *w);

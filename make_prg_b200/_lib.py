@@ -102,6 +102,7 @@ SIGNATURES = {
     "mprg_prg_to_gfa": (C.c_int, [P, I64, P, I64, C.POINTER(I64)]),
     "mprg_writer_open": (C.c_int, [C.c_char_p, I32, C.POINTER(P)]),
     "mprg_writer_add": (C.c_int, [P, P, P, P, I32, I32]),
+    "mprg_writer_add_ds": (C.c_int, [P, P, P, P, P, I32, I32, I32, I32]),
     "mprg_writer_close": (C.c_int, [P, C.POINTER(I64), C.POINTER(I64)]),
     "mprg_writer_abort": (None, [P]),
     "mprg_writer_error": (C.c_char_p, [P]),

@@ -1515,6 +1515,9 @@ struct mprg_writer {
     int64_t n_added = 0, bytes = 0;
     ZipFile zbin, zgfa;
     bool zips_open = false;
+    ZipFile zds;  // <prefix>.update_DS.zip: one table-shaped member per locus (mprg_writer_add_ds)
+    bool ds_open = false;
+    int64_t n_ds = 0;
 };
 
 extern "C" int mprg_encode_prg(const char *prg, int64_t length, uint32_t *out, int64_t capacity, int64_t *n) {
@@ -1669,6 +1672,104 @@ extern "C" int mprg_writer_add(mprg_writer *w, const mprg_result *res, const int
     return MPRG_OK;
 }
 
+// ---- update_DS archive (prg_builder.py:145-147, input_output_files.py:95-104) ---------------------------------
+// One member per locus, named by the locus, holding what a PrgBuilder is made of as TABLES instead of a pickle
+// of Python objects: the pre-order node table, the row subsets, the record titles, the root alignment (4-bit
+// packed rows) and the PRG string.  make_prg_b200.prg_builder.PrgBuilder.deserialize_from_bytes builds the
+// objects on load; make_prg_b200/utils/reference_export.py turns the archive into the reference's pickles
+// where Biopython is installed.  Layout (little endian):
+//   char magic[8] = "MPRGDS01"
+//   int32 max_nesting, min_match_length, n_rows, n_cols, n_nodes, n_sites, packed_stride, reserved
+//   int64 pool_len, titles_len, prg_len
+//   int32 kind[n], parent[n], nesting_level[n], c0[n], c1[n], n_rows[n], n_children[n]; int64 row_off[n]
+//   int32 pool[pool_len]; titles (joined by '\n'); packed rows (n_rows * packed_stride); prg
+extern "C" int mprg_writer_add_ds(mprg_writer *w, const mprg_result *res, const mprg_msa_set *msas,
+                                  const int32_t *h_loci, const char *const *names, int32_t n, int32_t max_nesting,
+                                  int32_t min_match_length, int32_t n_threads) {
+    if (!w || !res || !msas || n < 0 || (n > 0 && (!h_loci || !names))) return MPRG_E_BAD_ARG;
+    if (n == 0) return MPRG_OK;
+    const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("MPRG_NO_AVX2");
+    std::vector<std::string> blobs((size_t)n);
+    std::vector<uint32_t> crcs((size_t)n);
+    std::vector<int> rcs((size_t)n, MPRG_OK);
+    parallel_for(n, n_threads, [&](int i) {
+        const int l = h_loci[i];
+        if (l < 0 || l >= msas->n || l >= mprg_result_n_loci(res)) {
+            rcs[(size_t)i] = MPRG_E_BAD_ARG;
+            return;
+        }
+        const int32_t n_nodes = mprg_result_n_nodes(res, l);
+        const int64_t pool_len = mprg_result_row_pool_size(res, l);
+        const int32_t rows = msas->n_rows[(size_t)l], cols = msas->n_cols[(size_t)l];
+        const int64_t stride = packed_stride(cols);
+        int64_t prg_len = 0;
+        const char *prg = mprg_result_prg(res, l, &prg_len);
+        const std::string &titles = msas->titles[(size_t)l];
+        const size_t header = 8 + 8 * 4 + 3 * 8;
+        const size_t total = header + (size_t)n_nodes * (7 * 4 + 8) + (size_t)pool_len * 4 + titles.size() +
+                             (size_t)rows * (size_t)stride + (size_t)prg_len;
+        std::string &b = blobs[(size_t)i];
+        b.resize(total);
+        char *p = &b[0];
+        memcpy(p, "MPRGDS01", 8);
+        int32_t h32[8] = {max_nesting, min_match_length, rows, cols, n_nodes, mprg_result_n_sites(res, l), (int32_t)stride, 0};
+        memcpy(p + 8, h32, sizeof(h32));
+        int64_t h64[3] = {pool_len, (int64_t)titles.size(), prg_len};
+        memcpy(p + 8 + sizeof(h32), h64, sizeof(h64));
+        char *q = p + header;
+        // int32/int64 stores through memcpy-free aligned views are not guaranteed: use temporaries
+        std::vector<int32_t> cols32((size_t)std::max(n_nodes, 1) * 7);
+        std::vector<int64_t> roff((size_t)std::max(n_nodes, 1));
+        int32_t *kind = cols32.data(), *parent = kind + n_nodes, *level = parent + n_nodes, *c0 = level + n_nodes;
+        int32_t *c1 = c0 + n_nodes, *nr = c1 + n_nodes, *nch = nr + n_nodes;
+        if (n_nodes > 0 && mprg_result_nodes(res, l, kind, parent, level, c0, c1, nr, roff.data(), nch) != MPRG_OK) {
+            rcs[(size_t)i] = MPRG_E_INTERNAL;
+            return;
+        }
+        memcpy(q, cols32.data(), (size_t)n_nodes * 7 * 4);
+        q += (size_t)n_nodes * 7 * 4;
+        memcpy(q, roff.data(), (size_t)n_nodes * 8);
+        q += (size_t)n_nodes * 8;
+        if (pool_len > 0) {
+            std::vector<int32_t> pool((size_t)pool_len);
+            mprg_result_row_pool(res, l, pool.data());
+            memcpy(q, pool.data(), (size_t)pool_len * 4);
+            q += (size_t)pool_len * 4;
+        }
+        memcpy(q, titles.data(), titles.size());
+        q += titles.size();
+        if (rows > 0 && stride > 0) {
+            if (msas->packed) {
+                memcpy(q, msas->packed + msas->packed_offsets[(size_t)l], (size_t)rows * (size_t)stride);
+            } else {
+                pack_matrix(msas->ascii + msas->offsets[(size_t)l], rows, cols, (uint8_t *)q, avx2);
+            }
+            q += (size_t)rows * (size_t)stride;
+        }
+        if (prg_len > 0) memcpy(q, prg, (size_t)prg_len);
+        crcs[(size_t)i] = (uint32_t)crc32(0L, (const Bytef *)b.data(), (uInt)b.size());
+    });
+    for (int i = 0; i < n; ++i)
+        if (rcs[(size_t)i] != MPRG_OK) {
+            w->err = std::string("cannot serialise the update data of ") + names[i];
+            return rcs[(size_t)i];
+        }
+    if (!w->ds_open) {
+        if (!w->zds.open_path(w->prefix + ".update_DS.zip")) {
+            w->err = "cannot create " + w->prefix + ".update_DS.zip: " + strerror(errno);
+            return MPRG_E_INTERNAL;
+        }
+        w->ds_open = true;
+    }
+    for (int i = 0; i < n; ++i)
+        if (!w->zds.add(names[i], blobs[(size_t)i].data(), blobs[(size_t)i].size(), crcs[(size_t)i])) {
+            w->err = "cannot write " + w->prefix + ".update_DS.zip: " + strerror(errno);
+            return MPRG_E_INTERNAL;
+        }
+    w->n_ds += n;
+    return MPRG_OK;
+}
+
 extern "C" int mprg_writer_close(mprg_writer *w, int64_t *n_loci, int64_t *bytes_written) {
     if (!w) return MPRG_E_BAD_ARG;
     int rc = MPRG_OK;
@@ -1719,6 +1820,14 @@ extern "C" int mprg_writer_close(mprg_writer *w, int64_t *n_loci, int64_t *bytes
             if (rc && w->err.empty()) w->err = "cannot finish the archives of " + w->prefix;
         }
     }
+    if (w->ds_open) {
+        if (!w->zds.finish()) {
+            rc = MPRG_E_INTERNAL;
+            if (w->err.empty()) w->err = "cannot finish " + w->prefix + ".update_DS.zip";
+        }
+        bytes += (int64_t)w->zds.pos;
+        w->ds_open = false;
+    }
     if (n_loci) *n_loci = w->n_added;
     if (bytes_written) *bytes_written = bytes;
     if (rc == MPRG_OK) delete w;  // on failure the caller reads mprg_writer_error, then mprg_writer_abort
@@ -1729,6 +1838,7 @@ extern "C" void mprg_writer_abort(mprg_writer *w) {
     if (!w) return;
     w->zbin.discard();  // closes and removes the unfinished archives
     w->zgfa.discard();
+    w->zds.discard();
     delete w;
 }
 
@@ -1738,7 +1848,7 @@ extern "C" void mprg_writer_abort(mprg_writer *w) {
 // (input_output_files.py:113-135).  Parts that do not exist hold no locus.  The parts are removed afterwards.
 extern "C" int mprg_merge_outputs(const char *const *part_prefixes, int32_t n_parts, const char *output_prefix,
                                   int32_t what, int64_t *n_loci, char *err_buf, int64_t err_capacity) {
-    if (!part_prefixes || n_parts < 0 || !output_prefix || (what & ~7) || what == 0) return MPRG_E_BAD_ARG;
+    if (!part_prefixes || n_parts < 0 || !output_prefix || (what & ~(7 | MPRG_WRITE_DS)) || what == 0) return MPRG_E_BAD_ARG;
     std::string err;
     auto fail = [&](const std::string &m) {
         if (err_buf && err_capacity > 0) {
@@ -1795,6 +1905,25 @@ extern "C" int mprg_merge_outputs(const char *const *part_prefixes, int32_t n_pa
             if (!zf.finish()) return fail("cannot finish " + out + k.zip_ext);
         }
         for (const std::string &p : parts) unlink(p.c_str());
+    }
+    // ---- update_DS archives: always an archive, members appended part by part ----
+    if (what & MPRG_WRITE_DS) {
+        std::vector<std::string> parts;
+        for (int i = 0; i < n_parts; ++i) {
+            const std::string p = std::string(part_prefixes[i]) + ".update_DS.zip";
+            if (exists(p)) parts.push_back(p);
+        }
+        if (!parts.empty()) {
+            ZipFile zf;
+            if (!zf.open_path(out + ".update_DS.zip")) return fail("cannot create " + out + ".update_DS.zip: " + strerror(errno));
+            for (const std::string &p : parts)
+                if (!zf.append_archive(p, err)) {
+                    zf.discard();
+                    return fail(err);
+                }
+            if (!zf.finish()) return fail("cannot finish " + out + ".update_DS.zip");
+            for (const std::string &p : parts) unlink(p.c_str());
+        }
     }
     // ---- .prg.fa: every part is sorted by "<name>.prg.fa"; merge ----
     if (what & MPRG_WRITE_PRG) {

@@ -18,7 +18,7 @@ from .utils import io_utils
 
 LOAD_OK, LOAD_NO_RECORDS, LOAD_RAGGED, LOAD_IO_ERROR, LOAD_NOT_ASCII = 0, 1, 2, 3, 4
 FLAG_HAS_N, FLAG_DUPLICATE_IDS = 1, 2
-WRITE_PRG, WRITE_BIN, WRITE_GFA, WRITE_PART = 1, 2, 4, 8
+WRITE_PRG, WRITE_BIN, WRITE_GFA, WRITE_PART, WRITE_DS = 1, 2, 4, 8, 16
 
 
 def default_threads():
@@ -276,11 +276,12 @@ class PrgStrings:
             pass
 
 
-def merge_outputs(part_prefixes, output_prefix, prg=True, binary=True, gfa=True):
-    """Final .prg.fa / .prg.bin(.zip) / .prg.gfa(.zip) from the parts of a sharded run (mprg_merge_outputs);
-    returns the number of loci.  The parts are removed."""
+def merge_outputs(part_prefixes, output_prefix, prg=True, binary=True, gfa=True, update_ds=False):
+    """Final .prg.fa / .prg.bin(.zip) / .prg.gfa(.zip) (and .update_DS.zip) from the parts of a sharded run
+    (mprg_merge_outputs); returns the number of loci.  The parts are removed."""
     lib = _lib.load()
     what = (WRITE_PRG if prg else 0) | (WRITE_BIN if binary else 0) | (WRITE_GFA if gfa else 0)
+    what |= WRITE_DS if update_ds else 0
     arr, _keep = _c_strings([os.fspath(p) for p in part_prefixes])
     n = C.c_int64()
     err = C.create_string_buffer(1024)
@@ -318,6 +319,18 @@ class OutputWriter:
             self.abort()
             if rc > 0:
                 _raise_encoding(rc, message)
+            raise OSError(message)
+
+    def add_ds(self, result, msas, loci, names, max_nesting, min_match_length):
+        """Appends the update data of these loci (tables: node table, row subsets, titles, packed root alignment,
+        PRG) to <prefix>.update_DS.zip (mprg_writer_add_ds); msas: the MsaSet the result was built from."""
+        loci = np.ascontiguousarray(loci, np.int32)
+        arr, _keep = _c_strings(names)
+        rc = self.lib.mprg_writer_add_ds(self.handle, result.handle, msas.handle, ptr(loci), C.cast(arr, C.c_void_p),
+                                         len(loci), max_nesting, min_match_length, self.threads)
+        if rc != 0:
+            message = self.lib.mprg_writer_error(self.handle).decode()
+            self.abort()
             raise OSError(message)
 
     def close(self):

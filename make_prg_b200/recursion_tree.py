@@ -190,11 +190,79 @@ class LeafNode(RecursiveTreeNode):
             if do_indexing:
                 self.prg_builder.update_PRG_index(start, end, node=self)
 
+    # ---- update methods (make_prg/recursion_tree.py:303-388) --------------------------------------------
+    def add_data_to_batch_update(self, update_data):
+        """Process the given update data and add a new sequence to self.new_sequences (:305-343)."""
+        interval = update_data.ml_path_node_key
+        if interval not in self.indexed_PRG_intervals:
+            raise UpdateError(f"PRG interval {interval} not found in indexed PRG intervals for node: "
+                              f"{self.indexed_PRG_intervals}")
+        parts = []
+        for prg_interval in sorted(self.indexed_PRG_intervals):
+            if prg_interval == interval:
+                parts.append(update_data.new_node_sequence)
+            else:
+                try:
+                    parts.append(update_data.ml_path.get_node_given_interval_in_PRG_space(prg_interval).sequence)
+                except Exception as err:  # MLPathError of the (out-of-scope) denovo-path parser
+                    if type(err).__name__ != "MLPathError":
+                        raise
+        self.new_sequences.add("".join(parts))
+
     def add_indexed_PRG_interval(self, interval):
         self.indexed_PRG_intervals.add(interval)
 
+    def batch_update(self):
+        if len(self.new_sequences) == 0:
+            return
+        self._update_leaf()
+
+    def updated_alignment(self):
+        """The leaf's alignment with its new sequences added by the builder's aligner (:362-368)."""
+        assert self.prg_builder.aligner is not None, "Cannot make updates without a Multiple Sequence Aligner."
+        return self.prg_builder.aligner.get_updated_alignment(current_alignment=self.alignment,
+                                                              new_sequences=self.new_sequences)
+
+    def swap_in(self, updated_child):
+        """Puts the re-built node in this leaf's place and invalidates the builder's PRG index (:378-388)."""
+        if self.is_root():
+            self.prg_builder.replace_root(updated_child)
+        else:
+            self.parent.replace_child(self, updated_child)
+        self.prg_builder.clear_PRG_index()
+
+    def _update_leaf(self):
+        """Update this leaf, replacing it by an updated node, which can be of a different subclass (:353-388)."""
+        updated_child = NodeFactory.build(self.updated_alignment(), self.prg_builder, self.parent)
+        self.swap_in(updated_child)
+
     def clear_PRG_interval_index(self):
         self.indexed_PRG_intervals.clear()
+
+
+def batch_update_leaves(leaves, ctx=None):
+    """LeafNode.batch_update for MANY leaves (of any number of loci) with ONE device batch per (max_nesting,
+    min_match_length): every updated alignment is re-built below its leaf's parent in the same level-synchronous
+    launches (mprg_build_sub), then swapped in -- the batched form of `make_prg update`'s re-partitioning
+    (recursion_tree.py:345-388; leaves are visited in the given order, so node ids are handed out as a loop of
+    _update_leaf calls would hand them out).  Returns the number of leaves updated."""
+    todo = [leaf for leaf in leaves if len(leaf.new_sequences) > 0]
+    groups = {}
+    for leaf in todo:
+        b = leaf.prg_builder
+        groups.setdefault((b.max_nesting, b.min_match_length), []).append(leaf)
+    for (max_nesting, mml), group in groups.items():
+        alignments = [leaf.updated_alignment() for leaf in group]
+        levels = [-1 if leaf.parent is None else leaf.parent.nesting_level for leaf in group]
+        results = engine.build_matrices([a.matrix for a in alignments], max_nesting, mml, ctx=ctx,
+                                        parent_levels=levels)
+        for leaf, alignment, result in zip(group, alignments, results):
+            builder = leaf.prg_builder
+            result.raise_for_status(builder.locus_name)
+            first = builder.next_node_id
+            builder.next_node_id += result.n_nodes
+            leaf.swap_in(nodes_from_table(alignment, result.nodes, builder, leaf.parent, first))
+    return len(todo)
 
 
 _CLASSES = {NODE_LEAF: LeafNode, NODE_INTERVAL: MultiIntervalNode, NODE_CLUSTER: MultiClusterNode}

@@ -194,7 +194,8 @@ def iter_built_chunks(input_files, options, device_ordinal=0, chunks=None):
 
 
 def _update_ds_pickles(names, msas, res, ok, options):
-    """(name, pickled PrgBuilder) for the update_DS archive (prg_builder.py:145-147)."""
+    """(name, pickled PrgBuilder): the update_DS members as Python pickles (prg_builder.py:145-147) -- the
+    MPRG_PICKLE_DS=1 alternative to the table-shaped records of the native writer."""
     import pickle
 
     out = []
@@ -212,7 +213,9 @@ def _update_ds_pickles(names, msas, res, ok, options):
 
 def build_and_write(input_files, options, device_ordinal=0, output_prefix=None, part=False):
     """One GPU: the whole run, files in -> final files out.  Returns the number of PRGs written.
-    The update_DS archive (Python PrgBuilder pickles) is written unless options.skip_update_ds.
+    The update_DS archive is written by the library as table-shaped records (mprg_writer_add_ds; objects are
+    built on load, PrgBuilderZipDatabase) unless options.skip_update_ds; MPRG_PICKLE_DS=1 writes pickled
+    PrgBuilder objects instead.
     part: the files are one part of a sharded run (hostio.merge_outputs makes the final files).
     Every file appears under its final name only when it is complete; an aborted run leaves none."""
     from concurrent.futures import ThreadPoolExecutor
@@ -223,10 +226,16 @@ def build_and_write(input_files, options, device_ordinal=0, output_prefix=None, 
     chunks = cut_chunks(input_files)
     writer = hostio.OutputWriter(prefix, prg=ot.prg, binary=ot.binary, gfa=ot.gfa,
                                  threads=side_threads(len(chunks), writer=True), part=part)
+    pickle_ds = want_ds and bool(os.environ.get("MPRG_PICKLE_DS"))
     ds_zip = None
     ds_tmp = f"{prefix}.update_DS.zip.tmp{os.getpid()}"
     n_ok = 0
     pending = None  # (future, msas, res): the chunk being encoded / written on the writer thread
+
+    def write_chunk(res, msas, ok, ok_names):
+        writer.add(res, ok, ok_names)
+        if want_ds and not pickle_ds and len(ok):
+            writer.add_ds(res, msas, ok, ok_names, options.max_nesting, options.min_match_length)
 
     def finish(p):
         fut, msas, res = p
@@ -242,14 +251,14 @@ def build_and_write(input_files, options, device_ordinal=0, output_prefix=None, 
                 if pending is not None:
                     finish(pending)
                     pending = None
-                if want_ds and ok:
+                if pickle_ds and ok:
                     if ds_zip is None:
                         ds_zip = zipfile.ZipFile(ds_tmp, "w")
                     for name, blob in _update_ds_pickles(names, msas, res, ok, options):
                         ds_zip.writestr(name, blob)
                 n_ok += len(ok)
                 ok_names = names if len(ok) == len(names) else [names[i] for i in ok]
-                pending = (pool.submit(writer.add, res, ok, ok_names), msas, res)
+                pending = (pool.submit(write_chunk, res, msas, ok, ok_names), msas, res)
             if pending is not None:
                 finish(pending)
                 pending = None
@@ -331,18 +340,8 @@ def merge_parts(part_prefixes, options):
     """Final files from the shards' parts: native merge of .prg.fa / archives, update_DS members appended."""
     ot = options.output_type
     prefix = options.output_prefix
-    n = hostio.merge_outputs(part_prefixes, prefix, prg=ot.prg, binary=ot.binary, gfa=ot.gfa)
-    ds_parts = [p + ".update_DS.zip" for p in part_prefixes if os.path.exists(p + ".update_DS.zip")]
-    if ds_parts:
-        tmp = f"{prefix}.update_DS.zip.tmp{os.getpid()}"
-        with zipfile.ZipFile(tmp, "w") as out:
-            for part in ds_parts:
-                with zipfile.ZipFile(part) as zf:
-                    for info in zf.infolist():
-                        out.writestr(info.filename, zf.read(info))
-                os.unlink(part)
-        os.replace(tmp, prefix + ".update_DS.zip")
-    return n
+    want_ds = ot.prg and not getattr(options, "skip_update_ds", False)
+    return hostio.merge_outputs(part_prefixes, prefix, prg=ot.prg, binary=ot.binary, gfa=ot.gfa, update_ds=want_ds)
 
 
 def _run_sharded(input_files, options, gpus):

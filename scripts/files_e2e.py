@@ -51,7 +51,7 @@ def replicate(paths, copies, directory):
     return out
 
 
-def measure(n_loci=1000, reps=5, copies=1, python_io=False):
+def measure(n_loci=1000, reps=5, copies=1, python_io=False, update_ds=False):
     root = Path(os.environ.get("MPRG_FILES_DIR", "/dev/shm/mprg_files"))
     paths = write_fastas(root / f"config2_{n_loci}", n_loci)
     if copies > 1:
@@ -68,7 +68,7 @@ def measure(n_loci=1000, reps=5, copies=1, python_io=False):
     out.mkdir(parents=True)
     opts = Namespace(input=str(root), suffix="", output_prefix=str(out / "run"), alignment_format="fasta",
                      max_nesting=5, min_match_length=7, output_type=OutputType("a"), force=True, threads=1,
-                     gpus=1, skip_update_ds=True)
+                     gpus=1, skip_update_ds=not update_ds)
     from loguru import logger
 
     logger.remove()
@@ -88,7 +88,9 @@ def measure(n_loci=1000, reps=5, copies=1, python_io=False):
             "chunks": len(from_msa.cut_chunks(paths)), "host_cores": os.cpu_count(),
             "timing": "host wall clock around build_and_write (files in page cache, outputs to tmpfs), "
                       "warm pinned-buffer pool",
-            "outputs": "prg.fa + prg.bin.zip + prg.gfa.zip (no update_DS pickles)"}
+            "outputs": "prg.fa + prg.bin.zip + prg.gfa.zip" +
+                       (" + update_DS.zip (table-shaped records, the default -O a run)" if update_ds
+                        else " (--skip-update-ds)")}
     if copies > 1:
         return line
     # stages, one after the other

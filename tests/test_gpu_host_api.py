@@ -131,10 +131,64 @@ def test_cli_sample_example_outputs_equal_truth(tmp_path):
             assert sorted(got.namelist()) == sorted(want.namelist())
             for member in want.namelist():
                 assert got.read(member) == want.read(member), member
+    # update_DS: table-shaped records written by the library, PrgBuilder objects built on load
+    from make_prg_b200.prg_builder import DS_MAGIC, PrgBuilder, PrgBuilderZipDatabase
+
     with zipfile.ZipFile(tmp_path / "sample_example.update_DS.zip") as zf:
         assert sorted(zf.namelist()) == ["GC00006032", "GC00010897"]
+        assert zf.read("GC00006032")[:8] == DS_MAGIC
+    db = PrgBuilderZipDatabase(tmp_path / "sample_example.update_DS.zip")
+    db.load()
+    assert db.get_number_of_loci() == 2 and db.get_loci_names() == ["GC00006032", "GC00010897"]
+    for locus in db.get_loci_names():
+        b = db.get_PrgBuilder(locus)
+        assert b.build_prg() == truth_multi("sample_example")[locus]
+        # the same object as a build through the Python API of the locus' file
+        direct = PrgBuilder(locus, REF / "sample_example" / f"{locus}.fa", "fasta", 5, 7)
+        direct.build_prg()
+        assert b == direct and b.prg_index.keys() == direct.prg_index.keys()
+        assert [r.id for r in b.root.alignment] == [r.id for r in direct.root.alignment]
+        assert pickle.loads(pickle.dumps(b, protocol=4)) == b
+    assert db == db
+    db.close()
+
+
+def test_cli_pickled_update_ds_and_sharded_merge_of_archives(tmp_path, monkeypatch):
+    """MPRG_PICKLE_DS=1 keeps the pickled-object members; parts of a sharded run merge their update_DS archives."""
+    from make_prg_b200 import hostio
+    from make_prg_b200.prg_builder import PrgBuilderZipDatabase
+
+    monkeypatch.setenv("MPRG_PICKLE_DS", "1")
+    _run_cli(tmp_path, REF / "sample_example", "pk")
+    with zipfile.ZipFile(tmp_path / "pk.update_DS.zip") as zf:
         b = pickle.loads(zf.read("GC00006032"))
         assert b.build_prg() == truth_multi("sample_example")["GC00006032"]
+    monkeypatch.delenv("MPRG_PICKLE_DS")
+    _run_cli(tmp_path, REF / "sample_example", "tb")
+    pk, tb = PrgBuilderZipDatabase(tmp_path / "pk.update_DS.zip"), PrgBuilderZipDatabase(tmp_path / "tb.update_DS.zip")
+    pk.load(), tb.load()
+    assert pk == tb
+    pk.close(), tb.close()
+    # two parts (one locus each) -> one archive with both members
+    from make_prg_b200.subcommands import from_msa
+
+    files = sorted((REF / "sample_example").glob("*.fa"))
+    opts = _run_cli(tmp_path, REF / "sample_example", "whole", force=True)
+    parts = []
+    for k, f in enumerate(files):
+        from_msa.build_and_write([f], opts, output_prefix=str(tmp_path / f"part{k}"), part=True)
+        parts.append(str(tmp_path / f"part{k}"))
+    opts.output_prefix = str(tmp_path / "merged")
+    assert from_msa.merge_parts(parts, opts) == 2
+    for ext in (".prg.fa", ".update_DS.zip", ".prg.bin.zip", ".prg.gfa.zip"):
+        got, want = tmp_path / f"merged{ext}", tmp_path / f"whole{ext}"
+        if ext == ".prg.fa":
+            assert got.read_bytes() == want.read_bytes()
+        else:
+            with zipfile.ZipFile(got) as a, zipfile.ZipFile(want) as b:
+                assert sorted(a.namelist()) == sorted(b.namelist())
+                for m in b.namelist():
+                    assert a.read(m) == b.read(m), (ext, m)
 
 
 def test_cli_single_msa_and_skip_semantics(tmp_path):
@@ -251,3 +305,83 @@ def test_packed_host_rows_equal_device_pack_and_text_build():
         assert res_packed.prg(i) == res_text.prg(i)
         assert np.array_equal(b2.packed(i), packed[i])
     assert res_text.status(2) == 1 and res_text.status(0) == 0
+
+
+class _VectorAligner:
+    """Stands in for the MSA aligner of `make_prg update`: hands back the alignment of a golden vector."""
+
+    def __init__(self):
+        self.next = {}
+
+    def get_updated_alignment(self, current_alignment, new_sequences):
+        return self.next[frozenset(new_sequences)]
+
+
+def test_leaf_update_through_sub_builds(tmp_path):
+    """LeafNode._update_leaf / batch_update / batch_update_leaves (recursion_tree.py:345-388) driven by the 216
+    NodeFactory.build(alignment, builder, parent_node) vectors of the unmodified reference: the leaf is replaced
+    by the re-built node (any subclass), node ids count on from next_node_id, the PRG index is invalidated, and
+    the batched form (one device batch for all leaves) gives the same trees as one call per leaf."""
+    from helpers import sub_build_cases
+    from make_prg_b200.msa import MSA, SeqRecord
+    from make_prg_b200.prg_builder import PrgBuilder
+    from make_prg_b200.recursion_tree import LeafNode, MultiIntervalNode, batch_update_leaves
+
+    def dump(node):
+        out = []
+
+        def walk(n):
+            out.append([type(n).__name__, n.node_id, n.nesting_level, len(n.alignment),
+                        n.alignment.get_alignment_length(), len(n.children)])
+            for c in n.children:
+                walk(c)
+
+        walk(node)
+        return out
+
+    def make_case(r, k):
+        """A builder whose root (nesting level = the vector's parent level) holds one leaf to be updated."""
+        builder = PrgBuilder.__new__(PrgBuilder)
+        builder._locus_name = f"locus{k}"
+        builder.max_nesting, builder.min_match_length = r["N"], r["L"]
+        builder.aligner = _VectorAligner()
+        builder.next_node_id = r["first_node_id"]
+        builder.site_num, builder.prg_index, builder.engine_prg = 5, {}, None
+        old = MSA([SeqRecord("ACGT", "old0"), SeqRecord("ACGA", "old1")])
+        root = MultiIntervalNode(r["parent_level"], old, None, builder, 0)
+        leaf = LeafNode(r["parent_level"], old, root, builder, 1)
+        root._children.append(leaf)
+        builder.root = root
+        builder.update_PRG_index(0, 4, leaf)
+        leaf.new_sequences = {f"NEW{k}"}
+        builder.aligner.next[frozenset(leaf.new_sequences)] = MSA(
+            [SeqRecord(s, f"s{i}") for i, s in enumerate(r["rows"])])
+        return builder, root, leaf
+
+    def check(builder, root, leaf, r):
+        node = root.children[0]
+        assert node is not leaf and node.parent is root and node.node_id == r["first_node_id"]
+        assert builder.next_node_id == r["next_node_id"] and builder.prg_index == {}
+        builder.site_num = 5
+        parts = []
+        node.preorder_traversal_to_build_prg(parts)
+        assert "".join(parts) == r["prg"]
+        assert dump(node) == [list(t) for t in r["tree"]]
+
+    cases = sub_build_cases()
+    assert len(cases) == 216
+    # one call per leaf (LeafNode.batch_update -> _update_leaf), on a sample
+    for k, r in enumerate(cases[::9]):
+        builder, root, leaf = make_case(r, k)
+        leaf.batch_update()
+        check(builder, root, leaf, r)
+    # all 216 leaves in one device batch per (N, L)
+    made = [make_case(r, k) for k, r in enumerate(cases)]
+    assert batch_update_leaves([leaf for _b, _r, leaf in made]) == 216
+    for (builder, root, leaf), r in zip(made, cases):
+        check(builder, root, leaf, r)
+    # a leaf without new sequences is left alone
+    builder, root, leaf = make_case(cases[0], 999)
+    leaf.new_sequences = set()
+    leaf.batch_update()
+    assert root.children[0] is leaf and batch_update_leaves([leaf]) == 0
