@@ -82,8 +82,15 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
+        // buffers grow level by level within a build and batch by batch across builds: double while that is cheap
+        // (every reallocation is a cudaFree that synchronises the device), a quarter of headroom above 1 GiB
+        size_t want = bytes < ((size_t)1 << 30) ? 2 * bytes + 256 : bytes + bytes / 4 + 256;
         cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess && want > bytes + 256) {
+            cudaGetLastError();
+            want = bytes + 256;
+            e = cudaMalloc(&p, want);
+        }
         if (e == cudaSuccess) cap = want;
         return e;
     }

@@ -38,7 +38,7 @@ struct DevCounters {
     int n_tasks, n_units;
     long long total_cols, total_iv, level_iters, sum_rw, sum_rows, max_rw, algo_bytes;
     int max_rows, n_ctasks;
-    long long g_total, row_total;
+    long long g_total, row_total, scratch_total;
     // clustering problems of the current level
     int np, max_n, n_big, n_rounds_pad;
     long long useq_total, ints_total, tab_total, x_total, memoff_total, memrows_total, assign_total, maj_total,
@@ -99,7 +99,7 @@ __global__ void level_begin_kernel(DevCounters *C) {
     C->n_units = 0;
     C->total_cols = C->total_iv = C->level_iters = C->sum_rw = C->sum_rows = C->max_rw = C->algo_bytes = 0;
     C->max_rows = C->n_ctasks = 0;
-    C->g_total = C->row_total = 0;
+    C->g_total = C->row_total = C->scratch_total = 0;
     C->np = C->max_n = C->n_big = 0;
     C->useq_total = C->ints_total = C->tab_total = C->x_total = C->memoff_total = C->memrows_total = 0;
     C->assign_total = C->maj_total = C->kmd_total = C->kmi_total = C->seqrows_total = C->max_elements = C->max_P = 0;
@@ -233,6 +233,7 @@ struct ClusterTaskArrays {
     int *R;
     int *node;           // node of the task
     int *want;           // nesting_level + 1 < max_nesting
+    long long *sc_off;   // scratch ints of expand_clusters (2 R + 32 per task)
 };
 
 __device__ __forceinline__ int first_row_of(const DNode &nd, const int *pool) {
@@ -297,6 +298,7 @@ expand_partition_kernel(DevCounters *C, const int *__restrict__ pending, DNode *
     const int q = warp_alloc(&C->n_ctasks, is_ct);
     const long long g0 = warp_alloc(&C->g_total, rw);
     const long long r0 = warp_alloc(&C->row_total, R);
+    const long long s0 = warp_alloc(&C->scratch_total, is_ct ? 2 * R + 32 : 0LL);
     if (!active) return;
     if (child0 + n_child > node_capacity || item0 + n_match > item_capacity) {
         atomicOr(&C->err, ERR_OVERFLOW);
@@ -351,6 +353,7 @@ expand_partition_kernel(DevCounters *C, const int *__restrict__ pending, DNode *
         ct.R[q] = nd.n_rows;
         ct.node[q] = ni;
         ct.want[q] = (nd.level + 1 < max_nesting) ? 1 : 0;
+        ct.sc_off[q] = s0;
     } else {
         loci[nd.locus - l0].status = 2;  // zero-column root: the reference trips an assertion here
     }
@@ -547,7 +550,9 @@ expand_clusters_kernel(DevCounters *C, ClusterTaskArrays ct, ProblemArrays pa, c
     // cluster index of every distinct ungapped sequence: KMeans label for the long ones, one cluster per
     // small one behind them; the cluster of row 0 moves to the front (merge_clusters), the others keep
     // their order
-    int *idx_of_group = scratch + 2 * ro + 32LL * q;  // nu ints
+    // (the region is allocated with the task: offsets derived from row_off and q would not be disjoint, the two
+    // are bump-allocated from different counters and need not come in the same order)
+    int *idx_of_group = scratch + ct.sc_off[q];  // nu ints
     int *cl_end = idx_of_group + R + 16;              // up to 10 + nu ints
     const int *lg = long_of_group + ro;
     const int *assign = assign_all + st->assign_off;
@@ -998,7 +1003,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         MPRG_CUDA(ctx, ctx->d_iv.reserve(sizeof(DInterval) * total_iv));
         MPRG_CUDA(ctx, ctx->d_ivcnt.reserve(sizeof(int) * (nt + 1)));
         // cluster-task arrays (bounded by the level's tasks), zero-filled: entries past n_ctasks are empty tasks
-        const size_t ct_misc_bytes = (sizeof(long long) * 2 + sizeof(int) * 8) * (size_t)nt + 64;
+        const size_t ct_misc_bytes = (sizeof(long long) * 3 + sizeof(int) * 8) * (size_t)nt + 64;
         MPRG_CUDA(ctx, V[V_CT_TASKS].reserve(sizeof(DTask) * (size_t)nt));
         MPRG_CUDA(ctx, V[V_CT_MISC].reserve(ct_misc_bytes));
         MPRG_CUDA(ctx, cudaMemsetAsync(V[V_CT_TASKS].p, 0, sizeof(DTask) * (size_t)nt, s));
@@ -1007,7 +1012,8 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         ct.tasks = V[V_CT_TASKS].as<DTask>();
         ct.g_off = V[V_CT_MISC].as<long long>();
         ct.row_off = ct.g_off + nt;
-        ct.R = reinterpret_cast<int *>(ct.row_off + nt);
+        ct.sc_off = ct.row_off + nt;
+        ct.R = reinterpret_cast<int *>(ct.sc_off + nt);
         ct.node = ct.R + nt;
         ct.want = ct.node + nt;
         int *d_nu = ct.want + nt, *d_ng = d_nu + nt;
@@ -1205,7 +1211,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
                 }
             }
             if (n_ct > 0) {
-                MPRG_CUDA(ctx, V[V_SCRATCH].reserve(sizeof(int) * (size_t)(2 * cnt->row_total + 32LL * n_ct + 64)));
+                MPRG_CUDA(ctx, V[V_SCRATCH].reserve(sizeof(int) * (size_t)(cnt->scratch_total + 64)));
                 expand_clusters_kernel<<<(n_ct + 3) / 4, 128, 0, s>>>(
                     d_cnt, ct, pa, d_states, d_assign, d_nu, d_ng, d_group, d_leaders, d_leader_u, V[V_SCRATCH].as<int>(),
                     V[V_NODES].as<DNode>(), d_loci, l_begin, V[V_POOL].as<int>(), V[nxt].as<int>(),

@@ -1689,13 +1689,27 @@ extern "C" int mprg_writer_add_ds(mprg_writer *w, const mprg_result *res, const 
     if (!w || !res || !msas || n < 0 || (n > 0 && (!h_loci || !names))) return MPRG_E_BAD_ARG;
     if (n == 0) return MPRG_OK;
     const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("MPRG_NO_AVX2");
-    std::vector<std::string> blobs((size_t)n);
-    std::vector<uint32_t> crcs((size_t)n);
-    std::vector<int> rcs((size_t)n, MPRG_OK);
+    // Every member is header + tables (small, built per locus) followed by the packed rows and the PRG, which
+    // are written straight from where they are: sizes first, then every locus is checksummed and written at its
+    // own offset by the host threads in parallel (pwrite), the archive's directory entries in locus order.
+    struct Member {
+        std::string head;  // header + node table + row pool + titles
+        const uint8_t *rows = nullptr;
+        std::vector<uint8_t> packed_here;  // rows packed now (text loader)
+        size_t rows_bytes = 0;
+        const char *prg = nullptr;
+        size_t prg_bytes = 0;
+        uint32_t crc = 0;
+        uint64_t offset = 0;
+        int rc = MPRG_OK;
+        size_t size() const { return head.size() + rows_bytes + prg_bytes; }
+    };
+    std::vector<Member> mem((size_t)n);
     parallel_for(n, n_threads, [&](int i) {
+        Member &m = mem[(size_t)i];
         const int l = h_loci[i];
         if (l < 0 || l >= msas->n || l >= mprg_result_n_loci(res)) {
-            rcs[(size_t)i] = MPRG_E_BAD_ARG;
+            m.rc = MPRG_E_BAD_ARG;
             return;
         }
         const int32_t n_nodes = mprg_result_n_nodes(res, l);
@@ -1703,27 +1717,24 @@ extern "C" int mprg_writer_add_ds(mprg_writer *w, const mprg_result *res, const 
         const int32_t rows = msas->n_rows[(size_t)l], cols = msas->n_cols[(size_t)l];
         const int64_t stride = packed_stride(cols);
         int64_t prg_len = 0;
-        const char *prg = mprg_result_prg(res, l, &prg_len);
+        m.prg = mprg_result_prg(res, l, &prg_len);
+        m.prg_bytes = (size_t)prg_len;
         const std::string &titles = msas->titles[(size_t)l];
         const size_t header = 8 + 8 * 4 + 3 * 8;
-        const size_t total = header + (size_t)n_nodes * (7 * 4 + 8) + (size_t)pool_len * 4 + titles.size() +
-                             (size_t)rows * (size_t)stride + (size_t)prg_len;
-        std::string &b = blobs[(size_t)i];
-        b.resize(total);
-        char *p = &b[0];
+        m.head.resize(header + (size_t)n_nodes * (7 * 4 + 8) + (size_t)pool_len * 4 + titles.size());
+        char *p = &m.head[0];
         memcpy(p, "MPRGDS01", 8);
         int32_t h32[8] = {max_nesting, min_match_length, rows, cols, n_nodes, mprg_result_n_sites(res, l), (int32_t)stride, 0};
         memcpy(p + 8, h32, sizeof(h32));
         int64_t h64[3] = {pool_len, (int64_t)titles.size(), prg_len};
         memcpy(p + 8 + sizeof(h32), h64, sizeof(h64));
         char *q = p + header;
-        // int32/int64 stores through memcpy-free aligned views are not guaranteed: use temporaries
         std::vector<int32_t> cols32((size_t)std::max(n_nodes, 1) * 7);
         std::vector<int64_t> roff((size_t)std::max(n_nodes, 1));
         int32_t *kind = cols32.data(), *parent = kind + n_nodes, *level = parent + n_nodes, *c0 = level + n_nodes;
         int32_t *c1 = c0 + n_nodes, *nr = c1 + n_nodes, *nch = nr + n_nodes;
         if (n_nodes > 0 && mprg_result_nodes(res, l, kind, parent, level, c0, c1, nr, roff.data(), nch) != MPRG_OK) {
-            rcs[(size_t)i] = MPRG_E_INTERNAL;
+            m.rc = MPRG_E_INTERNAL;
             return;
         }
         memcpy(q, cols32.data(), (size_t)n_nodes * 7 * 4);
@@ -1737,23 +1748,33 @@ extern "C" int mprg_writer_add_ds(mprg_writer *w, const mprg_result *res, const 
             q += (size_t)pool_len * 4;
         }
         memcpy(q, titles.data(), titles.size());
-        q += titles.size();
-        if (rows > 0 && stride > 0) {
+        m.rows_bytes = (size_t)rows * (size_t)stride;
+        if (m.rows_bytes) {
             if (msas->packed) {
-                memcpy(q, msas->packed + msas->packed_offsets[(size_t)l], (size_t)rows * (size_t)stride);
+                m.rows = msas->packed + msas->packed_offsets[(size_t)l];
             } else {
-                pack_matrix(msas->ascii + msas->offsets[(size_t)l], rows, cols, (uint8_t *)q, avx2);
+                m.packed_here.resize(m.rows_bytes);
+                pack_matrix(msas->ascii + msas->offsets[(size_t)l], rows, cols, m.packed_here.data(), avx2);
+                m.rows = m.packed_here.data();
             }
-            q += (size_t)rows * (size_t)stride;
         }
-        if (prg_len > 0) memcpy(q, prg, (size_t)prg_len);
-        crcs[(size_t)i] = (uint32_t)crc32(0L, (const Bytef *)b.data(), (uInt)b.size());
+        uLong crc = crc32(0L, (const Bytef *)m.head.data(), (uInt)m.head.size());
+        for (size_t at = 0; at < m.rows_bytes; at += (size_t)1 << 30)
+            crc = crc32(crc, (const Bytef *)m.rows + at, (uInt)std::min<size_t>(m.rows_bytes - at, (size_t)1 << 30));
+        for (size_t at = 0; at < m.prg_bytes; at += (size_t)1 << 30)
+            crc = crc32(crc, (const Bytef *)m.prg + at, (uInt)std::min<size_t>(m.prg_bytes - at, (size_t)1 << 30));
+        m.crc = (uint32_t)crc;
     });
-    for (int i = 0; i < n; ++i)
-        if (rcs[(size_t)i] != MPRG_OK) {
+    for (int i = 0; i < n; ++i) {
+        if (mem[(size_t)i].rc != MPRG_OK) {
             w->err = std::string("cannot serialise the update data of ") + names[i];
-            return rcs[(size_t)i];
+            return mem[(size_t)i].rc;
         }
+        if (mem[(size_t)i].size() > 0xFFFFFFFEull) {
+            w->err = std::string("update data of ") + names[i] + " exceeds 4 GiB";
+            return MPRG_E_INTERNAL;
+        }
+    }
     if (!w->ds_open) {
         if (!w->zds.open_path(w->prefix + ".update_DS.zip")) {
             w->err = "cannot create " + w->prefix + ".update_DS.zip: " + strerror(errno);
@@ -1761,11 +1782,70 @@ extern "C" int mprg_writer_add_ds(mprg_writer *w, const mprg_result *res, const 
         }
         w->ds_open = true;
     }
-    for (int i = 0; i < n; ++i)
-        if (!w->zds.add(names[i], blobs[(size_t)i].data(), blobs[(size_t)i].size(), crcs[(size_t)i])) {
-            w->err = "cannot write " + w->prefix + ".update_DS.zip: " + strerror(errno);
+    // local headers in order (small), data regions left as holes and filled in parallel
+    ZipFile &z = w->zds;
+    if (fflush(z.f) != 0) {
+        w->err = "cannot write " + w->prefix + ".update_DS.zip: " + strerror(errno);
+        return MPRG_E_INTERNAL;
+    }
+    const int fd = fileno(z.f);
+    std::vector<std::string> heads((size_t)n);
+    uint64_t pos = z.pos;
+    for (int i = 0; i < n; ++i) {
+        Member &m = mem[(size_t)i];
+        const std::string name = names[i];
+        if (name.size() > 0xFFFF) {
+            w->err = "locus name too long: " + name;
             return MPRG_E_INTERNAL;
         }
+        std::string &h = heads[(size_t)i];
+        ZipFile::le32(h, 0x04034b50u);
+        ZipFile::le16(h, 20);
+        ZipFile::le16(h, 0x0800);
+        ZipFile::le16(h, 0);
+        ZipFile::le16(h, z.dos_time);
+        ZipFile::le16(h, z.dos_date);
+        ZipFile::le32(h, m.crc);
+        ZipFile::le32(h, (uint32_t)m.size());
+        ZipFile::le32(h, (uint32_t)m.size());
+        ZipFile::le16(h, (uint16_t)name.size());
+        ZipFile::le16(h, 0);
+        h += name;
+        z.entries.push_back({name, m.crc, (uint32_t)m.size(), pos});
+        m.offset = pos;
+        pos += h.size() + m.size();
+    }
+    std::atomic<int> failed{0};
+    auto put = [&](const void *data, size_t len, uint64_t at) {
+        const char *p = (const char *)data;
+        while (len > 0) {
+            const ssize_t k = pwrite(fd, p, len, (off_t)at);
+            if (k <= 0) {
+                if (k < 0 && errno == EINTR) continue;
+                failed = errno ? errno : EIO;
+                return;
+            }
+            p += k;
+            at += (uint64_t)k;
+            len -= (size_t)k;
+        }
+    };
+    parallel_for(n, n_threads, [&](int i) {
+        const Member &m = mem[(size_t)i];
+        uint64_t at = m.offset;
+        put(heads[(size_t)i].data(), heads[(size_t)i].size(), at);
+        at += heads[(size_t)i].size();
+        put(m.head.data(), m.head.size(), at);
+        at += m.head.size();
+        if (m.rows_bytes) put(m.rows, m.rows_bytes, at);
+        at += m.rows_bytes;
+        if (m.prg_bytes) put(m.prg, m.prg_bytes, at);
+    });
+    if (failed.load() || fseeko(z.f, (off_t)pos, SEEK_SET) != 0) {
+        w->err = "cannot write " + w->prefix + ".update_DS.zip: " + strerror(failed.load() ? failed.load() : errno);
+        return MPRG_E_INTERNAL;
+    }
+    z.pos = pos;
     w->n_ds += n;
     return MPRG_OK;
 }

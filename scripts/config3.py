@@ -1,0 +1,151 @@
+"""BASELINE config #3 through the product's own sharding: 25,000 loci x 500 rows x U[600,1400] columns (synth seeds
+2,000,000 + i), -N 5 -L 7, loci LPT-partitioned by rows x cols over the ranks (make_prg_b200.engine.lpt_partition:
+STRONG scaling, no data-path collective), every rank builds its shard from packed host rows (mprg_build_packed,
+chunks of CHUNK loci) and writes its own part with the native writer; rank 0 merges the parts (mprg_merge_outputs)
+and prints the sha256 of the merged .prg.fa -- which must not depend on the number of GPUs.
+
+    python scripts/config3.py [n_loci]                                   # one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/config3.py [n_loci]
+
+One JSON line on rank 0 (appended to gpurun_out/config3_r2.jsonl): loci/s and columns/s of the whole job (time =
+max over ranks, device-synchronised wall clock around the builds), the root-level scan launches as timed inside the
+builds (GB/s, fraction of the measured HBM peak), oracle parity on a sample, sha256 of the merged .prg.fa."""
+import hashlib, json, os, sys, time
+from concurrent.futures import ProcessPoolExecutor
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO)); sys.path.insert(0, str(REPO / "oracle"))
+import numpy as np
+
+N_LOCI = int(sys.argv[1]) if len(sys.argv) > 1 else 25_000
+CHUNK = int(os.environ.get("CONFIG3_CHUNK", "5000"))
+ROWS = 500
+
+
+def shape_of(i):
+    from make_prg_b200 import synth
+    rng = np.random.default_rng(synth.CONFIG3_SEED0 + i)
+    return ROWS, int(rng.integers(600, 1401))
+
+
+def make_packed(i):
+    """Locus i as packed rows (the loader's output format), its alphabet flags and shape."""
+    from make_prg_b200 import hostio, synth
+    M = synth.config_msa(3, i)
+    P, flags = hostio.pack_rows(M)
+    return i, P, flags, M.shape
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the synthetic loci of this rank's shard first (worker processes), CUDA afterwards
+    from make_prg_b200 import engine
+    shapes = [shape_of(i) for i in range(N_LOCI)]
+    parts = engine.lpt_partition([r * c for r, c in shapes], world)
+    mine = parts[rank]
+    cores = max(1, (os.cpu_count() or 1) // world)
+    t0 = time.perf_counter()
+    import multiprocessing as mp
+    with ProcessPoolExecutor(cores, mp_context=mp.get_context("spawn")) as pool:
+        made = list(pool.map(make_packed, mine, chunksize=16))
+    t_gen = time.perf_counter() - t0
+    import torch
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        saved = os.dup(1); os.dup2(2, 1)  # NCCL's banner stays off stdout
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    from make_prg_b200 import device, hostio
+    ctx = device.Context(local)
+    out_dir = Path(os.environ.get("CONFIG3_OUT", "/dev/shm/mprg_config3")); out_dir.mkdir(parents=True, exist_ok=True)
+    part_prefix = out_dir / f"part{rank}_of{world}"
+    # warm-up on a small chunk (buffers, pinned pools)
+    def build(chunk):
+        flat = np.concatenate([p.reshape(-1) for _i, p, _f, _s in chunk])
+        pinned = torch.from_numpy(flat).pin_memory().numpy()
+        offs = np.cumsum([0] + [p.size for _i, p, _f, _s in chunk[:-1]])
+        return pinned, offs, [s[0] for *_x, s in chunk], [s[1] for *_x, s in chunk], [f for _i, _p, f, _s in chunk]
+    chunks = [made[a:a + CHUNK] for a in range(0, len(made), CHUNK)]
+    staged = [build(c) for c in chunks]
+    b, r = ctx.build_packed(*[x[:200] if isinstance(x, list) else x for x in (staged[0][0], staged[0][1][:200], staged[0][2][:200], staged[0][3][:200], staged[0][4][:200])], 5, 7)
+    r.free(); b.free()
+    ctx.scan_log(reset=True); ctx.copy_stats(reset=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    writer = hostio.OutputWriter(part_prefix, prg=True, binary=False, gfa=False, part=True)
+    t0 = time.perf_counter()
+    t_write = 0.0
+    n_ok = 0
+    sample = {}
+    chunk_ms = []
+    for chunk, st in zip(chunks, staged):
+        tc = time.perf_counter()
+        batch, res = ctx.build_packed(*st, 5, 7)
+        chunk_ms.append(1e3 * (time.perf_counter() - tc))
+        status, _len = res.statuses()
+        ok = np.nonzero(status == 0)[0]
+        n_ok += len(ok)
+        tw = time.perf_counter()
+        writer.add(res, ok, [f"locus{chunk[int(k)][0]:06d}" for k in ok])
+        t_write += time.perf_counter() - tw
+        for k in range(min(2, len(chunk))):
+            if len(sample) < 4:
+                sample[chunk[k][0]] = res.prg(k)
+        res.free(); batch.free()
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0 - t_write
+    writer.close()
+    log_bytes, log_ms = ctx.scan_log(reset=True)
+    copies = ctx.copy_stats(reset=True)
+    times = torch.tensor([t_build, t_build + t_write, t_gen], dtype=torch.float64, device="cuda")
+    oks = torch.tensor([n_ok], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX); dist.all_reduce(oks); dist.barrier()
+    # oracle parity on this rank's sample
+    import make_prg_oracle as mo
+    from make_prg_b200 import synth
+    bad = 0
+    for i, prg in sample.items():
+        M = synth.config_msa(3, i)
+        bad += mo.build_prg_from_matrix([f"s{r}" for r in range(M.shape[0])], M, 5, 7)[0] != prg
+    bads = torch.tensor([bad, len(sample)], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(bads)
+    if rank == 0:
+        prefixes = [out_dir / f"part{r}_of{world}" for r in range(world)]
+        final = out_dir / f"config3_N{world}"
+        n_merged = hostio.merge_outputs(prefixes, final, prg=True, binary=False, gfa=False)
+        sha = hashlib.sha256((Path(str(final) + ".prg.fa")).read_bytes()).hexdigest()
+        peak = json.loads((REPO / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (REPO / "MEASURED_PEAKS.json").exists() else 6650.0
+        root = log_bytes >= 0.5 * log_bytes.max() if len(log_bytes) else np.zeros(0, bool)
+        t = float(times[0])
+        line = {"config": 3, "n_gpus": world, "n_loci": N_LOCI, "loci_ok": int(oks[0]), "merged": n_merged,
+                "scaling": "strong (LPT partition of the loci by rows x cols)", "chunk_loci": CHUNK,
+                "build_s_max_over_ranks": t, "rank0_chunk_ms": [round(x, 2) for x in chunk_ms], "build_plus_write_s": float(times[1]), "generate_s": float(times[2]),
+                "loci_per_s": N_LOCI / t, "columns_per_s": sum(c for _r, c in shapes) / t,
+                "rank0_h2d_bytes": copies["h2d_bytes"], "rank0_d2h_bytes": copies["d2h_bytes"],
+                "scan_root_level_in_step": {"launches": int(root.sum()),
+                                            "bytes_per_launch": float(log_bytes[root].mean()) if root.any() else None,
+                                            "gbs": float(log_bytes[root].sum() / (log_ms[root].sum() * 1e-3) / 1e9) if root.any() else None,
+                                            "frac_of_hbm_peak": float(log_bytes[root].sum() / (log_ms[root].sum() * 1e-3) / 1e9) / peak if root.any() else None},
+                "scan_all_launches_gbs": float(log_bytes.sum() / (log_ms.sum() * 1e-3) / 1e9) if len(log_bytes) else None,
+                "oracle_checked": int(bads[1]), "oracle_mismatch": int(bads[0]), "prg_fa_sha256": sha,
+                "prg_fa_bytes": Path(str(final) + ".prg.fa").stat().st_size, "host_cores": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+        (REPO / "gpurun_out").mkdir(exist_ok=True)
+        with open(REPO / "gpurun_out" / "config3_r2.jsonl", "a") as fh:
+            fh.write(json.dumps(line) + "\n")
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
