@@ -76,6 +76,14 @@ def main():
     staged = [build(c) for c in chunks]
     b, r = ctx.build_packed(*[x[:200] if isinstance(x, list) else x for x in (staged[0][0], staged[0][1][:200], staged[0][2][:200], staged[0][3][:200], staged[0][4][:200])], 5, 7)
     r.free(); b.free()
+    # "cold": the first build of a shard-sized chunk grows every device buffer (what a one-shot run pays);
+    # "warm": the same builds again with the buffers in place (what a long run pays per chunk)
+    torch.cuda.synchronize()
+    tc0 = time.perf_counter()
+    b, r = ctx.build_packed(*staged[0], 5, 7)
+    torch.cuda.synchronize()
+    cold_first_ms = 1e3 * (time.perf_counter() - tc0)
+    r.free(); b.free()
     ctx.scan_log(reset=True); ctx.copy_stats(reset=True)
     if dist is not None:
         dist.barrier()
@@ -101,11 +109,13 @@ def main():
                 sample[chunk[k][0]] = res.prg(k)
         res.free(); batch.free()
     torch.cuda.synchronize()
+    print(f"[config3] rank {rank}: cold first chunk {cold_first_ms:.1f} ms, chunks {[round(x, 1) for x in chunk_ms]} ms, "
+          f"write {1e3 * t_write:.1f} ms", file=sys.stderr, flush=True)
     t_build = time.perf_counter() - t0 - t_write
     writer.close()
     log_bytes, log_ms = ctx.scan_log(reset=True)
     copies = ctx.copy_stats(reset=True)
-    times = torch.tensor([t_build, t_build + t_write, t_gen], dtype=torch.float64, device="cuda")
+    times = torch.tensor([t_build, t_build + t_write, t_gen, cold_first_ms], dtype=torch.float64, device="cuda")
     oks = torch.tensor([n_ok], dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX); dist.all_reduce(oks); dist.barrier()
@@ -129,6 +139,9 @@ def main():
         t = float(times[0])
         line = {"config": 3, "n_gpus": world, "n_loci": N_LOCI, "loci_ok": int(oks[0]), "merged": n_merged,
                 "scaling": "strong (LPT partition of the loci by rows x cols)", "chunk_loci": CHUNK,
+                "timing": "warm: every rank built one chunk before the timed region (device buffers in place); "
+                          "cold_first_chunk_ms = that first build, max over ranks",
+                "cold_first_chunk_ms": float(times[3]),
                 "build_s_max_over_ranks": t, "rank0_chunk_ms": [round(x, 2) for x in chunk_ms], "build_plus_write_s": float(times[1]), "generate_s": float(times[2]),
                 "loci_per_s": N_LOCI / t, "columns_per_s": sum(c for _r, c in shapes) / t,
                 "rank0_h2d_bytes": copies["h2d_bytes"], "rank0_d2h_bytes": copies["d2h_bytes"],
@@ -141,7 +154,7 @@ def main():
                 "prg_fa_bytes": Path(str(final) + ".prg.fa").stat().st_size, "host_cores": os.cpu_count()}
         print(json.dumps(line), flush=True)
         (REPO / "gpurun_out").mkdir(exist_ok=True)
-        with open(REPO / "gpurun_out" / "config3_r2.jsonl", "a") as fh:
+        with open(REPO / "gpurun_out" / f"config3_r2_N{world}.jsonl", "a") as fh:
             fh.write(json.dumps(line) + "\n")
     if dist is not None:
         dist.destroy_process_group()
