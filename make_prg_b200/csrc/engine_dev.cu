@@ -18,9 +18,17 @@
 #include <cstring>
 #include <thread>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up in Nsight Systems / Compute, no cost without a tool
+
 #include "engine.cuh"
 
 namespace mprg {
+
+// NVTX range for the phases of the level loop (tracing)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DLocus {
     long long base;
@@ -961,8 +969,12 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
     };
     TRACE("dev: setup");
 
+    NvtxRange nvtx_build("mprg: device-resident level loop");
     for (int level = 0;; ++level) {
         if (pending_bound == 0) break;
+        char nvtx_name[48];
+        snprintf(nvtx_name, sizeof(nvtx_name), "mprg: recursion level %d", level);
+        NvtxRange nvtx_level(nvtx_name);
         // ---- tasks and scan tiles of the level ----
         const int pb = (int)((pending_bound + 255) / 256);
         MPRG_CUDA(ctx, ctx->d_tasks.reserve(sizeof(DTask) * (size_t)pending_bound));
@@ -1053,6 +1065,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         // ---- clustering pass: a locus root never clusters, so level 0 of from_msa skips it ----
         const bool may_cluster = !(level == 0 && !root_levels);
         if (may_cluster) {
+            NvtxRange nvtx_cluster("mprg: clustering pass");
             // sized by the bound "every task of the level clusters"
             const long long g_bound = std::max<long long>(cnt->sum_rw, 1), r_bound = std::max<long long>(cnt->sum_rows, 1);
             MPRG_CUDA(ctx, V[V_G].reserve((size_t)g_bound));
@@ -1239,6 +1252,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
     bool expansion = getenv("MPRG_HOST_ASSEMBLY") != nullptr;  // RYKMSW: the cartesian product is made on the host
     for (int i = 0; i < nl && !expansion; ++i) expansion = h_loci[i].status == MPRG_LOCUS_OK && (h_loci[i].flags & 4);
     if (!expansion) {
+        NvtxRange nvtx_prg("mprg: PRG strings on the device");
         // ---- PRG strings assembled on the device: only the strings and the raw tree cross PCIe ----
         MPRG_CUDA(ctx, V[V_OUTLEN].reserve(sizeof(int) * (size_t)std::max(na, 1)));
         MPRG_CUDA(ctx, V[V_PRGINFO].reserve(sizeof(PrgInfo) * (size_t)nl + 64));

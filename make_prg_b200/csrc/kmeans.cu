@@ -843,10 +843,10 @@ kmeans_prepare_kernel(const ClusterState *__restrict__ states, const double *__r
 
 // grid (problems, KM_NINIT): every CTA runs one initialisation; the last CTA of a problem to finish
 // (ticket counter) does the selection, the prediction and the loop control of kmeans_cluster_seqs
-__global__ void __launch_bounds__(KM_THREADS)
-kmeans_kernel(ClusterState *__restrict__ states, const double *__restrict__ X_all,
-              double *__restrict__ dscratch, int *__restrict__ iscratch, int *__restrict__ assign_all,
-              int *__restrict__ newlab_all, int *__restrict__ tickets) {
+__device__ __forceinline__ void
+kmeans_kernel_body(ClusterState *__restrict__ states, const double *__restrict__ X_all,
+                   double *__restrict__ dscratch, int *__restrict__ iscratch, int *__restrict__ assign_all,
+                   int *__restrict__ newlab_all, int *__restrict__ tickets) {
     __shared__ double s_scalar[4];
     __shared__ int s_int[8];
     ClusterState &st = states[blockIdx.x];
@@ -882,6 +882,24 @@ kmeans_kernel(ClusterState *__restrict__ states, const double *__restrict__ X_al
         __threadfence();
         st.run_kmeans = 0;
     }
+}
+
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_kernel(ClusterState *__restrict__ states, const double *__restrict__ X_all,
+              double *__restrict__ dscratch, int *__restrict__ iscratch, int *__restrict__ assign_all,
+              int *__restrict__ newlab_all, int *__restrict__ tickets) {
+    kmeans_kernel_body(states, X_all, dscratch, iscratch, assign_all, newlab_all, tickets);
+}
+
+// The same for the one-warp CTAs of a pangenome level (thousands of problems with n <= 8, F <= 70): the level
+// is bound by latency (sequential float64 sums on one lane while the others wait), so what counts is how many
+// initialisations are resident.  At 128 registers an SM holds 16 one-warp CTAs; bounded to 64 registers
+// (spills stay in L1) it holds the 32 the CTA slots allow.
+__global__ void __launch_bounds__(32, 32)
+kmeans_kernel_w32(ClusterState *__restrict__ states, const double *__restrict__ X_all,
+                  double *__restrict__ dscratch, int *__restrict__ iscratch, int *__restrict__ assign_all,
+                  int *__restrict__ newlab_all, int *__restrict__ tickets) {
+    kmeans_kernel_body(states, X_all, dscratch, iscratch, assign_all, newlab_all, tickets);
 }
 
 // stand-alone problem (mprg_kmeans): prepare <<<1>>> then grid (1, KM_NINIT)
@@ -1058,8 +1076,12 @@ cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, con
     // (max_elements is counted with the bound F <= positions when the level does not wait for F: 8 x 241)
     int threads = max_elements <= 2048 ? 32 : (max_elements <= 16384 ? 64 : KM_THREADS);
     if (const char *e = getenv("MPRG_KM_THREADS")) threads = std::max(32, std::min(atoi(e) & ~31, KM_THREADS));
-    kmeans_kernel<<<dim3(n_probs, KM_NINIT), threads, 0, s>>>(states, X, dscratch, iscratch, assign, newlab,
-                                                              tickets);
+    static const bool w32 = getenv("MPRG_KM_NO_W32") == nullptr;
+    if (threads == 32 && w32)
+        kmeans_kernel_w32<<<dim3(n_probs, KM_NINIT), 32, 0, s>>>(states, X, dscratch, iscratch, assign, newlab, tickets);
+    else
+        kmeans_kernel<<<dim3(n_probs, KM_NINIT), threads, 0, s>>>(states, X, dscratch, iscratch, assign, newlab,
+                                                                  tickets);
     return cudaGetLastError();
 }
 

@@ -183,12 +183,20 @@ __device__ void run_partition(const uint32_t *starbits, const int *reach, int n,
     *out_count = s.n;
 }
 
-// one thread per task (the state machine is inherently sequential; it touches O(#runs) words)
-__global__ void __launch_bounds__(64)
+// One warp per task.  The state machine is inherently sequential (lane 0 runs it), but every push / pop of its
+// interval stack used to be a round trip to global memory (162 us at the root level of the bench batch): the
+// stack now lives in shared memory whenever the task cannot produce more intervals than fit -- the number of
+// class runs of its consensus bounds them and the warp counts it first -- and the warp copies the result out.
+constexpr int PART_WARPS = 4;
+constexpr int PART_SMEM_IV = 448;  // intervals per warp in shared memory (21 KB per CTA)
+
+__global__ void __launch_bounds__(32 * PART_WARPS)
 partition_kernel(const DTask *__restrict__ tasks, int n_tasks, const uint32_t *__restrict__ starbits,
                  const int *__restrict__ reach, int mml, DInterval *__restrict__ intervals,
                  int *__restrict__ iv_count, int *__restrict__ err) {
-    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ DInterval s_iv[PART_WARPS][PART_SMEM_IV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ti = blockIdx.x * PART_WARPS + warp;
     if (ti >= n_tasks) return;
     const DTask t = tasks[ti];
     const int n = t.c1 - t.c0;
@@ -196,8 +204,30 @@ partition_kernel(const DTask *__restrict__ tasks, int n_tasks, const uint32_t *_
     // starbits / reach of this task are stored at a0-relative positions; the state machine wants
     // c0-relative ones.  classify_kernel wrote starbits already c0-relative (bit i0+lane), and reach
     // at col_off + shift + i.
-    run_partition(starbits + ((long long)t.col_off >> 5), reach + (long long)t.col_off + shift, n, mml,
-                  intervals + t.iv_off, iv_count + ti, err);
+    const uint32_t *sb = starbits + ((long long)t.col_off >> 5);
+    // class runs of the consensus = 1 + transitions between neighbouring columns
+    int transitions = 0;
+    const int n_words = (n + 31) >> 5;
+    for (int w = lane; w < n_words; w += 32) {
+        const uint32_t x = sb[w];
+        const uint32_t nxt = (w + 1 < n_words) ? sb[w + 1] : 0u;
+        uint32_t d = x ^ ((x >> 1) | (nxt << 31));  // bit i: column 32 w + i differs from column 32 w + i + 1
+        const int valid = min(32, n - 1 - (w << 5));  // pairs (i, i + 1) with i + 1 < n
+        if (valid < 32) d &= valid <= 0 ? 0u : ((1u << valid) - 1u);
+        transitions += __popc(d);
+    }
+    transitions = __reduce_add_sync(0xffffffffu, transitions);
+    const bool in_smem = transitions + 2 <= PART_SMEM_IV;
+    DInterval *out = intervals + t.iv_off;
+    if (lane == 0)
+        run_partition(sb, reach + (long long)t.col_off + shift, n, mml, in_smem ? s_iv[warp] : out, iv_count + ti, err);
+    __syncwarp();
+    if (in_smem) {
+        const int count = iv_count[ti];
+        const int *src = reinterpret_cast<const int *>(s_iv[warp]);
+        int *dst = reinterpret_cast<int *>(out);
+        for (int i = lane; i < 3 * count; i += 32) dst[i] = src[i];
+    }
 }
 
 // consensus supplied by the caller (mprg_partition_consensus): single task, c0 = 0
@@ -288,8 +318,8 @@ cudaError_t launch_partition(cudaStream_t stream, const DTask *d_tasks, int n_ta
                              const uint32_t *starbits, const int *reach, int mml, DInterval *intervals,
                              int *iv_count, int *err) {
     if (n_tasks <= 0) return cudaSuccess;
-    partition_kernel<<<(n_tasks + 63) / 64, 64, 0, stream>>>(d_tasks, n_tasks, starbits, reach, mml,
-                                                            intervals, iv_count, err);
+    partition_kernel<<<(n_tasks + PART_WARPS - 1) / PART_WARPS, 32 * PART_WARPS, 0, stream>>>(
+        d_tasks, n_tasks, starbits, reach, mml, intervals, iv_count, err);
     return cudaGetLastError();
 }
 
