@@ -938,12 +938,15 @@ gather2_kernel(const long long *__restrict__ src_off, const int *__restrict__ co
     }
 }
 
-// member lists of a clustering problem: rows of every distinct long sequence, in row order
+// member lists of a clustering problem: rows of every distinct long sequence, in row order.  One warp per
+// problem: the long-sequence index of every group by a ballot prefix, the member counts by atomics on the
+// problem's own offset array, the stable placement chunk by chunk (rows of one chunk that share a sequence
+// are ranked with __match_any_sync, so every list keeps the row order).
 __global__ void __launch_bounds__(32)
 members_kernel(const MemberProb *__restrict__ probs, const int *__restrict__ group,
                const int *__restrict__ leader_len, int *__restrict__ long_of_group,
                int *__restrict__ mem_off_all, int *__restrict__ mem_rows_all) {
-    if (threadIdx.x != 0) return;
+    const int lane = threadIdx.x;
     const MemberProb p = probs[blockIdx.x];
     const int *grp = group + p.row_off;
     const int *ll = leader_len + p.row_off;
@@ -951,20 +954,54 @@ members_kernel(const MemberProb *__restrict__ probs, const int *__restrict__ gro
     int *mem_off = mem_off_all + p.mem_off;
     int *mem_rows = mem_rows_all + p.mem_rows_off;
     int n = 0;
-    for (int g = 0; g < p.n_groups; ++g) lg[g] = ll[g] >= p.k ? n++ : -1;
-    for (int j = 0; j <= n; ++j) mem_off[j] = 0;
-    for (int r = 0; r < p.R; ++r) {
-        const int j = lg[grp[r]];
-        if (j >= 0) mem_off[j + 1]++;
+    for (int g0 = 0; g0 < p.n_groups; g0 += 32) {
+        const int g = g0 + lane;
+        const bool is_long = g < p.n_groups && ll[g] >= p.k;
+        const unsigned m = __ballot_sync(0xffffffffu, is_long);
+        if (g < p.n_groups) lg[g] = is_long ? n + __popc(m & ((1u << lane) - 1u)) : -1;
+        n += __popc(m);
     }
-    for (int j = 0; j < n; ++j) mem_off[j + 1] += mem_off[j];
-    // stable placement in row order: advance mem_off[j] as a cursor, then shift the offsets back
-    for (int r = 0; r < p.R; ++r) {
+    for (int j = lane; j <= n; j += 32) mem_off[j] = 0;
+    __syncwarp();
+    for (int r = lane; r < p.R; r += 32) {
         const int j = lg[grp[r]];
-        if (j >= 0) mem_rows[mem_off[j]++] = r;
+        if (j >= 0) atomicAdd(&mem_off[j + 1], 1);
     }
-    for (int j = n; j > 0; --j) mem_off[j] = mem_off[j - 1];
-    mem_off[0] = 0;
+    __syncwarp();
+    // inclusive prefix over mem_off[1..n] (n <= R; chunks of 32 with a running carry)
+    int carry = 0;
+    for (int j0 = 1; j0 <= n; j0 += 32) {
+        const int j = j0 + lane;
+        int v = j <= n ? mem_off[j] : 0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += o;
+        }
+        v += carry;
+        if (j <= n) mem_off[j] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+    __syncwarp();
+    // stable placement in row order: mem_off[j] is advanced as the cursor of list j (it starts at the
+    // exclusive offset because mem_off[j] holds the inclusive sum of the lists before j), then shifted back
+    for (int r0 = 0; r0 < p.R; r0 += 32) {
+        const int r = r0 + lane;
+        const int j = r < p.R ? lg[grp[r]] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, j);
+        if (j >= 0) mem_rows[mem_off[j] + __popc(peers & ((1u << lane) - 1u))] = r;
+        __syncwarp();
+        if (j >= 0 && (peers & ((1u << lane) - 1u)) == 0) mem_off[j] += __popc(peers);
+        __syncwarp();
+    }
+    // the cursors now stand at the END of their lists: mem_off[j] = offset of list j + 1; shift back
+    for (int j0 = ((n + 32) / 32) * 32 - 32; j0 >= 0; j0 -= 32) {  // highest chunk first
+        const int j = j0 + lane;
+        const int v = (j >= 1 && j <= n) ? mem_off[j - 1] : 0;
+        __syncwarp();
+        if (j >= 1 && j <= n) mem_off[j] = v;
+        __syncwarp();
+    }
+    if (lane == 0) mem_off[0] = 0;
 }
 
 cudaError_t launch_scan_counts(cudaStream_t s, const int *counts, int n, int *offs) {

@@ -715,12 +715,27 @@ __device__ __forceinline__ void marker_put(char *dst, int m) {
 
 constexpr int PRG_STACK = 64;  // nesting depth of the tree: at most 2 * max_nesting + 2 in practice
 
-// WRITE == false: measure; WRITE == true: markers into the blob, items[a].out_off = where allele a goes
+// text length of every leaf without its markers (sum of its alleles' ungapped lengths): one thread per node,
+// so that the per-locus walks below touch nodes only, never alleles
+__global__ void __launch_bounds__(256)
+leaf_len_kernel(const DNode *__restrict__ nodes, int n_nodes, const int *__restrict__ allele_len,
+                long long *__restrict__ leaf_len) {
+    const int ni = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ni >= n_nodes) return;
+    const DNode nd = nodes[ni];
+    long long sum = 0;
+    if (nd.kind == MPRG_NODE_LEAF)
+        for (int a = 0; a < nd.allele_count; ++a) sum += allele_len[nd.allele_first + a];
+    leaf_len[ni] = sum;
+}
+
+// WRITE == false: measure; WRITE == true: cluster markers into the blob, and for every leaf where its text
+// starts (leaf_at) and its site number (leaf_site, 0 = single allele) -- leaf_write_kernel does the rest
 template <bool WRITE>
 __global__ void __launch_bounds__(128)
 prg_walk_kernel(const DNode *__restrict__ nodes, const DLocus *__restrict__ loci, int nl,
-                const int *__restrict__ allele_len, PrgInfo *__restrict__ info, ExtractItem *__restrict__ items,
-                char *__restrict__ blob, int *__restrict__ err) {
+                const long long *__restrict__ leaf_len, PrgInfo *__restrict__ info, long long *__restrict__ leaf_at,
+                int *__restrict__ leaf_site, char *__restrict__ blob, int *__restrict__ err) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nl) return;
     if (loci[i].status != MPRG_LOCUS_OK) {
@@ -741,20 +756,20 @@ prg_walk_kernel(const DNode *__restrict__ nodes, const DLocus *__restrict__ loci
             ++n_nodes;
             if (nd.kind == MPRG_NODE_LEAF) {
                 if (nd.allele_count == 1) {
-                    if (WRITE) items[nd.allele_first].out_off = at;
-                    at += allele_len[nd.allele_first];
+                    if (WRITE) {
+                        leaf_at[ni] = at;
+                        leaf_site[ni] = 0;
+                    }
+                    at += leaf_len[ni];
                 } else {
                     const int sn = site;
                     site += 2;
-                    if (WRITE) marker_put(blob + at, sn);
-                    at += marker_len(sn);
-                    for (int a = 0; a < nd.allele_count; ++a) {
-                        if (WRITE) items[nd.allele_first + a].out_off = at;
-                        at += allele_len[nd.allele_first + a];
-                        const int m = a + 1 < nd.allele_count ? sn + 1 : sn;
-                        if (WRITE) marker_put(blob + at, m);
-                        at += marker_len(m);
+                    if (WRITE) {
+                        leaf_at[ni] = at;
+                        leaf_site[ni] = sn;
                     }
+                    // " sn " a1 " sn+1 " a2 ... " sn+1 " ak " sn "
+                    at += 2LL * marker_len(sn) + (long long)(nd.allele_count - 1) * marker_len(sn + 1) + leaf_len[ni];
                 }
                 --depth;
                 continue;
@@ -786,6 +801,32 @@ prg_walk_kernel(const DNode *__restrict__ nodes, const DLocus *__restrict__ loci
         }
     }
     if (!WRITE) info[i] = PrgInfo{0, at, (site - 5) / 2, n_nodes, MPRG_LOCUS_OK, 0};
+}
+
+// one thread per leaf: where each of its alleles goes (items[a].out_off) and the markers between them
+__global__ void __launch_bounds__(256)
+leaf_write_kernel(const DNode *__restrict__ nodes, int n_nodes, const DLocus *__restrict__ loci, int l0,
+                  const int *__restrict__ allele_len, const long long *__restrict__ leaf_at,
+                  const int *__restrict__ leaf_site, ExtractItem *__restrict__ items, char *__restrict__ blob) {
+    const int ni = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ni >= n_nodes) return;
+    const DNode nd = nodes[ni];
+    if (nd.kind != MPRG_NODE_LEAF || nd.allele_count <= 0 || loci[nd.locus - l0].status != MPRG_LOCUS_OK) return;
+    long long at = leaf_at[ni];
+    if (nd.allele_count == 1) {
+        items[nd.allele_first].out_off = at;
+        return;
+    }
+    const int sn = leaf_site[ni];
+    marker_put(blob + at, sn);
+    at += marker_len(sn);
+    for (int a = 0; a < nd.allele_count; ++a) {
+        items[nd.allele_first + a].out_off = at;
+        at += allele_len[nd.allele_first + a];
+        const int m = a + 1 < nd.allele_count ? sn + 1 : sn;
+        marker_put(blob + at, m);
+        at += marker_len(m);
+    }
 }
 
 // exclusive prefix sum of the PRG lengths (single CTA); total -> *total_out
@@ -844,7 +885,7 @@ static cudaError_t reserve_keep(DevBuf &b, size_t bytes, size_t used, cudaStream
 // buffers of the device-resident loop (ctx->d_dev)
 enum {
     V_COUNTERS = 0, V_LOCI, V_NODES, V_POOL, V_ITEMS, V_PEND_A, V_PEND_B, V_CT_TASKS, V_CT_MISC, V_G, V_SIG, V_ROWINTS,
-    V_PROBS, V_PROB_MISC, V_SCRATCH, V_USEQ, V_INTS, V_KEYS, V_MING, V_X, V_STATE_MISC, V_B14, V_KM, V_OUT, V_OUTLEN, V_UNIT_OFF, V_PRGINFO,
+    V_PROBS, V_PROB_MISC, V_SCRATCH, V_USEQ, V_INTS, V_KEYS, V_MING, V_X, V_STATE_MISC, V_B14, V_KM, V_OUT, V_OUTLEN, V_UNIT_OFF, V_PRGINFO, V_LEAF,
     V_COUNT
 };
 
@@ -1261,11 +1302,16 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         int *d_len = V[V_OUTLEN].as<int>();
         ExtractItem *d_items = V[V_ITEMS].as<ExtractItem>();
         int *d_errflag = &d_cnt->err;
+        MPRG_CUDA(ctx, V[V_LEAF].reserve((sizeof(long long) * 2 + sizeof(int)) * (size_t)std::max(n_nodes, 1) + 64));
+        long long *d_leaf_len = V[V_LEAF].as<long long>();
+        long long *d_leaf_at = d_leaf_len + std::max(n_nodes, 1);
+        int *d_leaf_site = reinterpret_cast<int *>(d_leaf_at + std::max(n_nodes, 1));
         if (na > 0) allele_len_kernel<<<(na + 3) / 4, 128, 0, s>>>(batch->d_packed, d_items, na, d_len);
-        prg_walk_kernel<false><<<(nl + 127) / 128, 128, 0, s>>>(V[V_NODES].as<DNode>(), d_loci, nl, d_len, d_info, d_items,
-                                                               nullptr, d_errflag);
+        leaf_len_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(V[V_NODES].as<DNode>(), n_nodes, d_len, d_leaf_len);
+        prg_walk_kernel<false><<<(nl + 127) / 128, 128, 0, s>>>(V[V_NODES].as<DNode>(), d_loci, nl, d_leaf_len, d_info,
+                                                               d_leaf_at, d_leaf_site, nullptr, d_errflag);
         prg_offsets_kernel<<<1, 1024, 0, s>>>(d_info, nl, d_total);
-        ctx->launches += 3;
+        ctx->launches += 4;
         MPRG_CUDA(ctx, cudaGetLastError());
         // the raw tree travels while the strings are being laid out
         RawTree raw;
@@ -1288,11 +1334,13 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         PinnedBlock blob = pinned_acquire((size_t)std::max<long long>(blob_bytes, 1));
         if (!blob.p) MPRG_FAIL(ctx, MPRG_E_CUDA, "pinned allocation for the result failed");
         MPRG_CUDA(ctx, V[V_OUT].reserve((size_t)std::max<long long>(blob_bytes, 1)));
-        prg_walk_kernel<true><<<(nl + 127) / 128, 128, 0, s>>>(V[V_NODES].as<DNode>(), d_loci, nl, d_len, d_info, d_items,
-                                                              V[V_OUT].as<char>(), d_errflag);
+        prg_walk_kernel<true><<<(nl + 127) / 128, 128, 0, s>>>(V[V_NODES].as<DNode>(), d_loci, nl, d_leaf_len, d_info,
+                                                              d_leaf_at, d_leaf_site, V[V_OUT].as<char>(), d_errflag);
+        leaf_write_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(V[V_NODES].as<DNode>(), n_nodes, d_loci, l_begin, d_len,
+                                                              d_leaf_at, d_leaf_site, d_items, V[V_OUT].as<char>());
         if (na > 0)
             MPRG_CUDA(ctx, launch_extract(s, batch->d_packed, d_items, na, V[V_OUT].as<uint8_t>(), d_len));
-        ctx->launches += 2;
+        ctx->launches += 3;
         MPRG_CUDA(ctx, cudaGetLastError());
         if (blob_bytes > 0) MPRG_CUDA(ctx, mprg::copy_d2h(ctx, blob.p, V[V_OUT].p, (size_t)blob_bytes, s));
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_info, d_info, sizeof(PrgInfo) * (size_t)nl, s));
