@@ -8,8 +8,9 @@
  * Conventions
  *   - every function returns 0 on success, a negative MPRG_E_* code otherwise; no C++ exception
  *     crosses the ABI; mprg_last_error(ctx) gives the text of the last failure on that context.
- *   - plain pointers and sizes only.  Pointers named h_* are HOST memory, d_* are DEVICE memory
- *     owned by the caller (e.g. torch tensors' data_ptr()); the library never frees caller memory.
+ *   - plain pointers and sizes only.  Every pointer an entry point takes (h_*) is HOST memory owned by the
+ *     caller (pinned or pageable; the library never frees caller memory).  Device memory is owned by the
+ *     library: batches (mprg_batch) hold the packed MSAs in HBM, results (mprg_result) hold what came back.
  *   - one context per GPU, used from one host thread at a time; all work is enqueued on the
  *     context's stream; entry points that return host results synchronise that stream.
  *   - there is NO CPU fallback: without a CUDA device mprg_create fails with MPRG_E_NO_DEVICE.
@@ -96,9 +97,11 @@ int mprg_path_counts(mprg_ctx *ctx, int64_t *out, int reset);
  * kernel accumulated since the last reset; used by bench.py for the roofline object */
 int mprg_scan_stats(mprg_ctx *ctx, double *ms, double *bytes, int64_t *launches, int reset);
 
-/* host threads (each with its own stream and scratch) mprg_build may use to overlap the host
- * bookkeeping of one range of loci with the kernels of the others; default min(4, cores) or
- * the MPRG_WORKERS environment variable */
+/* Upper bound of the ranges (one host thread + stream + scratch set each) a build is cut into; default
+ * min(8, host cores / ranks on this host) or the MPRG_WORKERS environment variable.  The device-resident level
+ * loop uses ONE range for a resident batch and TWO from host buffers (the upload of one overlaps the kernels of
+ * the other; MPRG_DEV_RANGES overrides); the full count only applies to the host-driven loop kept as the checked
+ * alternative (MPRG_HOST_LOOP=1) and to the host threads that assemble PRG strings of loci holding RYKMSW. */
 int mprg_set_workers(mprg_ctx *ctx, int32_t n_workers);
 /* host<->device bytes copied by this context since the last reset (bench.py's e2e object) */
 int mprg_copy_stats(mprg_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes, int reset);

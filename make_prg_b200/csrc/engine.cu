@@ -315,7 +315,7 @@ int run_problems_host(mprg_ctx *ctx, cudaStream_t s, const std::vector<HostProbl
             // loci over ACGT- only (no N, no RYKMSW, no even code): bit-sliced counting on the packed rows;
             // MPRG_REFCHECK_BYTES=1 keeps the byte-wise kernels (the checked alternative)
             static const bool bytes_only = getenv("MPRG_REFCHECK_BYTES") != nullptr;
-            if (d_packed && !(p.alpha_flags & (2 | 4 | 8)) && !bytes_only) {
+            if (d_packed && !(p.alpha_flags & (2 | 4 | 8)) && !bytes_only && p.R <= 65535) {  // 16-bit count fields
                 DTask t;
                 t.base = p.base;
                 t.stride = p.stride;

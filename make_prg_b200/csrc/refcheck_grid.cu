@@ -12,9 +12,10 @@
 // themselves, so the kernel is bound by reading the rows once from HBM (profiles/).
 //
 //   cluster_rows_kernel   member rows of every cluster, in member order (one warp per cluster)
-//   majority_count_kernel one warp per (cluster, 128 rows, 256 columns): SWAR bit-plane counters in registers
-//                         -- codes A C G T = 1 3 5 7 share bit 0, so four sums (b0, b0 b1, b0 b2, b0 b1 b2) give
-//                         the five symbol counts -- nibble fields spilled to byte fields every 15 rows
+//   majority_count_kernel one warp per (cluster, 240 rows, 1,024 columns), a 128-bit load per lane and row: SWAR
+//                         bit-plane counters in registers -- codes A C G T = 1 3 5 7 share bit 0, so four sums
+//                         (b0, b0 b1, b0 b2, b0 b1 b2) give the five symbol counts -- nibble fields spilled to byte
+//                         fields every 15 rows, published as one 64-bit atomic (4 x 16 bits) per column and tile
 //   majority_pick_kernel  arg-max per (cluster, column); exact ties resolved by reading the rows in order
 //   hamming_packed_kernel one warp per member row: popcount of the non-zero nibbles of row XOR majority
 #include "common.cuh"
@@ -22,7 +23,11 @@
 
 namespace mprg {
 
-constexpr int RG_ROWS = 128;   // rows per tile of the counting kernel (byte fields hold up to 255)
+#ifndef MPRG_RG_WARP_ROWS
+#define MPRG_RG_WARP_ROWS 60
+#endif
+constexpr int RG_WARP_ROWS = MPRG_RG_WARP_ROWS;  // rows a warp counts in registers (groups of 15; byte fields hold 255)
+constexpr int RG_ROWS = 4 * RG_WARP_ROWS;     // rows per CTA of the counting kernel: its four warps share a column group
 constexpr unsigned NIB = 0x11111111u;
 
 struct RefGrid {
@@ -74,16 +79,25 @@ cluster_rows_kernel(const ClusterState *__restrict__ states, int q, RefGrid g, c
     if (lane == 0) ccount[c] = total;
 }
 
-// counts[(c * w + col) * 4 + p]: p = 0 rows with a base, 1 bases with bit 1 (C or T), 2 bases with bit 2 (G or T),
-// 3 bases with both (T)
-__global__ void __launch_bounds__(128)
+// counts[c * w + col]: four 16-bit fields in one 64-bit word -- rows with a base | bases with bit 1 (C or T) << 16 |
+// bases with bit 2 (G or T) << 32 | bases with both (T) << 48 -- so a tile publishes ONE atomic per column (the
+// first version did four 32-bit ones per column and tile of 128 rows: 7 M atomics per pass were what bounded it).
+// One CTA per (cluster, RG_ROWS rows, 32 chunks = 1,024 columns): each of its four warps counts a quarter of the
+// rows in registers (a lane owns one chunk: 32 columns, a 128-bit load per row), the warps add up through shared
+// memory and the CTA publishes one atomic per column.
+#ifndef MPRG_RG_MIN_BLOCKS
+#define MPRG_RG_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, MPRG_RG_MIN_BLOCKS)
 majority_count_kernel(const ClusterState *__restrict__ states, int q, RefGrid g, const uint8_t *__restrict__ packed,
                       const int *__restrict__ rows_arena, const int *__restrict__ crows, const int *__restrict__ ccount,
-                      int *__restrict__ counts) {
+                      unsigned long long *__restrict__ counts) {
     const ClusterState &st = states[q];
     if (st.status != 0) return;
-    const int lane = threadIdx.x & 31;
-    const int k = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 32 + lane;  // word of the window
+    __shared__ unsigned long long s_cnt[4][1024];  // [warp][column of the group]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_chunks = g.n_words >> 2;
+    const int ch = blockIdx.x * 32 + lane;  // chunk of the window
     // row block -> (cluster, first row)
     int c = 0, blk = blockIdx.y, nrows = 0;
     for (; c < st.K; ++c) {
@@ -93,62 +107,80 @@ majority_count_kernel(const ClusterState *__restrict__ states, int q, RefGrid g,
         blk -= nb;
     }
     if (c >= st.K) return;
-    const bool in_window = k < g.n_words;
-    const int i0 = blk * RG_ROWS, i1 = min(i0 + RG_ROWS, nrows);
+    const bool in_window = ch < n_chunks;
+    const int i0 = min(blk * RG_ROWS + warp * RG_WARP_ROWS, nrows), i1 = min(i0 + RG_WARP_ROWS, nrows);
     const int *rows = crows + (long long)c * g.R;
-    unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;                                  // nibble fields
-    unsigned l0 = 0, h0 = 0, l1 = 0, h1 = 0, l2 = 0, h2 = 0, l3 = 0, h3 = 0;  // byte fields (even / odd nibbles)
-    int pending = 0;
-    auto spill = [&]() {
-        l0 += a0 & 0x0f0f0f0fu; h0 += (a0 >> 4) & 0x0f0f0f0fu;
-        l1 += a1 & 0x0f0f0f0fu; h1 += (a1 >> 4) & 0x0f0f0f0fu;
-        l2 += a2 & 0x0f0f0f0fu; h2 += (a2 >> 4) & 0x0f0f0f0fu;
-        l3 += a3 & 0x0f0f0f0fu; h3 += (a3 >> 4) & 0x0f0f0f0fu;
-        a0 = a1 = a2 = a3 = 0;
-        pending = 0;
-    };
-    auto add = [&](unsigned x) {
-        const unsigned t1 = x >> 1, t2 = x >> 2;
-        const unsigned p1 = x & t1 & NIB;
-        a0 += x & NIB;
-        a1 += p1;
-        a2 += x & t2 & NIB;
-        a3 += p1 & t2;
-    };
-    int i = i0;
-    for (; i + 5 <= i1; i += 5) {  // five independent row loads in flight per lane, three trips per spill
-        unsigned x[5];
+    unsigned a[4][4];      // [word][plane] nibble fields
+    unsigned lo[4][4], hi[4][4];  // byte fields of the even / odd nibbles
 #pragma unroll
-        for (int u = 0; u < 5; ++u) {
-            const uint32_t *rw = row_words(packed, g, rows_arena, rows[i + u]);
-            x[u] = in_window ? __ldg(rw + k) : 0u;
+    for (int wd = 0; wd < 4; ++wd)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) a[wd][p] = lo[wd][p] = hi[wd][p] = 0;
+    auto add = [&](const uint4 &v) {
+        const unsigned x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int wd = 0; wd < 4; ++wd) {
+            const unsigned t1 = x[wd] >> 1, t2 = x[wd] >> 2;
+            const unsigned p1 = x[wd] & t1 & NIB;
+            a[wd][0] += x[wd] & NIB;
+            a[wd][1] += p1;
+            a[wd][2] += x[wd] & t2 & NIB;
+            a[wd][3] += p1 & t2;
         }
+    };
+    auto spill = [&]() {
 #pragma unroll
-        for (int u = 0; u < 5; ++u) add(x[u]);
-        pending += 5;
-        if (pending == 15) spill();
+        for (int wd = 0; wd < 4; ++wd)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                lo[wd][p] += a[wd][p] & 0x0f0f0f0fu;
+                hi[wd][p] += (a[wd][p] >> 4) & 0x0f0f0f0fu;
+                a[wd][p] = 0;
+            }
+    };
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int i = i0; i < i1; i += 15) {  // nibble fields hold 15 rows
+        const int n15 = min(15, i1 - i);
+        // the row numbers of the group: one coalesced read, handed out by shuffles
+        int rid = 0;
+        if (lane < n15) {
+            const int tr = rows[i + lane];
+            rid = g.rows_off >= 0 ? rows_arena[g.rows_off + tr] : tr;
+        }
+        for (int u0 = 0; u0 < n15; u0 += 5) {  // five independent 128-bit loads in flight per lane
+            uint4 v[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                const int r = __shfl_sync(0xffffffffu, rid, min(u0 + u, 14));
+                const uint4 *rw = reinterpret_cast<const uint4 *>(packed + g.base + (long long)r * g.stride +
+                                                                  (long long)g.ch0 * 16);
+                v[u] = (in_window && u0 + u < n15) ? __ldg(rw + ch) : zero;
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u) add(v[u]);
+        }
+        spill();
     }
-    for (; i < i1; ++i) {
-        const uint32_t *rw = row_words(packed, g, rows_arena, rows[i]);
-        add(in_window ? __ldg(rw + k) : 0u);
-        if (++pending == 15) spill();
-    }
-    spill();
-    if (!in_window) return;
+    // the lane's 32 columns into the warp's slab (column 4 j + wd of chunk `lane`)
+#pragma unroll
+    for (int wd = 0; wd < 4; ++wd)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int sh = (j >> 1) * 8;
+            unsigned long long v = 0;
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                v |= (unsigned long long)((((j & 1) ? hi[wd][p] : lo[wd][p]) >> sh) & 255u) << (16 * p);
+            s_cnt[warp][lane * 32 + 4 * j + wd] = v;
+        }
+    __syncthreads();
     const int w = g.c1 - g.c0;
-    const int col_base = (g.ch0 + (k >> 2)) * 32 + (k & 3);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int col = col_base + 4 * j;
+    const int col0 = (g.ch0 + blockIdx.x * 32) * 32;  // first column of the group
+    for (int k = threadIdx.x; k < 1024; k += 128) {
+        const int col = col0 + k;
         if (col < g.c0 || col >= g.c1) continue;
-        const int sh = (j >> 1) * 8;
-        const unsigned v0 = (((j & 1) ? h0 : l0) >> sh) & 255u, v1 = (((j & 1) ? h1 : l1) >> sh) & 255u;
-        const unsigned v2 = (((j & 1) ? h2 : l2) >> sh) & 255u, v3 = (((j & 1) ? h3 : l3) >> sh) & 255u;
-        int *dst = counts + ((long long)c * w + (col - g.c0)) * 4;
-        if (v0) atomicAdd(dst + 0, (int)v0);
-        if (v1) atomicAdd(dst + 1, (int)v1);
-        if (v2) atomicAdd(dst + 2, (int)v2);
-        if (v3) atomicAdd(dst + 3, (int)v3);
+        const unsigned long long v = s_cnt[0][k] + s_cnt[1][k] + s_cnt[2][k] + s_cnt[3][k];
+        if (v) atomicAdd(&counts[(long long)c * w + (col - g.c0)], v);
     }
 }
 
@@ -156,7 +188,8 @@ majority_count_kernel(const ClusterState *__restrict__ states, int q, RefGrid g,
 __global__ void __launch_bounds__(128)
 majority_pick_kernel(const ClusterState *__restrict__ states, int q, RefGrid g, const uint8_t *__restrict__ packed,
                      const int *__restrict__ rows_arena, const int *__restrict__ crows, const int *__restrict__ ccount,
-                     const int *__restrict__ counts, uint8_t *__restrict__ maj_all, uint32_t *__restrict__ majw) {
+                     const unsigned long long *__restrict__ counts, uint8_t *__restrict__ maj_all,
+                     uint32_t *__restrict__ majw) {
     const ClusterState &st = states[q];
     if (st.status != 0) return;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,8 +203,9 @@ majority_pick_kernel(const ClusterState *__restrict__ states, int q, RefGrid g, 
     for (int j = 0; j < 8; ++j) {
         const int col = col_base + 4 * j;
         if (col < g.c0 || col >= g.c1 || nrows == 0) continue;
-        const int *cn = counts + ((long long)c * w + (col - g.c0)) * 4;
-        const int b = cn[0], p1 = cn[1], p2 = cn[2], p3 = cn[3];
+        const unsigned long long cn = counts[(long long)c * w + (col - g.c0)];
+        const int b = (int)(cn & 0xffff), p1 = (int)((cn >> 16) & 0xffff), p2 = (int)((cn >> 32) & 0xffff),
+                  p3 = (int)(cn >> 48);
         // symbol codes: gap 0, A 1, C 3, G 5, T 7
         int cnt[5] = {nrows - b, b - p1 - p2 + p3, p1 - p3, p2 - p3, p3};
         const int code[5] = {0, 1, 3, 5, 7};
@@ -224,13 +258,12 @@ hamming_packed_kernel(const ClusterState *__restrict__ states, int q, RefGrid g,
     if (c >= st.K) return;
     const int w = g.c1 - g.c0;
     const int thr = w < 5 ? 1 : (int)(0.2 * (double)w);
-    const uint32_t *rw = row_words(packed, g, rows_arena, crows[(long long)c * g.R + i]);
-    const uint32_t *mw = majw + (long long)c * g.n_words;
+    const uint4 *rw = reinterpret_cast<const uint4 *>(row_words(packed, g, rows_arena, crows[(long long)c * g.R + i]));
+    const uint4 *mw = reinterpret_cast<const uint4 *>(majw + (long long)c * g.n_words);
     // nibbles of the first / last chunk that lie outside the window do not count
     const int lead = g.c0 & 31, tail = g.c1 & 31;
-    int d = 0;
-    for (int k = lane; k < g.n_words; k += 32) {
-        const uint32_t x = __ldg(rw + k) ^ mw[k];
+    const int n_chunks = g.n_words >> 2;
+    auto differing = [&](uint32_t x, int k) {  // k = word of the window
         uint32_t z = (x | (x >> 1) | (x >> 2) | (x >> 3)) & NIB;
         if (k < 4 && lead) {
             // column of nibble j in this word: 4 j + (k & 3); keep those >= lead
@@ -242,7 +275,33 @@ hamming_packed_kernel(const ClusterState *__restrict__ states, int q, RefGrid g,
             const int n_j = tail > wlane ? (tail - wlane + 3) >> 2 : 0;  // nibbles j with 4 j + wlane < tail
             z &= n_j >= 8 ? 0xffffffffu : ((1u << (4 * n_j)) - 1u);
         }
-        d += __popc(z);
+        return __popc(z);
+    };
+    int d = 0;
+    for (int k0 = lane; k0 < n_chunks; k0 += 64) {  // two independent 128-bit loads in flight per lane
+        const int k1 = k0 + 32;
+        const uint4 x0 = __ldg(rw + k0);
+        const uint4 x1 = k1 < n_chunks ? __ldg(rw + k1) : make_uint4(0, 0, 0, 0);
+        const uint4 m0 = mw[k0];
+        const uint4 m1 = k1 < n_chunks ? mw[k1] : make_uint4(0, 0, 0, 0);
+        if (k0 == 0 || k0 == n_chunks - 1) {
+            d += differing(x0.x ^ m0.x, 4 * k0) + differing(x0.y ^ m0.y, 4 * k0 + 1) + differing(x0.z ^ m0.z, 4 * k0 + 2) +
+                 differing(x0.w ^ m0.w, 4 * k0 + 3);
+        } else {
+            const uint32_t e0 = x0.x ^ m0.x, e1 = x0.y ^ m0.y, e2 = x0.z ^ m0.z, e3 = x0.w ^ m0.w;
+            d += __popc((e0 | (e0 >> 1) | (e0 >> 2) | (e0 >> 3)) & NIB) + __popc((e1 | (e1 >> 1) | (e1 >> 2) | (e1 >> 3)) & NIB) +
+                 __popc((e2 | (e2 >> 1) | (e2 >> 2) | (e2 >> 3)) & NIB) + __popc((e3 | (e3 >> 1) | (e3 >> 2) | (e3 >> 3)) & NIB);
+        }
+        if (k1 < n_chunks) {
+            if (k1 == n_chunks - 1) {
+                d += differing(x1.x ^ m1.x, 4 * k1) + differing(x1.y ^ m1.y, 4 * k1 + 1) + differing(x1.z ^ m1.z, 4 * k1 + 2) +
+                     differing(x1.w ^ m1.w, 4 * k1 + 3);
+            } else {
+                const uint32_t e0 = x1.x ^ m1.x, e1 = x1.y ^ m1.y, e2 = x1.z ^ m1.z, e3 = x1.w ^ m1.w;
+                d += __popc((e0 | (e0 >> 1) | (e0 >> 2) | (e0 >> 3)) & NIB) + __popc((e1 | (e1 >> 1) | (e1 >> 2) | (e1 >> 3)) & NIB) +
+                     __popc((e2 | (e2 >> 1) | (e2 >> 2) | (e2 >> 3)) & NIB) + __popc((e3 | (e3 >> 1) | (e3 >> 2) | (e3 >> 3)) & NIB);
+            }
+        }
     }
     d = __reduce_add_sync(0xffffffffu, d);
     if (d > thr && lane == 0) {
@@ -253,7 +312,7 @@ hamming_packed_kernel(const ClusterState *__restrict__ states, int q, RefGrid g,
 
 // scratch ints a problem of R rows and a window of w columns / n_words words needs (K_max clusters)
 long long refgrid_scratch_ints(int R, int w, int n_words, int K_max) {
-    return (long long)K_max * R + 16 + 4LL * K_max * w + (long long)K_max * n_words + 64;
+    return (long long)K_max * R + 16 + 2LL * K_max * w + 2 + (long long)K_max * n_words + 64;
 }
 
 cudaError_t launch_refcheck_grid(cudaStream_t s, ClusterState *states, int q, const DTask &t, int K_max,
@@ -272,12 +331,14 @@ cudaError_t launch_refcheck_grid(cudaStream_t s, ClusterState *states, int q, co
     const int w = t.c1 - t.c0;
     int *crows = scratch;
     int *ccount = crows + (long long)K_max * g.R;
-    int *counts = ccount + 16;
-    uint32_t *majw = reinterpret_cast<uint32_t *>(counts + 4LL * K_max * w);
-    cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * 4 * (size_t)K_max * w, s);
+    // (8-byte aligned: K_max * R + 16 ints before it may be odd)
+    unsigned long long *counts = reinterpret_cast<unsigned long long *>(
+        (reinterpret_cast<uintptr_t>(ccount + 16) + 7) & ~(uintptr_t)7);
+    uint32_t *majw = reinterpret_cast<uint32_t *>(counts + (long long)K_max * w);
+    cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)K_max * w, s);
     if (e != cudaSuccess) return e;
     cluster_rows_kernel<<<1, 32 * K_max, 0, s>>>(states, q, g, mem_off, mem_rows, assign, crows, ccount);
-    const int col_groups = (g.n_words + 127) / 128;  // four warps of 32 words per CTA
+    const int col_groups = ((g.n_words >> 2) + 31) / 32;  // 32 chunks = 1,024 columns per CTA
     const int row_blocks = (n_member_rows + RG_ROWS - 1) / RG_ROWS + K_max;
     majority_count_kernel<<<dim3(col_groups, row_blocks), 128, 0, s>>>(states, q, g, packed, rows_arena, crows, ccount,
                                                                       counts);
