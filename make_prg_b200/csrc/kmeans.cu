@@ -1046,7 +1046,8 @@ cudaError_t launch_kmeans_group(cudaStream_t s, ClusterState *states, int q, con
             if (e != cudaSuccess) return e;
         }
     }
-    int G = std::max(1, std::min((sm_count * occ) / KM_NINIT, 32));
+    // as many CTAs per initialisation as stay co-resident (B200 at 136 registers: 148 x 3 / 10 = 44)
+    int G = std::max(1, std::min((sm_count * occ) / KM_NINIT, 64));
     if (const char *env = getenv("MPRG_KM_G")) G = std::max(1, std::min(atoi(env), G));  // debugging knob
     const dim3 grid((unsigned)(KM_NINIT * G));
     void *args[] = {(void *)&states, (void *)&q, (void *)&X, (void *)&dscratch, (void *)&iscratch,
