@@ -62,19 +62,28 @@ cluster_rows_kernel(const ClusterState *__restrict__ states, int q, RefGrid g, c
     const int *assign = assign_all + st.assign_off;
     int *out = crows + (long long)c * g.R;
     int total = 0;
-    for (int j0 = 0; j0 < st.n; j0 += 32) {
-        const int j = j0 + lane;
-        const bool mine = j < st.n && assign[j] == c;
-        const int m0 = mine ? mem_off[j] : 0;
-        const int cnt = mine ? mem_off[j + 1] - m0 : 0;
-        int incl = cnt;
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
+    // four chunks of 32 sequences per trip: their loads are issued together (the loop is bound by the latency
+    // of these reads: 313 dependent trips for 10,000 sequences took 470 us), the ordered placement follows
+    for (int j0 = 0; j0 < st.n; j0 += 128) {
+        int m0[4], cnt[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 32 * u + lane;
+            const bool mine = j < st.n && assign[j] == c;
+            m0[u] = mine ? mem_off[j] : 0;
+            cnt[u] = mine ? mem_off[j + 1] - m0[u] : 0;
         }
-        const int pos = total + incl - cnt;
-        for (int m = 0; m < cnt; ++m) out[pos + m] = mem_rows[m0 + m];
-        total += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int incl = cnt[u];
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const int pos = total + incl - cnt[u];
+            for (int m = 0; m < cnt[u]; ++m) out[pos + m] = mem_rows[m0[u] + m];
+            total += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
     if (lane == 0) ccount[c] = total;
 }
@@ -312,7 +321,7 @@ hamming_packed_kernel(const ClusterState *__restrict__ states, int q, RefGrid g,
 
 // scratch ints a problem of R rows and a window of w columns / n_words words needs (K_max clusters)
 long long refgrid_scratch_ints(int R, int w, int n_words, int K_max) {
-    return (long long)K_max * R + 16 + 2LL * K_max * w + 2 + (long long)K_max * n_words + 64;
+    return (long long)K_max * R + 16 + 2LL * K_max * w + 4 + (long long)K_max * n_words + 64;
 }
 
 cudaError_t launch_refcheck_grid(cudaStream_t s, ClusterState *states, int q, const DTask &t, int K_max,
@@ -331,9 +340,9 @@ cudaError_t launch_refcheck_grid(cudaStream_t s, ClusterState *states, int q, co
     const int w = t.c1 - t.c0;
     int *crows = scratch;
     int *ccount = crows + (long long)K_max * g.R;
-    // (8-byte aligned: K_max * R + 16 ints before it may be odd)
+    // (16-byte aligned: the packed majority words that follow are read as 128-bit vectors)
     unsigned long long *counts = reinterpret_cast<unsigned long long *>(
-        (reinterpret_cast<uintptr_t>(ccount + 16) + 7) & ~(uintptr_t)7);
+        (reinterpret_cast<uintptr_t>(ccount + 16) + 15) & ~(uintptr_t)15);
     uint32_t *majw = reinterpret_cast<uint32_t *>(counts + (long long)K_max * w);
     cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)K_max * w, s);
     if (e != cudaSuccess) return e;

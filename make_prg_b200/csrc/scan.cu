@@ -30,6 +30,8 @@
 // by one trip.  A TMA variant (per-warp shared-memory ring filled by cp.async.bulk on mbarriers) and a
 // persistent-grid variant with a global tile counter were built and measured slower on B200 for this
 // access pattern (profiles/r1_scan_variants.txt); they are not kept.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -45,6 +47,39 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
+}
+
+// ---- TMA (bulk async copy) variant: a tile whose rows are consecutive AND complete (the tile spans the whole
+// packed row) is one contiguous block of global memory, so ONE lane fetches it with ONE cp.async.bulk into the
+// warp's shared-memory slab and the warp waits on an mbarrier; the row loop then reads 128-bit vectors from
+// shared memory.  Many warps per SM keep many such copies in flight.  (Round 1 measured a ring of per-lane 2 KB
+// copies per warp, which serialised in the issue path.)
+constexpr int SCAN_TMA_SLAB = 8192;  // bytes per warp: 16 rows of 512 bytes (1,000-column loci)
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 // bit 4k+3 set iff nibble k of w is zero (the gap code), exact: no carry crosses a nibble
@@ -165,7 +200,7 @@ __device__ MPRG_GAP_INLINE void scan_gap_rows(uint32_t g, bool todo, const ScanL
     }
 }
 
-template <bool HAS_N>
+template <bool HAS_N, bool TMA>
 #ifndef MPRG_SCAN_MIN_BLOCKS
 #define MPRG_SCAN_MIN_BLOCKS 8  // 64 registers (11 words spilled): 32 resident warps per SM instead of 28, +6..11 % measured
 #endif
@@ -175,6 +210,13 @@ scan_kernel(const uint8_t *__restrict__ packed, const ScanUnit *__restrict__ uni
             uint32_t *__restrict__ colNOR, unsigned *__restrict__ colB) {
     const int lane = threadIdx.x & 31;
     const int ui = blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5);
+    __shared__ __align__(128) uint8_t s_slab[TMA ? SCAN_WARPS : 1][TMA ? SCAN_TMA_SLAB : 16];
+    __shared__ uint64_t s_bar[SCAN_WARPS];
+    if (TMA) {
+        if (threadIdx.x < SCAN_WARPS) mbar_init(&s_bar[threadIdx.x], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
     if (ui >= n_units) return;
     const ScanUnit t = units[ui];
     const int bn = t.ch_count;
@@ -228,14 +270,41 @@ scan_kernel(const uint8_t *__restrict__ packed, const ScanUnit *__restrict__ uni
                 dst[u] = ld_stream(reinterpret_cast<const uint4 *>(col_ptr + (long long)row_of(first_it + u) * t.stride));
         }
     };
+    // TMA: the whole tile in one bulk copy when it is one contiguous block that fits the slab
+    const uint8_t *slab = s_slab[TMA ? (threadIdx.x >> 5) : 0];
+    bool staged = false;
+    if (TMA) {
+        const long long tile_bytes = (long long)row_count * t.stride;
+        staged = rows == nullptr && t.ch_begin == 0 && bn * CHUNK_BYTES == t.stride && tile_bytes <= SCAN_TMA_SLAB;
+        if (staged) {
+            uint64_t *bar = &s_bar[threadIdx.x >> 5];
+            if (lane == 0) {
+                mbar_expect_tx(bar, (uint32_t)tile_bytes);
+                bulk_g2s(const_cast<uint8_t *>(slab), msa + (long long)t.row_begin * t.stride, (uint32_t)tile_bytes, bar);
+            }
+            mbar_wait(bar, 0);
+        }
+    }
+    const int slab_col = (chunk - t.ch_begin) << 4;
+    auto load_staged = [&](int first_it, uint4 *dst) {
+#pragma unroll
+        for (int u = 0; u < SCAN_UNROLL; ++u) {
+            const int rl = min((first_it + u) * rpw + lane_slot, last_row);
+            dst[u] = *reinterpret_cast<const uint4 *>(slab + rl * t.stride + slab_col);
+        }
+    };
     uint4 vnext[SCAN_UNROLL];
-    load_trip(0, vnext);
+    if (TMA && staged) load_staged(0, vnext);
+    else load_trip(0, vnext);
     // software pipelined by one trip: the loads of trip i+1 are in flight while trip i is processed
     for (int it0 = 0; it0 < n_iters; it0 += SCAN_UNROLL) {
         uint4 v[SCAN_UNROLL];
 #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; ++u) v[u] = vnext[u];
-        if (it0 + SCAN_UNROLL < n_iters) load_trip(it0 + SCAN_UNROLL, vnext);
+        if (it0 + SCAN_UNROLL < n_iters) {
+            if (TMA && staged) load_staged(it0 + SCAN_UNROLL, vnext);
+            else load_trip(it0 + SCAN_UNROLL, vnext);
+        }
         uint32_t gm[SCAN_UNROLL];  // gap mask of my chunk in each of the rows (0 outside the window)
 #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; u += 2) {
@@ -296,10 +365,15 @@ cudaError_t launch_scan(cudaStream_t stream, bool has_n, const uint8_t *packed, 
                         int n_units, const int *d_rows, uint32_t *colOR, uint32_t *colNOR, unsigned *colB) {
     if (n_units <= 0) return cudaSuccess;
     const int grid = (n_units + SCAN_WARPS - 1) / SCAN_WARPS;
+    // MPRG_SCAN_TMA=1: tiles that are one contiguous block of rows come in by one bulk async copy per warp
+    // (profiles/r2_scan_tma.txt has the comparison)
+    static const bool tma = getenv("MPRG_SCAN_TMA") != nullptr;
     if (has_n)
-        scan_kernel<true><<<grid, SCAN_THREADS, 0, stream>>>(packed, d_units, n_units, d_rows, colOR, colNOR, colB);
+        scan_kernel<true, false><<<grid, SCAN_THREADS, 0, stream>>>(packed, d_units, n_units, d_rows, colOR, colNOR, colB);
+    else if (tma)
+        scan_kernel<false, true><<<grid, SCAN_THREADS, 0, stream>>>(packed, d_units, n_units, d_rows, colOR, colNOR, colB);
     else
-        scan_kernel<false><<<grid, SCAN_THREADS, 0, stream>>>(packed, d_units, n_units, d_rows, colOR, colNOR, colB);
+        scan_kernel<false, false><<<grid, SCAN_THREADS, 0, stream>>>(packed, d_units, n_units, d_rows, colOR, colNOR, colB);
     return cudaGetLastError();
 }
 
