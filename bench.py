@@ -36,9 +36,31 @@ sys.path.insert(0, str(REPO))
 LOCI_PER_GPU = 1000
 ROWS, COLS = 200, 1000
 MAX_NESTING, MIN_MATCH = 5, 7
-# dram__bytes_read.sum + dram__bytes_write.sum of one root-level scan launch of this workload from the
-# ncu --set full capture committed under profiles/ (per launch, like `achieved`); None if not captured
-NCU_TRAFFIC_BYTES = 107.68e6  # profiles/r1_scan_kernel_ncu_v12.txt: 104.32 MB read + 3.36 MB written
+
+
+def ncu_counters(name, wanted):
+    """Counters of the committed `ncu --set full` summary profiles/r2_ncu_<name>.txt (scripts/ncu_summary.py
+    output: metric, value, unit per line); {} when the file is not there."""
+    f = REPO / "profiles" / f"r2_ncu_{name}.txt"
+    out = {}
+    if not f.exists():
+        return out
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+    for line in f.read_text().splitlines():
+        parts = line.split("\t")
+        if len(parts) >= 2 and parts[0] in wanted:
+            try:
+                out[parts[0]] = float(parts[1].replace(",", "")) * scale.get(parts[2] if len(parts) > 2 else "", 1.0)
+            except ValueError:
+                pass
+    return out
+
+
+def ncu_scan_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one root-level scan launch of this workload, read from
+    the committed capture (per launch, like `achieved`); None if not captured."""
+    c = ncu_counters("scan_kernel", ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    return sum(c.values()) if len(c) == 2 else None
 CACHE = Path(os.environ.get("MPRG_BENCH_CACHE", "/tmp/mprg_bench_cache"))
 CPU_BASELINE_SAMPLE = 100
 
@@ -404,6 +426,7 @@ def main():
         flush.zero_()
     barrier()
     ctx.scan_log(reset=True)
+    ctx.kmeans_stats(reset=True)
     launches0 = ctx.launch_count()
     with ClockSampler(local_rank) as clocks:
         t_dev = 0.0
@@ -420,6 +443,7 @@ def main():
     barrier()
     launches = ctx.launch_count() - launches0
     log_bytes, log_ms = ctx.scan_log(reset=True)
+    km = ctx.kmeans_stats(reset=True)
 
     # ---- roofline pass: the dominant kernel (root-level column scan of the whole batch) alone on one
     # stream, CUDA events around the kernel (mprg_scan_log), L2 flushed between launches ----
@@ -527,7 +551,9 @@ def main():
     if len(iso_bytes):
         achieved = float(iso_bytes.sum() / (iso_ms.sum() * 1e-3) / 1e9)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES,
+                "traffic": ncu_scan_traffic(),
+                "traffic_source": "profiles/r2_ncu_scan_kernel.txt (ncu --set full of the same launch: "
+                                  "dram__bytes_read.sum + dram__bytes_write.sum)",
                 "kernel": "scan_kernel<false>, root-level launch over the whole batch, timed alone",
                 "bytes_per_launch": float(iso_bytes.mean()), "ms_per_launch": float(iso_ms.mean()),
                 "launches_timed": int(len(iso_bytes)), "peak_source": peak_src,
@@ -589,6 +615,18 @@ def main():
                               "h2d_bytes_per_step": text_copies["h2d_bytes"] // len(text_steps)}},
         "gpu_launches": int(launches),
         "roofline": roof,
+        # the time-dominant kernel of a step is not bandwidth-bound: float64 KMeans of thousands of tiny problems
+        # (sequential-order sums), reported as problems/s with its pipe counters
+        "kmeans": {"kernel": "kmeans_kernel_w32 / kmeans_kernel: one warp (CTA) per initialisation, 10 per problem",
+                   "ms_per_step": km["ms"] / args.steps, "launches_per_step": km["launches"] / args.steps,
+                   "problems_per_step": km["problems"] / args.steps,
+                   "problem_fits_per_s": km["problems"] / (km["ms"] * 1e-3) if km["ms"] > 0 else None,
+                   "timing": "CUDA events around every KMeans launch inside the timed steps (rank 0)",
+                   "ncu": dict(ncu_counters("kmeans_kernel_w32", (
+                       "gpu__time_duration.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+                       "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                       "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread")),
+                       source="profiles/r2_ncu_kmeans_kernel_w32.txt (largest launch: 2,489 problems x 10)")},
         "cpu_baseline": {"value": cpu_v, "unit": "loci/s", "cores": 1, "kind": "port",
                          "sample": f"first {sample} loci of the workload, oracle/make_prg_oracle.py, "
                                    f"{cpu_dt:.1f} s"},

@@ -93,6 +93,10 @@ int64_t mprg_launch_count(const mprg_ctx *ctx);
 #define MPRG_PATH_DEDUPE_GRID 6       /* whole-grid de-duplication */
 #define MPRG_PATH_COUNT 8
 int mprg_path_counts(mprg_ctx *ctx, int64_t *out, int reset);
+/* Device time (ms, CUDA events around every launch) of the KMeans launches of the level loop since the last reset,
+ * their number, and the problems they covered (a launch covers every clustering problem of its level; a problem
+ * that has left the loop costs an early exit): bench.py's "kmeans" object.  Worker contexts included. */
+int mprg_kmeans_stats(mprg_ctx *ctx, double *ms, int64_t *launches, int64_t *problems, int reset);
 /* device time (ms, CUDA events on the context's stream) and algorithmic bytes of the column-scan
  * kernel accumulated since the last reset; used by bench.py for the roofline object */
 int mprg_scan_stats(mprg_ctx *ctx, double *ms, double *bytes, int64_t *launches, int reset);

@@ -57,6 +57,7 @@ SIGNATURES = {
     "mprg_launch_count": (I64, [P]),
     "mprg_scan_stats": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(I64), C.c_int]),
     "mprg_path_counts": (C.c_int, [P, P, C.c_int]),
+    "mprg_kmeans_stats": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(I64), C.POINTER(I64), C.c_int]),
     "mprg_set_workers": (C.c_int, [P, I32]),
     "mprg_copy_stats": (C.c_int, [P, C.POINTER(I64), C.POINTER(I64), C.c_int]),
     "mprg_timer": (C.c_int, [P, C.c_int, C.POINTER(C.c_double)]),

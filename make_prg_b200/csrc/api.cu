@@ -107,6 +107,29 @@ extern "C" int mprg_copy_stats(mprg_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_b
     return MPRG_OK;
 }
 
+extern "C" int mprg_kmeans_stats(mprg_ctx *ctx, double *ms, int64_t *launches, int64_t *problems, int reset) {
+    if (!ctx) return MPRG_E_BAD_ARG;
+    double t = ctx->km_ms;
+    long long l = ctx->km_launches, p = ctx->km_problems;
+    for (mprg_ctx *w : ctx->workers) {
+        t += w->km_ms;
+        l += w->km_launches;
+        p += w->km_problems;
+    }
+    if (ms) *ms = t;
+    if (launches) *launches = l;
+    if (problems) *problems = p;
+    if (reset) {
+        ctx->km_ms = 0;
+        ctx->km_launches = ctx->km_problems = 0;
+        for (mprg_ctx *w : ctx->workers) {
+            w->km_ms = 0;
+            w->km_launches = w->km_problems = 0;
+        }
+    }
+    return MPRG_OK;
+}
+
 extern "C" int mprg_path_counts(mprg_ctx *ctx, int64_t *out, int reset) {
     if (!ctx || !out) return MPRG_E_BAD_ARG;
     for (int k = 0; k < MPRG_PATH_COUNT; ++k) {

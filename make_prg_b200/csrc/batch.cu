@@ -211,6 +211,9 @@ extern "C" void mprg_destroy(mprg_ctx *ctx) {
     ctx->h_b.release();
     ctx->h_c.release();
     ctx->h_d.release();
+    for (int a = 0; a < 2; ++a)
+        for (int r = 0; r < 12; ++r)
+            if (ctx->ev_km[a][r]) cudaEventDestroy(ctx->ev_km[a][r]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);

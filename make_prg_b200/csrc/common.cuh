@@ -173,6 +173,13 @@ struct mprg_ctx {
     mprg::PinnedBuf h_cnt;  // the counter block the host reads twice per level
     bool pending_scan = false;  // a scan launch whose events have not been read yet
     double pending_scan_bytes = 0;
+    // device time of the KMeans launches of the level loop (mprg_kmeans_stats): event pairs of the current
+    // clustering pass, read after the next synchronisation
+    cudaEvent_t ev_km[2][12] = {};
+    int km_pending = 0;
+    long long km_pending_problems = 0;
+    double km_ms = 0;
+    long long km_launches = 0, km_problems = 0;
     // scratch (pinned host)
     mprg::PinnedBuf h_a, h_b, h_c, h_d;
     // packed arenas of freed batches, kept for the next batch of about the same size: cudaMalloc and

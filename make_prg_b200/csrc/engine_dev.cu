@@ -1069,6 +1069,14 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
     const int any_n = batch->any_n ? 1 : 0;
     // device time of the level's scan launch, read after the next synchronisation (roofline object of bench.py)
     auto account = [&]() {
+        for (int r = 0; r < ctx->km_pending; ++r) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->ev_km[0][r], ctx->ev_km[1][r]) == cudaSuccess) ctx->km_ms += ms;
+        }
+        ctx->km_launches += ctx->km_pending;
+        ctx->km_problems += ctx->km_pending_problems;
+        ctx->km_pending = 0;
+        ctx->km_pending_problems = 0;
         if (!ctx->pending_scan) return;
         ctx->pending_scan = false;
         float ms = 0;
@@ -1271,8 +1279,19 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
                     // a problem with n distinct sequences stops at K == n: rounds 2 .. max n - 1 at most
                     const int last_round = std::min(10, cnt->max_n - 1);
                     for (int round = 2; round <= last_round; ++round) {
+                        const int slot = ctx->km_pending < 12 ? ctx->km_pending : -1;
+                        if (slot >= 0) {
+                            for (int a = 0; a < 2; ++a)
+                                if (!ctx->ev_km[a][slot]) MPRG_CUDA(ctx, cudaEventCreate(&ctx->ev_km[a][slot]));
+                            MPRG_CUDA(ctx, cudaEventRecord(ctx->ev_km[0][slot], s));
+                        }
                         MPRG_CUDA(ctx, launch_kmeans(s, states, np, V[V_X].as<double>(), d_kmd, d_kmi, d_asg, d_newlab,
                                                      d_tickets, cnt->max_elements));
+                        if (slot >= 0) {
+                            MPRG_CUDA(ctx, cudaEventRecord(ctx->ev_km[1][slot], s));
+                            ctx->km_pending++;
+                            ctx->km_pending_problems += np;
+                        }
                         MPRG_CUDA(ctx, launch_refcheck(s, states, np, V[V_G].as<uint8_t>(), d_memoff, d_memrows, d_asg,
                                                        d_maj, 10));
                         ctx->launches += 2;

@@ -92,6 +92,12 @@ class Context:
         self._check(self.lib.mprg_path_counts(self.handle, ptr(out), int(reset)))
         return dict(zip(self.PATHS, out.tolist()))
 
+    def kmeans_stats(self, reset=False):
+        """Device ms / launches / problems of the level loop's KMeans launches since the last reset."""
+        ms, n, p = C.c_double(), C.c_int64(), C.c_int64()
+        self._check(self.lib.mprg_kmeans_stats(self.handle, C.byref(ms), C.byref(n), C.byref(p), int(reset)))
+        return {"ms": ms.value, "launches": n.value, "problems": p.value}
+
     def copy_stats(self, reset=False):
         a, b = C.c_int64(), C.c_int64()
         self._check(self.lib.mprg_copy_stats(self.handle, C.byref(a), C.byref(b), int(reset)))
