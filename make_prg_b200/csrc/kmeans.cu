@@ -843,10 +843,41 @@ kmeans_prepare_kernel(const ClusterState *__restrict__ states, const double *__r
 
 // grid (problems, KM_NINIT): every CTA runs one initialisation; the last CTA of a problem to finish
 // (ticket counter) does the selection, the prediction and the loop control of kmeans_cluster_seqs
+// Scratch of ONE initialisation in shared memory (doubles then ints), laid out for the problem's own K: the
+// tiny problems of a pangenome level (n <= 8, F <= 70, K = 2..3) spend their time in sequential float64 sections
+// on one lane, and every store-then-load of the global scratch was an L2 round trip.
+__device__ __forceinline__ long long km_smem_bytes(int n, int F, int K) {
+    const long long d = 2LL * K * F + (long long)n * K + 8LL * n + (long long)K * K + 4LL * K + 8;
+    return 8 * d + 4 * 2LL * n;
+}
+__device__ __forceinline__ void km_bind_smem(KM &k, double *sm) {
+    const int n = k.n, F = k.F, K = k.K;
+    double *d = sm;
+    k.ca = d; d += (long long)K * F;
+    k.cb = d; d += (long long)K * F;
+    k.lb = d; d += (long long)n * K;
+    k.ub = d; d += n;
+    k.closest = d; d += n;
+    k.cum = d; d += n;
+    k.D = d; d += 4LL * n;
+    k.dist = d; d += n;
+    k.half = d; d += K * K;
+    k.nxt = d; d += K;
+    k.shift = d; d += K;
+    k.wts = d; d += K;
+    k.cc = d; d += K;
+    k.res = d; d += 8;
+    int *ii = reinterpret_cast<int *>(d);
+    k.labels = ii; ii += n;
+    k.labels_old = ii;
+}
+
+extern __shared__ double km_dyn_smem[];
+
 __device__ __forceinline__ void
 kmeans_kernel_body(ClusterState *__restrict__ states, const double *__restrict__ X_all,
                    double *__restrict__ dscratch, int *__restrict__ iscratch, int *__restrict__ assign_all,
-                   int *__restrict__ newlab_all, int *__restrict__ tickets) {
+                   int *__restrict__ newlab_all, int *__restrict__ tickets, int smem_bytes) {
     __shared__ double s_scalar[4];
     __shared__ int s_int[8];
     ClusterState &st = states[blockIdx.x];
@@ -857,7 +888,21 @@ kmeans_kernel_body(ClusterState *__restrict__ states, const double *__restrict__
     int *i0 = iscratch + st.kmi_off;
     KM k;
     km_bind_init(k, n, F, K, X0, d0, i0, init);
+    const bool in_smem = km_smem_bytes(n, F, K) <= (long long)smem_bytes;
+    KM g = k;  // where the selection step (any CTA of the problem) reads this initialisation's results
+    if (in_smem) km_bind_smem(k, km_dyn_smem);
     kmeans_run_init(k, init, s_scalar, s_int);
+    if (in_smem) {
+        // results out: inertia + centre selector, labels, final centres
+        const double *Cs = (k.res[1] == 0.0) ? k.ca : k.cb;
+        double *Cg = (k.res[1] == 0.0) ? g.ca : g.cb;
+        for (int p = threadIdx.x; p < K * F; p += blockDim.x) Cg[p] = Cs[p];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) g.labels[i] = k.labels[i];
+        if (threadIdx.x == 0) {
+            g.res[0] = k.res[0];
+            g.res[1] = k.res[1];
+        }
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_int[7] = atomicAdd(&tickets[blockIdx.x], 1);
@@ -887,8 +932,8 @@ kmeans_kernel_body(ClusterState *__restrict__ states, const double *__restrict__
 __global__ void __launch_bounds__(KM_THREADS)
 kmeans_kernel(ClusterState *__restrict__ states, const double *__restrict__ X_all,
               double *__restrict__ dscratch, int *__restrict__ iscratch, int *__restrict__ assign_all,
-              int *__restrict__ newlab_all, int *__restrict__ tickets) {
-    kmeans_kernel_body(states, X_all, dscratch, iscratch, assign_all, newlab_all, tickets);
+              int *__restrict__ newlab_all, int *__restrict__ tickets, int smem_bytes) {
+    kmeans_kernel_body(states, X_all, dscratch, iscratch, assign_all, newlab_all, tickets, smem_bytes);
 }
 
 // The same for the one-warp CTAs of a pangenome level (thousands of problems with n <= 8, F <= 70): the level
@@ -898,8 +943,8 @@ kmeans_kernel(ClusterState *__restrict__ states, const double *__restrict__ X_al
 __global__ void __launch_bounds__(32, 32)
 kmeans_kernel_w32(ClusterState *__restrict__ states, const double *__restrict__ X_all,
                   double *__restrict__ dscratch, int *__restrict__ iscratch, int *__restrict__ assign_all,
-                  int *__restrict__ newlab_all, int *__restrict__ tickets) {
-    kmeans_kernel_body(states, X_all, dscratch, iscratch, assign_all, newlab_all, tickets);
+                  int *__restrict__ newlab_all, int *__restrict__ tickets, int smem_bytes) {
+    kmeans_kernel_body(states, X_all, dscratch, iscratch, assign_all, newlab_all, tickets, smem_bytes);
 }
 
 // stand-alone problem (mprg_kmeans): prepare <<<1>>> then grid (1, KM_NINIT)
@@ -1078,11 +1123,18 @@ cudaError_t launch_kmeans(cudaStream_t s, ClusterState *states, int n_probs, con
     int threads = max_elements <= 2048 ? 32 : (max_elements <= 16384 ? 64 : KM_THREADS);
     if (const char *e = getenv("MPRG_KM_THREADS")) threads = std::max(32, std::min(atoi(e) & ~31, KM_THREADS));
     static const bool w32 = getenv("MPRG_KM_NO_W32") == nullptr;
-    if (threads == 32 && w32)
-        kmeans_kernel_w32<<<dim3(n_probs, KM_NINIT), 32, 0, s>>>(states, X, dscratch, iscratch, assign, newlab, tickets);
-    else
-        kmeans_kernel<<<dim3(n_probs, KM_NINIT), threads, 0, s>>>(states, X, dscratch, iscratch, assign, newlab,
-                                                                  tickets);
+    // shared-memory scratch per initialisation (problems that do not fit keep the global scratch): 4 KB keep 32
+    // one-warp CTAs per SM, 16 KB are free for the few big CTAs; MPRG_KM_SMEM overrides (0 = global scratch only)
+    static const int smem_env = getenv("MPRG_KM_SMEM") ? atoi(getenv("MPRG_KM_SMEM")) : -1;
+    if (threads == 32 && w32) {
+        const int smem = smem_env >= 0 ? smem_env : 4096;
+        kmeans_kernel_w32<<<dim3(n_probs, KM_NINIT), 32, smem, s>>>(states, X, dscratch, iscratch, assign, newlab, tickets,
+                                                                   smem);
+    } else {
+        const int smem = smem_env >= 0 ? smem_env : 16384;
+        kmeans_kernel<<<dim3(n_probs, KM_NINIT), threads, smem, s>>>(states, X, dscratch, iscratch, assign, newlab,
+                                                                     tickets, smem);
+    }
     return cudaGetLastError();
 }
 
