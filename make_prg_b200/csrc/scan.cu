@@ -352,11 +352,19 @@ scan_kernel(const uint8_t *__restrict__ packed, const ScanUnit *__restrict__ uni
         }
     }
     if (lane_slot == 0 && chunk_valid) {
+        // col_off and the chunk base are multiples of 32 columns, so the lane's 4 words are 16-byte aligned:
+        // two 64-bit reductions per array instead of four 32-bit ones (the publishing atomics measured ~6 % of
+        // the 105 MB launch)
         const long long word = (((long long)t.col_off + (colbase - a0)) >> 3);
+        unsigned long long *o64 = reinterpret_cast<unsigned long long *>(colOR + word);
+        unsigned long long *n64 = reinterpret_cast<unsigned long long *>(colNOR + word);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (a_or[j]) atomicOr(&colOR[word + j], a_or[j]);
-            if (~a_and[j]) atomicOr(&colNOR[word + j], ~a_and[j]);  // published as OR of complements
+        for (int j = 0; j < 2; ++j) {
+            const unsigned long long vo = (unsigned long long)a_or[2 * j] | ((unsigned long long)a_or[2 * j + 1] << 32);
+            const unsigned long long vn =
+                (unsigned long long)(~a_and[2 * j]) | ((unsigned long long)(~a_and[2 * j + 1]) << 32);
+            if (vo) atomicOr(&o64[j], vo);
+            if (vn) atomicOr(&n64[j], vn);  // published as OR of complements
         }
     }
 }
