@@ -743,9 +743,10 @@ expand_clusters_kernel(DevCounters *C, ClusterTaskArrays ct, ProblemArrays pa, c
 // ---- PRG strings on the device (recursion_tree.py:194-300, prg_builder.py:100-110) -------------------------
 // Loci without RYKMSW: the distinct ungapped rows of a leaf are its alleles, so the PRG of a locus is the
 // pre-order concatenation of allele strings and site markers.  allele_len: ungapped length of every allele;
-// prg_measure: length / sites / nodes per locus (one thread per locus walks its tree); a prefix sum gives the
-// position of every locus in the blob; prg_write walks the tree again, writes the markers and tells every
-// allele where it goes; the extraction kernel then cuts the alleles straight into the blob.
+// leaf_len: text length of every leaf; prg_walk: one thread per locus walks its tree once and records where
+// every node's text starts and ends and its site number; a prefix sum gives the position of every locus in the
+// blob; prg_emit (one thread per node) writes the markers and tells every allele where it goes; the extraction
+// kernel then cuts the alleles straight into the blob.
 struct PrgInfo {
     long long off, len;
     int n_sites, n_nodes, status, pad;
@@ -802,17 +803,18 @@ leaf_len_kernel(const DNode *__restrict__ nodes, int n_nodes, const int *__restr
     leaf_len[ni] = sum;
 }
 
-// WRITE == false: measure; WRITE == true: cluster markers into the blob, and for every leaf where its text
-// starts (leaf_at) and its site number (leaf_site, 0 = single allele) -- leaf_write_kernel does the rest
-template <bool WRITE>
+// one thread per locus walks its tree once (pre-order, the order site numbers are handed out in) and records
+// for every node where its text starts and ends relative to the locus (node_at / node_end) and its site number
+// (node_site; 0 = none); lengths, sites and node counts per locus go to info.  Everything that writes is then
+// per node (prg_emit_kernel).
 __global__ void __launch_bounds__(128)
 prg_walk_kernel(const DNode *__restrict__ nodes, const DLocus *__restrict__ loci, int nl,
-                const long long *__restrict__ leaf_len, PrgInfo *__restrict__ info, long long *__restrict__ leaf_at,
-                int *__restrict__ leaf_site, char *__restrict__ blob, int *__restrict__ err) {
+                const long long *__restrict__ leaf_len, PrgInfo *__restrict__ info, long long *__restrict__ node_at,
+                long long *__restrict__ node_end, int *__restrict__ node_site, int *__restrict__ err) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nl) return;
     if (loci[i].status != MPRG_LOCUS_OK) {
-        if (!WRITE) info[i] = PrgInfo{0, 0, 0, 0, loci[i].status, 0};
+        info[i] = PrgInfo{0, 0, 0, 0, loci[i].status, 0};
         return;
     }
     int st_node[PRG_STACK], st_next[PRG_STACK], st_site[PRG_STACK];
@@ -820,42 +822,37 @@ prg_walk_kernel(const DNode *__restrict__ nodes, const DLocus *__restrict__ loci
     st_node[0] = i;  // the root of locus i is node i
     st_next[0] = 0;
     st_site[0] = 0;
-    long long at = WRITE ? info[i].off : 0;
+    long long at = 0;
     int site = 5, n_nodes = 0;
     while (depth >= 0) {
         const int ni = st_node[depth];
         const DNode nd = nodes[ni];
         if (st_next[depth] == 0) {
             ++n_nodes;
+            node_at[ni] = at;
             if (nd.kind == MPRG_NODE_LEAF) {
                 if (nd.allele_count == 1) {
-                    if (WRITE) {
-                        leaf_at[ni] = at;
-                        leaf_site[ni] = 0;
-                    }
+                    node_site[ni] = 0;
                     at += leaf_len[ni];
                 } else {
                     const int sn = site;
                     site += 2;
-                    if (WRITE) {
-                        leaf_at[ni] = at;
-                        leaf_site[ni] = sn;
-                    }
+                    node_site[ni] = sn;
                     // " sn " a1 " sn+1 " a2 ... " sn+1 " ak " sn "
                     at += 2LL * marker_len(sn) + (long long)(nd.allele_count - 1) * marker_len(sn + 1) + leaf_len[ni];
                 }
+                node_end[ni] = at;
                 --depth;
                 continue;
             }
             if (nd.kind == MPRG_NODE_CLUSTER) {
                 st_site[depth] = site;
                 site += 2;
-                if (WRITE) marker_put(blob + at, st_site[depth]);
                 at += marker_len(st_site[depth]);
             }
+            node_site[ni] = st_site[depth];
         } else if (nd.kind == MPRG_NODE_CLUSTER) {
             const int m = st_next[depth] < nd.n_children ? st_site[depth] + 1 : st_site[depth];  // after a child
-            if (WRITE) marker_put(blob + at, m);
             at += marker_len(m);
         }
         if (st_next[depth] < nd.n_children) {
@@ -870,27 +867,41 @@ prg_walk_kernel(const DNode *__restrict__ nodes, const DLocus *__restrict__ loci
             st_next[depth] = 0;
             st_site[depth] = 0;
         } else {
+            node_end[ni] = at;
             --depth;
         }
     }
-    if (!WRITE) info[i] = PrgInfo{0, at, (site - 5) / 2, n_nodes, MPRG_LOCUS_OK, 0};
+    info[i] = PrgInfo{0, at, (site - 5) / 2, n_nodes, MPRG_LOCUS_OK, 0};
 }
 
-// one thread per leaf: where each of its alleles goes (items[a].out_off) and the markers between them
+// one thread per node: the opening marker of a cluster node, the marker that follows a child of a cluster node
+// (" s+1 " between children, " s " after the last), and for a leaf where each of its alleles goes
+// (items[a].out_off) with the markers between them.  node_at < 0: the walk never reached the node.
 __global__ void __launch_bounds__(256)
-leaf_write_kernel(const DNode *__restrict__ nodes, int n_nodes, const DLocus *__restrict__ loci, int l0,
-                  const int *__restrict__ allele_len, const long long *__restrict__ leaf_at,
-                  const int *__restrict__ leaf_site, ExtractItem *__restrict__ items, char *__restrict__ blob) {
+prg_emit_kernel(const DNode *__restrict__ nodes, int n_nodes, const DLocus *__restrict__ loci, int l0,
+                const PrgInfo *__restrict__ info, const int *__restrict__ allele_len,
+                const long long *__restrict__ node_at, const long long *__restrict__ node_end,
+                const int *__restrict__ node_site, ExtractItem *__restrict__ items, char *__restrict__ blob) {
     const int ni = blockIdx.x * blockDim.x + threadIdx.x;
     if (ni >= n_nodes) return;
     const DNode nd = nodes[ni];
-    if (nd.kind != MPRG_NODE_LEAF || nd.allele_count <= 0 || loci[nd.locus - l0].status != MPRG_LOCUS_OK) return;
-    long long at = leaf_at[ni];
+    if (loci[nd.locus - l0].status != MPRG_LOCUS_OK || node_at[ni] < 0) return;
+    char *base = blob + info[nd.locus - l0].off;
+    if (nd.parent >= 0) {
+        const DNode pa = nodes[nd.parent];
+        if (pa.kind == MPRG_NODE_CLUSTER) {
+            const int ps = node_site[nd.parent];
+            marker_put(base + node_end[ni], ni - pa.first_child + 1 < pa.n_children ? ps + 1 : ps);
+        }
+    }
+    if (nd.kind == MPRG_NODE_CLUSTER) marker_put(base + node_at[ni], node_site[ni]);
+    if (nd.kind != MPRG_NODE_LEAF || nd.allele_count <= 0) return;
+    long long at = (base - blob) + node_at[ni];
     if (nd.allele_count == 1) {
         items[nd.allele_first].out_off = at;
         return;
     }
-    const int sn = leaf_site[ni];
+    const int sn = node_site[ni];
     marker_put(blob + at, sn);
     at += marker_len(sn);
     for (int a = 0; a < nd.allele_count; ++a) {
@@ -1394,14 +1405,17 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         int *d_len = V[V_OUTLEN].as<int>();
         ExtractItem *d_items = V[V_ITEMS].as<ExtractItem>();
         int *d_errflag = &d_cnt->err;
-        MPRG_CUDA(ctx, V[V_LEAF].reserve((sizeof(long long) * 2 + sizeof(int)) * (size_t)std::max(n_nodes, 1) + 64));
+        const size_t nn1 = (size_t)std::max(n_nodes, 1);
+        MPRG_CUDA(ctx, V[V_LEAF].reserve((sizeof(long long) * 3 + sizeof(int)) * nn1 + 64));
         long long *d_leaf_len = V[V_LEAF].as<long long>();
-        long long *d_leaf_at = d_leaf_len + std::max(n_nodes, 1);
-        int *d_leaf_site = reinterpret_cast<int *>(d_leaf_at + std::max(n_nodes, 1));
+        long long *d_node_at = d_leaf_len + nn1;
+        long long *d_node_end = d_node_at + nn1;
+        int *d_node_site = reinterpret_cast<int *>(d_node_end + nn1);
+        MPRG_CUDA(ctx, cudaMemsetAsync(d_node_at, 0xFF, sizeof(long long) * nn1, s));  // < 0: not reached by the walk
         if (na > 0) allele_len_kernel<<<(na + 3) / 4, 128, 0, s>>>(batch->d_packed, d_items, na, d_len);
         leaf_len_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(V[V_NODES].as<DNode>(), n_nodes, d_len, d_leaf_len);
-        prg_walk_kernel<false><<<(nl + 127) / 128, 128, 0, s>>>(V[V_NODES].as<DNode>(), d_loci, nl, d_leaf_len, d_info,
-                                                               d_leaf_at, d_leaf_site, nullptr, d_errflag);
+        prg_walk_kernel<<<(nl + 127) / 128, 128, 0, s>>>(V[V_NODES].as<DNode>(), d_loci, nl, d_leaf_len, d_info, d_node_at,
+                                                        d_node_end, d_node_site, d_errflag);
         prg_offsets_kernel<<<1, 1024, 0, s>>>(d_info, nl, d_total);
         ctx->launches += 4;
         MPRG_CUDA(ctx, cudaGetLastError());
@@ -1426,13 +1440,12 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         PinnedBlock blob = pinned_acquire((size_t)std::max<long long>(blob_bytes, 1));
         if (!blob.p) MPRG_FAIL(ctx, MPRG_E_CUDA, "pinned allocation for the result failed");
         MPRG_CUDA(ctx, V[V_OUT].reserve((size_t)std::max<long long>(blob_bytes, 1)));
-        prg_walk_kernel<true><<<(nl + 127) / 128, 128, 0, s>>>(V[V_NODES].as<DNode>(), d_loci, nl, d_leaf_len, d_info,
-                                                              d_leaf_at, d_leaf_site, V[V_OUT].as<char>(), d_errflag);
-        leaf_write_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(V[V_NODES].as<DNode>(), n_nodes, d_loci, l_begin, d_len,
-                                                              d_leaf_at, d_leaf_site, d_items, V[V_OUT].as<char>());
+        prg_emit_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(V[V_NODES].as<DNode>(), n_nodes, d_loci, l_begin, d_info,
+                                                            d_len, d_node_at, d_node_end, d_node_site, d_items,
+                                                            V[V_OUT].as<char>());
         if (na > 0)
             MPRG_CUDA(ctx, launch_extract(s, batch->d_packed, d_items, na, V[V_OUT].as<uint8_t>(), d_len));
-        ctx->launches += 3;
+        ctx->launches += 2;
         MPRG_CUDA(ctx, cudaGetLastError());
         if (blob_bytes > 0) MPRG_CUDA(ctx, mprg::copy_d2h(ctx, blob.p, V[V_OUT].p, (size_t)blob_bytes, s));
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_info, d_info, sizeof(PrgInfo) * (size_t)nl, s));
