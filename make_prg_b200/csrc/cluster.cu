@@ -124,6 +124,146 @@ __device__ bool same_ungapped(const uint8_t *a, const uint8_t *b, int w) {
     }
 }
 
+// Small tasks (most of a pangenome level: tens of thousands of tasks of a few columns) take one WARP each.
+// Rows are taken 32 at a time in row order; a row is compared with the distinct rows found so far (a short
+// list in shared memory whose position IS the first-seen group number) and, if new, with the other new rows
+// of its 32 (match.any), so the work per row is O(#distinct) and there is no block barrier.  Same outputs as
+// dedupe_kernel (group, ulen, leaders, leader_len, the counts).
+constexpr int DW_ROWS = 256, DW_WARPS = 4;
+// one word into the running key: the full finaliser per word (a multiply and a fold alone let differences in
+// the top nibbles of consecutive words cancel -- found by the verification below); still a bijection of x
+__device__ __forceinline__ uint64_t word_step(uint64_t h, uint64_t x) { return mix64(h ^ x) + 0x9e3779b97f4a7c15ULL; }
+__device__ __forceinline__ bool dedupe_small(int R, int w) { return R <= DW_ROWS && (long long)R * w <= 16384; }
+
+__global__ void __launch_bounds__(DW_WARPS * 32)
+dedupe_warp_kernel(const DTask *__restrict__ tasks, int n_tasks, const long long *__restrict__ g_off,
+                   const uint8_t *__restrict__ G, const long long *__restrict__ row_off, int *__restrict__ group,
+                   int *__restrict__ ulen, int *__restrict__ leaders, int *__restrict__ leader_len,
+                   int *__restrict__ n_ungapped, int *__restrict__ n_gapped, int *__restrict__ err) {
+    __shared__ uint64_t s_ku[DW_WARPS][DW_ROWS], s_kg[DW_WARPS][DW_ROWS];  // keys of the distinct rows so far
+    __shared__ int s_ru[DW_WARPS][DW_ROWS], s_rg[DW_WARPS][DW_ROWS];        // ... and their rows
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ti = blockIdx.x * DW_WARPS + warp;
+    if (ti >= n_tasks) return;
+    const DTask t = tasks[ti];
+    const int w = t.c1 - t.c0, R = t.n_rows;
+    if (!dedupe_small(R, w)) return;
+    const uint8_t *g = G + g_off[ti];
+    const long long ro = row_off[ti];
+    uint64_t *ku = s_ku[warp], *kg = s_kg[warp];
+    int *ru = s_ru[warp], *rg = s_rg[warp];
+    int nu = 0, ng = 0;
+    for (int r0 = 0; r0 < R; r0 += 32) {
+        const int r = r0 + lane;
+        const bool valid = r < R;
+        const uint8_t *row = g + (long long)r * w;
+        // keys over 16-symbol words of 4-bit codes (one 64-bit mixing step per word, not per symbol).  Every
+        // step is a bijection of the word, so for w <= 16 the keys ARE the rows and need no verification
+        // (non-gap codes are non-zero: the ungapped word also fixes the length).
+        uint64_t hu = 0x9e3779b97f4a7c15ULL, hg = 0x2545f4914f6cdd1dULL, wu = 0, wg = 0;
+        int len = 0;
+        if (valid) {
+            for (int i = 0; i < w; ++i) {
+                const uint64_t c = row[i];
+                wg |= c << (4 * (i & 15));
+                if ((i & 15) == 15) {
+                    hg = word_step(hg, wg);
+                    wg = 0;
+                }
+                if (c != SYM_GAP) {
+                    wu |= c << (4 * (len & 15));
+                    if ((++len & 15) == 0) {
+                        hu = word_step(hu, wu);
+                        wu = 0;
+                    }
+                }
+            }
+            ulen[ro + r] = len;
+        }
+        const bool exact = w <= 16;
+        const uint64_t mu = word_step(hu, wu) ^ (exact ? 0ULL : (uint64_t)len * 0xd6e8feb86659fd93ULL);
+        const uint64_t mg = word_step(hg, wg);
+        // ---- ungapped: group number = position of the row's distinct sequence in first-seen order ----
+        int gi = -1;
+        if (valid)
+            for (int j = 0; j < nu; ++j)
+                if (ku[j] == mu) {
+                    gi = j;
+                    break;
+                }
+        {
+            const bool fresh = valid && gi < 0;
+            const unsigned fresh_mask = __ballot_sync(0xffffffffu, fresh);
+            const unsigned peers = __match_any_sync(0xffffffffu, mu) & fresh_mask;
+            const int first = __ffs(peers) - 1;  // lowest fresh lane with my key
+            const bool lead = fresh && first == lane;
+            const unsigned lead_mask = __ballot_sync(0xffffffffu, lead);
+            if (fresh) gi = nu + __popc(lead_mask & ((1u << (first & 31)) - 1u));
+            if (lead) {
+                ku[gi] = mu;
+                ru[gi] = r;
+                leaders[ro + gi] = r;
+                leader_len[ro + gi] = len;
+            }
+            nu += __popc(lead_mask);
+            __syncwarp();
+        }
+        // ---- gapped: only the number of distinct rows is kept ----
+        int gj = -1;
+        if (valid)
+            for (int j = 0; j < ng; ++j)
+                if (kg[j] == mg) {
+                    gj = j;
+                    break;
+                }
+        {
+            const bool fresh = valid && gj < 0;
+            const unsigned fresh_mask = __ballot_sync(0xffffffffu, fresh);
+            const unsigned peers = __match_any_sync(0xffffffffu, mg) & fresh_mask;
+            const int first = __ffs(peers) - 1;
+            const bool lead = fresh && first == lane;
+            const unsigned lead_mask = __ballot_sync(0xffffffffu, lead);
+            if (fresh) gj = ng + __popc(lead_mask & ((1u << (first & 31)) - 1u));
+            if (lead) {
+                kg[gj] = mg;
+                rg[gj] = r;
+            }
+            ng += __popc(lead_mask);
+            __syncwarp();
+        }
+        if (valid) {
+            group[ro + r] = gi;
+            // verify the merges exactly (key equality is only a filter)
+            const int a = ru[gi], b = rg[gj];
+#ifdef MPRG_DEDUPE_DEBUG
+            if (!exact && a != r && !same_ungapped(g + (long long)a * w, row, w))
+                printf("U ti %d r %d a %d w %d R %d len %d gi %d nu %d key %llx akey %llx\n", ti, r, a, w, R, len, gi, nu,
+                       (unsigned long long)mu, (unsigned long long)ku[gi]);
+#endif
+            if (!exact && a != r && !same_ungapped(g + (long long)a * w, row, w)) atomicExch(err, 2);
+            if (!exact && b != r) {
+                const uint8_t *x = g + (long long)b * w;
+                bool eq = true;
+                for (int i = 0; i < w && eq; ++i) eq = x[i] == row[i];
+#ifdef MPRG_DEDUPE_DEBUG
+                if (!eq)
+                {
+                    printf("G ti %d r %d b %d w %d R %d gj %d ng %d key %llx bkey %llx\n", ti, r, b, w, R, gj, ng,
+                           (unsigned long long)mg, (unsigned long long)kg[gj]);
+                    for (int i = 0; i < w; ++i) printf("%d:%d/%d ", i, (int)x[i], (int)row[i]);
+                    printf("\n");
+                }
+#endif
+                if (!eq) atomicExch(err, 2);
+            }
+        }
+    }
+    if (lane == 0) {
+        n_ungapped[ti] = nu;
+        n_gapped[ti] = ng;
+    }
+}
+
 // one CTA per task.  Outputs per row (at row_off[t]): group = index of the row's distinct ungapped
 // sequence in first-seen order, ulen = ungapped length; per task the distinct counts.
 __global__ void __launch_bounds__(256)
@@ -136,6 +276,7 @@ dedupe_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ g_o
     const int ti = blockIdx.x;
     const DTask t = tasks[ti];
     const int w = t.c1 - t.c0, R = t.n_rows;
+    if (dedupe_small(R, w)) return;  // dedupe_warp_kernel has it
     const uint8_t *g = G + g_off[ti];
     const long long ro = row_off[ti];
     RowSig *s = sig + ro;
@@ -1067,6 +1208,9 @@ cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, con
                           int *leader_g, int *group, int *ulen, int *leaders, int *leader_len,
                           int *n_ungapped, int *n_gapped, int *err) {
     if (n_tasks <= 0) return cudaSuccess;
+    // every task is taken by exactly one of the two (dedupe_small): a warp for the small ones, a CTA otherwise
+    dedupe_warp_kernel<<<(n_tasks + DW_WARPS - 1) / DW_WARPS, DW_WARPS * 32, 0, s>>>(
+        d_tasks, n_tasks, g_off, G, row_off, group, ulen, leaders, leader_len, n_ungapped, n_gapped, err);
     dedupe_kernel<<<n_tasks, 256, 0, s>>>(d_tasks, g_off, G, row_off, (RowSig *)sig, leader_u, leader_g,
                                           group, ulen, leaders, leader_len, n_ungapped, n_gapped, err);
     return cudaGetLastError();

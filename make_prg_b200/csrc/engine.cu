@@ -575,6 +575,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         MPRG_CUDA(ctx, launch_dedupe(s, B[0].as<DTask>(), n_tasks, B[1].as<long long>(), B[3].as<uint8_t>(),
                                      B[2].as<long long>(), B[4].p, d_leader_u, d_leader_g, d_group, d_ulen,
                                      d_leaders, d_leadlen, d_nu, d_ng, d_err));
+        ctx->launches += 1;  // two kernels: a warp per small task, a CTA per other task
     }
     // Results of the de-duplication in ONE trip when the level is small (nu | ng | err and the per-row
     // leader arrays as they are, O(rows)); big levels first fetch the counts, compact the leaders on the
