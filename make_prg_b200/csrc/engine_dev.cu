@@ -789,18 +789,25 @@ __device__ __forceinline__ void marker_put(char *dst, int m) {
 
 constexpr int PRG_STACK = 64;  // nesting depth of the tree: at most 2 * max_nesting + 2 in practice
 
-// text length of every leaf without its markers (sum of its alleles' ungapped lengths): one thread per node,
-// so that the per-locus walks below touch nodes only, never alleles
+// what the per-locus walk needs of a node, in one 32-byte sector (a DNode is 56 bytes and the leaf length a
+// second dependent load): the walk is a chain of dependent loads, one per visit
+struct __align__(32) WalkNode {
+    int kind, n_children, first_child, allele_count;
+    long long leaf_len;  // text length of a leaf without its markers (sum of its alleles' ungapped lengths)
+    long long pad;
+};
+
+// one thread per node, so that the per-locus walks below touch WalkNodes only, never alleles
 __global__ void __launch_bounds__(256)
 leaf_len_kernel(const DNode *__restrict__ nodes, int n_nodes, const int *__restrict__ allele_len,
-                long long *__restrict__ leaf_len) {
+                WalkNode *__restrict__ walk) {
     const int ni = blockIdx.x * blockDim.x + threadIdx.x;
     if (ni >= n_nodes) return;
     const DNode nd = nodes[ni];
     long long sum = 0;
     if (nd.kind == MPRG_NODE_LEAF)
         for (int a = 0; a < nd.allele_count; ++a) sum += allele_len[nd.allele_first + a];
-    leaf_len[ni] = sum;
+    walk[ni] = WalkNode{nd.kind, nd.n_children, nd.first_child, nd.allele_count, sum, 0};
 }
 
 // one thread per locus walks its tree once (pre-order, the order site numbers are handed out in) and records
@@ -808,8 +815,8 @@ leaf_len_kernel(const DNode *__restrict__ nodes, int n_nodes, const int *__restr
 // (node_site; 0 = none); lengths, sites and node counts per locus go to info.  Everything that writes is then
 // per node (prg_emit_kernel).
 __global__ void __launch_bounds__(128)
-prg_walk_kernel(const DNode *__restrict__ nodes, const DLocus *__restrict__ loci, int nl,
-                const long long *__restrict__ leaf_len, PrgInfo *__restrict__ info, long long *__restrict__ node_at,
+prg_walk_kernel(const WalkNode *__restrict__ nodes, const DLocus *__restrict__ loci, int nl,
+                PrgInfo *__restrict__ info, long long *__restrict__ node_at,
                 long long *__restrict__ node_end, int *__restrict__ node_site, int *__restrict__ err) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nl) return;
@@ -826,25 +833,28 @@ prg_walk_kernel(const DNode *__restrict__ nodes, const DLocus *__restrict__ loci
     int site = 5, n_nodes = 0;
     while (depth >= 0) {
         const int ni = st_node[depth];
-        const DNode nd = nodes[ni];
+        const WalkNode nd = nodes[ni];
         if (st_next[depth] == 0) {
             ++n_nodes;
             node_at[ni] = at;
             if (nd.kind == MPRG_NODE_LEAF) {
                 if (nd.allele_count == 1) {
                     node_site[ni] = 0;
-                    at += leaf_len[ni];
+                    at += nd.leaf_len;
                 } else {
                     const int sn = site;
                     site += 2;
                     node_site[ni] = sn;
                     // " sn " a1 " sn+1 " a2 ... " sn+1 " ak " sn "
-                    at += 2LL * marker_len(sn) + (long long)(nd.allele_count - 1) * marker_len(sn + 1) + leaf_len[ni];
+                    at += 2LL * marker_len(sn) + (long long)(nd.allele_count - 1) * marker_len(sn + 1) + nd.leaf_len;
                 }
                 node_end[ni] = at;
                 --depth;
                 continue;
             }
+            // the children are contiguous: ask for all of them now, so that only the first of them is a wait
+            for (int k = 1; k < nd.n_children && k < 64; ++k)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + nd.first_child + k));
             if (nd.kind == MPRG_NODE_CLUSTER) {
                 st_site[depth] = site;
                 site += 2;
@@ -1407,16 +1417,16 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         ExtractItem *d_items = V[V_ITEMS].as<ExtractItem>();
         int *d_errflag = &d_cnt->err;
         const size_t nn1 = (size_t)std::max(n_nodes, 1);
-        MPRG_CUDA(ctx, V[V_LEAF].reserve((sizeof(long long) * 3 + sizeof(int)) * nn1 + 64));
-        long long *d_leaf_len = V[V_LEAF].as<long long>();
-        long long *d_node_at = d_leaf_len + nn1;
+        MPRG_CUDA(ctx, V[V_LEAF].reserve((sizeof(WalkNode) + sizeof(long long) * 2 + sizeof(int)) * nn1 + 64));
+        WalkNode *d_walk = V[V_LEAF].as<WalkNode>();
+        long long *d_node_at = reinterpret_cast<long long *>(d_walk + nn1);
         long long *d_node_end = d_node_at + nn1;
         int *d_node_site = reinterpret_cast<int *>(d_node_end + nn1);
         MPRG_CUDA(ctx, cudaMemsetAsync(d_node_at, 0xFF, sizeof(long long) * nn1, s));  // < 0: not reached by the walk
         if (na > 0) allele_len_kernel<<<(na + 3) / 4, 128, 0, s>>>(batch->d_packed, d_items, na, d_len);
-        leaf_len_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(V[V_NODES].as<DNode>(), n_nodes, d_len, d_leaf_len);
-        prg_walk_kernel<<<(nl + 127) / 128, 128, 0, s>>>(V[V_NODES].as<DNode>(), d_loci, nl, d_leaf_len, d_info, d_node_at,
-                                                        d_node_end, d_node_site, d_errflag);
+        leaf_len_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(V[V_NODES].as<DNode>(), n_nodes, d_len, d_walk);
+        prg_walk_kernel<<<(nl + 127) / 128, 128, 0, s>>>(d_walk, d_loci, nl, d_info, d_node_at, d_node_end, d_node_site,
+                                                        d_errflag);
         prg_offsets_kernel<<<1, 1024, 0, s>>>(d_info, nl, d_total);
         ctx->launches += 4;
         MPRG_CUDA(ctx, cudaGetLastError());
