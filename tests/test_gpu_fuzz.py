@@ -1,0 +1,111 @@
+"""-m gpu: seeded random small alignments through mprg_build against the oracle port, several (max_nesting,
+min_match_length) settings per batch.  The generator aims at the corners the fixed cases leave thin: one-row and
+one-column alignments, all-gap columns and rows that differ only in gap placement, N and RYKMSW symbols, blocks of
+identical rows, clades with private indels, windows shorter than the k-mer size, symbols outside the alphabet
+(locus skipped with status 1, as SequenceCurationError does in from_msa.py:147-151)."""
+import numpy as np
+import pytest
+
+import make_prg_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+SETTINGS = [(5, 7), (3, 3), (1, 5), (2, 1), (4, 9)]
+PER_SETTING = 48
+
+
+def random_msa(rng):
+    """One alignment as FASTA text (so that the oracle's loader rules -- upper-casing, N replacement -- apply)."""
+    style = rng.integers(0, 7)
+    R = int(rng.integers(1, 4)) if style == 0 else int(rng.integers(2, 29))
+    C = int(rng.integers(1, 9)) if style == 1 else int(rng.integers(5, 161))
+    base = rng.choice(list(b"ACGT"), size=C).astype(np.uint8)
+    n_clades = int(rng.integers(1, 6))
+    clades = []
+    for _ in range(n_clades):
+        s = base.copy()
+        rate = rng.choice([0.0, 0.02, 0.08, 0.3])
+        mut = rng.random(C) < rate
+        s[mut] = rng.choice(list(b"ACGT"), size=int(mut.sum()))
+        for _ in range(int(rng.integers(0, 3))):  # clade-level indels
+            a = int(rng.integers(0, C))
+            s[a:a + int(rng.integers(1, 12))] = ord("-")
+        clades.append(s)
+    rows = []
+    for _ in range(R):
+        s = clades[int(rng.integers(0, n_clades))].copy()
+        if rng.random() < 0.5:  # private SNPs
+            mut = rng.random(C) < rng.choice([0.01, 0.05])
+            s[mut] = rng.choice(list(b"ACGT"), size=int(mut.sum()))
+        if rng.random() < 0.2:  # private indel
+            a = int(rng.integers(0, C))
+            s[a:a + int(rng.integers(1, 6))] = ord("-")
+        if rng.random() < 0.1:  # the same letters, another gap placement
+            nz = np.flatnonzero(s != ord("-"))
+            if len(nz) > 1 and len(nz) < C:
+                t = np.full(C, ord("-"), np.uint8)
+                keep = np.sort(rng.choice(C, size=len(nz), replace=False))
+                t[keep] = s[nz]
+                s = t
+        if style == 2 and rng.random() < 0.3:
+            pos = rng.integers(0, C, size=int(rng.integers(1, 4)))
+            s[pos] = ord("N")
+        if style == 3 and rng.random() < 0.15:
+            s[int(rng.integers(0, C))] = rng.choice(list(b"RYKMSW"))
+        rows.append(s)
+    if style == 4 and C > 3:  # an all-gap column block
+        a = int(rng.integers(0, C - 1))
+        for s in rows:
+            s[a:a + int(rng.integers(1, 4))] = ord("-")
+    if style == 6 and rng.random() < 0.5:  # a symbol outside the alphabet: the locus is skipped, the batch goes on
+        rows[int(rng.integers(0, R))][int(rng.integers(0, C))] = rng.choice(list(b"XBZ*"))
+    if style == 5:  # lower case input
+        rows = [np.frombuffer(bytes(s).lower(), np.uint8).copy() if rng.random() < 0.5 else s for s in rows]
+    return "".join(f">s{i} d\n{bytes(s).decode()}\n" for i, s in enumerate(rows))
+
+
+def oracle_outcome(text, N, L):
+    try:
+        ids, M = mo.load_msa(text, is_text=True)
+    except Exception as e:  # noqa: BLE001 -- the loader's verdict is part of the comparison
+        return None, ("load", type(e).__name__)
+    try:
+        prg, b = mo.build_prg_from_matrix(ids, M, N, L)
+        return M, ("ok", prg, b.next_node_id)
+    except mo.SequenceCurationError:
+        return M, ("curation",)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from make_prg_b200 import device
+
+    return device.Context(0)
+
+
+@pytest.mark.parametrize("setting", range(len(SETTINGS)))
+def test_random_alignments_equal_oracle(ctx, setting):
+    N, L = SETTINGS[setting]
+    rng = np.random.default_rng(77_000 + setting)
+    mats, expect = [], []
+    while len(mats) < PER_SETTING:
+        text = random_msa(rng)
+        M, out = oracle_outcome(text, N, L)
+        if M is None:
+            continue
+        mats.append(M)
+        expect.append(out)
+    batch = ctx.upload(mats)
+    res = ctx.build(batch, N, L)
+    n_ok = 0
+    for i, out in enumerate(expect):
+        if out[0] == "ok":
+            assert res.status(i) == 0, (setting, i)
+            assert res.prg(i) == out[1], (setting, i, mats[i].shape)
+            assert res.n_nodes(i) == out[2], (setting, i)
+            n_ok += 1
+        else:
+            assert res.status(i) == 1 and res.prg(i) == "", (setting, i)
+    assert n_ok >= PER_SETTING // 2
+    res.free()
+    batch.free()
