@@ -129,29 +129,36 @@ __device__ bool same_ungapped(const uint8_t *a, const uint8_t *b, int w) {
 // list in shared memory whose position IS the first-seen group number) and, if new, with the other new rows
 // of its 32 (match.any), so the work per row is O(#distinct) and there is no block barrier.  Same outputs as
 // dedupe_kernel (group, ulen, leaders, leader_len, the counts).
-constexpr int DW_ROWS = 256, DW_WARPS = 4;
+constexpr int DW_ROWS = 512, DW_WARPS = 4;  // rows per task at most / tasks per CTA; the lists are sized per launch
 // one word into the running key: the full finaliser per word (a multiply and a fold alone let differences in
 // the top nibbles of consecutive words cancel -- found by the verification below); still a bijection of x
 __device__ __forceinline__ uint64_t word_step(uint64_t h, uint64_t x) { return mix64(h ^ x) + 0x9e3779b97f4a7c15ULL; }
-__device__ __forceinline__ bool dedupe_small(int R, int w) { return R <= DW_ROWS && (long long)R * w <= 16384; }
+__host__ __device__ __forceinline__ int dedupe_list_cap(int max_rows) {  // list entries per warp of a launch
+    int cap = 64;
+    while (cap < max_rows && cap < DW_ROWS) cap <<= 1;
+    return cap;
+}
+__device__ __forceinline__ bool dedupe_small(int R, int w, int cap) { return R <= cap && (long long)R * w <= 32768; }
 
 __global__ void __launch_bounds__(DW_WARPS * 32)
 dedupe_warp_kernel(const DTask *__restrict__ tasks, int n_tasks, const long long *__restrict__ g_off,
                    const uint8_t *__restrict__ G, const long long *__restrict__ row_off, int *__restrict__ group,
                    int *__restrict__ ulen, int *__restrict__ leaders, int *__restrict__ leader_len,
-                   int *__restrict__ n_ungapped, int *__restrict__ n_gapped, int *__restrict__ err) {
-    __shared__ uint64_t s_ku[DW_WARPS][DW_ROWS], s_kg[DW_WARPS][DW_ROWS];  // keys of the distinct rows so far
-    __shared__ int s_ru[DW_WARPS][DW_ROWS], s_rg[DW_WARPS][DW_ROWS];        // ... and their rows
+                   int *__restrict__ n_ungapped, int *__restrict__ n_gapped, int *__restrict__ err, int cap) {
+    // per warp: keys of the distinct rows so far (ungapped | gapped), then their rows; cap entries each
+    extern __shared__ __align__(16) unsigned char dw_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ti = blockIdx.x * DW_WARPS + warp;
     if (ti >= n_tasks) return;
     const DTask t = tasks[ti];
     const int w = t.c1 - t.c0, R = t.n_rows;
-    if (!dedupe_small(R, w)) return;
+    if (!dedupe_small(R, w, cap)) return;
     const uint8_t *g = G + g_off[ti];
     const long long ro = row_off[ti];
-    uint64_t *ku = s_ku[warp], *kg = s_kg[warp];
-    int *ru = s_ru[warp], *rg = s_rg[warp];
+    uint64_t *ku = reinterpret_cast<uint64_t *>(dw_smem) + (size_t)warp * 2 * cap, *kg = ku + cap;
+    int *ru = reinterpret_cast<int *>(reinterpret_cast<uint64_t *>(dw_smem) + (size_t)DW_WARPS * 2 * cap) +
+              (size_t)warp * 2 * cap;
+    int *rg = ru + cap;
     int nu = 0, ng = 0;
     for (int r0 = 0; r0 < R; r0 += 32) {
         const int r = r0 + lane;
@@ -272,11 +279,11 @@ dedupe_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ g_o
               RowSig *__restrict__ sig, int *__restrict__ leader_u, int *__restrict__ leader_g,
               int *__restrict__ group, int *__restrict__ ulen, int *__restrict__ leaders,
               int *__restrict__ leader_len, int *__restrict__ n_ungapped, int *__restrict__ n_gapped,
-              int *__restrict__ err) {
+              int *__restrict__ err, int cap) {
     const int ti = blockIdx.x;
     const DTask t = tasks[ti];
     const int w = t.c1 - t.c0, R = t.n_rows;
-    if (dedupe_small(R, w)) return;  // dedupe_warp_kernel has it
+    if (dedupe_small(R, w, cap)) return;  // dedupe_warp_kernel has it
     const uint8_t *g = G + g_off[ti];
     const long long ro = row_off[ti];
     RowSig *s = sig + ro;
@@ -1203,16 +1210,18 @@ cudaError_t launch_dedupe_big(cudaStream_t s, const DTask *d_tasks, int n_tasks,
     return cudaGetLastError();
 }
 
-cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, const long long *g_off,
+cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, int max_rows, const long long *g_off,
                           const uint8_t *G, const long long *row_off, void *sig, int *leader_u,
                           int *leader_g, int *group, int *ulen, int *leaders, int *leader_len,
                           int *n_ungapped, int *n_gapped, int *err) {
     if (n_tasks <= 0) return cudaSuccess;
     // every task is taken by exactly one of the two (dedupe_small): a warp for the small ones, a CTA otherwise
-    dedupe_warp_kernel<<<(n_tasks + DW_WARPS - 1) / DW_WARPS, DW_WARPS * 32, 0, s>>>(
-        d_tasks, n_tasks, g_off, G, row_off, group, ulen, leaders, leader_len, n_ungapped, n_gapped, err);
+    const int cap = dedupe_list_cap(max_rows);
+    const size_t smem = (size_t)DW_WARPS * cap * 2 * (sizeof(uint64_t) + sizeof(int));  // <= 48 KB at cap 512
+    dedupe_warp_kernel<<<(n_tasks + DW_WARPS - 1) / DW_WARPS, DW_WARPS * 32, smem, s>>>(
+        d_tasks, n_tasks, g_off, G, row_off, group, ulen, leaders, leader_len, n_ungapped, n_gapped, err, cap);
     dedupe_kernel<<<n_tasks, 256, 0, s>>>(d_tasks, g_off, G, row_off, (RowSig *)sig, leader_u, leader_g,
-                                          group, ulen, leaders, leader_len, n_ungapped, n_gapped, err);
+                                          group, ulen, leaders, leader_len, n_ungapped, n_gapped, err, cap);
     return cudaGetLastError();
 }
 

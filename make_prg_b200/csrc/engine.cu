@@ -572,7 +572,7 @@ static int cluster_level(mprg_ctx *ctx, const mprg_batch *batch, const mprg_task
         ctx->launches += 3;
         ctx->path_counts[MPRG_PATH_DEDUPE_GRID]++;
     } else {
-        MPRG_CUDA(ctx, launch_dedupe(s, B[0].as<DTask>(), n_tasks, B[1].as<long long>(), B[3].as<uint8_t>(),
+        MPRG_CUDA(ctx, launch_dedupe(s, B[0].as<DTask>(), n_tasks, max_rows, B[1].as<long long>(), B[3].as<uint8_t>(),
                                      B[2].as<long long>(), B[4].p, d_leader_u, d_leader_g, d_group, d_ulen,
                                      d_leaders, d_leadlen, d_nu, d_ng, d_err));
         ctx->launches += 1;  // two kernels: a warp per small task, a CTA per other task

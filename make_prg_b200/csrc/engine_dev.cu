@@ -1228,7 +1228,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
                 ctx->launches += 3;
                 ctx->path_counts[MPRG_PATH_DEDUPE_GRID]++;
             } else {
-                MPRG_CUDA(ctx, launch_dedupe(s, ct.tasks, nt, ct.g_off, V[V_G].as<uint8_t>(), ct.row_off, V[V_SIG].p,
+                MPRG_CUDA(ctx, launch_dedupe(s, ct.tasks, nt, cnt->max_rows, ct.g_off, V[V_G].as<uint8_t>(), ct.row_off, V[V_SIG].p,
                                              d_leader_u, d_leader_g, d_group, d_ulen, d_leaders, d_leadlen, d_nu, d_ng,
                                              d_err));
                 ctx->launches += 1;  // two kernels: a warp per small task, a CTA per other task

@@ -98,7 +98,7 @@ cudaError_t launch_dedupe_big(cudaStream_t s, const DTask *d_tasks, int n_tasks,
                               const uint8_t *G, uint8_t *U, const long long *row_off, void *sig, int *leader_u,
                               int *leader_g, int *group, int *ulen, int *leaders, int *leader_len, int *n_ungapped,
                               int *n_gapped, int *err);
-cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, const long long *g_off,
+cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, int max_rows, const long long *g_off,
                           const uint8_t *G, const long long *row_off, void *sig, int *leader_u,
                           int *leader_g, int *group, int *ulen, int *leaders, int *leader_len,
                           int *n_ungapped, int *n_gapped, int *err);
