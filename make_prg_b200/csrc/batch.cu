@@ -204,6 +204,7 @@ extern "C" void mprg_destroy(mprg_ctx *ctx) {
     for (DevBuf &b : ctx->d_c) b.release();
     for (DevBuf &b : ctx->d_dev) b.release();
     ctx->h_cnt.release();
+    ctx->h_setup.release();
     ctx->d_ref.release();
     for (auto &a : ctx->idle_arenas) cudaFree(a.first);
     ctx->idle_arenas.clear();
@@ -218,6 +219,8 @@ extern "C" void mprg_destroy(mprg_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->stream_side) cudaStreamDestroy(ctx->stream_side);
+    if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

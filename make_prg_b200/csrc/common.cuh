@@ -148,6 +148,8 @@ struct mprg_ctx {
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_side = nullptr;  // result copies that overlap the PRG assembly (engine_dev.cu)
+    cudaEvent_t ev_side = nullptr;
     std::string err;
     long long launches = 0;
     int n_workers = 1;                // host threads / streams mprg_build may use
@@ -171,6 +173,7 @@ struct mprg_ctx {
     mprg::DevBuf d_dev[32];
     mprg::DevBuf d_ref;  // scratch of the whole-grid one-reference-like check (refcheck_grid.cu)
     mprg::PinnedBuf h_cnt;  // the counter block the host reads twice per level
+    mprg::PinnedBuf h_setup;  // staging of a range's start state (counters, locus table, root nodes, pending list)
     bool pending_scan = false;  // a scan launch whose events have not been read yet
     double pending_scan_bytes = 0;
     // device time of the KMeans launches of the level loop (mprg_kmeans_stats): event pairs of the current

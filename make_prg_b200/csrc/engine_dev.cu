@@ -156,6 +156,47 @@ __device__ __forceinline__ int pow2_ceil_dev(int x) {
     return p;
 }
 
+// ---- zero-filling several buffers with one launch (a level needs five, a clustering pass three; as
+// cudaMemsetAsync calls they were 40 of the ~190 stream operations of a build) ---------------------------
+struct ZeroSegs {
+    void *p[5];
+    unsigned long long bytes[5];  // multiples of 4, pointers 4-byte aligned
+    int n;
+};
+__global__ void __launch_bounds__(256) zero_segments_kernel(ZeroSegs z) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    for (int k = 0; k < z.n; ++k) {
+        if (((uintptr_t)z.p[k] & 15) == 0) {
+            uint4 *q = reinterpret_cast<uint4 *>(z.p[k]);
+            const size_t n16 = z.bytes[k] >> 4;
+            for (size_t i = tid; i < n16; i += nthr) q[i] = make_uint4(0u, 0u, 0u, 0u);
+            uint32_t *t = reinterpret_cast<uint32_t *>(q + n16);
+            const size_t rest = (z.bytes[k] & 15) >> 2;
+            if (tid < rest) t[tid] = 0u;
+        } else {
+            uint32_t *q = reinterpret_cast<uint32_t *>(z.p[k]);
+            const size_t n4 = z.bytes[k] >> 2;
+            for (size_t i = tid; i < n4; i += nthr) q[i] = 0u;
+        }
+    }
+}
+static cudaError_t launch_zero(cudaStream_t s, std::initializer_list<std::pair<void *, size_t>> segs) {
+    ZeroSegs z;
+    z.n = 0;
+    size_t most = 0;
+    for (const auto &sg : segs) {
+        if (sg.second == 0) continue;
+        z.p[z.n] = sg.first;
+        z.bytes[z.n] = sg.second;
+        most = std::max(most, sg.second);
+        ++z.n;
+    }
+    if (z.n == 0) return cudaSuccess;
+    const size_t blocks = std::min<size_t>(std::max<size_t>((most / 16 + 255) / 256, 1), 148 * 8);
+    zero_segments_kernel<<<(unsigned)blocks, 256, 0, s>>>(z);
+    return cudaGetLastError();
+}
+
 // ---- level set-up ---------------------------------------------------------------------------------------
 __global__ void level_begin_kernel(DevCounters *C) {
     C->n_tasks = C->n_next;
@@ -1075,12 +1116,24 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
     h_cnt.n_next = (int)h_pending.size();
     DevCounters *d_cnt = V[V_COUNTERS].as<DevCounters>();
     DLocus *d_loci = V[V_LOCI].as<DLocus>();
-    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_cnt, &h_cnt, sizeof(h_cnt), s));
-    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_loci, h_loci.data(), sizeof(DLocus) * nl, s));
-    MPRG_CUDA(ctx, mprg::copy_h2d(ctx, V[V_NODES].p, h_roots.data(), sizeof(DNode) * nl, s));
-    if (!h_pending.empty())
-        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, V[V_PEND_B].p, h_pending.data(), sizeof(int) * h_pending.size(), s));
-    // the copies above read pageable host vectors: they are staged before the call returns
+    {
+        // start state of the range through ONE pinned staging block: copies from pageable vectors are staged
+        // synchronously by the driver, one at a time (4 of them cost ~0.1 ms of a 3 ms build)
+        const size_t o_loci = (sizeof(DevCounters) + 63) & ~(size_t)63;
+        const size_t o_roots = (o_loci + sizeof(DLocus) * (size_t)nl + 63) & ~(size_t)63;
+        const size_t o_pend = (o_roots + sizeof(DNode) * (size_t)nl + 63) & ~(size_t)63;
+        MPRG_CUDA(ctx, ctx->h_setup.reserve(o_pend + sizeof(int) * (size_t)nl + 64));
+        unsigned char *st = ctx->h_setup.as<unsigned char>();
+        memcpy(st, &h_cnt, sizeof(h_cnt));
+        memcpy(st + o_loci, h_loci.data(), sizeof(DLocus) * (size_t)nl);
+        memcpy(st + o_roots, h_roots.data(), sizeof(DNode) * (size_t)nl);
+        if (!h_pending.empty()) memcpy(st + o_pend, h_pending.data(), sizeof(int) * h_pending.size());
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_cnt, st, sizeof(h_cnt), s));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, d_loci, st + o_loci, sizeof(DLocus) * nl, s));
+        MPRG_CUDA(ctx, mprg::copy_h2d(ctx, V[V_NODES].p, st + o_roots, sizeof(DNode) * nl, s));
+        if (!h_pending.empty())
+            MPRG_CUDA(ctx, mprg::copy_h2d(ctx, V[V_PEND_B].p, st + o_pend, sizeof(int) * h_pending.size(), s));
+    }
     int cur = V_PEND_B, nxt = V_PEND_A;  // level_begin turns "next" into "pending": the lists swap first
     long long pending_bound = (long long)h_pending.size();
     PinnedBuf &hc = ctx->h_cnt;
@@ -1161,8 +1214,6 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         const size_t ct_misc_bytes = (sizeof(long long) * 3 + sizeof(int) * 8) * (size_t)nt + 64;
         MPRG_CUDA(ctx, V[V_CT_TASKS].reserve(sizeof(DTask) * (size_t)nt));
         MPRG_CUDA(ctx, V[V_CT_MISC].reserve(ct_misc_bytes));
-        MPRG_CUDA(ctx, cudaMemsetAsync(V[V_CT_TASKS].p, 0, sizeof(DTask) * (size_t)nt, s));
-        MPRG_CUDA(ctx, cudaMemsetAsync(V[V_CT_MISC].p, 0, ct_misc_bytes, s));
         ClusterTaskArrays ct;
         ct.tasks = V[V_CT_TASKS].as<DTask>();
         ct.g_off = V[V_CT_MISC].as<long long>();
@@ -1175,9 +1226,12 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         int *d_prob_of_ctask = d_ng + nt, *d_clustered = d_prob_of_ctask + nt;
         int *d_err = d_clustered + nt;  // [0] hash collision codes of the clustering kernels
 
-        MPRG_CUDA(ctx, cudaMemsetAsync(ctx->d_colwords.p, 0, sizeof(uint32_t) * 2 * words, s));
-        MPRG_CUDA(ctx, cudaMemsetAsync(ctx->d_colB.p, 0, sizeof(unsigned) * total_cols, s));
-        MPRG_CUDA(ctx, cudaMemsetAsync(ctx->d_ivcnt.p, 0, sizeof(int) * (nt + 1), s));
+        MPRG_CUDA(ctx, launch_zero(s, {{V[V_CT_TASKS].p, sizeof(DTask) * (size_t)nt},
+                                       {V[V_CT_MISC].p, ct_misc_bytes},
+                                       {ctx->d_colwords.p, sizeof(uint32_t) * 2 * (size_t)words},
+                                       {ctx->d_colB.p, sizeof(unsigned) * (size_t)total_cols},
+                                       {ctx->d_ivcnt.p, sizeof(int) * (size_t)(nt + 1)}}));
+        ctx->launches += 1;
         uint32_t *colOR = ctx->d_colwords.as<uint32_t>();
         uint32_t *colNOR = colOR + words;
         const int *d_pool = V[V_POOL].as<int>();
@@ -1285,15 +1339,16 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
                     double *d_kmd = V[V_KM].as<double>();
                     int *d_kmi = reinterpret_cast<int *>(d_kmd + cnt->kmd_total);
                     ClusterState *states = pa.st;
-                    MPRG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, sizeof(int) * (size_t)np, s));
+                    MPRG_CUDA(ctx, launch_zero(s, {{d_tickets, sizeof(int) * (size_t)np},
+                                                   {V[V_X].p, sizeof(double) * (size_t)cnt->x_total},
+                                                   {d_asg, sizeof(int) * (size_t)cnt->assign_total}}));
+                    ctx->launches += 1;
                     MPRG_CUDA(ctx, launch_members(s, pa.mp, np, d_group, d_leadlen, d_leader_u, d_memoff, d_memrows));
                     MPRG_CUDA(ctx, launch_kmer(s, pa.kp, np, pa.seq_rows, V[V_G].as<uint8_t>(), min_match_length,
                                                V[V_USEQ].as<uint8_t>(), V[V_INTS].as<int>(), V[V_KEYS].as<uint64_t>(),
                                                V[V_MING].as<int>(), d_F, d_err));
-                    MPRG_CUDA(ctx, cudaMemsetAsync(V[V_X].p, 0, sizeof(double) * (size_t)cnt->x_total, s));
                     MPRG_CUDA(ctx, launch_kmer_fill(s, pa.kp, np, cnt->max_P, V[V_INTS].as<int>(), d_F, V[V_X].as<double>()));
                     MPRG_CUDA(ctx, launch_set_features(s, states, d_F, np));
-                    MPRG_CUDA(ctx, cudaMemsetAsync(d_asg, 0, sizeof(int) * (size_t)cnt->assign_total, s));
                     MPRG_CUDA(ctx, launch_refcheck(s, states, np, V[V_G].as<uint8_t>(), d_memoff, d_memrows, d_asg, d_maj, 10));
                     MPRG_CUDA(ctx, launch_kmeans_prepare(s, states, np, V[V_X].as<double>(), d_kmd, d_kmi));
                     ctx->launches += 6;
@@ -1423,14 +1478,10 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         long long *d_node_end = d_node_at + nn1;
         int *d_node_site = reinterpret_cast<int *>(d_node_end + nn1);
         MPRG_CUDA(ctx, cudaMemsetAsync(d_node_at, 0xFF, sizeof(long long) * nn1, s));  // < 0: not reached by the walk
-        if (na > 0) allele_len_kernel<<<(na + 3) / 4, 128, 0, s>>>(batch->d_packed, d_items, na, d_len);
-        leaf_len_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(V[V_NODES].as<DNode>(), n_nodes, d_len, d_walk);
-        prg_walk_kernel<<<(nl + 127) / 128, 128, 0, s>>>(d_walk, d_loci, nl, d_info, d_node_at, d_node_end, d_node_site,
-                                                        d_errflag);
-        prg_offsets_kernel<<<1, 1024, 0, s>>>(d_info, nl, d_total);
-        ctx->launches += 4;
-        MPRG_CUDA(ctx, cudaGetLastError());
-        // the raw tree travels while the strings are being laid out
+        // the raw tree (node table + row pool, final once the level loop has ended) travels on a second stream
+        // while the strings are laid out: its 4-5 MB would otherwise sit between the walk and the emission
+        if (!ctx->stream_side) MPRG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream_side, cudaStreamNonBlocking));
+        if (!ctx->ev_side) MPRG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
         RawTree raw;
         raw.l_begin = l_begin;
         raw.l_end = l_end;
@@ -1438,18 +1489,43 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         raw.pool_size = pool_size;
         raw.nodes = pinned_acquire(sizeof(DNode) * (size_t)std::max(n_nodes, 1));
         raw.pool = pinned_acquire(sizeof(int) * (size_t)std::max<long long>(pool_size, 1));
+        if (!raw.nodes.p || !raw.pool.p) MPRG_FAIL(ctx, MPRG_E_CUDA, "pinned allocation for the result failed");
+        auto drop_raw = [&]() {
+            cudaStreamSynchronize(ctx->stream_side);
+            pinned_release(raw.nodes);
+            pinned_release(raw.pool);
+        };
+        {
+            cudaError_t e = cudaEventRecord(ctx->ev_side, s);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream_side, ctx->ev_side, 0);
+            if (e == cudaSuccess)
+                e = mprg::copy_d2h(ctx, raw.nodes.p, V[V_NODES].p, sizeof(DNode) * (size_t)n_nodes, ctx->stream_side);
+            if (e == cudaSuccess && pool_size > 0)
+                e = mprg::copy_d2h(ctx, raw.pool.p, V[V_POOL].p, sizeof(int) * (size_t)pool_size, ctx->stream_side);
+            if (e != cudaSuccess) {
+                drop_raw();
+                MPRG_CUDA(ctx, e);
+            }
+        }
+        if (na > 0) allele_len_kernel<<<(na + 3) / 4, 128, 0, s>>>(batch->d_packed, d_items, na, d_len);
+        leaf_len_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(V[V_NODES].as<DNode>(), n_nodes, d_len, d_walk);
+        prg_walk_kernel<<<(nl + 127) / 128, 128, 0, s>>>(d_walk, d_loci, nl, d_info, d_node_at, d_node_end, d_node_site,
+                                                        d_errflag);
+        prg_offsets_kernel<<<1, 1024, 0, s>>>(d_info, nl, d_total);
+        ctx->launches += 4;
+        MPRG_CUDA(ctx, cudaGetLastError());
         MPRG_CUDA(ctx, ctx->h_d.reserve(sizeof(PrgInfo) * (size_t)nl + 64));
         PrgInfo *h_info = ctx->h_d.as<PrgInfo>();
         long long *h_total = reinterpret_cast<long long *>(h_info + nl);
-        if (!raw.nodes.p || !raw.pool.p) MPRG_FAIL(ctx, MPRG_E_CUDA, "pinned allocation for the result failed");
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_total, d_total, sizeof(long long), s));
-        MPRG_CUDA(ctx, mprg::copy_d2h(ctx, raw.nodes.p, V[V_NODES].p, sizeof(DNode) * (size_t)n_nodes, s));
-        if (pool_size > 0) MPRG_CUDA(ctx, mprg::copy_d2h(ctx, raw.pool.p, V[V_POOL].p, sizeof(int) * (size_t)pool_size, s));
         MPRG_CUDA(ctx, cudaStreamSynchronize(s));
         const long long blob_bytes = *h_total;
         TRACE("dev: measure + raw tree D2H");
         PinnedBlock blob = pinned_acquire((size_t)std::max<long long>(blob_bytes, 1));
-        if (!blob.p) MPRG_FAIL(ctx, MPRG_E_CUDA, "pinned allocation for the result failed");
+        if (!blob.p) {
+            drop_raw();
+            MPRG_FAIL(ctx, MPRG_E_CUDA, "pinned allocation for the result failed");
+        }
         MPRG_CUDA(ctx, V[V_OUT].reserve((size_t)std::max<long long>(blob_bytes, 1)));
         prg_emit_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(V[V_NODES].as<DNode>(), n_nodes, d_loci, l_begin, d_info,
                                                             d_len, d_node_at, d_node_end, d_node_site, d_items,
@@ -1462,11 +1538,11 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_info, d_info, sizeof(PrgInfo) * (size_t)nl, s));
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, cnt, d_cnt, sizeof(DevCounters), s));
         MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        MPRG_CUDA(ctx, cudaStreamSynchronize(ctx->stream_side));
         TRACE("dev: strings D2H");
         if (cnt->err & ERR_OVERFLOW) {
             pinned_release(blob);
-            pinned_release(raw.nodes);
-            pinned_release(raw.pool);
+            drop_raw();
             MPRG_FAIL(ctx, MPRG_E_INTERNAL, "tree deeper than the PRG walk supports");
         }
         int raw_index;
