@@ -2,21 +2,41 @@
 real step (not ncu's cold serialised launches), GPU busy time and the idle gaps between kernels."""
 import os, sys, json, collections
 from pathlib import Path
-os.environ.setdefault("MPRG_WORKERS", "1")
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO))
 import torch
 from torch.profiler import profile, ProfilerActivity
 import bench
 from make_prg_b200 import device
+import numpy as np
+E2E = len(sys.argv) > 1 and sys.argv[1] == "e2e"   # from pinned packed host rows (mprg_build_packed), as bench.py's e2e
+if not E2E:
+    os.environ.setdefault("MPRG_WORKERS", "1")
 ctx = device.Context(0)
 data = bench.workload(0, 1000)
-batch = ctx.upload((data.reshape(-1), [(bench.ROWS, bench.COLS)] * 1000))
+if E2E:
+    from make_prg_b200 import hostio
+    n, R, Cc = 1000, bench.ROWS, bench.COLS
+    stride = hostio.packed_stride(Cc)
+    packed_np = torch.empty(n * R * stride, dtype=torch.uint8).pin_memory().numpy()
+    flags = np.zeros(n, np.int32)
+    for i in range(n):
+        rows, flags[i] = hostio.pack_rows(data[i])
+        packed_np[i * R * stride:(i + 1) * R * stride] = rows.reshape(-1)
+    offs = np.arange(n, dtype=np.int64) * (R * stride)
+    nr, nc = np.full(n, R, np.int32), np.full(n, Cc, np.int32)
+    def run():
+        b, r = ctx.build_packed(packed_np, offs, nr, nc, flags, 5, 7)
+        r.free(); b.free()
+else:
+    batch = ctx.upload((data.reshape(-1), [(bench.ROWS, bench.COLS)] * 1000))
+    def run():
+        ctx.build(batch, 5, 7).free()
 for _ in range(3):
-    ctx.build(batch, 5, 7).free()
+    run()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    res = ctx.build(batch, 5, 7)
+    run()
     torch.cuda.synchronize()
 out = REPO / "gpurun_out" / "timeline_trace.json"
 prof.export_chrome_trace(str(out))
@@ -33,6 +53,14 @@ tot = collections.defaultdict(float); cnt = collections.Counter()
 for e in ev:
     n = e["name"].split("(")[0].replace("void ", "").replace("mprg::", "")
     tot[n] += e["dur"]; cnt[n] += 1
+if E2E:
+    h2d = [e for e in ev if "HtoD" in e["name"] and e["dur"] > 50]
+    print("big H2D copies:", [(round(e["ts"] - t0), round(e["dur"]), e.get("args", {}).get("stream")) for e in h2d])
+    streams = collections.defaultdict(lambda: [1e18, 0])
+    for e in ev:
+        st = e.get("args", {}).get("stream")
+        streams[st][0] = min(streams[st][0], e["ts"] - t0); streams[st][1] = max(streams[st][1], e["ts"] + e["dur"] - t0)
+    print("streams (first, last us):", {k: (round(v[0]), round(v[1])) for k, v in streams.items()})
 print(f"span {t1 - t0:.1f} us, busy {busy:.1f} us, idle {t1 - t0 - busy:.1f} us, events {len(ev)}")
 for k, v in sorted(tot.items(), key=lambda x: -x[1])[:28]:
     print(f"{v:9.1f} us  n={cnt[k]:3d}  {k}")
