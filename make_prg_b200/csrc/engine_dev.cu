@@ -1142,7 +1142,9 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
     *cnt = h_cnt;  // what the result phase reads when no level runs (no buildable locus)
     const int any_n = batch->any_n ? 1 : 0;
     // device time of the level's scan launch, read after the next synchronisation (roofline object of bench.py)
-    auto account = [&]() {
+    // Both are called while the GPU is busy with freshly launched work, not in the idle gap after a
+    // synchronisation (a dozen cudaEventElapsedTime calls are ~20 us of host time).
+    auto account_km = [&]() {
         for (int r = 0; r < ctx->km_pending; ++r) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, ctx->ev_km[0][r], ctx->ev_km[1][r]) == cudaSuccess) ctx->km_ms += ms;
@@ -1151,6 +1153,8 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         ctx->km_problems += ctx->km_pending_problems;
         ctx->km_pending = 0;
         ctx->km_pending_problems = 0;
+    };
+    auto account_scan = [&]() {  // before ev0 / ev1 are recorded again
         if (!ctx->pending_scan) return;
         ctx->pending_scan = false;
         float ms = 0;
@@ -1184,7 +1188,6 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         MPRG_CUDA(ctx, cudaGetLastError());
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, cnt, d_cnt, sizeof(DevCounters), s));
         MPRG_CUDA(ctx, cudaStreamSynchronize(s));  // ---- sync A ----
-        account();
         TRACE("dev: prepare+sync A");
         if (cnt->err) break;
         const int nt = cnt->n_tasks;
@@ -1202,6 +1205,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
                                                           ctx->d_tasks.as<DTask>(), ctx->sm_count, forced_iters,
                                                           V[V_UNIT_OFF].as<int>(), ctx->d_units.as<ScanUnit>());
         ctx->launches++;
+        account_scan();  // (the previous level's launch, when that level had no clustering pass)
         const size_t words = (size_t)total_cols / 8;
         MPRG_CUDA(ctx, ctx->d_colwords.reserve(sizeof(uint32_t) * 2 * words));
         MPRG_CUDA(ctx, ctx->d_colB.reserve(sizeof(unsigned) * total_cols));
@@ -1257,6 +1261,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
             ctx->pending_scan_bytes = (double)cnt->algo_bytes;
             ctx->pending_scan = n_units > 0;
         }
+        account_km();  // the previous level's KMeans launches
         TRACE("dev: partition pass launch");
 
         // ---- clustering pass: a locus root never clusters, so level 0 of from_msa skips it ----
@@ -1306,7 +1311,6 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
             MPRG_CUDA(ctx, cudaGetLastError());
             MPRG_CUDA(ctx, mprg::copy_d2h(ctx, cnt, d_cnt, sizeof(DevCounters), s));
             MPRG_CUDA(ctx, cudaStreamSynchronize(s));  // ---- sync C ----
-            account();
             TRACE("dev: dedupe+problems+sync C");
             if (cnt->err) break;
             const int np = cnt->np, n_ct = cnt->n_ctasks;
@@ -1449,6 +1453,8 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         std::swap(cur, nxt);
     }
 
+    account_scan();  // the last level's launches (the loop ends right after a synchronisation)
+    account_km();
     // ---- results: node table, row pool, allele strings ----
     if (cnt->err) {
         if (allow_trace || trace_all) g_trace = nullptr;
