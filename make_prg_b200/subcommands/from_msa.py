@@ -126,8 +126,23 @@ def side_threads(n_chunks, writer=False):
 
 
 def _load_chunk(paths, alignment_format, threads=None):
-    if alignment_format != "fasta":
-        raise ValueError(f"only the fasta alignment format is supported, got {alignment_format}")
+    if alignment_format.lower() != "fasta":
+        # other formats (utils/alignment_formats.py) are rewritten as FASTA text for the native loader, so that
+        # upper-casing, N replacement and packing are the same code as for FASTA input
+        import tempfile
+
+        from ..utils.alignment_formats import read_records, to_fasta_text
+
+        tmp = tempfile.TemporaryDirectory(prefix="mprg_fmt_")
+        converted = []
+        for i, path in enumerate(paths):
+            out = os.path.join(tmp.name, f"{i}.fa")
+            with open(out, "w") as fh:
+                fh.write(to_fasta_text(read_records(path, alignment_format)))
+            converted.append(out)
+        msas = hostio.load_fasta_files(converted, threads=threads, packed=not os.environ.get("MPRG_TEXT_UPLOAD"))
+        msas.converted_from = tmp  # the FASTA copies live as long as the set (its error paths re-read a file)
+        return msas
     # the loader emits the matrices in the 4-bit device layout: half the bytes cross PCIe, no pack kernel
     # (MPRG_TEXT_UPLOAD=1 keeps the text path: upload of ASCII rows + pack_rows_kernel)
     return hostio.load_fasta_files(paths, threads=threads, packed=not os.environ.get("MPRG_TEXT_UPLOAD"))

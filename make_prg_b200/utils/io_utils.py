@@ -52,9 +52,12 @@ def get_majority_consensus_from_MSA(alignment):
 
 
 def load_alignment_file(msa_file, alignment_format="fasta"):
-    if alignment_format != "fasta":
-        raise ValueError(f"only the fasta alignment format is supported, got {alignment_format}")
-    if isinstance(msa_file, StringIO):
+    if alignment_format.lower() != "fasta":
+        # clustal / stockholm / phylip*: utils/alignment_formats.py (no Biopython here)
+        from .alignment_formats import read_records
+
+        alignment = MSA([SeqRecord(seq, rid, rid, rid) for rid, seq in read_records(msa_file, alignment_format)])
+    elif isinstance(msa_file, StringIO):
         alignment = parse_fasta(msa_file)
     else:
         path = str(msa_file)

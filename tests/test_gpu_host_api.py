@@ -211,6 +211,43 @@ def test_cli_single_msa_and_skip_semantics(tmp_path):
     _run_cli(tmp_path, REF / "match.nonmatch.fa", "one", force=True)
 
 
+def test_cli_other_alignment_formats_equal_fasta_input(tmp_path):
+    """-f clustal / stockholm / phylip-relaxed (from_msa.py:48-55 passes the name to Bio.AlignIO): the same
+    alignments in another layout give the same .prg.fa / .bin / .gfa as the FASTA files."""
+    from make_prg_b200.utils.io_utils import parse_fasta
+
+    names = ["GC00006032", "GC00010897"]
+    recs = {}
+    for n in names:
+        with open(REF / "sample_example" / f"{n}.fa") as fh:
+            recs[n] = [(r.id, r.seq) for r in parse_fasta(fh)]
+
+    def clustal(rows):
+        out = ["CLUSTAL W (1.83) multiple sequence alignment", "", ""]
+        width, pad = len(rows[0][1]), max(len(rid) for rid, _ in rows) + 6
+        for a in range(0, width, 60):
+            out += [f"{rid:<{pad}}{seq[a:a + 60]}" for rid, seq in rows] + [" " * pad, ""]
+        return "\n".join(out) + "\n"
+
+    def stockholm(rows):
+        return "# STOCKHOLM 1.0\n" + "".join(f"{rid} {seq}\n" for rid, seq in rows) + "//\n"
+
+    def phylip_relaxed(rows):
+        return f"{len(rows)} {len(rows[0][1])}\n" + "".join(f"{rid} {seq}\n" for rid, seq in rows)
+
+    _run_cli(tmp_path, REF / "sample_example", "fasta")
+    want = (tmp_path / "fasta.prg.fa").read_bytes()
+    for fmt, writer, ext in (("clustal", clustal, "aln"), ("stockholm", stockholm, "sto"),
+                             ("phylip-relaxed", phylip_relaxed, "phy")):
+        d = tmp_path / f"in_{ext}"
+        d.mkdir()
+        for n in names:
+            (d / f"{n}.{ext}").write_text(writer(recs[n]))
+        _run_cli(tmp_path, d, fmt, alignment_format=fmt, suffix=ext)
+        got = (tmp_path / f"{fmt}.prg.fa").read_bytes().replace(f".{ext}".encode(), b"")
+        assert got == want.replace(b".fa", b""), fmt
+
+
 def test_cli_chunked_pipeline_equals_one_batch(tmp_path, monkeypatch):
     """The load -> build -> write pipeline cuts a run into chunks of MPRG_CHUNK_MB of input: the final files
     do not depend on the cut (amira_MSAs + sample_example + the small cases, one file per chunk vs one chunk)."""
