@@ -129,36 +129,31 @@ __device__ bool same_ungapped(const uint8_t *a, const uint8_t *b, int w) {
 // list in shared memory whose position IS the first-seen group number) and, if new, with the other new rows
 // of its 32 (match.any), so the work per row is O(#distinct) and there is no block barrier.  Same outputs as
 // dedupe_kernel (group, ulen, leaders, leader_len, the counts).
-constexpr int DW_ROWS = 512, DW_WARPS = 4;  // rows per task at most / tasks per CTA; the lists are sized per launch
+constexpr int DW_ROWS = 512, DW_WARPS = 4;  // rows per task at most / tasks per CTA
+constexpr int DW_LIST = 64;                 // distinct rows a warp keeps; a task with more goes to dedupe_kernel
+constexpr int DW_OVERFLOW = -1;             // n_ungapped[task] of such a task after dedupe_warp_kernel
 // one word into the running key: the full finaliser per word (a multiply and a fold alone let differences in
 // the top nibbles of consecutive words cancel -- found by the verification below); still a bijection of x
 __device__ __forceinline__ uint64_t word_step(uint64_t h, uint64_t x) { return mix64(h ^ x) + 0x9e3779b97f4a7c15ULL; }
-__host__ __device__ __forceinline__ int dedupe_list_cap(int max_rows) {  // list entries per warp of a launch
-    int cap = 64;
-    while (cap < max_rows && cap < DW_ROWS) cap <<= 1;
-    return cap;
-}
-__device__ __forceinline__ bool dedupe_small(int R, int w, int cap) { return R <= cap && (long long)R * w <= 32768; }
+__device__ __forceinline__ bool dedupe_small(int R, int w) { return R <= DW_ROWS && (long long)R * w <= 32768; }
 
 __global__ void __launch_bounds__(DW_WARPS * 32)
 dedupe_warp_kernel(const DTask *__restrict__ tasks, int n_tasks, const long long *__restrict__ g_off,
                    const uint8_t *__restrict__ G, const long long *__restrict__ row_off, int *__restrict__ group,
                    int *__restrict__ ulen, int *__restrict__ leaders, int *__restrict__ leader_len,
-                   int *__restrict__ n_ungapped, int *__restrict__ n_gapped, int *__restrict__ err, int cap) {
-    // per warp: keys of the distinct rows so far (ungapped | gapped), then their rows; cap entries each
-    extern __shared__ __align__(16) unsigned char dw_smem[];
+                   int *__restrict__ n_ungapped, int *__restrict__ n_gapped, int *__restrict__ err) {
+    __shared__ uint64_t s_ku[DW_WARPS][DW_LIST], s_kg[DW_WARPS][DW_LIST];  // keys of the distinct rows so far
+    __shared__ int s_ru[DW_WARPS][DW_LIST], s_rg[DW_WARPS][DW_LIST];        // ... and their rows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ti = blockIdx.x * DW_WARPS + warp;
     if (ti >= n_tasks) return;
     const DTask t = tasks[ti];
     const int w = t.c1 - t.c0, R = t.n_rows;
-    if (!dedupe_small(R, w, cap)) return;
+    if (!dedupe_small(R, w)) return;
     const uint8_t *g = G + g_off[ti];
     const long long ro = row_off[ti];
-    uint64_t *ku = reinterpret_cast<uint64_t *>(dw_smem) + (size_t)warp * 2 * cap, *kg = ku + cap;
-    int *ru = reinterpret_cast<int *>(reinterpret_cast<uint64_t *>(dw_smem) + (size_t)DW_WARPS * 2 * cap) +
-              (size_t)warp * 2 * cap;
-    int *rg = ru + cap;
+    uint64_t *ku = s_ku[warp], *kg = s_kg[warp];
+    int *ru = s_ru[warp], *rg = s_rg[warp];
     int nu = 0, ng = 0;
     for (int r0 = 0; r0 < R; r0 += 32) {
         const int r = r0 + lane;
@@ -205,6 +200,10 @@ dedupe_warp_kernel(const DTask *__restrict__ tasks, int n_tasks, const long long
             const int first = __ffs(peers) - 1;  // lowest fresh lane with my key
             const bool lead = fresh && first == lane;
             const unsigned lead_mask = __ballot_sync(0xffffffffu, lead);
+            if (nu + __popc(lead_mask) > DW_LIST) {  // more distinct rows than the list holds: dedupe_kernel redoes it
+                if (lane == 0) n_ungapped[ti] = DW_OVERFLOW;
+                return;
+            }
             if (fresh) gi = nu + __popc(lead_mask & ((1u << (first & 31)) - 1u));
             if (lead) {
                 ku[gi] = mu;
@@ -230,6 +229,10 @@ dedupe_warp_kernel(const DTask *__restrict__ tasks, int n_tasks, const long long
             const int first = __ffs(peers) - 1;
             const bool lead = fresh && first == lane;
             const unsigned lead_mask = __ballot_sync(0xffffffffu, lead);
+            if (ng + __popc(lead_mask) > DW_LIST) {
+                if (lane == 0) n_ungapped[ti] = DW_OVERFLOW;
+                return;
+            }
             if (fresh) gj = ng + __popc(lead_mask & ((1u << (first & 31)) - 1u));
             if (lead) {
                 kg[gj] = mg;
@@ -279,11 +282,11 @@ dedupe_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ g_o
               RowSig *__restrict__ sig, int *__restrict__ leader_u, int *__restrict__ leader_g,
               int *__restrict__ group, int *__restrict__ ulen, int *__restrict__ leaders,
               int *__restrict__ leader_len, int *__restrict__ n_ungapped, int *__restrict__ n_gapped,
-              int *__restrict__ err, int cap) {
+              int *__restrict__ err) {
     const int ti = blockIdx.x;
     const DTask t = tasks[ti];
     const int w = t.c1 - t.c0, R = t.n_rows;
-    if (dedupe_small(R, w, cap)) return;  // dedupe_warp_kernel has it
+    if (dedupe_small(R, w) && n_ungapped[ti] != DW_OVERFLOW) return;  // dedupe_warp_kernel did it
     const uint8_t *g = G + g_off[ti];
     const long long ro = row_off[ti];
     RowSig *s = sig + ro;
@@ -1215,13 +1218,12 @@ cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, int
                           int *leader_g, int *group, int *ulen, int *leaders, int *leader_len,
                           int *n_ungapped, int *n_gapped, int *err) {
     if (n_tasks <= 0) return cudaSuccess;
-    // every task is taken by exactly one of the two (dedupe_small): a warp for the small ones, a CTA otherwise
-    const int cap = dedupe_list_cap(max_rows);
-    const size_t smem = (size_t)DW_WARPS * cap * 2 * (sizeof(uint64_t) + sizeof(int));  // <= 48 KB at cap 512
-    dedupe_warp_kernel<<<(n_tasks + DW_WARPS - 1) / DW_WARPS, DW_WARPS * 32, smem, s>>>(
-        d_tasks, n_tasks, g_off, G, row_off, group, ulen, leaders, leader_len, n_ungapped, n_gapped, err, cap);
+    // a warp for every small task; a CTA for the others and for the small ones with more than DW_LIST distinct rows
+    (void)max_rows;
+    dedupe_warp_kernel<<<(n_tasks + DW_WARPS - 1) / DW_WARPS, DW_WARPS * 32, 0, s>>>(
+        d_tasks, n_tasks, g_off, G, row_off, group, ulen, leaders, leader_len, n_ungapped, n_gapped, err);
     dedupe_kernel<<<n_tasks, 256, 0, s>>>(d_tasks, g_off, G, row_off, (RowSig *)sig, leader_u, leader_g,
-                                          group, ulen, leaders, leader_len, n_ungapped, n_gapped, err, cap);
+                                          group, ulen, leaders, leader_len, n_ungapped, n_gapped, err);
     return cudaGetLastError();
 }
 

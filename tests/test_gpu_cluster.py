@@ -46,6 +46,29 @@ def test_dedupe_rows(ctx):
         assert group.tolist() == g and ulen.tolist() == ul and (nu, ng) == (n_u, n_g)
 
 
+def test_dedupe_rows_around_the_warp_list_capacity(ctx):
+    """Small tasks de-duplicate on one warp that keeps at most 64 distinct rows (dedupe_warp_kernel); a task with
+    more is redone by the one-CTA kernel.  63 / 64 / 65 / 130 distinct rows, with and without gap-only differences,
+    first occurrences spread over the 32-row passes."""
+    rng = np.random.default_rng(11)
+    mats, tasks = [], []
+    for distinct in (1, 31, 63, 64, 65, 130):
+        pats = set()
+        while len(pats) < distinct:
+            pats.add(bytes(rng.choice(list(b"ACGT-"), size=24).astype(np.uint8)))
+        pats = [np.frombuffer(p, np.uint8) for p in sorted(pats)]
+        rows = [pats[int(i)] for i in rng.permutation(np.concatenate([np.arange(distinct),
+                                                                    rng.integers(0, distinct, 200 - min(distinct, 200))]))]
+        mats.append(np.stack(rows))
+        tasks.append((len(mats) - 1, None, 0, 24))
+        tasks.append((len(mats) - 1, np.sort(rng.choice(len(rows), len(rows) // 2, replace=False)), 3, 21))
+    batch = ctx.upload(mats)
+    for (l, rows, c0, c1), (group, ulen, nu, ng) in zip(tasks, ctx.dedupe_rows(batch, tasks)):
+        S = mats[l][:, c0:c1] if rows is None else mats[l][rows, c0:c1]
+        g, ul, n_u, n_g = _oracle_dedupe(S)
+        assert group.tolist() == g and ulen.tolist() == ul and (nu, ng) == (n_u, n_g), (l, c0, c1)
+
+
 def test_dedupe_rows_whole_grid_path(ctx, monkeypatch):
     """Deep tasks de-duplicate with the whole grid (dedupe_big_* kernels): same outputs as the one-CTA
     kernel, on the forced path for small windows and on a task that takes it by size."""
