@@ -150,6 +150,62 @@ __device__ __forceinline__ int block_alloc(int *counter, int amount, long long *
     return base;
 }
 
+// N allocations of a block at once: the scans as above, then ONE round of atomics -- lane k of warp 0 bumps
+// counter k, all N are in flight together -- instead of N global round trips one after the other on every
+// CTA's critical path.  amt[k]: this thread's request in, its offset out.  s_buf: N * 33 words.
+struct AllocCounter {
+    void *p;
+    bool wide;  // long long counter (else int)
+};
+template <int N>
+__device__ __forceinline__ void block_alloc_n(const AllocCounter (&ctr)[N], long long (&amt)[N], long long *s_buf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    long long incl[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        long long v = amt[k];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += o;
+        }
+        incl[k] = v;
+        if (lane == 31) s_buf[k * 33 + warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        long long total[N], base[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            long long v = lane < nw ? s_buf[k * 33 + lane] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long o = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += o;
+            }
+            s_buf[k * 33 + lane] = v;  // inclusive over the warps
+            total[k] = __shfl_sync(0xffffffffu, v, 31);
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) {  // issued back to back: nothing below waits for one of them before the next
+            base[k] = 0;
+            if (lane == k && total[k]) {
+                if (ctr[k].wide)
+                    base[k] = (long long)atomicAdd((unsigned long long *)ctr[k].p, (unsigned long long)total[k]);
+                else
+                    base[k] = (long long)atomicAdd((int *)ctr[k].p, (int)total[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            if (lane == k) s_buf[k * 33 + 32] = base[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) amt[k] = s_buf[k * 33 + 32] + (warp ? s_buf[k * 33 + warp - 1] : 0) + incl[k] - amt[k];
+    __syncthreads();
+}
+
 __device__ __forceinline__ int pow2_ceil_dev(int x) {
     int p = 1;
     while (p < x) p <<= 1;
@@ -216,6 +272,7 @@ __global__ void __launch_bounds__(256)
 prepare_tasks_kernel(DevCounters *C, const int *__restrict__ pending, const DNode *__restrict__ nodes,
                      const DLocus *__restrict__ loci, int l0, int any_n, DTask *__restrict__ tasks) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)(blockIdx.x * blockDim.x) >= C->n_tasks) return;  // the grid is sized by a bound of the task count
     const bool active = i < C->n_tasks;
     long long aligned = 0, ivn = 0, iters = 0, rw = 0, rows = 0, algo = 0;
     DTask t;
@@ -243,13 +300,15 @@ prepare_tasks_kernel(DevCounters *C, const int *__restrict__ pending, const DNod
         rw = (long long)nd.n_rows * (nd.c1 - nd.c0);
         algo = rw / 2 + (nd.row_off >= 0 ? 4LL * nd.n_rows : 0) + 5LL * (nd.c1 - nd.c0);
     }
-    __shared__ long long s_buf[34];
+    __shared__ long long s_buf[2 * 33];
     __shared__ unsigned long long s_sum[4];
     __shared__ long long s_max[2];
     if (threadIdx.x < 4) s_sum[threadIdx.x] = 0;
     if (threadIdx.x < 2) s_max[threadIdx.x] = 0;
-    const long long col_off = block_alloc(&C->total_cols, aligned, s_buf);  // (its barriers order the zeroing above)
-    const long long iv_off = block_alloc(&C->total_iv, ivn, s_buf);
+    const AllocCounter ctr[2] = {{&C->total_cols, true}, {&C->total_iv, true}};
+    long long off[2] = {aligned, ivn};
+    block_alloc_n<2>(ctr, off, s_buf);  // (its barriers order the zeroing above)
+    const long long col_off = off[0], iv_off = off[1];
     const long long s_it = warp_sum(iters), s_rw = warp_sum(rw), s_rows = warp_sum(rows), s_algo = warp_sum(algo);
     const long long m_rw = warp_max(rw), m_rows = warp_max(rows);
     if ((threadIdx.x & 31) == 0 && s_rows) {
@@ -300,6 +359,7 @@ __global__ void __launch_bounds__(256)
 count_units_kernel(DevCounters *C, const DTask *__restrict__ tasks, int sm_count, int forced_iters,
                    int *__restrict__ unit_off) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)(blockIdx.x * blockDim.x) >= C->n_tasks) return;  // the grid is sized by a bound of the task count
     const bool active = i < C->n_tasks;
     const int tile_iters = tile_iters_of(C->level_iters, sm_count, forced_iters);
     int count = 0;
@@ -411,15 +471,16 @@ expand_partition_kernel(DevCounters *C, const int *__restrict__ pending, DNode *
             rw = (long long)nd.n_rows * (nd.c1 - nd.c0);
         }
     }
-    __shared__ long long s_buf[34];
-    const int child0 = block_alloc(&C->n_nodes, n_child, s_buf);
-    const int item0 = block_alloc(&C->n_alleles, n_match, s_buf);
-    const long long byte0 = block_alloc(&C->allele_bytes, match_bytes, s_buf);
-    const int next0 = block_alloc(&C->n_next, n_non, s_buf);
-    const int q = block_alloc(&C->n_ctasks, is_ct, s_buf);
-    const long long g0 = block_alloc(&C->g_total, rw, s_buf);
-    const long long r0 = block_alloc(&C->row_total, R, s_buf);
-    const long long s0 = block_alloc(&C->scratch_total, is_ct ? 2 * R + 32 : 0LL, s_buf);
+    __shared__ long long s_buf[8 * 33];
+    const AllocCounter ctr[8] = {{&C->n_nodes, false},     {&C->n_alleles, false}, {&C->allele_bytes, true},
+                                 {&C->n_next, false},      {&C->n_ctasks, false},  {&C->g_total, true},
+                                 {&C->row_total, true},    {&C->scratch_total, true}};
+    long long off[8] = {n_child, n_match, match_bytes, n_non, is_ct, rw, R, is_ct ? 2LL * R + 32 : 0LL};
+    block_alloc_n<8>(ctr, off, s_buf);
+    const int child0 = (int)off[0], item0 = (int)off[1];
+    const long long byte0 = off[2];
+    const int next0 = (int)off[3], q = (int)off[4];
+    const long long g0 = off[5], r0 = off[6], s0 = off[7];
     if (!active) return;
     if (child0 + n_child > node_capacity || item0 + n_match > item_capacity) {
         atomicOr(&C->err, ERR_OVERFLOW);
@@ -527,19 +588,28 @@ make_problems_kernel(DevCounters *C, ClusterTaskArrays ct, const int *__restrict
     int T = 64;
     while (T < 2 * PP && T < (1 << 30)) T <<= 1;
     const bool big_ref = is_prob && (long long)R * w >= REFCHECK_BIG_SYMBOLS;
-    __shared__ long long s_buf[34];
-    const int pq = block_alloc(&C->np, is_prob, s_buf);
-    const long long seq_off = block_alloc(&C->seqrows_total, nn, s_buf);
-    const long long useq_off = block_alloc(&C->useq_total, nn * w, s_buf);
-    const long long pos_off = block_alloc(&C->ints_total, is_prob ? 2 * nn + 1 + 2 * PP : 0LL, s_buf);
-    const long long tab_off = block_alloc(&C->tab_total, is_prob ? (long long)T : 0LL, s_buf);
-    const long long x_off = block_alloc(&C->x_total, nn * PP, s_buf);
-    const long long mem_off = block_alloc(&C->memoff_total, is_prob ? nn + 1 : 0LL, s_buf);
-    const long long mem_rows_off = block_alloc(&C->memrows_total, is_prob ? (long long)R : 0LL, s_buf);
-    const long long assign_off = block_alloc(&C->assign_total, nn, s_buf);
-    const long long maj_off = block_alloc(&C->maj_total, is_prob ? (big_ref ? 10LL * w : (long long)w) : 0LL, s_buf);
-    const long long kmd_off = block_alloc(&C->kmd_total, is_prob ? km_dscratch_doubles(nn, PP) : 0LL, s_buf);
-    const long long kmi_off = block_alloc(&C->kmi_total, is_prob ? km_iscratch_ints(nn) : 0LL, s_buf);
+    __shared__ long long s_buf[12 * 33];
+    const AllocCounter ctr[12] = {{&C->np, false},           {&C->seqrows_total, true}, {&C->useq_total, true},
+                                  {&C->ints_total, true},    {&C->tab_total, true},     {&C->x_total, true},
+                                  {&C->memoff_total, true},  {&C->memrows_total, true}, {&C->assign_total, true},
+                                  {&C->maj_total, true},     {&C->kmd_total, true},     {&C->kmi_total, true}};
+    long long off[12] = {is_prob,
+                         nn,
+                         nn * w,
+                         is_prob ? 2 * nn + 1 + 2 * PP : 0LL,
+                         is_prob ? (long long)T : 0LL,
+                         nn * PP,
+                         is_prob ? nn + 1 : 0LL,
+                         is_prob ? (long long)R : 0LL,
+                         nn,
+                         is_prob ? (big_ref ? 10LL * w : (long long)w) : 0LL,
+                         is_prob ? km_dscratch_doubles(nn, PP) : 0LL,
+                         is_prob ? km_iscratch_ints(nn) : 0LL};
+    block_alloc_n<12>(ctr, off, s_buf);
+    const int pq = (int)off[0];
+    const long long seq_off = off[1], useq_off = off[2], pos_off = off[3], tab_off = off[4], x_off = off[5];
+    const long long mem_off = off[6], mem_rows_off = off[7], assign_off = off[8], maj_off = off[9];
+    const long long kmd_off = off[10], kmi_off = off[11];
     const long long m_n = warp_max(nn), m_el = warp_max(nn * PP), m_P = warp_max(PP);
     const bool big = is_prob && (PP >= KMER_BIG_POSITIONS || nn * PP >= KMEANS_BIG_ELEMENTS || big_ref ||
                                  PP > 0x3fffffffLL);
