@@ -422,16 +422,22 @@ __device__ __forceinline__ int first_row_of(const DNode &nd, const int *pool) {
 
 // NodeFactory.build's decision per task (recursion_tree.py:436-471): single match interval -> leaf;
 // several intervals (or a locus root) -> MultiIntervalNode with one child per interval, pure match
-// children become leaves at once; a single non-match interval -> clustering task
+// children become leaves at once; a single non-match interval -> clustering task.
+// LPT lanes per task: 1 for the wide levels (one thread per task, a few children each), 32 for the levels with
+// few tasks and many children (a locus root has ~60 intervals: one thread per root was 57 us of serial stores on
+// 8 SMs); the children of a task are then counted and written by a warp, 32 at a time.
+template <int LPT>
 __global__ void __launch_bounds__(128)
 expand_partition_kernel(DevCounters *C, const int *__restrict__ pending, DNode *__restrict__ nodes,
                         DLocus *__restrict__ loci, int l0, const DTask *__restrict__ tasks,
                         const DInterval *__restrict__ iv, const int *__restrict__ iv_cnt, const int *__restrict__ pool,
                         int max_nesting, int *__restrict__ next, ExtractItem *__restrict__ items,
                         ClusterTaskArrays ct, int node_capacity, int item_capacity) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt / LPT, sub = gt % LPT;
+    const unsigned lt = LPT == 32 ? ((1u << sub) - 1u) : 0u;
     const bool active = i < C->n_tasks;
-    if (i == 0 && iv_cnt[C->n_tasks]) atomicOr(&C->err, ERR_PARTITION);  // bijection check of partition_kernel
+    if (gt == 0 && iv_cnt[C->n_tasks]) atomicOr(&C->err, ERR_PARTITION);  // bijection check of partition_kernel
     int ni = -1, c = 0, n_child = 0, n_match = 0, n_non = 0, is_ct = 0;
     long long match_bytes = 0, rw = 0, R = 0;
     DNode nd;
@@ -455,7 +461,7 @@ expand_partition_kernel(DevCounters *C, const int *__restrict__ pending, DNode *
             } else {
                 mode = 2;
                 n_child = c;
-                for (int k = 0; k < c; ++k) {
+                for (int k = sub; k < c; k += LPT) {
                     if (ivs[k].type == MPRG_IV_MATCH) {
                         ++n_match;
                         match_bytes += ivs[k].stop + 1 - ivs[k].start;
@@ -471,44 +477,89 @@ expand_partition_kernel(DevCounters *C, const int *__restrict__ pending, DNode *
             rw = (long long)nd.n_rows * (nd.c1 - nd.c0);
         }
     }
+    if (LPT == 32) {  // the task's totals on its first lane, which is the one that asks for the space
+        n_match = (int)warp_sum(mode == 2 ? n_match : (sub == 0 ? n_match : 0));
+        n_non = (int)warp_sum(n_non);
+        match_bytes = warp_sum(mode == 2 ? match_bytes : (sub == 0 ? match_bytes : 0));
+    }
+    const bool asks = sub == 0;
     __shared__ long long s_buf[8 * 33];
     const AllocCounter ctr[8] = {{&C->n_nodes, false},     {&C->n_alleles, false}, {&C->allele_bytes, true},
                                  {&C->n_next, false},      {&C->n_ctasks, false},  {&C->g_total, true},
                                  {&C->row_total, true},    {&C->scratch_total, true}};
     long long off[8] = {n_child, n_match, match_bytes, n_non, is_ct, rw, R, is_ct ? 2LL * R + 32 : 0LL};
+    if (!asks) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) off[k] = 0;
+    }
     block_alloc_n<8>(ctr, off, s_buf);
+    if (LPT == 32) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) off[k] = __shfl_sync(0xffffffffu, off[k], 0);
+    }
     const int child0 = (int)off[0], item0 = (int)off[1];
     const long long byte0 = off[2];
     const int next0 = (int)off[3], q = (int)off[4];
     const long long g0 = off[5], r0 = off[6], s0 = off[7];
     if (!active) return;
     if (child0 + n_child > node_capacity || item0 + n_match > item_capacity) {
-        atomicOr(&C->err, ERR_OVERFLOW);
+        if (asks) atomicOr(&C->err, ERR_OVERFLOW);
         return;
     }
     const DLocus lc = loci[nd.locus - l0];
     if (mode == 1) {
+        if (!asks) return;
         nd.kind = MPRG_NODE_LEAF;
         nd.allele_first = item0;
         nd.allele_count = 1;
         items[item0] = ExtractItem{lc.base, lc.stride, first_row_of(nd, pool), nd.c0, nd.c1, byte0};
         nodes[ni] = nd;
     } else if (mode == 2) {
-        nd.kind = MPRG_NODE_INTERVAL;
-        nd.first_child = child0;
-        nd.n_children = c;
-        nodes[ni] = nd;
-        int a = item0, nx = next0;
-        long long by = byte0;
+        if (asks) {
+            nd.kind = MPRG_NODE_INTERVAL;
+            nd.first_child = child0;
+            nd.n_children = c;
+            nodes[ni] = nd;
+        }
+        int a0 = item0, nx0 = next0;  // of the current group of LPT children
+        long long by0 = byte0;
         const int frow = first_row_of(nd, pool);
-        for (int k = 0; k < c; ++k) {
+        for (int k0 = 0; k0 < c; k0 += LPT) {
+            const int k = k0 + sub;
+            const bool valid = k < c;
+            const DInterval me = valid ? ivs[k] : DInterval{0, 0, 0};
+            const bool is_match = valid && me.type == MPRG_IV_MATCH;
+            const long long width = is_match ? me.stop + 1 - me.start : 0;
+            int a = a0, nx = nx0;
+            long long by = by0;
+            if (LPT == 32) {
+                const unsigned m_mask = __ballot_sync(0xffffffffu, is_match);
+                const unsigned n_mask = __ballot_sync(0xffffffffu, valid && !is_match);
+                long long incl = width;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const long long o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (sub >= d) incl += o;
+                }
+                a += __popc(m_mask & lt);
+                nx += __popc(n_mask & lt);
+                by += incl - width;
+                a0 += __popc(m_mask);
+                nx0 += __popc(n_mask);
+                by0 += __shfl_sync(0xffffffffu, incl, 31);
+            } else {
+                a0 += is_match ? 1 : 0;
+                nx0 += (valid && !is_match) ? 1 : 0;
+                by0 += width;
+            }
+            if (!valid) continue;
             DNode ch;
             ch.locus = nd.locus;
             ch.parent = ni;
             ch.level = nd.level;
             ch.kind = -1;
-            ch.c0 = nd.c0 + ivs[k].start;
-            ch.c1 = nd.c0 + ivs[k].stop + 1;
+            ch.c0 = nd.c0 + me.start;
+            ch.c1 = nd.c0 + me.stop + 1;
             ch.row_off = nd.row_off;
             ch.n_rows = nd.n_rows;
             ch.first_child = -1;
@@ -516,19 +567,19 @@ expand_partition_kernel(DevCounters *C, const int *__restrict__ pending, DNode *
             ch.allele_first = -1;
             ch.allele_count = 0;
             ch.pad = 0;
-            if (ivs[k].type == MPRG_IV_MATCH) {
+            if (is_match) {
                 // a pure match interval re-partitions to itself: leaf without another scan
                 ch.kind = MPRG_NODE_LEAF;
                 ch.allele_first = a;
                 ch.allele_count = 1;
-                items[a++] = ExtractItem{lc.base, lc.stride, frow, ch.c0, ch.c1, by};
-                by += ch.c1 - ch.c0;
+                items[a] = ExtractItem{lc.base, lc.stride, frow, ch.c0, ch.c1, by};
             } else {
-                next[nx++] = child0 + k;
+                next[nx] = child0 + k;
             }
             nodes[child0 + k] = ch;
         }
     } else if (mode == 3) {
+        if (!asks) return;
         ct.tasks[q] = t;
         ct.g_off[q] = g0;
         ct.row_off[q] = r0;
@@ -536,7 +587,7 @@ expand_partition_kernel(DevCounters *C, const int *__restrict__ pending, DNode *
         ct.node[q] = ni;
         ct.want[q] = (nd.level + 1 < max_nesting) ? 1 : 0;
         ct.sc_off[q] = s0;
-    } else {
+    } else if (asks) {
         loci[nd.locus - l0].status = 2;  // zero-column root: the reference trips an assertion here
     }
 }
@@ -1320,10 +1371,16 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
                                         min_match_length, ctx->d_iv.as<DInterval>(), ivcnt, ivcnt + nt));
         MPRG_CUDA(ctx, launch_demote(s, batch->d_packed, ctx->d_tasks.as<DTask>(), nt, d_pool, ctx->d_iv.as<DInterval>(),
                                      ivcnt));
-        expand_partition_kernel<<<(nt + 127) / 128, 128, 0, s>>>(
-            d_cnt, V[cur].as<int>(), V[V_NODES].as<DNode>(), d_loci, l_begin, ctx->d_tasks.as<DTask>(),
-            ctx->d_iv.as<DInterval>(), ivcnt, d_pool, max_nesting, V[nxt].as<int>(), V[V_ITEMS].as<ExtractItem>(), ct,
-            (int)std::min<long long>(node_cap, 0x7fffffff), (int)std::min<long long>(item_cap, 0x7fffffff));
+        if (nt <= 16384)  // few tasks (a root level: many children each): a warp per task
+            expand_partition_kernel<32><<<(nt + 3) / 4, 128, 0, s>>>(
+                d_cnt, V[cur].as<int>(), V[V_NODES].as<DNode>(), d_loci, l_begin, ctx->d_tasks.as<DTask>(),
+                ctx->d_iv.as<DInterval>(), ivcnt, d_pool, max_nesting, V[nxt].as<int>(), V[V_ITEMS].as<ExtractItem>(), ct,
+                (int)std::min<long long>(node_cap, 0x7fffffff), (int)std::min<long long>(item_cap, 0x7fffffff));
+        else
+            expand_partition_kernel<1><<<(nt + 127) / 128, 128, 0, s>>>(
+                d_cnt, V[cur].as<int>(), V[V_NODES].as<DNode>(), d_loci, l_begin, ctx->d_tasks.as<DTask>(),
+                ctx->d_iv.as<DInterval>(), ivcnt, d_pool, max_nesting, V[nxt].as<int>(), V[V_ITEMS].as<ExtractItem>(), ct,
+                (int)std::min<long long>(node_cap, 0x7fffffff), (int)std::min<long long>(item_cap, 0x7fffffff));
         ctx->launches += (n_units ? 1 : 0) + 4;
         MPRG_CUDA(ctx, cudaGetLastError());
         {
