@@ -276,17 +276,13 @@ dedupe_warp_kernel(const DTask *__restrict__ tasks, int n_tasks, const long long
 
 // one CTA per task.  Outputs per row (at row_off[t]): group = index of the row's distinct ungapped
 // sequence in first-seen order, ulen = ungapped length; per task the distinct counts.
-__global__ void __launch_bounds__(256)
-dedupe_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ g_off,
-              const uint8_t *__restrict__ G, const long long *__restrict__ row_off,
-              RowSig *__restrict__ sig, int *__restrict__ leader_u, int *__restrict__ leader_g,
-              int *__restrict__ group, int *__restrict__ ulen, int *__restrict__ leaders,
-              int *__restrict__ leader_len, int *__restrict__ n_ungapped, int *__restrict__ n_gapped,
-              int *__restrict__ err) {
-    const int ti = blockIdx.x;
-    const DTask t = tasks[ti];
+__device__ void dedupe_task(int ti, const DTask &t, const long long *__restrict__ g_off,
+                            const uint8_t *__restrict__ G, const long long *__restrict__ row_off,
+                            RowSig *__restrict__ sig, int *__restrict__ leader_u, int *__restrict__ leader_g,
+                            int *__restrict__ group, int *__restrict__ ulen, int *__restrict__ leaders,
+                            int *__restrict__ leader_len, int *__restrict__ n_ungapped, int *__restrict__ n_gapped,
+                            int *__restrict__ err) {
     const int w = t.c1 - t.c0, R = t.n_rows;
-    if (dedupe_small(R, w) && n_ungapped[ti] != DW_OVERFLOW) return;  // dedupe_warp_kernel did it
     const uint8_t *g = G + g_off[ti];
     const long long ro = row_off[ti];
     RowSig *s = sig + ro;
@@ -356,6 +352,24 @@ dedupe_kernel(const DTask *__restrict__ tasks, const long long *__restrict__ g_o
     if (threadIdx.x == 0) {
         n_ungapped[ti] = nu;
         n_gapped[ti] = s_ng;
+    }
+}
+
+// The CTAs walk the task list (most entries are small tasks that dedupe_warp_kernel has done, or empty slots of
+// the cluster-task table: a CTA per entry was tens of thousands of CTAs that left at once).
+__global__ void __launch_bounds__(256)
+dedupe_kernel(const DTask *__restrict__ tasks, int n_tasks, const long long *__restrict__ g_off,
+              const uint8_t *__restrict__ G, const long long *__restrict__ row_off,
+              RowSig *__restrict__ sig, int *__restrict__ leader_u, int *__restrict__ leader_g,
+              int *__restrict__ group, int *__restrict__ ulen, int *__restrict__ leaders,
+              int *__restrict__ leader_len, int *__restrict__ n_ungapped, int *__restrict__ n_gapped,
+              int *__restrict__ err) {
+    for (int ti = blockIdx.x; ti < n_tasks; ti += gridDim.x) {
+        const DTask t = tasks[ti];
+        if (dedupe_small(t.n_rows, t.c1 - t.c0) && n_ungapped[ti] != DW_OVERFLOW) continue;  // dedupe_warp_kernel did it
+        dedupe_task(ti, t, g_off, G, row_off, sig, leader_u, leader_g, group, ulen, leaders, leader_len, n_ungapped,
+                    n_gapped, err);
+        __syncthreads();
     }
 }
 
@@ -1191,6 +1205,7 @@ cudaError_t launch_members(cudaStream_t s, const MemberProb *probs, int n, const
 cudaError_t launch_unpack(cudaStream_t s, const uint8_t *packed, const DTask *d_tasks, int n_tasks,
                           const int *d_rows, const long long *g_off, uint8_t *G, int row_split) {
     if (n_tasks <= 0) return cudaSuccess;
+    // (a warp per task on the wide levels was measured: 122 us against 92 us per step for one CTA per task)
     unpack_kernel<<<dim3(n_tasks, std::max(1, std::min(row_split, 4096))), 256, 0, s>>>(packed, d_tasks, d_rows,
                                                                                      g_off, G);
     return cudaGetLastError();
@@ -1222,8 +1237,9 @@ cudaError_t launch_dedupe(cudaStream_t s, const DTask *d_tasks, int n_tasks, int
     (void)max_rows;
     dedupe_warp_kernel<<<(n_tasks + DW_WARPS - 1) / DW_WARPS, DW_WARPS * 32, 0, s>>>(
         d_tasks, n_tasks, g_off, G, row_off, group, ulen, leaders, leader_len, n_ungapped, n_gapped, err);
-    dedupe_kernel<<<n_tasks, 256, 0, s>>>(d_tasks, g_off, G, row_off, (RowSig *)sig, leader_u, leader_g,
-                                          group, ulen, leaders, leader_len, n_ungapped, n_gapped, err);
+    dedupe_kernel<<<std::min(n_tasks, 148 * 8), 256, 0, s>>>(d_tasks, n_tasks, g_off, G, row_off, (RowSig *)sig, leader_u,
+                                                             leader_g, group, ulen, leaders, leader_len, n_ungapped,
+                                                             n_gapped, err);
     return cudaGetLastError();
 }
 

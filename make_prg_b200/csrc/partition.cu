@@ -249,16 +249,20 @@ __global__ void partition_consensus_kernel(const uint8_t *__restrict__ cons, con
 // One CTA per task; warp w takes non-match intervals w, w+4, ...; lanes take rows and compare them
 // with the first row of the task in ungapped order.  All equal and no RYKMSW (N-free by contract)
 // => fewer than two expanded sequences => the interval becomes a match interval.
+// wpt warps per task (4: the CTA's warps share the intervals of one task -- a root level, few tasks with ~60
+// intervals each; 1: a warp per task -- the wide levels, tens of thousands of tasks with one or two intervals)
 __global__ void __launch_bounds__(128)
-demote_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks,
+demote_kernel(const uint8_t *__restrict__ packed, const DTask *__restrict__ tasks, int n_tasks, int wpt,
               const int *__restrict__ rows_arena, DInterval *__restrict__ intervals,
               const int *__restrict__ iv_count) {
-    const int ti = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int cta_warp = threadIdx.x >> 5;
+    const int ti = wpt == 1 ? blockIdx.x * (blockDim.x >> 5) + cta_warp : blockIdx.x;
+    if (ti >= n_tasks) return;
     const DTask t = tasks[ti];
     if (t.n_rows <= 0) return;  // "for testing convenience" (interval_partition.py:200-201)
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int nw = blockDim.x >> 5;
+    const int warp = wpt == 1 ? 0 : cta_warp;
+    const int nw = wpt == 1 ? 1 : (blockDim.x >> 5);
     const int n_iv = iv_count[ti];
     const int *rows = t.rows_off >= 0 ? rows_arena + t.rows_off : nullptr;
     const uint8_t *msa = packed + t.base;
@@ -334,7 +338,9 @@ cudaError_t launch_partition_consensus(cudaStream_t stream, const uint8_t *cons,
 cudaError_t launch_demote(cudaStream_t stream, const uint8_t *packed, const DTask *d_tasks, int n_tasks,
                           const int *d_rows, DInterval *intervals, const int *iv_count) {
     if (n_tasks <= 0) return cudaSuccess;
-    demote_kernel<<<n_tasks, 128, 0, stream>>>(packed, d_tasks, d_rows, intervals, iv_count);
+    const int wpt = n_tasks >= 4096 ? 1 : 4;
+    const int grid = wpt == 1 ? (n_tasks + 3) / 4 : n_tasks;
+    demote_kernel<<<grid, 128, 0, stream>>>(packed, d_tasks, n_tasks, wpt, d_rows, intervals, iv_count);
     return cudaGetLastError();
 }
 
