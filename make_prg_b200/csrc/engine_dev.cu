@@ -271,9 +271,14 @@ __global__ void level_begin_kernel(DevCounters *C) {
 __global__ void __launch_bounds__(256)
 prepare_tasks_kernel(DevCounters *C, const int *__restrict__ pending, const DNode *__restrict__ nodes,
                      const DLocus *__restrict__ loci, int l0, int any_n, DTask *__restrict__ tasks) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((int)(blockIdx.x * blockDim.x) >= C->n_tasks) return;  // the grid is sized by a bound of the task count
-    const bool active = i < C->n_tasks;
+    // the host knows only a bound of the task count: a machine-sized grid walks the tasks
+    __shared__ long long s_buf[2 * 33];
+    __shared__ unsigned long long s_sum[4];
+    __shared__ long long s_max[2];
+    const int n_tasks = C->n_tasks;
+    for (int base = blockIdx.x * blockDim.x; base < n_tasks; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
+    const bool active = i < n_tasks;
     long long aligned = 0, ivn = 0, iters = 0, rw = 0, rows = 0, algo = 0;
     DTask t;
     if (active) {
@@ -300,9 +305,6 @@ prepare_tasks_kernel(DevCounters *C, const int *__restrict__ pending, const DNod
         rw = (long long)nd.n_rows * (nd.c1 - nd.c0);
         algo = rw / 2 + (nd.row_off >= 0 ? 4LL * nd.n_rows : 0) + 5LL * (nd.c1 - nd.c0);
     }
-    __shared__ long long s_buf[2 * 33];
-    __shared__ unsigned long long s_sum[4];
-    __shared__ long long s_max[2];
     if (threadIdx.x < 4) s_sum[threadIdx.x] = 0;
     if (threadIdx.x < 2) s_max[threadIdx.x] = 0;
     const AllocCounter ctr[2] = {{&C->total_cols, true}, {&C->total_iv, true}};
@@ -334,6 +336,8 @@ prepare_tasks_kernel(DevCounters *C, const int *__restrict__ pending, const DNod
         if (col_off + aligned > 0x7fffffffLL || iv_off + ivn > 0x7fffffffLL) atomicOr(&C->err, ERR_OVERFLOW);
         tasks[i] = t;
     }
+    __syncthreads();  // s_sum / s_max are reused by the next trip
+    }
 }
 
 __device__ __forceinline__ int tile_iters_of(long long level_iters, int sm_count, int forced) {
@@ -358,24 +362,26 @@ __device__ __forceinline__ int tiles_of_strip(int n_rows, int tile_rows) {
 __global__ void __launch_bounds__(256)
 count_units_kernel(DevCounters *C, const DTask *__restrict__ tasks, int sm_count, int forced_iters,
                    int *__restrict__ unit_off) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((int)(blockIdx.x * blockDim.x) >= C->n_tasks) return;  // the grid is sized by a bound of the task count
-    const bool active = i < C->n_tasks;
+    __shared__ long long s_buf[34];
+    const int n_tasks = C->n_tasks;
     const int tile_iters = tile_iters_of(C->level_iters, sm_count, forced_iters);
-    int count = 0;
-    if (active) {
-        const DTask t = tasks[i];
-        if (t.n_rows > 0) {
-            const int ch0 = t.c0 >> 5, ch1 = max((t.c1 + 31) >> 5, ch0 + 1);
-            for (int cb = ch0; cb < ch1; cb += 32) {
-                const int bn = min(32, ch1 - cb);
-                count += tiles_of_strip(t.n_rows, tile_iters * (32 / pow2_ceil_dev(bn)));
+    for (int base = blockIdx.x * blockDim.x; base < n_tasks; base += gridDim.x * blockDim.x) {  // (as prepare_tasks)
+        const int i = base + threadIdx.x;
+        const bool active = i < n_tasks;
+        int count = 0;
+        if (active) {
+            const DTask t = tasks[i];
+            if (t.n_rows > 0) {
+                const int ch0 = t.c0 >> 5, ch1 = max((t.c1 + 31) >> 5, ch0 + 1);
+                for (int cb = ch0; cb < ch1; cb += 32) {
+                    const int bn = min(32, ch1 - cb);
+                    count += tiles_of_strip(t.n_rows, tile_iters * (32 / pow2_ceil_dev(bn)));
+                }
             }
         }
+        const int off = block_alloc(&C->n_units, count, s_buf);
+        if (active) unit_off[i] = off;
     }
-    __shared__ long long s_buf[34];
-    const int off = block_alloc(&C->n_units, count, s_buf);
-    if (active) unit_off[i] = off;
 }
 
 // pass 2: the tiles
@@ -1297,7 +1303,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         snprintf(nvtx_name, sizeof(nvtx_name), "mprg: recursion level %d", level);
         NvtxRange nvtx_level(nvtx_name);
         // ---- tasks and scan tiles of the level ----
-        const int pb = (int)((pending_bound + 255) / 256);
+        const int pb = (int)std::min<long long>((pending_bound + 255) / 256, (long long)std::max(ctx->sm_count, 1) * 8);
         MPRG_CUDA(ctx, ctx->d_tasks.reserve(sizeof(DTask) * (size_t)pending_bound));
         level_begin_kernel<<<1, 1, 0, s>>>(d_cnt);
         prepare_tasks_kernel<<<pb, 256, 0, s>>>(d_cnt, V[cur].as<int>(), V[V_NODES].as<DNode>(), d_loci, l_begin, any_n,
