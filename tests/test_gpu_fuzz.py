@@ -3,6 +3,8 @@ min_match_length) settings per batch.  The generator aims at the corners the fix
 one-column alignments, all-gap columns and rows that differ only in gap placement, N and RYKMSW symbols, blocks of
 identical rows, clades with private indels, windows shorter than the k-mer size, symbols outside the alphabet
 (locus skipped with status 1, as SequenceCurationError does in from_msa.py:147-151)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -86,7 +88,8 @@ def ctx():
 @pytest.mark.parametrize("setting", range(len(SETTINGS)))
 def test_random_alignments_equal_oracle(ctx, setting):
     N, L = SETTINGS[setting]
-    rng = np.random.default_rng(77_000 + setting)
+    # MPRG_FUZZ_SEED=<int> draws another set of alignments (for soak runs; the default set is the pinned one)
+    rng = np.random.default_rng(77_000 + setting + 1000 * int(os.environ.get("MPRG_FUZZ_SEED", "0")))
     mats, expect = [], []
     while len(mats) < PER_SETTING:
         text = random_msa(rng)
