@@ -6,9 +6,14 @@
 Workload (BASELINE.json configs[1]): synthetic 1,000-locus set, 200 seqs x 1 kb MSAs, -N 5 -L 7, per
 GPU.  A step = one pass of the whole hot path (level-synchronous scan / partition / clustering /
 KMeans / PRG emission, `mprg_build`) over that batch.
-  value     loci/sec with the packed batch already resident in HBM when the timed region starts
+  value     loci/sec with the packed batches already resident in HBM when the timed region starts: K steps
+            issued back to back through device.BuildPipeline (several builds in flight on their own streams,
+            one C-ABI call per step), host clock between barrier + synchronize; `one_at_a_time` = one build at
+            a time on one stream (device time per step, L2 flushed between steps)
   e2e       loci/sec through the public API from pinned HOST buffers in the loader's 4-bit layout: H2D copy
-            + build + PRG strings back on the host, every step (from_text: the same from ASCII rows)
+            + build + PRG strings back on the host, every step, the same pipeline (the upload of step k+1
+            overlaps the level loop of step k); `e2e.one_at_a_time` = the latency of one such step;
+            from_text: the same from ASCII rows
   roofline  the dominant kernel (column scan, root level launch): algorithmic bytes / CUDA-event time
   files     the same metric file to file (FASTA files in page cache -> .prg.fa/.bin.zip/.gfa.zip on tmpfs)
             through the native loader and writers (scripts/files_e2e.py), host wall clock
@@ -362,6 +367,9 @@ def main():
     from make_prg_b200 import device
 
     ctx = device.Context(local_rank)
+    # builds in flight side by side in the two throughput measurements (the product's own pipeline object)
+    pipe = device.BuildPipeline(local_rank)
+    LANES = pipe.depth
     n_loci = args.loci
     data = workload(rank, n_loci)
     shapes = [(ROWS, COLS)] * n_loci
@@ -471,6 +479,47 @@ def main():
     step_resident(batch, keep=gpu_prgs)
     if not np.array_equal(timed_lengths, seen_lengths["resident"]):
         raise SystemExit("bench: PRG lengths differ between two builds of the same batch")
+    # ---- `value`: throughput with the batches resident: LANES copies of the batch in HBM (LANES x 100 MB of
+    # inputs, larger than L2), lane i builds copy i, K builds issued back to back, LANES of them in flight: the
+    # two host synchronisations per recursion level of one build are filled by the kernels of the others ----
+    lane_batches = [batch] + [ctx.upload((host_np, shapes)) for _ in range(LANES - 1)]
+
+    def consume_resident(b, res):
+        status, lengths = res.statuses()
+        total_len = int(lengths.sum()) + sum(len(res.prg(i)) for i in range(0, n_loci, 97))
+        return int((status == 0).sum()), lengths.copy(), total_len
+
+    def run_lanes(steps, submit):
+        import collections
+
+        futs, done = collections.deque(), []
+        for _ in range(steps):
+            futs.append(submit())
+            flush.zero_()  # one 256 MiB write per step on torch's stream, beside the builds
+            while len(futs) > LANES:
+                done.append(futs.popleft().result())
+        while futs:
+            done.append(futs.popleft().result())
+        return done
+
+    def submit_resident():
+        return pipe.submit_resident(lane_batches[pipe.next_lane], MAX_NESTING, MIN_MATCH, consume=consume_resident)
+
+    run_lanes(max(args.warmup, 2 * LANES), submit_resident)
+    barrier()
+    lane_launches0 = pipe.launch_count()
+    with ClockSampler(local_rank) as lane_clocks:
+        t0 = time.perf_counter()
+        lane_results = run_lanes(args.steps, submit_resident)
+        torch.cuda.synchronize()
+        t_lanes = 1e3 * (time.perf_counter() - t0)
+    barrier()
+    lane_launches = pipe.launch_count() - lane_launches0
+    for ok_k, lengths_k, _ in lane_results:
+        if ok_k != n_ok or not np.array_equal(lengths_k, timed_lengths):
+            raise SystemExit("bench: a build in the lanes differs from the one-at-a-time build")
+    for b in lane_batches[1:]:
+        b.free()
     batch.free()
     # the same kernel on a launch 8x the size (the batch repeated), to separate launch-size effects from
     # kernel quality: 8,000 root tasks, 840 MB per launch
@@ -500,20 +549,48 @@ def main():
                "bare_read_gbs": float(sum(b for b, _ in y8) / (sum(m for _, m in y8) * 1e-3) / 1e9)}
 
     # ---- end to end: host buffers in, PRG strings out ----
+    # (1) one call at a time: the latency of one step (upload, level loop, strings back), device time per step
     for _ in range(2):
         step_e2e()
     barrier()
     ctx.copy_stats(reset=True)
-    t_e2e = 0.0
+    t_serial = 0.0
     e2e_steps = []
     for _ in range(args.steps):
         ctx.timer_start()
         step_e2e()
         e2e_steps.append(ctx.timer_stop())
-        t_e2e += e2e_steps[-1]
+        t_serial += e2e_steps[-1]
         flush.zero_()
     barrier()
-    copies = ctx.copy_stats(reset=True)
+    serial_copies = ctx.copy_stats(reset=True)
+    # (2) the headline: the same K steps, every one the same C-ABI call on the same pinned host rows with its own
+    # H2D copy and its own PRG strings back, but LANES of them in flight (device.BuildPipeline, what the
+    # from_msa pipeline runs): the upload of step k+1 crosses PCIe while step k is in its level loop.  Timed on
+    # the host clock between barrier + synchronize on both sides; a step's result is read on the host (statuses,
+    # lengths, sampled PRG strings) before its buffers are released.
+    def consume(b, res):
+        status, lengths = res.statuses()
+        total_len = int(lengths.sum()) + sum(len(res.prg(i)) for i in range(0, n_loci, 97))
+        return int((status == 0).sum()), lengths.copy(), total_len
+
+    def submit_e2e():
+        return pipe.submit_packed(packed_np, pk_offsets, pk_rows, pk_cols, pk_flags, MAX_NESTING, MIN_MATCH,
+                                  consume=consume)
+
+    run_lanes(max(args.warmup, 2 * LANES), submit_e2e)
+    barrier()
+    pipe.copy_stats(reset=True)
+    t0 = time.perf_counter()
+    pipelined = run_lanes(args.steps, submit_e2e)
+    torch.cuda.synchronize()
+    t_e2e = 1e3 * (time.perf_counter() - t0)
+    barrier()
+    copies = pipe.copy_stats(reset=True)
+    for ok_k, lengths_k, _ in pipelined:
+        if ok_k != n_ok or not np.array_equal(lengths_k, seen_lengths["e2e"]):
+            raise SystemExit("bench: a pipelined end-to-end step differs from the one-at-a-time build")
+    pipe.close()
     # the same from pinned host TEXT (ASCII rows copied and packed on the device), for callers without the loader
     for _ in range(2):
         step_e2e(text=True)
@@ -527,11 +604,11 @@ def main():
     barrier()
     text_copies = ctx.copy_stats(reset=True)
 
-    t_dev_s, t_e2e_s = t_dev / 1e3, t_e2e / 1e3
+    t_dev_s, t_e2e_s, t_serial_s = t_lanes / 1e3, t_e2e / 1e3, t_dev / 1e3
     if dist is not None:
-        tt = torch.tensor([t_dev_s, t_e2e_s], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([t_dev_s, t_e2e_s, t_serial_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev_s, t_e2e_s = float(tt[0]), float(tt[1])
+        t_dev_s, t_e2e_s, t_serial_s = float(tt[0]), float(tt[1]), float(tt[2])
         ok = torch.tensor([n_ok], dtype=torch.int64, device="cuda")
         dist.all_reduce(ok)
         n_ok_total = int(ok[0])
@@ -599,8 +676,18 @@ def main():
         "metric": "MSA loci/sec (from_msa, byte-identical PRG)", "value": value, "unit": "loci/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_dict(),
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": dict(config_dict(), builds_in_flight=LANES),
         "columns_per_sec": value * COLS, "loci_ok": n_ok_total,
+        "mode": f"throughput: {args.steps} builds (steps) of resident batches issued back to back, {LANES} in flight "
+                f"(device.BuildPipeline: {LANES} lanes = contexts with their own stream and host thread, lane i builds "
+                f"its own copy of the batch, {LANES} x 100 MB of inputs > L2), host clock between barrier + "
+                f"synchronize, max over ranks",
+        "one_at_a_time": {"note": "one build at a time on one stream (latency of a step), device time per step, L2 "
+                                  "flushed between steps, max over ranks; roofline.in_step, kmeans and "
+                                  "step_ms.resident come from these steps",
+                          "ms_per_step": 1e3 * t_serial_s / args.steps,
+                          "value": total_loci * args.steps / t_serial_s,
+                          "gpu_launches": int(launches)},
         "parity": {"prgs_equal_oracle": sample, "of": sample,
                    "note": "PRG strings of the first loci of the timed batch == oracle port; PRG lengths of "
                            "every locus equal across resident / e2e / checked builds"},
@@ -609,11 +696,22 @@ def main():
                 "d2h_bytes_per_step": copies["d2h_bytes"] // args.steps,
                 "ms_per_step": 1e3 * t_e2e_s / args.steps,
                 "input": "pinned host rows in the 4-bit layout the native loader emits (mprg_build_packed)",
+                "mode": f"{LANES} steps in flight (device.BuildPipeline: one mprg_build_packed call per step, "
+                        f"each with its own H2D copy and its own results on the host; the upload of step k+1 "
+                        f"overlaps the level loop of step k); {args.steps} steps on the host clock between "
+                        f"barrier + synchronize, max over ranks; L2: {LANES} input arenas of 102 MB take turns in a "
+                        f"126 MB L2, plus one 256 MiB flush write per step on a third stream",
+                "one_at_a_time": {"note": "the same call, one step at a time (latency of a step), device time, "
+                                          "L2 flushed between steps, rank 0",
+                                  "ms_per_step": t_serial / args.steps,
+                                  "value": n_loci / (t_serial / args.steps * 1e-3),
+                                  "h2d_bytes_per_step": serial_copies["h2d_bytes"] // args.steps,
+                                  "d2h_bytes_per_step": serial_copies["d2h_bytes"] // args.steps},
                 "from_text": {"note": "same call from pinned host ASCII rows (mprg_build_ascii: copy + device pack), rank 0",
                               "ms_per_step": float(np.mean(text_steps)),
                               "value": n_loci / (float(np.mean(text_steps)) * 1e-3),
                               "h2d_bytes_per_step": text_copies["h2d_bytes"] // len(text_steps)}},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(lane_launches),
         "roofline": roof,
         # the time-dominant kernel of a step is not bandwidth-bound: float64 KMeans of thousands of tiny problems
         # (sequential-order sums), reported as problems/s with its pipe counters
@@ -631,12 +729,13 @@ def main():
                          "sample": f"first {sample} loci of the workload, oracle/make_prg_oracle.py, "
                                    f"{cpu_dt:.1f} s"},
         "files": files,
-        "clocks": clocks.summary(),
+        "clocks": lane_clocks.summary(),
+        "clocks_one_at_a_time": clocks.summary(),
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "step_ms": {"resident": {"min": float(np.min(dev_steps)), "median": float(np.median(dev_steps)),
                                  "max": float(np.max(dev_steps))},
-                    "e2e": {"min": float(np.min(e2e_steps)), "median": float(np.median(e2e_steps)),
-                            "max": float(np.max(e2e_steps))}, "note": "rank 0, device time per step"},
+                    "e2e_one_at_a_time": {"min": float(np.min(e2e_steps)), "median": float(np.median(e2e_steps)),
+                                          "max": float(np.max(e2e_steps))}, "note": "rank 0, device time per step"},
         "host": {"cores": os.cpu_count(), "loadavg": list(os.getloadavg())},
     }
     print(json.dumps(line), flush=True)

@@ -301,6 +301,14 @@ int batch_prepare(mprg_ctx *ctx, const int32_t *n_rows, const int32_t *n_cols, i
     return MPRG_OK;
 }
 
+// One big host-to-device copy at a time per GPU, across the ranges of one build AND across builds that are in
+// flight side by side (device.BuildPipeline: the upload of build k+1 runs while build k is in its level loop):
+// copies that share the link finish together, copies in turn let the first one's kernels start early.
+static std::mutex &link_mutex(int device) {
+    static std::mutex m[64];
+    return m[(unsigned)device & 63u];
+}
+
 // Loci [l0, l1) of the batch: ASCII host -> device stage of `ctx` (its stream), packed on the device
 // into the batch arena, alphabet flags back.  Ranges are independent, so the worker contexts of
 // mprg_build_ascii upload theirs concurrently and the copies overlap the other workers' kernels.
@@ -347,7 +355,7 @@ int batch_upload_range(mprg_ctx *ctx, mprg_batch *b, const uint8_t *h_ascii, con
     }
     // One range at a time on the PCIe link: concurrent copies of several workers would share the
     // bandwidth and finish together; in turn, the first range is being built while the next is copied.
-    std::unique_lock<std::mutex> link(b->copy_mutex);
+    std::unique_lock<std::mutex> link(link_mutex(ctx->device));
     if (d_host_view) {
         for (int i = 0; i < n; ++i) aoff[i] = h_offsets[l0 + i];  // offsets into the caller's buffer
     } else {
@@ -401,7 +409,7 @@ int batch_upload_range_packed(mprg_ctx *ctx, mprg_batch *b, const uint8_t *h_pac
     if (l1 <= l0) return MPRG_OK;
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
-    std::unique_lock<std::mutex> link(b->copy_mutex);  // one range at a time on the PCIe link
+    std::unique_lock<std::mutex> link(link_mutex(ctx->device));  // one range at a time on the PCIe link
     int run0 = l0;
     for (int l = l0; l < l1; ++l) {
         const long long bytes_l = (long long)b->stride[l] * b->n_rows[l];

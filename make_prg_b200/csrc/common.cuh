@@ -139,7 +139,6 @@ struct mprg_batch {
     long long packed_bytes = 0;
     uint8_t *d_packed = nullptr;
     size_t packed_capacity = 0;
-    std::mutex copy_mutex;  // orders the host-to-device copies of the ranges of mprg_build_ascii
     std::atomic<bool> any_n{false};  // set by whichever upload finds an N; a stale read only picks the slower scan variant
 };
 

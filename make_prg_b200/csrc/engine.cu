@@ -56,7 +56,9 @@ static void randomstate_doubles(uint32_t seed, double *out, int count) {
 }
 
 static bool g_rand_uploaded = false;
+static std::mutex g_rand_mutex;  // first builds of two contexts may arrive together (device.BuildPipeline)
 int ensure_rand(mprg_ctx *ctx) {
+    std::lock_guard<std::mutex> lock(g_rand_mutex);
     if (g_rand_uploaded) return MPRG_OK;
     double r[KM_RAND_COUNT];
     randomstate_doubles(2u, r, KM_RAND_COUNT);

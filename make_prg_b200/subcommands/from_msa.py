@@ -161,51 +161,81 @@ def locus_name_of(path):
 
 
 def iter_built_chunks(input_files, options, device_ordinal=0, chunks=None):
-    """Loads (native loader, one chunk ahead on a host thread) and builds (mprg_build_ascii) the input
-    files chunk by chunk.  Yields (names, msas, result, ok) with ok = indices of the chunk's loci that
-    were built; the consumer frees result and msas.  Errors follow from_msa.py:142-151: an empty MSA
-    aborts the run, a locus with a disallowed base is skipped with a warning."""
+    """Loads (native loader, one chunk ahead on a host thread) and builds the input files chunk by chunk.  The
+    builds go through device.BuildPipeline: chunk k+1 is submitted before the result of chunk k is handed on, so
+    its host-to-device copy overlaps the level loop of chunk k (one lane for a one-chunk run).  Yields (names,
+    msas, result, ok) in input order, ok = indices of the chunk's loci that were built; the consumer frees result
+    and msas.  Errors follow from_msa.py:142-151: an empty MSA aborts the run, a locus with a disallowed base
+    is skipped with a warning."""
+    from collections import deque
     from concurrent.futures import ThreadPoolExecutor
 
     from .. import device
 
-    ctx = device.default_context(device_ordinal)
     if chunks is None:
         chunks = cut_chunks(input_files)
-    with ThreadPoolExecutor(1) as pool:
-        threads = side_threads(len(chunks))
-        future = pool.submit(_load_chunk, chunks[0], options.alignment_format, threads) if chunks else None
-        for k, paths in enumerate(chunks):
-            msas = future.result()
-            future = (pool.submit(_load_chunk, chunks[k + 1], options.alignment_format, threads)
-                      if k + 1 < len(chunks) else None)
-            names = [locus_name_of(path) for path in paths]
-            logger.info(f"Generating PRGs for {names[0]} ... {names[-1]} ({len(names)} loci)...")
-            for i in np.nonzero(msas.flags & hostio.FLAG_DUPLICATE_IDS)[0]:
-                logger.warning(f"{names[int(i)]}: duplicated record ids; clusters are cut by row here, the reference "
-                               "pulls every record with a clustered id (recursion_tree.py:558-572), so its PRG may "
-                               "differ for this locus")
-            curation = set()  # loci whose rows hold non-ASCII characters: skipped like any disallowed base
-            for i in np.nonzero(msas.status != hostio.LOAD_OK)[0]:
+    pipe = device.default_pipeline(device_ordinal, min(3, device.default_lanes(), max(1, len(chunks))))
+    in_flight = deque()  # (names, msas, curation, future of (batch, result)), oldest first
+
+    def built(entry):
+        names, msas, curation, fut = entry
+        batch, res = fut.result()
+        batch.free()
+        statuses, _lengths = res.statuses()
+        ok = np.nonzero(statuses == LOCUS_OK)[0].tolist()
+        for i in np.nonzero(statuses != LOCUS_OK)[0].tolist():
+            if statuses[i] == LOCUS_CURATION_ERROR or i in curation:
+                logger.warning(f"Skipping building PRG for {names[i]}. Error: a slice of a sequence has a "
+                               "disallowed base. Redo sequence curation.")
+            else:
                 try:
-                    hostio.raise_for_load_status(msas, int(i))
-                except hostio.NonAsciiSequenceError:
-                    curation.add(int(i))
-                except ValueError as err:
-                    if "No records found in handle" in str(err.args[0]):
-                        raise EmptyMSAError(f"No records found in MSA of locus {names[int(i)]}")
-                    raise
-            batch, res = ctx.build_msa_set(msas, options.max_nesting, options.min_match_length)
-            batch.free()
-            statuses, _lengths = res.statuses()
-            ok = np.nonzero(statuses == LOCUS_OK)[0].tolist()
-            for i in np.nonzero(statuses != LOCUS_OK)[0].tolist():
-                if statuses[i] == LOCUS_CURATION_ERROR or i in curation:
-                    logger.warning(f"Skipping building PRG for {names[i]}. Error: a slice of a sequence has a "
-                                   "disallowed base. Redo sequence curation.")
-                else:
                     engine.LocusBuild(int(statuses[i]), "", 0, 0, None).raise_for_status(names[i])
-            yield names, msas, res, ok
+                except BaseException:
+                    res.free()
+                    raise
+        return names, msas, res, ok
+
+    try:
+        with ThreadPoolExecutor(1) as pool:
+            threads = side_threads(len(chunks))
+            future = pool.submit(_load_chunk, chunks[0], options.alignment_format, threads) if chunks else None
+            for k, paths in enumerate(chunks):
+                msas = future.result()
+                future = (pool.submit(_load_chunk, chunks[k + 1], options.alignment_format, threads)
+                          if k + 1 < len(chunks) else None)
+                names = [locus_name_of(path) for path in paths]
+                logger.info(f"Generating PRGs for {names[0]} ... {names[-1]} ({len(names)} loci)...")
+                for i in np.nonzero(msas.flags & hostio.FLAG_DUPLICATE_IDS)[0]:
+                    logger.warning(f"{names[int(i)]}: duplicated record ids; clusters are cut by row here, the "
+                                   "reference pulls every record with a clustered id (recursion_tree.py:558-572), so "
+                                   "its PRG may differ for this locus")
+                curation = set()  # loci whose rows hold non-ASCII characters: skipped like any disallowed base
+                for i in np.nonzero(msas.status != hostio.LOAD_OK)[0]:
+                    try:
+                        hostio.raise_for_load_status(msas, int(i))
+                    except hostio.NonAsciiSequenceError:
+                        curation.add(int(i))
+                    except ValueError as err:
+                        if "No records found in handle" in str(err.args[0]):
+                            raise EmptyMSAError(f"No records found in MSA of locus {names[int(i)]}")
+                        raise
+                in_flight.append((names, msas, curation,
+                                  pipe.submit_msa_set(msas, options.max_nesting, options.min_match_length)))
+                while len(in_flight) > 1:
+                    yield built(in_flight.popleft())
+            while in_flight:
+                yield built(in_flight.popleft())
+    finally:
+        # an error (here or in the consumer) with builds still in flight: wait for them and drop their results
+        while in_flight:
+            _names, msas, _curation, fut = in_flight.popleft()
+            try:
+                batch, res = fut.result()
+                batch.free()
+                res.free()
+            except Exception:
+                pass
+            msas.free()
 
 
 def _update_ds_pickles(names, msas, res, ok, options):

@@ -344,6 +344,52 @@ def test_packed_host_rows_equal_device_pack_and_text_build():
     assert res_text.status(2) == 1 and res_text.status(0) == 0
 
 
+def test_build_pipeline_lanes_equal_one_at_a_time_builds():
+    """device.BuildPipeline: builds in flight side by side on two lanes (own contexts, own host threads) return
+    exactly what one build at a time returns -- PRG strings, statuses, trees -- for every submission, whichever
+    lane took it, with and without a consume callback."""
+    import numpy as np
+    from make_prg_b200 import device, hostio, synth
+
+    ctx = device.default_context(0)
+    sets = []
+    for s in range(5):
+        mats = [synth.synth_msa(4 + (i * 5 + s) % 40, 40 + (37 * i + 11 * s) % 700, 7000 + 100 * s + i,
+                                var_frac=0.05 + 0.03 * (i % 4), n_dels=i % 3) for i in range(48)]
+        if s == 1:
+            mats[3][0, 2] = ord("Z")  # a locus that is skipped
+        if s == 2:
+            mats[5][1, 10:13] = np.frombuffer(b"RYK", np.uint8)  # host assembly (IUPAC product)
+        packed, flags = zip(*(hostio.pack_rows(m) for m in mats))
+        flat = np.concatenate([p.reshape(-1) for p in packed])
+        offsets = np.cumsum([0] + [p.size for p in packed[:-1]])
+        args = (flat, offsets, [m.shape[0] for m in mats], [m.shape[1] for m in mats], flags, 5, 7)
+        b, res = ctx.build_packed(*args)
+        want = [(res.status(i), res.prg(i), res.n_nodes(i)) for i in range(len(mats))]
+        want_tree = {k: v.tolist() for k, v in res.nodes(7).items()}
+        res.free()
+        b.free()
+        sets.append((args, want, want_tree))
+
+    def consume(b, res):
+        return ([(res.status(i), res.prg(i), res.n_nodes(i)) for i in range(res.n_loci)],
+                {k: v.tolist() for k, v in res.nodes(7).items()})
+
+    with device.BuildPipeline(0, depth=2) as pipe:
+        order = [0, 1, 2, 3, 4, 4, 3, 2, 1, 0, 2, 2, 0]
+        futs = [pipe.submit_packed(*sets[k][0], consume=consume) for k in order]
+        for k, f in zip(order, futs):
+            got, tree = f.result()
+            assert got == sets[k][1], k
+            assert tree == sets[k][2], k
+        # without a callback the caller owns batch and result
+        b, res = pipe.submit_packed(*sets[1][0]).result()
+        assert [(res.status(i), res.prg(i), res.n_nodes(i)) for i in range(res.n_loci)] == sets[1][1]
+        res.free()
+        b.free()
+        assert pipe.launch_count() > 0 and pipe.copy_stats()["h2d_bytes"] > 0
+
+
 class _VectorAligner:
     """Stands in for the MSA aligner of `make_prg update`: hands back the alignment of a golden vector."""
 
