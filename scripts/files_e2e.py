@@ -97,6 +97,8 @@ def measure(n_loci=1000, reps=5, copies=1, python_io=False, update_ds=False):
     t0 = time.perf_counter()
     msas = hostio.load_fasta_files(paths, packed=True)
     t_load = time.perf_counter() - t0
+    # the context build_and_write's one-chunk run used (a lane of the process-wide pipeline): warm buffers
+    ctx = device.default_pipeline(0, 1).contexts[0]
     t0 = time.perf_counter()
     batch, res = ctx.build_msa_set(msas, 5, 7)
     t_build = time.perf_counter() - t0
