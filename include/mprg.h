@@ -107,6 +107,12 @@ int mprg_scan_stats(mprg_ctx *ctx, double *ms, double *bytes, int64_t *launches,
  * the other; MPRG_DEV_RANGES overrides); the full count only applies to the host-driven loop kept as the checked
  * alternative (MPRG_HOST_LOOP=1) and to the host threads that assemble PRG strings of loci holding RYKMSW. */
 int mprg_set_workers(mprg_ctx *ctx, int32_t n_workers);
+/* How the host thread of a build waits for the device at the synchronisation points of the level loop and of the
+ * uploads: 0 (default) = cudaStreamSynchronize (the driver's choice, in practice a spin: lowest latency for one
+ * build at a time), 1 = the thread sleeps on an event created with cudaEventBlockingSync, 2 = it polls
+ * cudaStreamQuery and yields the core between polls.  Contexts that run side by side (device.BuildPipeline:
+ * several builds in flight per GPU, one host thread each) choose by measurement (profiles/r2_lanes_sweep.txt). */
+int mprg_set_wait_mode(mprg_ctx *ctx, int32_t mode);
 /* host<->device bytes copied by this context since the last reset (bench.py's e2e object) */
 int mprg_copy_stats(mprg_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes, int reset);
 /* CUDA-event stopwatch on the context's stream: op 0 records the start, op 1 records the stop,

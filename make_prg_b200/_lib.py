@@ -59,6 +59,7 @@ SIGNATURES = {
     "mprg_path_counts": (C.c_int, [P, P, C.c_int]),
     "mprg_kmeans_stats": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(I64), C.POINTER(I64), C.c_int]),
     "mprg_set_workers": (C.c_int, [P, I32]),
+    "mprg_set_wait_mode": (C.c_int, [P, I32]),
     "mprg_copy_stats": (C.c_int, [P, C.POINTER(I64), C.POINTER(I64), C.c_int]),
     "mprg_timer": (C.c_int, [P, C.c_int, C.POINTER(C.c_double)]),
     "mprg_scan_log": (C.c_int, [P, P, P, I32, C.POINTER(I32), C.c_int]),

@@ -221,6 +221,7 @@ extern "C" void mprg_destroy(mprg_ctx *ctx) {
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->stream_side) cudaStreamDestroy(ctx->stream_side);
     if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
+    if (ctx->ev_wait) cudaEventDestroy(ctx->ev_wait);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -421,7 +422,7 @@ int batch_upload_range_packed(mprg_ctx *ctx, mprg_batch *b, const uint8_t *h_pac
             MPRG_CUDA(ctx, mprg::copy_h2d(ctx, b->d_packed + b->base[run0], h_packed + h_offsets[run0], (size_t)nbytes, s));
         run0 = l + 1;
     }
-    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    MPRG_CUDA(ctx, mprg::wait_stream(ctx, s));
     link.unlock();
     for (int l = l0; l < l1; ++l) {
         b->flags[l] = h_flags ? h_flags[l] : 0;

@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <sched.h>
 #include <string>
 #include <vector>
 
@@ -152,6 +153,8 @@ struct mprg_ctx {
     std::string err;
     long long launches = 0;
     int n_workers = 1;                // host threads / streams mprg_build may use
+    int wait_mode = 0;                // mprg_set_wait_mode: 0 cudaStreamSynchronize, 1 sleep on ev_wait, 2 poll + yield
+    cudaEvent_t ev_wait = nullptr;    // cudaEventBlockingSync | cudaEventDisableTiming, made on first use
     std::vector<mprg_ctx *> workers;  // lazily created worker contexts (same device)
     long long h2d_bytes = 0, d2h_bytes = 0;
     // which variants the engine chose (mprg_path_counts): see MPRG_PATH_* in mprg.h
@@ -191,6 +194,21 @@ struct mprg_ctx {
 };
 
 namespace mprg {
+// The host waits for everything queued on `st` (a stream of this context): see mprg_set_wait_mode.
+inline cudaError_t wait_stream(mprg_ctx *c, cudaStream_t st) {
+    if (c->wait_mode == 0) return cudaStreamSynchronize(st);
+    cudaError_t e = cudaSuccess;
+    if (c->wait_mode == 2) {
+        // poll, and hand the core to any other runnable thread between polls: as quick as a spin on an idle host,
+        // and the waiting lanes of several builds in flight do not starve the lanes that are launching
+        while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) sched_yield();
+        return e;
+    }
+    if (!c->ev_wait) e = cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_wait, st);
+    if (e == cudaSuccess) e = cudaEventSynchronize(c->ev_wait);
+    return e;
+}
 inline cudaError_t copy_h2d(mprg_ctx *c, void *dst, const void *src, size_t n, cudaStream_t st) {
     c->h2d_bytes += (long long)n;
     return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st);

@@ -1443,6 +1443,13 @@ static int build_range(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end,
     return MPRG_OK;
 }
 
+extern "C" int mprg_set_wait_mode(mprg_ctx *ctx, int32_t mode) {
+    if (!ctx || mode < 0 || mode > 2) return MPRG_E_BAD_ARG;
+    ctx->wait_mode = mode;
+    for (mprg_ctx *w : ctx->workers) w->wait_mode = mode;
+    return MPRG_OK;
+}
+
 extern "C" int mprg_set_workers(mprg_ctx *ctx, int32_t n_workers) {
     if (!ctx || n_workers < 1 || n_workers > 64) return MPRG_E_BAD_ARG;
     ctx->n_workers = n_workers;
@@ -1518,6 +1525,7 @@ static int build_ranges(mprg_ctx *ctx, mprg_batch *batch, int32_t max_nesting, i
             delete res;
             MPRG_FAIL(ctx, rc, "could not create a worker context");
         }
+        w->wait_mode = ctx->wait_mode;
         ctx->workers.push_back(w);
     }
     // contiguous ranges of roughly equal rows x cols, dealt round-robin; from host ASCII there are

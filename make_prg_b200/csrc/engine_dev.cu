@@ -1314,7 +1314,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         ctx->launches += 3;
         MPRG_CUDA(ctx, cudaGetLastError());
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, cnt, d_cnt, sizeof(DevCounters), s));
-        MPRG_CUDA(ctx, cudaStreamSynchronize(s));  // ---- sync A ----
+        MPRG_CUDA(ctx, mprg::wait_stream(ctx, s));  // ---- sync A ----
         TRACE("dev: prepare+sync A");
         if (cnt->err) break;
         const int nt = cnt->n_tasks;
@@ -1443,7 +1443,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
             ctx->launches += 3;
             MPRG_CUDA(ctx, cudaGetLastError());
             MPRG_CUDA(ctx, mprg::copy_d2h(ctx, cnt, d_cnt, sizeof(DevCounters), s));
-            MPRG_CUDA(ctx, cudaStreamSynchronize(s));  // ---- sync C ----
+            MPRG_CUDA(ctx, mprg::wait_stream(ctx, s));  // ---- sync C ----
             TRACE("dev: dedupe+problems+sync C");
             if (cnt->err) break;
             const int np = cnt->np, n_ct = cnt->n_ctasks;
@@ -1529,7 +1529,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
                     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, task_of.data(), pa.task_of_prob, sizeof(int) * np, s));
                     if (!seq_rows.empty())
                         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, seq_rows.data(), pa.seq_rows, sizeof(int) * seq_rows.size(), s));
-                    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+                    MPRG_CUDA(ctx, mprg::wait_stream(ctx, s));
                     // problems in the order of the device table; each names its slice of seq_rows
                     std::vector<HostProblem> hp(np);
                     std::vector<int> seq_sorted;
@@ -1630,7 +1630,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         raw.pool = pinned_acquire(sizeof(int) * (size_t)std::max<long long>(pool_size, 1));
         if (!raw.nodes.p || !raw.pool.p) MPRG_FAIL(ctx, MPRG_E_CUDA, "pinned allocation for the result failed");
         auto drop_raw = [&]() {
-            cudaStreamSynchronize(ctx->stream_side);
+            mprg::wait_stream(ctx, ctx->stream_side);
             pinned_release(raw.nodes);
             pinned_release(raw.pool);
         };
@@ -1657,7 +1657,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         PrgInfo *h_info = ctx->h_d.as<PrgInfo>();
         long long *h_total = reinterpret_cast<long long *>(h_info + nl);
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_total, d_total, sizeof(long long), s));
-        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+        MPRG_CUDA(ctx, mprg::wait_stream(ctx, s));
         const long long blob_bytes = *h_total;
         TRACE("dev: measure + raw tree D2H");
         PinnedBlock blob = pinned_acquire((size_t)std::max<long long>(blob_bytes, 1));
@@ -1676,8 +1676,8 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
         if (blob_bytes > 0) MPRG_CUDA(ctx, mprg::copy_d2h(ctx, blob.p, V[V_OUT].p, (size_t)blob_bytes, s));
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_info, d_info, sizeof(PrgInfo) * (size_t)nl, s));
         MPRG_CUDA(ctx, mprg::copy_d2h(ctx, cnt, d_cnt, sizeof(DevCounters), s));
-        MPRG_CUDA(ctx, cudaStreamSynchronize(s));
-        MPRG_CUDA(ctx, cudaStreamSynchronize(ctx->stream_side));
+        MPRG_CUDA(ctx, mprg::wait_stream(ctx, s));
+        MPRG_CUDA(ctx, mprg::wait_stream(ctx, ctx->stream_side));
         TRACE("dev: strings D2H");
         if (cnt->err & ERR_OVERFLOW) {
             pinned_release(blob);
@@ -1735,7 +1735,7 @@ int build_range_dev(mprg_ctx *ctx, mprg_batch *batch, int l_begin, int l_end, in
     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_nodes, V[V_NODES].p, sizeof(DNode) * (size_t)n_nodes, s));
     if (pool_size > 0) MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_pool, V[V_POOL].p, sizeof(int) * (size_t)pool_size, s));
     MPRG_CUDA(ctx, mprg::copy_d2h(ctx, h_loci_back, d_loci, sizeof(DLocus) * nl, s));
-    MPRG_CUDA(ctx, cudaStreamSynchronize(s));
+    MPRG_CUDA(ctx, mprg::wait_stream(ctx, s));
     TRACE("dev: results D2H");
 
     // ---- per-locus node tables (children contiguous, local indices), then the PRG strings ----

@@ -83,6 +83,13 @@ class Context:
     def set_workers(self, n):
         self._check(self.lib.mprg_set_workers(self.handle, int(n)))
 
+    WAIT_MODES = {"spin": 0, "block": 1, "yield": 2}
+
+    def set_wait_mode(self, mode):
+        """How the host thread of a build waits at the level loop's synchronisation points (mprg_set_wait_mode):
+        "spin" (cudaStreamSynchronize), "block" (sleep on an event), "yield" (poll + sched_yield)."""
+        self._check(self.lib.mprg_set_wait_mode(self.handle, self.WAIT_MODES[mode]))
+
     PATHS = ("kmeans_cta", "kmeans_group", "refcheck_cta", "refcheck_grid", "refcheck_grid_multi", "kmer_grid",
              "dedupe_grid")
 
@@ -393,18 +400,23 @@ class BuildResult:
 
 
 def default_lanes():
-    """Builds in flight per GPU: each lane is a host thread that waits on its stream, so the count follows this
-    process's share of the host cores (LOCAL_WORLD_SIZE ranks share them): 6 on a 16-core host with one GPU
-    (measured: 2 lanes 3.7 ms, 3 lanes 2.75, 4 lanes 2.5, 6 lanes 2.2 ms per 1,000-locus step from host rows, one
-    at a time 4.6), 3 when eight ranks share 32 cores.  MPRG_BUILD_LANES overrides."""
+    """Builds in flight per GPU.  Each lane is a host thread that launches the kernels of its build and waits at
+    two synchronisation points per recursion level, so the count follows this process's share of the host cores
+    (its CPU affinity, divided among LOCAL_WORLD_SIZE ranks): 6 lanes from 7 cores up, 3 on a 4-core share (eight
+    ranks on a 32-core host).  Measured per 1,000-locus step (profiles/r2_lanes_sweep.txt; one build at a time:
+    2.7 ms resident, 4.6 ms from host rows): 6 lanes 1.3-1.4 ms / 2.2-2.3 ms on 16-24 cores, 3 lanes on a 4-core
+    share 1.8 / 2.7 ms.  MPRG_BUILD_LANES overrides."""
     import os
 
     env = os.environ.get("MPRG_BUILD_LANES")
     if env:
         return max(1, int(env))
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
     share = cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-    return max(2, min(6, share - 1))
+    return max(3, min(6, share - 1))
 
 
 class BuildPipeline:
@@ -428,8 +440,14 @@ class BuildPipeline:
             raise ValueError("depth must be >= 1")
         self.depth = depth
         self.contexts = [Context(device) for _ in range(depth)]
+        import os
+
+        # a waiting lane polls and yields its core (mprg_set_wait_mode): with plain spinning, 2 ranks x 6 lanes on a
+        # 24-core host ran a resident step in 3.2 ms instead of 1.3, sleeping on an event in 2.5
+        wait = os.environ.get("MPRG_LANE_WAIT", "yield") if depth > 1 else "spin"
         for c in self.contexts:
             c.set_workers(1)  # one range per build: the overlap comes from the other lanes
+            c.set_wait_mode(wait)
         self._lanes = [ThreadPoolExecutor(1, thread_name_prefix=f"mprg-lane{i}") for i in range(depth)]
         self._next = 0
 
