@@ -61,3 +61,19 @@ def test_two_rank_gloo_shard_gather_is_order_invariant(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").read_text() == "1"
+
+
+def test_default_lanes_follow_the_core_share(monkeypatch):
+    """device.default_lanes: builds in flight per GPU = this process's share of the host cores minus one, between
+    3 and 6; MPRG_BUILD_LANES overrides (no device needed)."""
+    import os
+
+    from make_prg_b200 import device
+
+    monkeypatch.delenv("MPRG_BUILD_LANES", raising=False)
+    for cores, ranks, want in ((16, 1, 6), (24, 2, 6), (32, 4, 6), (32, 8, 3), (8, 2, 3), (2, 1, 3), (12, 2, 5)):
+        monkeypatch.setattr(os, "sched_getaffinity", lambda pid, n=cores: set(range(n)))
+        monkeypatch.setenv("LOCAL_WORLD_SIZE", str(ranks))
+        assert device.default_lanes() == want, (cores, ranks)
+    monkeypatch.setenv("MPRG_BUILD_LANES", "9")
+    assert device.default_lanes() == 9
