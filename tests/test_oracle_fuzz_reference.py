@@ -3,6 +3,8 @@
 one-row / one-column alignments, gap-placement twins, all-gap column blocks, N, RYKMSW, lower case, symbols outside
 the alphabet.  The reference runs in-process from /root/reference (or the copy staged under oracle/_ref) under the
 Biopython stand-in of oracle/run_reference.py; skipped where neither is present."""
+import os
+
 import numpy as np
 import pytest
 
@@ -29,7 +31,8 @@ def reference_outcome(path, N, L):
 @pytest.mark.parametrize("setting", range(len(SETTINGS)))
 def test_oracle_equals_unmodified_reference_on_fuzz_alignments(setting, tmp_path):
     N, L = SETTINGS[setting]
-    rng = np.random.default_rng(77_000 + setting)  # the GPU test's default stream (MPRG_FUZZ_SEED=0)
+    # the GPU test's streams: MPRG_FUZZ_SEED=<int> draws another set there and here
+    rng = np.random.default_rng(77_000 + setting + 1000 * int(os.environ.get("MPRG_FUZZ_SEED", "0")))
     done = n_ok = 0
     while done < PER_SETTING:
         text = random_msa(rng)
