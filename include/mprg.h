@@ -11,8 +11,11 @@
  *   - plain pointers and sizes only.  Every pointer an entry point takes (h_*) is HOST memory owned by the
  *     caller (pinned or pageable; the library never frees caller memory).  Device memory is owned by the
  *     library: batches (mprg_batch) hold the packed MSAs in HBM, results (mprg_result) hold what came back.
- *   - one context per GPU, used from one host thread at a time; all work is enqueued on the
- *     context's stream; entry points that return host results synchronise that stream.
+ *   - a context is used from one host thread at a time; all its work is enqueued on the context's
+ *     stream; entry points that return host results synchronise that stream.  Several contexts of one
+ *     GPU may build side by side from their own host threads (that is how throughput is reached:
+ *     INTEGRATION.md section 5, make_prg_b200.device.BuildPipeline); batches and results may be
+ *     freed from any thread, a batch may be built by any context of its GPU.
  *   - there is NO CPU fallback: without a CUDA device mprg_create fails with MPRG_E_NO_DEVICE.
  *
  * Symbol codes of the 4-bit packed MSA (rows padded to 16 bytes = 32 columns with MPRG_SYM_PAD; inside
