@@ -14,7 +14,7 @@
  *   - a context is used from one host thread at a time; all its work is enqueued on the context's
  *     stream; entry points that return host results synchronise that stream.  Several contexts of one
  *     GPU may build side by side from their own host threads (that is how throughput is reached:
- *     INTEGRATION.md section 5, make_prg_b200.device.BuildPipeline); batches and results may be
+ *     INTEGRATION.md section 6, make_prg_b200.device.BuildPipeline); batches and results may be
  *     freed from any thread, a batch may be built by any context of its GPU.
  *   - there is NO CPU fallback: without a CUDA device mprg_create fails with MPRG_E_NO_DEVICE.
  *
