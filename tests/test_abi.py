@@ -45,3 +45,29 @@ def test_no_cpu_fallback_without_device():
 
     with pytest.raises(_lib.MprgError):
         device.Context(0)
+
+
+def build_c_caller(tmp_path):
+    """tests/c_abi/lanes.c: a plain C99 + pthreads caller of include/mprg.h (the header must be valid C)."""
+    import subprocess
+
+    from make_prg_b200 import build
+
+    lib = build.build_library()
+    exe = tmp_path / "lanes"
+    subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", str(REPO / "include"),
+                    str(REPO / "tests" / "c_abi" / "lanes.c"), "-o", str(exe), str(lib), "-lpthread",
+                    f"-Wl,-rpath,{lib.parent}"], check=True)
+    return exe
+
+
+def test_c_caller_compiles_links_and_fails_loudly_without_device(tmp_path):
+    import subprocess
+
+    import torch
+
+    exe = build_c_caller(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present (tests/test_gpu_host_api.py runs the program)")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 77 and "MPRG_E_NO_DEVICE" in out.stdout

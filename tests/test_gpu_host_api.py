@@ -390,6 +390,19 @@ def test_build_pipeline_lanes_equal_one_at_a_time_builds():
         assert pipe.launch_count() > 0 and pipe.copy_stats()["h2d_bytes"] > 0
 
 
+def test_c_caller_with_several_contexts_in_flight(tmp_path):
+    """tests/c_abi/lanes.c on the GPU: four host threads of a plain C program, one context each, build the same
+    loci from packed host rows side by side; every PRG equals the one a single context built."""
+    import subprocess
+
+    from test_abi import build_c_caller
+
+    exe = build_c_caller(tmp_path)
+    out = subprocess.run([str(exe), "4", "6"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "0 mismatches" in out.stdout
+
+
 class _VectorAligner:
     """Stands in for the MSA aligner of `make_prg update`: hands back the alignment of a golden vector."""
 
