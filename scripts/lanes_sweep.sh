@@ -18,3 +18,5 @@ run2 n2_8c_spin2 0-7 MPRG_LANE_WAIT=spin MPRG_BUILD_LANES=2
 run2 n2_8c_yield3 0-7 MPRG_LANE_WAIT=yield MPRG_BUILD_LANES=3
 run1 n1_16c_spin4 0-15 MPRG_LANE_WAIT=spin MPRG_BUILD_LANES=4
 run1 n1_16c_yield6 0-15 MPRG_LANE_WAIT=yield MPRG_BUILD_LANES=6
+# 1-GPU box: more lanes than the default
+# for l in 8 10; do run1 n1_16c_yield$l 0-15 MPRG_BUILD_LANES=$l; done
