@@ -612,6 +612,37 @@ void replace_n(uint8_t *m, int64_t n_rows, int64_t n_cols) {
 }
 
 // Mirrors make_prg_b200.utils.io_utils.parse_fasta + the upper-casing of load_alignment_file.
+// True when two of the record ids (first whitespace-separated token of each title) are equal.  The common case --
+// all distinct -- is settled by sorting 64-bit hashes of the tokens; equal hashes are compared as strings.
+bool has_duplicate_ids(const std::string &t, int n_rows) {
+    struct Tok { uint64_t h; uint32_t a, n; };
+    static thread_local std::vector<Tok> toks;
+    toks.clear();
+    toks.reserve((size_t)n_rows);
+    size_t at = 0;
+    auto is_ws = [](unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r') || (c >= 0x1c && c <= 0x1f); };
+    for (int r = 0; r < n_rows; ++r) {
+        size_t e = t.find('\n', at);
+        if (e == std::string::npos) e = t.size();
+        size_t a = at;
+        while (a < e && is_ws((unsigned char)t[a])) ++a;
+        size_t b = a;
+        uint64_t h = 0xcbf29ce484222325ull;
+        while (b < e && !is_ws((unsigned char)t[b])) {
+            h = (h ^ (unsigned char)t[b]) * 0x100000001b3ull;
+            ++b;
+        }
+        toks.push_back(Tok{h, (uint32_t)a, (uint32_t)(b - a)});
+        at = e + 1;
+    }
+    std::sort(toks.begin(), toks.end(), [](const Tok &x, const Tok &y) { return x.h < y.h; });
+    for (size_t i = 0; i + 1 < toks.size(); ++i) {
+        for (size_t j = i + 1; j < toks.size() && toks[j].h == toks[i].h; ++j)
+            if (toks[j].n == toks[i].n && t.compare(toks[j].a, toks[j].n, t, toks[i].a, toks[i].n) == 0) return true;
+    }
+    return false;
+}
+
 void parse_file(const char *path, ParsedFile &pf, bool avx2, Slab &slab) {
     // the read buffer is reused by the files of one thread (a pool block as the target of read() made the
     // threads of a call run one after the other here: 34 instead of 7.5 ms for 200 files on 8 threads)
@@ -683,23 +714,7 @@ void parse_file(const char *path, ParsedFile &pf, bool avx2, Slab &slab) {
         pf.status = MPRG_LOAD_RAGGED;
         return;
     }
-    {
-        // duplicate record ids (first whitespace-separated token of each title)
-        std::unordered_map<std::string, int> seen;
-        seen.reserve((size_t)pf.n_rows * 2);
-        size_t at = 0;
-        const std::string &t = pf.titles;
-        for (int r = 0; r < pf.n_rows; ++r) {
-            size_t e = t.find('\n', at);
-            if (e == std::string::npos) e = t.size();
-            size_t a = at;
-            while (a < e && (t[a] == ' ' || (t[a] >= '\t' && t[a] <= '\r') || (t[a] >= 0x1c && t[a] <= 0x1f))) ++a;
-            size_t b = a;
-            while (b < e && !(t[b] == ' ' || (t[b] >= '\t' && t[b] <= '\r') || (t[b] >= 0x1c && t[b] <= 0x1f))) ++b;
-            if (++seen[t.substr(a, b - a)] == 2) pf.flags |= MPRG_LOAD_FLAG_DUPLICATE_IDS;
-            at = e + 1;
-        }
-    }
+    if (has_duplicate_ids(pf.titles, pf.n_rows)) pf.flags |= MPRG_LOAD_FLAG_DUPLICATE_IDS;
     pf.n_cols = (int32_t)first_len;
     pf.matrix_bytes = (int64_t)pf.n_rows * first_len;
     if (first_len > INT32_MAX) pf.status = MPRG_LOAD_IO_ERROR;
@@ -761,17 +776,22 @@ inline int pack_chunk_scalar(const uint8_t *src, int valid, uint8_t *dst) {
 }
 
 __attribute__((target("avx2"))) int pack_row_avx2(const uint8_t *src, int cols, uint8_t *dst) {
-    const PackTables &t = pack_tables();
-    // letters by their low five bits: two 16-entry tables ('@'..'O', 'P'..'_')
-    alignas(32) uint8_t lo[32], hi[32], cls[32];
-    for (int k = 0; k < 16; ++k) {
-        lo[k] = lo[k + 16] = t.code[0x40 + k];
-        hi[k] = hi[k + 16] = t.code[0x50 + k];
-        cls[k] = cls[k + 16] = t.cls[k];
-    }
-    lo[0] = lo[16] = MPRG_SYM_PAD;  // '@' / '`' are no letters
-    const __m256i t_lo = _mm256_load_si256((const __m256i *)lo), t_hi = _mm256_load_si256((const __m256i *)hi);
-    const __m256i t_cls = _mm256_load_si256((const __m256i *)cls);
+    // letters by their low five bits: two 16-entry tables ('@'..'O', 'P'..'_'), made once (this runs per row)
+    struct Vec {
+        alignas(32) uint8_t lo[32], hi[32], cls[32];
+        Vec() {
+            const PackTables &t = pack_tables();
+            for (int k = 0; k < 16; ++k) {
+                lo[k] = lo[k + 16] = t.code[0x40 + k];
+                hi[k] = hi[k + 16] = t.code[0x50 + k];
+                cls[k] = cls[k + 16] = t.cls[k];
+            }
+            lo[0] = lo[16] = MPRG_SYM_PAD;  // '@' / '`' are no letters
+        }
+    };
+    static const Vec tv;
+    const __m256i t_lo = _mm256_load_si256((const __m256i *)tv.lo), t_hi = _mm256_load_si256((const __m256i *)tv.hi);
+    const __m256i t_cls = _mm256_load_si256((const __m256i *)tv.cls);
     const __m256i v_dash = _mm256_set1_epi8('-'), v_case = _mm256_set1_epi8(0x20), v_a = _mm256_set1_epi8('a' - 1);
     const __m256i v_z = _mm256_set1_epi8('z' + 1), v_0f = _mm256_set1_epi8(0x0f), v_10 = _mm256_set1_epi8(0x10);
     const __m256i v_pad = _mm256_set1_epi8(MPRG_SYM_PAD);
