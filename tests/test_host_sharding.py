@@ -77,3 +77,102 @@ def test_default_lanes_follow_the_core_share(monkeypatch):
         assert device.default_lanes() == want, (cores, ranks)
     monkeypatch.setenv("MPRG_BUILD_LANES", "9")
     assert device.default_lanes() == 9
+
+
+def test_build_pipeline_lane_logic_with_stub_contexts(monkeypatch):
+    """device.BuildPipeline without a device: contexts replaced by stubs.  Submissions go to the lanes round
+    robin, a lane runs its submissions in order, consume runs before batch and result are freed, without consume
+    the caller gets (batch, result) un-freed, resident batches are never freed by the pipeline, an exception of a
+    build reaches the future and the lane keeps working."""
+    import threading
+    import time
+
+    from make_prg_b200 import device
+
+    log = []
+
+    class Obj:
+        def __init__(self, name):
+            self.name, self.freed = name, False
+
+        def free(self):
+            self.freed = True
+            log.append(("free", self.name))
+
+    class StubContext:
+        n = 0
+
+        def __init__(self, dev=0):
+            self.id = StubContext.n
+            StubContext.n += 1
+            self.workers = self.wait = None
+            self.thread_ids = set()
+
+        def set_workers(self, n):
+            self.workers = n
+
+        def set_wait_mode(self, mode):
+            self.wait = mode
+
+        def build_packed(self, tag, *a):
+            self.thread_ids.add(threading.get_ident())
+            if tag == "boom":
+                raise device.MprgError(-2, "injected")
+            time.sleep(0.01 if self.id == 0 else 0.0)  # lane 0 is the slow one
+            log.append(("build", self.id, tag))
+            return Obj(f"batch{tag}"), Obj(f"res{tag}")
+
+        def build(self, batch, *a):
+            log.append(("build_resident", self.id, batch.name))
+            return Obj("res_" + batch.name)
+
+        def launch_count(self):
+            return 1
+
+        def copy_stats(self, reset=False):
+            return {"h2d_bytes": 10, "d2h_bytes": 1}
+
+        def close(self):
+            log.append(("close", self.id))
+
+    monkeypatch.setattr(device, "Context", StubContext)
+    monkeypatch.delenv("MPRG_LANE_WAIT", raising=False)
+    pipe = device.BuildPipeline(0, depth=3)
+    assert [c.workers for c in pipe.contexts] == [1, 1, 1] and {c.wait for c in pipe.contexts} == {"yield"}
+    seen = []
+
+    def consume(batch, res):
+        assert not batch.freed and not res.freed
+        seen.append(res.name)
+        return res.name
+
+    futs = [pipe.submit_packed(k, None, None, None, None, 5, 7, consume=consume) for k in range(9)]
+    assert [f.result() for f in futs] == [f"res{k}" for k in range(9)]
+    builds = [e for e in log if e[0] == "build"]
+    assert sorted((lane, tag) for _, lane, tag in builds) == sorted((k % 3, k) for k in range(9))
+    for lane in range(3):  # in order per lane
+        assert [tag for _, l, tag in builds if l == lane] == [k for k in range(9) if k % 3 == lane]
+    assert sum(1 for e in log if e[0] == "free") == 18
+    assert all(len(c.thread_ids) == 1 for c in pipe.contexts)  # one host thread per lane
+    # no consume: the caller owns both objects
+    batch, res = pipe.submit_packed("x", None, None, None, None, 5, 7).result()
+    assert not batch.freed and not res.freed
+    # resident batches stay the caller's
+    mine = Obj("mine")
+    assert pipe.submit_resident(mine, 5, 7, consume=lambda b, r: (b is mine, r.name)).result() == (True, "res_mine")
+    assert not mine.freed
+    # a failing build: the error reaches the future, the lane goes on
+    lane = pipe.next_lane
+    bad = pipe.submit_packed("boom", None, None, None, None, 5, 7, consume=consume)
+    with pytest.raises(device.MprgError):
+        bad.result()
+    for _ in range(2):
+        pipe.submit_packed("skip", None, None, None, None, 5, 7, consume=consume).result()
+    assert pipe.next_lane == lane
+    assert pipe.submit_packed("after", None, None, None, None, 5, 7, consume=consume).result() == "resafter"
+    assert pipe.launch_count() == 3 and pipe.copy_stats() == {"h2d_bytes": 30, "d2h_bytes": 3}
+    pipe.close()
+    assert sum(1 for e in log if e[0] == "close") == 3
+    single = device.BuildPipeline(0, depth=1)
+    assert single.contexts[0].wait == "spin"
+    single.close()
