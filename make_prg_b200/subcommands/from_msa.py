@@ -179,6 +179,13 @@ def iter_built_chunks(input_files, options, device_ordinal=0, chunks=None):
 
     def built(entry):
         names, msas, curation, fut = entry
+        try:
+            return checked(names, msas, curation, fut)
+        except BaseException:
+            msas.free()  # this chunk is not handed on: nobody else would release its matrices
+            raise
+
+    def checked(names, msas, curation, fut):
         batch, res = fut.result()
         batch.free()
         statuses, _lengths = res.statuses()
@@ -195,12 +202,14 @@ def iter_built_chunks(input_files, options, device_ordinal=0, chunks=None):
                     raise
         return names, msas, res, ok
 
+    future = None  # the chunk being loaded ahead
+    loaded = None  # a chunk that has been loaded and not yet submitted
     try:
         with ThreadPoolExecutor(1) as pool:
             threads = side_threads(len(chunks))
             future = pool.submit(_load_chunk, chunks[0], options.alignment_format, threads) if chunks else None
             for k, paths in enumerate(chunks):
-                msas = future.result()
+                msas = loaded = future.result()
                 future = (pool.submit(_load_chunk, chunks[k + 1], options.alignment_format, threads)
                           if k + 1 < len(chunks) else None)
                 names = [locus_name_of(path) for path in paths]
@@ -221,6 +230,7 @@ def iter_built_chunks(input_files, options, device_ordinal=0, chunks=None):
                         raise
                 in_flight.append((names, msas, curation,
                                   pipe.submit_msa_set(msas, options.max_nesting, options.min_match_length)))
+                loaded = None
                 while len(in_flight) > 1:
                     yield built(in_flight.popleft())
             while in_flight:
@@ -236,6 +246,13 @@ def iter_built_chunks(input_files, options, device_ordinal=0, chunks=None):
             except Exception:
                 pass
             msas.free()
+        if loaded is not None:  # (an empty MSA in it ended the run)
+            loaded.free()
+        if future is not None:  # a chunk that was loaded ahead and never built
+            try:
+                future.result().free()
+            except Exception:
+                pass
 
 
 def _update_ds_pickles(names, msas, res, ok, options):

@@ -377,3 +377,98 @@ def test_pipeline_helpers(tmp_path, monkeypatch):
     monkeypatch.setenv("MPRG_CHUNK_MB", "0.0001")  # ~105 bytes
     assert len(fm.cut_chunks(files)) == 5
     assert fm.side_threads(1) >= fm.side_threads(4) >= 1 and fm.side_threads(4, writer=True) >= 1
+
+
+def test_chunk_generator_with_stub_pipeline(tmp_path, monkeypatch):
+    """from_msa.iter_built_chunks without a device: the native loader is real, the build pipeline is a stub.
+    Chunk k+1 is submitted before the result of chunk k is handed on, results come in input order, a skipped locus
+    (disallowed base) is left out of `ok`, and an error -- in a build or in the consumer -- leaves no build in
+    flight and frees what was loaded."""
+    from argparse import Namespace
+    from concurrent.futures import Future
+
+    from make_prg_b200 import device
+    from make_prg_b200._lib import MprgError
+    from make_prg_b200.subcommands import from_msa as fm
+
+    files = []
+    for i in range(5):
+        p = tmp_path / f"l{i}.fa"
+        p.write_text(f">a\nACGT{'ACGT'[i % 4]}A\n>b\nACGTTA\n")
+        files.append(p)
+    chunks = [files[:2], files[2:3], files[3:]]
+    events, freed = [], []
+
+    class Res:
+        def __init__(self, n, bad):
+            self.n, self.bad = n, bad
+
+        def statuses(self):
+            st = np.zeros(self.n, np.int32)
+            for i in self.bad:
+                st[i] = 1
+            return st, np.full(self.n, 7, np.int64)
+
+        def free(self):
+            freed.append("res")
+
+    class Batch:
+        def free(self):
+            freed.append("batch")
+
+    class StubPipe:
+        fail_at = None
+
+        def __init__(self):
+            self.k = 0
+
+        def submit_msa_set(self, msas, N, L, consume=None):
+            k, self.k = self.k, self.k + 1
+            events.append(("submit", k, msas.n_loci))
+            fut = Future()
+            if StubPipe.fail_at == k:
+                fut.set_exception(MprgError(-2, "injected"))
+            else:
+                fut.set_result((Batch(), Res(msas.n_loci, [1] if k == 0 else [])))
+            return fut
+
+    monkeypatch.setattr(device, "default_pipeline", lambda dev=0, depth=None: StubPipe())
+    real_free = hostio.MsaSet.free
+
+    def counted_free(self):  # (also called by __del__: count a set once)
+        if not getattr(self, "_counted", False):
+            self._counted = True
+            freed.append("msas")
+        return real_free(self)
+
+    monkeypatch.setattr(hostio.MsaSet, "free", counted_free)
+    opts = Namespace(alignment_format="fasta", max_nesting=5, min_match_length=7)
+    got = []
+    for names, msas, res, ok in fm.iter_built_chunks(files, opts, chunks=chunks):
+        events.append(("yield", names[0]))
+        got.append((names, ok))
+        res.free()
+        msas.free()
+    assert got == [(["l0", "l1"], [0]), (["l2"], [0]), (["l3", "l4"], [0, 1])]
+    # one build of lookahead: chunk 1 is submitted before chunk 0 is yielded, chunk 2 before chunk 1
+    assert events == [("submit", 0, 2), ("submit", 1, 1), ("yield", "l0"), ("submit", 2, 2), ("yield", "l2"),
+                      ("yield", "l3")]
+    assert freed.count("batch") == 3 and freed.count("res") == 3 and freed.count("msas") == 3
+    # a build fails: the error surfaces, the chunk that was in flight behind it is waited for and dropped
+    del events[:], freed[:]
+    StubPipe.fail_at = 1
+    with pytest.raises(MprgError):
+        for names, msas, res, ok in fm.iter_built_chunks(files, opts, chunks=chunks):
+            res.free()
+            msas.free()
+    assert ("submit", 2, 2) in events and freed.count("msas") == 2 + 1  # chunk 0 by the consumer, chunk 2 by the cleanup
+    # the consumer fails: the build in flight is waited for, its batch / result / matrices are released
+    del events[:], freed[:]
+    StubPipe.fail_at = None
+    with pytest.raises(RuntimeError):
+        for names, msas, res, ok in fm.iter_built_chunks(files, opts, chunks=chunks):
+            res.free()
+            msas.free()
+            raise RuntimeError("consumer")
+    # (chunk 0 by the consumer, chunk 1 in flight, chunk 2 loaded ahead)
+    assert freed.count("msas") == 3 and freed.count("batch") == 2 and freed.count("res") == 2
