@@ -115,14 +115,20 @@ def cut_chunks(input_files, max_bytes=None, max_loci=16384):
 
 def side_threads(n_chunks, writer=False):
     """Host threads of the loader and of the writers.  With one chunk nothing overlaps and each stage may
-    use every core; with several, loading chunk k+1 and writing chunk k-1 run beside the build of chunk
-    k.  The build itself needs two host threads (the level loop runs on the device), so the loader and the
-    writers share the rest of this process's cores."""
+    use every core; with several, loading chunk k+1 and writing chunk k-1 run beside the build of chunk k.
+    The stages do not take the same time and the build threads mostly wait, so a fixed split of the cores
+    leaves some idle while the slowest stage (the writers, at a quarter of the cores) sets the pace: both stages
+    get nearly all of this process's cores and the scheduler shares them (4,000 loci in 4 chunks on 8 cores
+    with the device stage stubbed, scripts/files_pipeline_cpu.py: loader 4 + writers 2 threads 301-323 ms,
+    7 + 6 threads 224 ms).  MPRG_LOAD_THREADS / MPRG_WRITE_THREADS override."""
+    override = os.environ.get("MPRG_WRITE_THREADS" if writer else "MPRG_LOAD_THREADS")
+    if override:
+        return max(1, int(override))
     cores = os.cpu_count() or 1
     share = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)))
     if n_chunks <= 1:
         return max(1, min(32, share))
-    return max(1, min(8, share // 4)) if writer else max(1, min(24, (share - 2) * 2 // 3))
+    return max(1, min(16, share * 3 // 4)) if writer else max(1, min(24, share - 1))
 
 
 def _load_chunk(paths, alignment_format, threads=None):
