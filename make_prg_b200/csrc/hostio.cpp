@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <memory>
 #include <mutex>
+#include <sched.h>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -1589,7 +1590,7 @@ extern "C" int mprg_writer_add(mprg_writer *w, const mprg_result *res, const int
     if (!w || !res || n < 0 || (n > 0 && (!h_loci || !names))) return MPRG_E_BAD_ARG;
     std::vector<Encoded> enc((size_t)n);
     const int what = w->what;
-    parallel_for(n, n_threads, [&](int i) {
+    auto encode_one = [&](int i) {
         Encoded &e = enc[(size_t)i];
         e.name = names[i];
         int64_t len = 0;
@@ -1608,7 +1609,91 @@ extern "C" int mprg_writer_add(mprg_writer *w, const mprg_result *res, const int
             if (e.rc) return;
             e.crc_gfa = (uint32_t)crc32(0L, (const Bytef *)e.gfa.data(), (uInt)e.gfa.size());
         }
-    });
+    };
+    if (n_threads > 1 && n >= 64 && (w->n_added > 0 || (w->what & MPRG_WRITE_PART) || n > 1)) {
+        // Streaming: the archives are appended in locus order by one thread each WHILE the host threads encode
+        // (the indices are handed out in increasing order, so entry i is ready about when the appenders get to
+        // it); the serial appends -- a third of the writers' time on 8-16 cores -- hide behind the encoding.
+        if (!w->zips_open) {
+            if ((what & MPRG_WRITE_BIN) && !w->zbin.open_path(w->prefix + ".prg.bin.zip")) {
+                w->err = "cannot create " + w->prefix + ".prg.bin.zip: " + strerror(errno);
+                return MPRG_E_INTERNAL;
+            }
+            if ((what & MPRG_WRITE_GFA) && !w->zgfa.open_path(w->prefix + ".prg.gfa.zip")) {
+                w->err = "cannot create " + w->prefix + ".prg.gfa.zip: " + strerror(errno);
+                return MPRG_E_INTERNAL;
+            }
+            w->zips_open = true;
+            if (w->n_added == 1) {
+                const int rc = writer_flush_entry(w, w->first);
+                if (rc) return rc;
+                w->first = Encoded();
+            }
+        }
+        std::unique_ptr<std::atomic<int>[]> state(new std::atomic<int>[(size_t)n]);  // 0 pending, 1 encoded, 2 failed
+        for (int i = 0; i < n; ++i) state[(size_t)i].store(0, std::memory_order_relaxed);
+        std::atomic<bool> stop{false};
+        int rc_bin = MPRG_OK, rc_gfa = MPRG_OK;
+        std::string err_bin, err_gfa;
+        auto appender = [&](bool bin) {
+            for (int i = 0; i < n; ++i) {
+                int st;
+                while ((st = state[(size_t)i].load(std::memory_order_acquire)) == 0) {
+                    if (stop.load(std::memory_order_relaxed)) return;
+                    sched_yield();
+                }
+                if (st != 1 || stop.load(std::memory_order_relaxed)) return;
+                const Encoded &e = enc[(size_t)i];
+                const bool ok = bin ? w->zbin.add(e.name + ".bin", e.bin.data(), e.bin.size() * sizeof(uint32_t), e.crc_bin)
+                                    : w->zgfa.add(e.name + ".gfa", e.gfa.data(), e.gfa.size(), e.crc_gfa);
+                if (!ok) {
+                    (bin ? err_bin : err_gfa) = "cannot write " + w->prefix + (bin ? ".prg.bin.zip: " : ".prg.gfa.zip: ") +
+                                               strerror(errno);
+                    (bin ? rc_bin : rc_gfa) = MPRG_E_INTERNAL;
+                    stop.store(true);
+                    return;
+                }
+            }
+        };
+        std::thread t_bin, t_gfa;
+        if (what & MPRG_WRITE_BIN) t_bin = std::thread(appender, true);
+        if (what & MPRG_WRITE_GFA) t_gfa = std::thread(appender, false);
+        parallel_for(n, n_threads, [&](int i) {
+            if (!stop.load(std::memory_order_relaxed)) encode_one(i);
+            else enc[(size_t)i].rc = MPRG_E_INTERNAL;  // (another locus failed: nothing more is written)
+            const bool bad = enc[(size_t)i].rc != 0;
+            if (bad) stop.store(true);
+            state[(size_t)i].store(bad ? 2 : 1, std::memory_order_release);
+        });
+        if (what & MPRG_WRITE_PRG) {
+            w->fa.reserve(w->fa.size() + (size_t)n);
+            for (int i = 0; i < n && !stop.load(); ++i) {
+                int64_t len = 0;
+                const char *prg = mprg_result_prg(res, h_loci[i], &len);
+                w->fa.emplace_back(enc[(size_t)i].name, std::string(prg, (size_t)len));
+            }
+        }
+        if (t_bin.joinable()) t_bin.join();
+        if (t_gfa.joinable()) t_gfa.join();
+        if (rc_bin != MPRG_OK || rc_gfa != MPRG_OK) {
+            w->err = rc_bin != MPRG_OK ? err_bin : err_gfa;
+            return MPRG_E_INTERNAL;
+        }
+        for (int i = 0; i < n; ++i) {
+            const int rc = enc[(size_t)i].rc;
+            if (rc && rc != MPRG_E_INTERNAL) {  // the locus that could not be encoded (not the ones skipped after it)
+                w->err = "PRG of " + enc[(size_t)i].name + " cannot be encoded";
+                return rc;
+            }
+        }
+        if (stop.load()) {
+            w->err = "writer stopped";
+            return MPRG_E_INTERNAL;
+        }
+        w->n_added += n;
+        return MPRG_OK;
+    }
+    parallel_for(n, n_threads, encode_one);
     for (int i = 0; i < n; ++i)
         if (enc[(size_t)i].rc) {
             w->err = "PRG of " + enc[(size_t)i].name + " cannot be encoded";

@@ -472,3 +472,40 @@ def test_chunk_generator_with_stub_pipeline(tmp_path, monkeypatch):
             raise RuntimeError("consumer")
     # (chunk 0 by the consumer, chunk 1 in flight, chunk 2 loaded ahead)
     assert freed.count("msas") == 3 and freed.count("batch") == 2 and freed.count("res") == 2
+
+
+def test_writer_streaming_appends_equal_serial_and_stop_on_a_bad_prg(tmp_path):
+    """mprg_writer_add with many loci and several threads appends the archives while the PRGs are still being
+    encoded: the files equal those of a one-thread writer (and of a writer fed locus by locus), and a PRG that
+    cannot be encoded raises the reference's error and leaves no file behind."""
+    prgs = all_truth_prgs()
+    many = [prgs[i % len(prgs)] for i in range(300)]
+    names = [f"l{i:04d}" for i in range(300)]
+    strings = hostio.PrgStrings(many)
+    for tag, threads, step in (("serial", 1, 300), ("streamed", 6, 300), ("two_adds", 6, 150), ("one_by_one", 3, 1)):
+        w = hostio.OutputWriter(tmp_path / tag, threads=threads)
+        for a in range(0, 300, step):
+            w.add(strings, np.arange(a, min(300, a + step)), names[a:a + step])
+        assert w.close()[0] == 300
+    for tag in ("streamed", "two_adds", "one_by_one"):
+        for ext in ("prg.fa", "prg.bin.zip", "prg.gfa.zip"):
+            a, b = (tmp_path / f"serial.{ext}").read_bytes(), (tmp_path / f"{tag}.{ext}").read_bytes()
+            if ext.endswith("zip"):  # (the DOS time stamp of the members may differ by a tick)
+                with zipfile.ZipFile(tmp_path / f"serial.{ext}") as za, zipfile.ZipFile(tmp_path / f"{tag}.{ext}") as zb:
+                    assert za.namelist() == zb.namelist() and zb.testzip() is None
+                    assert all(za.read(m) == zb.read(m) for m in za.namelist())
+            else:
+                assert a == b
+    strings.free()
+    bad = list(many)
+    bad[211] = "ACGT 5 A 6 X 5 "  # not a PRG: a letter outside ACGT
+    strings = hostio.PrgStrings(bad)
+    w = hostio.OutputWriter(tmp_path / "bad", threads=6)
+    with pytest.raises(Exception) as err:
+        w.add(strings, np.arange(300), names)
+    assert type(err.value).__name__ in ("EncodeError", "AssertionError", "ValueError", "MprgError")
+    one = hostio.OutputWriter(tmp_path / "bad1", threads=1)
+    with pytest.raises(type(err.value)):
+        one.add(strings, np.arange(300), names)  # the one-thread path raises the same error
+    assert not list(tmp_path.glob("bad*"))
+    strings.free()
