@@ -42,8 +42,16 @@ def main():
            "impl": "unmodified reference, make_prg from_msa -t 1 (oracle/run_reference.py harness)", "cores": 1,
            "cap_s": CAP, "oracle_port_seconds_1core": golden["oracle_seconds_1core"]}
     try:
-        subprocess.run([sys.executable, "-c", CHILD, str(REPO), str(tmp / "msas"), str(tmp / "out")], timeout=CAP,
-                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        # own session: the reference's worker pool is a grandchild, the cap must end the whole group
+        proc = subprocess.Popen([sys.executable, "-c", CHILD, str(REPO), str(tmp / "msas"), str(tmp / "out")],
+                                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, start_new_session=True)
+        try:
+            if proc.wait(timeout=CAP) != 0:
+                raise subprocess.CalledProcessError(proc.returncode, "make_prg from_msa")
+        except subprocess.TimeoutExpired:
+            os.killpg(proc.pid, 9)
+            proc.wait()
+            raise
         rec["wall_s"] = time.perf_counter() - t0
         prg = (tmp / "out.prg.fa").read_text().split("\n")[1]
         rec["prg_len"] = len(prg)
