@@ -311,11 +311,17 @@ def run_reference(args, rank, world):
 def config_dict():
     """The same object in both arms (the arms differ in what they time, not in the workload)."""
     cores = os.cpu_count() or 1
+    from make_prg_b200.device import default_lanes  # (a rule on the host's core count; loads no library)
+
+    lanes = default_lanes()
     return {"workload": "BASELINE configs[1]: synthetic 1,000-locus set, 200 seqs x 1 kb MSAs, -N 5 -L 7, "
                         "per GPU (make_prg_b200.synth seeds 1000+i)",
             "loci_per_gpu": LOCI_PER_GPU, "rows": ROWS, "cols": COLS, "max_nesting": MAX_NESTING,
             "min_match_length": MIN_MATCH,
-            "l2": "L2 flushed between steps by writing a 256 MiB device buffer (packed batch is 100 MB < L2)",
+            "builds_in_flight": lanes,
+            "l2": f"throughput steps (value, e2e): {lanes} builds in flight on {lanes} input arenas of 100 MB each "
+                  f"(> the 126 MB L2) plus one 256 MiB flush write per step on a third stream; one-at-a-time steps: "
+                  f"L2 flushed between steps by writing a 256 MiB device buffer (packed batch is 100 MB < L2)",
             "cpu_sample": f"CPU arms time a bounded sample of the same loci: --impl reference the first "
                           f"{reference_sample_size(cores)} loci per step on {cores} cores, cpu_baseline the "
                           f"first {CPU_BASELINE_SAMPLE} loci on 1 core"}
@@ -676,7 +682,7 @@ def main():
         "metric": "MSA loci/sec (from_msa, byte-identical PRG)", "value": value, "unit": "loci/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": dict(config_dict(), builds_in_flight=LANES),
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_dict(),
         "columns_per_sec": value * COLS, "loci_ok": n_ok_total,
         "mode": f"throughput: {args.steps} builds (steps) of resident batches issued back to back, {LANES} in flight "
                 f"(device.BuildPipeline: {LANES} lanes = contexts with their own stream and host thread, lane i builds "
