@@ -60,7 +60,7 @@ def main():
             n = msas.n_loci
 
             def job():
-                time.sleep(build_ms * 1e-3 * n / 1000)
+                time.sleep(max(2e-3, build_ms * 1e-3 * n / 1000))  # (a build is at least a level loop's latency)
                 return Batch(), Res(n)
 
             return self.pool.submit(job)
